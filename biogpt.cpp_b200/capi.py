@@ -1,0 +1,269 @@
+"""ctypes view of include/bgpt_cuda.h (libbgpt_cuda.so) for tests and bench.py.
+
+This is NOT a second implementation: every function here forwards to the C ABI that the C++
+host library (host/biogpt_b200.cpp) also calls.  `Model.load` walks a `.bin` file the way the
+reference's biogpt_model_load does (/root/reference/biogpt.cpp:27-453) and hands each tensor's
+raw bytes to bgpt_cuda_upload_tensor.  If the shared library is missing, importing succeeds but
+any use raises -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import ggml_file as gf
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libbgpt_cuda.so")
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+
+# every symbol include/bgpt_cuda.h declares (tests/test_capi_symbols.py checks header <-> list)
+SYMBOLS = [
+    "bgpt_cuda_last_error", "bgpt_cuda_device_count", "bgpt_cuda_version",
+    "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
+    "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
+    "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
+    "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
+    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
+    "bgpt_cuda_op_attention", "bgpt_cuda_op_gelu", "bgpt_cuda_op_dequantize",
+]
+
+_lib = None
+
+
+class BgptError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libbgpt_cuda.so (built by `make -C biogpt.cpp_b200`); fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BgptError(f"{LIB_PATH} is missing: build it with `make -C biogpt.cpp_b200` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.bgpt_cuda_last_error.restype = C.c_char_p
+    L.bgpt_cuda_version.restype = C.c_char_p
+    L.bgpt_cuda_device_count.restype = C.c_int
+    L.bgpt_cuda_model_create.restype = C.c_void_p
+    L.bgpt_cuda_model_create.argtypes = [_i32p, C.c_int, C.c_int]
+    L.bgpt_cuda_upload_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int64, C.c_int64,
+                                          C.c_void_p, C.c_size_t]
+    L.bgpt_cuda_set_tables.argtypes = [C.c_void_p, _u16p, _u16p]
+    L.bgpt_host_build_tables.restype = None
+    L.bgpt_host_build_tables.argtypes = [_u16p, _u16p]
+    L.bgpt_cuda_model_finalize.argtypes = [C.c_void_p]
+    L.bgpt_cuda_model_free.restype = None
+    L.bgpt_cuda_model_free.argtypes = [C.c_void_p]
+    L.bgpt_cuda_eval.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, _f32p]
+    L.bgpt_cuda_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.bgpt_cuda_logits_device.restype = C.c_void_p
+    L.bgpt_cuda_logits_device.argtypes = [C.c_void_p]
+    L.bgpt_cuda_synchronize.argtypes = [C.c_void_p]
+    L.bgpt_cuda_decode_greedy.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_int, _i32p,
+                                          C.POINTER(C.c_float)]
+    L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
+    L.bgpt_cuda_hparams.restype = None
+    L.bgpt_cuda_hparams.argtypes = [C.c_void_p, _i32p]
+    L.bgpt_cuda_weight_bytes.restype = C.c_size_t
+    L.bgpt_cuda_weight_bytes.argtypes = [C.c_void_p]
+    L.bgpt_cuda_launch_count.restype = C.c_uint64
+    L.bgpt_cuda_launch_count.argtypes = [C.c_void_p]
+    L.bgpt_cuda_last_eval_ms.restype = C.c_float
+    L.bgpt_cuda_last_eval_ms.argtypes = [C.c_void_p]
+    L.bgpt_cuda_set_taps.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.bgpt_cuda_op_mul_mat.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+    L.bgpt_cuda_op_quantize_act.argtypes = [C.c_int, _f32p, _u8p, C.c_int]
+    L.bgpt_cuda_op_norm.argtypes = [_f32p, C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float]
+    L.bgpt_cuda_op_attention.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u16p]
+    L.bgpt_cuda_op_gelu.argtypes = [_f32p, _f32p, C.c_int, _u16p]
+    L.bgpt_cuda_op_dequantize.argtypes = [C.c_int, _u8p, _f32p, C.c_int, C.c_int]
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise BgptError(f"{what} failed ({rc}): {lib().bgpt_cuda_last_error().decode()}")
+
+
+def last_error() -> str:
+    return lib().bgpt_cuda_last_error().decode()
+
+
+def device_count() -> int:
+    return int(lib().bgpt_cuda_device_count())
+
+
+def build_tables():
+    """(gelu_f16, exp_f16) built with the host libm by the library's own helper."""
+    g = np.zeros(65536, dtype=np.uint16)
+    e = np.zeros(65536, dtype=np.uint16)
+    lib().bgpt_host_build_tables(g, e)
+    return g, e
+
+
+TAP_NAMES = ("embed", "layer0_q", "layer0_att", "layer0_out", "final_in")
+
+
+class Model:
+    """A `.bin` model resident on one GPU (mirrors biogpt_model_load / biogpt_eval)."""
+
+    def __init__(self, handle, hparams):
+        self.h = handle
+        self.hparams = hparams
+        self.n_vocab = int(hparams[0])
+        self.n_positions = int(hparams[3])
+        self.d_model = int(hparams[5])
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, max_batch: int = 8) -> "Model":
+        L = lib()
+        mf = gf.read_model(path)
+        hp = np.array([mf.hparams.n_vocab, mf.hparams.n_layer, mf.hparams.n_head, mf.hparams.n_positions,
+                       mf.hparams.d_ff, mf.hparams.d_model, mf.hparams.ftype], dtype=np.int32)
+        h = L.bgpt_cuda_model_create(hp, device, max_batch)
+        if not h:
+            raise BgptError(f"bgpt_cuda_model_create: {last_error()}")
+        m = cls(h, hp)
+        try:
+            with open(path, "rb") as f:
+                for name, e in mf.tensors.items():
+                    f.seek(e.offset)
+                    raw = f.read(e.nbytes)
+                    ne0 = e.ne[0]
+                    ne1 = e.ne[1] if len(e.ne) > 1 else 1
+                    buf = C.create_string_buffer(raw, len(raw))
+                    _check(L.bgpt_cuda_upload_tensor(h, name.encode(), e.ggml_type, ne0, ne1,
+                                                     C.cast(buf, C.c_void_p), len(raw)),
+                           f"upload_tensor({name})")
+            g, ex = build_tables()
+            _check(L.bgpt_cuda_set_tables(h, g, ex), "set_tables")
+            _check(L.bgpt_cuda_model_finalize(h), "model_finalize")
+        except Exception:
+            m.close()
+            raise
+        return m
+
+    def eval(self, tokens: Sequence[int], n_past: int, taps: bool = False):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(self.n_vocab, dtype=np.float32)
+        bufs = {}
+        if taps:
+            arr = (C.c_void_p * 5)()
+            for i, nme in enumerate(TAP_NAMES):
+                bufs[nme] = np.zeros((len(t), self.d_model), dtype=np.float32)
+                arr[i] = bufs[nme].ctypes.data
+            _check(lib().bgpt_cuda_set_taps(self.h, arr), "set_taps")
+        _check(lib().bgpt_cuda_eval(self.h, t, len(t), n_past, out), "eval")
+        return (out, bufs) if taps else out
+
+    def eval_streams(self, tokens: Sequence[int], n_past: int, fetch: bool = True) -> Optional[np.ndarray]:
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty((len(t), self.n_vocab), dtype=np.float32) if fetch else None
+        _check(lib().bgpt_cuda_eval_streams(self.h, t, len(t), n_past,
+                                            out.ctypes.data if fetch else None), "eval_streams")
+        return out
+
+    def set_streams(self, n: int):
+        _check(lib().bgpt_cuda_set_streams(self.h, n), "set_streams")
+
+    def decode_greedy(self, first_token: int, n_past: int, n_steps: int):
+        ids = np.zeros(n_steps, dtype=np.int32)
+        ms = C.c_float(0)
+        _check(lib().bgpt_cuda_decode_greedy(self.h, first_token, n_past, n_steps, ids, C.byref(ms)),
+               "decode_greedy")
+        return ids, float(ms.value)
+
+    @property
+    def last_eval_ms(self) -> float:
+        return float(lib().bgpt_cuda_last_eval_ms(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().bgpt_cuda_launch_count(self.h))
+
+    @property
+    def weight_bytes(self) -> int:
+        return int(lib().bgpt_cuda_weight_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().bgpt_cuda_model_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- unit-level operators ------------------------------------------------------------------
+
+def op_mul_mat(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, k = x.shape
+    y = np.empty((n, rows), dtype=np.float32)
+    _check(lib().bgpt_cuda_op_mul_mat(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
+           "op_mul_mat")
+    return y
+
+
+def op_quantize_act(weight_type: int, x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    k = x.size
+    kind_bytes = {gf.GGML_TYPE_F32: 4 * k, gf.GGML_TYPE_F16: 2 * k,
+                  gf.GGML_TYPE_Q4_0: k // 32 * 34, gf.GGML_TYPE_Q5_0: k // 32 * 34, gf.GGML_TYPE_Q8_0: k // 32 * 34,
+                  gf.GGML_TYPE_Q4_1: k // 32 * 40, gf.GGML_TYPE_Q5_1: k // 32 * 40}[weight_type]
+    out = np.zeros(kind_bytes, dtype=np.uint8)
+    _check(lib().bgpt_cuda_op_quantize_act(weight_type, x, out, k), "op_quantize_act")
+    return out
+
+
+def op_norm(x: np.ndarray, w=None, b=None, eps: float = 1e-5) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    rows, nc = x.shape
+    y = np.empty_like(x)
+    wp = np.ascontiguousarray(w, dtype=np.float32) if w is not None else None
+    bp = np.ascontiguousarray(b, dtype=np.float32) if b is not None else None
+    _check(lib().bgpt_cuda_op_norm(x, wp.ctypes.data if wp is not None else None,
+                                   bp.ctypes.data if bp is not None else None, y, rows, nc, eps), "op_norm")
+    return y
+
+
+def op_attention(q, k, v, n_past: int, n_head: int, exp_tab: np.ndarray) -> np.ndarray:
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    k = np.ascontiguousarray(k, dtype=np.float32)
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    n, d = q.shape
+    out = np.empty_like(q)
+    _check(lib().bgpt_cuda_op_attention(q, k, v, out, n, n_past, d, n_head,
+                                        np.ascontiguousarray(exp_tab, dtype=np.uint16)), "op_attention")
+    return out
+
+
+def op_gelu(x: np.ndarray, gelu_tab: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    y = np.empty_like(x)
+    _check(lib().bgpt_cuda_op_gelu(x, y, x.size, np.ascontiguousarray(gelu_tab, dtype=np.uint16)), "op_gelu")
+    return y
+
+
+def op_dequantize(ggml_type: int, w_bytes: np.ndarray, k: int, rows: int) -> np.ndarray:
+    y = np.empty((rows, k), dtype=np.float32)
+    _check(lib().bgpt_cuda_op_dequantize(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), y, k, rows),
+           "op_dequantize")
+    return y

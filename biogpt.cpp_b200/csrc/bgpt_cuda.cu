@@ -1,0 +1,700 @@
+// bgpt_cuda.cu -- device engine + the extern "C" boundary declared in include/bgpt_cuda.h.
+//
+// Replaces everything beneath the reference's biogpt_eval (biogpt.cpp:812-847): instead of
+// building a 1282-node ggml graph per call and running it on a spin-barrier thread pool, the
+// weights live in HBM (re-tiled once at upload, bgpt_layout.h) and one eval is a fixed
+// schedule of fused kernels (bgpt_kernels.cuh) on one stream:
+//
+//   embed                                                   biogpt.cpp:663-686
+//   per layer: act(LN0) -> gemv{q,k,v}+bias+scale+KV append -> attn -> act -> gemv(o)+bias+res
+//              -> act(LN1) -> gemv(fc1)+bias+GELU -> act -> gemv(fc2)+bias+res
+//                                                           biogpt.cpp:688-796
+//   act(LN) -> gemv(lm_head) on the last row only           biogpt.cpp:798-803, 844
+//
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include "../../include/bgpt_cuda.h"
+#include "bgpt_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char * fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(BGPT_E_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fail(BGPT_E_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return nullptr; } } while (0)
+#define RET(x) do { int r_ = (x); if (r_ != BGPT_OK) return r_; } while (0)
+
+extern "C" const char * bgpt_cuda_last_error(void) { return g_err; }
+extern "C" const char * bgpt_cuda_version(void) { return "biogpt-b200 0.1 (sm_100a, lane-order exact)"; }
+extern "C" int bgpt_cuda_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(BGPT_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+struct DevTensor {
+    int type = -1; int64_t ne0 = 0, ne1 = 0;
+    uint8_t * ptr = nullptr; size_t bytes = 0;
+    bool repacked = false; RowLayout L{};
+};
+struct LayerW {
+    DevTensor *q_w, *k_w, *v_w, *o_w, *q_b, *k_b, *v_b, *o_b, *ln0_w, *ln0_b, *ln1_w, *ln1_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+};
+struct bgpt_model {
+    int32_t n_vocab, n_layer, n_head, n_positions, d_ff, d_model, ftype;
+    int wtype = -1;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::map<std::string, DevTensor> tensors;
+    DevTensor *embed_tokens = nullptr, *embed_pos = nullptr, *ln_w = nullptr, *ln_b = nullptr, *lm_head = nullptr;
+    std::vector<LayerW> layers;
+    bool finalized = false;
+    // state
+    int n_streams = 1;
+    float * kcache = nullptr, * vcache = nullptr;    // [stream][layer][pos][d]
+    size_t stream_stride = 0;                         // floats per stream
+    uint16_t * gelu_tab = nullptr, * exp_tab = nullptr; bool have_tabs = false;
+    DevState * st = nullptr;
+    // arena for `cap` token rows
+    int cap = 0;
+    int * d_tokens = nullptr; int * d_idlog = nullptr; int idlog_cap = 0;
+    float *x = nullptr, *x1 = nullptr, *q = nullptr, *att = nullptr, *hff = nullptr, *logits = nullptr;
+    uint8_t *act_d = nullptr, *act_ff = nullptr;
+    ActLayout A_d{}, A_ff{};
+    // pinned staging
+    int * h_tokens = nullptr; DevState * h_st = nullptr; float * h_logits = nullptr; size_t h_logits_rows = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    uint64_t launches = 0;
+    size_t weight_bytes = 0;
+    float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
+    float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+};
+
+static int ftype_to_type(int f) {
+    switch (f) { case 0: return BG_F32; case 1: return BG_F16; case 2: return BG_Q4_0; case 3: return BG_Q4_1;
+                 case 7: return BG_Q8_0; case 8: return BG_Q5_0; case 9: return BG_Q5_1; }
+    return -1;
+}
+
+static void free_arena(bgpt_model * m) {
+    cudaFree(m->d_tokens); cudaFree(m->x); cudaFree(m->x1); cudaFree(m->q); cudaFree(m->att); cudaFree(m->hff);
+    cudaFree(m->logits); cudaFree(m->act_d); cudaFree(m->act_ff);
+    for (int i = 0; i < 5; i++) { cudaFree(m->d_taps[i]); m->d_taps[i] = nullptr; }
+    if (m->h_tokens) cudaFreeHost(m->h_tokens);
+    if (m->h_logits) cudaFreeHost(m->h_logits);
+    m->d_tokens = nullptr; m->x = m->x1 = m->q = m->att = m->hff = m->logits = nullptr; m->act_d = m->act_ff = nullptr;
+    m->h_tokens = nullptr; m->h_logits = nullptr; m->cap = 0;
+}
+
+static int ensure_arena(bgpt_model * m, int rows) {
+    if (rows <= m->cap) return BGPT_OK;
+    free_arena(m);
+    const size_t d = m->d_model, ff = m->d_ff, R = rows;
+    CK(cudaMalloc(&m->d_tokens, R * sizeof(int)));
+    CK(cudaMalloc(&m->x,   R * d * 4)); CK(cudaMalloc(&m->x1,  R * d * 4));
+    CK(cudaMalloc(&m->q,   R * d * 4)); CK(cudaMalloc(&m->att, R * d * 4));
+    CK(cudaMalloc(&m->hff, R * ff * 4));
+    CK(cudaMalloc(&m->logits, R * (size_t) m->n_vocab * 4));
+    CK(cudaMalloc(&m->act_d,  R * (size_t) m->A_d.bytes));
+    CK(cudaMalloc(&m->act_ff, R * (size_t) m->A_ff.bytes));
+    CK(cudaMemset(m->act_d, 0, R * (size_t) m->A_d.bytes));
+    CK(cudaMemset(m->act_ff, 0, R * (size_t) m->A_ff.bytes));
+    for (int i = 0; i < 5; i++) CK(cudaMalloc(&m->d_taps[i], R * d * 4));
+    CK(cudaMallocHost(&m->h_tokens, R * sizeof(int)));
+    CK(cudaMallocHost(&m->h_logits, R * (size_t) m->n_vocab * 4));
+    m->cap = rows;
+    return BGPT_OK;
+}
+
+static int alloc_kv(bgpt_model * m, int n_streams) {
+    cudaFree(m->kcache); cudaFree(m->vcache); m->kcache = m->vcache = nullptr;
+    m->stream_stride = (size_t) m->n_layer * m->n_positions * m->d_model;
+    const size_t bytes = m->stream_stride * 4 * (size_t) n_streams;
+    CK(cudaMalloc(&m->kcache, bytes)); CK(cudaMalloc(&m->vcache, bytes));
+    CK(cudaMemset(m->kcache, 0, bytes)); CK(cudaMemset(m->vcache, 0, bytes));
+    m->n_streams = n_streams;
+    return BGPT_OK;
+}
+
+extern "C" bgpt_model * bgpt_cuda_model_create(const int32_t hp[7], int device, int max_batch) {
+    if (!hp) { fail(BGPT_E_ARG, "hparams is NULL"); return nullptr; }
+    int ndev = 0;
+    CKP(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0 || device < 0 || device >= ndev) { fail(BGPT_E_CUDA, "no CUDA device %d (count %d): this library has no CPU path", device, ndev); return nullptr; }
+    const int wtype = ftype_to_type(hp[6]);
+    if (wtype < 0) { fail(BGPT_E_ARG, "unsupported ftype %d", hp[6]); return nullptr; }
+    if (hp[0] <= 0 || hp[1] <= 0 || hp[2] <= 0 || hp[3] <= 0 || hp[4] <= 0 || hp[5] <= 0 ||
+        hp[5] % 32 || hp[4] % 32 || hp[5] % hp[2]) { fail(BGPT_E_ARG, "bad hparams"); return nullptr; }
+    const int dk = hp[5] / hp[2];
+    if (dk != 16 && dk != 32 && dk != 64 && dk != 128) { fail(BGPT_E_UNSUPPORTED, "head dim %d not in {16,32,64,128}", dk); return nullptr; }
+    CKP(cudaSetDevice(device));
+    bgpt_model * m = new bgpt_model();
+    m->n_vocab = hp[0]; m->n_layer = hp[1]; m->n_head = hp[2]; m->n_positions = hp[3]; m->d_ff = hp[4]; m->d_model = hp[5]; m->ftype = hp[6];
+    m->wtype = wtype; m->device = device;
+    m->layers.resize(m->n_layer);
+    m->A_d = bg_act_layout(wtype, m->d_model); m->A_ff = bg_act_layout(wtype, m->d_ff);
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&m->ev0) == cudaSuccess && cudaEventCreate(&m->ev1) == cudaSuccess;
+    ok = ok && cudaMalloc(&m->st, sizeof(DevState)) == cudaSuccess && cudaMemset(m->st, 0, sizeof(DevState)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&m->h_st, sizeof(DevState)) == cudaSuccess;
+    ok = ok && cudaMalloc(&m->gelu_tab, 65536 * 2) == cudaSuccess && cudaMalloc(&m->exp_tab, 65536 * 2) == cudaSuccess;
+    if (!ok) { fail(BGPT_E_CUDA, "model_create: %s", cudaGetErrorString(cudaGetLastError())); bgpt_cuda_model_free(m); return nullptr; }
+    if (alloc_kv(m, 1) != BGPT_OK || ensure_arena(m, max_batch > 0 ? max_batch : 8) != BGPT_OK) { bgpt_cuda_model_free(m); return nullptr; }
+    return m;
+}
+
+extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (auto & kv : m->tensors) cudaFree(kv.second.ptr);
+    free_arena(m);
+    cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
+    if (m->h_st) cudaFreeHost(m->h_st);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" void bgpt_cuda_hparams(const bgpt_model * m, int32_t o[7]) {
+    o[0] = m->n_vocab; o[1] = m->n_layer; o[2] = m->n_head; o[3] = m->n_positions; o[4] = m->d_ff; o[5] = m->d_model; o[6] = m->ftype;
+}
+extern "C" size_t bgpt_cuda_weight_bytes(const bgpt_model * m) { return m->weight_bytes; }
+extern "C" uint64_t bgpt_cuda_launch_count(const bgpt_model * m) { return m->launches; }
+extern "C" float bgpt_cuda_last_eval_ms(const bgpt_model * m) { return m->last_ms; }
+
+// which tensors are matmul operands (re-tiled) vs gather tables / vectors (kept as in the file)
+static bool is_matmul_weight(const std::string & n) {
+    if (n == "output_projection.weight") return true;
+    if (n.rfind("biogpt.layers.", 0) != 0) return false;
+    return n.find("_proj.weight") != std::string::npos || n.find(".fc1.weight") != std::string::npos || n.find(".fc2.weight") != std::string::npos;
+}
+
+static int upload_matrix(DevTensor & t, int type, int K, int rows, const uint8_t * data) {
+    t.L = bg_row_layout(type, K);
+    t.bytes = (size_t) t.L.stride * rows;
+    std::vector<uint8_t> tmp(t.bytes, 0);
+    const size_t frb = bg_file_row_bytes(type, K);
+    for (int r = 0; r < rows; r++) bg_repack_row(t.L, data + frb * r, tmp.data() + (size_t) t.L.stride * r);
+    CK(cudaMalloc(&t.ptr, t.bytes));
+    CK(cudaMemcpy(t.ptr, tmp.data(), t.bytes, cudaMemcpyHostToDevice));
+    t.repacked = true;
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_upload_tensor(bgpt_model * m, const char * name, int type, int64_t ne0, int64_t ne1, const void * data, size_t nbytes) {
+    if (!m || !name || !data) return fail(BGPT_E_ARG, "upload_tensor: NULL argument");
+    if (m->finalized) return fail(BGPT_E_STATE, "upload_tensor after finalize");
+    if (!bg_type_ok(type)) return fail(BGPT_E_ARG, "tensor '%s': unsupported ggml_type %d", name, type);
+    if (ne0 <= 0 || ne1 <= 0 || ne0 % bg_file_block_elems(type)) return fail(BGPT_E_ARG, "tensor '%s': bad shape", name);
+    const size_t expect = bg_file_row_bytes(type, (int) ne0) * (size_t) ne1;
+    if (expect != nbytes) return fail(BGPT_E_ARG, "tensor '%s' has wrong size in model file: got %zu, expected %zu", name, nbytes, expect);
+    CK(cudaSetDevice(m->device));
+    const std::string n(name);
+    // expected shape / type per name (biogpt.cpp:245-321)
+    const int d = m->d_model, ff = m->d_ff, V = m->n_vocab;
+    int64_t e0 = -1, e1 = -1; bool mat = false;
+    if (n == "biogpt.embed_tokens.weight") { e0 = d; e1 = V; mat = true; }
+    else if (n == "biogpt.embed_positions.weight") { e0 = d; e1 = d + 2; mat = true; }
+    else if (n == "output_projection.weight") { e0 = d; e1 = V; mat = true; }
+    else if (n == "biogpt.layer_norm.weight" || n == "biogpt.layer_norm.bias") { e0 = d; e1 = 1; }
+    else if (n.rfind("biogpt.layers.", 0) == 0) {
+        if (n.find("_proj.weight") != std::string::npos) { e0 = d; e1 = d; mat = true; }
+        else if (n.find(".fc1.weight") != std::string::npos) { e0 = d; e1 = ff; mat = true; }
+        else if (n.find(".fc2.weight") != std::string::npos) { e0 = ff; e1 = d; mat = true; }
+        else if (n.find(".fc1.bias") != std::string::npos) { e0 = ff; e1 = 1; }
+        else { e0 = d; e1 = 1; }
+    } else return fail(BGPT_E_ARG, "unknown tensor '%s' in model file", name);
+    if (ne0 != e0 || ne1 != e1) return fail(BGPT_E_ARG, "tensor '%s' has wrong shape in model file: got [%lld, %lld], expected [%lld, %lld]",
+                                             name, (long long) ne0, (long long) ne1, (long long) e0, (long long) e1);
+    if (mat && type != m->wtype) return fail(BGPT_E_ARG, "tensor '%s': type %d does not match the file's ftype", name, type);
+    if (!mat && type != BG_F32) return fail(BGPT_E_ARG, "tensor '%s': 1-D tensors must be F32", name);
+    if (m->tensors.count(n)) return fail(BGPT_E_ARG, "tensor '%s' uploaded twice", name);
+    DevTensor t; t.type = type; t.ne0 = ne0; t.ne1 = ne1;
+    if (is_matmul_weight(n)) { RET(upload_matrix(t, type, (int) ne0, (int) ne1, (const uint8_t *) data)); }
+    else {
+        t.bytes = nbytes;
+        CK(cudaMalloc(&t.ptr, nbytes));
+        CK(cudaMemcpy(t.ptr, data, nbytes, cudaMemcpyHostToDevice));
+    }
+    m->weight_bytes += t.bytes;
+    m->tensors[n] = t;
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_set_tables(bgpt_model * m, const uint16_t * gelu, const uint16_t * ex) {
+    if (!m || !gelu || !ex) return fail(BGPT_E_ARG, "set_tables: NULL argument");
+    CK(cudaSetDevice(m->device));
+    CK(cudaMemcpy(m->gelu_tab, gelu, 65536 * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m->exp_tab, ex, 65536 * 2, cudaMemcpyHostToDevice));
+    m->have_tabs = true;
+    return BGPT_OK;
+}
+
+static DevTensor * find(bgpt_model * m, const std::string & n) {
+    auto it = m->tensors.find(n);
+    return it == m->tensors.end() ? nullptr : &it->second;
+}
+
+template <typename K> static void allow_big_smem(K kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+static void init_kernel_attrs() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+#define ATTR_Q(F) allow_big_smem(k_gemv_q<F, 1>); allow_big_smem(k_gemv_q<F, 2>); allow_big_smem(k_gemv_q<F, 4>); allow_big_smem(k_gemv_q<F, 8>);
+#define ATTR_F(F) allow_big_smem(k_gemv_f<F, 1>); allow_big_smem(k_gemv_f<F, 2>); allow_big_smem(k_gemv_f<F, 4>); allow_big_smem(k_gemv_f<F, 8>);
+    ATTR_Q(BG_Q4_0) ATTR_Q(BG_Q4_1) ATTR_Q(BG_Q5_0) ATTR_Q(BG_Q5_1) ATTR_Q(BG_Q8_0) ATTR_F(BG_F16) ATTR_F(BG_F32)
+    allow_big_smem(k_attn<16>); allow_big_smem(k_attn<32>); allow_big_smem(k_attn<64>); allow_big_smem(k_attn<128>);
+    allow_big_smem(k_act);
+    cudaGetLastError();
+}
+
+extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
+    if (!m) return fail(BGPT_E_ARG, "finalize: NULL model");
+    if (!m->have_tabs) return fail(BGPT_E_STATE, "finalize: lookup tables not set (bgpt_cuda_set_tables)");
+    const int expect = 5 + 16 * m->n_layer;
+    if ((int) m->tensors.size() != expect) return fail(BGPT_E_STATE, "not all tensors loaded from model file - expected %d, got %zu", expect, m->tensors.size());
+    auto need = [&](const std::string & n, DevTensor *& slot) -> int {
+        slot = find(m, n);
+        return slot ? BGPT_OK : fail(BGPT_E_STATE, "missing tensor '%s'", n.c_str());
+    };
+    RET(need("biogpt.embed_tokens.weight", m->embed_tokens));
+    RET(need("biogpt.embed_positions.weight", m->embed_pos));
+    RET(need("biogpt.layer_norm.weight", m->ln_w));
+    RET(need("biogpt.layer_norm.bias", m->ln_b));
+    RET(need("output_projection.weight", m->lm_head));
+    for (int i = 0; i < m->n_layer; i++) {
+        const std::string p = "biogpt.layers." + std::to_string(i) + ".";
+        LayerW & L = m->layers[i];
+        RET(need(p + "self_attn.q_proj.weight", L.q_w)); RET(need(p + "self_attn.k_proj.weight", L.k_w));
+        RET(need(p + "self_attn.v_proj.weight", L.v_w)); RET(need(p + "self_attn.out_proj.weight", L.o_w));
+        RET(need(p + "self_attn.q_proj.bias", L.q_b));   RET(need(p + "self_attn.k_proj.bias", L.k_b));
+        RET(need(p + "self_attn.v_proj.bias", L.v_b));   RET(need(p + "self_attn.out_proj.bias", L.o_b));
+        RET(need(p + "self_attn_layer_norm.weight", L.ln0_w)); RET(need(p + "self_attn_layer_norm.bias", L.ln0_b));
+        RET(need(p + "final_layer_norm.weight", L.ln1_w));     RET(need(p + "final_layer_norm.bias", L.ln1_b));
+        RET(need(p + "fc1.weight", L.fc1_w)); RET(need(p + "fc1.bias", L.fc1_b));
+        RET(need(p + "fc2.weight", L.fc2_w)); RET(need(p + "fc2.bias", L.fc2_b));
+    }
+    CK(cudaSetDevice(m->device));
+    init_kernel_attrs();
+    m->finalized = true;
+    return BGPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------
+static int launch_act(bgpt_model * m, cudaStream_t s, const float * in, int ld_in, const DevTensor * lnw, const DevTensor * lnb,
+                      int K, int wtype, uint8_t * act, const ActLayout & A, int rows, float * f32_out, int ld_out) {
+    ActArgs a{};
+    a.in = in; a.ld_in = ld_in; a.lnw = lnw ? (const float *) lnw->ptr : nullptr; a.lnb = lnb ? (const float *) lnb->ptr : nullptr;
+    a.do_ln = lnw != nullptr || lnb != nullptr; a.eps = 1e-5f;   // NORM_EPS, biogpt.cpp:24
+    a.K = K; a.wtype = wtype; a.act = act; a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_d = A.off_d; a.off_s = A.off_s;
+    a.code_off = bg_code_offset(wtype); a.f32_out = f32_out; a.ld_out = ld_out;
+    k_act<<<rows, 256, (size_t) K * 4, s>>>(a);
+    if (m) m->launches++;
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+
+template <int FMT> static void launch_gemv_q_tn(int TN, dim3 grid, int threads, size_t smem, cudaStream_t s, const GemvArgs & a) {
+    switch (TN) {
+        case 1: k_gemv_q<FMT, 1><<<grid, threads, smem, s>>>(a); break;
+        case 2: k_gemv_q<FMT, 2><<<grid, threads, smem, s>>>(a); break;
+        case 4: k_gemv_q<FMT, 4><<<grid, threads, smem, s>>>(a); break;
+        default: k_gemv_q<FMT, 8><<<grid, threads, smem, s>>>(a); break;
+    }
+}
+template <int FMT> static void launch_gemv_f_tn(int TN, dim3 grid, int threads, size_t smem, cudaStream_t s, const GemvArgs & a) {
+    switch (TN) {
+        case 1: k_gemv_f<FMT, 1><<<grid, threads, smem, s>>>(a); break;
+        case 2: k_gemv_f<FMT, 2><<<grid, threads, smem, s>>>(a); break;
+        case 4: k_gemv_f<FMT, 4><<<grid, threads, smem, s>>>(a); break;
+        default: k_gemv_f<FMT, 8><<<grid, threads, smem, s>>>(a); break;
+    }
+}
+
+// y = W . act for rows tok0..n-1; W = up to 3 stacked matrices sharing one layout
+static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
+                       int n, int tok0, const Epi & epi) {
+    const RowLayout & L = W[0]->L;
+    GemvArgs a{};
+    for (int i = 0; i < 3; i++) a.W[i] = W[i < nmat ? i : 0]->ptr;
+    a.rows_per = (int) W[0]->ne1; a.M = a.rows_per * nmat; a.G = L.G; a.stride = L.stride;
+    a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
+    a.act = act; a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s;
+    a.n = n; a.tok0 = tok0; a.epi = epi;
+    const int cnt = n - tok0;
+    const int TN = cnt <= 1 ? 1 : cnt == 2 ? 2 : cnt <= 4 ? 4 : 8;
+    const int gy = (cnt + TN - 1) / TN;
+    const size_t smem = (size_t) TN * A.bytes;
+    const bool quant = bg_is_quant(L.type);
+    const int groups = quant ? (a.M + 7) / 8 : a.M;        // warps of work
+    int nw = (groups + 295) / 296; nw = nw < 1 ? 1 : nw > 8 ? 8 : nw;
+    dim3 grid((groups + nw - 1) / nw, gy);
+    switch (L.type) {
+        case BG_Q4_0: launch_gemv_q_tn<BG_Q4_0>(TN, grid, nw * 32, smem, s, a); break;
+        case BG_Q4_1: launch_gemv_q_tn<BG_Q4_1>(TN, grid, nw * 32, smem, s, a); break;
+        case BG_Q5_0: launch_gemv_q_tn<BG_Q5_0>(TN, grid, nw * 32, smem, s, a); break;
+        case BG_Q5_1: launch_gemv_q_tn<BG_Q5_1>(TN, grid, nw * 32, smem, s, a); break;
+        case BG_Q8_0: launch_gemv_q_tn<BG_Q8_0>(TN, grid, nw * 32, smem, s, a); break;
+        case BG_F16:  launch_gemv_f_tn<BG_F16>(TN, grid, nw * 32, smem, s, a); break;
+        case BG_F32:  launch_gemv_f_tn<BG_F32>(TN, grid, nw * 32, smem, s, a); break;
+        default: return fail(BGPT_E_UNSUPPORTED, "gemv: type %d", L.type);
+    }
+    if (m) m->launches++;
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+
+static int launch_attn(bgpt_model * m, cudaStream_t s, const AttnArgs & a, int n_head, int rows, int dk) {
+    const size_t smem = ((size_t) a.Tmax + 32 * (size_t) dk) * 4;
+    dim3 grid(n_head, rows);
+    switch (dk) {
+        case 16:  k_attn<16><<<grid, 256, smem, s>>>(a); break;
+        case 32:  k_attn<32><<<grid, 256, smem, s>>>(a); break;
+        case 64:  k_attn<64><<<grid, 256, smem, s>>>(a); break;
+        case 128: k_attn<128><<<grid, 256, smem, s>>>(a); break;
+        default: return fail(BGPT_E_UNSUPPORTED, "attention: head dim %d", dk);
+    }
+    if (m) m->launches++;
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+
+static Epi make_epi(int kind, const DevTensor * b0, float * out, int ld_out) {
+    Epi e{}; e.kind = kind; e.bias[0] = b0 ? (const float *) b0->ptr : nullptr; e.bias[1] = e.bias[2] = nullptr;
+    e.out = out; e.ld_out = ld_out;
+    return e;
+}
+
+// enqueue one forward pass for `n` rows.  mode 0: prompt rows of stream 0 (logits for the last
+// row only); mode 1: one token per stream (logits for every row).  Reads n_past from m->st.
+static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
+    cudaStream_t s = m->stream;
+    const int d = m->d_model, ff = m->d_ff, dk = d / m->n_head, wt = m->wtype;
+    k_embed<<<n, 256, 0, s>>>(m->embed_tokens->ptr, m->embed_pos->ptr, wt, d_tokens, m->st, mode, n, d, m->n_vocab,
+                              (int) m->embed_pos->ne1, sqrtf((float) d), m->x);
+    m->launches++;
+    CK(cudaGetLastError());
+    if (m->taps_armed) CK(cudaMemcpyAsync(m->d_taps[0], m->x, (size_t) n * d * 4, cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < m->n_layer; l++) {
+        const LayerW & L = m->layers[l];
+        float * kc = m->kcache + (size_t) l * m->n_positions * d;
+        float * vc = m->vcache + (size_t) l * m->n_positions * d;
+        RET(launch_act(m, s, m->x, d, L.ln0_w, L.ln0_b, d, wt, m->act_d, m->A_d, n, nullptr, 0));
+        {
+            const DevTensor * W[3] = { L.q_w, L.k_w, L.v_w };
+            Epi e = make_epi(EPI_QKV, L.q_b, m->q, d);
+            e.bias[1] = (const float *) L.k_b->ptr; e.bias[2] = (const float *) L.v_b->ptr;
+            e.kcache = kc; e.vcache = vc; e.stream_stride = m->stream_stride; e.d = d;
+            e.qscale = 1.0f / sqrtf((float) dk);       // biogpt.cpp:681
+            e.st = m->st; e.mode = mode; e.n = n;
+            RET(launch_gemv(m, s, W, 3, m->act_d, m->A_d, n, 0, e));
+        }
+        if (m->taps_armed && l == 0) CK(cudaMemcpyAsync(m->d_taps[1], m->q, (size_t) n * d * 4, cudaMemcpyDeviceToDevice, s));
+        {
+            AttnArgs a{};
+            a.q = m->q; a.ld_q = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
+            a.out = m->att; a.ld_out = d; a.d = d; a.n = n; a.mode = mode; a.st = m->st; a.exp_tab = m->exp_tab; a.Tmax = m->n_positions;
+            RET(launch_attn(m, s, a, m->n_head, n, dk));
+        }
+        if (m->taps_armed && l == 0) CK(cudaMemcpyAsync(m->d_taps[2], m->att, (size_t) n * d * 4, cudaMemcpyDeviceToDevice, s));
+        RET(launch_act(m, s, m->att, d, nullptr, nullptr, d, wt, m->act_d, m->A_d, n, nullptr, 0));
+        {
+            const DevTensor * W[3] = { L.o_w, nullptr, nullptr };
+            Epi e = make_epi(EPI_RESID, L.o_b, m->x1, d); e.resid = m->x; e.ld_resid = d;
+            RET(launch_gemv(m, s, W, 1, m->act_d, m->A_d, n, 0, e));
+        }
+        RET(launch_act(m, s, m->x1, d, L.ln1_w, L.ln1_b, d, wt, m->act_d, m->A_d, n, nullptr, 0));
+        {
+            const DevTensor * W[3] = { L.fc1_w, nullptr, nullptr };
+            Epi e = make_epi(EPI_GELU, L.fc1_b, m->hff, ff); e.gelu = m->gelu_tab;
+            RET(launch_gemv(m, s, W, 1, m->act_d, m->A_d, n, 0, e));
+        }
+        RET(launch_act(m, s, m->hff, ff, nullptr, nullptr, ff, wt, m->act_ff, m->A_ff, n, nullptr, 0));
+        {
+            const DevTensor * W[3] = { L.fc2_w, nullptr, nullptr };
+            Epi e = make_epi(EPI_RESID, L.fc2_b, m->x, d); e.resid = m->x1; e.ld_resid = d;
+            RET(launch_gemv(m, s, W, 1, m->act_ff, m->A_ff, n, 0, e));
+        }
+        if (m->taps_armed && l == 0) CK(cudaMemcpyAsync(m->d_taps[3], m->x, (size_t) n * d * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if (m->taps_armed) CK(cudaMemcpyAsync(m->d_taps[4], m->x, (size_t) n * d * 4, cudaMemcpyDeviceToDevice, s));
+    RET(launch_act(m, s, m->x, d, m->ln_w, m->ln_b, d, wt, m->act_d, m->A_d, n, nullptr, 0));
+    {
+        // the reference computes all n rows and returns the last (biogpt.cpp:803, 844); rows are
+        // independent, so only the returned row is computed here
+        const int tok0 = mode == 0 ? n - 1 : 0;
+        const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };
+        Epi e = make_epi(EPI_STORE, nullptr, m->logits - (size_t) tok0 * m->n_vocab, m->n_vocab);
+        RET(launch_gemv(m, s, W, 1, m->act_d, m->A_d, n, tok0, e));
+    }
+    return BGPT_OK;
+}
+
+static int check_eval_args(bgpt_model * m, int n, int n_past, int rows_of_stream) {
+    if (!m) return fail(BGPT_E_ARG, "eval: NULL model");
+    if (!m->finalized) return fail(BGPT_E_STATE, "eval before bgpt_cuda_model_finalize");
+    if (n < 1 || n_past < 0 || n_past + rows_of_stream > m->n_positions)
+        return fail(BGPT_E_ARG, "eval: n=%d n_past=%d exceeds n_positions=%d", n, n_past, m->n_positions);
+    return BGPT_OK;
+}
+
+static int fetch_taps(bgpt_model * m, int n) {
+    if (!m->taps_armed) return BGPT_OK;
+    for (int i = 0; i < 5; i++)
+        if (m->taps[i]) CK(cudaMemcpy(m->taps[i], m->d_taps[i], (size_t) n * m->d_model * 4, cudaMemcpyDeviceToHost));
+    m->taps_armed = false;
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_set_taps(bgpt_model * m, float * const taps5[5]) {
+    if (!m) return fail(BGPT_E_ARG, "set_taps: NULL model");
+    m->taps_armed = false;
+    if (taps5) for (int i = 0; i < 5; i++) { m->taps[i] = taps5[i]; if (taps5[i]) m->taps_armed = true; }
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int n_past, float * logits_out) {
+    RET(check_eval_args(m, n, n_past, n));
+    if (!tokens || !logits_out) return fail(BGPT_E_ARG, "eval: NULL buffer");
+    CK(cudaSetDevice(m->device));
+    RET(ensure_arena(m, n));
+    cudaStream_t s = m->stream;
+    memcpy(m->h_tokens, tokens, (size_t) n * sizeof(int));
+    m->h_st->n_past = n_past; m->h_st->step = 0; m->h_st->pad0 = m->h_st->pad1 = 0;
+    CK(cudaEventRecord(m->ev0, s));
+    CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+    RET(enqueue_forward(m, m->d_tokens, n, 0));
+    CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(m->ev1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
+    RET(fetch_taps(m, n));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, int n, int n_past) {
+    RET(check_eval_args(m, n, n_past, n));
+    if (!d_tokens) return fail(BGPT_E_ARG, "eval_device: NULL tokens");
+    CK(cudaSetDevice(m->device));
+    if (n > m->cap) return fail(BGPT_E_ARG, "eval_device: n=%d exceeds the arena (%d rows); create the model with a larger max_batch", n, m->cap);
+    // n_past travels as a 16-byte kernel-visible struct; written with a tiny async memset-like copy
+    // from pinned memory that is safe to overwrite only after the copy ran, so sync first
+    CK(cudaStreamSynchronize(m->stream));
+    m->h_st->n_past = n_past; m->h_st->step = 0;
+    CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, m->stream));
+    RET(enqueue_forward(m, d_tokens, n, 0));
+    return BGPT_OK;
+}
+extern "C" const float * bgpt_cuda_logits_device(bgpt_model * m) { return m ? m->logits : nullptr; }
+extern "C" int bgpt_cuda_synchronize(bgpt_model * m) {
+    if (!m) return fail(BGPT_E_ARG, "synchronize: NULL model");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int n_steps, int32_t * ids_out, float * ms_out) {
+    RET(check_eval_args(m, 1, n_past, n_steps));
+    if (!ids_out || n_steps < 1) return fail(BGPT_E_ARG, "decode_greedy: bad arguments");
+    CK(cudaSetDevice(m->device));
+    RET(ensure_arena(m, 1));
+    cudaStream_t s = m->stream;
+    if (n_steps > m->idlog_cap) {
+        cudaFree(m->d_idlog); m->d_idlog = nullptr;
+        CK(cudaMalloc(&m->d_idlog, (size_t) n_steps * sizeof(int)));
+        m->idlog_cap = n_steps;
+    }
+    CK(cudaStreamSynchronize(s));
+    m->h_tokens[0] = first_token;
+    m->h_st->n_past = n_past; m->h_st->step = 0;
+    CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(m->ev0, s));
+    for (int i = 0; i < n_steps; i++) {
+        RET(enqueue_forward(m, m->d_tokens, 1, 0));
+        k_argmax_advance<<<1, 1024, 0, s>>>(m->logits, m->n_vocab, m->d_tokens, m->d_idlog, m->st, 1);
+        m->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(m->ev1, s));
+    CK(cudaMemcpyAsync(m->h_logits, m->d_idlog, (size_t) n_steps * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    memcpy(ids_out, m->h_logits, (size_t) n_steps * sizeof(int));
+    if (ms_out) *ms_out = m->last_ms;
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_set_streams(bgpt_model * m, int n_streams) {
+    if (!m || n_streams < 1) return fail(BGPT_E_ARG, "set_streams: bad arguments");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    if (n_streams != m->n_streams) RET(alloc_kv(m, n_streams));
+    RET(ensure_arena(m, n_streams));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, int n_streams, int n_past, float * logits_out) {
+    RET(check_eval_args(m, n_streams, n_past, 1));
+    if (!tokens) return fail(BGPT_E_ARG, "eval_streams: NULL tokens");
+    if (n_streams > m->n_streams) return fail(BGPT_E_ARG, "eval_streams: %d streams requested, %d allocated (bgpt_cuda_set_streams)", n_streams, m->n_streams);
+    CK(cudaSetDevice(m->device));
+    RET(ensure_arena(m, n_streams));
+    cudaStream_t s = m->stream;
+    memcpy(m->h_tokens, tokens, (size_t) n_streams * sizeof(int));
+    m->h_st->n_past = n_past; m->h_st->step = 0;
+    CK(cudaEventRecord(m->ev0, s));
+    CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n_streams * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+    RET(enqueue_forward(m, m->d_tokens, n_streams, 1));
+    if (logits_out) CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) n_streams * m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(m->ev1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    if (logits_out) memcpy(logits_out, m->h_logits, (size_t) n_streams * m->n_vocab * 4);
+    return BGPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// unit-level operators (host pointers in, host pointers out; parity tests)
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void * p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t n) { cudaError_t e = cudaMalloc(&p, n ? n : 16); return e == cudaSuccess ? BGPT_OK : fail(BGPT_E_CUDA, "cudaMalloc(%zu): %s", n, cudaGetErrorString(e)); }
+    template <typename T> T * as() { return (T *) p; }
+};
+static int need_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(BGPT_E_CUDA, "no CUDA device: this library has no CPU path (%s)", cudaGetErrorString(e));
+    init_kernel_attrs();
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_op_quantize_act(int wtype, const float * x, void * out, int k) {
+    RET(need_device());
+    if (!bg_type_ok(wtype) || !x || !out || k <= 0 || k % 32) return fail(BGPT_E_ARG, "op_quantize_act: bad arguments");
+    const ActLayout A = bg_act_layout(wtype, k);
+    const int kind = A.kind;
+    const size_t out_bytes = kind == ACT_F32 ? (size_t) k * 4 : kind == ACT_F16 ? (size_t) k * 2 : (size_t) (k / 32) * (kind == ACT_Q8_0 ? 34 : 40);
+    DevBuf dx, da, dout;
+    RET(dx.alloc((size_t) k * 4)); RET(da.alloc(A.bytes)); RET(dout.alloc(out_bytes));
+    CK(cudaMemcpy(dx.p, x, (size_t) k * 4, cudaMemcpyHostToDevice));
+    RET(launch_act(nullptr, 0, dx.as<float>(), k, nullptr, nullptr, k, wtype, da.as<uint8_t>(), A, 1, nullptr, 0));
+    k_act_export<<<1, 256>>>(da.as<uint8_t>(), wtype, k, A.off_d, A.off_s, dout.as<uint8_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, out_bytes, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_op_mul_mat(int type, const void * w, const float * x, float * y, int k, int rows, int n) {
+    RET(need_device());
+    if (!bg_type_ok(type) || !w || !x || !y || k <= 0 || k % 32 || rows <= 0 || n <= 0) return fail(BGPT_E_ARG, "op_mul_mat: bad arguments");
+    DevTensor t; t.type = type; t.ne0 = k; t.ne1 = rows;
+    RET(upload_matrix(t, type, k, rows, (const uint8_t *) w));
+    DevBuf wguard; wguard.p = t.ptr;
+    const ActLayout A = bg_act_layout(type, k);
+    DevBuf dx, da, dy;
+    RET(dx.alloc((size_t) n * k * 4)); RET(da.alloc((size_t) n * A.bytes)); RET(dy.alloc((size_t) n * rows * 4));
+    CK(cudaMemcpy(dx.p, x, (size_t) n * k * 4, cudaMemcpyHostToDevice));
+    RET(launch_act(nullptr, 0, dx.as<float>(), k, nullptr, nullptr, k, type, da.as<uint8_t>(), A, n, nullptr, 0));
+    const DevTensor * W[3] = { &t, nullptr, nullptr };
+    Epi e = make_epi(EPI_STORE, nullptr, dy.as<float>(), rows);
+    RET(launch_gemv(nullptr, 0, W, 1, da.as<uint8_t>(), A, n, 0, e));
+    CK(cudaMemcpy(y, dy.p, (size_t) n * rows * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_op_norm(const float * x, const float * w, const float * b, float * y, int rows, int nc, float eps) {
+    RET(need_device());
+    if (!x || !y || rows <= 0 || nc <= 0) return fail(BGPT_E_ARG, "op_norm: bad arguments");
+    DevBuf dx, dw, db, dy;
+    RET(dx.alloc((size_t) rows * nc * 4)); RET(dy.alloc((size_t) rows * nc * 4)); RET(dw.alloc((size_t) nc * 4)); RET(db.alloc((size_t) nc * 4));
+    CK(cudaMemcpy(dx.p, x, (size_t) rows * nc * 4, cudaMemcpyHostToDevice));
+    if (w) CK(cudaMemcpy(dw.p, w, (size_t) nc * 4, cudaMemcpyHostToDevice));
+    if (b) CK(cudaMemcpy(db.p, b, (size_t) nc * 4, cudaMemcpyHostToDevice));
+    ActArgs a{};
+    a.in = dx.as<float>(); a.ld_in = nc; a.lnw = w ? dw.as<float>() : nullptr; a.lnb = b ? db.as<float>() : nullptr; a.do_ln = 1; a.eps = eps;
+    a.K = nc; a.wtype = BG_F32; a.act = nullptr; a.f32_out = dy.as<float>(); a.ld_out = nc;
+    k_act<<<rows, 256, (size_t) nc * 4>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(y, dy.p, (size_t) rows * nc * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_op_attention(const float * q, const float * k, const float * v, float * out, int n, int n_past, int d_model, int n_head,
+                                      const uint16_t * exp_f16) {
+    RET(need_device());
+    if (!q || !k || !v || !out || !exp_f16 || n <= 0 || n_past < 0 || n_head <= 0 || d_model % n_head) return fail(BGPT_E_ARG, "op_attention: bad arguments");
+    const int T = n_past + n, dk = d_model / n_head;
+    DevBuf dq, dkk, dv, dout, dtab, dst;
+    RET(dq.alloc((size_t) n * d_model * 4)); RET(dkk.alloc((size_t) T * d_model * 4)); RET(dv.alloc((size_t) T * d_model * 4));
+    RET(dout.alloc((size_t) n * d_model * 4)); RET(dtab.alloc(65536 * 2)); RET(dst.alloc(sizeof(DevState)));
+    CK(cudaMemcpy(dq.p, q, (size_t) n * d_model * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dkk.p, k, (size_t) T * d_model * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dv.p, v, (size_t) T * d_model * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtab.p, exp_f16, 65536 * 2, cudaMemcpyHostToDevice));
+    DevState hs{}; hs.n_past = n_past;
+    CK(cudaMemcpy(dst.p, &hs, sizeof hs, cudaMemcpyHostToDevice));
+    AttnArgs a{};
+    a.q = dq.as<float>(); a.ld_q = d_model; a.kcache = dkk.as<float>(); a.vcache = dv.as<float>(); a.stream_stride = 0;
+    a.out = dout.as<float>(); a.ld_out = d_model; a.d = d_model; a.n = n; a.mode = 0; a.st = dst.as<DevState>(); a.exp_tab = dtab.as<uint16_t>(); a.Tmax = T;
+    RET(launch_attn(nullptr, 0, a, n_head, n, dk));
+    CK(cudaMemcpy(out, dout.p, (size_t) n * d_model * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_op_gelu(const float * x, float * y, int n, const uint16_t * gelu_f16) {
+    RET(need_device());
+    if (!x || !y || !gelu_f16 || n <= 0) return fail(BGPT_E_ARG, "op_gelu: bad arguments");
+    DevBuf dx, dy, dtab;
+    RET(dx.alloc((size_t) n * 4)); RET(dy.alloc((size_t) n * 4)); RET(dtab.alloc(65536 * 2));
+    CK(cudaMemcpy(dx.p, x, (size_t) n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtab.p, gelu_f16, 65536 * 2, cudaMemcpyHostToDevice));
+    k_gelu<<<(n + 255) / 256, 256>>>(dx.as<float>(), dy.as<float>(), n, dtab.as<uint16_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(y, dy.p, (size_t) n * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_op_dequantize(int type, const void * w, float * y, int k, int rows) {
+    RET(need_device());
+    if (!bg_type_ok(type) || !w || !y || k <= 0 || k % bg_file_block_elems(type) || rows <= 0) return fail(BGPT_E_ARG, "op_dequantize: bad arguments");
+    const size_t wb = bg_file_row_bytes(type, k) * (size_t) rows;
+    DevBuf dw, dy;
+    RET(dw.alloc(wb)); RET(dy.alloc((size_t) rows * k * 4));
+    CK(cudaMemcpy(dw.p, w, wb, cudaMemcpyHostToDevice));
+    k_dequant_rows<<<rows, 256>>>(dw.as<uint8_t>(), type, k, dy.as<float>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(y, dy.p, (size_t) rows * k * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}

@@ -1,0 +1,686 @@
+// bgpt_kernels.cuh -- hand-written sm_100a kernels of the `biogpt_eval` hot path.
+//
+// Arithmetic contract ("lane order").  Every kernel below reproduces the floating-point
+// operation ORDER of the reference's AVX2 CPU path, so the logits are the reference's logits
+// bit for bit, not merely close:
+//   * quantised dots keep the 8 running sums of ggml_vec_dot_q*_q8_* (ggml.c:2518-2541,
+//     2824-2857, 3071-3093, 3386-3411, 3597-3618): sum l takes elements 4l..4l+3 of each
+//     block, acc_l = fma(d_w*d_a, (float) isum_l, acc_l) in block order, then hsum_float_8
+//     (ggml.c:611-617); the Q4_1/Q5_1 `summs` chain is fma(m_w, s_a, summs).
+//   * F16/F32 dots keep the 4x8 accumulators of ggml_vec_dot_f16/f32 (ggml.c:2372-2443) and
+//     the GGML_F32x8_REDUCE tree (ggml.c:1981-1999): lane = element % 32, reduced with
+//     xor-shuffles 16, 8, 4, 1, 2.
+//   * LayerNorm and softmax accumulate in double like ggml.c:11403-11420, 12955-12974; the
+//     fp16 GELU/exp tables are the host-built tables of ggml.c:4620-4640.
+// The file is compiled with -fmad=false: a multiply-add is fused only where it is written as
+// fmaf(), exactly where the reference binary fuses it.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "bgpt_layout.h"
+
+#define BG_WARP 32
+#define FULLMASK 0xffffffffu
+
+__device__ __forceinline__ float bg_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+__device__ __forceinline__ uint16_t bg_f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
+
+// streaming 128-bit weight load: read-only path, do not pollute L1 (each byte is used once)
+__device__ __forceinline__ uint4 ldg_stream128(const void * p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream64(const void * p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream32(const void * p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-eval state that lives on the device, so that a captured CUDA graph can be replayed for
+// any position: kernels read n_past through this pointer.
+// ---------------------------------------------------------------------------------------------
+struct DevState {
+    int n_past;     // positions already in the KV cache
+    int step;       // greedy-decode step counter (index into the id log)
+    int pad0, pad1;
+};
+// batch row -> (stream, position, attention length).  mode 0: prompt rows of stream 0 at
+// n_past+row, all attending to n_past+n positions (NO causal mask, biogpt.cpp:741-744).
+// mode 1: lock-step streams, row = stream, one token each at n_past.
+__device__ __forceinline__ void bg_row_info(int mode, int n, int n_past, int row, int & stream, int & pos, int & T) {
+    if (mode == 0) { stream = 0; pos = n_past + row; T = n_past + n; }
+    else           { stream = row; pos = n_past;     T = n_past + 1; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// embedding: get_rows(embed_tokens) * sqrt(d_model) + get_rows(embed_pos, n_past+i+2)
+// (biogpt.cpp:663-686; dequantize_row_q*, ggml.c:1536-1646).  Embedding tables stay in the
+// file's AoS layout: two rows per token are read, nothing streams.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bg_dequant_elem(int type, const uint8_t * row, int c) {
+    if (type == BG_F32) return ((const float *) row)[c];
+    if (type == BG_F16) return bg_h2f(((const uint16_t *) row)[c]);
+    const int b = c >> 5, e = c & 31, j = e & 15;
+    const uint8_t * blk = row + (size_t) b * (type == BG_Q4_0 ? 18 : type == BG_Q4_1 ? 20 : type == BG_Q5_0 ? 22 : type == BG_Q5_1 ? 24 : 34);
+    const float d = bg_h2f(*(const uint16_t *) blk);
+    if (type == BG_Q8_0) return __fmul_rn((float) (int) (int8_t) blk[2 + e], d);
+    if (type == BG_Q4_0) { const int q = (e < 16) ? (blk[2 + j] & 0x0F) : (blk[2 + j] >> 4); return __fmul_rn((float) (q - 8), d); }
+    if (type == BG_Q4_1) {
+        const float m = bg_h2f(*(const uint16_t *) (blk + 2));
+        const int q = (e < 16) ? (blk[4 + j] & 0x0F) : (blk[4 + j] >> 4);
+        return __fadd_rn(__fmul_rn((float) q, d), m);
+    }
+    if (type == BG_Q5_0) {
+        const uint32_t qh = (uint32_t) blk[2] | ((uint32_t) blk[3] << 8) | ((uint32_t) blk[4] << 16) | ((uint32_t) blk[5] << 24);
+        const int nib = (e < 16) ? (blk[6 + j] & 0x0F) : (blk[6 + j] >> 4);
+        const int q = nib | (int) (((qh >> e) & 1u) << 4);
+        return __fmul_rn((float) (q - 16), d);
+    }
+    { // Q5_1
+        const float m = bg_h2f(*(const uint16_t *) (blk + 2));
+        const uint32_t qh = (uint32_t) blk[4] | ((uint32_t) blk[5] << 8) | ((uint32_t) blk[6] << 16) | ((uint32_t) blk[7] << 24);
+        const int nib = (e < 16) ? (blk[8 + j] & 0x0F) : (blk[8 + j] >> 4);
+        const int q = nib | (int) (((qh >> e) & 1u) << 4);
+        return __fadd_rn(__fmul_rn((float) q, d), m);
+    }
+}
+
+__global__ void k_embed(const uint8_t * __restrict__ tokW, const uint8_t * __restrict__ posW, int type,
+                        const int * __restrict__ toks, const DevState * __restrict__ st, int mode, int n,
+                        int d, int n_vocab, int n_pos_rows, float scale, float * __restrict__ x) {
+    const int row = blockIdx.x;
+    int stream, pos, T; bg_row_info(mode, n, st->n_past, row, stream, pos, T);
+    int tok = toks[row]; tok = tok < 0 ? 0 : (tok >= n_vocab ? n_vocab - 1 : tok);
+    int prow = pos + 2; prow = prow >= n_pos_rows ? n_pos_rows - 1 : prow;
+    const size_t rb = (size_t) d / (bg_is_quant(type) ? 32 : 1) * (type == BG_F32 ? 4 : type == BG_F16 ? 2 : type == BG_Q4_0 ? 18 : type == BG_Q4_1 ? 20 : type == BG_Q5_0 ? 22 : type == BG_Q5_1 ? 24 : 34);
+    const uint8_t * tr = tokW + rb * (size_t) tok;
+    const uint8_t * pr = posW + rb * (size_t) prow;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float a = __fmul_rn(bg_dequant_elem(type, tr, c), scale);
+        x[(size_t) row * d + c] = __fadd_rn(a, bg_dequant_elem(type, pr, c));
+    }
+}
+
+__global__ void k_dequant_rows(const uint8_t * __restrict__ W, int type, int K, float * __restrict__ y) {
+    const size_t rb = (size_t) K / (bg_is_quant(type) ? 32 : 1) * (type == BG_F32 ? 4 : type == BG_F16 ? 2 : type == BG_Q4_0 ? 18 : type == BG_Q4_1 ? 20 : type == BG_Q5_0 ? 22 : type == BG_Q5_1 ? 24 : 34);
+    const uint8_t * r = W + rb * blockIdx.x;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) y[(size_t) blockIdx.x * K + c] = bg_dequant_elem(type, r, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// block reductions (256 threads)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bg_block_sum_f64(double v, double * scratch /*>= 8*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; i++) t += scratch[i];
+    return t;
+}
+__device__ __forceinline__ float bg_block_max_f32(float v, float * scratch /*>= 8*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, o));
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[w] = v;
+    __syncthreads();
+    float t = scratch[0];
+    for (int i = 1; i < nw; i++) t = fmaxf(t, scratch[i]);
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_act: (optional LayerNorm + affine) then conversion of one token row to the activation
+// record its consumer matmul needs -- the work mul_mat's INIT phase does on the CPU
+// (ggml.c:11909-11925), fused behind the producer.
+//   LayerNorm: ggml_compute_forward_norm_f32, ggml.c:11377-11426, then w*y, +b as separate
+//              roundings (biogpt.cpp:693-700).
+//   Q8_0: quantize_row_q8_0 AVX branch ggml.c:1166-1203 (d=amax/127 -> fp16, id=127/amax, RNE)
+//   Q8_1: quantize_row_q8_1 AVX2 branch ggml.c:1403-1450 (f32 d, s = d*sum(q))
+//   F16 : ggml_fp32_to_fp16_row, ggml.c:493-510
+// grid = token rows, block = 256, dynamic smem = K floats.
+// ---------------------------------------------------------------------------------------------
+struct ActArgs {
+    const float * in; int ld_in;         // [rows][ld_in]
+    const float * lnw; const float * lnb; int do_ln; float eps;
+    int K; int wtype;                    // consumer weight type -> record kind
+    uint8_t * act; int act_bytes;        // record base and stride
+    int off_n, off_d, off_s, code_off;
+    float * f32_out; int ld_out;         // optional copy of the f32 row (taps / unit tests)
+};
+
+__global__ void __launch_bounds__(256) k_act(ActArgs a) {
+    extern __shared__ float srow[];
+    __shared__ double sd[8];
+    const int row = blockIdx.x, tid = threadIdx.x, K = a.K;
+    const float * in = a.in + (size_t) row * a.ld_in;
+    for (int c = tid; c < K; c += blockDim.x) srow[c] = in[c];
+    __syncthreads();
+    if (a.do_ln) {
+        double s = 0.0;
+        for (int c = tid; c < K; c += blockDim.x) s += (double) srow[c];
+        s = bg_block_sum_f64(s, sd);
+        const float mean = (float) (s / K);
+        double s2 = 0.0;
+        for (int c = tid; c < K; c += blockDim.x) {
+            const float v = __fsub_rn(srow[c], mean);
+            srow[c] = v;
+            s2 += (double) __fmul_rn(v, v);
+        }
+        s2 = bg_block_sum_f64(s2, sd);
+        const float variance = (float) (s2 / K);
+        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, a.eps)));
+        for (int c = tid; c < K; c += blockDim.x) {
+            float y = __fmul_rn(srow[c], scale);
+            if (a.lnw) y = __fmul_rn(a.lnw[c], y);
+            if (a.lnb) y = __fadd_rn(y, a.lnb[c]);
+            srow[c] = y;
+        }
+        __syncthreads();
+    }
+    if (a.f32_out) for (int c = tid; c < K; c += blockDim.x) a.f32_out[(size_t) row * a.ld_out + c] = srow[c];
+    if (!a.act) return;
+
+    uint8_t * rec = a.act + (size_t) row * a.act_bytes;
+    const int kind = bg_act_kind(a.wtype);
+    if (kind == ACT_F32) {
+        float * o = (float *) rec;
+        const int Kp = a.act_bytes / 4;
+        for (int i = tid; i < Kp; i += blockDim.x) {     // i = ((gg*32 + lane)*4 + e)
+            const int e = i & 3, lane = (i >> 2) & 31, gg = i >> 7;
+            const int c = gg * 128 + e * 32 + lane;
+            o[i] = c < K ? srow[c] : 0.0f;
+        }
+        return;
+    }
+    if (kind == ACT_F16) {
+        float * o = (float *) rec;
+        const int Kp = a.act_bytes / 4;
+        for (int i = tid; i < Kp; i += blockDim.x) {     // i = (((gg*2 + eh)*32 + lane)*4 + ee)
+            const int ee = i & 3, lane = (i >> 2) & 31, eh = (i >> 7) & 1, gg = i >> 8;
+            const int c = gg * 256 + (eh * 4 + ee) * 32 + lane;
+            o[i] = c < K ? bg_h2f(bg_f2h(srow[c])) : 0.0f;
+        }
+        return;
+    }
+    // quantised records: one warp per 32-element block
+    const int nb = K >> 5, nbp = ((nb + 3) >> 2) << 2;
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    uint32_t * aq = (uint32_t *) rec;
+    int32_t  * an = (int32_t *) (rec + a.off_n);
+    float    * ad = (float *) (rec + a.off_d);
+    float    * as = (float *) (rec + a.off_s);
+    for (int b = warp; b < nbp; b += nw) {
+        const int g = b >> 2, i = b & 3;
+        if (b >= nb) {   // padding block: all-zero codes and scales
+            if ((lane & 3) == 0) { aq[(g * 8 + (lane >> 2)) * 4 + i] = 0u; an[(g * 8 + (lane >> 2)) * 4 + i] = 0; }
+            if (lane == 0) { ad[b] = 0.0f; as[b] = 0.0f; }
+            continue;
+        }
+        const float v = srow[b * 32 + lane];
+        float amax = fabsf(v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, o));
+        const float d  = __fdiv_rn(amax, 127.0f);
+        const float id = (amax != 0.0f) ? __fdiv_rn(127.0f, amax) : 0.0f;
+        const int q = __float2int_rn(__fmul_rn(v, id));
+        const uint32_t byte = (uint32_t) q & 0xFFu;
+        uint32_t w = byte;
+        w |= __shfl_down_sync(FULLMASK, byte, 1) << 8;
+        w |= __shfl_down_sync(FULLMASK, byte, 2) << 16;
+        w |= __shfl_down_sync(FULLMASK, byte, 3) << 24;
+        int s4 = q;
+        s4 += __shfl_down_sync(FULLMASK, q, 1);
+        s4 += __shfl_down_sync(FULLMASK, q, 2);
+        s4 += __shfl_down_sync(FULLMASK, q, 3);
+        int stot = q;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) stot += __shfl_xor_sync(FULLMASK, stot, o);
+        if ((lane & 3) == 0) {
+            const int l = lane >> 2;
+            aq[(g * 8 + l) * 4 + i] = w;
+            an[(g * 8 + l) * 4 + i] = -a.code_off * s4;
+        }
+        if (lane == 0) {
+            if (kind == ACT_Q8_0) { ad[b] = bg_h2f(bg_f2h(d)); as[b] = 0.0f; }
+            else                  { ad[b] = d; as[b] = __fmul_rn(d, (float) stot); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMV / skinny GEMM epilogues (all the bias / scale / residual / GELU / KV-append nodes of
+// biogpt.cpp:705-727, 767-772, 783-795 folded behind the dot products)
+// ---------------------------------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_GELU = 3 };
+struct Epi {
+    int kind;
+    const float * bias[3];
+    float * out; int ld_out;
+    const float * resid; int ld_resid;
+    float * kcache; float * vcache;      // layer base of stream 0
+    size_t stream_stride;                // floats between streams' caches
+    int d; float qscale;
+    const DevState * st; int mode; int n;
+    const uint16_t * gelu;
+};
+__device__ __forceinline__ void bg_epilogue(const Epi & e, int tok, int r, float v) {
+    switch (e.kind) {
+    case EPI_STORE:
+        e.out[(size_t) tok * e.ld_out + r] = e.bias[0] ? __fadd_rn(e.bias[0][r], v) : v;
+        break;
+    case EPI_QKV: {
+        const int mat = r / e.d, rr = r - mat * e.d;
+        const float t = __fadd_rn(e.bias[mat][rr], v);
+        if (mat == 0) { e.out[(size_t) tok * e.ld_out + rr] = __fmul_rn(t, e.qscale); }
+        else {
+            int stream, pos, T; bg_row_info(e.mode, e.n, e.st->n_past, tok, stream, pos, T);
+            float * c = (mat == 1 ? e.kcache : e.vcache) + (size_t) stream * e.stream_stride + (size_t) pos * e.d + rr;
+            *c = t;
+        }
+        break; }
+    case EPI_RESID: {
+        const float t = __fadd_rn(v, e.bias[0][r]);
+        e.out[(size_t) tok * e.ld_out + r] = __fadd_rn(t, e.resid[(size_t) tok * e.ld_resid + r]);
+        break; }
+    case EPI_GELU: {
+        const float t = __fadd_rn(e.bias[0][r], v);
+        e.out[(size_t) tok * e.ld_out + r] = bg_h2f(e.gelu[bg_f2h(t)]);
+        break; }
+    }
+}
+
+struct GemvArgs {
+    const uint8_t * W[3];     // up to three stacked matrices (q,k,v) of rows_per rows each
+    int rows_per;             // rows of one matrix
+    int M;                    // total rows = rows_per * (#matrices)
+    int G;                    // groups per row
+    int stride;               // device row stride (bytes)
+    int off_qh, off_d, off_m;
+    const uint8_t * act; int act_bytes; int off_n, off_dd, off_s;
+    int n;                    // token rows
+    int tok0;                 // first token row handled (lm_head: last row only)
+    Epi epi;
+};
+
+// expand 4 bits (bit k -> byte k) to 0x10 per set bit
+__device__ __forceinline__ uint32_t bg_spread4(uint32_t nib) { return (nib * 0x02040810u) & 0x10101010u; }
+
+// ---------------------------------------------------------------------------------------------
+// k_gemv_q: y[tok][row] = dot(W[row], act[tok]) for the five block-quantised formats.
+// 4 threads per row (thread j: running sums j and j+4), 8 rows per warp, TN token rows per
+// CTA pass with their activation records staged in shared memory.  grid.x strides over row
+// tiles, grid.y over token tiles.
+// ---------------------------------------------------------------------------------------------
+template <int FMT, int TN>
+__global__ void __launch_bounds__(256) k_gemv_q(GemvArgs a) {
+    extern __shared__ uint4 s_act4[];
+    constexpr bool IS8   = (FMT == BG_Q8_0);
+    constexpr bool HASQH = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM  = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    constexpr bool HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
+    const int tid = threadIdx.x;
+    const int tokbase = a.tok0 + blockIdx.y * TN;
+    {   // stage TN activation records (zeros for rows past n)
+        const int v16 = a.act_bytes >> 4;
+        for (int i = tid; i < TN * v16; i += blockDim.x) {
+            const int t = i / v16, o = i - t * v16;
+            uint4 z = make_uint4(0, 0, 0, 0);
+            if (tokbase + t < a.n) z = *(const uint4 *) (a.act + (size_t) (tokbase + t) * a.act_bytes + (size_t) o * 16);
+            s_act4[i] = z;
+        }
+    }
+    __syncthreads();
+    const uint8_t * s_act = (const uint8_t *) s_act4;
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const int rr = lane >> 2, j = lane & 3;
+    for (int rowbase = (blockIdx.x * nw + warp) * 8; rowbase < a.M; rowbase += gridDim.x * nw * 8) {
+        const int row = rowbase + rr;
+        const int rowc = row < a.M ? row : a.M - 1;
+        const int mat = rowc / a.rows_per;
+        const uint8_t * wrow = a.W[mat] + (size_t) (rowc - mat * a.rows_per) * a.stride;
+        float acc0[TN], acc1[TN], summ[TN];
+#pragma unroll
+        for (int t = 0; t < TN; t++) { acc0[t] = 0.0f; acc1[t] = 0.0f; summ[t] = 0.0f; }
+#pragma unroll 2
+        for (int g = 0; g < a.G; g++) {
+            uint32_t lo[4], hi[4];
+            if (IS8) {
+                const uint4 w0 = ldg_stream128(wrow + (size_t) ((g * 2 + 0) * 4 + j) * 16);
+                const uint4 w1 = ldg_stream128(wrow + (size_t) ((g * 2 + 1) * 4 + j) * 16);
+                lo[0] = w0.x; lo[1] = w0.y; lo[2] = w0.z; lo[3] = w0.w;
+                hi[0] = w1.x; hi[1] = w1.y; hi[2] = w1.z; hi[3] = w1.w;
+            } else {
+                const uint4 w = ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
+                const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+                uint32_t qh = 0;
+                if (HASQH) qh = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    lo[i] = ww[i] & 0x0F0F0F0Fu;
+                    hi[i] = (ww[i] >> 4) & 0x0F0F0F0Fu;
+                    if (HASQH) {
+                        const uint32_t hb = (qh >> (8 * i)) & 0xFFu;
+                        lo[i] |= bg_spread4(hb & 0xFu);
+                        hi[i] |= bg_spread4(hb >> 4);
+                    }
+                }
+            }
+            const uint2 dh = ldg_stream64(wrow + a.off_d + g * 8);
+            float dw[4];
+            dw[0] = bg_h2f((uint16_t) (dh.x & 0xFFFF)); dw[1] = bg_h2f((uint16_t) (dh.x >> 16));
+            dw[2] = bg_h2f((uint16_t) (dh.y & 0xFFFF)); dw[3] = bg_h2f((uint16_t) (dh.y >> 16));
+            float mw[4] = { 0.f, 0.f, 0.f, 0.f };
+            if (HASM) {
+                const uint2 mh = ldg_stream64(wrow + a.off_m + g * 8);
+                mw[0] = bg_h2f((uint16_t) (mh.x & 0xFFFF)); mw[1] = bg_h2f((uint16_t) (mh.x >> 16));
+                mw[2] = bg_h2f((uint16_t) (mh.y & 0xFFFF)); mw[3] = bg_h2f((uint16_t) (mh.y >> 16));
+            }
+#pragma unroll
+            for (int t = 0; t < TN; t++) {
+                const uint8_t * rec = s_act + (size_t) t * a.act_bytes;
+                const uint4 a0 = *(const uint4 *) (rec + (g * 8 + j) * 16);
+                const uint4 a1 = *(const uint4 *) (rec + (g * 8 + j + 4) * 16);
+                int4 n0 = make_int4(0, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
+                if (HASOFF) {
+                    n0 = *(const int4 *) (rec + a.off_n + (g * 8 + j) * 16);
+                    n1 = *(const int4 *) (rec + a.off_n + (g * 8 + j + 4) * 16);
+                }
+                const float4 da = *(const float4 *) (rec + a.off_dd + g * 16);
+                float4 sa = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HASM) sa = *(const float4 *) (rec + a.off_s + g * 16);
+                const uint32_t a0w[4] = { a0.x, a0.y, a0.z, a0.w }, a1w[4] = { a1.x, a1.y, a1.z, a1.w };
+                const int n0w[4] = { n0.x, n0.y, n0.z, n0.w }, n1w[4] = { n1.x, n1.y, n1.z, n1.w };
+                const float daw[4] = { da.x, da.y, da.z, da.w }, saw[4] = { sa.x, sa.y, sa.z, sa.w };
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float s  = __fmul_rn(dw[i], daw[i]);
+                    const float p0 = (float) __dp4a((int) lo[i], (int) a0w[i], n0w[i]);
+                    const float p1 = (float) __dp4a((int) hi[i], (int) a1w[i], n1w[i]);
+                    acc0[t] = fmaf(s, p0, acc0[t]);
+                    acc1[t] = fmaf(s, p1, acc1[t]);
+                    if (HASM) summ[t] = fmaf(mw[i], saw[i], summ[t]);
+                }
+            }
+        }
+        // hsum_float_8: ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7))
+#pragma unroll
+        for (int t = 0; t < TN; t++) {
+            float r = __fadd_rn(acc1[t], acc0[t]);
+            r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 2));
+            r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 1));
+            if (HASM) r = __fadd_rn(r, summ[t]);
+            if (j == 0 && row < a.M && tokbase + t < a.n) bg_epilogue(a.epi, tokbase + t, row, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gemv_f: F16 / F32 weights.  One warp per row, lane = running sum (element % 32).
+// F16 activations were rounded through fp16 by k_act and are held as f32, so
+// fma(h2f(w), a, acc) is the reference's GGML_F16_VEC_FMA (ggml.c:2421-2431).
+// ---------------------------------------------------------------------------------------------
+template <int FMT, int TN>
+__global__ void __launch_bounds__(256) k_gemv_f(GemvArgs a) {
+    extern __shared__ uint4 s_act4[];
+    const int tid = threadIdx.x;
+    const int tokbase = a.tok0 + blockIdx.y * TN;
+    {
+        const int v16 = a.act_bytes >> 4;
+        for (int i = tid; i < TN * v16; i += blockDim.x) {
+            const int t = i / v16, o = i - t * v16;
+            uint4 z = make_uint4(0, 0, 0, 0);
+            if (tokbase + t < a.n) z = *(const uint4 *) (a.act + (size_t) (tokbase + t) * a.act_bytes + (size_t) o * 16);
+            s_act4[i] = z;
+        }
+    }
+    __syncthreads();
+    const uint8_t * s_act = (const uint8_t *) s_act4;
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    for (int row = blockIdx.x * nw + warp; row < a.M; row += gridDim.x * nw) {
+        const int mat = row / a.rows_per;
+        const uint8_t * wrow = a.W[mat] + (size_t) (row - mat * a.rows_per) * a.stride;
+        float acc[TN];
+#pragma unroll
+        for (int t = 0; t < TN; t++) acc[t] = 0.0f;
+#pragma unroll 2
+        for (int g = 0; g < a.G; g++) {
+            const uint4 w = ldg_stream128(wrow + (size_t) (g * 32 + lane) * 16);
+            if (FMT == BG_F16) {
+                float wf[8];
+                const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                for (int i = 0; i < 4; i++) { wf[2 * i] = bg_h2f((uint16_t) (ww[i] & 0xFFFF)); wf[2 * i + 1] = bg_h2f((uint16_t) (ww[i] >> 16)); }
+#pragma unroll
+                for (int t = 0; t < TN; t++) {
+                    const uint8_t * rec = s_act + (size_t) t * a.act_bytes;
+                    const float4 x0 = *(const float4 *) (rec + (size_t) ((g * 2 + 0) * 32 + lane) * 16);
+                    const float4 x1 = *(const float4 *) (rec + (size_t) ((g * 2 + 1) * 32 + lane) * 16);
+                    float c = acc[t];
+                    c = fmaf(wf[0], x0.x, c); c = fmaf(wf[1], x0.y, c); c = fmaf(wf[2], x0.z, c); c = fmaf(wf[3], x0.w, c);
+                    c = fmaf(wf[4], x1.x, c); c = fmaf(wf[5], x1.y, c); c = fmaf(wf[6], x1.z, c); c = fmaf(wf[7], x1.w, c);
+                    acc[t] = c;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < TN; t++) {
+                    const uint8_t * rec = s_act + (size_t) t * a.act_bytes;
+                    const float4 x0 = *(const float4 *) (rec + (size_t) (g * 32 + lane) * 16);
+                    float c = acc[t];
+                    c = fmaf(__uint_as_float(w.x), x0.x, c); c = fmaf(__uint_as_float(w.y), x0.y, c);
+                    c = fmaf(__uint_as_float(w.z), x0.z, c); c = fmaf(__uint_as_float(w.w), x0.w, c);
+                    acc[t] = c;
+                }
+            }
+        }
+        // GGML_F32x8_REDUCE: (s0+s2), (s1+s3), sum, then lanes l+4, pairs, pairs
+#pragma unroll
+        for (int t = 0; t < TN; t++) {
+            float r = acc[t];
+            r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 16));
+            r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 8));
+            r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 4));
+            r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 1));
+            r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 2));
+            if (lane == 0 && tokbase + t < a.n) bg_epilogue(a.epi, tokbase + t, row, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_attn: softmax(K q) V for one (head, token row), un-masked over T positions.
+//   scores : ggml_vec_dot_f32(d_kv, K[t], q)            (mul_mat on F32 src0, ggml.c:2372-2407)
+//   softmax: max, fp16-table exp of fp16(x-max), double sum (ggml.c:12914-12983)
+//   output : ggml_vec_dot_f32(T, V_trans[c], p): 32 running sums by t%32, the reduce tree, then
+//            the as-built tail of the reference binary (unfused in groups of 4, fused last <=3)
+// grid = (n_head, rows), block = 256, dynamic smem = (Tmax + 32*DK) floats
+// ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+    const float * q; int ld_q;
+    const float * kcache; const float * vcache; size_t stream_stride;
+    float * out; int ld_out;
+    int d; int n; int mode; const DevState * st;
+    const uint16_t * exp_tab;
+    int Tmax;
+};
+
+template <int DK>
+__global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
+    extern __shared__ float s_f[];
+    __shared__ double sd[8];
+    __shared__ float sm[8];
+    float * sc  = s_f;                 // [Tmax]
+    float * red = s_f + a.Tmax;        // [32][DK]
+    const int h = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    int stream, pos, T; bg_row_info(a.mode, a.n, a.st->n_past, row, stream, pos, T);
+    const float * Kb = a.kcache + (size_t) stream * a.stream_stride + (size_t) h * DK;
+    const float * Vb = a.vcache + (size_t) stream * a.stream_stride + (size_t) h * DK;
+    const float * q  = a.q + (size_t) row * a.ld_q + (size_t) h * DK;
+    constexpr int NP = DK & ~31;                 // vectorised part of the d_kv-long dot
+    constexpr int NV = NP + ((DK - NP) & ~3);
+
+    // ---- scores
+    float qreg[(NP > 0 ? NP / 32 : 1)];
+#pragma unroll
+    for (int i = 0; i < NP / 32; i++) qreg[i] = q[i * 32 + lane];
+    for (int t = warp; t < T; t += 8) {
+        const float * kr = Kb + (size_t) t * a.d;
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NP / 32; i++) s = fmaf(kr[i * 32 + lane], qreg[i], s);
+        if (NP > 0) {
+            s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 16));
+            s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 8));
+            s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 4));
+            s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 1));
+            s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 2));
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = NP; i < NV; i++) s = __fadd_rn(s, __fmul_rn(kr[i], q[i]));
+#pragma unroll
+            for (int i = NV; i < DK; i++) s = fmaf(kr[i], q[i], s);
+            sc[t] = s;
+        }
+    }
+    __syncthreads();
+    // ---- softmax
+    float mx = -INFINITY;
+    for (int t = tid; t < T; t += blockDim.x) mx = fmaxf(mx, sc[t]);
+    mx = bg_block_max_f32(mx, sm);
+    double sum = 0.0;
+    for (int t = tid; t < T; t += blockDim.x) {
+        const float v = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(sc[t], mx))]);
+        sc[t] = v;
+        sum += (double) v;
+    }
+    sum = bg_block_sum_f64(sum, sd);
+    const float inv = (float) (1.0 / sum);
+    for (int t = tid; t < T; t += blockDim.x) sc[t] = __fmul_rn(sc[t], inv);
+    __syncthreads();
+    // ---- output: 32 running sums per column
+    constexpr int NG = 256 / DK;          // thread groups
+    constexpr int CH = 32 / NG;           // running sums per thread
+    const int c = tid % DK, grp = tid / DK;
+    const int np = T & ~31;
+    {
+        float acc[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) acc[u] = 0.0f;
+        for (int s0 = 0; s0 < np; s0 += 32) {
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                const int t = s0 + grp * CH + u;
+                acc[u] = fmaf(Vb[(size_t) t * a.d + c], sc[t], acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; u++) red[(grp * CH + u) * DK + c] = acc[u];
+    }
+    __syncthreads();
+    if (tid < DK) {
+        float x0[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const float a02 = __fadd_rn(red[(0 * 8 + l) * DK + tid], red[(2 * 8 + l) * DK + tid]);
+            const float a13 = __fadd_rn(red[(1 * 8 + l) * DK + tid], red[(3 * 8 + l) * DK + tid]);
+            x0[l] = __fadd_rn(a02, a13);
+        }
+        const float t0 = __fadd_rn(x0[0], x0[4]), t1 = __fadd_rn(x0[1], x0[5]);
+        const float t2 = __fadd_rn(x0[2], x0[6]), t3 = __fadd_rn(x0[3], x0[7]);
+        float sumf = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+        const int nv = np + ((T - np) & ~3);
+        int t = np;
+        for (; t < nv; t++) sumf = __fadd_rn(sumf, __fmul_rn(Vb[(size_t) t * a.d + tid], sc[t]));
+        for (; t < T;  t++) sumf = fmaf(Vb[(size_t) t * a.d + tid], sc[t], sumf);
+        a.out[(size_t) row * a.ld_out + (size_t) h * DK + tid] = sumf;
+    }
+}
+
+// fp16-table GELU as a stand-alone op (unit tests); the eval fuses it into the fc1 epilogue
+__global__ void k_gelu(const float * __restrict__ x, float * __restrict__ y, int n, const uint16_t * __restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = bg_h2f(tab[bg_f2h(x[i])]);
+}
+
+// convert an activation record back to the reference's block_q8_0 / block_q8_1 / fp16 bytes
+__global__ void k_act_export(const uint8_t * __restrict__ rec, int wtype, int K, int off_d, int off_s, uint8_t * __restrict__ out) {
+    const int kind = bg_act_kind(wtype);
+    const int nb = K >> 5;
+    if (kind == ACT_F16) {
+        const float * f = (const float *) rec;
+        for (int c = threadIdx.x; c < K; c += blockDim.x) {
+            const int gg = c / 256, e = (c % 256) / 32, lane = c % 32;
+            ((uint16_t *) out)[c] = bg_f2h(f[(((gg * 2 + (e >> 2)) * 32 + lane) * 4) + (e & 3)]);
+        }
+        return;
+    }
+    if (kind == ACT_F32) {
+        const float * f = (const float *) rec;
+        for (int c = threadIdx.x; c < K; c += blockDim.x) {
+            const int gg = c / 128, e = (c % 128) / 32, lane = c % 32;
+            ((float *) out)[c] = f[(gg * 32 + lane) * 4 + e];
+        }
+        return;
+    }
+    const uint32_t * aq = (const uint32_t *) rec;
+    const float * ad = (const float *) (rec + off_d), * as = (const float *) (rec + off_s);
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        const int g = b >> 2, i = b & 3;
+        uint8_t * o = out + (size_t) b * (kind == ACT_Q8_0 ? 34 : 40);
+        int hdr;
+        if (kind == ACT_Q8_0) { const uint16_t hd = bg_f2h(ad[b]); o[0] = hd & 0xFF; o[1] = hd >> 8; hdr = 2; }
+        else {
+            const uint32_t d = __float_as_uint(ad[b]), s = __float_as_uint(as[b]);
+            for (int k = 0; k < 4; k++) { o[k] = (d >> (8 * k)) & 0xFF; o[4 + k] = (s >> (8 * k)) & 0xFF; }
+            hdr = 8;
+        }
+        for (int l = 0; l < 8; l++) {
+            const uint32_t w = aq[(g * 8 + l) * 4 + i];
+            for (int k = 0; k < 4; k++) o[hdr + 4 * l + k] = (w >> (8 * k)) & 0xFF;
+        }
+    }
+}
+
+// greedy sampling on the device: argmax (first index wins), log the id, feed it back and
+// advance n_past -- lets a whole decode loop run without the host (bgpt_cuda_decode_greedy)
+__global__ void __launch_bounds__(1024) k_argmax_advance(const float * __restrict__ logits, int n_vocab,
+                                                         int * __restrict__ next_tok, int * __restrict__ id_log,
+                                                         DevState * st, int n_advance) {
+    __shared__ float sv[32]; __shared__ int si[32];
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
+        const float v = logits[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULLMASK, best, o); const int oi = __shfl_xor_sync(FULLMASK, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int) (blockDim.x >> 5); w++)
+            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+        if (bi == 0x7fffffff) bi = 0;
+        next_tok[0] = bi;
+        id_log[st->step] = bi;
+        st->step += 1;
+        st->n_past += n_advance;
+    }
+}

@@ -1,0 +1,155 @@
+/* include/bgpt_cuda.h -- the drop-in boundary of the B200 `biogpt_eval` hot path.
+ *
+ * A plain C ABI (extern "C", pointers and sizes only, no C++ / torch types) exported by
+ * biogpt.cpp_b200/csrc/libbgpt_cuda.so.  It is what the reference's C++ model API binds to
+ * when its ggml CPU graph is replaced by the device engine:
+ *
+ *   reference interface (under /root/reference)              replaced by
+ *   -------------------------------------------------------  ---------------------------------
+ *   biogpt_model_load: ggml_init / ggml_backend_alloc_buffer  bgpt_cuda_model_create
+ *     biogpt.cpp:215-242, KV cache biogpt.cpp:324-358
+ *   biogpt_model_load: tensor loop, the non-CPU upload hook   bgpt_cuda_upload_tensor
+ *     ggml_backend_tensor_set, biogpt.cpp:369-434 (421-427)
+ *   ggml fp16 GELU / exp tables, ggml.c:4620-4640             bgpt_cuda_set_tables
+ *   "all tensors present" check, biogpt.cpp:442-447           bgpt_cuda_model_finalize
+ *   biogpt_eval + biogpt_graph + ggml_backend_graph_compute   bgpt_cuda_eval
+ *     biogpt.cpp:812-847, 624-810
+ *   ggml_free / ggml_backend_buffer_free / ggml_backend_free  bgpt_cuda_model_free
+ *     examples/main/main.cpp:164-169
+ *
+ * The host side (biogpt.cpp_b200/host/, C++) keeps the reference's own signatures
+ * (biogpt_model_load / biogpt_eval / biogpt_sample_top_k_top_p, biogpt.h:128-172) and calls
+ * only the functions below.  Every function returns 0 on success or a negative BGPT_E_* code;
+ * bgpt_cuda_last_error() describes the last failure on the calling thread.  Nothing here ever
+ * falls back to the CPU: without a CUDA device every entry point fails with BGPT_E_CUDA.
+ */
+#ifndef BGPT_CUDA_H
+#define BGPT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGPT_OK            0
+#define BGPT_E_CUDA      (-1)  /* CUDA runtime error / no device */
+#define BGPT_E_ARG       (-2)  /* bad argument (shape, type, range) */
+#define BGPT_E_STATE     (-3)  /* call order (e.g. eval before finalize) */
+#define BGPT_E_UNSUPPORTED (-4)
+
+/* ggml_type codes used in the `.bin` tensor headers (ggml.h:306-314) */
+#define BGPT_TYPE_F32   0
+#define BGPT_TYPE_F16   1
+#define BGPT_TYPE_Q4_0  2
+#define BGPT_TYPE_Q4_1  3
+#define BGPT_TYPE_Q5_0  6
+#define BGPT_TYPE_Q5_1  7
+#define BGPT_TYPE_Q8_0  8
+
+typedef struct bgpt_model bgpt_model;
+
+/* ---- library / device ------------------------------------------------------------------ */
+const char * bgpt_cuda_last_error(void);
+int          bgpt_cuda_device_count(void);               /* <0 on error */
+const char * bgpt_cuda_version(void);
+
+/* ---- model life cycle ------------------------------------------------------------------- */
+/* hparams7 = { n_vocab, n_layer, n_head, n_positions, d_ff, d_model, ftype } exactly as stored
+ * in the file header (biogpt.cpp:54-60).  Allocates the F32 KV cache
+ * [n_layer][n_positions][d_model] x2 (biogpt.cpp:324-335) and the activation arena for up to
+ * `max_batch` tokens per eval (the reference's n_batch; evals with more tokens re-size it). */
+bgpt_model * bgpt_cuda_model_create(const int32_t hparams7[7], int device, int max_batch);
+
+/* One tensor of the file, `data` = the raw bytes that follow its header in the `.bin`
+ * (nbytes is checked against ne0*ne1 and the type, like biogpt.cpp:412-417). Names are the
+ * loader's lookup keys (biogpt.cpp:258-317). Matrices are re-tiled on upload (same bytes,
+ * permuted inside each row) so that device loads are aligned 128-bit; see DESIGN.md. */
+int bgpt_cuda_upload_tensor(bgpt_model * m, const char * name, int ggml_type,
+                            int64_t ne0, int64_t ne1, const void * data, size_t nbytes);
+
+/* The two 65536-entry fp16 lookup tables of ggml (GELU and exp, ggml.c:4620-4640), built by
+ * the caller with the host libm so that they are the tables the reference would build on
+ * this machine. */
+int bgpt_cuda_set_tables(bgpt_model * m, const uint16_t * gelu_f16, const uint16_t * exp_f16);
+/* Host helper (no GPU involved): fills both tables with the host libm, the way ggml_init
+ * does (ggml.c:4620-4640). */
+void bgpt_host_build_tables(uint16_t * gelu_f16, uint16_t * exp_f16);
+
+/* Checks that all 4 + 18*n_layer tensors and the tables arrived; after this the model is
+ * immutable and bgpt_cuda_eval may be called. */
+int bgpt_cuda_model_finalize(bgpt_model * m);
+
+void bgpt_cuda_model_free(bgpt_model * m);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* biogpt_eval (biogpt.cpp:812-847): `n` tokens at positions [n_past, n_past+n) of stream 0;
+ * `logits_out` (HOST) receives the n_vocab logits of the last token.  Attention is
+ * un-masked over all n_past+n positions exactly like the reference graph
+ * (biogpt.cpp:741-744). Host->device copy of the ids and device->host copy of the logits
+ * are part of the call. */
+int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int n_past, float * logits_out);
+
+/* Same step with everything resident in HBM: token ids are read from `d_tokens` (device
+ * pointer) and the logits stay in the model's device buffer (bgpt_cuda_logits_device).
+ * Asynchronous on the model's stream; used by the bench to time the kernels alone. */
+int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, int n, int n_past);
+const float * bgpt_cuda_logits_device(bgpt_model * m);
+int bgpt_cuda_synchronize(bgpt_model * m);
+
+/* Greedy decode entirely on the device: starting from `first_token` at position n_past,
+ * run `n_steps` evals of one token each, feeding argmax(logits) back in (first index wins
+ * ties, like std::partial_sort with top_k = 1 in biogpt_sample_top_k_top_p,
+ * biogpt.cpp:908-980).  ids_out (HOST, n_steps entries) receives the sampled ids.
+ * `ms_out` (optional) receives the device time of the loop measured with CUDA events. */
+int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int n_steps,
+                            int32_t * ids_out, float * ms_out);
+
+/* multi-stream state: `n_streams` independent sequences, each with its own KV cache
+ * (SURVEY 8(d) config 4).  Stream 0 always exists. */
+int bgpt_cuda_set_streams(bgpt_model * m, int n_streams);
+/* lock-step decode: one token per stream at the same n_past; logits_out = [n_streams][n_vocab]
+ * on the HOST (may be NULL to leave them on the device). */
+int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, int n_streams, int n_past,
+                           float * logits_out);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+void   bgpt_cuda_hparams(const bgpt_model * m, int32_t out7[7]);
+size_t bgpt_cuda_weight_bytes(const bgpt_model * m);     /* device bytes of all uploaded tensors */
+/* kernels launched by the library since load (the bench reports launches per step) */
+uint64_t bgpt_cuda_launch_count(const bgpt_model * m);
+/* device time of the last bgpt_cuda_eval / eval_streams call, CUDA events on its stream */
+float  bgpt_cuda_last_eval_ms(const bgpt_model * m);
+/* debug taps of the last eval, [n][d_model] floats each, HOST pointers, any may be NULL:
+ * which = 0 embed (token*sqrt(d)+pos), 1 layer-0 scaled q, 2 layer-0 merged attention,
+ * 3 layer-0 output, 4 input of the final LayerNorm.  Must be armed before the eval. */
+int    bgpt_cuda_set_taps(bgpt_model * m, float * const taps5[5]);
+
+/* ---- unit-level operators (same arithmetic the eval uses; parity tests call these) ------- */
+/* y[n][rows] = W[rows][k] . x[n][k]; `w` in file layout for `ggml_type`
+ * (ggml_compute_forward_mul_mat, ggml.c:11804-12013).  All pointers HOST. */
+int bgpt_cuda_op_mul_mat(int ggml_type, const void * w, const float * x, float * y,
+                         int k, int rows, int n);
+/* activation quantisers applied to src1 by mul_mat (ggml.c:1166-1249, 1403-1494, 493-510):
+ * out = k/32 blocks of block_q8_0 (34 B) / block_q8_1 (40 B) for the weight type's
+ * vec_dot_type, or k fp16 values for F16 weights. */
+int bgpt_cuda_op_quantize_act(int weight_type, const float * x, void * out, int k);
+/* LayerNorm + affine (ggml.c:11377-11426 then mul, add; biogpt.cpp:693-700); w or b may be
+ * NULL for the bare norm. */
+int bgpt_cuda_op_norm(const float * x, const float * w, const float * b, float * y,
+                      int rows, int nc, float eps);
+/* one attention call: q [n][d_model] (already scaled), caches k,v [T][d_model] with
+ * T = n_past + n; out [n][d_model]  (biogpt.cpp:730-764) */
+int bgpt_cuda_op_attention(const float * q, const float * k, const float * v, float * out,
+                           int n, int n_past, int d_model, int n_head,
+                           const uint16_t * exp_f16);
+/* y = fp16-table GELU (ggml.c:3853-3861) */
+int bgpt_cuda_op_gelu(const float * x, float * y, int n, const uint16_t * gelu_f16);
+/* dequantise `rows` rows of k elements (get_rows, ggml.c:12524-12628) */
+int bgpt_cuda_op_dequantize(int ggml_type, const void * w, float * y, int k, int rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGPT_CUDA_H */

@@ -1,0 +1,118 @@
+"""GPU tier: whole `biogpt_eval` steps through the C ABI against the oracle and the committed
+reference logits -- bit for bit, every format, prompt batches (un-masked) and decode steps."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FTYPES, ROOT, gf
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _diff(tag, got, want):
+    bad = np.flatnonzero(_bits(got).ravel() != _bits(want).ravel())
+    return f"{tag}: {bad.size}/{got.size} logits differ, max|d|={np.abs(got - want).max():.3e}"
+
+
+@pytest.mark.parametrize("ftype", FTYPES)
+def test_tiny_matches_reference_golden(capi, zoo, ftype):
+    """the committed logits came from the UNMODIFIED reference (tests/golden/make_golden.py)"""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tiny_logits.npz"))
+    M = capi.Model.load(zoo.path("tiny", ftype))
+    toks, sched, want = gold["tokens"], gold["schedule"], gold[f"logits_{ftype}"]
+    pos = 0
+    for i, (n, n_past) in enumerate(sched):
+        got = M.eval(toks[pos:pos + n], int(n_past))
+        pos += n
+        assert np.array_equal(_bits(got), _bits(want[i])), _diff(f"{ftype} eval {i} (n={n}, n_past={n_past})", got, want[i])
+    M.close()
+
+
+@pytest.mark.parametrize("ftype", FTYPES)
+def test_small_matches_oracle_with_taps(checkers, capi, zoo, ftype):
+    """d_model 256, d_kv 64, d_ff 1024, 3 layers; intermediate taps localise any mismatch"""
+    p = zoo.path("small", ftype)
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p, max_batch=16)
+    toks = gf.synth_tokens(70, gf.SMALL.n_vocab, seed=21)
+    pos = 0
+    for n in (8, 8, 1, 1, 5, 1, 16, 1, 1, 9, 1):
+        want, wt = O.eval(toks[pos:pos + n], pos, taps=True)
+        got, gt = M.eval(toks[pos:pos + n], pos, taps=True)
+        for a, b in (("embed", "embed"), ("layer0_q", "layer0_q"), ("layer0_att", "layer0_att"), ("layer0_out", "layer0_out")):
+            assert np.array_equal(_bits(gt[a]), _bits(wt[b])), _diff(f"{ftype} tap {a} at pos {pos} n={n}", gt[a], wt[b])
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} logits at pos {pos} n={n}", got, want)
+        pos += n
+    O.close(); M.close()
+
+
+@pytest.mark.parametrize("ftype", ["f16", "q4_0", "q8_0"])
+def test_greedy_ids_identical(checkers, capi, zoo, ftype):
+    """device-side greedy loop (argmax on the GPU, no host round trip) == oracle greedy ids"""
+    p = zoo.path("small", ftype)
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p)
+    prompt = gf.synth_tokens(6, gf.SMALL.n_vocab, seed=2)
+    lo = O.eval(prompt, 0)
+    lg = M.eval(prompt, 0)
+    assert np.array_equal(_bits(lo), _bits(lg))
+    first = int(np.argmax(lo))
+    steps = 48
+    ids, ms = M.decode_greedy(first, len(prompt), steps)
+    want = []
+    tok = first
+    for i in range(steps):
+        l = O.eval(np.array([tok], np.int32), len(prompt) + i)
+        tok = int(np.argmax(l))
+        want.append(tok)
+    assert ids.tolist() == want
+    O.close(); M.close()
+
+
+@pytest.mark.parametrize("ftype", ["q5_1", "f16"])
+def test_lockstep_streams_equal_single_stream(capi, zoo, ftype):
+    """config 4: S sequences decoded in lock step share each weight read; every stream must equal
+    its own single-stream run bit for bit"""
+    p = zoo.path("small", ftype)
+    S, steps = 5, 12
+    seqs = [gf.synth_tokens(steps, gf.SMALL.n_vocab, seed=100 + s) for s in range(S)]
+    single = []
+    M = capi.Model.load(p)
+    for s in range(S):
+        single.append(np.stack([M.eval(seqs[s][i:i + 1], i) for i in range(steps)]))
+    M.set_streams(S)
+    for i in range(steps):
+        out = M.eval_streams(np.array([seqs[s][i] for s in range(S)], np.int32), i)
+        for s in range(S):
+            assert np.array_equal(_bits(out[s]), _bits(single[s][i])), (ftype, s, i)
+    M.close()
+
+
+@pytest.mark.parametrize("ftype", ["q4_0", "f16", "q8_0", "q5_1"])
+def test_base_shape_matches_oracle(checkers, capi, zoo, ftype):
+    """true BioGPT-base shapes (d_model 1024, 24 layers, 16 heads, d_ff 4096, vocab 42384),
+    synthetic weights: an 8-token un-masked prompt batch, then decode steps"""
+    p = zoo.path("base", ftype)
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p)
+    toks = gf.synth_tokens(12, gf.BASE.n_vocab, seed=9)
+    want = O.eval(toks[:8], 0); got = M.eval(toks[:8], 0)
+    assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} prompt", got, want)
+    for i in range(8, 12):
+        want = O.eval(toks[i:i + 1], i); got = M.eval(toks[i:i + 1], i)
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} decode {i}", got, want)
+    O.close(); M.close()
+
+
+def test_errors_are_reported_not_swallowed(capi, zoo):
+    M = capi.Model.load(zoo.path("tiny", "q4_0"))
+    with pytest.raises(capi.BgptError):
+        M.eval(np.zeros(4, np.int32), gf.TINY.n_positions - 2)   # runs past n_positions
+    with pytest.raises(capi.BgptError):
+        M.eval_streams(np.zeros(3, np.int32), 0)                 # streams not allocated
+    M.close()

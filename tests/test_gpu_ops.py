@@ -1,0 +1,146 @@
+"""GPU tier: each device operator against the CPU oracle, through the C ABI, bit for bit.
+
+The oracle restates the reference's AVX2 arithmetic order (oracle/biogpt_oracle.c); the kernels
+follow the same order (bgpt_kernels.cuh, "lane order"), so every comparison here is exact
+equality of the float bit patterns, not a tolerance."""
+import numpy as np
+import pytest
+
+from conftest import gf
+
+pytestmark = pytest.mark.gpu
+
+TYPES = {"f32": 0, "f16": 1, "q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_0": 8}
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _report(name, got, want):
+    bad = np.flatnonzero(_bits(got).ravel() != _bits(want).ravel())
+    return f"{name}: {bad.size}/{got.size} differ, max|d|={np.abs(got - want).max():.3e}, first={bad[:5]}"
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+@pytest.mark.parametrize("k", [64, 1024, 4096])
+def test_quantize_act(checkers, capi, name, k):
+    """mul_mat's src1 conversion: Q8_0 / Q8_1 blocks or fp16, incl. an all-zero block"""
+    t = TYPES[name]
+    rng = np.random.default_rng(k + t)
+    x = (rng.standard_normal(k) * 2.5).astype(np.float32)
+    x[32:64] = 0.0
+    got = capi.op_quantize_act(t, x)
+    O = checkers.oracle_lib()
+    if t == 0:
+        want = x.view(np.uint8)
+    elif t == 1:
+        h = np.zeros(k, np.uint16); O.bo_fp32_to_fp16_row(x, h, k); want = h.view(np.uint8)
+    elif t in (2, 6, 8):
+        want = np.zeros(k // 32 * 34, np.uint8); O.bo_quantize_row_q8_0(x, want, k)
+    else:
+        want = np.zeros(k // 32 * 40, np.uint8); O.bo_quantize_row_q8_1(x, want, k)
+    assert np.array_equal(got, want), f"{name} k={k}: {np.flatnonzero(got != want)[:8]}"
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+@pytest.mark.parametrize("shape", [(64, 24, 1), (1024, 1024, 1), (4096, 1024, 1), (1024, 4096, 3),
+                                   (1024, 1000, 8), (4096, 264, 9), (1024, 2649 * 16, 1), (128, 8, 2)])
+def test_mul_mat(checkers, capi, name, shape):
+    """the seven weight formats x the BioGPT shapes (K 1024/4096, M 1024/4096/42384) and ragged
+    ones (rows not a multiple of the tile, 9 token rows = one full tile + 1)"""
+    k, rows, n = shape
+    t = TYPES[name]
+    rng = np.random.default_rng(k * 7 + rows + n + t)
+    w = (rng.standard_normal((rows, k)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    wb = np.frombuffer(gf.encode_tensor(w, t), dtype=np.uint8).copy()
+    want = np.zeros((n, rows), dtype=np.float32)
+    checkers.oracle_lib().bo_mul_mat(t, wb, x, want, k, rows, n)
+    got = capi.op_mul_mat(t, wb, x, rows)
+    assert np.array_equal(_bits(got), _bits(want)), _report(f"{name} {shape}", got, want)
+
+
+@pytest.mark.parametrize("nc", [64, 256, 1024, 4096])
+def test_norm(checkers, capi, nc):
+    rng = np.random.default_rng(nc)
+    rows = 5
+    x = (rng.standard_normal((rows, nc)) * 3 + 0.5).astype(np.float32)
+    w = (1 + 0.05 * rng.standard_normal(nc)).astype(np.float32)
+    b = (0.02 * rng.standard_normal(nc)).astype(np.float32)
+    want = np.zeros_like(x)
+    for r in range(rows):
+        y = np.zeros(nc, np.float32)
+        checkers.oracle_lib().bo_norm(x[r], y, nc, 1e-5)
+        want[r] = y
+    got = capi.op_norm(x, None, None, 1e-5)
+    assert np.array_equal(_bits(got), _bits(want)), _report("norm", got, want)
+    want_aff = ((w * want).astype(np.float32) + b).astype(np.float32)
+    got_aff = capi.op_norm(x, w, b, 1e-5)
+    assert np.array_equal(_bits(got_aff), _bits(want_aff)), _report("norm+affine", got_aff, want_aff)
+
+
+def _oracle_attention(O, q, k, v, n_head):
+    """softmax(K q) V per head, composed from the oracle's own ops (biogpt_oracle.c bo_eval)"""
+    n, d = q.shape
+    T = k.shape[0]
+    dk = d // n_head
+    out = np.zeros_like(q)
+    sc = np.zeros(T, np.float32)
+    for h in range(n_head):
+        for i in range(n):
+            qh = np.ascontiguousarray(q[i, h * dk:(h + 1) * dk])
+            for t in range(T):
+                sc[t] = O.bo_vec_dot_f32(dk, np.ascontiguousarray(k[t, h * dk:(h + 1) * dk]), qh)
+            p = np.zeros(T, np.float32)
+            O.bo_soft_max(sc, p, T)
+            for c in range(dk):
+                out[i, h * dk + c] = O.bo_vec_dot_f32(T, np.ascontiguousarray(v[:, h * dk + c]), p)
+    return out
+
+
+@pytest.mark.parametrize("cfg", [(64, 4, 1, 0), (64, 4, 3, 5), (256, 4, 1, 40), (256, 4, 2, 62), (1024, 16, 1, 97),
+                                 (1024, 16, 1, 31), (256, 2, 1, 200), (128, 4, 1, 35)])
+def test_attention(checkers, capi, cfg):
+    """un-masked attention: T = n_past + n below / at / above the 32-wide vector boundary, with a
+    4-multiple tail and a <4 remainder; head dims 16, 32, 64, 128"""
+    d, n_head, n, n_past = cfg
+    rng = np.random.default_rng(d + n_past)
+    T = n_past + n
+    q = (rng.standard_normal((n, d)) * 0.5).astype(np.float32)
+    k = rng.standard_normal((T, d)).astype(np.float32)
+    v = rng.standard_normal((T, d)).astype(np.float32)
+    O = checkers.oracle_lib()
+    g, e = capi.build_tables()
+    want = _oracle_attention(O, q, k, v, n_head)
+    got = capi.op_attention(q, k, v, n_past, n_head, e)
+    assert np.array_equal(_bits(got), _bits(want)), _report(f"attention {cfg}", got, want)
+
+
+def test_gelu(checkers, capi):
+    x = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
+    x = np.where(np.isfinite(x), x, 0).astype(np.float32)
+    x = np.concatenate([x, (np.random.default_rng(0).standard_normal(4096) * 4).astype(np.float32)])
+    want = np.zeros_like(x)
+    checkers.oracle_lib().bo_gelu(x, want, x.size)
+    g, e = capi.build_tables()
+    got = capi.op_gelu(x, g)
+    assert np.array_equal(_bits(got), _bits(want))
+
+
+@pytest.mark.parametrize("name", list(TYPES))
+def test_dequantize_rows(checkers, capi, name):
+    """get_rows on every storage type (embedding gather)"""
+    t = TYPES[name]
+    rng = np.random.default_rng(t)
+    k, rows = 1024, 7
+    w = (rng.standard_normal((rows, k)) * 0.02).astype(np.float32)
+    wb = np.frombuffer(gf.encode_tensor(w, t), dtype=np.uint8).copy()
+    want = np.zeros((rows, k), np.float32)
+    rb = gf.row_bytes(t, k)
+    for r in range(rows):
+        y = np.zeros(k, np.float32)
+        checkers.oracle_lib().bo_dequantize_row(t, wb[r * rb:(r + 1) * rb].copy(), y, k)
+        want[r] = y
+    got = capi.op_dequantize(t, wb, k, rows)
+    assert np.array_equal(_bits(got), _bits(want))
