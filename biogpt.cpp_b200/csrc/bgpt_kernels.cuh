@@ -641,17 +641,19 @@ __global__ void k_act_export(const uint8_t * __restrict__ rec, int wtype, int K,
     const float * ad = (const float *) (rec + off_d), * as = (const float *) (rec + off_s);
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
         const int g = b >> 2, i = b & 3;
-        uint8_t * o = out + (size_t) b * (kind == ACT_Q8_0 ? 34 : 40);
-        int hdr;
-        if (kind == ACT_Q8_0) { const uint16_t hd = bg_f2h(ad[b]); o[0] = hd & 0xFF; o[1] = hd >> 8; hdr = 2; }
-        else {
-            const uint32_t d = __float_as_uint(ad[b]), s = __float_as_uint(as[b]);
-            for (int k = 0; k < 4; k++) { o[k] = (d >> (8 * k)) & 0xFF; o[4 + k] = (s >> (8 * k)) & 0xFF; }
-            hdr = 8;
-        }
-        for (int l = 0; l < 8; l++) {
-            const uint32_t w = aq[(g * 8 + l) * 4 + i];
-            for (int k = 0; k < 4; k++) o[hdr + 4 * l + k] = (w >> (8 * k)) & 0xFF;
+        if (kind == ACT_Q8_0) {          // block_q8_0: fp16 d, 32 x int8 (2-byte aligned)
+            uint16_t * o16 = (uint16_t *) (out + (size_t) b * 34);
+            o16[0] = bg_f2h(ad[b]);
+            for (int l = 0; l < 8; l++) {
+                const uint32_t w = aq[(g * 8 + l) * 4 + i];
+                o16[1 + 2 * l] = (uint16_t) (w & 0xFFFFu);
+                o16[2 + 2 * l] = (uint16_t) (w >> 16);
+            }
+        } else {                          // block_q8_1: f32 d, f32 s, 32 x int8 (8-byte aligned)
+            uint32_t * o32 = (uint32_t *) (out + (size_t) b * 40);
+            o32[0] = __float_as_uint(ad[b]);
+            o32[1] = __float_as_uint(as[b]);
+            for (int l = 0; l < 8; l++) o32[2 + l] = aq[(g * 8 + l) * 4 + i];
         }
     }
 }
