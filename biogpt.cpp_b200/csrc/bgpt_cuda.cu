@@ -14,12 +14,14 @@
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
 #include "../../include/bgpt_cuda.h"
 #include "bgpt_kernels.cuh"
+#include "bgpt_mega.cuh"
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -85,6 +87,12 @@ struct bgpt_model {
     float last_ms = 0.f;
     uint64_t launches = 0;
     size_t weight_bytes = 0;
+    // persistent decode kernel (bgpt_mega.cuh)
+    bool mega_ok = false; int decode_path = 1;          // 1: k_mega for n == 1, 0: per-op kernels
+    MegaParams mp{}; MegaLayer * d_mega_layers = nullptr;
+    unsigned long long * d_bar = nullptr; unsigned long long bar_epoch = 0;
+    float * d_cand_val = nullptr; int * d_cand_idx = nullptr; int mega_grid = 0;
+    long long * d_prof = nullptr; int prof_n = 0;
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -170,6 +178,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     for (auto & kv : m->tensors) cudaFree(kv.second.ptr);
     free_arena(m);
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
+    cudaFree(m->d_prof); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
@@ -272,6 +281,8 @@ static void init_kernel_attrs() {
     cudaGetLastError();
 }
 
+static int mega_setup(bgpt_model * m);
+
 extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (!m) return fail(BGPT_E_ARG, "finalize: NULL model");
     if (!m->have_tabs) return fail(BGPT_E_STATE, "finalize: lookup tables not set (bgpt_cuda_set_tables)");
@@ -300,6 +311,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     }
     CK(cudaSetDevice(m->device));
     init_kernel_attrs();
+    RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
 }
@@ -371,7 +383,7 @@ static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W
 }
 
 static int launch_attn(bgpt_model * m, cudaStream_t s, const AttnArgs & a, int n_head, int rows, int dk) {
-    const size_t smem = ((size_t) a.Tmax + 32 * (size_t) dk) * 4;
+    const size_t smem = ((size_t) a.Tmax + 64 * (size_t) dk) * 4;
     dim3 grid(n_head, rows);
     switch (dk) {
         case 16:  k_attn<16><<<grid, 256, smem, s>>>(a); break;
@@ -456,6 +468,141 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
     return BGPT_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// persistent decode kernel: host side
+// ------------------------------------------------------------------------------------------
+template <int FMT> static const void * mega_fn_dk(int dk) {
+    switch (dk) {
+        case 16:  return (const void *) k_mega<FMT, 16>;
+        case 32:  return (const void *) k_mega<FMT, 32>;
+        case 64:  return (const void *) k_mega<FMT, 64>;
+        case 128: return (const void *) k_mega<FMT, 128>;
+    }
+    return nullptr;
+}
+static const void * mega_fn(int wtype, int dk) {
+    switch (wtype) {
+        case BG_Q4_0: return mega_fn_dk<BG_Q4_0>(dk);
+        case BG_Q4_1: return mega_fn_dk<BG_Q4_1>(dk);
+        case BG_Q5_0: return mega_fn_dk<BG_Q5_0>(dk);
+        case BG_Q5_1: return mega_fn_dk<BG_Q5_1>(dk);
+        case BG_Q8_0: return mega_fn_dk<BG_Q8_0>(dk);
+        case BG_F16:  return mega_fn_dk<BG_F16>(dk);
+    }
+    return nullptr;   // F32 weights: per-op kernels only
+}
+
+static int mega_setup(bgpt_model * m) {
+    m->mega_ok = false;
+    const int dk = m->d_model / m->n_head;
+    const void * fn = mega_fn(m->wtype, dk);
+    if (!fn) return BGPT_OK;
+    MegaParams & p = m->mp;
+    p.d = m->d_model; p.ff = m->d_ff; p.n_head = m->n_head; p.dk = dk; p.n_layer = m->n_layer; p.n_vocab = m->n_vocab;
+    p.n_positions = m->n_positions; p.n_pos_rows = (int) m->embed_pos->ne1; p.wtype = m->wtype;
+    p.emb_scale = sqrtf((float) m->d_model); p.qscale = 1.0f / sqrtf((float) dk); p.eps = 1e-5f;
+    const RowLayout Ld = bg_row_layout(m->wtype, m->d_model), Lf = bg_row_layout(m->wtype, m->d_ff);
+    p.Gd = Ld.G; p.stride_d = Ld.stride; p.offqh_d = Ld.off_qh; p.offd_d = Ld.off_d; p.offm_d = Ld.off_m;
+    p.Gf = Lf.G; p.stride_f = Lf.stride; p.offqh_f = Lf.off_qh; p.offd_f = Lf.off_d; p.offm_f = Lf.off_m;
+    p.actb_d = m->A_d.bytes; p.offn_d = m->A_d.off_n; p.offdd_d = m->A_d.off_d; p.offs_d = m->A_d.off_s;
+    p.actb_f = m->A_ff.bytes; p.offn_f = m->A_ff.off_n; p.offdd_f = m->A_ff.off_d; p.offs_f = m->A_ff.off_s;
+    p.code_off = bg_code_offset(m->wtype);
+    std::vector<MegaLayer> hl(m->n_layer);
+    for (int i = 0; i < m->n_layer; i++) {
+        const LayerW & L = m->layers[i]; MegaLayer & o = hl[i];
+        o.q_w = L.q_w->ptr; o.k_w = L.k_w->ptr; o.v_w = L.v_w->ptr; o.o_w = L.o_w->ptr; o.fc1_w = L.fc1_w->ptr; o.fc2_w = L.fc2_w->ptr;
+        o.q_b = (const float *) L.q_b->ptr; o.k_b = (const float *) L.k_b->ptr; o.v_b = (const float *) L.v_b->ptr; o.o_b = (const float *) L.o_b->ptr;
+        o.ln0_w = (const float *) L.ln0_w->ptr; o.ln0_b = (const float *) L.ln0_b->ptr; o.ln1_w = (const float *) L.ln1_w->ptr; o.ln1_b = (const float *) L.ln1_b->ptr;
+        o.fc1_b = (const float *) L.fc1_b->ptr; o.fc2_b = (const float *) L.fc2_b->ptr;
+    }
+    CK(cudaMalloc(&m->d_mega_layers, hl.size() * sizeof(MegaLayer)));
+    CK(cudaMemcpy(m->d_mega_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+    p.layers = m->d_mega_layers;
+    p.embed_tok = m->embed_tokens->ptr; p.embed_pos = m->embed_pos->ptr; p.lm_head = m->lm_head->ptr;
+    p.lnf_w = (const float *) m->ln_w->ptr; p.lnf_b = (const float *) m->ln_b->ptr;
+    p.gelu = m->gelu_tab; p.exp_tab = m->exp_tab;
+    // shared-memory carve-up
+    auto al = [](int x) { return (x + 127) & ~127; };
+    int o = 0;
+    p.sm_row = o; o += al(std::max(m->d_model, m->d_ff) * 4);
+    p.sm_act = o; o += al(std::max(m->A_d.bytes, m->A_ff.bytes));
+    int smp = 0;
+    if (m->wtype != BG_F16) smp = std::max(MEGA_RT * 8 * (4 * Ld.G + 4) * 4, 8 * 8 * (4 * Lf.G + 4) * 4);
+    p.sm_p = o; o += al(smp); const int smp_bytes = smp;
+    p.sm_s = o; o += al(smp / 8);
+    p.sm_m = o; o += al(smp / 8);
+    p.sm_attn = o; o += al((m->n_positions + 64 * dk) * 4);
+    p.sm_total = o;
+    // the kernel reads the byte CAPACITY of the p-scratch from sm_p's neighbour: pass it explicitly
+    (void) smp_bytes;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, m->device));
+    if ((size_t) p.sm_total > (size_t) prop.sharedMemPerBlockOptin) return BGPT_OK;   // does not fit: per-op kernels
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, p.sm_total));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, MEGA_NT, p.sm_total));
+    if (occ < 1) return BGPT_OK;
+    m->mega_grid = prop.multiProcessorCount;
+    const char * eg = getenv("BGPT_MEGA_GRID");
+    if (eg && atoi(eg) > 0 && atoi(eg) <= prop.multiProcessorCount * occ) m->mega_grid = atoi(eg);
+    CK(cudaMalloc(&m->d_bar, 512)); CK(cudaMemset(m->d_bar, 0, 512));
+    {   // attention column split: largest divisor of d_kv that keeps >= 8 columns per CTA and fits the grid
+        int parts = 1;
+        for (int c = 1; c <= dk; c++) if (dk % c == 0 && dk / c >= 8 && m->n_head * c <= m->mega_grid) parts = c;
+        p.attn_parts = parts;
+    }
+    p.prof = nullptr;
+    if (getenv("BGPT_MEGA_PROF")) {
+        m->prof_n = ((m->n_layer + 1) * 5) * 3;
+        CK(cudaMalloc(&m->d_prof, m->prof_n * sizeof(long long))); CK(cudaMemset(m->d_prof, 0, m->prof_n * sizeof(long long)));
+        p.prof = m->d_prof;
+    }
+    CK(cudaMalloc(&m->d_cand_val, 1024 * sizeof(float))); CK(cudaMalloc(&m->d_cand_idx, 1024 * sizeof(int)));
+    p.bar = m->d_bar; p.cand_val = m->d_cand_val; p.cand_idx = m->d_cand_idx; p.n_cand = m->mega_grid;
+    m->bar_epoch = 0;
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
+    m->mega_ok = coop != 0;
+    const char * e = getenv("BGPT_DECODE_PATH");
+    if (e) m->decode_path = atoi(e);
+    return BGPT_OK;
+}
+
+// one token at n_past on the persistent kernel.  token source: d_tok (device) or the previous
+// launch's argmax candidates (use_cand).  Asynchronous on the model's stream.
+static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot) {
+    MegaParams p = m->mp;
+    p.kcache = m->kcache; p.vcache = m->vcache;
+    p.x = m->x; p.x1 = m->x1; p.q = m->q; p.att = m->att; p.hff = m->hff; p.logits = m->logits;
+    p.tok = d_tok; p.use_cand = use_cand; p.idlog = m->d_idlog; p.log_slot = log_slot; p.n_past = n_past;
+    p.bar_base = m->bar_epoch;
+    m->bar_epoch += (unsigned long long) 5 * m->n_layer * m->mega_grid;
+    void * args[] = { &p };
+    const void * fn = mega_fn(m->wtype, m->d_model / m->n_head);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(m->mega_grid), dim3(MEGA_NT), args, (size_t) p.sm_total, m->stream));
+    m->launches++;
+    return BGPT_OK;
+}
+static bool use_mega(const bgpt_model * m) { return m->mega_ok && m->decode_path == 1 && !m->taps_armed; }
+
+extern "C" int bgpt_cuda_set_decode_path(bgpt_model * m, int path) {
+    if (!m || (path != 0 && path != 1)) return fail(BGPT_E_ARG, "set_decode_path: path must be 0 (per-op kernels) or 1 (persistent kernel)");
+    if (path == 1 && !m->mega_ok) return fail(BGPT_E_UNSUPPORTED, "set_decode_path: the persistent kernel is not available for this model/device");
+    m->decode_path = path;
+    return BGPT_OK;
+}
+// debug: clock64 stamps of CTA 0 in the last persistent-kernel launch (BGPT_MEGA_PROF=1),
+// [n_layer+1][5 phases][start, matmul start, matmul end]
+extern "C" int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap) {
+    if (!m || !m->d_prof) return 0;
+    const int n = cap < m->prof_n ? cap : m->prof_n;
+    cudaStreamSynchronize(m->stream);
+    if (cudaMemcpy(out, m->d_prof, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" int bgpt_cuda_get_decode_path(const bgpt_model * m) { return m && m->mega_ok && m->decode_path == 1 ? 1 : 0; }
+
 static int check_eval_args(bgpt_model * m, int n, int n_past, int rows_of_stream) {
     if (!m) return fail(BGPT_E_ARG, "eval: NULL model");
     if (!m->finalized) return fail(BGPT_E_STATE, "eval before bgpt_cuda_model_finalize");
@@ -490,7 +637,8 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
     CK(cudaEventRecord(m->ev0, s));
     CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
-    RET(enqueue_forward(m, m->d_tokens, n, 0));
+    if (n == 1 && use_mega(m)) { RET(launch_mega(m, m->d_tokens, 0, n_past, -1)); }
+    else RET(enqueue_forward(m, m->d_tokens, n, 0));
     CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
@@ -510,7 +658,8 @@ extern "C" int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, i
     CK(cudaStreamSynchronize(m->stream));
     m->h_st->n_past = n_past; m->h_st->step = 0;
     CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, m->stream));
-    RET(enqueue_forward(m, d_tokens, n, 0));
+    if (n == 1 && use_mega(m)) { RET(launch_mega(m, d_tokens, 0, n_past, -1)); }
+    else RET(enqueue_forward(m, d_tokens, n, 0));
     return BGPT_OK;
 }
 extern "C" const float * bgpt_cuda_logits_device(bgpt_model * m) { return m ? m->logits : nullptr; }
@@ -538,11 +687,18 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
     CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(m->ev0, s));
-    for (int i = 0; i < n_steps; i++) {
-        RET(enqueue_forward(m, m->d_tokens, 1, 0));
-        k_argmax_advance<<<1, 1024, 0, s>>>(m->logits, m->n_vocab, m->d_tokens, m->d_idlog, m->st, 1);
+    if (use_mega(m)) {
+        for (int i = 0; i < n_steps; i++) RET(launch_mega(m, m->d_tokens, i > 0, n_past + i, i - 1));
+        k_mega_pick<<<1, 32, 0, s>>>(m->d_cand_val, m->d_cand_idx, m->mega_grid, m->d_idlog, n_steps - 1, m->d_tokens);
         m->launches++;
         CK(cudaGetLastError());
+    } else {
+        for (int i = 0; i < n_steps; i++) {
+            RET(enqueue_forward(m, m->d_tokens, 1, 0));
+            k_argmax_advance<<<1, 1024, 0, s>>>(m->logits, m->n_vocab, m->d_tokens, m->d_idlog, m->st, 1);
+            m->launches++;
+            CK(cudaGetLastError());
+        }
     }
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaMemcpyAsync(m->h_logits, m->d_idlog, (size_t) n_steps * sizeof(int), cudaMemcpyDeviceToHost, s));

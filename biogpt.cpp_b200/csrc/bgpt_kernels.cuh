@@ -119,7 +119,7 @@ __global__ void k_dequant_rows(const uint8_t * __restrict__ W, int type, int K, 
 // ---------------------------------------------------------------------------------------------
 // block reductions (256 threads)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double bg_block_sum_f64(double v, double * scratch /*>= 8*/) {
+__device__ __forceinline__ double bg_block_sum_f64(double v, double * scratch /*>= 32*/) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
     const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -130,7 +130,7 @@ __device__ __forceinline__ double bg_block_sum_f64(double v, double * scratch /*
     for (int i = 0; i < nw; i++) t += scratch[i];
     return t;
 }
-__device__ __forceinline__ float bg_block_max_f32(float v, float * scratch /*>= 8*/) {
+__device__ __forceinline__ float bg_block_max_f32(float v, float * scratch /*>= 32*/) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, o));
     const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -162,43 +162,41 @@ struct ActArgs {
     float * f32_out; int ld_out;         // optional copy of the f32 row (taps / unit tests)
 };
 
-__global__ void __launch_bounds__(256) k_act(ActArgs a) {
-    extern __shared__ float srow[];
-    __shared__ double sd[8];
-    const int row = blockIdx.x, tid = threadIdx.x, K = a.K;
-    const float * in = a.in + (size_t) row * a.ld_in;
-    for (int c = tid; c < K; c += blockDim.x) srow[c] = in[c];
-    __syncthreads();
-    if (a.do_ln) {
-        double s = 0.0;
-        for (int c = tid; c < K; c += blockDim.x) s += (double) srow[c];
-        s = bg_block_sum_f64(s, sd);
-        const float mean = (float) (s / K);
-        double s2 = 0.0;
-        for (int c = tid; c < K; c += blockDim.x) {
-            const float v = __fsub_rn(srow[c], mean);
-            srow[c] = v;
-            s2 += (double) __fmul_rn(v, v);
-        }
-        s2 = bg_block_sum_f64(s2, sd);
-        const float variance = (float) (s2 / K);
-        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, a.eps)));
-        for (int c = tid; c < K; c += blockDim.x) {
-            float y = __fmul_rn(srow[c], scale);
-            if (a.lnw) y = __fmul_rn(a.lnw[c], y);
-            if (a.lnb) y = __fadd_rn(y, a.lnb[c]);
-            srow[c] = y;
-        }
-        __syncthreads();
+// LayerNorm (+affine) of the K floats in shared memory `srow`, in place.  All threads of the CTA.
+__device__ __forceinline__ void bg_ln_row(float * srow, int K, const float * __restrict__ lnw, const float * __restrict__ lnb,
+                                          float eps, double * sd /*>= 32 doubles*/) {
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (int c = tid; c < K; c += blockDim.x) s += (double) srow[c];
+    s = bg_block_sum_f64(s, sd);
+    const float mean = (float) (s / K);
+    double s2 = 0.0;
+    for (int c = tid; c < K; c += blockDim.x) {
+        const float v = __fsub_rn(srow[c], mean);
+        srow[c] = v;
+        s2 += (double) __fmul_rn(v, v);
     }
-    if (a.f32_out) for (int c = tid; c < K; c += blockDim.x) a.f32_out[(size_t) row * a.ld_out + c] = srow[c];
-    if (!a.act) return;
+    s2 = bg_block_sum_f64(s2, sd);
+    const float variance = (float) (s2 / K);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
+    for (int c = tid; c < K; c += blockDim.x) {
+        float y = __fmul_rn(srow[c], scale);
+        if (lnw) y = __fmul_rn(lnw[c], y);
+        if (lnb) y = __fadd_rn(y, lnb[c]);
+        srow[c] = y;
+    }
+    __syncthreads();
+}
 
-    uint8_t * rec = a.act + (size_t) row * a.act_bytes;
-    const int kind = bg_act_kind(a.wtype);
+// f32 row in shared memory -> activation record (global or shared).  All threads of the CTA;
+// the caller synchronises before consuming the record.
+__device__ __forceinline__ void bg_row_to_record(const float * srow, int K, int wtype, uint8_t * rec, int act_bytes,
+                                                 int off_n, int off_d, int off_s, int code_off) {
+    const int tid = threadIdx.x;
+    const int kind = bg_act_kind(wtype);
     if (kind == ACT_F32) {
         float * o = (float *) rec;
-        const int Kp = a.act_bytes / 4;
+        const int Kp = act_bytes / 4;
         for (int i = tid; i < Kp; i += blockDim.x) {     // i = ((gg*32 + lane)*4 + e)
             const int e = i & 3, lane = (i >> 2) & 31, gg = i >> 7;
             const int c = gg * 128 + e * 32 + lane;
@@ -208,7 +206,7 @@ __global__ void __launch_bounds__(256) k_act(ActArgs a) {
     }
     if (kind == ACT_F16) {
         float * o = (float *) rec;
-        const int Kp = a.act_bytes / 4;
+        const int Kp = act_bytes / 4;
         for (int i = tid; i < Kp; i += blockDim.x) {     // i = (((gg*2 + eh)*32 + lane)*4 + ee)
             const int ee = i & 3, lane = (i >> 2) & 31, eh = (i >> 7) & 1, gg = i >> 8;
             const int c = gg * 256 + (eh * 4 + ee) * 32 + lane;
@@ -220,9 +218,9 @@ __global__ void __launch_bounds__(256) k_act(ActArgs a) {
     const int nb = K >> 5, nbp = ((nb + 3) >> 2) << 2;
     const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
     uint32_t * aq = (uint32_t *) rec;
-    int32_t  * an = (int32_t *) (rec + a.off_n);
-    float    * ad = (float *) (rec + a.off_d);
-    float    * as = (float *) (rec + a.off_s);
+    int32_t  * an = (int32_t *) (rec + off_n);
+    float    * ad = (float *) (rec + off_d);
+    float    * as = (float *) (rec + off_s);
     for (int b = warp; b < nbp; b += nw) {
         const int g = b >> 2, i = b & 3;
         if (b >= nb) {   // padding block: all-zero codes and scales
@@ -252,13 +250,26 @@ __global__ void __launch_bounds__(256) k_act(ActArgs a) {
         if ((lane & 3) == 0) {
             const int l = lane >> 2;
             aq[(g * 8 + l) * 4 + i] = w;
-            an[(g * 8 + l) * 4 + i] = -a.code_off * s4;
+            an[(g * 8 + l) * 4 + i] = -code_off * s4;
         }
         if (lane == 0) {
             if (kind == ACT_Q8_0) { ad[b] = bg_h2f(bg_f2h(d)); as[b] = 0.0f; }
             else                  { ad[b] = d; as[b] = __fmul_rn(d, (float) stot); }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_act(ActArgs a) {
+    extern __shared__ float srow[];
+    __shared__ double sd[32];
+    const int row = blockIdx.x, tid = threadIdx.x, K = a.K;
+    const float * in = a.in + (size_t) row * a.ld_in;
+    for (int c = tid; c < K; c += blockDim.x) srow[c] = in[c];
+    __syncthreads();
+    if (a.do_ln) bg_ln_row(srow, K, a.lnw, a.lnb, a.eps, sd);
+    if (a.f32_out) for (int c = tid; c < K; c += blockDim.x) a.f32_out[(size_t) row * a.ld_out + c] = srow[c];
+    if (!a.act) return;
+    bg_row_to_record(srow, K, a.wtype, a.act + (size_t) row * a.act_bytes, a.act_bytes, a.off_n, a.off_d, a.off_s, a.code_off);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(256) k_gemv_f(GemvArgs a) {
 //   softmax: max, fp16-table exp of fp16(x-max), double sum (ggml.c:12914-12983)
 //   output : ggml_vec_dot_f32(T, V_trans[c], p): 32 running sums by t%32, the reduce tree, then
 //            the as-built tail of the reference binary (unfused in groups of 4, fused last <=3)
-// grid = (n_head, rows), block = 256, dynamic smem = (Tmax + 32*DK) floats
+// grid = (n_head, rows), block = 256, dynamic smem = (Tmax + 64*DK) floats
 // ---------------------------------------------------------------------------------------------
 struct AttnArgs {
     const float * q; int ld_q;
@@ -517,31 +528,29 @@ struct AttnArgs {
     int Tmax;
 };
 
-template <int DK>
-__global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
-    extern __shared__ float s_f[];
-    __shared__ double sd[8];
-    __shared__ float sm[8];
+// one (head, row) of attention by the whole CTA of NT threads; `s_f` = (Tmax + 32*DK) floats of
+// shared memory.  KV reads bypass L1 (__ldcg): rows appended by other CTAs earlier in a
+// persistent kernel must never be served from a stale L1 line.
+template <int DK, int NT>
+__device__ __forceinline__ void bg_attention_head(const float * __restrict__ q /*DK*/, const float * Kb, const float * Vb, int ldkv, int T,
+                                                  const uint16_t * __restrict__ exp_tab, float * s_f, int Tmax,
+                                                  double * sd /*32*/, float * sm /*32*/, float * out /*DK*/) {
     float * sc  = s_f;                 // [Tmax]
-    float * red = s_f + a.Tmax;        // [32][DK]
-    const int h = blockIdx.x, row = blockIdx.y, tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    int stream, pos, T; bg_row_info(a.mode, a.n, a.st->n_past, row, stream, pos, T);
-    const float * Kb = a.kcache + (size_t) stream * a.stream_stride + (size_t) h * DK;
-    const float * Vb = a.vcache + (size_t) stream * a.stream_stride + (size_t) h * DK;
-    const float * q  = a.q + (size_t) row * a.ld_q + (size_t) h * DK;
+    float * red = s_f + Tmax;          // [32][DK]
+    float * tailv = red + 32 * DK;     // [<=31][DK] V rows of the scalar tail, staged so the tail is not a chain of global loads
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NWARP = NT / 32;
     constexpr int NP = DK & ~31;                 // vectorised part of the d_kv-long dot
     constexpr int NV = NP + ((DK - NP) & ~3);
-
     // ---- scores
     float qreg[(NP > 0 ? NP / 32 : 1)];
 #pragma unroll
     for (int i = 0; i < NP / 32; i++) qreg[i] = q[i * 32 + lane];
-    for (int t = warp; t < T; t += 8) {
-        const float * kr = Kb + (size_t) t * a.d;
+    for (int t = warp; t < T; t += NWARP) {
+        const float * kr = Kb + (size_t) t * ldkv;
         float s = 0.0f;
 #pragma unroll
-        for (int i = 0; i < NP / 32; i++) s = fmaf(kr[i * 32 + lane], qreg[i], s);
+        for (int i = 0; i < NP / 32; i++) s = fmaf(__ldcg(kr + i * 32 + lane), qreg[i], s);
         if (NP > 0) {
             s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 16));
             s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 8));
@@ -551,32 +560,33 @@ __global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
         }
         if (lane == 0) {
 #pragma unroll
-            for (int i = NP; i < NV; i++) s = __fadd_rn(s, __fmul_rn(kr[i], q[i]));
+            for (int i = NP; i < NV; i++) s = __fadd_rn(s, __fmul_rn(__ldcg(kr + i), q[i]));
 #pragma unroll
-            for (int i = NV; i < DK; i++) s = fmaf(kr[i], q[i], s);
+            for (int i = NV; i < DK; i++) s = fmaf(__ldcg(kr + i), q[i], s);
             sc[t] = s;
         }
     }
     __syncthreads();
     // ---- softmax
     float mx = -INFINITY;
-    for (int t = tid; t < T; t += blockDim.x) mx = fmaxf(mx, sc[t]);
+    for (int t = tid; t < T; t += NT) mx = fmaxf(mx, sc[t]);
     mx = bg_block_max_f32(mx, sm);
     double sum = 0.0;
-    for (int t = tid; t < T; t += blockDim.x) {
-        const float v = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(sc[t], mx))]);
+    for (int t = tid; t < T; t += NT) {
+        const float v = bg_h2f(exp_tab[bg_f2h(__fsub_rn(sc[t], mx))]);
         sc[t] = v;
         sum += (double) v;
     }
     sum = bg_block_sum_f64(sum, sd);
     const float inv = (float) (1.0 / sum);
-    for (int t = tid; t < T; t += blockDim.x) sc[t] = __fmul_rn(sc[t], inv);
+    for (int t = tid; t < T; t += NT) sc[t] = __fmul_rn(sc[t], inv);
     __syncthreads();
     // ---- output: 32 running sums per column
-    constexpr int NG = 256 / DK;          // thread groups
-    constexpr int CH = 32 / NG;           // running sums per thread
+    constexpr int NG = NT / DK;           // thread groups
+    constexpr int CH = (32 + NG - 1) / NG; // running sums per thread
     const int c = tid % DK, grp = tid / DK;
     const int np = T & ~31;
+    for (int i = tid; i < (T - np) * DK; i += NT) tailv[i] = __ldcg(Vb + (size_t) (np + i / DK) * ldkv + (i % DK));
     {
         float acc[CH];
 #pragma unroll
@@ -584,12 +594,12 @@ __global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
         for (int s0 = 0; s0 < np; s0 += 32) {
 #pragma unroll
             for (int u = 0; u < CH; u++) {
-                const int t = s0 + grp * CH + u;
-                acc[u] = fmaf(Vb[(size_t) t * a.d + c], sc[t], acc[u]);
+                const int r = grp * CH + u;
+                if (r < 32) { const int t = s0 + r; acc[u] = fmaf(__ldcg(Vb + (size_t) t * ldkv + c), sc[t], acc[u]); }
             }
         }
 #pragma unroll
-        for (int u = 0; u < CH; u++) red[(grp * CH + u) * DK + c] = acc[u];
+        for (int u = 0; u < CH; u++) { const int r = grp * CH + u; if (r < 32) red[r * DK + c] = acc[u]; }
     }
     __syncthreads();
     if (tid < DK) {
@@ -605,10 +615,24 @@ __global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
         float sumf = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
         const int nv = np + ((T - np) & ~3);
         int t = np;
-        for (; t < nv; t++) sumf = __fadd_rn(sumf, __fmul_rn(Vb[(size_t) t * a.d + tid], sc[t]));
-        for (; t < T;  t++) sumf = fmaf(Vb[(size_t) t * a.d + tid], sc[t], sumf);
-        a.out[(size_t) row * a.ld_out + (size_t) h * DK + tid] = sumf;
+        for (; t < nv; t++) sumf = __fadd_rn(sumf, __fmul_rn(tailv[(t - np) * DK + tid], sc[t]));
+        for (; t < T;  t++) sumf = fmaf(tailv[(t - np) * DK + tid], sc[t], sumf);
+        out[tid] = sumf;
     }
+    __syncthreads();
+}
+
+template <int DK>
+__global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
+    extern __shared__ float s_f[];
+    __shared__ double sd[32];
+    __shared__ float sm[32];
+    const int h = blockIdx.x, row = blockIdx.y;
+    int stream, pos, T; bg_row_info(a.mode, a.n, a.st->n_past, row, stream, pos, T);
+    const float * Kb = a.kcache + (size_t) stream * a.stream_stride + (size_t) h * DK;
+    const float * Vb = a.vcache + (size_t) stream * a.stream_stride + (size_t) h * DK;
+    bg_attention_head<DK, 256>(a.q + (size_t) row * a.ld_q + (size_t) h * DK, Kb, Vb, a.d, T, a.exp_tab, s_f, a.Tmax, sd, sm,
+                               a.out + (size_t) row * a.ld_out + (size_t) h * DK);
 }
 
 // fp16-table GELU as a stand-alone op (unit tests); the eval fuses it into the fc1 epilogue

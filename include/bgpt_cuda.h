@@ -106,6 +106,15 @@ int bgpt_cuda_synchronize(bgpt_model * m);
 int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int n_steps,
                             int32_t * ids_out, float * ms_out);
 
+/* Which schedule evaluates single-token steps (n == 1): 1 = one persistent kernel per token
+ * (default when available), 0 = one kernel per fused operator (the schedule used for n > 1 and
+ * for lock-step streams).  Both produce identical bits; tests compare them. */
+int bgpt_cuda_set_decode_path(bgpt_model * m, int path);
+int bgpt_cuda_get_decode_path(const bgpt_model * m);
+/* debug (env BGPT_MEGA_PROF=1 at load): per-phase clock64 stamps of CTA 0 of the last
+ * persistent-kernel launch; returns the number of entries copied (0 when profiling is off). */
+int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);
+
 /* multi-stream state: `n_streams` independent sequences, each with its own KV cache
  * (SURVEY 8(d) config 4).  Stream 0 always exists. */
 int bgpt_cuda_set_streams(bgpt_model * m, int n_streams);

@@ -109,6 +109,50 @@ def test_base_shape_matches_oracle(checkers, capi, zoo, ftype):
     O.close(); M.close()
 
 
+@pytest.mark.parametrize("ftype", ["f16", "q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+@pytest.mark.parametrize("size", ["tiny", "small"])
+def test_persistent_kernel_equals_oracle_and_per_op_path(checkers, capi, zoo, size, ftype):
+    """single-token steps run on ONE persistent kernel (grid barriers between phases); it must
+    give the oracle's bits and the per-operator schedule's bits at every position, including
+    T crossing the 32-wide boundary and the scalar tails (T % 32 in 1..3 and 4..31)"""
+    hp = {"tiny": gf.TINY, "small": gf.SMALL}[size]
+    p = zoo.path(size, ftype)
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p)
+    assert M.decode_path == 1, "persistent kernel not available: " + capi.last_error()
+    n_steps = min(hp.n_positions, 70)
+    toks = gf.synth_tokens(n_steps, hp.n_vocab, seed=33)
+    got1 = []
+    for i in range(n_steps):
+        want = O.eval(toks[i:i + 1], i)
+        got = M.eval(toks[i:i + 1], i)
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{size}/{ftype} persistent kernel at n_past={i}", got, want)
+        got1.append(got)
+    M.set_decode_path(0)
+    for i in range(n_steps):
+        got = M.eval(toks[i:i + 1], i)
+        assert np.array_equal(_bits(got), _bits(got1[i])), (size, ftype, i)
+    O.close(); M.close()
+
+
+def test_persistent_kernel_long_context(checkers, capi, zoo):
+    """prompt in un-masked batches of 8 (per-op kernels), then persistent-kernel decode near the end
+    of the context"""
+    p = zoo.path("small", "q4_0")
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p)
+    toks = gf.synth_tokens(gf.SMALL.n_positions, gf.SMALL.n_vocab, seed=4)
+    pos = 0
+    while pos < 240:
+        want = O.eval(toks[pos:pos + 8], pos); got = M.eval(toks[pos:pos + 8], pos)
+        assert np.array_equal(_bits(got), _bits(want)), pos
+        pos += 8
+    for i in range(240, gf.SMALL.n_positions):
+        want = O.eval(toks[i:i + 1], i); got = M.eval(toks[i:i + 1], i)
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"n_past={i}", got, want)
+    O.close(); M.close()
+
+
 def test_errors_are_reported_not_swallowed(capi, zoo):
     M = capi.Model.load(zoo.path("tiny", "q4_0"))
     with pytest.raises(capi.BgptError):

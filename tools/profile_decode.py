@@ -23,4 +23,18 @@ if a.warm:
     M.decode_greedy(2, a.n_past, a.warm)
 ids, ms = M.decode_greedy(2, a.n_past, a.steps)
 print(f"{a.ftype} n_past={a.n_past}: {a.steps} tokens in {ms:.3f} ms -> {ms / a.steps * 1e3:.1f} us/token, launches={M.launch_count}")
+prof = M.read_prof()
+if prof is not None:
+    import numpy as np
+    names = ["LN0+qkv", "attention", "out_proj", "LN1+fc1", "fc2"]
+    L = prof.shape[0] - 1
+    P = prof[:L].astype(np.float64)
+    nxt = np.empty((L, 5)); nxt[:, :4] = P[:, 1:, 0]; nxt[:-1, 4] = P[1:, 0, 0]; nxt[-1, 4] = prof[L, 0, 0]
+    print("per-phase cycles of CTA 0 (mean over layers; ~1.9 cycles/ns): prologue | matmul/attn | barrier wait | total")
+    for i, nme in enumerate(names):
+        pro = (P[:, i, 1] - P[:, i, 0]).mean() if i != 1 else 0.0
+        body = (P[:, i, 2] - P[:, i, 1]).mean() if i != 1 else (P[:, i, 2] - P[:, i, 0]).mean()
+        bar = (nxt[:, i] - P[:, i, 2]).mean()
+        print(f"  {nme:10s} {pro:9.0f} {body:9.0f} {bar:9.0f} {pro + body + bar:9.0f}")
+    print(f"  layer total {(nxt[:, 4] - P[:, 0, 0]).mean():9.0f} cycles;  lm_head: prologue {prof[L,0,1]-prof[L,0,0]} matmul {prof[L,0,2]-prof[L,0,1]}; whole kernel {prof[L,0,2]-prof[0,0,0]}")
 M.close()
