@@ -15,6 +15,7 @@
 #include "../../include/bgpt_cuda.h"
 #include "bgpt_kernels.cuh"
 #include "bgpt_mega.cuh"
+#include "bgpt_barbench.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -93,6 +94,7 @@ struct bgpt_model {
     unsigned long long * d_bar = nullptr; unsigned long long bar_epoch = 0;
     float * d_cand_val = nullptr; int * d_cand_idx = nullptr; int mega_grid = 0;
     long long * d_prof = nullptr; int prof_n = 0;
+    uint8_t * d_rec_att = nullptr, * d_rec_hff = nullptr;
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -178,7 +180,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     for (auto & kv : m->tensors) cudaFree(kv.second.ptr);
     free_arena(m);
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
-    cudaFree(m->d_prof); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx);
+    cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
@@ -473,11 +475,9 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
 // persistent decode kernel: host side
 // ------------------------------------------------------------------------------------------
 template <int FMT> static const void * mega_fn_dk(int dk) {
-    switch (dk) {
+    switch (dk) {   // head dims the persistent kernel is instantiated for; others use the per-op kernels
         case 16:  return (const void *) k_mega<FMT, 16>;
-        case 32:  return (const void *) k_mega<FMT, 32>;
         case 64:  return (const void *) k_mega<FMT, 64>;
-        case 128: return (const void *) k_mega<FMT, 128>;
     }
     return nullptr;
 }
@@ -546,20 +546,23 @@ static int mega_setup(bgpt_model * m) {
     m->mega_grid = prop.multiProcessorCount;
     const char * eg = getenv("BGPT_MEGA_GRID");
     if (eg && atoi(eg) > 0 && atoi(eg) <= prop.multiProcessorCount * occ) m->mega_grid = atoi(eg);
-    CK(cudaMalloc(&m->d_bar, 512)); CK(cudaMemset(m->d_bar, 0, 512));
-    {   // attention column split: largest divisor of d_kv that keeps >= 8 columns per CTA and fits the grid
-        int parts = 1;
-        for (int c = 1; c <= dk; c++) if (dk % c == 0 && dk / c >= 8 && m->n_head * c <= m->mega_grid) parts = c;
-        p.attn_parts = parts;
-    }
+    CK(cudaMalloc(&m->d_bar, 1024 * sizeof(unsigned long long))); CK(cudaMemset(m->d_bar, 0, 1024 * sizeof(unsigned long long)));
+    if (m->mega_grid > 1024) m->mega_grid = 1024;
+    // attention split: 32 output columns per CTA when d_kv allows it -- then each CTA owns exactly one
+    // 32-element activation block of out_proj's input and can quantise it itself
+    p.attn_parts = 1; p.att_prequant = 0;
+    if (dk % 32 == 0 && m->n_head * (dk / 32) <= m->mega_grid) { p.attn_parts = dk / 32; p.att_prequant = 1; }
+    CK(cudaMalloc(&m->d_rec_att, m->A_d.bytes)); CK(cudaMemset(m->d_rec_att, 0, m->A_d.bytes));
+    CK(cudaMalloc(&m->d_rec_hff, m->A_ff.bytes)); CK(cudaMemset(m->d_rec_hff, 0, m->A_ff.bytes));
+    p.rec_att = m->d_rec_att; p.rec_hff = m->d_rec_hff;
     p.prof = nullptr;
     if (getenv("BGPT_MEGA_PROF")) {
-        m->prof_n = ((m->n_layer + 1) * 5) * 3;
+        m->prof_n = ((m->n_layer + 1) * 5) * 6;
         CK(cudaMalloc(&m->d_prof, m->prof_n * sizeof(long long))); CK(cudaMemset(m->d_prof, 0, m->prof_n * sizeof(long long)));
         p.prof = m->d_prof;
     }
     CK(cudaMalloc(&m->d_cand_val, 1024 * sizeof(float))); CK(cudaMalloc(&m->d_cand_idx, 1024 * sizeof(int)));
-    p.bar = m->d_bar; p.cand_val = m->d_cand_val; p.cand_idx = m->d_cand_idx; p.n_cand = m->mega_grid;
+    p.flags = m->d_bar; p.cand_val = m->d_cand_val; p.cand_idx = m->d_cand_idx; p.n_cand = m->mega_grid;
     m->bar_epoch = 0;
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
@@ -576,7 +579,7 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
     p.kcache = m->kcache; p.vcache = m->vcache;
     p.x = m->x; p.x1 = m->x1; p.q = m->q; p.att = m->att; p.hff = m->hff; p.logits = m->logits;
     p.tok = d_tok; p.use_cand = use_cand; p.idlog = m->d_idlog; p.log_slot = log_slot; p.n_past = n_past;
-    p.bar_base = m->bar_epoch;
+    p.epoch0 = m->bar_epoch;
     m->bar_epoch += (unsigned long long) 5 * m->n_layer * m->mega_grid;
     void * args[] = { &p };
     const void * fn = mega_fn(m->wtype, m->d_model / m->n_head);
@@ -852,5 +855,35 @@ extern "C" int bgpt_cuda_op_dequantize(int type, const void * w, float * y, int 
     k_dequant_rows<<<rows, 256>>>(dw.as<uint8_t>(), type, k, dy.as<float>());
     CK(cudaGetLastError());
     CK(cudaMemcpy(y, dy.p, (size_t) rows * k * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+// debug: microseconds per grid barrier for variant `v` (bgpt_barbench.cuh); with_load adds one
+// dependent L2 load after each barrier
+extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, float * us_per_barrier) {
+    RET(need_device());
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    const int grid = prop.multiProcessorCount;
+    DevBuf w, sink, chase;
+    RET(w.alloc(4096 * 8)); RET(sink.alloc(grid * 4)); RET(chase.alloc(1024 * 4));
+    CK(cudaMemset(w.p, 0, 4096 * 8)); CK(cudaMemset(chase.p, 0, 1024 * 4));
+    const void * fns[7] = { (const void *) k_barbench<0>, (const void *) k_barbench<1>, (const void *) k_barbench<2>, (const void *) k_barbench<3>,
+                            (const void *) k_barbench<4>, (const void *) k_barbench<5>, (const void *) k_barbench<6> };
+    if (v < 0 || v > 6) return fail(BGPT_E_ARG, "barrier_bench: variant 0..6");
+    unsigned long long * wp = w.as<unsigned long long>(); float * sp = sink.as<float>(); const float * cp = with_load ? chase.as<float>() : nullptr;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaMemset(w.p, 0, 4096 * 8));
+        void * args[] = { &wp, &iters, &sp, &cp };
+        CK(cudaEventRecord(e0));
+        CK(cudaLaunchCooperativeKernel(fns[v], dim3(grid), dim3(512), args, 0, 0));
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *us_per_barrier = best * 1000.f / iters;
     return BGPT_OK;
 }

@@ -114,6 +114,9 @@ int bgpt_cuda_get_decode_path(const bgpt_model * m);
 /* debug (env BGPT_MEGA_PROF=1 at load): per-phase clock64 stamps of CTA 0 of the last
  * persistent-kernel launch; returns the number of entries copied (0 when profiling is off). */
 int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);
+/* debug: microseconds per grid-wide barrier for the candidate implementations in
+ * csrc/bgpt_barbench.cuh (one CTA per SM, `iters` back-to-back barriers). */
+int bgpt_cuda_debug_barrier_bench(int variant, int iters, int with_load, float * us_per_barrier);
 
 /* multi-stream state: `n_streams` independent sequences, each with its own KV cache
  * (SURVEY 8(d) config 4).  Stream 0 always exists. */

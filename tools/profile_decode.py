@@ -36,5 +36,9 @@ if prof is not None:
         body = (P[:, i, 2] - P[:, i, 1]).mean() if i != 1 else (P[:, i, 2] - P[:, i, 0]).mean()
         bar = (nxt[:, i] - P[:, i, 2]).mean()
         print(f"  {nme:10s} {pro:9.0f} {body:9.0f} {bar:9.0f} {pro + body + bar:9.0f}")
+    print("  LN0 prologue split (cycles): prefetch-issue %.0f | x load %.0f | LayerNorm %.0f | quantise %.0f" % (
+        (P[1:, 0, 5] - P[1:, 0, 0]).mean(), (P[1:, 0, 3] - P[1:, 0, 5]).mean(), (P[:, 0, 4] - P[:, 0, 3]).mean(), (P[:, 0, 1] - P[:, 0, 4]).mean()))
+    print("  LN1 prologue split (cycles): x1 load %.0f | LayerNorm %.0f | quantise %.0f" % (
+        (P[:, 3, 3] - P[:, 3, 0]).mean(), (P[:, 3, 4] - P[:, 3, 3]).mean(), (P[:, 3, 1] - P[:, 3, 4]).mean()))
     print(f"  layer total {(nxt[:, 4] - P[:, 0, 0]).mean():9.0f} cycles;  lm_head: prologue {prof[L,0,1]-prof[L,0,0]} matmul {prof[L,0,2]-prof[L,0,1]}; whole kernel {prof[L,0,2]-prof[0,0,0]}")
 M.close()
