@@ -278,15 +278,27 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the whole decode step (every kernel of a token streams weights once)
+    # ---- roofline of the dominant kernel: k_mega, the persistent kernel that IS the decode step
+    # (one launch per token).  achieved = algorithmic bytes per launch / CUDA-event duration per
+    # launch, both averaged over the seq launches of a step (n_past 0..seq-1).
     pk, pk_src = peaks()
     total_bytes = sum(bytes_per_token(args.ftype, p) for p in range(seq))
     step_ms = ms_total / args.steps
     achieved = total_bytes / (step_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "whole decode step (all kernels of one token, mean over n_past 0..seq-1)",
+    traffic = None
+    try:   # dram__bytes_read+write of one k_mega launch from the committed ncu capture (profiles/)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_mega_ncu_summary.json")))
+        if prof.get("ftype") == args.ftype:
+            traffic = {"bytes_per_launch": prof["dram_bytes_per_launch"], "at_n_past": prof["n_past"],
+                       "algorithmic_bytes_at_that_n_past": bytes_per_token(args.ftype, prof["n_past"]), "source": prof["source"]}
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": f"k_mega<{args.ftype}> (persistent decode kernel, 1 launch per token; mean over n_past 0..{seq - 1})",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None,
-                "algorithmic_bytes_per_token_mean": total_bytes / seq}
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                "algorithmic_bytes_per_launch_mean": total_bytes / seq,
+                "us_per_launch_mean": step_ms * 1e3 / seq,
+                "note": "latency-bound: 5 grid barriers + ~25 dependent L2 round trips per layer (DESIGN.md 4.2)"}
 
     cpu = None
     if not args.no_cpu_baseline:

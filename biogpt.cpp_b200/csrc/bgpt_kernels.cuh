@@ -169,7 +169,10 @@ __device__ __forceinline__ void bg_ln_row(float * srow, int K, const float * __r
     double s = 0.0;
     for (int c = tid; c < K; c += blockDim.x) s += (double) srow[c];
     s = bg_block_sum_f64(s, sd);
-    const float mean = (float) (s / K);
+    // s / K: for K a power of two the product with the exact reciprocal is the same double
+    const bool kpow2 = (K & (K - 1)) == 0;
+    const double invK = 1.0 / (double) K;
+    const float mean = (float) (kpow2 ? s * invK : s / K);
     double s2 = 0.0;
     for (int c = tid; c < K; c += blockDim.x) {
         const float v = __fsub_rn(srow[c], mean);
@@ -177,13 +180,41 @@ __device__ __forceinline__ void bg_ln_row(float * srow, int K, const float * __r
         s2 += (double) __fmul_rn(v, v);
     }
     s2 = bg_block_sum_f64(s2, sd);
-    const float variance = (float) (s2 / K);
+    const float variance = (float) (kpow2 ? s2 * invK : s2 / K);
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
     for (int c = tid; c < K; c += blockDim.x) {
         float y = __fmul_rn(srow[c], scale);
         if (lnw) y = __fmul_rn(lnw[c], y);
         if (lnb) y = __fadd_rn(y, lnb[c]);
         srow[c] = y;
+    }
+    __syncthreads();
+}
+
+// Same LayerNorm for a CTA of NT threads with K <= EPT*NT: the affine parameters of this thread's
+// elements (c = tid + i*NT) were loaded into registers earlier, so no global load sits between
+// the reductions and the output.
+template <int NT, int EPT>
+__device__ __forceinline__ void bg_ln_row_pre(float * srow, int K, const float (&lw)[EPT], const float (&lb)[EPT], float eps, double * sd) {
+    const int tid = threadIdx.x;
+    float xv[EPT];
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < EPT; i++) { const int c = tid + i * NT; xv[i] = c < K ? srow[c] : 0.0f; if (c < K) s += (double) xv[i]; }
+    s = bg_block_sum_f64(s, sd);
+    const bool kpow2 = (K & (K - 1)) == 0;
+    const double invK = 1.0 / (double) K;
+    const float mean = (float) (kpow2 ? s * invK : s / K);
+    double s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < EPT; i++) { const int c = tid + i * NT; xv[i] = __fsub_rn(xv[i], mean); if (c < K) s2 += (double) __fmul_rn(xv[i], xv[i]); }
+    s2 = bg_block_sum_f64(s2, sd);
+    const float variance = (float) (kpow2 ? s2 * invK : s2 / K);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
+#pragma unroll
+    for (int i = 0; i < EPT; i++) {
+        const int c = tid + i * NT;
+        if (c < K) srow[c] = __fadd_rn(__fmul_rn(lw[i], __fmul_rn(xv[i], scale)), lb[i]);
     }
     __syncthreads();
 }
@@ -214,53 +245,42 @@ __device__ __forceinline__ void bg_row_to_record(const float * srow, int K, int 
         }
         return;
     }
-    // quantised records: one warp per 32-element block
+    // quantised records: 8 threads per 32-element block, thread l owns elements 4l..4l+3 (= one
+    // 32-bit word of the record); the block maximum needs 3 shuffle levels
     const int nb = K >> 5, nbp = ((nb + 3) >> 2) << 2;
-    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
     uint32_t * aq = (uint32_t *) rec;
     int32_t  * an = (int32_t *) (rec + off_n);
     float    * ad = (float *) (rec + off_d);
     float    * as = (float *) (rec + off_s);
-    for (int b = warp; b < nbp; b += nw) {
+    for (int idx = tid; idx < nbp * 8; idx += blockDim.x) {      // nbp*8 is a multiple of 32: warps stay whole
+        const int b = idx >> 3, l = idx & 7;
         const int g = b >> 2, i = b & 3;
-        if (b >= nb) {   // padding block: all-zero codes and scales
-            if ((lane & 3) == 0) { aq[(g * 8 + (lane >> 2)) * 4 + i] = 0u; an[(g * 8 + (lane >> 2)) * 4 + i] = 0; }
-            if (lane == 0) { ad[b] = 0.0f; as[b] = 0.0f; }
-            continue;
-        }
-        const float v = srow[b * 32 + lane];
-        float amax = fabsf(v);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, o));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < nb) v = *(const float4 *) (srow + b * 32 + 4 * l);
+        float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+        amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 2));
+        amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 4));
         const float d  = __fdiv_rn(amax, 127.0f);
         const float id = (amax != 0.0f) ? __fdiv_rn(127.0f, amax) : 0.0f;
-        const int q = __float2int_rn(__fmul_rn(v, id));
-        const uint32_t byte = (uint32_t) q & 0xFFu;
-        uint32_t w = byte;
-        w |= __shfl_down_sync(FULLMASK, byte, 1) << 8;
-        w |= __shfl_down_sync(FULLMASK, byte, 2) << 16;
-        w |= __shfl_down_sync(FULLMASK, byte, 3) << 24;
-        int s4 = q;
-        s4 += __shfl_down_sync(FULLMASK, q, 1);
-        s4 += __shfl_down_sync(FULLMASK, q, 2);
-        s4 += __shfl_down_sync(FULLMASK, q, 3);
-        int stot = q;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) stot += __shfl_xor_sync(FULLMASK, stot, o);
-        if ((lane & 3) == 0) {
-            const int l = lane >> 2;
-            aq[(g * 8 + l) * 4 + i] = w;
-            an[(g * 8 + l) * 4 + i] = -code_off * s4;
-        }
-        if (lane == 0) {
-            if (kind == ACT_Q8_0) { ad[b] = bg_h2f(bg_f2h(d)); as[b] = 0.0f; }
-            else                  { ad[b] = d; as[b] = __fmul_rn(d, (float) stot); }
+        const int q0 = __float2int_rn(__fmul_rn(v.x, id)), q1 = __float2int_rn(__fmul_rn(v.y, id));
+        const int q2 = __float2int_rn(__fmul_rn(v.z, id)), q3 = __float2int_rn(__fmul_rn(v.w, id));
+        const int s4 = q0 + q1 + q2 + q3;
+        aq[(g * 8 + l) * 4 + i] = ((uint32_t) q0 & 0xFFu) | (((uint32_t) q1 & 0xFFu) << 8) | (((uint32_t) q2 & 0xFFu) << 16) | (((uint32_t) q3 & 0xFFu) << 24);
+        an[(g * 8 + l) * 4 + i] = -code_off * s4;
+        if (kind == ACT_Q8_0) { if (l == 0) { ad[b] = bg_h2f(bg_f2h(d)); as[b] = 0.0f; } }
+        else {
+            int stot = s4;
+            stot += __shfl_xor_sync(FULLMASK, stot, 1);
+            stot += __shfl_xor_sync(FULLMASK, stot, 2);
+            stot += __shfl_xor_sync(FULLMASK, stot, 4);
+            if (l == 0) { ad[b] = d; as[b] = __fmul_rn(d, (float) stot); }
         }
     }
 }
 
 __global__ void __launch_bounds__(256) k_act(ActArgs a) {
-    extern __shared__ float srow[];
+    extern __shared__ __align__(16) float srow[];
     __shared__ double sd[32];
     const int row = blockIdx.x, tid = threadIdx.x, K = a.K;
     const float * in = a.in + (size_t) row * a.ld_in;

@@ -93,14 +93,21 @@ __device__ __forceinline__ void mega_barrier_wait(unsigned long long * ctr, unsi
 }
 
 // L2 prefetch of a contiguous byte range (16-byte aligned): issue the HBM read now
-__device__ __forceinline__ void mega_prefetch_l2(const void * ptr, size_t bytes) {
-    const size_t CH = 8192;
-    const size_t n = (bytes + CH - 1) / CH;
-    for (size_t i = threadIdx.x; i < n; i += MEGA_NT) {
-        const size_t off = i * CH;
-        const unsigned sz = (unsigned) ((bytes - off) < CH ? (bytes - off) : CH) & ~15u;
+__device__ __forceinline__ void mega_prefetch_l2(const void * ptr, size_t bytes64) {
+    const unsigned bytes = (unsigned) bytes64;                 // slices are far below 4 GB
+    const unsigned n = (bytes + 8191u) >> 13;                  // 8 KB chunks spread over the threads
+    for (unsigned i = threadIdx.x; i < n; i += MEGA_NT) {
+        const unsigned off = i << 13;
+        const unsigned sz = ((bytes - off) < 8192u ? (bytes - off) : 8192u) & ~15u;
         if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"((const uint8_t *) ptr + off), "r"(sz) : "memory");
     }
+}
+
+// L2 prefetch by 128-byte lines through the LSU (cheap to issue, unlike the bulk form): lines
+// [0, bytes/128) of `ptr`, thread t takes lines t, t+MEGA_NT, ...
+__device__ __forceinline__ void mega_prefetch_lines(const void * ptr, unsigned bytes) {
+    for (unsigned off = threadIdx.x * 128u; off < bytes; off += MEGA_NT * 128u)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"((const uint8_t *) ptr + off));
 }
 
 // rows [r0, r1) of an M-row phase owned by this CTA: balanced contiguous runs of `tile`-row tiles
@@ -232,21 +239,21 @@ __device__ __forceinline__ void mega_compute_unit(const WUnit<FMT> & W, const MM
     }
 }
 
-// phase B: the 8 running sums of each of the rt rows, then the row epilogue.
-// pre(r) loads what the epilogue needs (bias, residual) BEFORE the chain so the latencies overlap.
-template <int FMT, class PreF, class FinF>
+// phase B: the 8 running sums of each of the rt rows, then the row epilogue.  The owner thread
+// of row (c >> 3) is thread c = 8*row: it fetched the epilogue's inputs (bias, residual) before
+// phase A, so their latency is hidden behind the whole tile.
+template <int FMT, class FinF>
 __device__ __forceinline__ void mega_phase_b(const MMDesc & D, int t0, int rt, const uint8_t * s_act,
-                                             const float * s_p, const float * s_s, const float * s_m, PreF pre, FinF fin) {
+                                             const float * s_p, const float * s_s, const float * s_m, float2 pv0, FinF fin) {
     constexpr bool HASM = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
     const int nbp = D.G * 4, PS = nbp + 4;
-    for (int c0 = (threadIdx.x >> 5) << 5; c0 < rt * 8; c0 += MEGA_NT) {
+    int it = 0;
+    for (int c0 = (threadIdx.x >> 5) << 5; c0 < rt * 8; c0 += MEGA_NT, it++) {
         const int c = c0 + (threadIdx.x & 31);
         const bool valid = c < rt * 8;
         const int cc = valid ? c : rt * 8 - 1;
         const int row = cc >> 3, l = cc & 7;
         const bool owner = valid && l == 0;
-        float2 pv0 = make_float2(0.f, 0.f);
-        if (owner) pv0 = pre(t0 + row);
         const float * pp = s_p + (size_t) cc * PS;
         const float * ss = s_s + (size_t) row * nbp;
         float acc = 0.0f, summ = 0.0f;
@@ -282,6 +289,9 @@ __device__ __forceinline__ void mega_mm_run_q(const MMDesc & D, WRegs<FMT> & cur
         const bool has_next = t0 + D.RT < D.r1;
         WRegs<FMT> nxt;
         if (has_next) mega_load_units<FMT>(nxt, D, t0 + D.RT, (D.r1 - t0 - D.RT) < D.RT ? (D.r1 - t0 - D.RT) : D.RT);
+        // epilogue inputs of the row this thread will finish (rt*8 <= MEGA_NT: one owner row per thread)
+        float2 pv0 = make_float2(0.f, 0.f);
+        if ((int) threadIdx.x < rt * 8 && (threadIdx.x & 7) == 0) pv0 = pre(t0 + (int) (threadIdx.x >> 3));
 #pragma unroll
         for (int k = 0; k < MEGA_UMAX; k++) {
             const int u = threadIdx.x + k * MEGA_NT;
@@ -292,7 +302,7 @@ __device__ __forceinline__ void mega_mm_run_q(const MMDesc & D, WRegs<FMT> & cur
             mega_compute_unit<FMT>(W, D, u, s_act, s_p, s_s, s_m);
         }
         __syncthreads();
-        mega_phase_b<FMT>(D, t0, rt, s_act, s_p, s_s, s_m, pre, fin);
+        mega_phase_b<FMT>(D, t0, rt, s_act, s_p, s_s, s_m, pv0, fin);
         __syncthreads();
         if (has_next) cur = nxt;
     }
@@ -329,33 +339,28 @@ __device__ __forceinline__ void mega_mm_run_f16(const MMDesc & D, const uint8_t 
     __syncthreads();
 }
 
-// one 32-element block of f32 values (lane = element) -> the quantised record piece of block b.
-// Same arithmetic as bg_row_to_record; executed by one full warp.
-__device__ __forceinline__ void mega_quant_block(float v, int b, int wtype, uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
-    const int lane = threadIdx.x & 31;
+// one 32-element block of f32 values in shared memory -> the quantised record piece of block b.
+// Same arithmetic as bg_row_to_record; executed by one full warp (lanes 0..7 own 4 elements each).
+__device__ __forceinline__ void mega_quant_block(const float * s_v, int b, int wtype, uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
+    const int lane = threadIdx.x & 31, l = lane & 7;
     const int kind = bg_act_kind(wtype);
     const int g = b >> 2, i = b & 3;
-    float amax = fabsf(v);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, o));
+    const float4 v = *(const float4 *) (s_v + 4 * l);
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 2));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 4));
     const float d  = __fdiv_rn(amax, 127.0f);
     const float id = (amax != 0.0f) ? __fdiv_rn(127.0f, amax) : 0.0f;
-    const int q = __float2int_rn(__fmul_rn(v, id));
-    const uint32_t byte = (uint32_t) q & 0xFFu;
-    uint32_t w = byte;
-    w |= __shfl_down_sync(FULLMASK, byte, 1) << 8;
-    w |= __shfl_down_sync(FULLMASK, byte, 2) << 16;
-    w |= __shfl_down_sync(FULLMASK, byte, 3) << 24;
-    int s4 = q;
-    s4 += __shfl_down_sync(FULLMASK, q, 1);
-    s4 += __shfl_down_sync(FULLMASK, q, 2);
-    s4 += __shfl_down_sync(FULLMASK, q, 3);
-    int stot = q;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) stot += __shfl_xor_sync(FULLMASK, stot, o);
-    if ((lane & 3) == 0) {
-        const int l = lane >> 2;
-        ((uint32_t *) rec)[(g * 8 + l) * 4 + i] = w;
+    const int q0 = __float2int_rn(__fmul_rn(v.x, id)), q1 = __float2int_rn(__fmul_rn(v.y, id));
+    const int q2 = __float2int_rn(__fmul_rn(v.z, id)), q3 = __float2int_rn(__fmul_rn(v.w, id));
+    const int s4 = q0 + q1 + q2 + q3;
+    int stot = s4;
+    stot += __shfl_xor_sync(FULLMASK, stot, 1);
+    stot += __shfl_xor_sync(FULLMASK, stot, 2);
+    stot += __shfl_xor_sync(FULLMASK, stot, 4);
+    if (lane < 8) {
+        ((uint32_t *) rec)[(g * 8 + l) * 4 + i] = ((uint32_t) q0 & 0xFFu) | (((uint32_t) q1 & 0xFFu) << 8) | (((uint32_t) q2 & 0xFFu) << 16) | (((uint32_t) q3 & 0xFFu) << 24);
         ((int32_t *) (rec + off_n))[(g * 8 + l) * 4 + i] = -code_off * s4;
     }
     if (lane == 0) {
@@ -385,24 +390,62 @@ __device__ __forceinline__ void mega_attention_cols(const float * s_q, const flo
     constexpr int NP = DK & ~31;
     constexpr int NV = NP + ((DK - NP) & ~3);
     constexpr int NQ = NP > 0 ? NP / 32 : 1;
-    constexpr int U = 16;              // rows in flight per warp
-    float qreg[NQ];
+    if (NP > 0 && NP == DK) {
+        // 32 rows per warp pass (row u -> position tb + u*NWARP).  Each lane first forms its
+        // running-sum lane of all 32 dots, then the 32 reduce trees (xor 16, 8, 4, 1, 2 -- the
+        // GGML_F32x8_REDUCE order) run as ONE transposing butterfly: at every level a lane keeps
+        // half of its rows and trades the other half, 31 shuffles per 32 rows instead of 160,
+        // and lane L ends up owning the finished dot of one row.
+        float qreg[NQ];
 #pragma unroll
-    for (int i = 0; i < NP / 32; i++) qreg[i] = s_q[i * 32 + lane];
-    for (int t0 = warp * U; t0 < T; t0 += NWARP * U) {
-        float kv[U][NQ];
+        for (int i = 0; i < NQ; i++) qreg[i] = s_q[i * 32 + lane];
+        for (int tb = warp; tb < T; tb += NWARP * 32) {
+            float s[32];
 #pragma unroll
-        for (int u = 0; u < U; u++)
+            for (int half = 0; half < 2; half++) {
+                float kv[16][NQ];
 #pragma unroll
-            for (int i = 0; i < NP / 32; i++)
-                kv[u][i] = (t0 + u < T) ? __ldcg(Kb + (size_t) (t0 + u) * ldkv + i * 32 + lane) : 0.0f;
+                for (int u = 0; u < 16; u++)
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int t = t0 + u;
-            if (t >= T) break;                      // warp-uniform
+                    for (int i = 0; i < NQ; i++) {
+                        const int t = tb + (half * 16 + u) * NWARP;
+                        kv[u][i] = (t < T) ? __ldcg(Kb + (size_t) t * ldkv + i * 32 + lane) : 0.0f;
+                    }
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    float a = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < NQ; i++) a = fmaf(kv[u][i], qreg[i], a);
+                    s[half * 16 + u] = a;
+                }
+            }
+            float a16[16], a8[8], a4[4], a2[2];
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+            for (int i = 0; i < 16; i++) { const float mine = b4 ? s[16 + i] : s[i], send = b4 ? s[i] : s[16 + i]; a16[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 16)); }
+#pragma unroll
+            for (int i = 0; i < 8; i++)  { const float mine = b3 ? a16[8 + i] : a16[i], send = b3 ? a16[i] : a16[8 + i]; a8[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 8)); }
+#pragma unroll
+            for (int i = 0; i < 4; i++)  { const float mine = b2 ? a8[4 + i] : a8[i], send = b2 ? a8[i] : a8[4 + i]; a4[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 4)); }
+#pragma unroll
+            for (int i = 0; i < 2; i++)  { const float mine = b0 ? a4[2 + i] : a4[i], send = b0 ? a4[i] : a4[2 + i]; a2[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 1)); }
+            const float mine = b1 ? a2[1] : a2[0], send = b1 ? a2[0] : a2[1];
+            const float dot = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 2));
+            // row owned by this lane: bit4..bit2 from the lane, then bit1 <- lane bit0, bit0 <- lane bit1
+            const int u = (lane & 28) | ((lane & 1) << 1) | ((lane & 2) >> 1);
+            const int t = tb + u * NWARP;
+            if (t < T) sc[t] = dot;
+        }
+    } else {
+        // generic head sizes (d_kv not a multiple of 32): one row at a time, scalar tail on lane 0
+        float qreg[NQ];
+#pragma unroll
+        for (int i = 0; i < NP / 32; i++) qreg[i] = s_q[i * 32 + lane];
+        for (int t = warp; t < T; t += NWARP) {
+            const float * kr = Kb + (size_t) t * ldkv;
             float s = 0.0f;
 #pragma unroll
-            for (int i = 0; i < NP / 32; i++) s = fmaf(kv[u][i], qreg[i], s);
+            for (int i = 0; i < NP / 32; i++) s = fmaf(__ldcg(kr + i * 32 + lane), qreg[i], s);
             if (NP > 0) {
                 s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 16));
                 s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 8));
@@ -411,7 +454,6 @@ __device__ __forceinline__ void mega_attention_cols(const float * s_q, const flo
                 s = __fadd_rn(s, __shfl_xor_sync(FULLMASK, s, 2));
             }
             if (lane == 0) {
-                const float * kr = Kb + (size_t) t * ldkv;
 #pragma unroll
                 for (int i = NP; i < NV; i++) s = __fadd_rn(s, __fmul_rn(__ldcg(kr + i), s_q[i]));
 #pragma unroll
@@ -437,27 +479,35 @@ __device__ __forceinline__ void mega_attention_cols(const float * s_q, const flo
     // ---- V: unit (r, col), r = t % 32
     const int np = T & ~31;
     for (int i = tid; i < (T - np) * ncol; i += MEGA_NT) tailv[i] = __ldcg(Vb + (size_t) (np + i / ncol) * ldkv + c0 + (i % ncol));
-    const int csh = (ncol & (ncol - 1)) == 0 ? 31 - __clz(ncol) : -1;
-    for (int u = tid; u < 32 * ncol; u += MEGA_NT) {
-        const int col = csh >= 0 ? (u & (ncol - 1)) : (u % ncol), r = csh >= 0 ? (u >> csh) : (u / ncol);
-        const float * vp = Vb + (size_t) r * ldkv + c0 + col;
-        float acc = 0.0f;
-        int s0 = 0;
-        for (; s0 + 8 * 32 <= np; s0 += 8 * 32) {
-            float v[8];
+    if ((ncol & 3) == 0 && (Tmax & 3) == 0 && (c0 & 3) == 0 && (ldkv & 3) == 0) {
+        // unit (r, 4 columns): one float4 load per step, 16 steps in flight -> one round trip per 512 positions
+        const int ncg = ncol >> 2;
+        for (int u = tid; u < 32 * ncg; u += MEGA_NT) {
+            const int cg = u % ncg, r = u / ncg;
+            const float * vp = Vb + (size_t) r * ldkv + c0 + 4 * cg;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s0 = 0; s0 < np; s0 += 16 * 32) {
+                float4 v[16];
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = __ldcg(vp + (size_t) (s0 + 32 * k) * ldkv);
+                for (int k = 0; k < 16; k++)
+                    v[k] = (s0 + 32 * k < np) ? __ldcg((const float4 *) (vp + (size_t) (s0 + 32 * k) * ldkv)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc = fmaf(v[k], sc[s0 + 32 * k + r], acc);
+                for (int k = 0; k < 16; k++) if (s0 + 32 * k < np) {
+                    const float pw = sc[s0 + 32 * k + r];
+                    acc.x = fmaf(v[k].x, pw, acc.x); acc.y = fmaf(v[k].y, pw, acc.y);
+                    acc.z = fmaf(v[k].z, pw, acc.z); acc.w = fmaf(v[k].w, pw, acc.w);
+                }
+            }
+            *(float4 *) (red + r * ncol + 4 * cg) = acc;
         }
-        {   // remaining < 8 steps, still issued together
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (s0 + 32 * k < np) ? __ldcg(vp + (size_t) (s0 + 32 * k) * ldkv) : 0.0f;
-#pragma unroll
-            for (int k = 0; k < 8; k++) if (s0 + 32 * k < np) acc = fmaf(v[k], sc[s0 + 32 * k + r], acc);
+    } else {
+        for (int u = tid; u < 32 * ncol; u += MEGA_NT) {
+            const int col = u % ncol, r = u / ncol;
+            const float * vp = Vb + (size_t) r * ldkv + c0 + col;
+            float acc = 0.0f;
+            for (int s0 = 0; s0 < np; s0 += 32) acc = fmaf(__ldcg(vp + (size_t) s0 * ldkv), sc[s0 + r], acc);
+            red[r * ncol + col] = acc;
         }
-        red[r * ncol + col] = acc;
     }
     __syncthreads();
     if (tid < ncol) {
@@ -496,11 +546,15 @@ __device__ __forceinline__ void mega_prefetch_layer(const MegaParams & p, const 
         mega_prefetch_l2(Ln.fc2_w + (size_t) R.o0 * p.stride_f, (size_t) (R.o1 - R.o0) * p.stride_f);
         mega_prefetch_l2(Ln.fc1_w + (size_t) R.f10 * p.stride_d, (size_t) (R.f11 - R.f10) * p.stride_d);
     }
-    if (blockIdx.x == gridDim.x - 1) {      // 53 KB of vectors per layer: one CTA asks for all of them
-        mega_prefetch_l2(Ln.ln0_w, (size_t) d * 4); mega_prefetch_l2(Ln.ln0_b, (size_t) d * 4);
-        mega_prefetch_l2(Ln.ln1_w, (size_t) d * 4); mega_prefetch_l2(Ln.ln1_b, (size_t) d * 4);
-        mega_prefetch_l2(Ln.q_b, (size_t) d * 4); mega_prefetch_l2(Ln.k_b, (size_t) d * 4); mega_prefetch_l2(Ln.v_b, (size_t) d * 4);
-        mega_prefetch_l2(Ln.o_b, (size_t) d * 4); mega_prefetch_l2(Ln.fc2_b, (size_t) d * 4); mega_prefetch_l2(Ln.fc1_b, (size_t) ff * 4);
+    // 53 KB of f32 vectors per layer, each asked for by one CTA
+    const unsigned db = (unsigned) d * 4u, fb = (unsigned) ff * 4u;
+    switch ((gridDim.x - 1 - blockIdx.x)) {
+        case 0: mega_prefetch_lines(Ln.ln0_w, db); mega_prefetch_lines(Ln.ln0_b, db); break;
+        case 1: mega_prefetch_lines(Ln.ln1_w, db); mega_prefetch_lines(Ln.ln1_b, db); break;
+        case 2: mega_prefetch_lines(Ln.q_b, db); mega_prefetch_lines(Ln.k_b, db); mega_prefetch_lines(Ln.v_b, db); break;
+        case 3: mega_prefetch_lines(Ln.o_b, db); mega_prefetch_lines(Ln.fc2_b, db); break;
+        case 4: mega_prefetch_lines(Ln.fc1_b, fb); break;
+        default: break;
     }
 }
 
@@ -509,7 +563,7 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ double sd[32];
     __shared__ float smx[32];
-    __shared__ float s_blk[128];
+    __shared__ __align__(16) float s_blk[128];
     __shared__ int s_tok;
     constexpr bool ISF16 = (FMT == BG_F16);
     float * s_row = (float *) (smem + p.sm_row);
@@ -529,6 +583,12 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
     mega_my_rows(p.n_vocab, 8, R.v0, R.v1);
     const int qkv0 = R.qkv0, qkv1 = R.qkv1, o0 = R.o0, o1 = R.o1, f10 = R.f10, f11 = R.f11, v0 = R.v0, v1 = R.v1;
 
+    const bool ln_fast = d <= 4 * MEGA_NT;     // LayerNorm parameters fit 4 registers per thread
+    float lw[4], lb[4];
+    auto load_ln = [&](const float * w, const float * b) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const int c = tid + i * MEGA_NT; lw[i] = (ln_fast && c < d) ? w[c] : 0.f; lb[i] = (ln_fast && c < d) ? b[c] : 0.f; }
+    };
     WRegs<FMT> wr;     // weights of the NEXT matmul phase, loaded one phase ahead
     {   // first phase of the first layer
         const MegaLayer L0 = p.layers[0];
@@ -583,19 +643,25 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
         PROF(0, 0);
         if (l + 1 < p.n_layer) mega_prefetch_layer(p, p.layers[l + 1], R, ISF16);
         else if (ISF16) mega_prefetch_l2(p.lm_head + (size_t) v0 * p.stride_d, (size_t) (v1 - v0) * p.stride_d);
-        {   // K/V rows this CTA will read in P2: start them towards L2 now (one 4*DK-byte row slice per thread)
+        {   // K/V rows this CTA will read in P2: start them towards L2 now (128-byte lines of its head slice)
+            constexpr int LPR = (DK * 4 + 127) / 128;          // lines per row slice
             for (int w = blockIdx.x; w < p.n_head * p.attn_parts; w += gridDim.x) {
                 const int h = w / p.attn_parts;
-                for (int t = tid; t < 2 * (T - 1); t += MEGA_NT) {
-                    const float * src = (t < T - 1 ? kc + (size_t) t * d : vc + (size_t) (t - (T - 1)) * d) + (size_t) h * DK;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"((unsigned) (DK * 4)) : "memory");
+                for (int t = tid; t < T - 1; t += MEGA_NT) {
+                    const float * ks = kc + (size_t) t * d + (size_t) h * DK, * vs = vc + (size_t) t * d + (size_t) h * DK;
+#pragma unroll
+                    for (int ln = 0; ln < LPR; ln++) {
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(ks + ln * 32));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(vs + ln * 32));
+                    }
                 }
             }
         }
+        load_ln(L.ln0_w, L.ln0_b);
         PROF(0, 5);
         if (l > 0) { for (int c = tid; c < d; c += MEGA_NT) s_row[c] = __ldcg(p.x + c); __syncthreads(); }
         PROF(0, 3);
-        bg_ln_row(s_row, d, L.ln0_w, L.ln0_b, p.eps, sd);
+        if (ln_fast) bg_ln_row_pre<MEGA_NT, 4>(s_row, d, lw, lb, p.eps, sd); else bg_ln_row(s_row, d, L.ln0_w, L.ln0_b, p.eps, sd);
         PROF(0, 4);
         bg_row_to_record(s_row, d, p.wtype, s_act, p.actb_d, p.offn_d, p.offdd_d, p.offs_d, p.code_off);
         __syncthreads();
@@ -629,7 +695,7 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
                 if (tid < 32) {
                     const int c = h * DK + c0 + tid;
                     if (ISF16) mega_f16_record_elem(s_blk[tid], c, p.rec_att);
-                    else mega_quant_block(s_blk[tid], c >> 5, p.wtype, p.rec_att, p.offn_d, p.offdd_d, p.offs_d, p.code_off);
+                    else mega_quant_block(s_blk, c >> 5, p.wtype, p.rec_att, p.offn_d, p.offdd_d, p.offs_d, p.code_off);
                 }
             } else if (tid < ncol) p.att[h * DK + c0 + tid] = s_blk[tid];
             __syncthreads();
@@ -662,10 +728,11 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
         mega_barrier_wait(p.flags, epoch);
         // ================= P4: LN1 + fc1 + bias + GELU (+ quantise own 32-row blocks) =================
         PROF(3, 0);
+        load_ln(L.ln1_w, L.ln1_b);
         for (int c = tid; c < d; c += MEGA_NT) s_row[c] = __ldcg(p.x1 + c);
         __syncthreads();
         PROF(3, 3);
-        bg_ln_row(s_row, d, L.ln1_w, L.ln1_b, p.eps, sd);
+        if (ln_fast) bg_ln_row_pre<MEGA_NT, 4>(s_row, d, lw, lb, p.eps, sd); else bg_ln_row(s_row, d, L.ln1_w, L.ln1_b, p.eps, sd);
         PROF(3, 4);
         bg_row_to_record(s_row, d, p.wtype, s_act, p.actb_d, p.offn_d, p.offdd_d, p.offs_d, p.code_off);
         __syncthreads();
@@ -678,10 +745,9 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
             else mega_mm_run_q<FMT>(D1, wr, s_act, s_p, s_s, s_m, pre, fin);
             // f11 - f10 is a multiple of 32: one warp per finished block
             for (int b = tid >> 5; b < (f11 - f10) >> 5; b += MEGA_NT / 32) {
-                const float v = s_h[b * 32 + (tid & 31)];
                 const int c = f10 + b * 32 + (tid & 31);
-                if (ISF16) mega_f16_record_elem(v, c, p.rec_hff);
-                else mega_quant_block(v, c >> 5, p.wtype, p.rec_hff, p.offn_f, p.offdd_f, p.offs_f, p.code_off);
+                if (ISF16) mega_f16_record_elem(s_h[b * 32 + (tid & 31)], c, p.rec_hff);
+                else mega_quant_block(s_h + b * 32, c >> 5, p.wtype, p.rec_hff, p.offn_f, p.offdd_f, p.offs_f, p.code_off);
             }
         }
         const MMDesc D2 = mega_mm_desc(p, L.fc2_w, L.fc2_w, L.fc2_w, d, o0, o1, true);
@@ -716,9 +782,10 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
     }
     // ================= final LayerNorm + lm_head =================
     { const int l = p.n_layer; PROF(0, 0); }
+    load_ln(p.lnf_w, p.lnf_b);
     for (int c = tid; c < d; c += MEGA_NT) s_row[c] = __ldcg(p.x + c);
     __syncthreads();
-    bg_ln_row(s_row, d, p.lnf_w, p.lnf_b, p.eps, sd);
+    if (ln_fast) bg_ln_row_pre<MEGA_NT, 4>(s_row, d, lw, lb, p.eps, sd); else bg_ln_row(s_row, d, p.lnf_w, p.lnf_b, p.eps, sd);
     bg_row_to_record(s_row, d, p.wtype, s_act, p.actb_d, p.offn_d, p.offdd_d, p.offs_d, p.code_off);
     __syncthreads();
     { const int l = p.n_layer; PROF(0, 1); }

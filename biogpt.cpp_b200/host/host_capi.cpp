@@ -1,0 +1,92 @@
+// host_capi.cpp -- extern "C" doors onto the C++ host API for the python tests (ctypes cannot
+// call functions that take std::string / std::vector).  Test plumbing only; the product entry
+// points are the C++ functions of biogpt.h.
+#include "biogpt.h"
+#include "mosestokenizer.h"
+
+#include <cstring>
+
+namespace {
+int join(const std::vector<std::string> & v, char * out, int cap) {
+    std::string s;
+    for (size_t i = 0; i < v.size(); i++) { if (i) s += '\n'; s += v[i]; }
+    if ((int) s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int) v.size();
+}
+std::vector<std::string> split_lines(const char * s) {
+    std::vector<std::string> v; std::string cur;
+    for (const char * p = s; *p; p++) { if (*p == '\n') { v.push_back(cur); cur.clear(); } else cur += *p; }
+    if (!cur.empty() || !v.empty()) v.push_back(cur);
+    return v;
+}
+struct Session { biogpt_model model; biogpt_vocab vocab; ggml_allocr * allocr = nullptr; ggml_backend_buffer_t buf = nullptr; std::vector<float> logits; };
+}
+
+extern "C" {
+
+int bgpt_host_moses_tokenize(const char * text, char * out, int cap) { return join(moses_tokenize(text, "en"), out, cap); }
+int bgpt_host_moses_detokenize(const char * tokens_nl, char * out, int cap) {
+    std::vector<std::string> v = split_lines(tokens_nl);
+    const std::string s = moses_detokenize(v, "en");
+    if ((int) s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int) s.size();
+}
+// merges: "left right" lines in priority order
+int bgpt_host_bpe(const char * word, const char * merges_nl, char * out, int cap) {
+    std::map<word_pair, int> ranks; int r = 0;
+    for (const std::string & line : split_lines(merges_nl)) {
+        const size_t sp = line.find(' ');
+        if (sp != std::string::npos) ranks[word_pair(line.substr(0, sp), line.substr(sp + 1))] = r++;
+    }
+    const std::string s = bpe(word, ranks);
+    if ((int) s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int) s.size();
+}
+int bgpt_host_sample(const float * logits, int n_vocab, int top_k, double top_p, double temp, uint32_t seed) {
+    biogpt_vocab vocab;
+    for (int i = 0; i < n_vocab; i++) vocab.id_to_token[i] = "";
+    std::mt19937 rng(seed);
+    return biogpt_sample_top_k_top_p(vocab, logits, top_k, top_p, temp, rng);
+}
+
+// the flow of examples/main/main.cpp:29-70: load, measure pass, allocator
+void * bgpt_host_open(const char * path, int n_batch) {
+    Session * s = new Session();
+    if (!biogpt_model_load(path, s->model, s->vocab, 0)) { delete s; return nullptr; }
+    ggml_allocr * m = ggml_allocr_new_measure(ggml_backend_get_alignment(s->model.backend));
+    const int n_tokens = std::min(s->model.hparams.n_positions, n_batch);
+    ggml_cgraph * gf = biogpt_graph(s->model, m, token_sequence(n_tokens, 0), s->model.hparams.n_positions - n_tokens);
+    const size_t mem = ggml_allocr_alloc_graph(m, gf);
+    ggml_allocr_free(m);
+    s->buf = ggml_backend_alloc_buffer(s->model.backend, mem);
+    s->allocr = ggml_allocr_new_from_buffer(s->buf);
+    return s;
+}
+int bgpt_host_n_vocab(void * h) { return ((Session *) h)->model.hparams.n_vocab; }
+int bgpt_host_eval(void * h, const int32_t * tokens, int n, int n_past, float * logits_out) {
+    Session * s = (Session *) h;
+    if (!biogpt_eval(s->model, token_sequence(tokens, tokens + n), s->logits, s->allocr, n_past, 4)) return 1;
+    memcpy(logits_out, s->logits.data(), s->logits.size() * sizeof(float));
+    return 0;
+}
+int bgpt_host_tokenize(void * h, const char * text, int32_t * out, int cap) {
+    Session * s = (Session *) h;
+    const token_sequence ids = gpt_tokenize(s->vocab, text, "en");
+    if ((int) ids.size() > cap) return -1;
+    for (size_t i = 0; i < ids.size(); i++) out[i] = ids[i];
+    return (int) ids.size();
+}
+void bgpt_host_close(void * h) {
+    Session * s = (Session *) h;
+    if (!s) return;
+    ggml_allocr_free(s->allocr);
+    ggml_free(s->model.ctx);
+    ggml_backend_buffer_free(s->model.buffer_w); ggml_backend_buffer_free(s->model.buffer_kv); ggml_backend_buffer_free(s->buf);
+    ggml_backend_free(s->model.backend);
+    delete s;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""The C++ host library (biogpt.cpp_b200/host): the reference's biogpt.h API on top of the C ABI.
+CPU tier: text rules, BPE, sampler draw, the quantize front end (the reference's UNMODIFIED
+quantize.cpp linked against our library) against the committed reference hashes.
+GPU tier: biogpt_model_load + biogpt_eval through the C++ API against the oracle."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FTYPES, ROOT, gf
+
+HOST = os.path.join(ROOT, "biogpt.cpp_b200", "host")
+LIB = os.path.join(HOST, "libbiogpt_b200.so")
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not os.path.exists(LIB):
+        subprocess.run(["make", "-C", ROOT, "product"], check=True, stdout=subprocess.DEVNULL)
+    L = C.CDLL(LIB)
+    L.bgpt_host_open.restype = C.c_void_p
+    L.bgpt_host_open.argtypes = [C.c_char_p, C.c_int]
+    L.bgpt_host_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.bgpt_host_n_vocab.argtypes = [C.c_void_p]
+    L.bgpt_host_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
+    L.bgpt_host_close.argtypes = [C.c_void_p]
+    L.bgpt_host_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint32]
+    return L
+
+
+def _tok(host, s):
+    buf = C.create_string_buffer(1 << 16)
+    n = host.bgpt_host_moses_tokenize(s.encode(), buf, len(buf))
+    assert n >= 0
+    return buf.value.decode().split("\n") if n else []
+
+
+def test_moses_unit_strings(host):
+    """the three strings of the reference's own unit test, mosestokenizer.cpp:491-497"""
+    assert _tok(host, "Hello World!") == ["Hello", "World", "!"]
+    assert _tok(host, "This ain't funny. It's actually hillarious, yet double Ls. | [] < > [ ] & You're gonna shake it off? Don't?") == [
+        "This", "ain", "&apos;t", "funny", ".", "It", "&apos;s", "actually", "hillarious", ",", "yet", "double", "Ls", ".",
+        "&#124;", "&#91;", "&#93;", "&lt;", "&gt;", "&#91;", "&#93;", "&amp;", "You", "&apos;re", "gonna", "shake", "it", "off", "?",
+        "Don", "&apos;t", "?"]
+    assert _tok(host, "this is a webpage https://stackoverflow.com/questions/6181381/how-to-print-variables-in-perl that kicks ass") == [
+        "this", "is", "a", "webpage", "https", ":", "/", "/", "stackoverflow.com", "/", "questions", "/", "6181381", "/",
+        "how", "@-@", "to", "@-@", "print", "@-@", "variables", "@-@", "in", "@-@", "perl", "that", "kicks", "ass"]
+
+
+def test_moses_edge_cases(host):
+    assert _tok(host, "") == []
+    assert _tok(host, "   \t\n ") == []
+    assert _tok(host, "Dr. Smith paid 1,000 dollars, e.g. in 1990's.") == [
+        "Dr.", "Smith", "paid", "1,000", "dollars", ",", "e.g.", "in", "1990", "&apos;s", "."]
+    buf = C.create_string_buffer(4096)
+    host.bgpt_host_moses_detokenize("Hello\nWorld\n!\nIt\n&apos;s\nhow\n@-@\nto\n(\nfine\n)\n.".encode(), buf, len(buf))
+    assert buf.value.decode() == "Hello World! It's how-to (fine)."
+
+
+def test_bpe_lowest_rank_merges_first(host):
+    buf = C.create_string_buffer(1024)
+    merges = "l o\nlo w</w>\ne r</w>\nn e\nne w\nnew er</w>"
+    host.bgpt_host_bpe(b"lower", merges.encode(), buf, len(buf))
+    assert buf.value.decode() == "lo w e r</w>".replace("w e r</w>", "w er</w>")
+    host.bgpt_host_bpe(b"newer", merges.encode(), buf, len(buf))
+    assert buf.value.decode() == "newer</w>"
+    host.bgpt_host_bpe(b"a", merges.encode(), buf, len(buf))
+    assert buf.value.decode() == "a</w>"
+
+
+def test_sampler_draw_identical_to_reference(host, checkers, zoo):
+    """same libstdc++ mt19937 + discrete_distribution draw as biogpt_sample_top_k_top_p (biogpt.cpp:908-980)"""
+    if not checkers.have_ref():
+        pytest.skip("reference build not available")
+    R = checkers.Ref(zoo.path("tiny", "f32"))
+    rng = np.random.default_rng(0)
+    for seed in range(20):
+        logits = (rng.standard_normal(R.n_vocab) * 3).astype(np.float32)
+        for top_k, top_p, temp in ((1, 1.0, 1.0), (40, 0.9, 0.9), (5, 0.5, 1.3), (R.n_vocab, 1.0, 0.7)):
+            want = R.sample(logits, top_k, top_p, temp, seed)
+            got = host.bgpt_host_sample(logits.ctypes.data, R.n_vocab, top_k, top_p, temp, seed)
+            assert got == want, (seed, top_k, top_p, temp)
+    R.close()
+
+
+@pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_reference_quantize_frontend_on_our_library(zoo, model_dir, ftype):
+    """the reference's UNMODIFIED examples/quantize/quantize.cpp, linked against libbiogpt_b200.so,
+    must write byte-identical files to the reference's own quantize tool (hash in tests/golden)"""
+    exe = os.path.join(HOST, "_build", "quantize")
+    if not os.path.exists(exe):
+        pytest.skip("front ends are only linked where /root/reference exists")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "quantize_ref.npz"))
+    out = os.path.join(model_dir, f"tiny-{ftype}-ourq.bin")
+    tname = {"q4_0": "2", "q4_1": "3", "q5_0": "8", "q5_1": "9", "q8_0": "7"}[ftype]
+    r = subprocess.run([exe, "-f", zoo.path("tiny", "f32"), "-o", out, "-t", tname], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert hashlib.sha256(open(out, "rb").read()).digest() == gold[f"sha_{ftype}"].tobytes()
+
+
+def test_main_frontend_links():
+    exe = os.path.join(HOST, "_build", "biogpt")
+    if not os.path.exists(exe):
+        pytest.skip("front ends are only linked where /root/reference exists")
+    r = subprocess.run([exe, "-h"], capture_output=True, text=True)
+    assert "usage:" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ftype", ["q4_0", "f16", "q5_1"])
+def test_cpp_api_eval_matches_oracle(host, checkers, zoo, ftype):
+    """biogpt_model_load -> measure pass -> biogpt_eval (the calls main.cpp makes) == oracle bits"""
+    p = zoo.path("small", ftype)
+    h = host.bgpt_host_open(p.encode(), 8)
+    assert h
+    O = checkers.Oracle(p)
+    toks = gf.synth_tokens(20, gf.SMALL.n_vocab, seed=12)
+    out = np.zeros(host.bgpt_host_n_vocab(h), np.float32)
+    pos = 0
+    for n in (8, 4, 1, 1, 1, 5):
+        t = np.ascontiguousarray(toks[pos:pos + n])
+        assert host.bgpt_host_eval(h, t.ctypes.data, n, pos, out.ctypes.data) == 0
+        want = O.eval(t, pos)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (ftype, pos, n)
+        pos += n
+    ids = np.zeros(16, np.int32)
+    n = host.bgpt_host_tokenize(h, b"a b c", ids.ctypes.data, 16)
+    assert ids[:n].tolist() == [2, 4, 5, 6]          # "a b c" -> 2 4 5 6
+    host.bgpt_host_close(h); O.close()
