@@ -140,7 +140,7 @@ def cpu_reference_tokens_per_s(ftype: str, seq: int, budget_s: float, threads: i
     reps = 1
     first = run(positions[len(positions) // 2], 1)
     reps = max(1, int(budget_s / max(first, 1e-4) / len(positions)))
-    reps = min(reps, 64)
+    reps = min(reps, 256)
     for p in positions:
         dt = run(p, reps)
         per_tok.append(dt / reps)

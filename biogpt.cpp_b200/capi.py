@@ -33,7 +33,7 @@ SYMBOLS = [
     "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
-    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
+    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
     "bgpt_cuda_op_attention", "bgpt_cuda_op_gelu", "bgpt_cuda_op_dequantize",
 ]
 
@@ -89,6 +89,7 @@ def lib():
     L.bgpt_cuda_last_eval_ms.argtypes = [C.c_void_p]
     L.bgpt_cuda_set_taps.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.bgpt_cuda_op_mul_mat.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+    L.bgpt_cuda_op_mul_mat_tc.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_quantize_act.argtypes = [C.c_int, _f32p, _u8p, C.c_int]
     L.bgpt_cuda_op_norm.argtypes = [_f32p, C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float]
     L.bgpt_cuda_op_attention.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u16p]
@@ -237,6 +238,15 @@ def op_mul_mat(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int) ->
     y = np.empty((n, rows), dtype=np.float32)
     _check(lib().bgpt_cuda_op_mul_mat(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
            "op_mul_mat")
+    return y
+
+
+def op_mul_mat_tc(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, k = x.shape
+    y = np.empty((n, rows), dtype=np.float32)
+    _check(lib().bgpt_cuda_op_mul_mat_tc(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
+           "op_mul_mat_tc")
     return y
 
 

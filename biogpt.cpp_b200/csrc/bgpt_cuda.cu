@@ -16,6 +16,7 @@
 #include "bgpt_kernels.cuh"
 #include "bgpt_mega.cuh"
 #include "bgpt_barbench.cuh"
+#include "bgpt_tc.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -89,6 +90,7 @@ struct bgpt_model {
     uint64_t launches = 0;
     size_t weight_bytes = 0;
     // persistent decode kernel (bgpt_mega.cuh)
+    bool tc_ok = true;                                   // tcgen05 batch matmul allowed (BGPT_TC=0 disables)
     bool mega_ok = false; int decode_path = 1;          // 1: k_mega for n == 1, 0: per-op kernels
     MegaParams mp{}; MegaLayer * d_mega_layers = nullptr;
     unsigned long long * d_bar = nullptr; unsigned long long bar_epoch = 0;
@@ -351,6 +353,10 @@ template <int FMT> static void launch_gemv_f_tn(int TN, dim3 grid, int threads, 
     }
 }
 
+static int tc_min_rows();
+static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
+                          int n, int tok0, const Epi & epi);
+
 // y = W . act for rows tok0..n-1; W = up to 3 stacked matrices sharing one layout
 static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
                        int n, int tok0, const Epi & epi) {
@@ -362,6 +368,7 @@ static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W
     a.act = act; a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s;
     a.n = n; a.tok0 = tok0; a.epi = epi;
     const int cnt = n - tok0;
+    if (bg_is_quant(L.type) && cnt >= tc_min_rows() && m && m->tc_ok) return launch_gemm_tc(m, s, W, nmat, act, A, n, tok0, epi);
     const int TN = cnt <= 1 ? 1 : cnt == 2 ? 2 : cnt <= 4 ? 4 : 8;
     const int gy = (cnt + TN - 1) / TN;
     const size_t smem = (size_t) TN * A.bytes;
@@ -378,6 +385,53 @@ static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W
         case BG_F16:  launch_gemv_f_tn<BG_F16>(TN, grid, nw * 32, smem, s, a); break;
         case BG_F32:  launch_gemv_f_tn<BG_F32>(TN, grid, nw * 32, smem, s, a); break;
         default: return fail(BGPT_E_UNSUPPORTED, "gemv: type %d", L.type);
+    }
+    if (m) m->launches++;
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+
+// ---- tensor-core (tcgen05) batch matmul for the quantised formats, bgpt_tc.cuh
+static int tc_min_rows() {
+    static int v = -1;
+    if (v < 0) {
+        const char * e = getenv("BGPT_TC"); const char * r = getenv("BGPT_TC_MIN_ROWS");
+        v = (e && atoi(e) == 0) ? (1 << 30) : (r ? std::max(1, atoi(r)) : 32);
+    }
+    return v;
+}
+static size_t tc_smem_bytes() { return std::max(sizeof(TcShared) + 128, (size_t) 120 * 1024); }   // >= half the SM: one CTA (512 TMEM columns) per SM
+static void tc_init_attrs() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const int sm = (int) tc_smem_bytes();
+    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q4_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q5_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q5_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaGetLastError();
+}
+static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
+                          int n, int tok0, const Epi & epi) {
+    const RowLayout & L = W[0]->L;
+    tc_init_attrs();
+    GemvArgs a{};
+    for (int i = 0; i < 3; i++) a.W[i] = W[i < nmat ? i : 0]->ptr;
+    a.rows_per = (int) W[0]->ne1; a.M = a.rows_per * nmat; a.G = L.G; a.stride = L.stride;
+    a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
+    a.act = act; a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s;
+    a.n = n; a.tok0 = tok0; a.epi = epi;
+    dim3 grid((a.M + TC_ROWS - 1) / TC_ROWS, (n - tok0 + TC_TOK - 1) / TC_TOK);
+    const size_t smem = tc_smem_bytes();
+    switch (L.type) {
+        case BG_Q4_0: k_gemm_tc_q<BG_Q4_0><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case BG_Q4_1: k_gemm_tc_q<BG_Q4_1><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case BG_Q5_0: k_gemm_tc_q<BG_Q5_0><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case BG_Q5_1: k_gemm_tc_q<BG_Q5_1><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case BG_Q8_0: k_gemm_tc_q<BG_Q8_0><<<grid, TC_THREADS, smem, s>>>(a); break;
+        default: return fail(BGPT_E_UNSUPPORTED, "tensor-core matmul: type %d", L.type);
     }
     if (m) m->launches++;
     CK(cudaGetLastError());
@@ -885,5 +939,26 @@ extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, fl
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *us_per_barrier = best * 1000.f / iters;
+    return BGPT_OK;
+}
+
+// y = W . x through the tcgen05 path regardless of n (parity tests; quantised types only)
+extern "C" int bgpt_cuda_op_mul_mat_tc(int type, const void * w, const float * x, float * y, int k, int rows, int n) {
+    RET(need_device());
+    if (!bg_is_quant(type)) return fail(BGPT_E_UNSUPPORTED, "op_mul_mat_tc: quantised weight types only");
+    if (!w || !x || !y || k <= 0 || k % 32 || rows <= 0 || n <= 0) return fail(BGPT_E_ARG, "op_mul_mat_tc: bad arguments");
+    DevTensor t; t.type = type; t.ne0 = k; t.ne1 = rows;
+    RET(upload_matrix(t, type, k, rows, (const uint8_t *) w));
+    DevBuf wguard; wguard.p = t.ptr;
+    const ActLayout A = bg_act_layout(type, k);
+    DevBuf dx, da, dy;
+    RET(dx.alloc((size_t) n * k * 4)); RET(da.alloc((size_t) n * A.bytes)); RET(dy.alloc((size_t) n * rows * 4));
+    CK(cudaMemcpy(dx.p, x, (size_t) n * k * 4, cudaMemcpyHostToDevice));
+    RET(launch_act(nullptr, 0, dx.as<float>(), k, nullptr, nullptr, k, type, da.as<uint8_t>(), A, n, nullptr, 0));
+    const DevTensor * W[3] = { &t, nullptr, nullptr };
+    Epi e = make_epi(EPI_STORE, nullptr, dy.as<float>(), rows);
+    RET(launch_gemm_tc(nullptr, 0, W, 1, da.as<uint8_t>(), A, n, 0, e));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(y, dy.p, (size_t) n * rows * 4, cudaMemcpyDeviceToHost));
     return BGPT_OK;
 }

@@ -1,0 +1,258 @@
+// bgpt_tc.cuh -- prompt-batch matmul on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+//   Y[n][r] = sum_b  fl(d_w[r,b] * d_a[n,b]) * (float) isum[r,n,b]   (+ m_w[r,b] * s_a[n,b])
+//   isum[r,n,b] = sum_{e<32} q_w[r,b,e] * q_a[n,b,e]                  exact int32
+//
+// i.e. ggml's block-quantised mul_mat (ggml.c:11804-12013 with the Q8_0/Q8_1 activation
+// conversion of ggml.c:11909-11925) for N token rows at once.  The integer dot of one 32-block
+// is exactly ONE tcgen05.mma.kind::i8 instruction (K = 32 bytes): 128 weight rows x 64 token
+// rows per CTA tile, int32 accumulators in TMEM, one accumulator per block because every block
+// has its own scale pair.  The epilogue reads each accumulator back (tcgen05.ld), converts,
+// scales and accumulates in f32 registers in block order.
+//
+// Parity note: the integer sums are exact and the per-block scale product is the reference's
+// single rounded f32 product, but the reference adds the blocks through 8 interleaved lanes
+// (bgpt_kernels.cuh "lane order") and a tensor-core instruction cannot expose 4-element partial
+// sums -- so this path is NOT bit-identical to the CPU reference, only tolerance-close (f32
+// summation order).  It is therefore used only for batches of >= BGPT_TC_MIN_ROWS token rows
+// (default 32; the reference's default n_batch = 8 stays on the exact path) and can be switched
+// off with BGPT_TC=0.
+//
+// Pipeline per CTA (256 threads), one K step = a group of 4 blocks, two stages:
+//   fill     all threads: weights of the group (re-tiled layout, 16-byte LDG) are unpacked to
+//            int8 and written in the canonical K-major no-swizzle UMMA layout (8x16B core
+//            matrices); the int8 activation words likewise; scales to shared memory
+//   mma      one thread: 4 x tcgen05.mma (M=128, N=64, K=32, accumulate=false) + tcgen05.commit
+//   epilogue 8 warps = 4 TMEM lane quadrants x 2 column halves: tcgen05.ld 32x32b.x32,
+//            acc[c] = fma(s_w*s_a, (float) d, acc[c])
+// fill(g+1) and the MMAs of g+1 are issued before the epilogue of g, so the tensor core works
+// while the CUDA cores drain the previous group.
+#pragma once
+#include "bgpt_kernels.cuh"
+
+#define TC_ROWS 128
+#define TC_TOK  64
+#define TC_THREADS 256
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: element (row, 16-byte chunk kc) of a [rows x 32 B] operand lives at
+// (row/8)*256 + kc*128 + (row%8)*16  -> LBO (between K chunks) = 128 B, SBO (between 8-row groups) = 256 B
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((smem_addr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t) ((128u >> 4) & 0x3FFF) << 16;         // leading byte offset
+    d |= (uint64_t) ((256u >> 4) & 0x3FFF) << 32;         // stride byte offset
+    d |= (uint64_t) 1 << 46;                              // descriptor version (Blackwell)
+    return d;                                             // base offset 0, SWIZZLE_NONE
+}
+// instruction descriptor: D = S32, A = B = S8, both K-major, M = 128, N = TC_TOK
+__device__ __forceinline__ uint32_t tc_idesc_i8() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (TC_TOK >> 3) << 17) | ((uint32_t) (TC_ROWS >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t mbar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar_addr) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_init(uint32_t mbar_addr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t mbar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n"
+        :: "r"(mbar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 4 nibble-codes (one byte each, value 0..15 / 0..31) -> signed int8 bytes of (code - off)
+__device__ __forceinline__ uint32_t tc_sub8(uint32_t v)  { const uint32_t t = v ^ 0x08080808u; return t | ((t & 0x08080808u) * 0x1Eu); }
+__device__ __forceinline__ uint32_t tc_sub16(uint32_t v) { const uint32_t t = v ^ 0x10101010u; return t | ((t & 0x10101010u) * 0x0Eu); }
+
+struct TcShared {
+    uint8_t A[2][4][TC_ROWS * 32];     // [stage][block in group][canonical layout]
+    uint8_t B[2][4][TC_TOK * 32];
+    float sw[2][4][TC_ROWS];           // weight scales d_w
+    float mw[2][4][TC_ROWS];           // weight mins   m_w   (Q4_1 / Q5_1)
+    float sa[2][4][TC_TOK];            // activation scales d_a
+    float ss[2][4][TC_TOK];            // activation s = d*sum(q) (Q8_1)
+    unsigned long long mbar[2];
+    uint32_t tmem_base;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_q(GemvArgs a) {
+    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+    TcShared & S = *reinterpret_cast<TcShared *>(tc_smem_raw);
+    constexpr bool IS8   = (FMT == BG_Q8_0);
+    constexpr bool HASQH = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM  = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * TC_ROWS;                 // first weight row of this tile (stacked row space)
+    const int tok0 = a.tok0 + blockIdx.y * TC_TOK;         // first token row
+
+    if (tid == 0) { tc_mbar_init(tc_smem_u32(&S.mbar[0]), 1); tc_mbar_init(tc_smem_u32(&S.mbar[1]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t idesc = tc_idesc_i8();
+
+    // ---- fill: stage s <- group g
+    auto fill = [&](int s, int g) {
+        {   // weights: thread (row, kc): kc = 0 -> elements 0..15 (low nibbles / first 16 bytes), kc = 1 -> 16..31
+            const int row = tid >> 1, kc = tid & 1;
+            int r = row0 + row; r = r < a.M ? r : a.M - 1;
+            const int mat = r / a.rows_per;
+            const uint8_t * wrow = a.W[mat] + (size_t) (r - mat * a.rows_per) * a.stride;
+            uint32_t out[4][4];                              // [block i][word j]
+            if (IS8) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint4 w = ldg_stream128(wrow + (size_t) ((g * 2 + kc) * 4 + j) * 16);
+                    out[0][j] = w.x; out[1][j] = w.y; out[2][j] = w.z; out[3][j] = w.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint4 w = ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
+                    uint32_t qh = 0;
+                    if (HASQH) qh = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
+                    const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        uint32_t v = kc ? ((ww[i] >> 4) & 0x0F0F0F0Fu) : (ww[i] & 0x0F0F0F0Fu);
+                        if (HASQH) { const uint32_t hb = (qh >> (8 * i)) & 0xFFu; v |= bg_spread4(kc ? (hb >> 4) : (hb & 0xFu)); }
+                        if (FMT == BG_Q4_0) v = tc_sub8(v);
+                        if (FMT == BG_Q5_0) v = tc_sub16(v);
+                        out[i][j] = v;
+                    }
+                }
+            }
+            const int off = (row >> 3) * 256 + kc * 128 + (row & 7) * 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) *(uint4 *) (&S.A[s][i][off]) = make_uint4(out[i][0], out[i][1], out[i][2], out[i][3]);
+            if (kc == 0) {
+                const uint2 dh = ldg_stream64(wrow + a.off_d + g * 8);
+                S.sw[s][0][row] = bg_h2f((uint16_t) (dh.x & 0xFFFF)); S.sw[s][1][row] = bg_h2f((uint16_t) (dh.x >> 16));
+                S.sw[s][2][row] = bg_h2f((uint16_t) (dh.y & 0xFFFF)); S.sw[s][3][row] = bg_h2f((uint16_t) (dh.y >> 16));
+            } else if (HASM) {
+                const uint2 mh = ldg_stream64(wrow + a.off_m + g * 8);
+                S.mw[s][0][row] = bg_h2f((uint16_t) (mh.x & 0xFFFF)); S.mw[s][1][row] = bg_h2f((uint16_t) (mh.x >> 16));
+                S.mw[s][2][row] = bg_h2f((uint16_t) (mh.y & 0xFFFF)); S.mw[s][3][row] = bg_h2f((uint16_t) (mh.y >> 16));
+            }
+        }
+        if (tid < 2 * TC_TOK) {   // activations: thread (token, kc)
+            const int tk = tid >> 1, kc = tid & 1;
+            const int n = tok0 + tk;
+            const bool valid = n < a.n;
+            const uint8_t * rec = a.act + (size_t) (valid ? n : 0) * a.act_bytes;
+            uint32_t out[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if (valid) w = *(const uint4 *) (rec + (size_t) (g * 8 + kc * 4 + j) * 16);
+                out[0][j] = w.x; out[1][j] = w.y; out[2][j] = w.z; out[3][j] = w.w;
+            }
+            const int off = (tk >> 3) * 256 + kc * 128 + (tk & 7) * 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) *(uint4 *) (&S.B[s][i][off]) = make_uint4(out[i][0], out[i][1], out[i][2], out[i][3]);
+            if (kc == 0) {
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) d = *(const float4 *) (rec + a.off_dd + g * 16);
+                S.sa[s][0][tk] = d.x; S.sa[s][1][tk] = d.y; S.sa[s][2][tk] = d.z; S.sa[s][3][tk] = d.w;
+            } else if (HASM) {
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) d = *(const float4 *) (rec + a.off_s + g * 16);
+                S.ss[s][0][tk] = d.x; S.ss[s][1][tk] = d.y; S.ss[s][2][tk] = d.z; S.ss[s][3][tk] = d.w;
+            }
+        }
+    };
+    auto issue = [&](int s) {
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                tc_mma_i8(tmem + (uint32_t) ((s * 4 + i) * TC_TOK), tc_make_desc(tc_smem_u32(&S.A[s][i][0])), tc_make_desc(tc_smem_u32(&S.B[s][i][0])), idesc, 0u);
+            tc_commit(tc_smem_u32(&S.mbar[s]));
+        }
+    };
+
+    // ---- epilogue state: this thread owns row (quadrant*32 + lane) and 32 of the 64 token columns
+    const int quad = warp & 3, chalf = warp >> 2;
+    const int erow = quad * 32 + lane;
+    float acc[32], summ[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) { acc[c] = 0.0f; summ[c] = 0.0f; }
+    auto epilogue = [&](int s, uint32_t parity) {
+        tc_mbar_wait(tc_smem_u32(&S.mbar[s]), parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t v[32];
+            tc_ld32(tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) ((s * 4 + i) * TC_TOK + chalf * 32), v);
+            const float dw = S.sw[s][i][erow];
+            const float mwv = HASM ? S.mw[s][i][erow] : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const float sc = __fmul_rn(dw, S.sa[s][i][chalf * 32 + c]);
+                acc[c] = fmaf(sc, (float) (int) v[c], acc[c]);
+                if (HASM) summ[c] = fmaf(mwv, S.ss[s][i][chalf * 32 + c], summ[c]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    // ---- main loop over groups of 4 blocks
+    const int G = a.G;
+    fill(0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    issue(0);
+    for (int g = 1; g < G; g++) {
+        const int s = g & 1;
+        fill(s, g);                                        // stage s was drained by epilogue(g-2)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        issue(s);
+        epilogue(s ^ 1, (uint32_t) (((g - 1) >> 1) & 1));
+        __syncthreads();                                   // scales of stage s^1 are free again
+    }
+    epilogue((G - 1) & 1, (uint32_t) (((G - 1) >> 1) & 1));
+
+    // ---- write out
+    const int r = row0 + erow;
+    if (r < a.M) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const int n = tok0 + chalf * 32 + c;
+            if (n < a.n) bg_epilogue(a.epi, n, r, HASM ? __fadd_rn(acc[c], summ[c]) : acc[c]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}

@@ -143,6 +143,11 @@ int    bgpt_cuda_set_taps(bgpt_model * m, float * const taps5[5]);
  * (ggml_compute_forward_mul_mat, ggml.c:11804-12013).  All pointers HOST. */
 int bgpt_cuda_op_mul_mat(int ggml_type, const void * w, const float * x, float * y,
                          int k, int rows, int n);
+/* the same product through the tcgen05 tensor-core kernel used for prompt batches
+ * (csrc/bgpt_tc.cuh; quantised types only).  Exact integer block dots, f32 block accumulation
+ * in block order: close to, not bit-identical with, the CPU reference (see the file header). */
+int bgpt_cuda_op_mul_mat_tc(int ggml_type, const void * w, const float * x, float * y,
+                            int k, int rows, int n);
 /* activation quantisers applied to src1 by mul_mat (ggml.c:1166-1249, 1403-1494, 493-510):
  * out = k/32 blocks of block_q8_0 (34 B) / block_q8_1 (40 B) for the weight type's
  * vec_dot_type, or k fp16 values for F16 weights. */

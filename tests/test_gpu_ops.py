@@ -144,3 +144,27 @@ def test_dequantize_rows(checkers, capi, name):
         want[r] = y
     got = capi.op_dequantize(t, wb, k, rows)
     assert np.array_equal(_bits(got), _bits(want))
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+@pytest.mark.parametrize("shape", [(1024, 256, 64), (4096, 136, 70), (1024, 1000, 200), (128, 128, 33), (64, 8, 5)])
+def test_mul_mat_tensor_core(checkers, capi, name, shape):
+    """tcgen05 prompt-batch matmul (csrc/bgpt_tc.cuh): integer block dots are exact, blocks are
+    accumulated in f32 in block order -- so the result is the oracle's up to f32 summation order.
+    Tolerance: 4 ulp-ish of the largest partial sum, |y_tc - y_oracle| <= 2e-6 * sum_b |term_b|,
+    checked through the cheaper bound 3e-5 * max|y| + 1e-6."""
+    k, rows, n = shape
+    t = TYPES[name]
+    rng = np.random.default_rng(k + rows * 3 + n + t)
+    w = (rng.standard_normal((rows, k)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    wb = np.frombuffer(gf.encode_tensor(w, t), dtype=np.uint8).copy()
+    want = np.zeros((n, rows), dtype=np.float32)
+    checkers.oracle_lib().bo_mul_mat(t, wb, x, want, k, rows, n)
+    got = capi.op_mul_mat_tc(t, wb, x, rows)
+    err = np.abs(got - want).max()
+    tol = 3e-5 * np.abs(want).max() + 1e-6
+    assert err <= tol, f"{name} {shape}: max|d|={err:.3e} tol={tol:.3e}"
+    # and it must agree with the exact-order GPU kernel to the same tolerance
+    exact = capi.op_mul_mat(t, wb, x, rows)
+    assert np.abs(got - exact).max() <= tol
