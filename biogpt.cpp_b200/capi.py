@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -77,6 +77,7 @@ def lib():
     L.bgpt_cuda_get_decode_path.argtypes = [C.c_void_p]
     L.bgpt_cuda_debug_read_prof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bgpt_cuda_debug_barrier_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.bgpt_cuda_debug_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
     L.bgpt_cuda_hparams.restype = None

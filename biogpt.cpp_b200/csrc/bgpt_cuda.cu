@@ -962,3 +962,45 @@ extern "C" int bgpt_cuda_op_mul_mat_tc(int type, const void * w, const float * x
     CK(cudaMemcpy(y, dy.p, (size_t) n * rows * 4, cudaMemcpyDeviceToHost));
     return BGPT_OK;
 }
+
+// debug: device time of `iters` back-to-back matmuls y[n][rows] = W[rows][k] . x[n][k] on synthetic
+// data; path 0 = exact-order SIMT kernels, 1 = tcgen05.  ms_out = milliseconds per matmul.
+extern "C" int bgpt_cuda_debug_gemm_bench(int type, int k, int rows, int n, int iters, int path, float * ms_out) {
+    RET(need_device());
+    if (!bg_type_ok(type) || k <= 0 || k % 32 || rows <= 0 || n <= 0 || iters <= 0) return fail(BGPT_E_ARG, "gemm_bench: bad arguments");
+    if (path == 1 && !bg_is_quant(type)) return fail(BGPT_E_UNSUPPORTED, "gemm_bench: tcgen05 path is for quantised types");
+    DevTensor t; t.type = type; t.ne0 = k; t.ne1 = rows;
+    std::vector<uint8_t> wfile(bg_file_row_bytes(type, k) * (size_t) rows);
+    uint32_t seed = 12345u;
+    for (auto & b : wfile) { seed = seed * 1664525u + 1013904223u; b = (uint8_t) (seed >> 24); }
+    if (bg_is_quant(type)) {        // keep the fp16 scale fields finite: overwrite them with 0x2C00 (= 0.0625)
+        const int bs = bg_file_block_bytes(type);
+        for (size_t o = 0; o + bs <= wfile.size(); o += bs) { wfile[o] = 0x00; wfile[o + 1] = 0x2C; if (type == BG_Q4_1 || type == BG_Q5_1) { wfile[o + 2] = 0x00; wfile[o + 3] = 0x2C; } }
+    } else if (type == BG_F16) { for (size_t o = 0; o + 2 <= wfile.size(); o += 2) wfile[o + 1] = (wfile[o + 1] & 0x83) | 0x28; }
+    else { for (size_t o = 0; o + 4 <= wfile.size(); o += 4) { wfile[o + 3] = 0x3C; } }
+    RET(upload_matrix(t, type, k, rows, wfile.data()));
+    DevBuf wguard; wguard.p = t.ptr;
+    const ActLayout A = bg_act_layout(type, k);
+    DevBuf dx, da, dy;
+    RET(dx.alloc((size_t) n * k * 4)); RET(da.alloc((size_t) n * A.bytes)); RET(dy.alloc((size_t) n * rows * 4));
+    std::vector<float> hx((size_t) n * k);
+    for (auto & v : hx) { seed = seed * 1664525u + 1013904223u; v = ((int) (seed >> 8) % 2001 - 1000) / 500.0f; }
+    CK(cudaMemcpy(dx.p, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+    RET(launch_act(nullptr, 0, dx.as<float>(), k, nullptr, nullptr, k, type, da.as<uint8_t>(), A, n, nullptr, 0));
+    const DevTensor * W[3] = { &t, nullptr, nullptr };
+    Epi e = make_epi(EPI_STORE, nullptr, dy.as<float>(), rows);
+    bgpt_model fake{}; fake.tc_ok = false;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {
+        if (rep == 1) CK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; i++) {
+            if (path == 1) RET(launch_gemm_tc(nullptr, 0, W, 1, da.as<uint8_t>(), A, n, 0, e));
+            else RET(launch_gemv(&fake, 0, W, 1, da.as<uint8_t>(), A, n, 0, e));
+        }
+    }
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_out = ms / iters;
+    return BGPT_OK;
+}

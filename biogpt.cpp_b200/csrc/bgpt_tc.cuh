@@ -81,8 +81,10 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// exact int32 -> f32 for |v| < 2^22 without the quarter-rate I2F: 1.5*2^23 + v is exact in f32
+__device__ __forceinline__ float tc_i2f(uint32_t v) { return __fsub_rn(__int_as_float((int) v + 0x4B400000), 12582912.0f); }
 
 // 4 nibble-codes (one byte each, value 0..15 / 0..31) -> signed int8 bytes of (code - off)
 __device__ __forceinline__ uint32_t tc_sub8(uint32_t v)  { const uint32_t t = v ^ 0x08080808u; return t | ((t & 0x08080808u) * 0x1Eu); }
@@ -121,74 +123,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_q(GemvArgs a) {
     const uint32_t tmem = S.tmem_base;
     const uint32_t idesc = tc_idesc_i8();
 
-    // ---- fill: stage s <- group g
-    auto fill = [&](int s, int g) {
-        {   // weights: thread (row, kc): kc = 0 -> elements 0..15 (low nibbles / first 16 bytes), kc = 1 -> 16..31
-            const int row = tid >> 1, kc = tid & 1;
-            int r = row0 + row; r = r < a.M ? r : a.M - 1;
-            const int mat = r / a.rows_per;
-            const uint8_t * wrow = a.W[mat] + (size_t) (r - mat * a.rows_per) * a.stride;
-            uint32_t out[4][4];                              // [block i][word j]
-            if (IS8) {
+    // ---- fill, split in two so that the global loads of group g+1 travel while group g-1 is
+    //      drained: load_group (global -> registers), store_group (unpack, registers -> smem)
+    const int frow = tid >> 1, fkc = tid & 1;               // weights: thread (row, kc): kc = 0 -> elements 0..15, 1 -> 16..31
+    const uint8_t * wrow;
+    {
+        int r = row0 + frow; r = r < a.M ? r : a.M - 1;
+        const int mat = r / a.rows_per;
+        wrow = a.W[mat] + (size_t) (r - mat * a.rows_per) * a.stride;
+    }
+    const int atk = tid >> 1, akc = tid & 1;                // activations: thread (token, kc), tid < 2*TC_TOK
+    const bool a_thread = tid < 2 * TC_TOK;
+    const bool a_valid = a_thread && (tok0 + atk) < a.n;
+    const uint8_t * arec = a.act + (size_t) (a_valid ? tok0 + atk : 0) * a.act_bytes;
+    uint4 wreg[4], areg[4]; uint32_t qhreg[4]; uint2 sreg; float4 asreg;
+    auto load_group = [&](int g) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint4 w = ldg_stream128(wrow + (size_t) ((g * 2 + kc) * 4 + j) * 16);
-                    out[0][j] = w.x; out[1][j] = w.y; out[2][j] = w.z; out[3][j] = w.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint4 w = ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
-                    uint32_t qh = 0;
-                    if (HASQH) qh = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
-                    const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        uint32_t v = kc ? ((ww[i] >> 4) & 0x0F0F0F0Fu) : (ww[i] & 0x0F0F0F0Fu);
-                        if (HASQH) { const uint32_t hb = (qh >> (8 * i)) & 0xFFu; v |= bg_spread4(kc ? (hb >> 4) : (hb & 0xFu)); }
-                        if (FMT == BG_Q4_0) v = tc_sub8(v);
-                        if (FMT == BG_Q5_0) v = tc_sub16(v);
-                        out[i][j] = v;
-                    }
-                }
-            }
-            const int off = (row >> 3) * 256 + kc * 128 + (row & 7) * 16;
-#pragma unroll
-            for (int i = 0; i < 4; i++) *(uint4 *) (&S.A[s][i][off]) = make_uint4(out[i][0], out[i][1], out[i][2], out[i][3]);
-            if (kc == 0) {
-                const uint2 dh = ldg_stream64(wrow + a.off_d + g * 8);
-                S.sw[s][0][row] = bg_h2f((uint16_t) (dh.x & 0xFFFF)); S.sw[s][1][row] = bg_h2f((uint16_t) (dh.x >> 16));
-                S.sw[s][2][row] = bg_h2f((uint16_t) (dh.y & 0xFFFF)); S.sw[s][3][row] = bg_h2f((uint16_t) (dh.y >> 16));
-            } else if (HASM) {
-                const uint2 mh = ldg_stream64(wrow + a.off_m + g * 8);
-                S.mw[s][0][row] = bg_h2f((uint16_t) (mh.x & 0xFFFF)); S.mw[s][1][row] = bg_h2f((uint16_t) (mh.x >> 16));
-                S.mw[s][2][row] = bg_h2f((uint16_t) (mh.y & 0xFFFF)); S.mw[s][3][row] = bg_h2f((uint16_t) (mh.y >> 16));
-            }
+        for (int j = 0; j < 4; j++) {
+            wreg[j] = IS8 ? ldg_stream128(wrow + (size_t) ((g * 2 + fkc) * 4 + j) * 16) : ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
+            if (HASQH) qhreg[j] = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
         }
-        if (tid < 2 * TC_TOK) {   // activations: thread (token, kc)
-            const int tk = tid >> 1, kc = tid & 1;
-            const int n = tok0 + tk;
-            const bool valid = n < a.n;
-            const uint8_t * rec = a.act + (size_t) (valid ? n : 0) * a.act_bytes;
-            uint32_t out[4][4];
+        sreg = make_uint2(0, 0);
+        if (fkc == 0) sreg = ldg_stream64(wrow + a.off_d + g * 8);
+        else if (HASM) sreg = ldg_stream64(wrow + a.off_m + g * 8);
+        asreg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; j++) areg[j] = make_uint4(0, 0, 0, 0);
+        if (a_valid) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) areg[j] = *(const uint4 *) (arec + (size_t) (g * 8 + akc * 4 + j) * 16);
+            if (akc == 0) asreg = *(const float4 *) (arec + a.off_dd + g * 16);
+            else if (HASM) asreg = *(const float4 *) (arec + a.off_s + g * 16);
+        }
+    };
+    auto store_group = [&](int s) {
+        {
+            uint32_t out[4][4];                              // [block i][word j]
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint4 w = make_uint4(0, 0, 0, 0);
-                if (valid) w = *(const uint4 *) (rec + (size_t) (g * 8 + kc * 4 + j) * 16);
-                out[0][j] = w.x; out[1][j] = w.y; out[2][j] = w.z; out[3][j] = w.w;
-            }
-            const int off = (tk >> 3) * 256 + kc * 128 + (tk & 7) * 16;
+                const uint32_t ww[4] = { wreg[j].x, wreg[j].y, wreg[j].z, wreg[j].w };
 #pragma unroll
-            for (int i = 0; i < 4; i++) *(uint4 *) (&S.B[s][i][off]) = make_uint4(out[i][0], out[i][1], out[i][2], out[i][3]);
-            if (kc == 0) {
-                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) d = *(const float4 *) (rec + a.off_dd + g * 16);
-                S.sa[s][0][tk] = d.x; S.sa[s][1][tk] = d.y; S.sa[s][2][tk] = d.z; S.sa[s][3][tk] = d.w;
-            } else if (HASM) {
-                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) d = *(const float4 *) (rec + a.off_s + g * 16);
-                S.ss[s][0][tk] = d.x; S.ss[s][1][tk] = d.y; S.ss[s][2][tk] = d.z; S.ss[s][3][tk] = d.w;
+                for (int i = 0; i < 4; i++) {
+                    uint32_t v = ww[i];
+                    if (!IS8) {
+                        v = fkc ? ((ww[i] >> 4) & 0x0F0F0F0Fu) : (ww[i] & 0x0F0F0F0Fu);
+                        if (HASQH) { const uint32_t hb = (qhreg[j] >> (8 * i)) & 0xFFu; v |= bg_spread4(fkc ? (hb >> 4) : (hb & 0xFu)); }
+                        if (FMT == BG_Q4_0) v = tc_sub8(v);
+                        if (FMT == BG_Q5_0) v = tc_sub16(v);
+                    }
+                    out[i][j] = v;
+                }
             }
+            const int off = (frow >> 3) * 256 + fkc * 128 + (frow & 7) * 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) *(uint4 *) (&S.A[s][i][off]) = make_uint4(out[i][0], out[i][1], out[i][2], out[i][3]);
+            float * dst = (fkc == 0) ? &S.sw[s][0][0] : &S.mw[s][0][0];
+            if (fkc == 0 || HASM) {
+                dst[0 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.x & 0xFFFF)); dst[1 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.x >> 16));
+                dst[2 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.y & 0xFFFF)); dst[3 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.y >> 16));
+            }
+        }
+        if (a_thread) {
+            const int off = (atk >> 3) * 256 + akc * 128 + (atk & 7) * 16;
+            *(uint4 *) (&S.B[s][0][off]) = make_uint4(areg[0].x, areg[1].x, areg[2].x, areg[3].x);
+            *(uint4 *) (&S.B[s][1][off]) = make_uint4(areg[0].y, areg[1].y, areg[2].y, areg[3].y);
+            *(uint4 *) (&S.B[s][2][off]) = make_uint4(areg[0].z, areg[1].z, areg[2].z, areg[3].z);
+            *(uint4 *) (&S.B[s][3][off]) = make_uint4(areg[0].w, areg[1].w, areg[2].w, areg[3].w);
+            float * dst = (akc == 0) ? &S.sa[s][0][0] : &S.ss[s][0][0];
+            if (akc == 0 || HASM) { dst[0 * TC_TOK + atk] = asreg.x; dst[1 * TC_TOK + atk] = asreg.y; dst[2 * TC_TOK + atk] = asreg.z; dst[3 * TC_TOK + atk] = asreg.w; }
         }
     };
     auto issue = [&](int s) {
@@ -210,16 +212,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_q(GemvArgs a) {
     auto epilogue = [&](int s, uint32_t parity) {
         tc_mbar_wait(tc_smem_u32(&S.mbar[s]), parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[2][32];
+        const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (s * 4 * TC_TOK + chalf * 32);
+        tc_ld32(tbase, v[0]);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            uint32_t v[32];
-            tc_ld32(tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) ((s * 4 + i) * TC_TOK + chalf * 32), v);
+            tc_ld_wait();                                        // accumulator i is in v[i&1]
+            if (i < 3) tc_ld32(tbase + (uint32_t) ((i + 1) * TC_TOK), v[(i + 1) & 1]);   // next one travels during the math
             const float dw = S.sw[s][i][erow];
             const float mwv = HASM ? S.mw[s][i][erow] : 0.0f;
 #pragma unroll
             for (int c = 0; c < 32; c++) {
                 const float sc = __fmul_rn(dw, S.sa[s][i][chalf * 32 + c]);
-                acc[c] = fmaf(sc, (float) (int) v[c], acc[c]);
+                acc[c] = fmaf(sc, tc_i2f(v[i & 1][c]), acc[c]);
                 if (HASM) summ[c] = fmaf(mwv, S.ss[s][i][chalf * 32 + c], summ[c]);
             }
         }
@@ -228,16 +233,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_q(GemvArgs a) {
 
     // ---- main loop over groups of 4 blocks
     const int G = a.G;
-    fill(0, 0);
+    load_group(0);
+    store_group(0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     issue(0);
+    if (G > 1) load_group(1);
     for (int g = 1; g < G; g++) {
         const int s = g & 1;
-        fill(s, g);                                        // stage s was drained by epilogue(g-2)
+        store_group(s);                                    // stage s was drained by epilogue(g-2)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         issue(s);
+        if (g + 1 < G) load_group(g + 1);                  // in flight during the epilogue below
         epilogue(s ^ 1, (uint32_t) (((g - 1) >> 1) & 1));
         __syncthreads();                                   // scales of stage s^1 are free again
     }

@@ -117,6 +117,9 @@ int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);
 /* debug: microseconds per grid-wide barrier for the candidate implementations in
  * csrc/bgpt_barbench.cuh (one CTA per SM, `iters` back-to-back barriers). */
 int bgpt_cuda_debug_barrier_bench(int variant, int iters, int with_load, float * us_per_barrier);
+/* debug: milliseconds per matmul y[n][rows] = W[rows][k].x[n][k] (synthetic data, device
+ * resident, `iters` back-to-back launches); path 0 = exact-order SIMT kernels, 1 = tcgen05. */
+int bgpt_cuda_debug_gemm_bench(int ggml_type, int k, int rows, int n, int iters, int path, float * ms_out);
 
 /* multi-stream state: `n_streams` independent sequences, each with its own KV cache
  * (SURVEY 8(d) config 4).  Stream 0 always exists. */
