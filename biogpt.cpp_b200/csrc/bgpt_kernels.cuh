@@ -655,6 +655,141 @@ __global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
                                a.out + (size_t) row * a.ld_out + (size_t) h * DK);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_attn_tile: un-masked attention for a TILE of AT_R query rows of one head (prompt batches).
+// All rows of a prompt batch see the same T = n_past + n positions of the same K/V, so one CTA
+// streams K and V once for AT_R queries instead of once per query.  Same arithmetic order as
+// k_attn: scores by the transposing butterfly (32 key rows per warp pass, xor 16,8,4,1,2 tree),
+// softmax per row with the fp16 exp table and a double sum, V reduction with lane = running sum
+// (t % 32) for 4 columns x AT_R queries, all-reduced in the same tree, then the scalar tail.
+// grid = (n_head, ceil(n / AT_R)), block = 256, dynamic smem = AT_R * (Tpad + 64) floats. d_kv = 64.
+// ---------------------------------------------------------------------------------------------
+#define AT_R 16
+__global__ void __launch_bounds__(256) k_attn_tile(AttnArgs a) {
+    constexpr int DK = 64, NW = 8;
+    extern __shared__ __align__(16) float s_at[];
+    const int h = blockIdx.x, r0 = blockIdx.y * AT_R, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.st->n_past + a.n;                       // mode 0 only
+    const int Tpad = (T + 31) & ~31;
+    float * sq = s_at;                                      // [AT_R][64]
+    float * sc = s_at + AT_R * DK;                          // [AT_R][Tpad]
+    const float * Kb = a.kcache + (size_t) h * DK;
+    const float * Vb = a.vcache + (size_t) h * DK;
+    for (int i = tid; i < AT_R * DK; i += 256) {
+        int row = r0 + i / DK; row = row < a.n ? row : a.n - 1;
+        sq[i] = a.q[(size_t) row * a.ld_q + (size_t) h * DK + (i % DK)];
+    }
+    __syncthreads();
+    // ---- scores
+    for (int tb = warp; tb < T; tb += NW * 32) {
+        float k0[32], k1[32];
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+            const int t = tb + u * NW;
+            k0[u] = t < T ? __ldcg(Kb + (size_t) t * a.d + lane) : 0.0f;
+            k1[u] = t < T ? __ldcg(Kb + (size_t) t * a.d + 32 + lane) : 0.0f;
+        }
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b0 = lane & 1, b1 = lane & 2;
+        const int urow = (lane & 28) | ((lane & 1) << 1) | ((lane & 2) >> 1);
+        const int tl = tb + urow * NW;
+#pragma unroll 1
+        for (int r = 0; r < AT_R; r++) {
+            const float q0 = sq[r * DK + lane], q1 = sq[r * DK + 32 + lane];
+            float s[32], a16[16], a8[8], a4[4], a2[2];
+#pragma unroll
+            for (int u = 0; u < 32; u++) s[u] = fmaf(k1[u], q1, fmaf(k0[u], q0, 0.0f));
+#pragma unroll
+            for (int i = 0; i < 16; i++) { const float mine = b4 ? s[16 + i] : s[i], send = b4 ? s[i] : s[16 + i]; a16[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 16)); }
+#pragma unroll
+            for (int i = 0; i < 8; i++)  { const float mine = b3 ? a16[8 + i] : a16[i], send = b3 ? a16[i] : a16[8 + i]; a8[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 8)); }
+#pragma unroll
+            for (int i = 0; i < 4; i++)  { const float mine = b2 ? a8[4 + i] : a8[i], send = b2 ? a8[i] : a8[4 + i]; a4[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 4)); }
+#pragma unroll
+            for (int i = 0; i < 2; i++)  { const float mine = b0 ? a4[2 + i] : a4[i], send = b0 ? a4[i] : a4[2 + i]; a2[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 1)); }
+            const float mine = b1 ? a2[1] : a2[0], send = b1 ? a2[0] : a2[1];
+            const float dot = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 2));
+            if (tl < T) sc[r * Tpad + tl] = dot;
+        }
+    }
+    __syncthreads();
+    // ---- softmax, one warp per query row
+    for (int r = warp; r < AT_R; r += NW) {
+        float * row = sc + r * Tpad;
+        float mx = -INFINITY;
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, row[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
+        double sum = 0.0;
+        for (int t = lane; t < T; t += 32) {
+            const float v = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(row[t], mx))]);
+            row[t] = v; sum += (double) v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULLMASK, sum, o);
+        const float inv = (float) (1.0 / sum);
+        for (int t = lane; t < T; t += 32) row[t] = __fmul_rn(row[t], inv);
+    }
+    __syncthreads();
+    // ---- V: warp = 4 output columns, lane = running sum (t % 32), AT_R queries at once
+    const int np = T & ~31, nv = np + ((T - np) & ~3);
+    for (int cg = warp; cg < DK / 4; cg += NW) {
+        float4 acc[AT_R];
+#pragma unroll
+        for (int r = 0; r < AT_R; r++) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float * vp = Vb + cg * 4;
+        for (int s0 = 0; s0 < np; s0 += 64) {
+            const int t0 = s0 + lane, t1 = s0 + 32 + lane;
+            const float4 v0 = __ldcg((const float4 *) (vp + (size_t) t0 * a.d));
+            float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool two = s0 + 32 < np;
+            if (two) v1 = __ldcg((const float4 *) (vp + (size_t) t1 * a.d));
+#pragma unroll
+            for (int r = 0; r < AT_R; r++) {
+                const float p0 = sc[r * Tpad + t0];
+                acc[r].x = fmaf(v0.x, p0, acc[r].x); acc[r].y = fmaf(v0.y, p0, acc[r].y);
+                acc[r].z = fmaf(v0.z, p0, acc[r].z); acc[r].w = fmaf(v0.w, p0, acc[r].w);
+            }
+            if (two) {
+#pragma unroll
+                for (int r = 0; r < AT_R; r++) {
+                    const float p1 = sc[r * Tpad + t1];
+                    acc[r].x = fmaf(v1.x, p1, acc[r].x); acc[r].y = fmaf(v1.y, p1, acc[r].y);
+                    acc[r].z = fmaf(v1.z, p1, acc[r].z); acc[r].w = fmaf(v1.w, p1, acc[r].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < AT_R; r++) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int o = k == 0 ? 16 : k == 1 ? 8 : k == 2 ? 4 : k == 3 ? 1 : 2;
+                acc[r].x = __fadd_rn(acc[r].x, __shfl_xor_sync(FULLMASK, acc[r].x, o));
+                acc[r].y = __fadd_rn(acc[r].y, __shfl_xor_sync(FULLMASK, acc[r].y, o));
+                acc[r].z = __fadd_rn(acc[r].z, __shfl_xor_sync(FULLMASK, acc[r].z, o));
+                acc[r].w = __fadd_rn(acc[r].w, __shfl_xor_sync(FULLMASK, acc[r].w, o));
+            }
+        }
+        for (int t = np; t < T; t++) {                       // scalar tail, identical on every lane
+            const float4 v = __ldcg((const float4 *) (vp + (size_t) t * a.d));
+            const bool fused = t >= nv;
+#pragma unroll
+            for (int r = 0; r < AT_R; r++) {
+                const float pw = sc[r * Tpad + t];
+                if (fused) {
+                    acc[r].x = fmaf(v.x, pw, acc[r].x); acc[r].y = fmaf(v.y, pw, acc[r].y);
+                    acc[r].z = fmaf(v.z, pw, acc[r].z); acc[r].w = fmaf(v.w, pw, acc[r].w);
+                } else {
+                    acc[r].x = __fadd_rn(acc[r].x, __fmul_rn(v.x, pw)); acc[r].y = __fadd_rn(acc[r].y, __fmul_rn(v.y, pw));
+                    acc[r].z = __fadd_rn(acc[r].z, __fmul_rn(v.z, pw)); acc[r].w = __fadd_rn(acc[r].w, __fmul_rn(v.w, pw));
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < AT_R; r++)
+            if (lane == r && r0 + r < a.n) *(float4 *) (a.out + (size_t) (r0 + r) * a.ld_out + (size_t) h * DK + cg * 4) = acc[r];
+    }
+}
+
 // fp16-table GELU as a stand-alone op (unit tests); the eval fuses it into the fc1 epilogue
 __global__ void k_gelu(const float * __restrict__ x, float * __restrict__ y, int n, const uint16_t * __restrict__ tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -100,7 +100,8 @@ def _oracle_attention(O, q, k, v, n_head):
 
 
 @pytest.mark.parametrize("cfg", [(64, 4, 1, 0), (64, 4, 3, 5), (256, 4, 1, 40), (256, 4, 2, 62), (1024, 16, 1, 97),
-                                 (1024, 16, 1, 31), (256, 2, 1, 200), (128, 4, 1, 35)])
+                                 (1024, 16, 1, 31), (256, 2, 1, 200), (128, 4, 1, 35),
+                                 (256, 4, 8, 40), (256, 4, 5, 27), (1024, 16, 16, 17), (256, 4, 19, 77), (256, 4, 33, 0)])
 def test_attention(checkers, capi, cfg):
     """un-masked attention: T = n_past + n below / at / above the 32-wide vector boundary, with a
     4-multiple tail and a <4 remainder; head dims 16, 32, 64, 128"""
