@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -75,6 +75,7 @@ def lib():
                                           C.POINTER(C.c_float)]
     L.bgpt_cuda_set_decode_path.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_get_decode_path.argtypes = [C.c_void_p]
+    L.bgpt_cuda_decode_kernel_generation.argtypes = [C.c_void_p]
     L.bgpt_cuda_debug_read_prof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bgpt_cuda_debug_barrier_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_debug_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -190,6 +191,11 @@ class Model:
     @property
     def decode_path(self) -> int:
         return int(lib().bgpt_cuda_get_decode_path(self.h))
+
+    @property
+    def decode_generation(self) -> int:
+        """4 / 3: persistent-kernel generation used for single-token steps; 0: per-operator kernels"""
+        return int(lib().bgpt_cuda_decode_kernel_generation(self.h))
 
     def read_prof(self):
         """[n_layer+1][5][3] clock64 stamps of CTA 0 (needs BGPT_MEGA_PROF=1 before load)"""

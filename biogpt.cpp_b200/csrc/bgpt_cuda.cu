@@ -15,6 +15,7 @@
 #include "../../include/bgpt_cuda.h"
 #include "bgpt_kernels.cuh"
 #include "bgpt_mega.cuh"
+#include "bgpt_mega4.cuh"
 #include "bgpt_barbench.cuh"
 #include "bgpt_tc.cuh"
 
@@ -97,6 +98,8 @@ struct bgpt_model {
     float * d_cand_val = nullptr; int * d_cand_idx = nullptr; int mega_grid = 0;
     long long * d_prof = nullptr; int prof_n = 0;
     uint8_t * d_rec_att = nullptr, * d_rec_hff = nullptr;
+    // generation-4 persistent kernel (bgpt_mega4.cuh): tagged-word exchange, no grid barrier
+    bool mega4_ok = false; M4Params m4{}; unsigned long long * d_xch = nullptr; unsigned int m4_tag = 0;
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -182,7 +185,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     for (auto & kv : m->tensors) cudaFree(kv.second.ptr);
     free_arena(m);
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
-    cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx);
+    cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
@@ -286,6 +289,7 @@ static void init_kernel_attrs() {
 }
 
 static int mega_setup(bgpt_model * m);
+static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop);
 
 extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (!m) return fail(BGPT_E_ARG, "finalize: NULL model");
@@ -631,12 +635,84 @@ static int mega_setup(bgpt_model * m) {
     m->mega_ok = coop != 0;
     const char * e = getenv("BGPT_DECODE_PATH");
     if (e) m->decode_path = atoi(e);
+    if (m->mega_ok) RET(mega4_setup(m, prop));
+    return BGPT_OK;
+}
+
+// generation 4: quantised weights at BioGPT-base shapes only (everything else stays on k_mega)
+static const void * mega4_fn(int wtype) {
+    switch (wtype) {
+        case BG_Q4_0: return (const void *) k_mega4<BG_Q4_0>;
+        case BG_Q4_1: return (const void *) k_mega4<BG_Q4_1>;
+        case BG_Q5_0: return (const void *) k_mega4<BG_Q5_0>;
+        case BG_Q5_1: return (const void *) k_mega4<BG_Q5_1>;
+        case BG_Q8_0: return (const void *) k_mega4<BG_Q8_0>;
+    }
+    return nullptr;
+}
+static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop) {
+    m->mega4_ok = false;
+    const void * fn = mega4_fn(m->wtype);
+    const int nC = m->mega_grid;
+    if (!fn || m->d_model != M4_D || m->d_ff != M4_FF || m->n_head != M4_NH || m->n_positions > 1024 || nC < M4_NB_F) return BGPT_OK;
+    const int qkv_max = (3 * M4_D + nC - 1) / nC, o_max = (M4_D + nC - 1) / nC;
+    if (qkv_max * 8 > M4_NT || qkv_max > 32) return BGPT_OK;
+    M4Params & P = m->m4;
+    P.b = m->mp;
+    auto al = [](int x) { return (x + 127) & ~127; };
+    const int sd = P.b.stride_d, sf = P.b.stride_f;
+    P.slot_bytes = al(std::max(std::max(32 * sd, o_max * sf), std::max(qkv_max, M4_LMRT) * sd));
+    const int PSd = 4 * P.b.Gd + 4, PSf = 4 * P.b.Gf + 4;
+    const int p_bytes = al(4 * std::max(32 * 8 * PSd, o_max * 8 * PSf));
+    const int s_bytes = al(4 * std::max(32 * 4 * P.b.Gd, o_max * 4 * P.b.Gf));
+    const int fixed = 2 * al(P.b.actb_f) + p_bytes + 2 * s_bytes + 2 * al(M4_D * 4) + al(m->n_positions * 4) + al(32 * 32 * 4) + al(31 * 32 * 4);
+    P.nslot = M4_NSLOT;
+    while (P.nslot > 2 && (size_t) (P.nslot * P.slot_bytes + fixed + 1024) > (size_t) prop.sharedMemPerBlockOptin) P.nslot--;
+    int o = 0;
+    P.sm_w = o; o += P.nslot * P.slot_bytes;
+    P.sm_act0 = o; o += al(P.b.actb_f);
+    P.sm_act1 = o; o += al(P.b.actb_f);
+    P.sm_p = o; o += p_bytes;
+    P.sm_s = o; o += s_bytes;
+    P.sm_m = o; o += s_bytes;
+    P.sm_x = o; o += al(M4_D * 4);
+    P.sm_x1 = o; o += al(M4_D * 4);
+    P.sm_sc = o; o += al(m->n_positions * 4);
+    P.sm_red = o; o += al(32 * 32 * 4);
+    P.sm_tail = o; o += al(31 * 32 * 4);
+    P.sm_total = o;
+    if ((size_t) P.sm_total + 1024 > (size_t) prop.sharedMemPerBlockOptin) return BGPT_OK;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sm_total));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, M4_NT, P.sm_total));
+    if (occ < 1 || nC > prop.multiProcessorCount * occ) return BGPT_OK;
+    const size_t xb = (size_t) m->n_layer * M4_LW * sizeof(unsigned long long);
+    CK(cudaMalloc(&m->d_xch, xb)); CK(cudaMemset(m->d_xch, 0, xb));
+    P.xch = m->d_xch;
+    P.prof_cta = nC - 1;
+    if (getenv("BGPT_MEGA_PROF_CTA")) P.prof_cta = atoi(getenv("BGPT_MEGA_PROF_CTA"));
+    m->m4_tag = 0;
+    const char * e3 = getenv("BGPT_MEGA_V");
+    m->mega4_ok = !(e3 && atoi(e3) == 3);
     return BGPT_OK;
 }
 
 // one token at n_past on the persistent kernel.  token source: d_tok (device) or the previous
 // launch's argmax candidates (use_cand).  Asynchronous on the model's stream.
 static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot) {
+    if (m->mega4_ok && m->decode_path == 1) {
+        M4Params P = m->m4;
+        MegaParams & q = P.b;
+        q.kcache = m->kcache; q.vcache = m->vcache; q.logits = m->logits;
+        q.x = m->x; q.x1 = m->x1; q.q = m->q; q.att = m->att; q.hff = m->hff;
+        q.tok = d_tok; q.use_cand = use_cand; q.idlog = m->d_idlog; q.log_slot = log_slot; q.n_past = n_past;
+        if (++m->m4_tag == 0) m->m4_tag = 1;                 // 0 is the "never written" tag of a fresh buffer
+        P.tag = m->m4_tag;
+        void * args[] = { &P };
+        CK(cudaLaunchCooperativeKernel(mega4_fn(m->wtype), dim3(m->mega_grid), dim3(M4_NT), args, (size_t) P.sm_total, m->stream));
+        m->launches++;
+        return BGPT_OK;
+    }
     MegaParams p = m->mp;
     p.kcache = m->kcache; p.vcache = m->vcache;
     p.x = m->x; p.x1 = m->x1; p.q = m->q; p.att = m->att; p.hff = m->hff; p.logits = m->logits;
@@ -649,11 +725,11 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
     m->launches++;
     return BGPT_OK;
 }
-static bool use_mega(const bgpt_model * m) { return m->mega_ok && m->decode_path == 1 && !m->taps_armed; }
+static bool use_mega(const bgpt_model * m) { return m->mega_ok && m->decode_path >= 1 && !m->taps_armed; }
 
 extern "C" int bgpt_cuda_set_decode_path(bgpt_model * m, int path) {
-    if (!m || (path != 0 && path != 1)) return fail(BGPT_E_ARG, "set_decode_path: path must be 0 (per-op kernels) or 1 (persistent kernel)");
-    if (path == 1 && !m->mega_ok) return fail(BGPT_E_UNSUPPORTED, "set_decode_path: the persistent kernel is not available for this model/device");
+    if (!m || path < 0 || path > 2) return fail(BGPT_E_ARG, "set_decode_path: path must be 0 (per-op kernels), 1 (persistent kernel) or 2 (persistent kernel with grid barriers)");
+    if (path >= 1 && !m->mega_ok) return fail(BGPT_E_UNSUPPORTED, "set_decode_path: the persistent kernel is not available for this model/device");
     m->decode_path = path;
     return BGPT_OK;
 }
@@ -666,7 +742,11 @@ extern "C" int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int ca
     if (cudaMemcpy(out, m->d_prof, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
 }
-extern "C" int bgpt_cuda_get_decode_path(const bgpt_model * m) { return m && m->mega_ok && m->decode_path == 1 ? 1 : 0; }
+extern "C" int bgpt_cuda_get_decode_path(const bgpt_model * m) { return m && m->mega_ok && m->decode_path >= 1 ? m->decode_path : 0; }
+extern "C" int bgpt_cuda_decode_kernel_generation(const bgpt_model * m) {
+    if (!m || !m->mega_ok || m->decode_path < 1) return 0;
+    return (m->mega4_ok && m->decode_path == 1) ? 4 : 3;
+}
 
 static int check_eval_args(bgpt_model * m, int n, int n_past, int rows_of_stream) {
     if (!m) return fail(BGPT_E_ARG, "eval: NULL model");

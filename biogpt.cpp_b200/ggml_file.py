@@ -69,6 +69,9 @@ class HParams:
 BASE = HParams()
 TINY = HParams(n_vocab=256, n_layer=2, n_head=4, n_positions=64, d_ff=128, d_model=64)
 SMALL = HParams(n_vocab=1000, n_layer=3, n_head=4, n_positions=256, d_ff=1024, d_model=256)
+# BioGPT-base layer shapes (what the generation-4 persistent kernel is specialised for) with few
+# layers and a small vocabulary, so the oracle walks the whole 1024-position context in seconds
+NARROW = HParams(n_vocab=3001, n_layer=2, n_head=16, n_positions=1024, d_ff=4096, d_model=1024)
 
 
 # --------------------------------------------------------------------------------------

@@ -107,10 +107,14 @@ int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int
                             int32_t * ids_out, float * ms_out);
 
 /* Which schedule evaluates single-token steps (n == 1): 1 = one persistent kernel per token
- * (default when available), 0 = one kernel per fused operator (the schedule used for n > 1 and
- * for lock-step streams).  Both produce identical bits; tests compare them. */
+ * (default when available: generation 4 -- tagged-word exchange, csrc/bgpt_mega4.cuh -- for
+ * quantised weights at BioGPT-base shapes, else generation 3), 2 = the generation-3 persistent
+ * kernel with grid barriers (csrc/bgpt_mega.cuh), 0 = one kernel per fused operator (the schedule
+ * used for n > 1 and for lock-step streams).  All produce identical bits; tests compare them. */
 int bgpt_cuda_set_decode_path(bgpt_model * m, int path);
 int bgpt_cuda_get_decode_path(const bgpt_model * m);
+/* 4 or 3: the persistent-kernel generation single-token steps run on; 0: per-operator kernels */
+int bgpt_cuda_decode_kernel_generation(const bgpt_model * m);
 /* debug (env BGPT_MEGA_PROF=1 at load): per-phase clock64 stamps of CTA 0 of the last
  * persistent-kernel launch; returns the number of entries copied (0 when profiling is off). */
 int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);

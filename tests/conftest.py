@@ -54,7 +54,7 @@ class ModelZoo:
 
     def tensors(self, size: str):
         if size not in self._tensors:
-            hp = {"tiny": gf.TINY, "small": gf.SMALL, "base": gf.BASE}[size]
+            hp = {"tiny": gf.TINY, "small": gf.SMALL, "base": gf.BASE, "narrow": gf.NARROW}[size]
             if size == "tiny":
                 self._tensors[size] = golden_tiny_tensors()
             else:
@@ -64,7 +64,7 @@ class ModelZoo:
     def path(self, size: str, ftype: str) -> str:
         p = os.path.join(self.root, f"{size}-{ftype}.bin")
         if not os.path.exists(p):
-            hp = {"tiny": gf.TINY, "small": gf.SMALL, "base": gf.BASE}[size]
+            hp = {"tiny": gf.TINY, "small": gf.SMALL, "base": gf.BASE, "narrow": gf.NARROW}[size]
             gf.write_model(p, hp, self.tensors(size), gf.FTYPE_BY_NAME[ftype])
         return p
 

@@ -135,6 +135,48 @@ def test_persistent_kernel_equals_oracle_and_per_op_path(checkers, capi, zoo, si
     O.close(); M.close()
 
 
+@pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_generation4_kernel_equals_oracle_and_generation3(checkers, capi, zoo, ftype):
+    """BioGPT-base layer shapes: single-token steps run on the generation-4 persistent kernel
+    (tagged-word exchange, TMA weight ring).  Bits must equal the oracle's and the generation-3
+    kernel's at every position class: T = 1, the 32-wide boundary and both scalar tails, the
+    second K pass (T > 512) and the end of the context; the vocabulary (3001 rows) leaves ragged
+    lm_head tiles."""
+    hp = gf.NARROW
+    p = zoo.path("narrow", ftype)
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p, max_batch=64)
+    assert M.decode_generation == 4, "generation-4 kernel not selected: " + capi.last_error()
+    toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=77)
+    windows = [(0, 70), (500, 531), (990, 1024)]
+    pos = 0
+    got4 = {}
+    for lo, hi in windows:
+        while pos < lo:                                   # fill the cache with un-masked prompt batches (per-op kernels)
+            n = min(16, lo - pos)                          # <= 16 rows: the exact SIMT matmul path
+            want = O.eval(toks[pos:pos + n], pos); got = M.eval(toks[pos:pos + n], pos)
+            assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} prompt at {pos}", got, want)
+            pos += n
+        for i in range(lo, hi):
+            want = O.eval(toks[i:i + 1], i)
+            got = M.eval(toks[i:i + 1], i)
+            assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} generation 4 at n_past={i}", got, want)
+            got4[i] = got
+        pos = hi
+    M.set_decode_path(2)
+    assert M.decode_generation == 3
+    for lo, hi in windows:
+        for i in range(lo, hi):                           # the cache rows are already there: same evals again
+            got = M.eval(toks[i:i + 1], i)
+            assert np.array_equal(_bits(got), _bits(got4[i])), (ftype, i)
+    M.set_decode_path(1)
+    ids4, _ = M.decode_greedy(int(toks[0]), 0, 40)
+    M.set_decode_path(2)
+    ids3, _ = M.decode_greedy(int(toks[0]), 0, 40)
+    assert ids4.tolist() == ids3.tolist()
+    O.close(); M.close()
+
+
 def test_persistent_kernel_long_context(checkers, capi, zoo):
     """prompt in un-masked batches of 8 (per-op kernels), then persistent-kernel decode near the end
     of the context"""
