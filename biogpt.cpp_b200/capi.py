@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_icache_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -77,6 +77,8 @@ def lib():
     L.bgpt_cuda_get_decode_path.argtypes = [C.c_void_p]
     L.bgpt_cuda_decode_kernel_generation.argtypes = [C.c_void_p]
     L.bgpt_cuda_debug_read_prof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.bgpt_cuda_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.bgpt_cuda_debug_icache_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_debug_barrier_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_debug_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
@@ -202,6 +204,16 @@ class Model:
         buf = np.zeros(4096, dtype=np.int64)
         n = lib().bgpt_cuda_debug_read_prof(self.h, buf.ctypes.data, buf.size)
         return buf[:n].reshape(-1, 5, 6) if n else None
+
+    def read_trace(self):
+        """generation-4 kernel: (stamps [n_cta][n_layer+1][5][12] clock64, calib [n_cta][4]) or None"""
+        buf = np.zeros(1 << 20, dtype=np.int64)
+        nc, per = C.c_int(0), C.c_int(0)
+        n = lib().bgpt_cuda_debug_read_trace(self.h, buf.ctypes.data, buf.size, C.byref(nc), C.byref(per))
+        if not n:
+            return None
+        nc, per = nc.value, per.value
+        return buf[:nc * per].reshape(nc, -1, 5, 12), buf[nc * per:nc * per + 4 * nc].reshape(nc, 4)
 
     def set_streams(self, n: int):
         _check(lib().bgpt_cuda_set_streams(self.h, n), "set_streams")

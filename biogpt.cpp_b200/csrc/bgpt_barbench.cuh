@@ -66,3 +66,111 @@ __global__ void __launch_bounds__(512, 1) k_barbench(unsigned long long * w, int
     }
     if (threadIdx.x == 0 && sink) sink[blockIdx.x] = acc;
 }
+
+// ---- exchange variants (generation-4 kernel): tagged 8-byte words, R replicas, every thread polls its own 2 words -------
+// LD: 0 ld.volatile, 1 ld.relaxed.gpu, 2 ld.acquire.gpu.  PT: polling threads per CTA (512, 256 or 128; a thread polls 1024/PT words)
+template <int LD>
+__device__ __forceinline__ void bx_ld2(const unsigned long long * p, unsigned long long & w0, unsigned long long & w1) {
+    if (LD == 0)      asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    else if (LD == 1) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    else if (LD == 2) asm volatile("ld.acquire.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    else              asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+// packed exchange: a CTA's 8 rows travel as three 16-byte units {3 x f32, tag} (the last holds 2), one st.v4 each per replica;
+// 342 threads poll one unit each
+template <int R>
+__global__ void __launch_bounds__(512, 1) k_xchpack(unsigned long long * wq, int iters, float * sink, int sleep_ns) {
+    const unsigned c = blockIdx.x;
+    const bool owner_cta = c < 128;                       // 128 producers x 8 rows
+    uint4 * w = (uint4 *) wq;
+    const int rep = c % R;
+    unsigned acc = 0;
+    __shared__ float s_out[8];
+    for (int i = 1; i <= iters; i++) {
+        uint4 * X = w + (size_t) (i & 1) * (R * 384);     // 384 units (3 per producer) per replica
+        if (owner_cta) {
+            if ((threadIdx.x & 31) == 28 && (threadIdx.x >> 5) < 8) s_out[threadIdx.x >> 5] = (float) (acc & 0xff);
+            __syncthreads();
+            if (threadIdx.x < 3 * R) {
+                const int u = threadIdx.x % 3, r = threadIdx.x / 3;
+                uint4 v; v.x = __float_as_uint(s_out[3 * u]); v.y = __float_as_uint(s_out[3 * u + 1]); v.z = u < 2 ? __float_as_uint(s_out[3 * u + 2]) : 0u; v.w = (unsigned) i;
+                asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(X + (size_t) r * 384 + c * 3 + u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        }
+        if (threadIdx.x < 384) {
+            const uint4 * src = X + (size_t) rep * 384 + threadIdx.x;
+            uint4 v;
+            for (;;) {
+                asm volatile("ld.volatile.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+                if (v.w == (unsigned) i) break;
+                if (sleep_ns) __nanosleep(sleep_ns);
+            }
+            acc += v.x + v.y;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sink) sink[blockIdx.x] = (float) acc;
+}
+template <int LD, int R, int PT>
+__global__ void __launch_bounds__(512, 1) k_xchbench(unsigned long long * w, int iters, float * sink, int sleep_ns) {
+    const unsigned nC = gridDim.x, c = blockIdx.x;
+    const int o0 = (int) ((c * 1024u) / nC), o1 = (int) (((c + 1u) * 1024u) / nC);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rep = c % R;
+    unsigned acc = 0;
+    for (int i = 1; i <= iters; i++) {
+        unsigned long long * X = w + (size_t) (i & 1) * (R * 1024);           // two generations of buffers
+        if (lane == 28 && warp < o1 - o0) {
+            const unsigned long long v = ((unsigned long long) (unsigned) i << 32) | (acc & 0xffffu);
+#pragma unroll
+            for (int r = 0; r < R; r++) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(X + (size_t) r * 1024 + o0 + warp), "l"(v) : "memory");
+        }
+        if ((int) threadIdx.x < PT) {
+#pragma unroll
+            for (int k = 0; k < 512 / PT; k++) {
+                const unsigned long long * src = X + (size_t) rep * 1024 + 2 * (threadIdx.x + k * PT);
+                unsigned long long w0, w1;
+                for (;;) {
+                    bx_ld2<LD>(src, w0, w1);
+                    if ((unsigned) (w0 >> 32) == (unsigned) i && (unsigned) (w1 >> 32) == (unsigned) i) break;
+                    if (sleep_ns) __nanosleep(sleep_ns);
+                }
+                acc += (unsigned) w0 + (unsigned) w1;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sink) sink[blockIdx.x] = (float) acc;
+}
+// ping-pong between CTA 0 and CTA `peer`: one word each way per iteration, one polling thread; time per iteration = 2 one-way latencies
+template <int LD>
+__global__ void __launch_bounds__(512, 1) k_pingpong(unsigned long long * w, int iters, float * sink, int peer) {
+    if (threadIdx.x != 0 || (blockIdx.x != 0 && (int) blockIdx.x != peer)) return;
+    const bool first = blockIdx.x == 0;
+    unsigned long long * mine = w + (first ? 0 : 64), * theirs = w + (first ? 64 : 0);
+    for (int i = 1; i <= iters; i++) {
+        unsigned long long w0, w1;
+        if (first) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(mine), "l"((unsigned long long) i) : "memory");
+        do { bx_ld2<LD>(theirs, w0, w1); } while (w0 != (unsigned long long) i);
+        if (!first) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(mine), "l"((unsigned long long) i) : "memory");
+    }
+    if (sink) sink[blockIdx.x] = 1.0f;
+}
+
+// ---- instruction-cache probe: a loop whose body is KB kilobytes of straight-line FFMA code, every SM in step ----
+template <int KB>
+__global__ void __launch_bounds__(512, 1) k_icbench(unsigned long long * w, int iters, float * sink, int nwarps) {
+    float a = threadIdx.x, b = 1.0f, c = 2.0f, d = 3.0f;
+    const float m = sink ? 1.0001f : 0.f;
+    long long t0 = 0;
+    if ((int) (threadIdx.x >> 5) < nwarps) {
+        for (int i = 0; i < iters; i++) {
+            if (i == 1) t0 = clock64();
+#pragma unroll
+            for (int k = 0; k < KB * 16; k++) { a = fmaf(a, m, b); b = fmaf(b, m, c); c = fmaf(c, m, d); d = fmaf(d, m, a); }
+        }
+        const long long t1 = clock64();
+        if (threadIdx.x == 0) w[blockIdx.x] = (unsigned long long) (t1 - t0);
+    }
+    if (sink && a + b + c + d == 12345.f) sink[blockIdx.x] = a;
+}

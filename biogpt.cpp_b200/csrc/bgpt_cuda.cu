@@ -93,13 +93,14 @@ struct bgpt_model {
     // persistent decode kernel (bgpt_mega.cuh)
     bool tc_ok = true;                                   // tcgen05 batch matmul allowed (BGPT_TC=0 disables)
     bool mega_ok = false; int decode_path = 1;          // 1: k_mega for n == 1, 0: per-op kernels
-    MegaParams mp{}; MegaLayer * d_mega_layers = nullptr;
+    MegaParams mp{}; MegaLayer * d_mega_layers = nullptr; std::vector<MegaLayer> h_mega_layers;
     unsigned long long * d_bar = nullptr; unsigned long long bar_epoch = 0;
     float * d_cand_val = nullptr; int * d_cand_idx = nullptr; int mega_grid = 0;
     long long * d_prof = nullptr; int prof_n = 0;
     uint8_t * d_rec_att = nullptr, * d_rec_hff = nullptr;
     // generation-4 persistent kernel (bgpt_mega4.cuh): tagged-word exchange, no grid barrier
     bool mega4_ok = false; M4Params m4{}; unsigned long long * d_xch = nullptr; unsigned int m4_tag = 0;
+    long long * d_trace = nullptr; size_t trace_n = 0;
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -185,7 +186,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     for (auto & kv : m->tensors) cudaFree(kv.second.ptr);
     free_arena(m);
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
-    cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch);
+    cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch); cudaFree(m->d_trace);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
@@ -574,7 +575,7 @@ static int mega_setup(bgpt_model * m) {
     p.actb_d = m->A_d.bytes; p.offn_d = m->A_d.off_n; p.offdd_d = m->A_d.off_d; p.offs_d = m->A_d.off_s;
     p.actb_f = m->A_ff.bytes; p.offn_f = m->A_ff.off_n; p.offdd_f = m->A_ff.off_d; p.offs_f = m->A_ff.off_s;
     p.code_off = bg_code_offset(m->wtype);
-    std::vector<MegaLayer> hl(m->n_layer);
+    std::vector<MegaLayer> & hl = m->h_mega_layers; hl.assign(m->n_layer, MegaLayer{});
     for (int i = 0; i < m->n_layer; i++) {
         const LayerW & L = m->layers[i]; MegaLayer & o = hl[i];
         o.q_w = L.q_w->ptr; o.k_w = L.k_w->ptr; o.v_w = L.v_w->ptr; o.o_w = L.o_w->ptr; o.fc1_w = L.fc1_w->ptr; o.fc2_w = L.fc2_w->ptr;
@@ -640,25 +641,29 @@ static int mega_setup(bgpt_model * m) {
 }
 
 // generation 4: quantised weights at BioGPT-base shapes only (everything else stays on k_mega)
-static const void * mega4_fn(int wtype) {
+// prof: the instantiation with clock stamps (BGPT_MEGA_PROF); the production kernel carries none of that code --
+// the per-layer loop has to stay inside the SM's instruction cache (profiles/README.md)
+static const void * mega4_fn(int wtype, bool prof) {
     switch (wtype) {
-        case BG_Q4_0: return (const void *) k_mega4<BG_Q4_0>;
-        case BG_Q4_1: return (const void *) k_mega4<BG_Q4_1>;
-        case BG_Q5_0: return (const void *) k_mega4<BG_Q5_0>;
-        case BG_Q5_1: return (const void *) k_mega4<BG_Q5_1>;
-        case BG_Q8_0: return (const void *) k_mega4<BG_Q8_0>;
+        case BG_Q4_0: return prof ? (const void *) k_mega4<BG_Q4_0, true> : (const void *) k_mega4<BG_Q4_0, false>;
+        case BG_Q4_1: return prof ? (const void *) k_mega4<BG_Q4_1, true> : (const void *) k_mega4<BG_Q4_1, false>;
+        case BG_Q5_0: return prof ? (const void *) k_mega4<BG_Q5_0, true> : (const void *) k_mega4<BG_Q5_0, false>;
+        case BG_Q5_1: return prof ? (const void *) k_mega4<BG_Q5_1, true> : (const void *) k_mega4<BG_Q5_1, false>;
+        case BG_Q8_0: return prof ? (const void *) k_mega4<BG_Q8_0, true> : (const void *) k_mega4<BG_Q8_0, false>;
     }
     return nullptr;
 }
 static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     m->mega4_ok = false;
-    const void * fn = mega4_fn(m->wtype);
+    const void * fn = mega4_fn(m->wtype, m->d_prof != nullptr);
     const int nC = m->mega_grid;
-    if (!fn || m->d_model != M4_D || m->d_ff != M4_FF || m->n_head != M4_NH || m->n_positions > 1024 || nC < M4_NB_F) return BGPT_OK;
+    static_assert(sizeof(M4Params) <= 4096, "M4Params must fit the 4 KB kernel parameter space");
+    if (!fn || m->n_layer > M4_MAXL || m->d_model != M4_D || m->d_ff != M4_FF || m->n_head != M4_NH || m->n_positions > 1024 || nC < M4_NB_F) return BGPT_OK;
     const int qkv_max = (3 * M4_D + nC - 1) / nC, o_max = (M4_D + nC - 1) / nC;
     if (qkv_max * 8 > M4_NT || qkv_max > 32) return BGPT_OK;
     M4Params & P = m->m4;
     P.b = m->mp;
+    for (int i = 0; i < m->n_layer; i++) P.layers[i] = m->h_mega_layers[i];
     auto al = [](int x) { return (x + 127) & ~127; };
     const int sd = P.b.stride_d, sf = P.b.stride_f;
     P.slot_bytes = al(std::max(std::max(32 * sd, o_max * sf), std::max(qkv_max, M4_LMRT) * sd));
@@ -686,12 +691,19 @@ static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, M4_NT, P.sm_total));
     if (occ < 1 || nC > prop.multiProcessorCount * occ) return BGPT_OK;
-    const size_t xb = (size_t) m->n_layer * M4_LW * sizeof(unsigned long long);
+    const size_t xb = (size_t) 2 * M4_LW * sizeof(unsigned long long);
     CK(cudaMalloc(&m->d_xch, xb)); CK(cudaMemset(m->d_xch, 0, xb));
     P.xch = m->d_xch;
     P.prof_cta = nC - 1;
-    if (getenv("BGPT_MEGA_PROF_CTA")) P.prof_cta = atoi(getenv("BGPT_MEGA_PROF_CTA"));
+    if (getenv("BGPT_MEGA_PROF_CTA")) P.prof_cta = std::min(std::max(atoi(getenv("BGPT_MEGA_PROF_CTA")), 0), nC - 1);
+    P.trace = nullptr; P.prof_n = (m->n_layer + 1) * 5 * M4_PK;
+    if (m->d_prof) {
+        m->trace_n = (size_t) nC * P.prof_n + 4 * (size_t) nC;
+        CK(cudaMalloc(&m->d_trace, m->trace_n * sizeof(long long))); CK(cudaMemset(m->d_trace, 0, m->trace_n * sizeof(long long)));
+        P.trace = m->d_trace;
+    }
     m->m4_tag = 0;
+    P.poll_sleep = getenv("M4_POLL_SLEEP") ? (unsigned) atoi(getenv("M4_POLL_SLEEP")) : 0u;
     const char * e3 = getenv("BGPT_MEGA_V");
     m->mega4_ok = !(e3 && atoi(e3) == 3);
     return BGPT_OK;
@@ -706,10 +718,10 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
         q.kcache = m->kcache; q.vcache = m->vcache; q.logits = m->logits;
         q.x = m->x; q.x1 = m->x1; q.q = m->q; q.att = m->att; q.hff = m->hff;
         q.tok = d_tok; q.use_cand = use_cand; q.idlog = m->d_idlog; q.log_slot = log_slot; q.n_past = n_past;
-        if (++m->m4_tag == 0) m->m4_tag = 1;                 // 0 is the "never written" tag of a fresh buffer
-        P.tag = m->m4_tag;
+        if (++m->m4_tag >= (1u << 26)) m->m4_tag = 1;        // 0 is the "never written" tag of a fresh buffer
+        P.tag = m->m4_tag << 6;
         void * args[] = { &P };
-        CK(cudaLaunchCooperativeKernel(mega4_fn(m->wtype), dim3(m->mega_grid), dim3(M4_NT), args, (size_t) P.sm_total, m->stream));
+        CK(cudaLaunchCooperativeKernel(mega4_fn(m->wtype, m->d_trace != nullptr), dim3(m->mega_grid), dim3(M4_NT), args, (size_t) P.sm_total, m->stream));
         m->launches++;
         return BGPT_OK;
     }
@@ -739,8 +751,21 @@ extern "C" int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int ca
     if (!m || !m->d_prof) return 0;
     const int n = cap < m->prof_n ? cap : m->prof_n;
     cudaStreamSynchronize(m->stream);
-    if (cudaMemcpy(out, m->d_prof, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    const long long * src = m->d_prof;
+    if (m->mega4_ok && m->decode_path == 1) return 0;      // generation 4 records every CTA: bgpt_cuda_debug_read_trace
+    if (cudaMemcpy(out, src, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
+}
+// debug: generation-4 kernel, stamps of EVERY CTA: [n_cta][prof_n] then [n_cta][4] = {globaltimer ns, clock64} at the
+// start and at the end of the launch (clock64 is per SM; the pairs put all CTAs on one time axis)
+extern "C" int bgpt_cuda_debug_read_trace(bgpt_model * m, long long * out, int cap, int * n_cta, int * per_cta) {
+    if (!m || !m->d_trace || !out) return 0;
+    if ((size_t) cap < m->trace_n) return 0;
+    cudaStreamSynchronize(m->stream);
+    if (cudaMemcpy(out, m->d_trace, m->trace_n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (n_cta) *n_cta = m->mega_grid;
+    if (per_cta) *per_cta = m->m4.prof_n;
+    return (int) m->trace_n;
 }
 extern "C" int bgpt_cuda_get_decode_path(const bgpt_model * m) { return m && m->mega_ok && m->decode_path >= 1 ? m->decode_path : 0; }
 extern "C" int bgpt_cuda_decode_kernel_generation(const bgpt_model * m) {
@@ -1007,19 +1032,27 @@ extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, fl
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int grid = prop.multiProcessorCount;
     DevBuf w, sink, chase;
-    RET(w.alloc(4096 * 8)); RET(sink.alloc(grid * 4)); RET(chase.alloc(1024 * 4));
-    CK(cudaMemset(w.p, 0, 4096 * 8)); CK(cudaMemset(chase.p, 0, 1024 * 4));
-    const void * fns[7] = { (const void *) k_barbench<0>, (const void *) k_barbench<1>, (const void *) k_barbench<2>, (const void *) k_barbench<3>,
-                            (const void *) k_barbench<4>, (const void *) k_barbench<5>, (const void *) k_barbench<6> };
-    if (v < 0 || v > 6) return fail(BGPT_E_ARG, "barrier_bench: variant 0..6");
+    RET(w.alloc(65536 * 8)); RET(sink.alloc(grid * 4)); RET(chase.alloc(1024 * 4));
+    CK(cudaMemset(chase.p, 0, 1024 * 4));
+    const void * fns[] = { (const void *) k_barbench<0>, (const void *) k_barbench<1>, (const void *) k_barbench<2>, (const void *) k_barbench<3>,
+                           (const void *) k_barbench<4>, (const void *) k_barbench<5>, (const void *) k_barbench<6>,
+                           /* 7..*/ (const void *) k_xchbench<0, 8, 512>, (const void *) k_xchbench<1, 8, 512>, (const void *) k_xchbench<2, 8, 512>,
+                           /*10..*/ (const void *) k_xchbench<0, 1, 512>, (const void *) k_xchbench<0, 2, 512>, (const void *) k_xchbench<0, 8, 128>,
+                           /*13..*/ (const void *) k_xchbench<1, 1, 512>, (const void *) k_xchbench<1, 8, 128>,
+                           /*15..*/ (const void *) k_pingpong<0>, (const void *) k_pingpong<1>, (const void *) k_pingpong<2>,
+                           /*18..*/ (const void *) k_xchbench<0, 16, 512>, (const void *) k_xchbench<0, 32, 512>, (const void *) k_xchbench<3, 8, 512>,
+                           /*21..*/ (const void *) k_xchpack<8>, (const void *) k_xchpack<16>, (const void *) k_xchpack<1> };
+    const int nv = (int) (sizeof(fns) / sizeof(fns[0]));
+    if (v < 0 || v >= nv) return fail(BGPT_E_ARG, "barrier_bench: variant out of range");
     unsigned long long * wp = w.as<unsigned long long>(); float * sp = sink.as<float>(); const float * cp = with_load ? chase.as<float>() : nullptr;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
-        CK(cudaMemset(w.p, 0, 4096 * 8));
+        CK(cudaMemset(w.p, 0, 65536 * 8));
         void * args[] = { &wp, &iters, &sp, &cp };
+        void * xargs[] = { &wp, &iters, &sp, &with_load };       // exchange: with_load = nanosleep back-off; ping-pong: the peer CTA
         CK(cudaEventRecord(e0));
-        CK(cudaLaunchCooperativeKernel(fns[v], dim3(grid), dim3(512), args, 0, 0));
+        CK(cudaLaunchCooperativeKernel(fns[v], dim3(grid), dim3(512), v < 7 ? args : xargs, 0, 0));
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -1027,6 +1060,33 @@ extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, fl
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *us_per_barrier = best * 1000.f / iters;
+    return BGPT_OK;
+}
+
+// debug: cycles per iteration of a loop with `kb` KB of straight-line code, on every SM at once (median over CTAs)
+extern "C" int bgpt_cuda_debug_icache_bench(int kb, int iters, int nwarps, float * cycles_per_iter) {
+    RET(need_device());
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    const int grid = prop.multiProcessorCount;
+    DevBuf w, sink;
+    RET(w.alloc(grid * 8)); RET(sink.alloc(grid * 4));
+    const void * fn = nullptr;
+    switch (kb) {
+        case 4: fn = (const void *) k_icbench<4>; break;     case 8: fn = (const void *) k_icbench<8>; break;
+        case 12: fn = (const void *) k_icbench<12>; break;   case 16: fn = (const void *) k_icbench<16>; break;
+        case 24: fn = (const void *) k_icbench<24>; break;   case 32: fn = (const void *) k_icbench<32>; break;
+        case 48: fn = (const void *) k_icbench<48>; break;   case 64: fn = (const void *) k_icbench<64>; break;
+        case 96: fn = (const void *) k_icbench<96>; break;   case 128: fn = (const void *) k_icbench<128>; break;
+        default: return fail(BGPT_E_ARG, "icache_bench: kb in {4,8,12,16,24,32,48,64,96,128}");
+    }
+    unsigned long long * wp = w.as<unsigned long long>(); float * sp = sink.as<float>();
+    void * args[] = { &wp, &iters, &sp, &nwarps };
+    CK(cudaLaunchKernel(fn, dim3(grid), dim3(512), args, 0, 0));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> h(grid);
+    CK(cudaMemcpy(h.data(), w.p, grid * 8, cudaMemcpyDeviceToHost));
+    std::sort(h.begin(), h.end());
+    *cycles_per_iter = (float) h[grid / 2] / (float) (iters - 1);
     return BGPT_OK;
 }
 

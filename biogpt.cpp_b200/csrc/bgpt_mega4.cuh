@@ -62,12 +62,17 @@
 #define M4_E5 (M4_E4 + M4_R * M4_NB_F * 10)
 #define M4_LW (M4_E5 + M4_R * M4_D)
 
+#define M4_MAXL 24        // layer table travels in the kernel parameters (constant bank): no pointer chase, no L2 miss on the chain
 struct M4Params {
     MegaParams b;
-    unsigned long long * xch;      // [n_layer][M4_LW] tagged words
-    unsigned int tag;              // launch serial (never 0)
-    int prof_cta;                  // CTA whose phase stamps are recorded (BGPT_MEGA_PROF_CTA)
+    MegaLayer layers[M4_MAXL];
+    unsigned long long * xch;      // [2][M4_LW] tagged words (layer parity): 0.5 MB, always L2-resident
+    unsigned int tag;              // launch serial << 6 (never 0); a word's tag = tag | (layer + 1)
+    int prof_cta;                  // CTA whose phase stamps bgpt_cuda_debug_read_prof returns (BGPT_MEGA_PROF_CTA)
+    long long * trace;             // BGPT_MEGA_PROF: [nC][prof_n] clock64 stamps of every CTA, then [nC][4] clock calibration
+    int prof_n;
     int nslot, slot_bytes;
+    unsigned poll_sleep;           // nanosleep between unsuccessful polls (0: spin)
     int sm_w, sm_act0, sm_act1, sm_p, sm_s, sm_m, sm_x, sm_x1, sm_sc, sm_red, sm_tail, sm_total;
 };
 
@@ -81,11 +86,13 @@ __device__ __forceinline__ void m4_put_rep(unsigned long long * p, int rep_strid
     for (int r = 0; r < M4_R; r++) m4_put(p + (size_t) r * rep_stride, payload, tag);
 }
 // two consecutive words (16-byte aligned); spins until both carry the tag
-__device__ __forceinline__ void m4_poll2(const unsigned long long * p, uint32_t tag, uint32_t & a, uint32_t & b) {
+__device__ __forceinline__ void m4_poll2(const unsigned long long * p, uint32_t tag, uint32_t & a, uint32_t & b, unsigned sleep_ns) {
     unsigned long long w0, w1;
-    do {
+    for (;;) {
         asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-    } while ((uint32_t) (w0 >> 32) != tag || (uint32_t) (w1 >> 32) != tag);
+        if ((uint32_t) (w0 >> 32) == tag && (uint32_t) (w1 >> 32) == tag) break;
+        if (sleep_ns) __nanosleep(sleep_ns);
+    }
     a = (uint32_t) w0; b = (uint32_t) w1;
 }
 
@@ -97,9 +104,14 @@ __device__ __forceinline__ void m4_mbar_init(uint64_t * bar, uint32_t count) {
 __device__ __forceinline__ void m4_mbar_expect(uint64_t * bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(m4_s32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void m4_bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(m4_s32(dst)), "l"(src), "r"(bytes), "r"(m4_s32(bar)) : "memory");
+// weights are read once per token and the set (194+ MB) exceeds the L2: stream them evict-first so they do not push the
+// kernel's own instructions, the lookup tables, the KV prefetches and the exchange words out of the L2
+__device__ __forceinline__ uint64_t m4_policy_evict_first() {
+    uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+__device__ __forceinline__ void m4_bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(m4_s32(dst)), "l"(src), "r"(bytes), "r"(m4_s32(bar)), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void m4_mbar_wait(uint64_t * bar, uint32_t parity) {
     uint32_t done;
@@ -126,21 +138,28 @@ __device__ __forceinline__ double m4_tree16(const double * s) {
 // bg_row_to_record (ggml.c:11403-11420, 1166-1203, 1403-1450); the double sums are combined in a
 // different (parallel) order, which only matters when a double rounding lands on a float tie.
 // Ends WITHOUT a barrier: the caller synchronises before the record is read.
-template <int FMT>
+template <int FMT, bool PROF>
 __device__ __forceinline__ void m4_ln_quant(float v0, float v1, float2 lw, float2 lb, float eps,
-                                            double * sredA, double * sredB, uint8_t * rec, int off_d, int off_s) {
+                                            double * sredA, double * sredB, uint8_t * rec, int off_d, int off_s, long long * stamp) {
     constexpr bool Q81 = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mean, variance;
+    long long t4 = 0, t6 = 0, t7 = 0, t8 = 0;
     double s = m4_warp_sum_f64((double) v0 + (double) v1);
     if (lane == 0) sredA[warp] = s;
     __syncthreads();
-    const float mean = (float) (m4_tree16(sredA) * (1.0 / M4_D));
-    const float d0 = __fsub_rn(v0, mean), d1 = __fsub_rn(v1, mean);
-    double s2 = m4_warp_sum_f64((double) __fmul_rn(d0, d0) + (double) __fmul_rn(d1, d1));
+    if (PROF && stamp) t4 = clock64();
+    mean = (float) (m4_tree16(sredA) * (1.0 / M4_D));
+    const float e0 = __fsub_rn(v0, mean), e1 = __fsub_rn(v1, mean);
+    double s2 = m4_warp_sum_f64((double) __fmul_rn(e0, e0) + (double) __fmul_rn(e1, e1));
     if (lane == 0) sredB[warp] = s2;
+    if (PROF && stamp) t6 = clock64();
     __syncthreads();
-    const float variance = (float) (m4_tree16(sredB) * (1.0 / M4_D));
+    if (PROF && stamp) t7 = clock64();
+    variance = (float) (m4_tree16(sredB) * (1.0 / M4_D));
+    const float d0 = __fsub_rn(v0, mean), d1 = __fsub_rn(v1, mean);
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
+    if (PROF && stamp) t8 = clock64();
     const float y0 = __fadd_rn(__fmul_rn(lw.x, __fmul_rn(d0, scale)), lb.x);
     const float y1 = __fadd_rn(__fmul_rn(lw.y, __fmul_rn(d1, scale)), lb.y);
     // quantise: a 32-element block = 16 consecutive threads
@@ -168,6 +187,8 @@ __device__ __forceinline__ void m4_ln_quant(float v0, float v1, float2 lw, float
         stot += __shfl_xor_sync(FULLMASK, stot, 8);
         if ((tid & 15) == 0) { ((float *) (rec + off_d))[b] = d; ((float *) (rec + off_s))[b] = __fmul_rn(d, (float) stot); }
     } else if ((tid & 15) == 0) { ((float *) (rec + off_d))[b] = bg_h2f(bg_f2h(d)); ((float *) (rec + off_s))[b] = 0.0f; }
+    if (PROF && stamp && tid == 0) { stamp[4] = t4; stamp[6] = t6; stamp[7] = t7; stamp[8] = t8; }
+    if (PROF && stamp && tid == 256) stamp[11] = t6;
 }
 
 // ---- one finished 32-element block (f32 in shared memory) -> 10 exchange words, R replicas -----
@@ -382,9 +403,17 @@ __device__ __forceinline__ void m4_phase_a(const M4MM & D, const uint8_t * wt, i
     }
 }
 
-#define M4PROF(ph, k) do { if (p.prof && (int) blockIdx.x == P.prof_cta && threadIdx.x == 0) p.prof[(l * 5 + (ph)) * 6 + (k)] = clock64(); } while (0)
+#define M4_PK 12          // stamps per (layer, phase) in the trace
+#define M4PROF(ph, k) do { if (PROF && P.trace && threadIdx.x == 0) P.trace[(size_t) blockIdx.x * P.prof_n + (l * 5 + (ph)) * M4_PK + (k)] = clock64(); } while (0)
+// (globaltimer edge, clock64) pair: spins until the nanosecond timer ticks, so the pair is exact whatever its resolution
+__device__ __forceinline__ void m4_calibrate(long long * out) {
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1)); } while (g1 == g0);
+    out[0] = (long long) g1; out[1] = clock64();
+}
 
-template <int FMT>
+template <int FMT, bool PROF>
 __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Params P) {
     const MegaParams & p = P.b;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -397,7 +426,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
     __shared__ int s_tok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nC = gridDim.x, cta = blockIdx.x;
-    const uint32_t tag = P.tag;
+    const uint32_t tag0 = P.tag;
     uint8_t * s_w = smem + P.sm_w;
     float * s_p = (float *) (smem + P.sm_p);
     float * s_s = (float *) (smem + P.sm_s);
@@ -427,7 +456,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
         TileSrc t{nullptr, nullptr, 0u, 0u};
         if (n >= n_tiles) return t;
         if (n < n_lt) {
-            const MegaLayer & L = p.layers[n >> 2];
+            const MegaLayer & L = P.layers[n >> 2];
             const int k = n & 3;
             if (k == 0) {
                 const int m0 = qkv0 / M4_D, e0 = min(qkv1, (m0 + 1) * M4_D);
@@ -446,13 +475,14 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
         }
         return t;
     };
+    const uint64_t pol_w = m4_policy_evict_first();
     auto fire_tile = [&](int n, const TileSrc & t) {
         if (t.b0 + t.b1 == 0) return;
         const int slot = n % P.nslot;
         uint8_t * dst = s_w + (size_t) slot * P.slot_bytes;
         m4_mbar_expect(&mbar[slot], t.b0 + t.b1);
-        m4_bulk_g2s(dst, t.src0, t.b0, &mbar[slot]);
-        if (t.b1) m4_bulk_g2s(dst + t.b0, t.src1, t.b1, &mbar[slot]);
+        m4_bulk_g2s(dst, t.src0, t.b0, &mbar[slot], pol_w);
+        if (t.b1) m4_bulk_g2s(dst + t.b0, t.src1, t.b1, &mbar[slot], pol_w);
     };
     constexpr int ISSUER = M4_NT - 32;
     uint32_t wphase = 0;
@@ -481,7 +511,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
         }
         const int who = nC - 1 - cta;                              // 16 vectors of <= 16 KB, one CTA each
         if (who < 16) {
-            const float * const * vecs = (const float * const *) &p.layers[Ln].q_b;     // q_b .. fc2_b: 10 consecutive pointers
+            const float * const * vecs = (const float * const *) &P.layers[Ln].q_b;     // q_b .. fc2_b: 10 consecutive pointers
             if (who < 10) {
                 const unsigned bytes = (who == 8 ? M4_FF : M4_D) * 4u;                  // fc1_b is the 9th
 #pragma unroll 1
@@ -491,6 +521,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
         }
     };
     prefetch_layer(0);
+    if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) nC * P.prof_n + 4 * cta);
 
     // ---- input token: given, or argmax over the candidates the previous launch left
     if (tid < 32) {
@@ -534,8 +565,10 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
         const bool lm = tn >= n_lt;
         const int kind = lm ? 4 : (tn & 3);                        // 0 P1, 1 P3, 2 P4, 3 P5, 4 lm_head
         const int l = lm ? p.n_layer : (tn >> 2);
-        const MegaLayer & L = p.layers[lm ? 0 : l];
-        unsigned long long * X = P.xch + (size_t) (lm ? p.n_layer - 1 : l) * M4_LW;
+        const MegaLayer & L = P.layers[lm ? 0 : l];
+        const int lx = lm ? p.n_layer - 1 : l;                     // layer whose exchange buffer (parity) and tag this tile uses
+        unsigned long long * X = P.xch + (size_t) (lx & 1) * M4_LW;
+        const uint32_t tag = tag0 | (uint32_t) (lx + 1);
         float * kc = p.kcache + (size_t) (lm ? 0 : l) * p.n_positions * M4_D;
         float * vc = p.vcache + (size_t) (lm ? 0 : l) * p.n_positions * M4_D;
         const int phs = kind == 0 ? 0 : kind + 1;                  // profiling slot (1 = attention)
@@ -573,24 +606,28 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
             const float * lnb = kind == 0 ? L.ln0_b : (kind == 2 ? L.ln1_b : p.lnf_b);
             const float2 lw = *(const float2 *) (lnw + 2 * tid), lb = *(const float2 *) (lnb + 2 * tid);
             if (tn > 0) {
-                const unsigned long long * src = kind == 2 ? X + M4_E3 : (kind == 0 ? X - M4_LW + M4_E5 : X + M4_E5);
+                const unsigned long long * src = kind == 2 ? X + M4_E3 : (kind == 0 ? P.xch + (size_t) ((l - 1) & 1) * M4_LW + M4_E5 : X + M4_E5);
                 uint32_t a, b;
-                m4_poll2(src + (size_t) rep * M4_D + 2 * tid, tag, a, b);
+                m4_poll2(src + (size_t) rep * M4_D + 2 * tid, kind == 0 ? tag - 1 : tag, a, b, P.poll_sleep);
                 xa = __uint_as_float(a); xb = __uint_as_float(b);
             }
             M4PROF(phs, 3);
             *(float2 *) ((kind == 2 ? s_x1 : s_x) + 2 * tid) = make_float2(xa, xb);
-            if (rt > 0) m4_ln_quant<FMT>(xa, xb, lw, lb, p.eps, sredA, sredB, rec, D.off_dd, D.off_s);
+            if (rt > 0)
+                m4_ln_quant<FMT, PROF>(xa, xb, lw, lb, p.eps, sredA, sredB, rec, D.off_dd, D.off_s,
+                                       PROF && P.trace ? P.trace + (size_t) cta * P.prof_n + (l * 5 + (lm ? 0 : phs)) * M4_PK : nullptr);
+            if (!lm) M4PROF(phs, 5);
         } else if (kind != 4) {
             const int nb10 = (kind == 1 ? M4_NB_D : M4_NB_F) * 10;
             const unsigned long long * src = X + (kind == 1 ? M4_E2 : M4_E4) + (size_t) rep * nb10;
 #pragma unroll 1
             for (int i = tid; 2 * i < nb10; i += M4_NT) {
                 uint32_t a, b;
-                m4_poll2(src + 2 * i, tag, a, b);
+                m4_poll2(src + 2 * i, tag, a, b, P.poll_sleep);
                 m4_scatter_word(rec, D.off_dd, D.off_s, 2 * i, a);
                 m4_scatter_word(rec, D.off_dd, D.off_s, 2 * i + 1, b);
             }
+            M4PROF(phs, 3);
         }
         // ---- matmul over the tile
         float dot0 = 0.f, dot1 = 0.f;
@@ -601,6 +638,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
             wphase ^= 1u << slot;
             wt = s_w + (size_t) slot * P.slot_bytes;
         }
+        if (!lm && (kind & 1)) M4PROF(phs, 5);
         __syncthreads();                                           // record complete; previous tile's shared scratch free
         if (tid == ISSUER) fire_tile(tn - 1 + P.nslot, nxt);
         M4PROF(lm ? 0 : phs, 1);
@@ -609,15 +647,18 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
                 if (warp < rt) {
                     M4Act A;
                     m4_load_act<FMT>(A, rec, D, p.code_off, lane >> 2, lane & 3);
+                    if (!lm) M4PROF(phs, 9);
                     const float2 dd = m4_two_rows<FMT>(wt, warp, warp + M4_NW < rt ? warp + M4_NW : warp, D, A);
                     dot0 = dd.x; dot1 = dd.y;
                 }
             } else {
                 m4_phase_a<FMT>(D, wt, rt, rec, p.code_off, s_p, s_s, s_m);
                 __syncthreads();
+                M4PROF(phs, 4);
                 dot0 = m4_phase_b<FMT>(D, rt, rec, s_p, s_s, s_m);
             }
         }
+        if (!lm) M4PROF(phs, 10);
         // ---- epilogue of the row owners
 #pragma unroll 1
         for (int e = 0; e < 2; e++) {
@@ -663,7 +704,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
             if (tid < 80) {          // q (64 words), k (64), v half (32) of this head
                 const int w = 2 * tid;
                 const unsigned long long * src = X + M4_E1 + (w < 64 ? att_h * M4_DK + w : (w < 128 ? M4_D + att_h * M4_DK + (w - 64) : 2 * M4_D + att_h * M4_DK + c0 + (w - 128)));
-                uint32_t a, b; m4_poll2(src, tag, a, b);
+                uint32_t a, b; m4_poll2(src, tag, a, b, P.poll_sleep);
                 float * dstp = w < 64 ? s_q + w : (w < 128 ? s_kn + (w - 64) : s_vn + (w - 128));
                 dstp[0] = __uint_as_float(a); dstp[1] = __uint_as_float(b);
             }
@@ -809,4 +850,5 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
         p.cand_val[cta] = best; p.cand_idx[cta] = bi;
     }
     { const int l = p.n_layer; M4PROF(0, 2); }
+    if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) nC * P.prof_n + 4 * cta + 2);
 }

@@ -118,8 +118,13 @@ int bgpt_cuda_decode_kernel_generation(const bgpt_model * m);
 /* debug (env BGPT_MEGA_PROF=1 at load): per-phase clock64 stamps of CTA 0 of the last
  * persistent-kernel launch; returns the number of entries copied (0 when profiling is off). */
 int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);
+/* debug, generation-4 kernel: the stamps of every CTA, [n_cta][per_cta], followed by [n_cta][4] =
+ * {globaltimer ns, clock64} pairs taken at the start and the end of the launch, which put the
+ * per-SM clocks on one time axis.  Returns the number of entries copied (0: off / cap too small). */
+int bgpt_cuda_debug_read_trace(bgpt_model * m, long long * out, int cap, int * n_cta, int * per_cta);
 /* debug: microseconds per grid-wide barrier for the candidate implementations in
  * csrc/bgpt_barbench.cuh (one CTA per SM, `iters` back-to-back barriers). */
+int bgpt_cuda_debug_icache_bench(int kb, int iters, int nwarps, float * cycles_per_iter);
 int bgpt_cuda_debug_barrier_bench(int variant, int iters, int with_load, float * us_per_barrier);
 /* debug: milliseconds per matmul y[n][rows] = W[rows][k].x[n][k] (synthetic data, device
  * resident, `iters` back-to-back launches); path 0 = exact-order SIMT kernels, 1 = tcgen05. */

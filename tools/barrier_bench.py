@@ -13,3 +13,23 @@ for v, n in enumerate(names):
         us = C.c_float(0)
         rc = capi.lib().bgpt_cuda_debug_barrier_bench(v, 2000, wl, C.byref(us))
         print(f"variant {v} ({n}){' + dependent L2 load' if wl else ''}: {us.value:.3f} us/barrier" if rc == 0 else capi.last_error())
+
+xn = ["exchange: ld.volatile, 8 replicas, 512 pollers (generation-4 kernel)", "exchange: ld.relaxed.gpu, 8 replicas, 512 pollers", "exchange: ld.acquire.gpu, 8 replicas, 512 pollers",
+      "exchange: ld.volatile, 1 replica", "exchange: ld.volatile, 2 replicas", "exchange: ld.volatile, 8 replicas, 128 pollers x 4", "exchange: ld.relaxed.gpu, 1 replica",
+      "exchange: ld.relaxed.gpu, 8 replicas, 128 pollers x 4"]
+for i, n in enumerate(xn):
+    for sl in (0, 100):
+        us = C.c_float(0)
+        rc = capi.lib().bgpt_cuda_debug_barrier_bench(7 + i, 2000, sl, C.byref(us))
+        print(f"variant {7 + i} ({n}){', nanosleep(100) back-off' if sl else ''}: {us.value:.3f} us/exchange" if rc == 0 else capi.last_error())
+for i, n in enumerate(["ld.volatile", "ld.relaxed.gpu", "ld.acquire.gpu"]):
+    for peer in (1, 2, 75, 147):
+        us = C.c_float(0)
+        rc = capi.lib().bgpt_cuda_debug_barrier_bench(15 + i, 2000, peer, C.byref(us))
+        print(f"ping-pong CTA 0 <-> CTA {peer} ({n}): {us.value * 500:.0f} ns one way" if rc == 0 else capi.last_error())
+
+for v, n in [(18, "exchange: ld.volatile, 16 replicas"), (19, "exchange: ld.volatile, 32 replicas"), (20, "exchange: ld.global.cg, 8 replicas"),
+             (21, "packed exchange {3 x f32, tag} 16-byte units, 8 replicas, 384 pollers"), (22, "packed exchange, 16 replicas"), (23, "packed exchange, 1 replica")]:
+    us = C.c_float(0)
+    rc = capi.lib().bgpt_cuda_debug_barrier_bench(v, 2000, 0, C.byref(us))
+    print(f"variant {v} ({n}): {us.value:.3f} us/exchange" if rc == 0 else capi.last_error())

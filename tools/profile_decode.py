@@ -41,24 +41,6 @@ if prof is not None:
     print("  LN1 prologue split (cycles): x1 load %.0f | LayerNorm %.0f | quantise %.0f" % (
         (P[:, 3, 3] - P[:, 3, 0]).mean(), (P[:, 3, 4] - P[:, 3, 3]).mean(), (P[:, 3, 1] - P[:, 3, 4]).mean()))
     print(f"  layer total {(nxt[:, 4] - P[:, 0, 0]).mean():9.0f} cycles;  lm_head: prologue {prof[L,0,1]-prof[L,0,0]} matmul {prof[L,0,2]-prof[L,0,1]}; whole kernel {prof[L,0,2]-prof[0,0,0]}")
-    if M.decode_generation == 4:
-        # generation 4 timeline of the profiled CTA (BGPT_MEGA_PROF_CTA): cycles since the layer's start, mean over layers
-        lab = {(0, 0): "P1 start", (0, 3): "P1 x polled", (0, 1): "P1 record+weights ready", (0, 2): "P1 published",
-               (1, 3): "att q,k,v polled", (1, 4): "att softmax done", (1, 2): "att published",
-               (2, 0): "P3 start", (2, 1): "P3 record+weights ready", (2, 2): "P3 published",
-               (3, 0): "P4 start", (3, 3): "P4 x1 polled", (3, 1): "P4 record+weights ready", (3, 2): "P4 published",
-               (4, 0): "P5 start", (4, 1): "P5 record+weights ready", (4, 2): "P5 published"}
-        ev = []
-        for (ph, k), nme in lab.items():
-            col = P[1:, ph, k] - P[1:, 0, 0]
-            if np.all(P[1:, ph, k] > 0): ev.append((col.mean(), nme))
-        ev.sort()
-        prev = 0.0
-        print("  generation-4 timeline (cycles since layer start | delta):")
-        for t, nme in ev:
-            print(f"    {t:9.0f} {t - prev:8.0f}  {nme}")
-            prev = t
-        print(f"    layer period {(P[2:, 0, 0] - P[1:-1, 0, 0]).mean():9.0f} cycles")
     if os.environ.get("M4_EXP"):
         for i, nme in enumerate(names):
             if i == 1: continue
