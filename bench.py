@@ -287,18 +287,21 @@ def main():
     achieved = total_bytes / (step_ms / 1e3) / 1e9
     traffic = None
     try:   # dram__bytes_read+write of one k_mega launch from the committed ncu capture (profiles/)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_mega_ncu_summary.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_mega4_ncu_summary.json")))
         if prof.get("ftype") == args.ftype:
             traffic = {"bytes_per_launch": prof["dram_bytes_per_launch"], "at_n_past": prof["n_past"],
                        "algorithmic_bytes_at_that_n_past": bytes_per_token(args.ftype, prof["n_past"]), "source": prof["source"]}
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": f"k_mega<{args.ftype}> (persistent decode kernel, 1 launch per token; mean over n_past 0..{seq - 1})",
+    gen = M.decode_generation
+    kname = {4: "k_mega4", 3: "k_mega"}.get(gen, "per-operator kernels")
+    roofline = {"bound": "hbm", "kernel": f"{kname}<{args.ftype}> (persistent decode kernel, generation {gen}, 1 launch per token; mean over n_past 0..{seq - 1})",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                 "algorithmic_bytes_per_launch_mean": total_bytes / seq,
                 "us_per_launch_mean": step_ms * 1e3 / seq,
-                "note": "latency-bound: 5 grid barriers + ~25 dependent L2 round trips per layer (DESIGN.md 4.2)"}
+                "note": "latency-bound: a batch-1 step is a chain of 5 all-to-all exchanges per layer through L2 (~1 us each) plus "
+                        "LayerNorm / dot / softmax latencies between them (profiles/README.md, DESIGN.md 4.2); bytes are not the limit"}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_icache_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_icache_bench", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_debug_quantize_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -78,6 +78,8 @@ def lib():
     L.bgpt_cuda_decode_kernel_generation.argtypes = [C.c_void_p]
     L.bgpt_cuda_debug_read_prof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bgpt_cuda_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.bgpt_cuda_op_quantize_weights.argtypes = [C.c_int, _f32p, C.c_longlong, _u8p]
+    L.bgpt_cuda_debug_quantize_bench.argtypes = [C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_debug_icache_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_debug_barrier_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.bgpt_cuda_debug_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -267,6 +269,22 @@ def op_mul_mat_tc(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int)
     _check(lib().bgpt_cuda_op_mul_mat_tc(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
            "op_mul_mat_tc")
     return y
+
+
+def op_quantize_weights(ggml_type: int, x: np.ndarray) -> np.ndarray:
+    """f32 -> Qx blocks (file layout) on the device: the reference's quantize_row_q*_reference bits"""
+    from . import ggml_file as gf
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    out = np.empty(gf.row_bytes(ggml_type, x.size), dtype=np.uint8)
+    _check(lib().bgpt_cuda_op_quantize_weights(ggml_type, x, x.size, out), "op_quantize_weights")
+    return out
+
+
+def quantize_bench(ggml_type: int, n: int, iters: int = 10) -> float:
+    """microseconds per launch of the device quantiser over n weights (device-resident)"""
+    us = C.c_float(0)
+    _check(lib().bgpt_cuda_debug_quantize_bench(ggml_type, n, iters, C.byref(us)), "quantize_bench")
+    return float(us.value)
 
 
 def op_quantize_act(weight_type: int, x: np.ndarray) -> np.ndarray:

@@ -174,3 +174,64 @@ __global__ void __launch_bounds__(512, 1) k_icbench(unsigned long long * w, int 
     }
     if (sink && a + b + c + d == 12345.f) sink[blockIdx.x] = a;
 }
+
+// producer patterns for the 1024-word all-to-all exchange (8 replicas, 512 pollers, ld.volatile):
+// PAT 0: row owners = lane 28 of warps < rows, 8 sequential stores each            (old x1 path)
+// PAT 1: row owners = threads 8*row (lanes 0,8,16,24 of warps 0,1), 8 sequential stores  (old x path)
+// PAT 2: gather in shared memory + sync, warp 0 lane = 8*(replica%4) + row, 2 stores
+// PAT 3: gather + sync, warp 0 lanes < rows, 8 sequential stores (one replica per instruction)
+// PAT 4: gather + sync, warp r writes replica r (lanes < rows), one store each
+// PAT 5: gather + sync, warp 0 lanes < rows write replica pairs as 16-byte {word(row), word(row)}?  -- not expressible; unused
+template <int PAT>
+__global__ void __launch_bounds__(512, 1) k_xchprod(unsigned long long * w, int iters, float * sink, int sleep_ns) {
+    constexpr int R = 8;
+    const unsigned nC = gridDim.x, c = blockIdx.x;
+    const int o0 = (int) ((c * 1024u) / nC), o1 = (int) (((c + 1u) * 1024u) / nC), rows = o1 - o0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rep = c % R;
+    __shared__ unsigned s_v[8];
+    unsigned acc = 0;
+    for (int i = 1; i <= iters; i++) {
+        unsigned long long * X = w + (size_t) (i & 1) * (R * 1024);
+        const unsigned long long tagw = (unsigned long long) (unsigned) i << 32;
+        if (PAT == 0) {
+            if (lane == 28 && warp < rows) {
+#pragma unroll
+                for (int r = 0; r < R; r++) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(X + (size_t) r * 1024 + o0 + warp), "l"(tagw | (acc & 0xffffu)) : "memory");
+            }
+        } else if (PAT == 1) {
+            if ((threadIdx.x & 7) == 0 && (int) (threadIdx.x >> 3) < rows) {
+#pragma unroll
+                for (int r = 0; r < R; r++) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(X + (size_t) r * 1024 + o0 + (threadIdx.x >> 3)), "l"(tagw | (acc & 0xffffu)) : "memory");
+            }
+        } else {
+            if (lane == 28 && warp < rows) s_v[warp] = acc & 0xffffu;
+            __syncthreads();
+            if (PAT == 2) {
+                if (warp == 0 && (lane & 7) < rows) {
+#pragma unroll
+                    for (int r0 = 0; r0 < R; r0 += 4) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(X + (size_t) (r0 + (lane >> 3)) * 1024 + o0 + (lane & 7)), "l"(tagw | s_v[lane & 7]) : "memory");
+                }
+            } else if (PAT == 3) {
+                if (warp == 0 && lane < rows) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(X + (size_t) r * 1024 + o0 + lane), "l"(tagw | s_v[lane]) : "memory");
+                }
+            } else if (PAT == 4) {
+                if (warp < R && lane < rows) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(X + (size_t) warp * 1024 + o0 + lane), "l"(tagw | s_v[lane]) : "memory");
+            }
+        }
+        {
+            const unsigned long long * src = X + (size_t) rep * 1024 + 2 * threadIdx.x;
+            unsigned long long w0, w1;
+            for (;;) {
+                bx_ld2<0>(src, w0, w1);
+                if ((unsigned) (w0 >> 32) == (unsigned) i && (unsigned) (w1 >> 32) == (unsigned) i) break;
+                if (sleep_ns) __nanosleep(sleep_ns);
+            }
+            acc += (unsigned) w0 + (unsigned) w1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sink) sink[blockIdx.x] = (float) acc;
+}

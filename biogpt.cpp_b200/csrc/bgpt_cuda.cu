@@ -18,6 +18,7 @@
 #include "bgpt_mega4.cuh"
 #include "bgpt_barbench.cuh"
 #include "bgpt_tc.cuh"
+#include "bgpt_quant.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -101,6 +102,9 @@ struct bgpt_model {
     // generation-4 persistent kernel (bgpt_mega4.cuh): tagged-word exchange, no grid barrier
     bool mega4_ok = false; M4Params m4{}; unsigned long long * d_xch = nullptr; unsigned int m4_tag = 0;
     long long * d_trace = nullptr; size_t trace_n = 0;
+    // per-operator schedule replayed as a CUDA graph, one per (rows, mode, token buffer): every kernel reads n_past from m->st
+    struct FwdGraph { cudaGraphExec_t exec; uint64_t launches; };
+    std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -111,7 +115,12 @@ static int ftype_to_type(int f) {
     return -1;
 }
 
+static void drop_graphs(bgpt_model * m) {
+    for (auto & g : m->graphs) cudaGraphExecDestroy(g.second.exec);
+    m->graphs.clear();
+}
 static void free_arena(bgpt_model * m) {
+    drop_graphs(m);                                   // the graphs hold the arena's pointers
     cudaFree(m->d_tokens); cudaFree(m->x); cudaFree(m->x1); cudaFree(m->q); cudaFree(m->att); cudaFree(m->hff);
     cudaFree(m->logits); cudaFree(m->act_d); cudaFree(m->act_ff);
     for (int i = 0; i < 5; i++) { cudaFree(m->d_taps[i]); m->d_taps[i] = nullptr; }
@@ -142,6 +151,7 @@ static int ensure_arena(bgpt_model * m, int rows) {
 }
 
 static int alloc_kv(bgpt_model * m, int n_streams) {
+    drop_graphs(m);
     cudaFree(m->kcache); cudaFree(m->vcache); m->kcache = m->vcache = nullptr;
     m->stream_stride = (size_t) m->n_layer * m->n_positions * m->d_model;
     const size_t bytes = m->stream_stride * 4 * (size_t) n_streams;
@@ -320,6 +330,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     }
     CK(cudaSetDevice(m->device));
     init_kernel_attrs();
+    if (getenv("BGPT_GRAPH")) m->use_graphs = atoi(getenv("BGPT_GRAPH")) != 0;
     RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
@@ -537,6 +548,36 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
     return BGPT_OK;
 }
 
+
+// the same forward pass as one CUDA-graph launch: ~220 dependent kernels per eval are launch-bound when enqueued one by one
+// (4-5 us each on the host side); a graph replays them back to back.  n_past, the step counter and the token ids live in device
+// memory (m->st, d_tokens), so one graph per (rows, mode, token buffer) serves every position.  BGPT_GRAPH=0 disables.
+static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
+    if (!m->use_graphs || m->taps_armed) return enqueue_forward(m, d_tokens, n, mode);
+    const uint64_t key = ((uint64_t) (uintptr_t) d_tokens << 16) ^ ((uint64_t) n << 1) ^ (uint64_t) mode;
+    auto it = m->graphs.find(key);
+    if (it == m->graphs.end()) {
+        tc_init_attrs();
+        cudaGraph_t g = nullptr;
+        const uint64_t l0 = m->launches;
+        CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_forward(m, d_tokens, n, mode);
+        const cudaError_t ce = cudaStreamEndCapture(m->stream, &g);
+        const uint64_t cnt = m->launches - l0;
+        m->launches = l0;
+        if (rc != BGPT_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        CK(ce);
+        bgpt_model::FwdGraph fg{nullptr, cnt};
+        const cudaError_t ie = cudaGraphInstantiate(&fg.exec, g, 0);
+        cudaGraphDestroy(g);
+        CK(ie);
+        if (m->graphs.size() >= 64) drop_graphs(m);
+        it = m->graphs.emplace(key, fg).first;
+    }
+    CK(cudaGraphLaunch(it->second.exec, m->stream));
+    m->launches += it->second.launches;
+    return BGPT_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // persistent decode kernel: host side
@@ -808,7 +849,7 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
     CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
     if (n == 1 && use_mega(m)) { RET(launch_mega(m, m->d_tokens, 0, n_past, -1)); }
-    else RET(enqueue_forward(m, m->d_tokens, n, 0));
+    else RET(forward(m, m->d_tokens, n, 0));
     CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
@@ -829,7 +870,7 @@ extern "C" int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, i
     m->h_st->n_past = n_past; m->h_st->step = 0;
     CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, m->stream));
     if (n == 1 && use_mega(m)) { RET(launch_mega(m, d_tokens, 0, n_past, -1)); }
-    else RET(enqueue_forward(m, d_tokens, n, 0));
+    else RET(forward(m, d_tokens, n, 0));
     return BGPT_OK;
 }
 extern "C" const float * bgpt_cuda_logits_device(bgpt_model * m) { return m ? m->logits : nullptr; }
@@ -864,7 +905,7 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
         CK(cudaGetLastError());
     } else {
         for (int i = 0; i < n_steps; i++) {
-            RET(enqueue_forward(m, m->d_tokens, 1, 0));
+            RET(forward(m, m->d_tokens, 1, 0));
             k_argmax_advance<<<1, 1024, 0, s>>>(m->logits, m->n_vocab, m->d_tokens, m->d_idlog, m->st, 1);
             m->launches++;
             CK(cudaGetLastError());
@@ -900,7 +941,7 @@ extern "C" int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, in
     CK(cudaEventRecord(m->ev0, s));
     CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n_streams * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
-    RET(enqueue_forward(m, m->d_tokens, n_streams, 1));
+    RET(forward(m, m->d_tokens, n_streams, 1));
     if (logits_out) CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) n_streams * m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
@@ -1041,7 +1082,8 @@ extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, fl
                            /*13..*/ (const void *) k_xchbench<1, 1, 512>, (const void *) k_xchbench<1, 8, 128>,
                            /*15..*/ (const void *) k_pingpong<0>, (const void *) k_pingpong<1>, (const void *) k_pingpong<2>,
                            /*18..*/ (const void *) k_xchbench<0, 16, 512>, (const void *) k_xchbench<0, 32, 512>, (const void *) k_xchbench<3, 8, 512>,
-                           /*21..*/ (const void *) k_xchpack<8>, (const void *) k_xchpack<16>, (const void *) k_xchpack<1> };
+                           /*21..*/ (const void *) k_xchpack<8>, (const void *) k_xchpack<16>, (const void *) k_xchpack<1>,
+                           /*24..*/ (const void *) k_xchprod<0>, (const void *) k_xchprod<1>, (const void *) k_xchprod<2>, (const void *) k_xchprod<3>, (const void *) k_xchprod<4> };
     const int nv = (int) (sizeof(fns) / sizeof(fns[0]));
     if (v < 0 || v >= nv) return fail(BGPT_E_ARG, "barrier_bench: variant out of range");
     unsigned long long * wp = w.as<unsigned long long>(); float * sp = sink.as<float>(); const float * cp = with_load ? chase.as<float>() : nullptr;
@@ -1060,6 +1102,60 @@ extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, fl
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *us_per_barrier = best * 1000.f / iters;
+    return BGPT_OK;
+}
+
+// ---- device weight quantiser (bgpt_quant.cuh): f32 -> Qx file blocks, the reference's quantize_row_q*_reference bits
+static int launch_quantize(int type, const float * d_x, long long nblocks, uint8_t * d_out, cudaStream_t s) {
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    long long want = (nblocks + 32 * (BQ_THREADS / 32) - 1) / (32 * (BQ_THREADS / 32));
+    const int grid = (int) std::max(1LL, std::min(want, (long long) n_sm * 8));
+    switch (type) {
+        case BG_Q4_0: k_quantize_weights<BG_Q4_0><<<grid, BQ_THREADS, 0, s>>>(d_x, nblocks, d_out); break;
+        case BG_Q4_1: k_quantize_weights<BG_Q4_1><<<grid, BQ_THREADS, 0, s>>>(d_x, nblocks, d_out); break;
+        case BG_Q5_0: k_quantize_weights<BG_Q5_0><<<grid, BQ_THREADS, 0, s>>>(d_x, nblocks, d_out); break;
+        case BG_Q5_1: k_quantize_weights<BG_Q5_1><<<grid, BQ_THREADS, 0, s>>>(d_x, nblocks, d_out); break;
+        case BG_Q8_0: k_quantize_weights<BG_Q8_0><<<grid, BQ_THREADS, 0, s>>>(d_x, nblocks, d_out); break;
+        default: return fail(BGPT_E_UNSUPPORTED, "quantize: type %d is not a block-quantised type", type);
+    }
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+extern "C" int bgpt_cuda_op_quantize_weights(int type, const float * x, long long n, uint8_t * out) {
+    RET(need_device());
+    if (!x || !out || n <= 0 || n % 32) return fail(BGPT_E_ARG, "quantize_weights: n must be a positive multiple of 32");
+    if (!bg_is_quant(type)) return fail(BGPT_E_UNSUPPORTED, "quantize_weights: type %d", type);
+    const long long nb = n / 32; const size_t ob = (size_t) nb * bg_file_row_bytes(type, 32);
+    DevBuf dx, dout;
+    RET(dx.alloc((size_t) n * 4)); RET(dout.alloc(ob));
+    CK(cudaMemcpy(dx.p, x, (size_t) n * 4, cudaMemcpyHostToDevice));
+    RET(launch_quantize(type, dx.as<float>(), nb, dout.as<uint8_t>(), 0));
+    CK(cudaMemcpy(out, dout.p, ob, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+// debug: device-resident timing of the quantiser over n synthetic weights; us_out = microseconds per launch (best of 5)
+extern "C" int bgpt_cuda_debug_quantize_bench(int type, long long n, int iters, float * us_out) {
+    RET(need_device());
+    if (n <= 0 || n % 32 || iters < 1 || !us_out || !bg_is_quant(type)) return fail(BGPT_E_ARG, "quantize_bench: bad arguments");
+    const long long nb = n / 32; const size_t ob = (size_t) nb * bg_file_row_bytes(type, 32);
+    DevBuf dx, dout;
+    RET(dx.alloc((size_t) n * 4)); RET(dout.alloc(ob));
+    std::vector<float> h(1 << 20);
+    for (size_t i = 0; i < h.size(); i++) h[i] = 0.02f * sinf((float) i * 0.37f) + 0.001f * (float) (i % 97);
+    for (long long off = 0; off < n; off += (long long) h.size())
+        CK(cudaMemcpy(dx.as<float>() + off, h.data(), (size_t) std::min<long long>(h.size(), n - off) * 4, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; i++) RET(launch_quantize(type, dx.as<float>(), nb, dout.as<uint8_t>(), 0));
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *us_out = best * 1000.f / iters;
     return BGPT_OK;
 }
 

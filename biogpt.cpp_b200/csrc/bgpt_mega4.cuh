@@ -620,12 +620,21 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
         } else if (kind != 4) {
             const int nb10 = (kind == 1 ? M4_NB_D : M4_NB_F) * 10;
             const unsigned long long * src = X + (kind == 1 ? M4_E2 : M4_E4) + (size_t) rep * nb10;
-#pragma unroll 1
-            for (int i = tid; 2 * i < nb10; i += M4_NT) {
-                uint32_t a, b;
-                m4_poll2(src + 2 * i, tag, a, b, P.poll_sleep);
-                m4_scatter_word(rec, D.off_dd, D.off_s, 2 * i, a);
-                m4_scatter_word(rec, D.off_dd, D.off_s, 2 * i + 1, b);
+            if (2 * tid < nb10) {                                  // <= 2 units of two words per thread, both loads in flight
+                const bool two = 2 * (tid + M4_NT) < nb10;
+                const unsigned long long * pa = src + 2 * tid, * pb = src + 2 * (two ? tid + M4_NT : tid);
+                unsigned long long a0, a1, b0, b1;
+                for (;;) {
+                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(pa) : "memory");
+                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(b0), "=l"(b1) : "l"(pb) : "memory");
+                    if ((uint32_t) (a0 >> 32) == tag && (uint32_t) (a1 >> 32) == tag && (uint32_t) (b0 >> 32) == tag && (uint32_t) (b1 >> 32) == tag) break;
+                }
+                m4_scatter_word(rec, D.off_dd, D.off_s, 2 * tid, (uint32_t) a0);
+                m4_scatter_word(rec, D.off_dd, D.off_s, 2 * tid + 1, (uint32_t) a1);
+                if (two) {
+                    m4_scatter_word(rec, D.off_dd, D.off_s, 2 * (tid + M4_NT), (uint32_t) b0);
+                    m4_scatter_word(rec, D.off_dd, D.off_s, 2 * (tid + M4_NT) + 1, (uint32_t) b1);
+                }
             }
             M4PROF(phs, 3);
         }
@@ -671,21 +680,32 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
                 float t = __fadd_rn(bias, dotv);
                 if (mat == 0) t = __fmul_rn(t, p.qscale);
                 else (mat == 1 ? kc : vc)[(size_t) pos * M4_D + rr] = t;
-                m4_put(X + M4_E1 + r_own, __float_as_uint(t), tag);
+                s_blk[row] = t;
             } else if (kind == 1) {
-                const float t = __fadd_rn(__fadd_rn(dotv, bias), s_x[r_own]);
-                m4_put_rep(X + M4_E3 + r_own, M4_D, __float_as_uint(t), tag);
+                s_blk[row] = __fadd_rn(__fadd_rn(dotv, bias), s_x[r_own]);
             } else if (kind == 2) {
                 s_blk[row] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dotv))]);
             } else if (kind == 3) {
-                const float t = __fadd_rn(__fadd_rn(bias, dotv), s_x1[r_own]);
-                m4_put_rep(X + M4_E5 + r_own, M4_D, __float_as_uint(t), tag);
+                s_blk[row] = __fadd_rn(__fadd_rn(bias, dotv), s_x1[r_own]);
             } else {
                 p.logits[r_own] = dotv;
                 if (dotv > best || (dotv == best && r_own < bi)) { best = dotv; bi = r_own; }
             }
         }
-        if (kind == 2) __syncthreads();
+        // ---- publish: the CTA's results are gathered in shared memory and ONE warp writes them as consecutive words, so a
+        //      polled line receives a few whole-sector writes instead of one partial 8-byte write per row (measured: words
+        //      land ~1 us sooner on lines that 19 CTAs are polling)
+        if (kind != 4) __syncthreads();
+        if (kind == 0 && tid < 32 && lane < rt) m4_put(X + M4_E1 + rbase + lane, __float_as_uint(s_blk[lane]), tag);
+        if ((kind == 1 || kind == 3) && tid < 32) {
+            const int row = lane & 7;
+            if (row < rt) {
+                const uint32_t v = __float_as_uint(s_blk[row]);
+                unsigned long long * dst = X + (kind == 1 ? M4_E3 : M4_E5) + rbase + row;
+#pragma unroll
+                for (int r0 = 0; r0 < M4_R; r0 += 4) m4_put(dst + (size_t) (r0 + (lane >> 3)) * M4_D, v, tag);
+            }
+        }
         if (kind == 2 && rt > 0 && tid < 32) m4_quant_publish<FMT>(s_blk, X + M4_E4 + (size_t) cta * 10, M4_NB_F * 10, tag);
         if (!lm) M4PROF(phs, 2);
         // ================= attention (32 CTAs: head, 32-column half), after P1 =================

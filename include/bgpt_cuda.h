@@ -124,6 +124,11 @@ int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);
 int bgpt_cuda_debug_read_trace(bgpt_model * m, long long * out, int cap, int * n_cta, int * per_cta);
 /* debug: microseconds per grid-wide barrier for the candidate implementations in
  * csrc/bgpt_barbench.cuh (one CTA per SM, `iters` back-to-back barriers). */
+/* f32 -> Q4_0/Q4_1/Q5_0/Q5_1/Q8_0 blocks in the file layout, on the device; bit-identical to the reference's
+ * quantize_row_q*_reference as its `quantize` tool runs them (ggml.c:892-1094, biogpt.cpp:459-621).  `type` is a
+ * ggml_type; n (a multiple of 32) host floats in, n/32 blocks out. */
+int bgpt_cuda_op_quantize_weights(int type, const float * x, long long n, uint8_t * out);
+int bgpt_cuda_debug_quantize_bench(int type, long long n, int iters, float * us_per_launch);
 int bgpt_cuda_debug_icache_bench(int kb, int iters, int nwarps, float * cycles_per_iter);
 int bgpt_cuda_debug_barrier_bench(int variant, int iters, int with_load, float * us_per_barrier);
 /* debug: milliseconds per matmul y[n][rows] = W[rows][k].x[n][k] (synthetic data, device

@@ -169,3 +169,29 @@ def test_mul_mat_tensor_core(checkers, capi, name, shape):
     # and it must agree with the exact-order GPU kernel to the same tolerance
     exact = capi.op_mul_mat(t, wb, x, rows)
     assert np.abs(got - exact).max() <= tol
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_quantize_weights_equals_reference_quantiser(capi, name):
+    """device f32 -> Qx blocks (csrc/bgpt_quant.cuh) == quantize_row_q*_reference as the reference's `quantize` tool
+    runs it (ggml.c:892-1094).  The checker is ggml_file's numpy restatement, itself pinned to the tool's output and to
+    ggml's own test signal (tests/test_oracle_golden.py).  Cases: ggml's 0.1 + 2 cos(i) signal, synthetic weights, an
+    all-zero block, ties of |max| with opposite signs (first occurrence wins), one block, a ragged warp (33 blocks)."""
+    t = TYPES[name]
+    rng = np.random.default_rng(99 + t)
+    cases = []
+    n = 32 * 128
+    cases.append((0.1 + 2.0 * np.cos(np.arange(n, dtype=np.float32))).astype(np.float32))          # ggml/tests/test-quantize-fns.cpp:26-30
+    w = (rng.standard_normal(32 * 4097) * 0.02).astype(np.float32)
+    w[64:96] = 0.0
+    w[96] = 0.5; w[97] = -0.5                                     # equal magnitudes: the first one sets the sign of d
+    w[128] = -0.25; w[140] = 0.25
+    cases.append(w)
+    cases.append((rng.standard_normal(32) * 3).astype(np.float32))
+    cases.append((rng.standard_normal(32 * 33) * 1e-3).astype(np.float32))
+    cases.append(np.linspace(-4, 4, 32 * 7, dtype=np.float32))
+    for i, x in enumerate(cases):
+        got = capi.op_quantize_weights(t, x)
+        want = gf.QUANTIZERS[t](x)
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, f"{name} case {i}: {bad.size}/{got.size} bytes differ, first at {bad[:8]} (block {bad[0] // gf.TYPE_SIZE[t]})"

@@ -33,3 +33,11 @@ for v, n in [(18, "exchange: ld.volatile, 16 replicas"), (19, "exchange: ld.vola
     us = C.c_float(0)
     rc = capi.lib().bgpt_cuda_debug_barrier_bench(v, 2000, 0, C.byref(us))
     print(f"variant {v} ({n}): {us.value:.3f} us/exchange" if rc == 0 else capi.last_error())
+
+for v, n in [(24, "producer: lane 28 of warps < rows, 8 sequential stores"), (25, "producer: threads 8*row, 8 sequential stores"),
+             (26, "producer: gather + sync, warp 0, 4 replicas x rows per store, 2 stores"), (27, "producer: gather + sync, warp 0 lanes < rows, 8 sequential stores"),
+             (28, "producer: gather + sync, warp r writes replica r")]:
+    for rep in range(2):
+        us = C.c_float(0)
+        rc = capi.lib().bgpt_cuda_debug_barrier_bench(v, 2000, 0, C.byref(us))
+        print(f"variant {v} ({n}): {us.value:.3f} us/exchange" if rc == 0 else capi.last_error())

@@ -32,7 +32,17 @@ launches)
 full)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mega -s 3 -c 1 -f -o $OUT/mega_full \
       python tools/profile_decode.py --n-past 511 --steps 5 --warm 0 > $OUT/mega_full.log 2>&1; echo "full rc=$?"
+  ncu -i $OUT/mega_full.ncu-rep --page raw --csv > $OUT/mega_full_raw.csv 2>/dev/null
   tail -3 $OUT/mega_full.log ;;
+promptfull)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc_q -s 8 -c 1 -f -o $OUT/gemm_tc_full \
+      python tools/profile_prompt.py --ftype q8_0 --n 1024 > $OUT/gemm_tc_full.log 2>&1; echo "promptfull rc=$?"
+  ncu -i $OUT/gemm_tc_full.ncu-rep --page raw --csv > $OUT/gemm_tc_full_raw.csv 2>/dev/null
+  tail -3 $OUT/gemm_tc_full.log ;;
+trace)
+  for np in 0 507; do BGPT_MEGA_PROF=1 timeout 200 python tools/trace_decode.py --n-past $np; done > $OUT/trace.log 2>&1; grep -v "Warning\|nanm\|return np" $OUT/trace.log | head -60 ;;
+streams)
+  timeout 600 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64 > $OUT/streams.log 2>&1; cat $OUT/streams.log ;;
 prompt)
   timeout 600 python tools/prompt_bench.py --ftype q8_0 --n 8,64,256,1024 > $OUT/prompt.log 2>&1; cat $OUT/prompt.log ;;
 promptncu)

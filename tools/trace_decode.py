@@ -34,12 +34,13 @@ if a.dump:
     np.savez_compressed(a.dump, st=st, cal=cal)
 nC, L1 = st.shape[0], st.shape[1]
 L = L1 - 1
-g0, c0, g1, c1 = (cal[:, i].astype(np.float64) for i in range(4))
+gbase = int(cal[:, 0].min())                               # epoch nanoseconds exceed float64's integer range: subtract first
+g0, c0, g1, c1 = ((cal[:, i] - (gbase if i in (0, 2) else 0)).astype(np.float64) for i in range(4))
 f = (c1 - c0) / (g1 - g0)                                  # cycles per ns of each SM
 print(f"{a.ftype} n_past={a.n_past + a.warm}: kernel {ms * 1e3:.1f} us; SM clock {f.mean():.4f} GHz (min {f.min():.4f} max {f.max():.4f}); "
       f"launch skew of CTA starts {g0.max() - g0.min():.0f} ns")
 valid = st > 0
-T = g0[:, None, None, None] + (st.astype(np.float64) - c0[:, None, None, None]) / f[:, None, None, None]   # ns
+T = g0[:, None, None, None] + (st - cal[:, 1][:, None, None, None]).astype(np.float64) / f[:, None, None, None]   # ns since the first CTA's start
 T[~valid] = np.nan
 ev = [((0, 0), "P1 tile start"), ((0, 3), "P1 x polled (warp 0)"), ((0, 4), "P1 all polled (sync 1)"), ((0, 6), "P1 LN before sync 2"), ((0, 7), "P1 LN after sync 2"), ((0, 8), "P1 LN scale known"), ((0, 5), "P1 LN + quantise done"),
       ((0, 1), "P1 record+weights ready"), ((0, 9), "P1 act loaded"), ((0, 10), "P1 dots done"), ((0, 2), "P1 q,k,v published"),
