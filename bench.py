@@ -204,7 +204,8 @@ def main():
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl")
+        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to stdout: rank 0 prints ONE json line
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
         if rank == 0:
             model_path(args.ftype)
