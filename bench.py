@@ -152,6 +152,56 @@ def cpu_reference_tokens_per_s(ftype: str, seq: int, budget_s: float, threads: i
     return tps, sample, kind
 
 
+def side_configs(capi, device: int, seq: int):
+    """BASELINE.json configs[2] (Q8_0 prompt, the reference's n_batch = 8 chunking) and configs[3] (Q5_1, 8 lock-step streams
+    per GPU), measured on rank 0 after the headline run; both run on the fused skinny-batch schedule (csrc/bgpt_skinny.cuh).
+    Device time = CUDA events inside each call (bgpt_cuda_last_eval_ms)."""
+    pk, _ = peaks()
+    out = {}
+    # ---- configs[2]: `seq` prompt tokens in evals of 8 rows, un-masked, logits of the last row of every eval
+    M = capi.Model.load(model_path("q8_0"), device=device, max_batch=8)
+    toks = gf.synth_tokens(seq, gf.BASE.n_vocab, seed=5)
+    for rep in range(3):
+        ms = 0.0; flops = 0.0; nbytes = 0.0
+        t0 = time.perf_counter()
+        for p in range(0, seq, 8):
+            M.eval(toks[p:p + 8], p)
+            ms += M.last_eval_ms
+            flops += 2.0 * 8 * 301989888 + 2 * 43401216 + 98304.0 * 8 * (p + 8)          # SURVEY 8(d), L_rows = 1
+            nbytes += bytes_per_token("q8_0", p + 7) + 7 * (196_608 + 2 * 1088)            # weights once, K/V rows of p+8 positions, 8 rows appended
+        wall = time.perf_counter() - t0
+    out["prompt_q8_0_n_batch_8"] = {
+        "workload": f"BioGPT-base Q8_0, {seq} prompt tokens in {seq // 8} un-masked evals of 8 rows (BASELINE.json configs[2])",
+        "tokens_per_s": seq / (ms / 1e3), "tokens_per_s_host_buffers_wall": seq / wall, "ms_total": ms, "tflops": flops / (ms / 1e3) / 1e12,
+        "roofline": {"bound": "hbm", "achieved": nbytes / (ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": nbytes / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "note": "AI ~ 15 FLOP/B at 8 rows: HBM-bound by SURVEY 8(d)"},
+        "schedule": "fused skinny-batch" if M.batch_path(8) else "per-operator", "launches_per_eval": None}
+    l0 = M.launch_count; M.eval(toks[:8], 0); out["prompt_q8_0_n_batch_8"]["launches_per_eval"] = M.launch_count - l0
+    M.close()
+    # ---- configs[3]: 8 independent sequences per GPU in lock step, each with its own F32 KV cache, greedy ids on the host
+    S = 8
+    M = capi.Model.load(model_path("q5_1"), device=device, max_batch=S)
+    M.set_streams(S)
+    first = gf.synth_tokens(S, gf.BASE.n_vocab, seed=9).astype(np.int32)
+    for rep in range(2):
+        cur = first.copy(); ms = 0.0; nbytes = 0.0
+        t0 = time.perf_counter()
+        for p in range(seq):
+            logits = M.eval_streams(cur, p)
+            ms += M.last_eval_ms
+            cur = np.argmax(logits, axis=1).astype(np.int32)
+            nbytes += bytes_per_token("q5_1", p) + (S - 1) * (196_608 * (p + 1) + 196_608 + 169_536 + 2 * 768)
+        wall = time.perf_counter() - t0
+    out["streams_q5_1_x8"] = {
+        "workload": f"BioGPT-base Q5_1, {S} lock-step streams on one GPU, seq 1->{seq} (BASELINE.json configs[3], per GPU)",
+        "tokens_per_s": S * seq / (ms / 1e3), "tokens_per_s_host_buffers_wall": S * seq / wall, "us_per_step": ms * 1e3 / seq,
+        "roofline": {"bound": "hbm", "achieved": nbytes / (ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": nbytes / (ms / 1e3) / 1e9 / pk["hbm_gbs"]},
+        "schedule": "fused skinny-batch" if M.batch_path(S) else "per-operator"}
+    M.close()
+    return out
+
+
 def run_reference_arm(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -185,6 +235,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE.json configs[2] / configs[3] side measurements")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
 
@@ -310,6 +361,15 @@ def main():
         tps, sample, kind = cpu_reference_tokens_per_s(args.ftype, seq, args.cpu_budget, threads)
         cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
 
+    extras = None
+    if not args.no_extras:
+        M.close()
+        try:
+            extras = side_configs(capi, local_rank, seq)
+        except Exception as e:                       # the headline line must survive a side measurement
+            extras = {"error": repr(e)}
+        M = capi.Model.load(path, device=local_rank, max_batch=8)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8*int8->f32 (Q8_0 activations), f32 KV", "data": "synthetic",
@@ -317,7 +377,8 @@ def main():
                        "ftype": args.ftype, "seq": seq, "streams_per_gpu": 1, "parallelism": f"replicas x{world}",
                        "l2": "inputs larger than L2: every token streams the full 194 MB weight set (+KV) through a 126 MB L2",
                        "parity": "logits bit-identical to the reference CPU path (tests/test_gpu_eval.py)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "other_configs": extras}
     print(json.dumps(line), flush=True)
     M.close()
     if dist is not None:

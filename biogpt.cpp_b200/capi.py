@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_icache_bench", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_debug_quantize_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_icache_bench", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_debug_quantize_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -76,6 +76,10 @@ def lib():
     L.bgpt_cuda_set_decode_path.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_get_decode_path.argtypes = [C.c_void_p]
     L.bgpt_cuda_decode_kernel_generation.argtypes = [C.c_void_p]
+    L.bgpt_cuda_set_batch_path.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_get_batch_path.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_debug_read_buffer.restype = C.c_longlong
+    L.bgpt_cuda_debug_read_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
     L.bgpt_cuda_debug_read_prof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bgpt_cuda_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bgpt_cuda_op_quantize_weights.argtypes = [C.c_int, _f32p, C.c_longlong, _u8p]
@@ -191,6 +195,21 @@ class Model:
     def set_decode_path(self, path: int):
         """1: persistent kernel per token (default), 0: one kernel per fused operator"""
         _check(lib().bgpt_cuda_set_decode_path(self.h, path), "set_decode_path")
+
+    def set_batch_path(self, path: int):
+        """1: fused skinny-batch schedule for 2..31 rows where it applies (default), 0: per-operator kernels"""
+        _check(lib().bgpt_cuda_set_batch_path(self.h, path), "set_batch_path")
+
+    def read_buffer(self, which: int, rows: int) -> np.ndarray:
+        """debug: raw bytes of an arena buffer after the last eval (0 x, 1 x1, 2 q, 3 act_d records, 4 act_ff records)"""
+        buf = np.empty(rows * 16 * 1024 * 4, dtype=np.uint8)
+        n = lib().bgpt_cuda_debug_read_buffer(self.h, which, rows, buf.ctypes.data, buf.size)
+        if n < 0:
+            raise BgptError("read_buffer: " + last_error())
+        return buf[:n].copy()
+
+    def batch_path(self, n_rows: int) -> int:
+        return int(lib().bgpt_cuda_get_batch_path(self.h, n_rows))
 
     @property
     def decode_path(self) -> int:

@@ -19,6 +19,7 @@
 #include "bgpt_barbench.cuh"
 #include "bgpt_tc.cuh"
 #include "bgpt_quant.cuh"
+#include "bgpt_skinny.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -105,6 +106,8 @@ struct bgpt_model {
     // per-operator schedule replayed as a CUDA graph, one per (rows, mode, token buffer): every kernel reads n_past from m->st
     struct FwdGraph { cudaGraphExec_t exec; uint64_t launches; };
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
+    int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
+    int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -331,6 +334,8 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     CK(cudaSetDevice(m->device));
     init_kernel_attrs();
     if (getenv("BGPT_GRAPH")) m->use_graphs = atoi(getenv("BGPT_GRAPH")) != 0;
+    if (getenv("BGPT_PDL")) m->use_pdl = atoi(getenv("BGPT_PDL")) != 0;
+    if (getenv("BGPT_BATCH_PATH")) m->batch_path = atoi(getenv("BGPT_BATCH_PATH")) != 0;
     RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
@@ -549,28 +554,167 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
 }
 
 
+// ------------------------------------------------------------------------------------------
+// fused skinny-batch schedule (bgpt_skinny.cuh): 5 launches per layer, programmatic dependent launch
+// ------------------------------------------------------------------------------------------
+static bool skinny_ok(const bgpt_model * m, int n) {
+    return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff % 1024 == 0 &&
+           m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < tc_min_rows();
+}
+static void sk_init_attrs() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+#define ATTR_SK(F) allow_big_smem(k_sk_mm<F, 4>); allow_big_smem(k_sk_mm<F, 8>);
+    ATTR_SK(BG_Q4_0) ATTR_SK(BG_Q4_1) ATTR_SK(BG_Q5_0) ATTR_SK(BG_Q5_1) ATTR_SK(BG_Q8_0)
+    cudaGetLastError();
+}
+template <int FMT> static const void * sk_mm_fn(int TN) { return TN == 4 ? (const void *) k_sk_mm<FMT, 4> : (const void *) k_sk_mm<FMT, 8>; }
+static const void * sk_mm_fn_of(int wtype, int TN) {
+    switch (wtype) {
+        case BG_Q4_0: return sk_mm_fn<BG_Q4_0>(TN); case BG_Q4_1: return sk_mm_fn<BG_Q4_1>(TN); case BG_Q5_0: return sk_mm_fn<BG_Q5_0>(TN);
+        case BG_Q5_1: return sk_mm_fn<BG_Q5_1>(TN); case BG_Q8_0: return sk_mm_fn<BG_Q8_0>(TN);
+    }
+    return nullptr;
+}
+static const void * sk_attn_fn_of(int wtype) {
+    switch (wtype) {
+        case BG_Q4_0: return (const void *) k_sk_attn<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_attn<BG_Q4_1>;
+        case BG_Q5_0: return (const void *) k_sk_attn<BG_Q5_0>; case BG_Q5_1: return (const void *) k_sk_attn<BG_Q5_1>;
+        case BG_Q8_0: return (const void *) k_sk_attn<BG_Q8_0>;
+    }
+    return nullptr;
+}
+// launch with the programmatic-stream-serialisation attribute: the kernel may start while its predecessor in the stream is
+// still running and blocks at griddepcontrol.wait (everything before that point touches weights only)
+static int sk_launch(bgpt_model * m, const void * fn, dim3 grid, int threads, size_t smem, void * arg) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = m->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = m->use_pdl ? 1 : 0;
+    void * args[1] = { arg };
+    CK(cudaLaunchKernelExC(&cfg, fn, args));
+    m->launches++;
+    return BGPT_OK;
+}
+// one k_sk_mm launch over token rows [tok0, n)
+static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int nmat, const ActLayout & A, int n, int tok0, int rpw) {
+    const RowLayout & L = W[0]->L;
+    for (int i = 0; i < 3; i++) a.W[i] = W[i < nmat ? i : 0]->ptr;
+    a.rows_per = (int) W[0]->ne1; a.M = a.rows_per * nmat; a.npass = L.K / 1024;
+    a.stride = L.stride; a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
+    a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s; a.code_off = bg_code_offset(m->wtype);
+    a.n = n; a.tok0 = tok0; a.rpw = rpw; a.eps = 1e-5f;         // NORM_EPS, biogpt.cpp:24
+    const int cnt = n - tok0, TN = cnt <= 4 ? 4 : 8;
+    dim3 grid((a.M + SK_NW * rpw - 1) / (SK_NW * rpw), (cnt + TN - 1) / TN);
+    const size_t smem = (size_t) TN * A.bytes + (size_t) SK_NW * SK_SCR * 4;
+    return sk_launch(m, sk_mm_fn_of(m->wtype, TN), grid, SK_NT, smem, &a);
+}
+
+static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, int mode) {
+    cudaStream_t s = m->stream;
+    const int d = m->d_model, ff = m->d_ff, dk = d / m->n_head, wt = m->wtype;
+    sk_init_attrs();
+    k_embed<<<n, 256, 0, s>>>(m->embed_tokens->ptr, m->embed_pos->ptr, wt, d_tokens, m->st, mode, n, d, m->n_vocab,
+                              (int) m->embed_pos->ne1, sqrtf((float) d), m->x);
+    m->launches++;
+    CK(cudaGetLastError());
+    for (int l = 0; l < m->n_layer; l++) {
+        const LayerW & L = m->layers[l];
+        float * kc = m->kcache + (size_t) l * m->n_positions * d;
+        float * vc = m->vcache + (size_t) l * m->n_positions * d;
+        {   // LayerNorm0 + q,k,v + bias + q scale + KV append      biogpt.cpp:693-727
+            SkArgs a{};
+            const DevTensor * W[3] = { L.q_w, L.k_w, L.v_w };
+            a.pro = 1; a.xin = m->x; a.ld_in = d; a.lnw = (const float *) L.ln0_w->ptr; a.lnb = (const float *) L.ln0_b->ptr;
+            a.epi = SK_EPI_QKV; a.bias[0] = (const float *) L.q_b->ptr; a.bias[1] = (const float *) L.k_b->ptr; a.bias[2] = (const float *) L.v_b->ptr;
+            a.out = m->q; a.ld_out = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
+            a.qscale = 1.0f / sqrtf((float) dk);                 // biogpt.cpp:681
+            a.st = m->st; a.mode = mode;
+            RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 1));
+        }
+        {   // attention + quantise for out_proj                     biogpt.cpp:730-764
+            SkAttnArgs a{};
+            a.q = m->q; a.ld_q = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
+            a.act = m->act_d; a.act_bytes = m->A_d.bytes; a.off_n = m->A_d.off_n; a.off_d = m->A_d.off_d; a.off_s = m->A_d.off_s;
+            a.code_off = bg_code_offset(wt); a.n = n; a.mode = mode; a.st = m->st; a.exp_tab = m->exp_tab;
+            RET(sk_launch(m, sk_attn_fn_of(wt), dim3(m->n_head, n), SK_ANT, 0, &a));
+        }
+        {   // out_proj + bias + residual                            biogpt.cpp:767-772
+            SkArgs a{};
+            const DevTensor * W[3] = { L.o_w, nullptr, nullptr };
+            a.pro = 0; a.act = m->act_d;
+            a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.o_b->ptr; a.out = m->x1; a.ld_out = d; a.resid = m->x; a.ld_resid = d;
+            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 1));
+        }
+        {   // LayerNorm1 + fc1 + bias + GELU + quantise for fc2     biogpt.cpp:779-787
+            SkArgs a{};
+            const DevTensor * W[3] = { L.fc1_w, nullptr, nullptr };
+            a.pro = 1; a.xin = m->x1; a.ld_in = d; a.lnw = (const float *) L.ln1_w->ptr; a.lnb = (const float *) L.ln1_b->ptr;
+            a.epi = SK_EPI_GELUQ; a.bias[0] = (const float *) L.fc1_b->ptr; a.gelu = m->gelu_tab;
+            a.act_out = m->act_ff; a.out_bytes = m->A_ff.bytes; a.out_off_n = m->A_ff.off_n; a.out_off_d = m->A_ff.off_d; a.out_off_s = m->A_ff.off_s;
+            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 4));
+        }
+        {   // fc2 + bias + residual                                 biogpt.cpp:790-795
+            SkArgs a{};
+            const DevTensor * W[3] = { L.fc2_w, nullptr, nullptr };
+            a.pro = 0; a.act = m->act_ff;
+            a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.fc2_b->ptr; a.out = m->x; a.ld_out = d; a.resid = m->x1; a.ld_resid = d;
+            RET(sk_mm(m, a, W, 1, m->A_ff, n, 0, 1));
+        }
+    }
+    // the reference computes all n rows and returns the last (biogpt.cpp:803, 844); rows are independent, so only the
+    // returned row is computed in prompt mode
+    const int tok0 = mode == 0 ? n - 1 : 0;
+    if (n - tok0 >= 2) {
+        SkArgs a{};
+        const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };
+        a.pro = 1; a.xin = m->x; a.ld_in = d; a.lnw = (const float *) m->ln_w->ptr; a.lnb = (const float *) m->ln_b->ptr;
+        a.epi = SK_EPI_STORE; a.out = m->logits - (size_t) tok0 * m->n_vocab; a.ld_out = m->n_vocab;
+        RET(sk_mm(m, a, W, 1, m->A_d, n, tok0, 4));
+    } else {
+        RET(launch_act(m, s, m->x, d, m->ln_w, m->ln_b, d, wt, m->act_d, m->A_d, n, nullptr, 0));
+        const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };
+        Epi e = make_epi(EPI_STORE, nullptr, m->logits - (size_t) tok0 * m->n_vocab, m->n_vocab);
+        RET(launch_gemv(m, s, W, 1, m->act_d, m->A_d, n, tok0, e));
+    }
+    (void) ff;
+    return BGPT_OK;
+}
+
 // the same forward pass as one CUDA-graph launch: ~220 dependent kernels per eval are launch-bound when enqueued one by one
 // (4-5 us each on the host side); a graph replays them back to back.  n_past, the step counter and the token ids live in device
 // memory (m->st, d_tokens), so one graph per (rows, mode, token buffer) serves every position.  BGPT_GRAPH=0 disables.
+static int enqueue_any(bgpt_model * m, const int * d_tokens, int n, int mode) {
+    return skinny_ok(m, n) ? enqueue_forward_skinny(m, d_tokens, n, mode) : enqueue_forward(m, d_tokens, n, mode);
+}
 static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
-    if (!m->use_graphs || m->taps_armed) return enqueue_forward(m, d_tokens, n, mode);
+    if (!m->use_graphs || m->taps_armed) return enqueue_any(m, d_tokens, n, mode);
     const uint64_t key = ((uint64_t) (uintptr_t) d_tokens << 16) ^ ((uint64_t) n << 1) ^ (uint64_t) mode;
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
         tc_init_attrs();
-        cudaGraph_t g = nullptr;
-        const uint64_t l0 = m->launches;
-        CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = enqueue_forward(m, d_tokens, n, mode);
-        const cudaError_t ce = cudaStreamEndCapture(m->stream, &g);
-        const uint64_t cnt = m->launches - l0;
-        m->launches = l0;
-        if (rc != BGPT_OK) { if (g) cudaGraphDestroy(g); return rc; }
-        CK(ce);
-        bgpt_model::FwdGraph fg{nullptr, cnt};
-        const cudaError_t ie = cudaGraphInstantiate(&fg.exec, g, 0);
-        cudaGraphDestroy(g);
-        CK(ie);
+        bgpt_model::FwdGraph fg{nullptr, 0};
+        for (int attempt = 0; attempt < 2 && !fg.exec; attempt++) {
+            cudaGraph_t g = nullptr;
+            const uint64_t l0 = m->launches;
+            CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_any(m, d_tokens, n, mode);
+            const cudaError_t ce = cudaStreamEndCapture(m->stream, &g);
+            fg.launches = m->launches - l0;
+            m->launches = l0;
+            cudaError_t ie = ce;
+            if (rc == BGPT_OK && ce == cudaSuccess) ie = cudaGraphInstantiate(&fg.exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (rc == BGPT_OK && ie == cudaSuccess) break;
+            fg.exec = nullptr;
+            cudaGetLastError();
+            if (attempt == 0 && m->use_pdl && skinny_ok(m, n)) { m->use_pdl = 0; continue; }   // programmatic edges refused: plain edges
+            if (rc != BGPT_OK) return rc;
+            CK(ie);
+        }
         if (m->graphs.size() >= 64) drop_graphs(m);
         it = m->graphs.emplace(key, fg).first;
     }
@@ -578,6 +722,32 @@ static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
     m->launches += it->second.launches;
     return BGPT_OK;
 }
+
+extern "C" int bgpt_cuda_set_batch_path(bgpt_model * m, int path) {
+    if (!m || path < 0 || path > 1) return fail(BGPT_E_ARG, "set_batch_path: path must be 0 or 1");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    if (path != m->batch_path) drop_graphs(m);
+    m->batch_path = path;
+    return BGPT_OK;
+}
+extern "C" long long bgpt_cuda_debug_read_buffer(bgpt_model * m, int which, int rows, void * out, long long cap) {
+    if (!m || !out || rows < 1 || rows > m->cap) { fail(BGPT_E_ARG, "debug_read_buffer: bad arguments"); return -1; }
+    const void * src = nullptr; size_t bytes = 0;
+    switch (which) {
+        case 0: src = m->x;      bytes = (size_t) rows * m->d_model * 4; break;
+        case 1: src = m->x1;     bytes = (size_t) rows * m->d_model * 4; break;
+        case 2: src = m->q;      bytes = (size_t) rows * m->d_model * 4; break;
+        case 3: src = m->act_d;  bytes = (size_t) rows * m->A_d.bytes; break;
+        case 4: src = m->act_ff; bytes = (size_t) rows * m->A_ff.bytes; break;
+        default: fail(BGPT_E_ARG, "debug_read_buffer: which must be 0..4"); return -1;
+    }
+    if ((long long) bytes > cap) { fail(BGPT_E_ARG, "debug_read_buffer: %zu bytes needed, %lld given", bytes, cap); return -1; }
+    if (cudaSetDevice(m->device) != cudaSuccess || cudaStreamSynchronize(m->stream) != cudaSuccess ||
+        cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { fail(BGPT_E_CUDA, "debug_read_buffer: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    return (long long) bytes;
+}
+extern "C" int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows) { return m && skinny_ok(m, n_rows) ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------
 // persistent decode kernel: host side

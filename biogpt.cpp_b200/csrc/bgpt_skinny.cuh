@@ -1,0 +1,491 @@
+// bgpt_skinny.cuh -- fused schedule for SKINNY batches (2..31 token rows) of the quantised formats
+// at BioGPT-base layer shapes (d_model 1024, 16 heads of 64, d_ff a multiple of 1024): the
+// reference's own prompt chunking (n_batch = 8, BASELINE configs[2]) and lock-step streams
+// (8 sequences per GPU, configs[3]).
+//
+// The per-operator schedule (bgpt_kernels.cuh) spends 9 launches per layer, and its GEMV keeps
+// 4 threads on a row walking K with dependent loads: 10-17 us per kernel on 16-128 CTAs, 2.8 ms
+// per 8-row step.  Here a layer is 5 launches, every one of them wide:
+//
+//   k_sk_mm  qkv   : LayerNorm0 + quantise in the prologue (each CTA redoes the <= 8 rows: 32 KB
+//                    from L2, one warp per row, no block-wide step), 3072 stacked rows, one warp
+//                    per weight row; epilogue bias, q scale, KV append          (384 CTAs)
+//   k_sk_attn      : one (head, row) per CTA, 16 K rows in flight per warp, transposing butterfly
+//                    for the reduce trees, V with 8 rows in flight per thread; the 64 outputs leave
+//                    as two quantised blocks of out_proj's activation record     (16 x rows CTAs)
+//   k_sk_mm  o     : records staged from global; bias + residual                 (128 CTAs)
+//   k_sk_mm  fc1   : LayerNorm1 prologue, 32 consecutive rows per CTA = one block of fc2's input;
+//                    bias + fp16-table GELU + quantise in the epilogue           (128 CTAs)
+//   k_sk_mm  fc2   : K = 4096 in four 1024-wide chunks; bias + residual          (128 CTAs)
+//   k_sk_mm lm_head: final LayerNorm prologue, 32 rows per CTA                   (1325 CTAs)
+//
+// Dot products (same bits as k_gemv_q and the persistent kernels: the 8 running sums of
+// ggml_vec_dot_q*_q8_*, acc_l = fma(d_w d_a, (float) isum_l, acc_l) in block order, hsum_float_8):
+// a warp owns a weight row.  Phase A: lane (g, j) turns its 16-byte weight word -- 4 blocks x the
+// 4-element groups of sums j and j+4 -- into 8 exact integer dots per token row (dp4a) and parks them,
+// with the 4 scale products, in a warp-private shared scratch.  Phase B: lane (token, l) walks sum l
+// of its token over the 32 blocks in order.  4 token rows per round (32 chains = 32 lanes), two rounds
+// for 8 rows; the next chunk's weight words are already in registers (1-deep prefetch), and the first
+// chunk is fetched BEFORE griddepcontrol.wait, i.e. while the previous kernel of the chain is still
+// running (programmatic dependent launch): weights never wait for activations.
+#pragma once
+#include "bgpt_kernels.cuh"
+
+#define SK_NT 256
+#define SK_NW 8
+#define SK_PS 36                                   // floats between two chains of the scratch (bank spread)
+#define SK_SCR (32 * SK_PS + 4 * SK_PS + 32)       // floats of scratch per warp: products, scales, mins
+#define SK_D 1024
+#define SK_DK 64
+#define SK_ANT 512                                 // threads of the attention kernel
+
+enum { SK_EPI_STORE = 0, SK_EPI_QKV = 1, SK_EPI_RESID = 2, SK_EPI_GELUQ = 3 };
+
+struct SkArgs {
+    const uint8_t * W[3];          // up to three stacked matrices (q, k, v) of rows_per rows each
+    int rows_per, M;               // rows of one matrix, total rows
+    int npass;                     // K / 1024
+    int stride, off_qh, off_d, off_m;
+    int pro;                       // 0: activation records from `act`; 1: LayerNorm(xin) + quantise (K = 1024)
+    const uint8_t * act;
+    const float * xin; int ld_in; const float * lnw; const float * lnb; float eps;
+    int act_bytes, off_n, off_dd, off_s, code_off;      // record layout of the input
+    int n, tok0;                   // token rows [tok0, n)
+    int rpw;                       // rows per warp: a CTA covers 8 * rpw consecutive rows
+    // epilogue
+    int epi;
+    const float * bias[3];
+    float * out; int ld_out;
+    const float * resid; int ld_resid;
+    float * kcache; float * vcache; size_t stream_stride; float qscale;
+    const DevState * st; int mode;
+    const uint16_t * gelu;
+    uint8_t * act_out; int out_bytes, out_off_n, out_off_d, out_off_s;    // SK_EPI_GELUQ: record of the next matmul
+};
+
+__device__ __forceinline__ void sk_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void sk_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- 8 consecutive lanes (l = lane & 7) hold one 32-element block, lane l its elements 4l..4l+3 ----
+// quantize_row_q8_0 / q8_1 (AVX branches, ggml.c:1166-1203, 1403-1450) into the record layout of
+// bgpt_layout.h.  All 32 lanes call; `write` selects the lanes whose block is real.
+template <int FMT>
+__device__ __forceinline__ void sk_quant_block(float4 v, int b, int l, uint8_t * rec, int off_n, int off_d, int off_s, int code_off, bool write) {
+    constexpr bool Q81 = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 2));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 4));
+    const float d  = __fdiv_rn(amax, 127.0f);
+    const float id = (amax != 0.0f) ? __fdiv_rn(127.0f, amax) : 0.0f;
+    const int q0 = __float2int_rn(__fmul_rn(v.x, id)), q1 = __float2int_rn(__fmul_rn(v.y, id));
+    const int q2 = __float2int_rn(__fmul_rn(v.z, id)), q3 = __float2int_rn(__fmul_rn(v.w, id));
+    const int s4 = q0 + q1 + q2 + q3;
+    int stot = s4;
+    stot += __shfl_xor_sync(FULLMASK, stot, 1);
+    stot += __shfl_xor_sync(FULLMASK, stot, 2);
+    stot += __shfl_xor_sync(FULLMASK, stot, 4);
+    if (write) {
+        const int g = b >> 2, i = b & 3;
+        ((uint32_t *) rec)[(g * 8 + l) * 4 + i] = ((uint32_t) q0 & 0xFFu) | (((uint32_t) q1 & 0xFFu) << 8) | (((uint32_t) q2 & 0xFFu) << 16) | (((uint32_t) q3 & 0xFFu) << 24);
+        ((int32_t *) (rec + off_n))[(g * 8 + l) * 4 + i] = -code_off * s4;
+        if (l == 0) {
+            ((float *) (rec + off_d))[b] = Q81 ? d : bg_h2f(bg_f2h(d));
+            ((float *) (rec + off_s))[b] = Q81 ? __fmul_rn(d, (float) stot) : 0.0f;
+        }
+    }
+}
+
+// ---- LayerNorm + affine + quantise of one 1024-wide row by ONE warp -> record in shared memory ----
+// Same operations as bg_ln_row + bg_row_to_record (ggml.c:11403-11420; biogpt.cpp:693-700); lane holds
+// elements p*128 + 4*lane .. +3 of pass p, which is block 4p + lane/8, word lane%8.
+template <int FMT>
+__device__ __forceinline__ void sk_ln_quant_row(const float * x, const float * __restrict__ lnw, const float * __restrict__ lnb, float eps,
+                                                uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
+    const int lane = threadIdx.x & 31;
+    float4 v[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) v[p] = __ldcg((const float4 *) (x + p * 128 + lane * 4));
+    double s = 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) s += ((double) v[p].x + (double) v[p].y) + ((double) v[p].z + (double) v[p].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLMASK, s, o);
+    const float mean = (float) (s * (1.0 / SK_D));
+    double s2 = 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        v[p].x = __fsub_rn(v[p].x, mean); v[p].y = __fsub_rn(v[p].y, mean); v[p].z = __fsub_rn(v[p].z, mean); v[p].w = __fsub_rn(v[p].w, mean);
+        s2 += ((double) __fmul_rn(v[p].x, v[p].x) + (double) __fmul_rn(v[p].y, v[p].y)) + ((double) __fmul_rn(v[p].z, v[p].z) + (double) __fmul_rn(v[p].w, v[p].w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(FULLMASK, s2, o);
+    const float variance = (float) (s2 * (1.0 / SK_D));
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const float4 w = *(const float4 *) (lnw + p * 128 + lane * 4), bb = *(const float4 *) (lnb + p * 128 + lane * 4);
+        float4 y;
+        y.x = __fadd_rn(__fmul_rn(w.x, __fmul_rn(v[p].x, scale)), bb.x);
+        y.y = __fadd_rn(__fmul_rn(w.y, __fmul_rn(v[p].y, scale)), bb.y);
+        y.z = __fadd_rn(__fmul_rn(w.z, __fmul_rn(v[p].z, scale)), bb.z);
+        y.w = __fadd_rn(__fmul_rn(w.w, __fmul_rn(v[p].w, scale)), bb.w);
+        sk_quant_block<FMT>(y, p * 4 + (lane >> 3), lane & 7, rec, off_n, off_d, off_s, code_off, true);
+    }
+}
+
+// ---- weight words of one 1024-wide chunk of a row, as this lane (g = 8*pass + lane/4, j = lane%4) sees them ----
+template <int FMT> struct SkW { uint4 w0, w1; uint32_t qh; uint2 dh, mh; };
+
+template <int FMT>
+__device__ __forceinline__ void sk_load_w(SkW<FMT> & w, const uint8_t * wrow, const SkArgs & a, int pass) {
+    constexpr bool IS8   = (FMT == BG_Q8_0);
+    constexpr bool HASQH = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM  = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    const int lane = threadIdx.x & 31, g = pass * 8 + (lane >> 2), j = lane & 3;
+    if (IS8) {
+        w.w0 = ldg_stream128(wrow + (size_t) ((g * 2 + 0) * 4 + j) * 16);
+        w.w1 = ldg_stream128(wrow + (size_t) ((g * 2 + 1) * 4 + j) * 16);
+    } else {
+        w.w0 = ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
+        w.w1 = make_uint4(0, 0, 0, 0);
+    }
+    w.qh = 0;
+    if (HASQH) w.qh = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
+    w.dh = ldg_stream64(wrow + a.off_d + g * 8);
+    w.mh = make_uint2(0, 0);
+    if (HASM) w.mh = ldg_stream64(wrow + a.off_m + g * 8);
+}
+
+// one chunk (32 blocks) of one weight row against TN token records: phase A (all lanes: integer dots
+// -> scratch) and phase B (lane = (token, running sum): the fma chain in block order)
+template <int FMT, int TN>
+__device__ __forceinline__ void sk_chunk(const SkW<FMT> & w, const SkArgs & a, const uint8_t * s_rec, int pass,
+                                         float * P, float * Sm, float * Mw, float (&acc)[TN / 4], float (&summ)[TN / 4]) {
+    constexpr bool IS8    = (FMT == BG_Q8_0);
+    constexpr bool HASQH  = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM   = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    constexpr bool HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
+    const int lane = threadIdx.x & 31, gl = lane >> 2, j = lane & 3;
+    const int g = pass * 8 + gl;
+    uint32_t lo[4], hi[4];
+    if (IS8) {
+        lo[0] = w.w0.x; lo[1] = w.w0.y; lo[2] = w.w0.z; lo[3] = w.w0.w;
+        hi[0] = w.w1.x; hi[1] = w.w1.y; hi[2] = w.w1.z; hi[3] = w.w1.w;
+    } else {
+        const uint32_t ww[4] = { w.w0.x, w.w0.y, w.w0.z, w.w0.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            lo[i] = ww[i] & 0x0F0F0F0Fu;
+            hi[i] = (ww[i] >> 4) & 0x0F0F0F0Fu;
+            if (HASQH) {
+                const uint32_t hb = (w.qh >> (8 * i)) & 0xFFu;
+                lo[i] |= bg_spread4(hb & 0xFu);
+                hi[i] |= bg_spread4(hb >> 4);
+            }
+        }
+    }
+    float dw[4];
+    dw[0] = bg_h2f((uint16_t) (w.dh.x & 0xFFFF)); dw[1] = bg_h2f((uint16_t) (w.dh.x >> 16));
+    dw[2] = bg_h2f((uint16_t) (w.dh.y & 0xFFFF)); dw[3] = bg_h2f((uint16_t) (w.dh.y >> 16));
+    if (HASM && j == 1)
+        *(float4 *) (Mw + 4 * gl) = make_float4(bg_h2f((uint16_t) (w.mh.x & 0xFFFF)), bg_h2f((uint16_t) (w.mh.x >> 16)),
+                                                bg_h2f((uint16_t) (w.mh.y & 0xFFFF)), bg_h2f((uint16_t) (w.mh.y >> 16)));
+    const int tq = lane >> 3, l = lane & 7;
+#pragma unroll
+    for (int r = 0; r < TN / 4; r++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint8_t * rec = s_rec + (size_t) (r * 4 + q) * a.act_bytes;
+            const uint4 a0 = *(const uint4 *) (rec + (g * 8 + j) * 16);
+            const uint4 a1 = *(const uint4 *) (rec + (g * 8 + j + 4) * 16);
+            int4 n0 = make_int4(0, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
+            if (HASOFF) {
+                n0 = *(const int4 *) (rec + a.off_n + (g * 8 + j) * 16);
+                n1 = *(const int4 *) (rec + a.off_n + (g * 8 + j + 4) * 16);
+            }
+            const float4 da = *(const float4 *) (rec + a.off_dd + g * 16);
+            float4 P0, P1, S;
+            P0.x = (float) __dp4a((int) lo[0], (int) a0.x, n0.x); P1.x = (float) __dp4a((int) hi[0], (int) a1.x, n1.x);
+            P0.y = (float) __dp4a((int) lo[1], (int) a0.y, n0.y); P1.y = (float) __dp4a((int) hi[1], (int) a1.y, n1.y);
+            P0.z = (float) __dp4a((int) lo[2], (int) a0.z, n0.z); P1.z = (float) __dp4a((int) hi[2], (int) a1.z, n1.z);
+            P0.w = (float) __dp4a((int) lo[3], (int) a0.w, n0.w); P1.w = (float) __dp4a((int) hi[3], (int) a1.w, n1.w);
+            S.x = __fmul_rn(dw[0], da.x); S.y = __fmul_rn(dw[1], da.y); S.z = __fmul_rn(dw[2], da.z); S.w = __fmul_rn(dw[3], da.w);
+            *(float4 *) (P + (q * 8 + j) * SK_PS + 4 * gl) = P0;
+            *(float4 *) (P + (q * 8 + j + 4) * SK_PS + 4 * gl) = P1;
+            if (j == 0) *(float4 *) (Sm + q * SK_PS + 4 * gl) = S;
+        }
+        __syncwarp();
+        const uint8_t * rec = s_rec + (size_t) (r * 4 + tq) * a.act_bytes;
+        float c = acc[r], sm = summ[r];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 pv = *(const float4 *) (P + (tq * 8 + l) * SK_PS + 4 * k);
+            const float4 sv = *(const float4 *) (Sm + tq * SK_PS + 4 * k);
+            c = fmaf(sv.x, pv.x, c); c = fmaf(sv.y, pv.y, c); c = fmaf(sv.z, pv.z, c); c = fmaf(sv.w, pv.w, c);
+            if (HASM && l == 0) {
+                const float4 mv = *(const float4 *) (Mw + 4 * k);
+                const float4 sa = *(const float4 *) (rec + a.off_s + (pass * 8 + k) * 16);
+                sm = fmaf(mv.x, sa.x, sm); sm = fmaf(mv.y, sa.y, sm); sm = fmaf(mv.z, sa.z, sm); sm = fmaf(mv.w, sa.w, sm);
+            }
+        }
+        acc[r] = c; summ[r] = sm;
+        __syncwarp();
+    }
+}
+
+// grid = (ceil(M / (8 * rpw)), ceil((n - tok0) / TN)), block = 256,
+// dynamic smem = TN * act_bytes + 8 * SK_SCR * 4
+template <int FMT, int TN>
+__global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkArgs a) {
+    constexpr bool HASM = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    extern __shared__ __align__(16) uint8_t sk_smem[];
+    __shared__ __align__(16) float s_g[8 * 32];               // SK_EPI_GELUQ: [token][row of the CTA]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t * s_rec = sk_smem;
+    float * P = (float *) (sk_smem + (size_t) TN * a.act_bytes) + (size_t) warp * SK_SCR;
+    float * Sm = P + 32 * SK_PS;
+    float * Mw = Sm + 4 * SK_PS;
+    const int tokbase = a.tok0 + blockIdx.y * TN;
+    const int rowbase = blockIdx.x * SK_NW * a.rpw;
+    const int total = a.rpw * a.npass;
+    auto wrow_of = [&](int i) -> const uint8_t * {
+        int row = rowbase + i * SK_NW + warp; row = row < a.M ? row : a.M - 1;
+        const int mat = row / a.rows_per;
+        return a.W[mat] + (size_t) (row - mat * a.rows_per) * a.stride;
+    };
+    SkW<FMT> cur, nxt;
+    sk_load_w<FMT>(cur, wrow_of(0), a, 0);                     // weights do not depend on the previous kernel
+    nxt = cur;
+    sk_pdl_launch_dependents();
+    sk_pdl_wait();                                             // from here on the previous kernel's results are visible
+    // ---- token records
+    if (a.pro == 1) {
+        if (warp < TN) {
+            uint8_t * rec = s_rec + (size_t) warp * a.act_bytes;
+            const int tok = tokbase + warp;
+            if (tok < a.n) sk_ln_quant_row<FMT>(a.xin + (size_t) tok * a.ld_in, a.lnw, a.lnb, a.eps, rec, a.off_n, a.off_dd, a.off_s, a.code_off);
+            else for (int i = lane; i < (a.act_bytes >> 4); i += 32) ((uint4 *) rec)[i] = make_uint4(0, 0, 0, 0);
+        }
+    } else {
+        const int v16 = a.act_bytes >> 4;
+        for (int i = tid; i < TN * v16; i += SK_NT) {
+            const int t = i / v16, o = i - t * v16;
+            uint4 z = make_uint4(0, 0, 0, 0);
+            if (tokbase + t < a.n) z = __ldcg((const uint4 *) (a.act + (size_t) (tokbase + t) * a.act_bytes + (size_t) o * 16));
+            ((uint4 *) s_rec)[i] = z;
+        }
+    }
+    __syncthreads();
+    const int tq = lane >> 3, l = lane & 7;
+    float acc[TN / 4], summ[TN / 4];
+#pragma unroll 1
+    for (int s = 0; s < total; s++) {
+        const int i = s / a.npass, pass = s - i * a.npass;
+        if (s + 1 < total) { const int i2 = (s + 1) / a.npass; sk_load_w<FMT>(nxt, wrow_of(i2), a, (s + 1) - i2 * a.npass); }
+        if (pass == 0) {
+#pragma unroll
+            for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
+        }
+        sk_chunk<FMT, TN>(cur, a, s_rec, pass, P, Sm, Mw, acc, summ);
+        if (pass == a.npass - 1) {
+            const int row = rowbase + i * SK_NW + warp;
+#pragma unroll
+            for (int r = 0; r < TN / 4; r++) {
+                // hsum_float_8: (a_l + a_{l+4}), then the pairs 2 apart, then 1 apart (ggml.c:611-617)
+                float v = __fadd_rn(acc[r], __shfl_xor_sync(FULLMASK, acc[r], 4));
+                v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 2));
+                v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 1));
+                if (HASM) v = __fadd_rn(v, summ[r]);
+                const int tok = tokbase + r * 4 + tq;
+                if (l == 0 && row < a.M && tok < a.n) {
+                    switch (a.epi) {
+                    case SK_EPI_STORE:
+                        a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(a.bias[0][row], v) : v;
+                        break;
+                    case SK_EPI_QKV: {
+                        const int mat = row / a.rows_per, rr = row - mat * a.rows_per;
+                        const float t = __fadd_rn(a.bias[mat][rr], v);
+                        if (mat == 0) a.out[(size_t) tok * a.ld_out + rr] = __fmul_rn(t, a.qscale);
+                        else {
+                            int stream, pos, T; bg_row_info(a.mode, a.n, a.st->n_past, tok, stream, pos, T);
+                            (mat == 1 ? a.kcache : a.vcache)[(size_t) stream * a.stream_stride + (size_t) pos * a.rows_per + rr] = t;
+                        }
+                        break; }
+                    case SK_EPI_RESID:
+                        a.out[(size_t) tok * a.ld_out + row] = __fadd_rn(__fadd_rn(v, a.bias[0][row]), __ldcg(a.resid + (size_t) tok * a.ld_resid + row));
+                        break;
+                    default:
+                        s_g[(r * 4 + tq) * 32 + (i * SK_NW + warp)] = bg_h2f(a.gelu[bg_f2h(__fadd_rn(a.bias[0][row], v))]);
+                        break;
+                    }
+                }
+            }
+        }
+        cur = nxt;
+    }
+    if (a.epi == SK_EPI_GELUQ) {                               // the CTA's 32 rows are block blockIdx.x of the next record
+        __syncthreads();
+        if (warp < TN) {
+            const int tok = tokbase + warp;
+            const float4 v = *(const float4 *) (s_g + warp * 32 + 4 * l);
+            const bool wr = tok < a.n && lane < 8;
+            uint8_t * rec = a.act_out + (size_t) (tok < a.n ? tok : 0) * a.out_bytes;
+            sk_quant_block<FMT>(v, blockIdx.x, l, rec, a.out_off_n, a.out_off_d, a.out_off_s, a.code_off, wr);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_sk_attn: softmax(K q) V of one (head, token row), un-masked over T positions, d_kv = 64,
+// T <= 1024; the 64 outputs are quantised into blocks 2h, 2h+1 of out_proj's activation record.
+// Arithmetic order = k_attn / the persistent kernels (ggml_vec_dot_f32 lanes, the xor 16,8,4,1,2
+// tree, fp16 exp table, double sum, the as-built scalar tail of the V product).
+// grid = (n_head, rows), block = 512.
+// ---------------------------------------------------------------------------------------------
+struct SkAttnArgs {
+    const float * q; int ld_q;
+    const float * kcache; const float * vcache; size_t stream_stride;
+    uint8_t * act; int act_bytes, off_n, off_d, off_s, code_off;
+    int n, mode; const DevState * st;
+    const uint16_t * exp_tab;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(SK_ANT, 1) k_sk_attn(const __grid_constant__ SkAttnArgs a) {
+    constexpr int NW = SK_ANT / 32;
+    __shared__ __align__(16) float sc[1024];
+    __shared__ __align__(16) float red[32 * SK_DK];
+    __shared__ __align__(16) float tailv[31 * SK_DK];
+    __shared__ __align__(16) float s_out[SK_DK];
+    __shared__ double sredA[NW];
+    __shared__ float sredF[NW];
+    const int h = blockIdx.x, row = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int stream, pos, T; bg_row_info(a.mode, a.n, a.st->n_past, row, stream, pos, T);     // n_past: constant of the whole graph
+    const float * Kb = a.kcache + (size_t) stream * a.stream_stride + (size_t) h * SK_DK;
+    const float * Vb = a.vcache + (size_t) stream * a.stream_stride + (size_t) h * SK_DK;
+    // rows cached by earlier evals can be pulled towards the L2 while the q,k,v projection is still running
+    {
+        const int told = a.st->n_past;
+        for (int t = tid; t < told; t += SK_ANT) {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(Kb + (size_t) t * SK_D));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(Kb + (size_t) t * SK_D + 32));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(Vb + (size_t) t * SK_D));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(Vb + (size_t) t * SK_D + 32));
+        }
+    }
+    sk_pdl_launch_dependents();
+    sk_pdl_wait();
+    const float q0 = __ldcg(a.q + (size_t) row * a.ld_q + h * SK_DK + lane), q1 = __ldcg(a.q + (size_t) row * a.ld_q + h * SK_DK + 32 + lane);
+    // ---- scores: 16 K rows per warp pass
+#pragma unroll 1
+    for (int tb = warp; tb < T; tb += NW * 16) {
+        float kr[16][2];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const int t = tb + u * NW;
+            kr[u][0] = (t < T) ? __ldcg(Kb + (size_t) t * SK_D + lane) : 0.0f;
+            kr[u][1] = (t < T) ? __ldcg(Kb + (size_t) t * SK_D + 32 + lane) : 0.0f;
+        }
+        float s[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) { float x = 0.0f; x = fmaf(kr[u][0], q0, x); x = fmaf(kr[u][1], q1, x); s[u] = x; }
+        // 16 reduce trees (xor 16, 8, 4, 1, 2: GGML_F32x8_REDUCE) as one transposing butterfly
+        float a8[8], a4[4], a2[2];
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b0 = lane & 1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float mine = b4 ? s[8 + i] : s[i], send = b4 ? s[i] : s[8 + i]; a8[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 16)); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float mine = b3 ? a8[4 + i] : a8[i], send = b3 ? a8[i] : a8[4 + i]; a4[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 8)); }
+#pragma unroll
+        for (int i = 0; i < 2; i++) { const float mine = b2 ? a4[2 + i] : a4[i], send = b2 ? a4[i] : a4[2 + i]; a2[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 4)); }
+        const float mine = b0 ? a2[1] : a2[0], send = b0 ? a2[0] : a2[1];
+        const float a1 = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 1));
+        const float dot = __fadd_rn(a1, __shfl_xor_sync(FULLMASK, a1, 2));
+        const int u = ((lane >> 1) & 14) | (lane & 1);              // bits 4,3,2 -> u bits 3,2,1; bit 0 -> u bit 0
+        const int t = tb + u * NW;
+        if (t < T && !(lane & 2)) sc[t] = dot;
+    }
+    // V rows of the scalar tail, staged so the tail is not a chain of global loads
+    const int np = T & ~31;
+    for (int i = tid; i < (T - np) * SK_DK; i += SK_ANT) tailv[i] = __ldcg(Vb + (size_t) (np + i / SK_DK) * SK_D + (i % SK_DK));
+    __syncthreads();
+    // ---- softmax over sc[0..T): max, fp16-table exp, sum in double (exact for fp16 values), scale
+    {
+        const float x0 = tid < T ? sc[tid] : -INFINITY, x1 = tid + SK_ANT < T ? sc[tid + SK_ANT] : -INFINITY;
+        float mx = fmaxf(x0, x1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
+        if (lane == 0) sredF[warp] = mx;
+        __syncthreads();
+        mx = sredF[lane & 15];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
+        float e0 = 0.f, e1 = 0.f;
+        if (tid < T) e0 = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(x0, mx))]);
+        if (tid + SK_ANT < T) e1 = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(x1, mx))]);
+        double sm = (double) e0 + (double) e1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(FULLMASK, sm, o);
+        if (lane == 0) sredA[warp] = sm;
+        __syncthreads();
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; i++) tot += sredA[i];
+        const float inv = (float) (1.0 / tot);
+        if (tid < T) sc[tid] = __fmul_rn(e0, inv);
+        if (tid + SK_ANT < T) sc[tid + SK_ANT] = __fmul_rn(e1, inv);
+    }
+    __syncthreads();
+    // ---- V: thread (r = tid / 16, 4 columns): running sum r over t = r, r + 32, ... < np, 8 rows in flight
+    {
+        const int vr = tid >> 4, vc = tid & 15;
+        const float * vp = Vb + (size_t) vr * SK_D + 4 * vc;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int s0 = 0; s0 < np; s0 += 256) {
+            float4 vv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int t = s0 + 32 * k + vr;
+                vv[k] = (t < np) ? __ldcg((const float4 *) (vp + (size_t) (s0 + 32 * k) * SK_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int t = s0 + 32 * k + vr;
+                if (t < np) {
+                    const float pw = sc[t];
+                    acc.x = fmaf(vv[k].x, pw, acc.x); acc.y = fmaf(vv[k].y, pw, acc.y);
+                    acc.z = fmaf(vv[k].z, pw, acc.z); acc.w = fmaf(vv[k].w, pw, acc.w);
+                }
+            }
+        }
+        *(float4 *) (red + vr * SK_DK + 4 * vc) = acc;
+    }
+    __syncthreads();
+    if (tid < SK_DK) {
+        float x0[8];
+#pragma unroll
+        for (int l8 = 0; l8 < 8; l8++) {
+            const float a02 = __fadd_rn(red[(0 * 8 + l8) * SK_DK + tid], red[(2 * 8 + l8) * SK_DK + tid]);
+            const float a13 = __fadd_rn(red[(1 * 8 + l8) * SK_DK + tid], red[(3 * 8 + l8) * SK_DK + tid]);
+            x0[l8] = __fadd_rn(a02, a13);
+        }
+        const float t0 = __fadd_rn(x0[0], x0[4]), t1 = __fadd_rn(x0[1], x0[5]);
+        const float t2 = __fadd_rn(x0[2], x0[6]), t3 = __fadd_rn(x0[3], x0[7]);
+        float sumf = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+        const int nv = np + ((T - np) & ~3);
+        int t = np;
+#pragma unroll 1
+        for (; t < nv; t++) sumf = __fadd_rn(sumf, __fmul_rn(tailv[(t - np) * SK_DK + tid], sc[t]));
+#pragma unroll 1
+        for (; t < T;  t++) sumf = fmaf(tailv[(t - np) * SK_DK + tid], sc[t], sumf);
+        s_out[tid] = sumf;
+    }
+    __syncthreads();
+    if (warp == 0) {                                             // lanes 0..15: block lane / 8, word lane % 8
+        const int blk = (lane >> 3) & 1, l = lane & 7;
+        const float4 v = *(const float4 *) (s_out + blk * 32 + 4 * l);
+        sk_quant_block<FMT>(v, h * 2 + blk, l, a.act + (size_t) row * a.act_bytes, a.off_n, a.off_d, a.off_s, a.code_off, lane < 16);
+    }
+}

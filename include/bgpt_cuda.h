@@ -113,6 +113,18 @@ int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int
  * used for n > 1 and for lock-step streams).  All produce identical bits; tests compare them. */
 int bgpt_cuda_set_decode_path(bgpt_model * m, int path);
 int bgpt_cuda_get_decode_path(const bgpt_model * m);
+/* Which schedule evaluates skinny batches (2 <= n < 32 token rows: prompt chunks of the reference's
+ * n_batch = 8 and lock-step streams): 1 = the fused schedule of csrc/bgpt_skinny.cuh (default where
+ * it applies: quantised weights at BioGPT-base layer shapes; 5 launches per layer, LayerNorm /
+ * quantise / GELU folded into the matmul kernels, programmatic dependent launch), 0 = one kernel
+ * per fused operator.  Identical bits; tests compare them.  get: 1 if an n_rows-row eval would run
+ * on the fused schedule. */
+int bgpt_cuda_set_batch_path(bgpt_model * m, int path);
+int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows);
+/* debug: copy one of the eval arena's buffers as the last eval left it (0 x, 1 x1, 2 q, 3 the d_model-wide activation
+ * records, 4 the d_ff-wide activation records; `rows` token rows) to HOST memory; returns the bytes copied, -1 on error.
+ * tools/skinny_check.py uses it to localise a mismatch between the two batch schedules. */
+long long bgpt_cuda_debug_read_buffer(bgpt_model * m, int which, int rows, void * out, long long cap_bytes);
 /* 4 or 3: the persistent-kernel generation single-token steps run on; 0: per-operator kernels */
 int bgpt_cuda_decode_kernel_generation(const bgpt_model * m);
 /* debug (env BGPT_MEGA_PROF=1 at load): per-phase clock64 stamps of CTA 0 of the last

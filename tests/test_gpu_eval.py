@@ -177,6 +177,65 @@ def test_generation4_kernel_equals_oracle_and_generation3(checkers, capi, zoo, f
     O.close(); M.close()
 
 
+@pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftype):
+    """BioGPT-base layer shapes, 2..31 token rows: the fused skinny-batch schedule (csrc/bgpt_skinny.cuh: LayerNorm /
+    quantise / GELU folded into warp-per-row matmul kernels, attention with a quantising epilogue, programmatic dependent
+    launch).  Un-masked prompt batches of every tile shape (4- and 8-row tiles, two tiles, ragged last tile) at T across
+    the 32-wide boundary, both scalar tails, T > 512 and the end of the context must give the oracle's bits and the
+    per-operator schedule's bits."""
+    hp = gf.NARROW
+    p = zoo.path("narrow", ftype)
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p, max_batch=32)
+    assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(32) == 0, capi.last_error()
+    toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=55)
+    sizes = [8, 8, 5, 2, 3, 4, 7, 16, 9, 1, 8, 31, 8, 6]             # 116 positions: T = 8, 16, 21, 23, 26, 30, 37, 53, 62, 63, 71, 102, ...
+    sched, pos = [], 0
+    for n in sizes:
+        sched.append((pos, n)); pos += n
+    while pos < 500:
+        sched.append((pos, 24)); pos += 24                              # 3 tiles of 8
+    for n in (8, 8, 8, 3, 8, 8):
+        sched.append((pos, n)); pos += n
+    while pos < 1000:
+        sched.append((pos, 16)); pos += 16
+    while pos < hp.n_positions:
+        n = min(8, hp.n_positions - pos); sched.append((pos, n)); pos += n
+    got_fused = []
+    for pos, n in sched:
+        want = O.eval(toks[pos:pos + n], pos)
+        got = M.eval(toks[pos:pos + n], pos)
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} fused schedule n={n} at {pos}", got, want)
+        got_fused.append(got)
+    M.set_batch_path(0)
+    assert M.batch_path(8) == 0
+    for (pos, n), ref in zip(sched, got_fused):
+        got = M.eval(toks[pos:pos + n], pos)
+        assert np.array_equal(_bits(got), _bits(ref)), (ftype, pos, n)
+    O.close(); M.close()
+
+
+@pytest.mark.parametrize("ftype", ["q5_1", "q4_0", "q8_0"])
+def test_skinny_lockstep_streams_equal_single_stream(capi, zoo, ftype):
+    """config 4 at BioGPT-base layer shapes: S sequences in lock step on the fused skinny-batch schedule; every stream must
+    equal its own single-stream run (generation-4 persistent kernel) bit for bit, for 4- and 8-row tiles and two tiles"""
+    hp = gf.NARROW
+    p = zoo.path("narrow", ftype)
+    steps = 40
+    for S in (8, 3, 12):
+        seqs = [gf.synth_tokens(steps, hp.n_vocab, seed=300 + 7 * S + s) for s in range(S)]
+        M = capi.Model.load(p, max_batch=16)
+        single = [np.stack([M.eval(seqs[s][i:i + 1], i) for i in range(steps)]) for s in range(S)]
+        M.set_streams(S)
+        assert M.batch_path(S) == 1
+        for i in range(steps):
+            out = M.eval_streams(np.array([seqs[s][i] for s in range(S)], np.int32), i)
+            for s in range(S):
+                assert np.array_equal(_bits(out[s]), _bits(single[s][i])), _diff(f"{ftype} S={S} stream {s} step {i}", out[s], single[s][i])
+        M.close()
+
+
 def test_persistent_kernel_long_context(checkers, capi, zoo):
     """prompt in un-masked batches of 8 (per-op kernels), then persistent-kernel decode near the end
     of the context"""

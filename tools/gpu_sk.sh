@@ -1,0 +1,47 @@
+#!/bin/bash
+# GPU-box visit for the fused skinny-batch schedule: bash tools/gpu_sk.sh <tag> "<stages>"
+TAG=${1:-sk}
+STAGES=${2:-"check tests perf"}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+for st in $STAGES; do
+case $st in
+check)
+  timeout 600 python tools/skinny_check.py > $OUT/check.log 2>&1; echo "check rc=$?"; cat $OUT/check.log | tail -40 ;;
+tests)
+  timeout 1500 python -m pytest tests/test_gpu_eval.py -m gpu -x -q -k "skinny or base_shape or generation4" > $OUT/pytest_sk.log 2>&1; echo "pytest rc=$?"
+  tail -15 $OUT/pytest_sk.log ;;
+alltests)
+  timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+  tail -20 $OUT/pytest_gpu.log ;;
+perf)
+  for pdl in 1 0; do
+    echo "== BGPT_PDL=$pdl"
+    BGPT_PDL=$pdl timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64
+    BGPT_PDL=$pdl timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480
+    BGPT_PDL=$pdl timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8,16
+  done > $OUT/perf.log 2>&1
+  echo "== BGPT_BATCH_PATH=0 (per-operator schedule)" >> $OUT/perf.log
+  BGPT_BATCH_PATH=0 timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64 >> $OUT/perf.log 2>&1
+  BGPT_BATCH_PATH=0 timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8 >> $OUT/perf.log 2>&1
+  cat $OUT/perf.log ;;
+launches)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_streams.csv \
+      python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 2 --n-past 511 --reps 1 > $OUT/launches_streams.log 2>&1; echo "launches rc=$?"
+  python tools/launch_summary.py $OUT/launches_streams.csv | tee $OUT/launches_streams_summary.txt ;;
+full)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sk_mm -s 6 -c 5 -f -o $OUT/sk_mm_full \
+      python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 2 --n-past 511 --reps 1 > $OUT/sk_mm_full.log 2>&1; echo "full rc=$?"
+  ncu -i $OUT/sk_mm_full.ncu-rep --page raw --csv > $OUT/sk_mm_full_raw.csv 2>/dev/null
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sk_attn -s 1 -c 1 -f -o $OUT/sk_attn_full \
+      python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 2 --n-past 511 --reps 1 > $OUT/sk_attn_full.log 2>&1; echo "full attn rc=$?"
+  ncu -i $OUT/sk_attn_full.ncu-rep --page raw --csv > $OUT/sk_attn_full_raw.csv 2>/dev/null
+  rm -f $OUT/*.ncu-rep.tmp; ls -la $OUT ;;
+bench)
+  timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+  cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
+smoke)
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke.log ;;
+esac
+done

@@ -1,5 +1,5 @@
 """BASELINE.json configs[3]: S independent streams decoded in lock-step on one GPU (each weight read is shared by the S
-streams; every stream has its own F32 KV cache), per-operator schedule.  Host argmax per stream (greedy).
+streams; every stream has its own F32 KV cache), fused skinny-batch schedule (BGPT_BATCH_PATH=0: per-operator schedule).  Host argmax per stream (greedy).
    python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64 [--n-past 0]"""
 import argparse, os, sys, time
 import numpy as np
@@ -12,13 +12,14 @@ ap.add_argument("--ftype", default="q5_1")
 ap.add_argument("--streams", type=int, default=8)
 ap.add_argument("--steps", type=int, default=64)
 ap.add_argument("--n-past", type=int, default=0)
+ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 capi = importlib.import_module("biogpt_cpp_b200.capi")
 gf = bench.gf
 M = capi.Model.load(bench.model_path(a.ftype), max_batch=max(8, a.streams))
 M.set_streams(a.streams)
 tok = gf.synth_tokens(a.streams, gf.BASE.n_vocab, seed=9).astype(np.int32)
-for warm in range(2):
+for warm in range(a.reps):
     t_dev = 0.0
     cur = tok.copy()
     t0 = time.perf_counter()
