@@ -108,6 +108,7 @@ struct bgpt_model {
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
+    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -336,6 +337,9 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_GRAPH")) m->use_graphs = atoi(getenv("BGPT_GRAPH")) != 0;
     if (getenv("BGPT_PDL")) m->use_pdl = atoi(getenv("BGPT_PDL")) != 0;
     if (getenv("BGPT_BATCH_PATH")) m->batch_path = atoi(getenv("BGPT_BATCH_PATH")) != 0;
+    if (getenv("BGPT_SK_PDL_TRIG")) m->sk_pdl_trig = atoi(getenv("BGPT_SK_PDL_TRIG")) != 0;
+    if (getenv("BGPT_SK_TN_PROJ")) m->sk_tn_proj = atoi(getenv("BGPT_SK_TN_PROJ")) == 8 ? 8 : 4;
+    if (getenv("BGPT_SK_TN_QKV")) m->sk_tn_qkv = atoi(getenv("BGPT_SK_TN_QKV")) == 4 ? 4 : 8;
     RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
@@ -600,16 +604,18 @@ static int sk_launch(bgpt_model * m, const void * fn, dim3 grid, int threads, si
     return BGPT_OK;
 }
 // one k_sk_mm launch over token rows [tok0, n)
-static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int nmat, const ActLayout & A, int n, int tok0, int rpw) {
+static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int nmat, const ActLayout & A, int n, int tok0, int rpw, int tn_pref) {
     const RowLayout & L = W[0]->L;
     for (int i = 0; i < 3; i++) a.W[i] = W[i < nmat ? i : 0]->ptr;
     a.rows_per = (int) W[0]->ne1; a.M = a.rows_per * nmat; a.npass = L.K / 1024;
     a.stride = L.stride; a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
     a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s; a.code_off = bg_code_offset(m->wtype);
     a.n = n; a.tok0 = tok0; a.rpw = rpw; a.eps = 1e-5f;         // NORM_EPS, biogpt.cpp:24
-    const int cnt = n - tok0, TN = cnt <= 4 ? 4 : 8;
+    a.pdl_trig = m->sk_pdl_trig;
+    // 4-row tiles double the CTAs of the kernels that have only 1024-4096 weight rows to spread over 148 SMs (a warp owns a row)
+    const int cnt = n - tok0, TN = (cnt <= 4 || tn_pref == 4) ? 4 : 8;
     dim3 grid((a.M + SK_NW * rpw - 1) / (SK_NW * rpw), (cnt + TN - 1) / TN);
-    const size_t smem = (size_t) TN * A.bytes + (size_t) SK_NW * SK_SCR * 4;
+    const size_t smem = (size_t) TN * A.bytes + (a.pro == 1 ? 2 * SK_D * 4 : 0) + (size_t) SK_NW * SK_SCR * 4;
     return sk_launch(m, sk_mm_fn_of(m->wtype, TN), grid, SK_NT, smem, &a);
 }
 
@@ -633,7 +639,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             a.out = m->q; a.ld_out = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
             a.qscale = 1.0f / sqrtf((float) dk);                 // biogpt.cpp:681
             a.st = m->st; a.mode = mode;
-            RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 1));
+            RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 1, m->sk_tn_qkv));
         }
         {   // attention + quantise for out_proj                     biogpt.cpp:730-764
             SkAttnArgs a{};
@@ -647,7 +653,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             const DevTensor * W[3] = { L.o_w, nullptr, nullptr };
             a.pro = 0; a.act = m->act_d;
             a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.o_b->ptr; a.out = m->x1; a.ld_out = d; a.resid = m->x; a.ld_resid = d;
-            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 1));
+            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 1, m->sk_tn_proj));
         }
         {   // LayerNorm1 + fc1 + bias + GELU + quantise for fc2     biogpt.cpp:779-787
             SkArgs a{};
@@ -655,14 +661,14 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             a.pro = 1; a.xin = m->x1; a.ld_in = d; a.lnw = (const float *) L.ln1_w->ptr; a.lnb = (const float *) L.ln1_b->ptr;
             a.epi = SK_EPI_GELUQ; a.bias[0] = (const float *) L.fc1_b->ptr; a.gelu = m->gelu_tab;
             a.act_out = m->act_ff; a.out_bytes = m->A_ff.bytes; a.out_off_n = m->A_ff.off_n; a.out_off_d = m->A_ff.off_d; a.out_off_s = m->A_ff.off_s;
-            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 4));
+            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 4, m->sk_tn_proj));
         }
         {   // fc2 + bias + residual                                 biogpt.cpp:790-795
             SkArgs a{};
             const DevTensor * W[3] = { L.fc2_w, nullptr, nullptr };
             a.pro = 0; a.act = m->act_ff;
             a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.fc2_b->ptr; a.out = m->x; a.ld_out = d; a.resid = m->x1; a.ld_resid = d;
-            RET(sk_mm(m, a, W, 1, m->A_ff, n, 0, 1));
+            RET(sk_mm(m, a, W, 1, m->A_ff, n, 0, 1, m->sk_tn_proj));
         }
     }
     // the reference computes all n rows and returns the last (biogpt.cpp:803, 844); rows are independent, so only the
@@ -673,7 +679,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
         const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };
         a.pro = 1; a.xin = m->x; a.ld_in = d; a.lnw = (const float *) m->ln_w->ptr; a.lnb = (const float *) m->ln_b->ptr;
         a.epi = SK_EPI_STORE; a.out = m->logits - (size_t) tok0 * m->n_vocab; a.ld_out = m->n_vocab;
-        RET(sk_mm(m, a, W, 1, m->A_d, n, tok0, 4));
+        RET(sk_mm(m, a, W, 1, m->A_d, n, tok0, 4, 8));
     } else {
         RET(launch_act(m, s, m->x, d, m->ln_w, m->ln_b, d, wt, m->act_d, m->A_d, n, nullptr, 0));
         const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };

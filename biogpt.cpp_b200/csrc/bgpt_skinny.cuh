@@ -10,8 +10,8 @@
 //   k_sk_mm  qkv   : LayerNorm0 + quantise in the prologue (each CTA redoes the <= 8 rows: 32 KB
 //                    from L2, one warp per row, no block-wide step), 3072 stacked rows, one warp
 //                    per weight row; epilogue bias, q scale, KV append          (384 CTAs)
-//   k_sk_attn      : one (head, row) per CTA, 16 K rows in flight per warp, transposing butterfly
-//                    for the reduce trees, V with 8 rows in flight per thread; the 64 outputs leave
+//   k_sk_attn      : one (head, row) per CTA of 1024 threads, 16 K rows in flight per warp, transposing butterfly
+//                    for the reduce trees, V with 16 rows in flight per thread; the 64 outputs leave
 //                    as two quantised blocks of out_proj's activation record     (16 x rows CTAs)
 //   k_sk_mm  o     : records staged from global; bias + residual                 (128 CTAs)
 //   k_sk_mm  fc1   : LayerNorm1 prologue, 32 consecutive rows per CTA = one block of fc2's input;
@@ -30,6 +30,7 @@
 // running (programmatic dependent launch): weights never wait for activations.
 #pragma once
 #include "bgpt_kernels.cuh"
+#include "bgpt_mega4.cuh"      // mbarrier / bulk-copy helpers
 
 #define SK_NT 256
 #define SK_NW 8
@@ -37,7 +38,7 @@
 #define SK_SCR (32 * SK_PS + 4 * SK_PS + 32)       // floats of scratch per warp: products, scales, mins
 #define SK_D 1024
 #define SK_DK 64
-#define SK_ANT 512                                 // threads of the attention kernel
+#define SK_ANT 1024                                // threads of the attention kernel
 
 enum { SK_EPI_STORE = 0, SK_EPI_QKV = 1, SK_EPI_RESID = 2, SK_EPI_GELUQ = 3 };
 
@@ -52,6 +53,7 @@ struct SkArgs {
     int act_bytes, off_n, off_dd, off_s, code_off;      // record layout of the input
     int n, tok0;                   // token rows [tok0, n)
     int rpw;                       // rows per warp: a CTA covers 8 * rpw consecutive rows
+    int pdl_trig;                  // griddepcontrol.launch_dependents: 0 at the start of the kernel, 1 after the dot products
     // epilogue
     int epi;
     const float * bias[3];
@@ -100,7 +102,7 @@ __device__ __forceinline__ void sk_quant_block(float4 v, int b, int l, uint8_t *
 // Same operations as bg_ln_row + bg_row_to_record (ggml.c:11403-11420; biogpt.cpp:693-700); lane holds
 // elements p*128 + 4*lane .. +3 of pass p, which is block 4p + lane/8, word lane%8.
 template <int FMT>
-__device__ __forceinline__ void sk_ln_quant_row(const float * x, const float * __restrict__ lnw, const float * __restrict__ lnb, float eps,
+__device__ __forceinline__ void sk_ln_quant_row(const float * x, const float * lnw /*shared*/, const float * lnb /*shared*/, float eps,
                                                 uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
     const int lane = threadIdx.x & 31;
     float4 v[8];
@@ -235,50 +237,68 @@ __device__ __forceinline__ void sk_chunk(const SkW<FMT> & w, const SkArgs & a, c
 }
 
 // grid = (ceil(M / (8 * rpw)), ceil((n - tok0) / TN)), block = 256,
-// dynamic smem = TN * act_bytes + 8 * SK_SCR * 4
+// dynamic smem = TN * act_bytes + (pro ? 8192 : 0) + 8 * SK_SCR * 4
 template <int FMT, int TN>
 __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkArgs a) {
     constexpr bool HASM = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
     extern __shared__ __align__(16) uint8_t sk_smem[];
     __shared__ __align__(16) float s_g[8 * 32];               // SK_EPI_GELUQ: [token][row of the CTA]
+    __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t * s_rec = sk_smem;
-    float * P = (float *) (sk_smem + (size_t) TN * a.act_bytes) + (size_t) warp * SK_SCR;
+    float * s_ln = (float *) (sk_smem + (size_t) TN * a.act_bytes);                 // LayerNorm weight | bias (pro == 1)
+    float * P = s_ln + (a.pro == 1 ? 2 * SK_D : 0) + (size_t) warp * SK_SCR;
     float * Sm = P + 32 * SK_PS;
     float * Mw = Sm + 4 * SK_PS;
     const int tokbase = a.tok0 + blockIdx.y * TN;
     const int rowbase = blockIdx.x * SK_NW * a.rpw;
     const int total = a.rpw * a.npass;
+    const int tq = lane >> 3, l = lane & 7;
     auto wrow_of = [&](int i) -> const uint8_t * {
         int row = rowbase + i * SK_NW + warp; row = row < a.M ? row : a.M - 1;
         const int mat = row / a.rows_per;
         return a.W[mat] + (size_t) (row - mat * a.rows_per) * a.stride;
     };
+    // ---- everything that does not depend on the previous kernel: first weight chunk, LayerNorm parameters, n_past
     SkW<FMT> cur, nxt;
-    sk_load_w<FMT>(cur, wrow_of(0), a, 0);                     // weights do not depend on the previous kernel
+    sk_load_w<FMT>(cur, wrow_of(0), a, 0);
     nxt = cur;
-    sk_pdl_launch_dependents();
+    int n_past = 0;
+    if (a.epi == SK_EPI_QKV) n_past = a.st->n_past;
+    if (a.pro == 1) {
+        for (int i = tid; i < 2 * SK_D / 4; i += SK_NT)
+            ((float4 *) s_ln)[i] = i < SK_D / 4 ? *((const float4 *) a.lnw + i) : *((const float4 *) a.lnb + (i - SK_D / 4));
+    } else if (tid == 0) {
+        m4_mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (a.pdl_trig == 0) sk_pdl_launch_dependents();
+    __syncthreads();
     sk_pdl_wait();                                             // from here on the previous kernel's results are visible
     // ---- token records
     if (a.pro == 1) {
         if (warp < TN) {
             uint8_t * rec = s_rec + (size_t) warp * a.act_bytes;
             const int tok = tokbase + warp;
-            if (tok < a.n) sk_ln_quant_row<FMT>(a.xin + (size_t) tok * a.ld_in, a.lnw, a.lnb, a.eps, rec, a.off_n, a.off_dd, a.off_s, a.code_off);
+            if (tok < a.n) sk_ln_quant_row<FMT>(a.xin + (size_t) tok * a.ld_in, s_ln, s_ln + SK_D, a.eps, rec, a.off_n, a.off_dd, a.off_s, a.code_off);
             else for (int i = lane; i < (a.act_bytes >> 4); i += 32) ((uint4 *) rec)[i] = make_uint4(0, 0, 0, 0);
         }
-    } else {
-        const int v16 = a.act_bytes >> 4;
-        for (int i = tid; i < TN * v16; i += SK_NT) {
-            const int t = i / v16, o = i - t * v16;
-            uint4 z = make_uint4(0, 0, 0, 0);
-            if (tokbase + t < a.n) z = __ldcg((const uint4 *) (a.act + (size_t) (tokbase + t) * a.act_bytes + (size_t) o * 16));
-            ((uint4 *) s_rec)[i] = z;
+    } else {                                                   // consecutive records are contiguous: ONE bulk copy (TMA), no register staging
+        int nv = a.n - tokbase; nv = nv > TN ? TN : nv;
+        const uint32_t bytes = (uint32_t) nv * (uint32_t) a.act_bytes;
+        if (tid == 0) {
+            m4_mbar_expect(&s_bar, bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(m4_s32(s_rec)), "l"(a.act + (size_t) tokbase * a.act_bytes), "r"(bytes), "r"(m4_s32(&s_bar)) : "memory");
         }
+        for (int i = (int) (bytes >> 4) + tid; i < TN * (a.act_bytes >> 4); i += SK_NT) ((uint4 *) s_rec)[i] = make_uint4(0, 0, 0, 0);
+        m4_mbar_wait(&s_bar, 0);
     }
     __syncthreads();
-    const int tq = lane >> 3, l = lane & 7;
     float acc[TN / 4], summ[TN / 4];
+    float pbias = 0.0f, presid[TN / 4];
+#pragma unroll
+    for (int r = 0; r < TN / 4; r++) presid[r] = 0.0f;
 #pragma unroll 1
     for (int s = 0; s < total; s++) {
         const int i = s / a.npass, pass = s - i * a.npass;
@@ -286,6 +306,16 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
         if (pass == 0) {
 #pragma unroll
             for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
+            // the row owner's bias / residual are in flight while the dots run
+            const int row = rowbase + i * SK_NW + warp;
+            if (l == 0 && row < a.M) {
+                if (a.epi == SK_EPI_QKV) { const int mat = row / a.rows_per; pbias = a.bias[mat][row - mat * a.rows_per]; }
+                else if (a.bias[0]) pbias = a.bias[0][row];
+                if (a.epi == SK_EPI_RESID) {
+#pragma unroll
+                    for (int r = 0; r < TN / 4; r++) { const int tok = tokbase + r * 4 + tq; if (tok < a.n) presid[r] = __ldcg(a.resid + (size_t) tok * a.ld_resid + row); }
+                }
+            }
         }
         sk_chunk<FMT, TN>(cur, a, s_rec, pass, P, Sm, Mw, acc, summ);
         if (pass == a.npass - 1) {
@@ -301,22 +331,22 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
                 if (l == 0 && row < a.M && tok < a.n) {
                     switch (a.epi) {
                     case SK_EPI_STORE:
-                        a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(a.bias[0][row], v) : v;
+                        a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(pbias, v) : v;
                         break;
                     case SK_EPI_QKV: {
                         const int mat = row / a.rows_per, rr = row - mat * a.rows_per;
-                        const float t = __fadd_rn(a.bias[mat][rr], v);
+                        const float t = __fadd_rn(pbias, v);
                         if (mat == 0) a.out[(size_t) tok * a.ld_out + rr] = __fmul_rn(t, a.qscale);
                         else {
-                            int stream, pos, T; bg_row_info(a.mode, a.n, a.st->n_past, tok, stream, pos, T);
+                            int stream, pos, T; bg_row_info(a.mode, a.n, n_past, tok, stream, pos, T);
                             (mat == 1 ? a.kcache : a.vcache)[(size_t) stream * a.stream_stride + (size_t) pos * a.rows_per + rr] = t;
                         }
                         break; }
                     case SK_EPI_RESID:
-                        a.out[(size_t) tok * a.ld_out + row] = __fadd_rn(__fadd_rn(v, a.bias[0][row]), __ldcg(a.resid + (size_t) tok * a.ld_resid + row));
+                        a.out[(size_t) tok * a.ld_out + row] = __fadd_rn(__fadd_rn(v, pbias), presid[r]);
                         break;
-                    default:
-                        s_g[(r * 4 + tq) * 32 + (i * SK_NW + warp)] = bg_h2f(a.gelu[bg_f2h(__fadd_rn(a.bias[0][row], v))]);
+                    default:                                   // GELU input; the table look-ups run as one batch after the loop
+                        s_g[(r * 4 + tq) * 32 + (i * SK_NW + warp)] = __fadd_rn(pbias, v);
                         break;
                     }
                 }
@@ -324,7 +354,10 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
         }
         cur = nxt;
     }
+    if (a.pdl_trig == 1) sk_pdl_launch_dependents();
     if (a.epi == SK_EPI_GELUQ) {                               // the CTA's 32 rows are block blockIdx.x of the next record
+        __syncthreads();
+        for (int i = tid; i < TN * 32; i += SK_NT) s_g[i] = bg_h2f(a.gelu[bg_f2h(s_g[i])]);
         __syncthreads();
         if (warp < TN) {
             const int tok = tokbase + warp;
@@ -341,7 +374,7 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
 // T <= 1024; the 64 outputs are quantised into blocks 2h, 2h+1 of out_proj's activation record.
 // Arithmetic order = k_attn / the persistent kernels (ggml_vec_dot_f32 lanes, the xor 16,8,4,1,2
 // tree, fp16 exp table, double sum, the as-built scalar tail of the V product).
-// grid = (n_head, rows), block = 512.
+// grid = (n_head, rows), block = 1024: at T <= 512 every K row and every V row of the head is requested in ONE batch of loads.
 // ---------------------------------------------------------------------------------------------
 struct SkAttnArgs {
     const float * q; int ld_q;
@@ -412,55 +445,52 @@ __global__ void __launch_bounds__(SK_ANT, 1) k_sk_attn(const __grid_constant__ S
     __syncthreads();
     // ---- softmax over sc[0..T): max, fp16-table exp, sum in double (exact for fp16 values), scale
     {
-        const float x0 = tid < T ? sc[tid] : -INFINITY, x1 = tid + SK_ANT < T ? sc[tid + SK_ANT] : -INFINITY;
-        float mx = fmaxf(x0, x1);
+        const float x0 = tid < T ? sc[tid] : -INFINITY;
+        float mx = x0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
         if (lane == 0) sredF[warp] = mx;
         __syncthreads();
-        mx = sredF[lane & 15];
+        mx = sredF[lane];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
-        float e0 = 0.f, e1 = 0.f;
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
+        float e0 = 0.f;
         if (tid < T) e0 = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(x0, mx))]);
-        if (tid + SK_ANT < T) e1 = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(x1, mx))]);
-        double sm = (double) e0 + (double) e1;
+        double sm = (double) e0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(FULLMASK, sm, o);
         if (lane == 0) sredA[warp] = sm;
         __syncthreads();
-        double tot = 0.0;
+        double tot = sredA[lane];
 #pragma unroll
-        for (int i = 0; i < NW; i++) tot += sredA[i];
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULLMASK, tot, o);
         const float inv = (float) (1.0 / tot);
         if (tid < T) sc[tid] = __fmul_rn(e0, inv);
-        if (tid + SK_ANT < T) sc[tid + SK_ANT] = __fmul_rn(e1, inv);
     }
     __syncthreads();
-    // ---- V: thread (r = tid / 16, 4 columns): running sum r over t = r, r + 32, ... < np, 8 rows in flight
+    // ---- V: thread (r = tid / 32, 2 columns): running sum r over t = r, r + 32, ... < np, 16 rows in flight
     {
-        const int vr = tid >> 4, vc = tid & 15;
-        const float * vp = Vb + (size_t) vr * SK_D + 4 * vc;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int vr = tid >> 5, vc = tid & 31;
+        const float * vp = Vb + (size_t) vr * SK_D + 2 * vc;
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll 1
-        for (int s0 = 0; s0 < np; s0 += 256) {
-            float4 vv[8];
+        for (int s0 = 0; s0 < np; s0 += 512) {
+            float2 vv[16];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < 16; k++) {
                 const int t = s0 + 32 * k + vr;
-                vv[k] = (t < np) ? __ldcg((const float4 *) (vp + (size_t) (s0 + 32 * k) * SK_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vv[k] = (t < np) ? __ldcg((const float2 *) (vp + (size_t) (s0 + 32 * k) * SK_D)) : make_float2(0.f, 0.f);
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < 16; k++) {
                 const int t = s0 + 32 * k + vr;
                 if (t < np) {
                     const float pw = sc[t];
                     acc.x = fmaf(vv[k].x, pw, acc.x); acc.y = fmaf(vv[k].y, pw, acc.y);
-                    acc.z = fmaf(vv[k].z, pw, acc.z); acc.w = fmaf(vv[k].w, pw, acc.w);
                 }
             }
         }
-        *(float4 *) (red + vr * SK_DK + 4 * vc) = acc;
+        *(float2 *) (red + vr * SK_DK + 2 * vc) = acc;
     }
     __syncthreads();
     if (tid < SK_DK) {

@@ -16,15 +16,12 @@ alltests)
   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"
   tail -20 $OUT/pytest_gpu.log ;;
 perf)
-  for pdl in 1 0; do
-    echo "== BGPT_PDL=$pdl"
-    BGPT_PDL=$pdl timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64
-    BGPT_PDL=$pdl timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480
-    BGPT_PDL=$pdl timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8,16
+  for v in "" "BGPT_PDL=0" "BGPT_SK_PDL_TRIG=0" "BGPT_SK_TN_PROJ=8" "BGPT_SK_TN_QKV=4" "BGPT_PDL=0 BGPT_SK_TN_QKV=4" "BGPT_BATCH_PATH=0"; do
+    echo "== variant: ${v:-default}"
+    env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64
+    env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 1
+    env $v timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8
   done > $OUT/perf.log 2>&1
-  echo "== BGPT_BATCH_PATH=0 (per-operator schedule)" >> $OUT/perf.log
-  BGPT_BATCH_PATH=0 timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64 >> $OUT/perf.log 2>&1
-  BGPT_BATCH_PATH=0 timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8 >> $OUT/perf.log 2>&1
   cat $OUT/perf.log ;;
 launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_streams.csv \
