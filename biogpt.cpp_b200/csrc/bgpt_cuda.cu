@@ -108,7 +108,7 @@ struct bgpt_model {
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
-    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV)
+    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8, sk_ln_kernel = 1, sk_skip = 0;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_LN, BGPT_SK_SKIP)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -340,6 +340,8 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_PDL_TRIG")) m->sk_pdl_trig = atoi(getenv("BGPT_SK_PDL_TRIG")) != 0;
     if (getenv("BGPT_SK_TN_PROJ")) m->sk_tn_proj = atoi(getenv("BGPT_SK_TN_PROJ")) == 8 ? 8 : 4;
     if (getenv("BGPT_SK_TN_QKV")) m->sk_tn_qkv = atoi(getenv("BGPT_SK_TN_QKV")) == 4 ? 4 : 8;
+    if (getenv("BGPT_SK_LN")) m->sk_ln_kernel = atoi(getenv("BGPT_SK_LN")) != 0;
+    if (getenv("BGPT_SK_SKIP")) m->sk_skip = atoi(getenv("BGPT_SK_SKIP"));
     RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
@@ -581,6 +583,14 @@ static const void * sk_mm_fn_of(int wtype, int TN) {
     }
     return nullptr;
 }
+static const void * sk_ln_fn_of(int wtype) {
+    switch (wtype) {
+        case BG_Q4_0: return (const void *) k_sk_ln<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_ln<BG_Q4_1>;
+        case BG_Q5_0: return (const void *) k_sk_ln<BG_Q5_0>; case BG_Q5_1: return (const void *) k_sk_ln<BG_Q5_1>;
+        case BG_Q8_0: return (const void *) k_sk_ln<BG_Q8_0>;
+    }
+    return nullptr;
+}
 static const void * sk_attn_fn_of(int wtype) {
     switch (wtype) {
         case BG_Q4_0: return (const void *) k_sk_attn<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_attn<BG_Q4_1>;
@@ -619,9 +629,26 @@ static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int n
     return sk_launch(m, sk_mm_fn_of(m->wtype, TN), grid, SK_NT, smem, &a);
 }
 
+// LayerNorm + quantise of n rows into the d_model-wide activation records (k_sk_ln), or -- BGPT_SK_LN=0 -- left to the
+// consumer matmul's prologue
+static int sk_ln(bgpt_model * m, SkArgs & a, const float * x, const DevTensor * w, const DevTensor * b, int n) {
+    if (!m->sk_ln_kernel) {
+        a.pro = 1; a.xin = x; a.ld_in = m->d_model; a.lnw = (const float *) w->ptr; a.lnb = (const float *) b->ptr;
+        return BGPT_OK;
+    }
+    a.pro = 0; a.act = m->act_d;
+    if (m->sk_skip & 64) return BGPT_OK;
+    SkLnArgs l{};
+    l.xin = x; l.ld_in = m->d_model; l.lnw = (const float *) w->ptr; l.lnb = (const float *) b->ptr; l.eps = 1e-5f;
+    l.act = m->act_d; l.act_bytes = m->A_d.bytes; l.off_n = m->A_d.off_n; l.off_d = m->A_d.off_d; l.off_s = m->A_d.off_s;
+    l.code_off = bg_code_offset(m->wtype); l.pdl_trig = m->sk_pdl_trig;
+    return sk_launch(m, sk_ln_fn_of(m->wtype), dim3(n), 256, 0, &l);
+}
+
 static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, int mode) {
     cudaStream_t s = m->stream;
     const int d = m->d_model, ff = m->d_ff, dk = d / m->n_head, wt = m->wtype;
+    const int skip = m->sk_skip;                                // timing breakdown only (BGPT_SK_SKIP): results are garbage when set
     sk_init_attrs();
     k_embed<<<n, 256, 0, s>>>(m->embed_tokens->ptr, m->embed_pos->ptr, wt, d_tokens, m->st, mode, n, d, m->n_vocab,
                               (int) m->embed_pos->ne1, sqrtf((float) d), m->x);
@@ -634,41 +661,41 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
         {   // LayerNorm0 + q,k,v + bias + q scale + KV append      biogpt.cpp:693-727
             SkArgs a{};
             const DevTensor * W[3] = { L.q_w, L.k_w, L.v_w };
-            a.pro = 1; a.xin = m->x; a.ld_in = d; a.lnw = (const float *) L.ln0_w->ptr; a.lnb = (const float *) L.ln0_b->ptr;
+            RET(sk_ln(m, a, m->x, L.ln0_w, L.ln0_b, n));
             a.epi = SK_EPI_QKV; a.bias[0] = (const float *) L.q_b->ptr; a.bias[1] = (const float *) L.k_b->ptr; a.bias[2] = (const float *) L.v_b->ptr;
             a.out = m->q; a.ld_out = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
             a.qscale = 1.0f / sqrtf((float) dk);                 // biogpt.cpp:681
             a.st = m->st; a.mode = mode;
-            RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 1, m->sk_tn_qkv));
+            if (!(skip & 1)) RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 1, m->sk_tn_qkv));
         }
         {   // attention + quantise for out_proj                     biogpt.cpp:730-764
             SkAttnArgs a{};
             a.q = m->q; a.ld_q = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
             a.act = m->act_d; a.act_bytes = m->A_d.bytes; a.off_n = m->A_d.off_n; a.off_d = m->A_d.off_d; a.off_s = m->A_d.off_s;
             a.code_off = bg_code_offset(wt); a.n = n; a.mode = mode; a.st = m->st; a.exp_tab = m->exp_tab;
-            RET(sk_launch(m, sk_attn_fn_of(wt), dim3(m->n_head, n), SK_ANT, 0, &a));
+            if (!(skip & 2)) RET(sk_launch(m, sk_attn_fn_of(wt), dim3(m->n_head, n), SK_ANT, 0, &a));
         }
         {   // out_proj + bias + residual                            biogpt.cpp:767-772
             SkArgs a{};
             const DevTensor * W[3] = { L.o_w, nullptr, nullptr };
             a.pro = 0; a.act = m->act_d;
             a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.o_b->ptr; a.out = m->x1; a.ld_out = d; a.resid = m->x; a.ld_resid = d;
-            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 1, m->sk_tn_proj));
+            if (!(skip & 4)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 1, m->sk_tn_proj));
         }
         {   // LayerNorm1 + fc1 + bias + GELU + quantise for fc2     biogpt.cpp:779-787
             SkArgs a{};
             const DevTensor * W[3] = { L.fc1_w, nullptr, nullptr };
-            a.pro = 1; a.xin = m->x1; a.ld_in = d; a.lnw = (const float *) L.ln1_w->ptr; a.lnb = (const float *) L.ln1_b->ptr;
+            RET(sk_ln(m, a, m->x1, L.ln1_w, L.ln1_b, n));
             a.epi = SK_EPI_GELUQ; a.bias[0] = (const float *) L.fc1_b->ptr; a.gelu = m->gelu_tab;
             a.act_out = m->act_ff; a.out_bytes = m->A_ff.bytes; a.out_off_n = m->A_ff.off_n; a.out_off_d = m->A_ff.off_d; a.out_off_s = m->A_ff.off_s;
-            RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 4, m->sk_tn_proj));
+            if (!(skip & 8)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 4, m->sk_tn_proj));
         }
         {   // fc2 + bias + residual                                 biogpt.cpp:790-795
             SkArgs a{};
             const DevTensor * W[3] = { L.fc2_w, nullptr, nullptr };
             a.pro = 0; a.act = m->act_ff;
             a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.fc2_b->ptr; a.out = m->x; a.ld_out = d; a.resid = m->x1; a.ld_resid = d;
-            RET(sk_mm(m, a, W, 1, m->A_ff, n, 0, 1, m->sk_tn_proj));
+            if (!(skip & 16)) RET(sk_mm(m, a, W, 1, m->A_ff, n, 0, 1, m->sk_tn_proj));
         }
     }
     // the reference computes all n rows and returns the last (biogpt.cpp:803, 844); rows are independent, so only the
@@ -677,9 +704,9 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
     if (n - tok0 >= 2) {
         SkArgs a{};
         const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };
-        a.pro = 1; a.xin = m->x; a.ld_in = d; a.lnw = (const float *) m->ln_w->ptr; a.lnb = (const float *) m->ln_b->ptr;
+        RET(sk_ln(m, a, m->x, m->ln_w, m->ln_b, n));
         a.epi = SK_EPI_STORE; a.out = m->logits - (size_t) tok0 * m->n_vocab; a.ld_out = m->n_vocab;
-        RET(sk_mm(m, a, W, 1, m->A_d, n, tok0, 4, 8));
+        if (!(skip & 32)) RET(sk_mm(m, a, W, 1, m->A_d, n, tok0, 4, 8));
     } else {
         RET(launch_act(m, s, m->x, d, m->ln_w, m->ln_b, d, wt, m->act_d, m->A_d, n, nullptr, 0));
         const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };

@@ -136,6 +136,47 @@ __device__ __forceinline__ void sk_ln_quant_row(const float * x, const float * l
     }
 }
 
+// ---- stand-alone LayerNorm + quantise: one token row per CTA of 256 threads (thread t: elements 4t..4t+3 = block t/8, word t%8),
+// record to global memory; the matmul kernels then stage the records with one bulk copy.  Doing the LayerNorm ONCE instead of
+// in the prologue of each of a matmul's 256-768 CTAs takes ~1000 instructions per warp off their critical path.
+struct SkLnArgs {
+    const float * xin; int ld_in; const float * lnw; const float * lnb; float eps;
+    uint8_t * act; int act_bytes, off_n, off_d, off_s, code_off;
+    int pdl_trig;
+};
+template <int FMT>
+__global__ void __launch_bounds__(256, 4) k_sk_ln(const __grid_constant__ SkLnArgs a) {
+    __shared__ double sA[8], sB[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = blockIdx.x;
+    const float4 w = *((const float4 *) a.lnw + tid), bb = *((const float4 *) a.lnb + tid);
+    if (a.pdl_trig == 0) sk_pdl_launch_dependents();
+    sk_pdl_wait();
+    float4 v = __ldcg((const float4 *) (a.xin + (size_t) row * a.ld_in) + tid);
+    double s = ((double) v.x + (double) v.y) + ((double) v.z + (double) v.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLMASK, s, o);
+    if (lane == 0) sA[warp] = s;
+    __syncthreads();
+    s = ((sA[0] + sA[1]) + (sA[2] + sA[3])) + ((sA[4] + sA[5]) + (sA[6] + sA[7]));
+    const float mean = (float) (s * (1.0 / SK_D));
+    v.x = __fsub_rn(v.x, mean); v.y = __fsub_rn(v.y, mean); v.z = __fsub_rn(v.z, mean); v.w = __fsub_rn(v.w, mean);
+    double s2 = ((double) __fmul_rn(v.x, v.x) + (double) __fmul_rn(v.y, v.y)) + ((double) __fmul_rn(v.z, v.z) + (double) __fmul_rn(v.w, v.w));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(FULLMASK, s2, o);
+    if (lane == 0) sB[warp] = s2;
+    __syncthreads();
+    s2 = ((sB[0] + sB[1]) + (sB[2] + sB[3])) + ((sB[4] + sB[5]) + (sB[6] + sB[7]));
+    if (a.pdl_trig == 1) sk_pdl_launch_dependents();
+    const float variance = (float) (s2 * (1.0 / SK_D));
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, a.eps)));
+    float4 y;
+    y.x = __fadd_rn(__fmul_rn(w.x, __fmul_rn(v.x, scale)), bb.x);
+    y.y = __fadd_rn(__fmul_rn(w.y, __fmul_rn(v.y, scale)), bb.y);
+    y.z = __fadd_rn(__fmul_rn(w.z, __fmul_rn(v.z, scale)), bb.z);
+    y.w = __fadd_rn(__fmul_rn(w.w, __fmul_rn(v.w, scale)), bb.w);
+    sk_quant_block<FMT>(y, tid >> 3, tid & 7, a.act + (size_t) row * a.act_bytes, a.off_n, a.off_d, a.off_s, a.code_off, true);
+}
+
 // ---- weight words of one 1024-wide chunk of a row, as this lane (g = 8*pass + lane/4, j = lane%4) sees them ----
 template <int FMT> struct SkW { uint4 w0, w1; uint32_t qh; uint2 dh, mh; };
 
@@ -254,15 +295,25 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
     const int rowbase = blockIdx.x * SK_NW * a.rpw;
     const int total = a.rpw * a.npass;
     const int tq = lane >> 3, l = lane & 7;
+    auto mat_of = [&](int row) -> int { return row >= 2 * a.rows_per ? 2 : (row >= a.rows_per ? 1 : 0); };       // no integer division in the loop
     auto wrow_of = [&](int i) -> const uint8_t * {
         int row = rowbase + i * SK_NW + warp; row = row < a.M ? row : a.M - 1;
-        const int mat = row / a.rows_per;
+        const int mat = mat_of(row);
         return a.W[mat] + (size_t) (row - mat * a.rows_per) * a.stride;
     };
-    // ---- everything that does not depend on the previous kernel: first weight chunk, LayerNorm parameters, n_past
+    // ---- everything that does not depend on the previous kernel: the warp's weight rows towards the L2, the first weight
+    //      chunk into registers, LayerNorm parameters, n_past
     SkW<FMT> cur, nxt;
     sk_load_w<FMT>(cur, wrow_of(0), a, 0);
     nxt = cur;
+    if (total > 1) {
+#pragma unroll 1
+        for (int i = 0; i < a.rpw; i++) {
+            const uint8_t * wr = wrow_of(i);
+#pragma unroll 1
+            for (int off = lane * 128; off < a.stride; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(wr + off));
+        }
+    }
     int n_past = 0;
     if (a.epi == SK_EPI_QKV) n_past = a.st->n_past;
     if (a.pro == 1) {
@@ -300,16 +351,15 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
 #pragma unroll
     for (int r = 0; r < TN / 4; r++) presid[r] = 0.0f;
 #pragma unroll 1
-    for (int s = 0; s < total; s++) {
-        const int i = s / a.npass, pass = s - i * a.npass;
-        if (s + 1 < total) { const int i2 = (s + 1) / a.npass; sk_load_w<FMT>(nxt, wrow_of(i2), a, (s + 1) - i2 * a.npass); }
+    for (int s = 0, i = 0, pass = 0; s < total; s++) {
+        if (s + 1 < total) { const bool wrap = pass + 1 == a.npass; sk_load_w<FMT>(nxt, wrow_of(wrap ? i + 1 : i), a, wrap ? 0 : pass + 1); }
         if (pass == 0) {
 #pragma unroll
             for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
             // the row owner's bias / residual are in flight while the dots run
             const int row = rowbase + i * SK_NW + warp;
             if (l == 0 && row < a.M) {
-                if (a.epi == SK_EPI_QKV) { const int mat = row / a.rows_per; pbias = a.bias[mat][row - mat * a.rows_per]; }
+                if (a.epi == SK_EPI_QKV) { const int mat = mat_of(row); pbias = a.bias[mat][row - mat * a.rows_per]; }
                 else if (a.bias[0]) pbias = a.bias[0][row];
                 if (a.epi == SK_EPI_RESID) {
 #pragma unroll
@@ -334,7 +384,7 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
                         a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(pbias, v) : v;
                         break;
                     case SK_EPI_QKV: {
-                        const int mat = row / a.rows_per, rr = row - mat * a.rows_per;
+                        const int mat = mat_of(row), rr = row - mat * a.rows_per;
                         const float t = __fadd_rn(pbias, v);
                         if (mat == 0) a.out[(size_t) tok * a.ld_out + rr] = __fmul_rn(t, a.qscale);
                         else {
@@ -353,6 +403,7 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
             }
         }
         cur = nxt;
+        if (++pass == a.npass) { pass = 0; i++; }
     }
     if (a.pdl_trig == 1) sk_pdl_launch_dependents();
     if (a.epi == SK_EPI_GELUQ) {                               // the CTA's 32 rows are block blockIdx.x of the next record

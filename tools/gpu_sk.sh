@@ -16,13 +16,21 @@ alltests)
   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"
   tail -20 $OUT/pytest_gpu.log ;;
 perf)
-  for v in "" "BGPT_PDL=0" "BGPT_SK_PDL_TRIG=0" "BGPT_SK_TN_PROJ=8" "BGPT_SK_TN_QKV=4" "BGPT_PDL=0 BGPT_SK_TN_QKV=4" "BGPT_BATCH_PATH=0"; do
+  for v in "" "BGPT_SK_PDL_TRIG=0" "BGPT_PDL=0" "BGPT_SK_LN=0" "BGPT_SK_LN=0 BGPT_SK_PDL_TRIG=0" "BGPT_BATCH_PATH=0"; do
     echo "== variant: ${v:-default}"
     env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64
     env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 1
     env $v timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8
   done > $OUT/perf.log 2>&1
   cat $OUT/perf.log ;;
+skips)
+  # in-graph cost of each kernel kind: the step time with that kind of launch left out (results are garbage, timing only)
+  for v in "" "BGPT_SK_PDL_TRIG=0"; do
+  for k in 0 1 2 4 8 16 32 64; do
+    echo "== $v BGPT_SK_SKIP=$k (1 qkv, 2 attention, 4 out_proj, 8 fc1, 16 fc2, 32 lm_head, 64 LayerNorm kernels)"
+    env $v BGPT_SK_SKIP=$k timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 2
+  done; done > $OUT/skips.log 2>&1
+  cat $OUT/skips.log ;;
 launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_streams.csv \
       python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 2 --n-past 511 --reps 1 > $OUT/launches_streams.log 2>&1; echo "launches rc=$?"
