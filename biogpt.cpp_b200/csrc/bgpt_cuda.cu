@@ -108,7 +108,7 @@ struct bgpt_model {
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
-    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8, sk_ln_kernel = 1, sk_skip = 0;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_LN, BGPT_SK_SKIP)
+    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8, sk_ln_kernel = 1, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_LN, BGPT_SK_SKIP)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -342,6 +342,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_TN_QKV")) m->sk_tn_qkv = atoi(getenv("BGPT_SK_TN_QKV")) == 4 ? 4 : 8;
     if (getenv("BGPT_SK_LN")) m->sk_ln_kernel = atoi(getenv("BGPT_SK_LN")) != 0;
     if (getenv("BGPT_SK_SKIP")) m->sk_skip = atoi(getenv("BGPT_SK_SKIP"));
+    if (getenv("BGPT_SK_KVPF")) m->sk_kv_prefetch = atoi(getenv("BGPT_SK_KVPF")) != 0;
     RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
@@ -564,22 +565,25 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
 // fused skinny-batch schedule (bgpt_skinny.cuh): 5 launches per layer, programmatic dependent launch
 // ------------------------------------------------------------------------------------------
 static bool skinny_ok(const bgpt_model * m, int n) {
-    return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff % 1024 == 0 &&
+    return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff == 4096 &&
            m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < tc_min_rows();
 }
 static void sk_init_attrs() {
     static bool done = false;
     if (done) return;
     done = true;
-#define ATTR_SK(F) allow_big_smem(k_sk_mm<F, 4>); allow_big_smem(k_sk_mm<F, 8>);
+#define ATTR_SK(F) allow_big_smem(k_sk_mm<F, 4, 1>); allow_big_smem(k_sk_mm<F, 8, 1>); allow_big_smem(k_sk_mm<F, 4, 4>); allow_big_smem(k_sk_mm<F, 8, 4>);
     ATTR_SK(BG_Q4_0) ATTR_SK(BG_Q4_1) ATTR_SK(BG_Q5_0) ATTR_SK(BG_Q5_1) ATTR_SK(BG_Q8_0)
     cudaGetLastError();
 }
-template <int FMT> static const void * sk_mm_fn(int TN) { return TN == 4 ? (const void *) k_sk_mm<FMT, 4> : (const void *) k_sk_mm<FMT, 8>; }
-static const void * sk_mm_fn_of(int wtype, int TN) {
+template <int FMT> static const void * sk_mm_fn(int TN, int nch) {
+    if (nch == 1) return TN == 4 ? (const void *) k_sk_mm<FMT, 4, 1> : (const void *) k_sk_mm<FMT, 8, 1>;
+    return TN == 4 ? (const void *) k_sk_mm<FMT, 4, 4> : (const void *) k_sk_mm<FMT, 8, 4>;
+}
+static const void * sk_mm_fn_of(int wtype, int TN, int nch) {
     switch (wtype) {
-        case BG_Q4_0: return sk_mm_fn<BG_Q4_0>(TN); case BG_Q4_1: return sk_mm_fn<BG_Q4_1>(TN); case BG_Q5_0: return sk_mm_fn<BG_Q5_0>(TN);
-        case BG_Q5_1: return sk_mm_fn<BG_Q5_1>(TN); case BG_Q8_0: return sk_mm_fn<BG_Q8_0>(TN);
+        case BG_Q4_0: return sk_mm_fn<BG_Q4_0>(TN, nch); case BG_Q4_1: return sk_mm_fn<BG_Q4_1>(TN, nch); case BG_Q5_0: return sk_mm_fn<BG_Q5_0>(TN, nch);
+        case BG_Q5_1: return sk_mm_fn<BG_Q5_1>(TN, nch); case BG_Q8_0: return sk_mm_fn<BG_Q8_0>(TN, nch);
     }
     return nullptr;
 }
@@ -626,7 +630,9 @@ static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int n
     const int cnt = n - tok0, TN = (cnt <= 4 || tn_pref == 4) ? 4 : 8;
     dim3 grid((a.M + SK_NW * rpw - 1) / (SK_NW * rpw), (cnt + TN - 1) / TN);
     const size_t smem = (size_t) TN * A.bytes + (a.pro == 1 ? 2 * SK_D * 4 : 0) + (size_t) SK_NW * SK_SCR * 4;
-    return sk_launch(m, sk_mm_fn_of(m->wtype, TN), grid, SK_NT, smem, &a);
+    const int nch = rpw * a.npass;
+    if (nch != 1 && nch != 4) return fail(BGPT_E_UNSUPPORTED, "skinny matmul: %d chunks per warp (d_ff must be 4096)", nch);
+    return sk_launch(m, sk_mm_fn_of(m->wtype, TN, nch), grid, SK_NT, smem, &a);
 }
 
 // LayerNorm + quantise of n rows into the d_model-wide activation records (k_sk_ln), or -- BGPT_SK_LN=0 -- left to the
@@ -666,6 +672,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             a.out = m->q; a.ld_out = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
             a.qscale = 1.0f / sqrtf((float) dk);                 // biogpt.cpp:681
             a.st = m->st; a.mode = mode;
+            if (m->sk_kv_prefetch) a.pf_streams = mode == 1 ? n : 1;      // the kernel reads n_past from device memory: one graph serves every position
             if (!(skip & 1)) RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 1, m->sk_tn_qkv));
         }
         {   // attention + quantise for out_proj                     biogpt.cpp:730-764

@@ -62,6 +62,7 @@ struct SkArgs {
     float * kcache; float * vcache; size_t stream_stride; float qscale;
     const DevState * st; int mode;
     const uint16_t * gelu;
+    int pf_streams;                // SK_EPI_QKV: streams whose cached K/V rows (n_past positions) are prefetched into the L2 for the attention kernel
     uint8_t * act_out; int out_bytes, out_off_n, out_off_d, out_off_s;    // SK_EPI_GELUQ: record of the next matmul
 };
 
@@ -279,8 +280,11 @@ __device__ __forceinline__ void sk_chunk(const SkW<FMT> & w, const SkArgs & a, c
 
 // grid = (ceil(M / (8 * rpw)), ceil((n - tok0) / TN)), block = 256,
 // dynamic smem = TN * act_bytes + (pro ? 8192 : 0) + 8 * SK_SCR * 4
-template <int FMT, int TN>
-__global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkArgs a) {
+// NCH = rpw * npass, the 1024-wide weight chunks a warp walks (1 or 4): ALL of them are requested before
+// griddepcontrol.wait and wait in registers, so no HBM / L2 round trip sits between two chunks.
+template <int FMT, int TN, int NCH>
+__global__ void __launch_bounds__(SK_NT, NCH == 1 ? 3 : 2) k_sk_mm(const __grid_constant__ SkArgs a) {
+    static_assert(NCH == 1 || NCH == 4, "a warp walks 1 or 4 chunks");
     constexpr bool HASM = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
     extern __shared__ __align__(16) uint8_t sk_smem[];
     __shared__ __align__(16) float s_g[8 * 32];               // SK_EPI_GELUQ: [token][row of the CTA]
@@ -301,21 +305,30 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
         const int mat = mat_of(row);
         return a.W[mat] + (size_t) (row - mat * a.rows_per) * a.stride;
     };
-    // ---- everything that does not depend on the previous kernel: the warp's weight rows towards the L2, the first weight
-    //      chunk into registers, LayerNorm parameters, n_past
-    SkW<FMT> cur, nxt;
+    // ---- everything that does not depend on the previous kernel: the warp's weight chunks into registers, the K/V rows the
+    //      attention kernel behind this one will read towards the L2, LayerNorm parameters, n_past
+    SkW<FMT> cur, w1, w2, w3;
     sk_load_w<FMT>(cur, wrow_of(0), a, 0);
-    nxt = cur;
-    if (total > 1) {
-#pragma unroll 1
-        for (int i = 0; i < a.rpw; i++) {
-            const uint8_t * wr = wrow_of(i);
-#pragma unroll 1
-            for (int off = lane * 128; off < a.stride; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(wr + off));
-        }
+    w1 = cur; w2 = cur; w3 = cur;
+    if (NCH == 4) {
+        const bool byrow = a.npass == 1;                      // 4 rows x 1 chunk (fc1, lm_head) or 1 row x 4 chunks (fc2)
+        sk_load_w<FMT>(w1, wrow_of(byrow ? 1 : 0), a, byrow ? 0 : 1);
+        sk_load_w<FMT>(w2, wrow_of(byrow ? 2 : 0), a, byrow ? 0 : 2);
+        sk_load_w<FMT>(w3, wrow_of(byrow ? 3 : 0), a, byrow ? 0 : 3);
     }
     int n_past = 0;
-    if (a.epi == SK_EPI_QKV) n_past = a.st->n_past;
+    if (a.epi == SK_EPI_QKV) {
+        n_past = a.st->n_past;
+        if (a.pf_streams > 0 && n_past > 0 && blockIdx.y == 0) {     // 64 lines of 128 bytes per cached position and stream (K row | V row)
+            const int per = n_past * 64, totl = per * a.pf_streams;
+#pragma unroll 1
+            for (int idx = blockIdx.x * SK_NT + tid; idx < totl; idx += gridDim.x * SK_NT) {
+                const int sidx = idx / per, rem = idx - sidx * per, t = rem >> 6, j = rem & 63;
+                const float * base = (j < 32 ? a.kcache : a.vcache) + (size_t) sidx * a.stream_stride + (size_t) t * SK_D + (j & 31) * 32;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(base));
+            }
+        }
+    }
     if (a.pro == 1) {
         for (int i = tid; i < 2 * SK_D / 4; i += SK_NT)
             ((float4 *) s_ln)[i] = i < SK_D / 4 ? *((const float4 *) a.lnw + i) : *((const float4 *) a.lnb + (i - SK_D / 4));
@@ -352,7 +365,6 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
     for (int r = 0; r < TN / 4; r++) presid[r] = 0.0f;
 #pragma unroll 1
     for (int s = 0, i = 0, pass = 0; s < total; s++) {
-        if (s + 1 < total) { const bool wrap = pass + 1 == a.npass; sk_load_w<FMT>(nxt, wrow_of(wrap ? i + 1 : i), a, wrap ? 0 : pass + 1); }
         if (pass == 0) {
 #pragma unroll
             for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
@@ -402,7 +414,7 @@ __global__ void __launch_bounds__(SK_NT, 3) k_sk_mm(const __grid_constant__ SkAr
                 }
             }
         }
-        cur = nxt;
+        if (NCH == 4) { cur = w1; w1 = w2; w2 = w3; }
         if (++pass == a.npass) { pass = 0; i++; }
     }
     if (a.pdl_trig == 1) sk_pdl_launch_dependents();

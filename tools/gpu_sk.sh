@@ -16,7 +16,7 @@ alltests)
   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"
   tail -20 $OUT/pytest_gpu.log ;;
 perf)
-  for v in "" "BGPT_SK_PDL_TRIG=0" "BGPT_PDL=0" "BGPT_SK_LN=0" "BGPT_SK_LN=0 BGPT_SK_PDL_TRIG=0" "BGPT_BATCH_PATH=0"; do
+  for v in "X=0" "BGPT_SK_KVPF=0" "BGPT_SK_PDL_TRIG=0" "BGPT_PDL=0"; do
     echo "== variant: ${v:-default}"
     env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64
     env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 1
@@ -25,7 +25,7 @@ perf)
   cat $OUT/perf.log ;;
 skips)
   # in-graph cost of each kernel kind: the step time with that kind of launch left out (results are garbage, timing only)
-  for v in "" "BGPT_SK_PDL_TRIG=0"; do
+  for v in "X=0"; do
   for k in 0 1 2 4 8 16 32 64; do
     echo "== $v BGPT_SK_SKIP=$k (1 qkv, 2 attention, 4 out_proj, 8 fc1, 16 fc2, 32 lm_head, 64 LayerNorm kernels)"
     env $v BGPT_SK_SKIP=$k timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 2
