@@ -108,7 +108,7 @@ struct bgpt_model {
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
-    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8, sk_ln_kernel = 1, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_LN, BGPT_SK_SKIP)
+    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -340,7 +340,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_PDL_TRIG")) m->sk_pdl_trig = atoi(getenv("BGPT_SK_PDL_TRIG")) != 0;
     if (getenv("BGPT_SK_TN_PROJ")) m->sk_tn_proj = atoi(getenv("BGPT_SK_TN_PROJ")) == 8 ? 8 : 4;
     if (getenv("BGPT_SK_TN_QKV")) m->sk_tn_qkv = atoi(getenv("BGPT_SK_TN_QKV")) == 4 ? 4 : 8;
-    if (getenv("BGPT_SK_LN")) m->sk_ln_kernel = atoi(getenv("BGPT_SK_LN")) != 0;
+    if (getenv("BGPT_SK_FC1_NW")) m->sk_fc1_nw = atoi(getenv("BGPT_SK_FC1_NW")) == 8 ? 8 : 16;
     if (getenv("BGPT_SK_SKIP")) m->sk_skip = atoi(getenv("BGPT_SK_SKIP"));
     if (getenv("BGPT_SK_KVPF")) m->sk_kv_prefetch = atoi(getenv("BGPT_SK_KVPF")) != 0;
     RET(mega_setup(m));
@@ -572,18 +572,15 @@ static void sk_init_attrs() {
     static bool done = false;
     if (done) return;
     done = true;
-#define ATTR_SK(F) allow_big_smem(k_sk_mm<F, 4, 1>); allow_big_smem(k_sk_mm<F, 8, 1>); allow_big_smem(k_sk_mm<F, 4, 4>); allow_big_smem(k_sk_mm<F, 8, 4>);
+#define ATTR_SK(F) allow_big_smem(k_sk_mm<F, 4>); allow_big_smem(k_sk_mm<F, 8>);
     ATTR_SK(BG_Q4_0) ATTR_SK(BG_Q4_1) ATTR_SK(BG_Q5_0) ATTR_SK(BG_Q5_1) ATTR_SK(BG_Q8_0)
     cudaGetLastError();
 }
-template <int FMT> static const void * sk_mm_fn(int TN, int nch) {
-    if (nch == 1) return TN == 4 ? (const void *) k_sk_mm<FMT, 4, 1> : (const void *) k_sk_mm<FMT, 8, 1>;
-    return TN == 4 ? (const void *) k_sk_mm<FMT, 4, 4> : (const void *) k_sk_mm<FMT, 8, 4>;
-}
-static const void * sk_mm_fn_of(int wtype, int TN, int nch) {
+template <int FMT> static const void * sk_mm_fn(int TN) { return TN == 4 ? (const void *) k_sk_mm<FMT, 4> : (const void *) k_sk_mm<FMT, 8>; }
+static const void * sk_mm_fn_of(int wtype, int TN) {
     switch (wtype) {
-        case BG_Q4_0: return sk_mm_fn<BG_Q4_0>(TN, nch); case BG_Q4_1: return sk_mm_fn<BG_Q4_1>(TN, nch); case BG_Q5_0: return sk_mm_fn<BG_Q5_0>(TN, nch);
-        case BG_Q5_1: return sk_mm_fn<BG_Q5_1>(TN, nch); case BG_Q8_0: return sk_mm_fn<BG_Q8_0>(TN, nch);
+        case BG_Q4_0: return sk_mm_fn<BG_Q4_0>(TN); case BG_Q4_1: return sk_mm_fn<BG_Q4_1>(TN); case BG_Q5_0: return sk_mm_fn<BG_Q5_0>(TN);
+        case BG_Q5_1: return sk_mm_fn<BG_Q5_1>(TN); case BG_Q8_0: return sk_mm_fn<BG_Q8_0>(TN);
     }
     return nullptr;
 }
@@ -617,35 +614,29 @@ static int sk_launch(bgpt_model * m, const void * fn, dim3 grid, int threads, si
     m->launches++;
     return BGPT_OK;
 }
-// one k_sk_mm launch over token rows [tok0, n)
-static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int nmat, const ActLayout & A, int n, int tok0, int rpw, int tn_pref) {
+// one k_sk_mm launch over token rows [tok0, n): CTAs of nw warps, rpw rows per warp
+static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int nmat, const ActLayout & A, int n, int tok0, int nw, int rpw, int tn_pref) {
     const RowLayout & L = W[0]->L;
     for (int i = 0; i < 3; i++) a.W[i] = W[i < nmat ? i : 0]->ptr;
     a.rows_per = (int) W[0]->ne1; a.M = a.rows_per * nmat; a.npass = L.K / 1024;
     a.stride = L.stride; a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
     a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s; a.code_off = bg_code_offset(m->wtype);
-    a.n = n; a.tok0 = tok0; a.rpw = rpw; a.eps = 1e-5f;         // NORM_EPS, biogpt.cpp:24
+    a.n = n; a.tok0 = tok0; a.rpw = rpw;
     a.pdl_trig = m->sk_pdl_trig;
-    // 4-row tiles double the CTAs of the kernels that have only 1024-4096 weight rows to spread over 148 SMs (a warp owns a row)
+    if (nmat > 1 && a.rows_per % (nw * rpw)) return fail(BGPT_E_UNSUPPORTED, "skinny matmul: %d rows per CTA do not divide %d", nw * rpw, a.rows_per);
+    // 4-row tiles double the warps of the kernels that have only 1024-4096 weight rows to spread over 148 SMs (a warp owns a row)
     const int cnt = n - tok0, TN = (cnt <= 4 || tn_pref == 4) ? 4 : 8;
-    dim3 grid((a.M + SK_NW * rpw - 1) / (SK_NW * rpw), (cnt + TN - 1) / TN);
-    const size_t smem = (size_t) TN * A.bytes + (a.pro == 1 ? 2 * SK_D * 4 : 0) + (size_t) SK_NW * SK_SCR * 4;
-    const int nch = rpw * a.npass;
-    if (nch != 1 && nch != 4) return fail(BGPT_E_UNSUPPORTED, "skinny matmul: %d chunks per warp (d_ff must be 4096)", nch);
-    return sk_launch(m, sk_mm_fn_of(m->wtype, TN, nch), grid, SK_NT, smem, &a);
+    dim3 grid((a.M + nw * rpw - 1) / (nw * rpw), (cnt + TN - 1) / TN);
+    const size_t smem = (size_t) TN * A.bytes + (size_t) nw * rpw * L.stride;
+    return sk_launch(m, sk_mm_fn_of(m->wtype, TN), grid, nw * 32, smem, &a);
 }
 
-// LayerNorm + quantise of n rows into the d_model-wide activation records (k_sk_ln), or -- BGPT_SK_LN=0 -- left to the
-// consumer matmul's prologue
+// LayerNorm + quantise of n rows into the d_model-wide activation records (k_sk_ln)
 static int sk_ln(bgpt_model * m, SkArgs & a, const float * x, const DevTensor * w, const DevTensor * b, int n) {
-    if (!m->sk_ln_kernel) {
-        a.pro = 1; a.xin = x; a.ld_in = m->d_model; a.lnw = (const float *) w->ptr; a.lnb = (const float *) b->ptr;
-        return BGPT_OK;
-    }
-    a.pro = 0; a.act = m->act_d;
+    a.act = m->act_d;
     if (m->sk_skip & 64) return BGPT_OK;
     SkLnArgs l{};
-    l.xin = x; l.ld_in = m->d_model; l.lnw = (const float *) w->ptr; l.lnb = (const float *) b->ptr; l.eps = 1e-5f;
+    l.xin = x; l.ld_in = m->d_model; l.lnw = (const float *) w->ptr; l.lnb = (const float *) b->ptr; l.eps = 1e-5f;   // NORM_EPS, biogpt.cpp:24
     l.act = m->act_d; l.act_bytes = m->A_d.bytes; l.off_n = m->A_d.off_n; l.off_d = m->A_d.off_d; l.off_s = m->A_d.off_s;
     l.code_off = bg_code_offset(m->wtype); l.pdl_trig = m->sk_pdl_trig;
     return sk_launch(m, sk_ln_fn_of(m->wtype), dim3(n), 256, 0, &l);
@@ -673,7 +664,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             a.qscale = 1.0f / sqrtf((float) dk);                 // biogpt.cpp:681
             a.st = m->st; a.mode = mode;
             if (m->sk_kv_prefetch) a.pf_streams = mode == 1 ? n : 1;      // the kernel reads n_past from device memory: one graph serves every position
-            if (!(skip & 1)) RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 1, m->sk_tn_qkv));
+            if (!(skip & 1)) RET(sk_mm(m, a, W, 3, m->A_d, n, 0, 8, 1, m->sk_tn_qkv));
         }
         {   // attention + quantise for out_proj                     biogpt.cpp:730-764
             SkAttnArgs a{};
@@ -685,9 +676,9 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
         {   // out_proj + bias + residual                            biogpt.cpp:767-772
             SkArgs a{};
             const DevTensor * W[3] = { L.o_w, nullptr, nullptr };
-            a.pro = 0; a.act = m->act_d;
+            a.act = m->act_d;
             a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.o_b->ptr; a.out = m->x1; a.ld_out = d; a.resid = m->x; a.ld_resid = d;
-            if (!(skip & 4)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 1, m->sk_tn_proj));
+            if (!(skip & 4)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 8, 1, m->sk_tn_proj));
         }
         {   // LayerNorm1 + fc1 + bias + GELU + quantise for fc2     biogpt.cpp:779-787
             SkArgs a{};
@@ -695,14 +686,14 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             RET(sk_ln(m, a, m->x1, L.ln1_w, L.ln1_b, n));
             a.epi = SK_EPI_GELUQ; a.bias[0] = (const float *) L.fc1_b->ptr; a.gelu = m->gelu_tab;
             a.act_out = m->act_ff; a.out_bytes = m->A_ff.bytes; a.out_off_n = m->A_ff.off_n; a.out_off_d = m->A_ff.off_d; a.out_off_s = m->A_ff.off_s;
-            if (!(skip & 8)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 4, m->sk_tn_proj));
+            if (!(skip & 8)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, m->sk_fc1_nw, 32 / m->sk_fc1_nw, m->sk_tn_proj));
         }
         {   // fc2 + bias + residual                                 biogpt.cpp:790-795
             SkArgs a{};
             const DevTensor * W[3] = { L.fc2_w, nullptr, nullptr };
-            a.pro = 0; a.act = m->act_ff;
+            a.act = m->act_ff;
             a.epi = SK_EPI_RESID; a.bias[0] = (const float *) L.fc2_b->ptr; a.out = m->x; a.ld_out = d; a.resid = m->x1; a.ld_resid = d;
-            if (!(skip & 16)) RET(sk_mm(m, a, W, 1, m->A_ff, n, 0, 1, m->sk_tn_proj));
+            if (!(skip & 16)) RET(sk_mm(m, a, W, 1, m->A_ff, n, 0, 8, 1, m->sk_tn_proj));
         }
     }
     // the reference computes all n rows and returns the last (biogpt.cpp:803, 844); rows are independent, so only the
@@ -713,7 +704,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
         const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };
         RET(sk_ln(m, a, m->x, m->ln_w, m->ln_b, n));
         a.epi = SK_EPI_STORE; a.out = m->logits - (size_t) tok0 * m->n_vocab; a.ld_out = m->n_vocab;
-        if (!(skip & 32)) RET(sk_mm(m, a, W, 1, m->A_d, n, tok0, 4, 8));
+        if (!(skip & 32)) RET(sk_mm(m, a, W, 1, m->A_d, n, tok0, m->sk_fc1_nw, 32 / m->sk_fc1_nw, 8));
     } else {
         RET(launch_act(m, s, m->x, d, m->ln_w, m->ln_b, d, wt, m->act_d, m->A_d, n, nullptr, 0));
         const DevTensor * W[3] = { m->lm_head, nullptr, nullptr };

@@ -47,12 +47,10 @@ struct SkArgs {
     int rows_per, M;               // rows of one matrix, total rows
     int npass;                     // K / 1024
     int stride, off_qh, off_d, off_m;
-    int pro;                       // 0: activation records from `act`; 1: LayerNorm(xin) + quantise (K = 1024)
-    const uint8_t * act;
-    const float * xin; int ld_in; const float * lnw; const float * lnb; float eps;
+    const uint8_t * act;           // activation records of the token rows (k_sk_ln, k_sk_attn or a GELU epilogue wrote them)
     int act_bytes, off_n, off_dd, off_s, code_off;      // record layout of the input
     int n, tok0;                   // token rows [tok0, n)
-    int rpw;                       // rows per warp: a CTA covers 8 * rpw consecutive rows
+    int rpw;                       // rows per warp: a CTA of nw warps covers nw * rpw consecutive rows
     int pdl_trig;                  // griddepcontrol.launch_dependents: 0 at the start of the kernel, 1 after the dot products
     // epilogue
     int epi;
@@ -99,44 +97,6 @@ __device__ __forceinline__ void sk_quant_block(float4 v, int b, int l, uint8_t *
     }
 }
 
-// ---- LayerNorm + affine + quantise of one 1024-wide row by ONE warp -> record in shared memory ----
-// Same operations as bg_ln_row + bg_row_to_record (ggml.c:11403-11420; biogpt.cpp:693-700); lane holds
-// elements p*128 + 4*lane .. +3 of pass p, which is block 4p + lane/8, word lane%8.
-template <int FMT>
-__device__ __forceinline__ void sk_ln_quant_row(const float * x, const float * lnw /*shared*/, const float * lnb /*shared*/, float eps,
-                                                uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
-    const int lane = threadIdx.x & 31;
-    float4 v[8];
-#pragma unroll
-    for (int p = 0; p < 8; p++) v[p] = __ldcg((const float4 *) (x + p * 128 + lane * 4));
-    double s = 0.0;
-#pragma unroll
-    for (int p = 0; p < 8; p++) s += ((double) v[p].x + (double) v[p].y) + ((double) v[p].z + (double) v[p].w);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLMASK, s, o);
-    const float mean = (float) (s * (1.0 / SK_D));
-    double s2 = 0.0;
-#pragma unroll
-    for (int p = 0; p < 8; p++) {
-        v[p].x = __fsub_rn(v[p].x, mean); v[p].y = __fsub_rn(v[p].y, mean); v[p].z = __fsub_rn(v[p].z, mean); v[p].w = __fsub_rn(v[p].w, mean);
-        s2 += ((double) __fmul_rn(v[p].x, v[p].x) + (double) __fmul_rn(v[p].y, v[p].y)) + ((double) __fmul_rn(v[p].z, v[p].z) + (double) __fmul_rn(v[p].w, v[p].w));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(FULLMASK, s2, o);
-    const float variance = (float) (s2 * (1.0 / SK_D));
-    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
-#pragma unroll
-    for (int p = 0; p < 8; p++) {
-        const float4 w = *(const float4 *) (lnw + p * 128 + lane * 4), bb = *(const float4 *) (lnb + p * 128 + lane * 4);
-        float4 y;
-        y.x = __fadd_rn(__fmul_rn(w.x, __fmul_rn(v[p].x, scale)), bb.x);
-        y.y = __fadd_rn(__fmul_rn(w.y, __fmul_rn(v[p].y, scale)), bb.y);
-        y.z = __fadd_rn(__fmul_rn(w.z, __fmul_rn(v[p].z, scale)), bb.z);
-        y.w = __fadd_rn(__fmul_rn(w.w, __fmul_rn(v[p].w, scale)), bb.w);
-        sk_quant_block<FMT>(y, p * 4 + (lane >> 3), lane & 7, rec, off_n, off_d, off_s, code_off, true);
-    }
-}
-
 // ---- stand-alone LayerNorm + quantise: one token row per CTA of 256 threads (thread t: elements 4t..4t+3 = block t/8, word t%8),
 // record to global memory; the matmul kernels then stage the records with one bulk copy.  Doing the LayerNorm ONCE instead of
 // in the prologue of each of a matmul's 256-768 CTAs takes ~1000 instructions per warp off their critical path.
@@ -178,143 +138,49 @@ __global__ void __launch_bounds__(256, 4) k_sk_ln(const __grid_constant__ SkLnAr
     sk_quant_block<FMT>(y, tid >> 3, tid & 7, a.act + (size_t) row * a.act_bytes, a.off_n, a.off_d, a.off_s, a.code_off, true);
 }
 
-// ---- weight words of one 1024-wide chunk of a row, as this lane (g = 8*pass + lane/4, j = lane%4) sees them ----
-template <int FMT> struct SkW { uint4 w0, w1; uint32_t qh; uint2 dh, mh; };
-
-template <int FMT>
-__device__ __forceinline__ void sk_load_w(SkW<FMT> & w, const uint8_t * wrow, const SkArgs & a, int pass) {
-    constexpr bool IS8   = (FMT == BG_Q8_0);
-    constexpr bool HASQH = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
-    constexpr bool HASM  = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
-    const int lane = threadIdx.x & 31, g = pass * 8 + (lane >> 2), j = lane & 3;
-    if (IS8) {
-        w.w0 = ldg_stream128(wrow + (size_t) ((g * 2 + 0) * 4 + j) * 16);
-        w.w1 = ldg_stream128(wrow + (size_t) ((g * 2 + 1) * 4 + j) * 16);
-    } else {
-        w.w0 = ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
-        w.w1 = make_uint4(0, 0, 0, 0);
-    }
-    w.qh = 0;
-    if (HASQH) w.qh = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
-    w.dh = ldg_stream64(wrow + a.off_d + g * 8);
-    w.mh = make_uint2(0, 0);
-    if (HASM) w.mh = ldg_stream64(wrow + a.off_m + g * 8);
-}
-
-// one chunk (32 blocks) of one weight row against TN token records: phase A (all lanes: integer dots
-// -> scratch) and phase B (lane = (token, running sum): the fma chain in block order)
+// ---------------------------------------------------------------------------------------------
+// k_sk_mm: y[tok][row] = dot(W[row], record[tok]) + epilogue, one warp per weight row.
+//
+// lane = (tq = lane / 8, l = lane % 8): the lane owns running sum l of token tq (TN = 8: of tokens tq and tq + 4) from
+// the first block of the row to the last -- integer dot (dp4a), conversion, scale product and the fma, in block order;
+// nothing is exchanged between lanes until hsum_float_8 at the end of the row.  The lane's operands of four
+// consecutive blocks are one 16-byte word each, by construction of the layouts in bgpt_layout.h:
+//   weights  [g][j][i]: word j = l % 4 of group g; sums 0..3 take the low nibbles, 4..7 the high ones (Q8_0: word c = l / 4)
+//   records  aq[g][l][i], an[g][l][i] (-offset * sum of the 4 codes), ad[blk], as[blk]
+// The CTA's weight rows are contiguous in HBM: ONE bulk copy (TMA) brings the whole tile into shared memory, issued
+// before griddepcontrol.wait -- the weights are in flight while the previous kernel of the chain is still running --
+// and one more brings the token records once that kernel has finished.  Lanes of different tokens read the same weight
+// word (broadcast), a token's eight lanes read 128 consecutive bytes of its record: no bank conflicts.
+// grid = (ceil(M / (nw * rpw)), ceil((n - tok0) / TN)), block = 32 * nw,
+// dynamic smem = TN * act_bytes + nw * rpw * stride
+// ---------------------------------------------------------------------------------------------
 template <int FMT, int TN>
-__device__ __forceinline__ void sk_chunk(const SkW<FMT> & w, const SkArgs & a, const uint8_t * s_rec, int pass,
-                                         float * P, float * Sm, float * Mw, float (&acc)[TN / 4], float (&summ)[TN / 4]) {
+__global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs a) {
     constexpr bool IS8    = (FMT == BG_Q8_0);
     constexpr bool HASQH  = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
     constexpr bool HASM   = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
     constexpr bool HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
-    const int lane = threadIdx.x & 31, gl = lane >> 2, j = lane & 3;
-    const int g = pass * 8 + gl;
-    uint32_t lo[4], hi[4];
-    if (IS8) {
-        lo[0] = w.w0.x; lo[1] = w.w0.y; lo[2] = w.w0.z; lo[3] = w.w0.w;
-        hi[0] = w.w1.x; hi[1] = w.w1.y; hi[2] = w.w1.z; hi[3] = w.w1.w;
-    } else {
-        const uint32_t ww[4] = { w.w0.x, w.w0.y, w.w0.z, w.w0.w };
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            lo[i] = ww[i] & 0x0F0F0F0Fu;
-            hi[i] = (ww[i] >> 4) & 0x0F0F0F0Fu;
-            if (HASQH) {
-                const uint32_t hb = (w.qh >> (8 * i)) & 0xFFu;
-                lo[i] |= bg_spread4(hb & 0xFu);
-                hi[i] |= bg_spread4(hb >> 4);
-            }
-        }
-    }
-    float dw[4];
-    dw[0] = bg_h2f((uint16_t) (w.dh.x & 0xFFFF)); dw[1] = bg_h2f((uint16_t) (w.dh.x >> 16));
-    dw[2] = bg_h2f((uint16_t) (w.dh.y & 0xFFFF)); dw[3] = bg_h2f((uint16_t) (w.dh.y >> 16));
-    if (HASM && j == 1)
-        *(float4 *) (Mw + 4 * gl) = make_float4(bg_h2f((uint16_t) (w.mh.x & 0xFFFF)), bg_h2f((uint16_t) (w.mh.x >> 16)),
-                                                bg_h2f((uint16_t) (w.mh.y & 0xFFFF)), bg_h2f((uint16_t) (w.mh.y >> 16)));
-    const int tq = lane >> 3, l = lane & 7;
-#pragma unroll
-    for (int r = 0; r < TN / 4; r++) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint8_t * rec = s_rec + (size_t) (r * 4 + q) * a.act_bytes;
-            const uint4 a0 = *(const uint4 *) (rec + (g * 8 + j) * 16);
-            const uint4 a1 = *(const uint4 *) (rec + (g * 8 + j + 4) * 16);
-            int4 n0 = make_int4(0, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
-            if (HASOFF) {
-                n0 = *(const int4 *) (rec + a.off_n + (g * 8 + j) * 16);
-                n1 = *(const int4 *) (rec + a.off_n + (g * 8 + j + 4) * 16);
-            }
-            const float4 da = *(const float4 *) (rec + a.off_dd + g * 16);
-            float4 P0, P1, S;
-            P0.x = (float) __dp4a((int) lo[0], (int) a0.x, n0.x); P1.x = (float) __dp4a((int) hi[0], (int) a1.x, n1.x);
-            P0.y = (float) __dp4a((int) lo[1], (int) a0.y, n0.y); P1.y = (float) __dp4a((int) hi[1], (int) a1.y, n1.y);
-            P0.z = (float) __dp4a((int) lo[2], (int) a0.z, n0.z); P1.z = (float) __dp4a((int) hi[2], (int) a1.z, n1.z);
-            P0.w = (float) __dp4a((int) lo[3], (int) a0.w, n0.w); P1.w = (float) __dp4a((int) hi[3], (int) a1.w, n1.w);
-            S.x = __fmul_rn(dw[0], da.x); S.y = __fmul_rn(dw[1], da.y); S.z = __fmul_rn(dw[2], da.z); S.w = __fmul_rn(dw[3], da.w);
-            *(float4 *) (P + (q * 8 + j) * SK_PS + 4 * gl) = P0;
-            *(float4 *) (P + (q * 8 + j + 4) * SK_PS + 4 * gl) = P1;
-            if (j == 0) *(float4 *) (Sm + q * SK_PS + 4 * gl) = S;
-        }
-        __syncwarp();
-        const uint8_t * rec = s_rec + (size_t) (r * 4 + tq) * a.act_bytes;
-        float c = acc[r], sm = summ[r];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float4 pv = *(const float4 *) (P + (tq * 8 + l) * SK_PS + 4 * k);
-            const float4 sv = *(const float4 *) (Sm + tq * SK_PS + 4 * k);
-            c = fmaf(sv.x, pv.x, c); c = fmaf(sv.y, pv.y, c); c = fmaf(sv.z, pv.z, c); c = fmaf(sv.w, pv.w, c);
-            if (HASM && l == 0) {
-                const float4 mv = *(const float4 *) (Mw + 4 * k);
-                const float4 sa = *(const float4 *) (rec + a.off_s + (pass * 8 + k) * 16);
-                sm = fmaf(mv.x, sa.x, sm); sm = fmaf(mv.y, sa.y, sm); sm = fmaf(mv.z, sa.z, sm); sm = fmaf(mv.w, sa.w, sm);
-            }
-        }
-        acc[r] = c; summ[r] = sm;
-        __syncwarp();
-    }
-}
-
-// grid = (ceil(M / (8 * rpw)), ceil((n - tok0) / TN)), block = 256,
-// dynamic smem = TN * act_bytes + (pro ? 8192 : 0) + 8 * SK_SCR * 4
-// NCH = rpw * npass, the 1024-wide weight chunks a warp walks (1 or 4): ALL of them are requested before
-// griddepcontrol.wait and wait in registers, so no HBM / L2 round trip sits between two chunks.
-template <int FMT, int TN, int NCH>
-__global__ void __launch_bounds__(SK_NT, NCH == 1 ? 3 : 2) k_sk_mm(const __grid_constant__ SkArgs a) {
-    static_assert(NCH == 1 || NCH == 4, "a warp walks 1 or 4 chunks");
-    constexpr bool HASM = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
     extern __shared__ __align__(16) uint8_t sk_smem[];
     __shared__ __align__(16) float s_g[8 * 32];               // SK_EPI_GELUQ: [token][row of the CTA]
-    __shared__ __align__(8) uint64_t s_bar;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ __align__(8) uint64_t s_bar[2];                 // weights, records
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = blockDim.x, nw = nt >> 5;
     uint8_t * s_rec = sk_smem;
-    float * s_ln = (float *) (sk_smem + (size_t) TN * a.act_bytes);                 // LayerNorm weight | bias (pro == 1)
-    float * P = s_ln + (a.pro == 1 ? 2 * SK_D : 0) + (size_t) warp * SK_SCR;
-    float * Sm = P + 32 * SK_PS;
-    float * Mw = Sm + 4 * SK_PS;
+    uint8_t * s_w = sk_smem + (size_t) TN * a.act_bytes;
     const int tokbase = a.tok0 + blockIdx.y * TN;
-    const int rowbase = blockIdx.x * SK_NW * a.rpw;
-    const int total = a.rpw * a.npass;
-    const int tq = lane >> 3, l = lane & 7;
-    auto mat_of = [&](int row) -> int { return row >= 2 * a.rows_per ? 2 : (row >= a.rows_per ? 1 : 0); };       // no integer division in the loop
-    auto wrow_of = [&](int i) -> const uint8_t * {
-        int row = rowbase + i * SK_NW + warp; row = row < a.M ? row : a.M - 1;
-        const int mat = mat_of(row);
-        return a.W[mat] + (size_t) (row - mat * a.rows_per) * a.stride;
-    };
-    // ---- everything that does not depend on the previous kernel: the warp's weight chunks into registers, the K/V rows the
-    //      attention kernel behind this one will read towards the L2, LayerNorm parameters, n_past
-    SkW<FMT> cur, w1, w2, w3;
-    sk_load_w<FMT>(cur, wrow_of(0), a, 0);
-    w1 = cur; w2 = cur; w3 = cur;
-    if (NCH == 4) {
-        const bool byrow = a.npass == 1;                      // 4 rows x 1 chunk (fc1, lm_head) or 1 row x 4 chunks (fc2)
-        sk_load_w<FMT>(w1, wrow_of(byrow ? 1 : 0), a, byrow ? 0 : 1);
-        sk_load_w<FMT>(w2, wrow_of(byrow ? 2 : 0), a, byrow ? 0 : 2);
-        sk_load_w<FMT>(w3, wrow_of(byrow ? 3 : 0), a, byrow ? 0 : 3);
+    const int rows_cta = nw * a.rpw;
+    const int rowbase = blockIdx.x * rows_cta;
+    const int tq = lane >> 3, l = lane & 7, j = l & 3, c = l >> 2;
+    auto mat_of = [&](int row) -> int { return row >= 2 * a.rows_per ? 2 : (row >= a.rows_per ? 1 : 0); };
+    // ---- everything that does not depend on the previous kernel: the weight tile, n_past, K/V rows towards the L2
+    if (tid == 0) {
+        m4_mbar_init(&s_bar[0], 1); m4_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int nr = a.M - rowbase; nr = nr > rows_cta ? rows_cta : nr;
+        const int mat = mat_of(rowbase);                       // a CTA's rows never straddle two of the stacked matrices
+        const uint32_t bytes = (uint32_t) nr * (uint32_t) a.stride;
+        m4_mbar_expect(&s_bar[0], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(m4_s32(s_w)), "l"(a.W[mat] + (size_t) (rowbase - mat * a.rows_per) * a.stride), "r"(bytes), "r"(m4_s32(&s_bar[0])) : "memory");
     }
     int n_past = 0;
     if (a.epi == SK_EPI_QKV) {
@@ -322,105 +188,135 @@ __global__ void __launch_bounds__(SK_NT, NCH == 1 ? 3 : 2) k_sk_mm(const __grid_
         if (a.pf_streams > 0 && n_past > 0 && blockIdx.y == 0) {     // 64 lines of 128 bytes per cached position and stream (K row | V row)
             const int per = n_past * 64, totl = per * a.pf_streams;
 #pragma unroll 1
-            for (int idx = blockIdx.x * SK_NT + tid; idx < totl; idx += gridDim.x * SK_NT) {
-                const int sidx = idx / per, rem = idx - sidx * per, t = rem >> 6, j = rem & 63;
-                const float * base = (j < 32 ? a.kcache : a.vcache) + (size_t) sidx * a.stream_stride + (size_t) t * SK_D + (j & 31) * 32;
+            for (int idx = blockIdx.x * nt + tid; idx < totl; idx += gridDim.x * nt) {
+                const int sidx = idx / per, rem = idx - sidx * per, t = rem >> 6, jj = rem & 63;
+                const float * base = (jj < 32 ? a.kcache : a.vcache) + (size_t) sidx * a.stream_stride + (size_t) t * SK_D + (jj & 31) * 32;
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(base));
             }
         }
     }
-    if (a.pro == 1) {
-        for (int i = tid; i < 2 * SK_D / 4; i += SK_NT)
-            ((float4 *) s_ln)[i] = i < SK_D / 4 ? *((const float4 *) a.lnw + i) : *((const float4 *) a.lnb + (i - SK_D / 4));
-    } else if (tid == 0) {
-        m4_mbar_init(&s_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if (a.pdl_trig == 0) sk_pdl_launch_dependents();
-    __syncthreads();
+    __syncthreads();                                           // barriers initialised
     sk_pdl_wait();                                             // from here on the previous kernel's results are visible
-    // ---- token records
-    if (a.pro == 1) {
-        if (warp < TN) {
-            uint8_t * rec = s_rec + (size_t) warp * a.act_bytes;
-            const int tok = tokbase + warp;
-            if (tok < a.n) sk_ln_quant_row<FMT>(a.xin + (size_t) tok * a.ld_in, s_ln, s_ln + SK_D, a.eps, rec, a.off_n, a.off_dd, a.off_s, a.code_off);
-            else for (int i = lane; i < (a.act_bytes >> 4); i += 32) ((uint4 *) rec)[i] = make_uint4(0, 0, 0, 0);
-        }
-    } else {                                                   // consecutive records are contiguous: ONE bulk copy (TMA), no register staging
+    // ---- token records: consecutive records are contiguous, ONE bulk copy
+    {
         int nv = a.n - tokbase; nv = nv > TN ? TN : nv;
         const uint32_t bytes = (uint32_t) nv * (uint32_t) a.act_bytes;
         if (tid == 0) {
-            m4_mbar_expect(&s_bar, bytes);
+            m4_mbar_expect(&s_bar[1], bytes);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(m4_s32(s_rec)), "l"(a.act + (size_t) tokbase * a.act_bytes), "r"(bytes), "r"(m4_s32(&s_bar)) : "memory");
+                         :: "r"(m4_s32(s_rec)), "l"(a.act + (size_t) tokbase * a.act_bytes), "r"(bytes), "r"(m4_s32(&s_bar[1])) : "memory");
         }
-        for (int i = (int) (bytes >> 4) + tid; i < TN * (a.act_bytes >> 4); i += SK_NT) ((uint4 *) s_rec)[i] = make_uint4(0, 0, 0, 0);
-        m4_mbar_wait(&s_bar, 0);
+        for (int i = (int) (bytes >> 4) + tid; i < TN * (a.act_bytes >> 4); i += nt) ((uint4 *) s_rec)[i] = make_uint4(0, 0, 0, 0);
+        m4_mbar_wait(&s_bar[0], 0);
+        m4_mbar_wait(&s_bar[1], 0);
     }
     __syncthreads();
-    float acc[TN / 4], summ[TN / 4];
-    float pbias = 0.0f, presid[TN / 4];
-#pragma unroll
-    for (int r = 0; r < TN / 4; r++) presid[r] = 0.0f;
+    const int ng = 8 * a.npass;                                // groups of 4 blocks in a row
+    const uint8_t * rec0 = s_rec + (size_t) tq * a.act_bytes;
 #pragma unroll 1
-    for (int s = 0, i = 0, pass = 0; s < total; s++) {
-        if (pass == 0) {
+    for (int i = 0; i < a.rpw; i++) {
+        const int rl = i * nw + warp, row = rowbase + rl;
+        const uint8_t * wrow = s_w + (size_t) rl * a.stride;
+        // the row owner's bias / residual are in flight while the dots run
+        float pbias = 0.0f, presid[TN / 4];
 #pragma unroll
-            for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
-            // the row owner's bias / residual are in flight while the dots run
-            const int row = rowbase + i * SK_NW + warp;
-            if (l == 0 && row < a.M) {
-                if (a.epi == SK_EPI_QKV) { const int mat = mat_of(row); pbias = a.bias[mat][row - mat * a.rows_per]; }
-                else if (a.bias[0]) pbias = a.bias[0][row];
-                if (a.epi == SK_EPI_RESID) {
+        for (int r = 0; r < TN / 4; r++) presid[r] = 0.0f;
+        if (l == 0 && row < a.M) {
+            if (a.epi == SK_EPI_QKV) { const int mat = mat_of(row); pbias = a.bias[mat][row - mat * a.rows_per]; }
+            else if (a.bias[0]) pbias = a.bias[0][row];
+            if (a.epi == SK_EPI_RESID) {
 #pragma unroll
-                    for (int r = 0; r < TN / 4; r++) { const int tok = tokbase + r * 4 + tq; if (tok < a.n) presid[r] = __ldcg(a.resid + (size_t) tok * a.ld_resid + row); }
-                }
+                for (int r = 0; r < TN / 4; r++) { const int tok = tokbase + r * 4 + tq; if (tok < a.n) presid[r] = __ldcg(a.resid + (size_t) tok * a.ld_resid + row); }
             }
         }
-        sk_chunk<FMT, TN>(cur, a, s_rec, pass, P, Sm, Mw, acc, summ);
-        if (pass == a.npass - 1) {
-            const int row = rowbase + i * SK_NW + warp;
+        float acc[TN / 4], summ[TN / 4];
+#pragma unroll
+        for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
+#pragma unroll 2
+        for (int g = 0; g < ng; g++) {
+            uint32_t wq[4];
+            if (IS8) {
+                const uint4 w = *(const uint4 *) (wrow + ((g * 2 + c) * 4 + j) * 16);
+                wq[0] = w.x; wq[1] = w.y; wq[2] = w.z; wq[3] = w.w;
+            } else {
+                const uint4 w = *(const uint4 *) (wrow + (g * 4 + j) * 16);
+                const int sh = 4 * c;
+                wq[0] = (w.x >> sh) & 0x0F0F0F0Fu; wq[1] = (w.y >> sh) & 0x0F0F0F0Fu;
+                wq[2] = (w.z >> sh) & 0x0F0F0F0Fu; wq[3] = (w.w >> sh) & 0x0F0F0F0Fu;
+                if (HASQH) {
+                    const uint32_t qh = *(const uint32_t *) (wrow + a.off_qh + g * 16 + j * 4) >> sh;
+                    wq[0] |= bg_spread4(qh & 0xFu);         wq[1] |= bg_spread4((qh >> 8) & 0xFu);
+                    wq[2] |= bg_spread4((qh >> 16) & 0xFu); wq[3] |= bg_spread4((qh >> 24) & 0xFu);
+                }
+            }
+            const uint2 dh = *(const uint2 *) (wrow + a.off_d + g * 8);
+            float dw[4];
+            dw[0] = bg_h2f((uint16_t) (dh.x & 0xFFFF)); dw[1] = bg_h2f((uint16_t) (dh.x >> 16));
+            dw[2] = bg_h2f((uint16_t) (dh.y & 0xFFFF)); dw[3] = bg_h2f((uint16_t) (dh.y >> 16));
+            float mw[4] = { 0.f, 0.f, 0.f, 0.f };
+            if (HASM && l == 0) {
+                const uint2 mh = *(const uint2 *) (wrow + a.off_m + g * 8);
+                mw[0] = bg_h2f((uint16_t) (mh.x & 0xFFFF)); mw[1] = bg_h2f((uint16_t) (mh.x >> 16));
+                mw[2] = bg_h2f((uint16_t) (mh.y & 0xFFFF)); mw[3] = bg_h2f((uint16_t) (mh.y >> 16));
+            }
 #pragma unroll
             for (int r = 0; r < TN / 4; r++) {
-                // hsum_float_8: (a_l + a_{l+4}), then the pairs 2 apart, then 1 apart (ggml.c:611-617)
-                float v = __fadd_rn(acc[r], __shfl_xor_sync(FULLMASK, acc[r], 4));
-                v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 2));
-                v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 1));
-                if (HASM) v = __fadd_rn(v, summ[r]);
-                const int tok = tokbase + r * 4 + tq;
-                if (l == 0 && row < a.M && tok < a.n) {
-                    switch (a.epi) {
-                    case SK_EPI_STORE:
-                        a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(pbias, v) : v;
-                        break;
-                    case SK_EPI_QKV: {
-                        const int mat = mat_of(row), rr = row - mat * a.rows_per;
-                        const float t = __fadd_rn(pbias, v);
-                        if (mat == 0) a.out[(size_t) tok * a.ld_out + rr] = __fmul_rn(t, a.qscale);
-                        else {
-                            int stream, pos, T; bg_row_info(a.mode, a.n, n_past, tok, stream, pos, T);
-                            (mat == 1 ? a.kcache : a.vcache)[(size_t) stream * a.stream_stride + (size_t) pos * a.rows_per + rr] = t;
-                        }
-                        break; }
-                    case SK_EPI_RESID:
-                        a.out[(size_t) tok * a.ld_out + row] = __fadd_rn(__fadd_rn(v, pbias), presid[r]);
-                        break;
-                    default:                                   // GELU input; the table look-ups run as one batch after the loop
-                        s_g[(r * 4 + tq) * 32 + (i * SK_NW + warp)] = __fadd_rn(pbias, v);
-                        break;
-                    }
+                const uint8_t * rec = rec0 + (size_t) (r * 4) * a.act_bytes;
+                const uint4 av = *(const uint4 *) (rec + (g * 8 + l) * 16);
+                int4 nv = make_int4(0, 0, 0, 0);
+                if (HASOFF) nv = *(const int4 *) (rec + a.off_n + (g * 8 + l) * 16);
+                const float4 da = *(const float4 *) (rec + a.off_dd + g * 16);
+                float cacc = acc[r];
+                cacc = fmaf(__fmul_rn(dw[0], da.x), (float) __dp4a((int) wq[0], (int) av.x, nv.x), cacc);
+                cacc = fmaf(__fmul_rn(dw[1], da.y), (float) __dp4a((int) wq[1], (int) av.y, nv.y), cacc);
+                cacc = fmaf(__fmul_rn(dw[2], da.z), (float) __dp4a((int) wq[2], (int) av.z, nv.z), cacc);
+                cacc = fmaf(__fmul_rn(dw[3], da.w), (float) __dp4a((int) wq[3], (int) av.w, nv.w), cacc);
+                acc[r] = cacc;
+                if (HASM && l == 0) {
+                    const float4 sa = *(const float4 *) (rec + a.off_s + g * 16);
+                    float sm = summ[r];
+                    sm = fmaf(mw[0], sa.x, sm); sm = fmaf(mw[1], sa.y, sm); sm = fmaf(mw[2], sa.z, sm); sm = fmaf(mw[3], sa.w, sm);
+                    summ[r] = sm;
                 }
             }
         }
-        if (NCH == 4) { cur = w1; w1 = w2; w2 = w3; }
-        if (++pass == a.npass) { pass = 0; i++; }
+#pragma unroll
+        for (int r = 0; r < TN / 4; r++) {
+            // hsum_float_8: (a_l + a_{l+4}), then the pairs 2 apart, then 1 apart (ggml.c:611-617)
+            float v = __fadd_rn(acc[r], __shfl_xor_sync(FULLMASK, acc[r], 4));
+            v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 2));
+            v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 1));
+            if (HASM) v = __fadd_rn(v, summ[r]);
+            const int tok = tokbase + r * 4 + tq;
+            if (l == 0 && row < a.M && tok < a.n) {
+                switch (a.epi) {
+                case SK_EPI_STORE:
+                    a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(pbias, v) : v;
+                    break;
+                case SK_EPI_QKV: {
+                    const int mat = mat_of(row), rr = row - mat * a.rows_per;
+                    const float t = __fadd_rn(pbias, v);
+                    if (mat == 0) a.out[(size_t) tok * a.ld_out + rr] = __fmul_rn(t, a.qscale);
+                    else {
+                        int stream, pos, T; bg_row_info(a.mode, a.n, n_past, tok, stream, pos, T);
+                        (mat == 1 ? a.kcache : a.vcache)[(size_t) stream * a.stream_stride + (size_t) pos * a.rows_per + rr] = t;
+                    }
+                    break; }
+                case SK_EPI_RESID:
+                    a.out[(size_t) tok * a.ld_out + row] = __fadd_rn(__fadd_rn(v, pbias), presid[r]);
+                    break;
+                default:                                       // GELU input; the table look-ups run as one batch after the loop
+                    s_g[(r * 4 + tq) * 32 + rl] = __fadd_rn(pbias, v);
+                    break;
+                }
+            }
+        }
     }
     if (a.pdl_trig == 1) sk_pdl_launch_dependents();
     if (a.epi == SK_EPI_GELUQ) {                               // the CTA's 32 rows are block blockIdx.x of the next record
         __syncthreads();
-        for (int i = tid; i < TN * 32; i += SK_NT) s_g[i] = bg_h2f(a.gelu[bg_f2h(s_g[i])]);
+        for (int i = tid; i < TN * 32; i += nt) s_g[i] = bg_h2f(a.gelu[bg_f2h(s_g[i])]);
         __syncthreads();
         if (warp < TN) {
             const int tok = tokbase + warp;
