@@ -627,7 +627,8 @@ static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int n
     // 4-row tiles double the warps of the kernels that have only 1024-4096 weight rows to spread over 148 SMs (a warp owns a row)
     const int cnt = n - tok0, TN = (cnt <= 4 || tn_pref == 4) ? 4 : 8;
     dim3 grid((a.M + nw * rpw - 1) / (nw * rpw), (cnt + TN - 1) / TN);
-    const size_t smem = (size_t) TN * A.bytes + (size_t) nw * rpw * L.stride;
+    const bool hasm = L.off_m >= 0, is8 = L.type == BG_Q8_0;
+    const size_t smem = (size_t) TN * A.bytes + (size_t) nw * rpw * ((size_t) L.stride + (is8 ? 0 : L.K) + (size_t) (L.K / 32) * 4 * (hasm ? 2 : 1));
     return sk_launch(m, sk_mm_fn_of(m->wtype, TN), grid, nw * 32, smem, &a);
 }
 

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256, 4) k_sk_ln(const __grid_constant__ SkLnAr
 // and one more brings the token records once that kernel has finished.  Lanes of different tokens read the same weight
 // word (broadcast), a token's eight lanes read 128 consecutive bytes of its record: no bank conflicts.
 // grid = (ceil(M / (nw * rpw)), ceil((n - tok0) / TN)), block = 32 * nw,
-// dynamic smem = TN * act_bytes + nw * rpw * stride
+// dynamic smem = TN * act_bytes + nw * rpw * (stride + (Q8_0 ? 0 : K) + K / 32 * 4 * (1 + has minima))
 // ---------------------------------------------------------------------------------------------
 template <int FMT, int TN>
 __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs a) {
@@ -164,12 +164,16 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
     __shared__ __align__(16) float s_g[8 * 32];               // SK_EPI_GELUQ: [token][row of the CTA]
     __shared__ __align__(8) uint64_t s_bar[2];                 // weights, records
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = blockDim.x, nw = nt >> 5;
-    uint8_t * s_rec = sk_smem;
-    uint8_t * s_w = sk_smem + (size_t) TN * a.act_bytes;
-    const int tokbase = a.tok0 + blockIdx.y * TN;
     const int rows_cta = nw * a.rpw;
+    const int K = a.npass * 1024, nb = K >> 5;
+    uint8_t * s_rec = sk_smem;                                                   // [TN][act_bytes] token records
+    uint8_t * s_w = s_rec + (size_t) TN * a.act_bytes;                           // [rows_cta][stride] weight rows as they lie in HBM
+    uint8_t * s_dec = s_w + (size_t) rows_cta * a.stride;                        // [rows_cta][K] int8 codes [g][l][i] (Q8_0: the raw rows already are)
+    float * s_dw = (float *) (s_dec + (IS8 ? 0 : (size_t) rows_cta * K));        // [rows_cta][nb] block scales as f32
+    float * s_mw = s_dw + (size_t) rows_cta * nb;                                // [rows_cta][nb] block minima as f32 (Q4_1 / Q5_1)
+    const int tokbase = a.tok0 + blockIdx.y * TN;
     const int rowbase = blockIdx.x * rows_cta;
-    const int tq = lane >> 3, l = lane & 7, j = l & 3, c = l >> 2;
+    const int tq = lane >> 3, l = lane & 7;
     auto mat_of = [&](int row) -> int { return row >= 2 * a.rows_per ? 2 : (row >= a.rows_per ? 1 : 0); };
     // ---- everything that does not depend on the previous kernel: the weight tile, n_past, K/V rows towards the L2
     if (tid == 0) {
@@ -197,6 +201,39 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
     }
     if (a.pdl_trig == 0) sk_pdl_launch_dependents();
     __syncthreads();                                           // barriers initialised
+    // ---- decode the tile ONCE per CTA (still nothing here depends on the previous kernel): 4/5-bit codes -> int8 words in
+    //      the lane order of the dot loop, fp16 scales / minima -> f32.  Every weight is then used by TN token lanes as is.
+    m4_mbar_wait(&s_bar[0], 0);
+    {
+        int nr = a.M - rowbase; nr = nr > rows_cta ? rows_cta : nr;
+        if (!IS8) {
+            const int upr = nb;                                // (g, j) units per row: one 16-byte weight word each
+            for (int u = tid; u < nr * upr; u += nt) {
+                const int rl = u / upr, gj = u - rl * upr, g = gj >> 2, jj = gj & 3;
+                const uint8_t * wr = s_w + (size_t) rl * a.stride;
+                const uint4 w = *(const uint4 *) (wr + gj * 16);
+                uint4 lo, hi;
+                lo.x = w.x & 0x0F0F0F0Fu; lo.y = w.y & 0x0F0F0F0Fu; lo.z = w.z & 0x0F0F0F0Fu; lo.w = w.w & 0x0F0F0F0Fu;
+                hi.x = (w.x >> 4) & 0x0F0F0F0Fu; hi.y = (w.y >> 4) & 0x0F0F0F0Fu; hi.z = (w.z >> 4) & 0x0F0F0F0Fu; hi.w = (w.w >> 4) & 0x0F0F0F0Fu;
+                if (HASQH) {
+                    const uint32_t qh = *(const uint32_t *) (wr + a.off_qh + gj * 4);
+                    lo.x |= bg_spread4(qh & 0xFu);          hi.x |= bg_spread4((qh >> 4) & 0xFu);
+                    lo.y |= bg_spread4((qh >> 8) & 0xFu);   hi.y |= bg_spread4((qh >> 12) & 0xFu);
+                    lo.z |= bg_spread4((qh >> 16) & 0xFu);  hi.z |= bg_spread4((qh >> 20) & 0xFu);
+                    lo.w |= bg_spread4((qh >> 24) & 0xFu);  hi.w |= bg_spread4((qh >> 28) & 0xFu);
+                }
+                uint8_t * dr = s_dec + (size_t) rl * K;
+                *(uint4 *) (dr + (g * 8 + jj) * 16) = lo;
+                *(uint4 *) (dr + (g * 8 + jj + 4) * 16) = hi;
+            }
+        }
+        for (int u = tid; u < nr * nb; u += nt) {
+            const int rl = u / nb, b = u - rl * nb;
+            const uint8_t * wr = s_w + (size_t) rl * a.stride;
+            s_dw[u] = bg_h2f(*(const uint16_t *) (wr + a.off_d + b * 2));
+            if (HASM) s_mw[u] = bg_h2f(*(const uint16_t *) (wr + a.off_m + b * 2));
+        }
+    }
     sk_pdl_wait();                                             // from here on the previous kernel's results are visible
     // ---- token records: consecutive records are contiguous, ONE bulk copy
     {
@@ -208,7 +245,6 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
                          :: "r"(m4_s32(s_rec)), "l"(a.act + (size_t) tokbase * a.act_bytes), "r"(bytes), "r"(m4_s32(&s_bar[1])) : "memory");
         }
         for (int i = (int) (bytes >> 4) + tid; i < TN * (a.act_bytes >> 4); i += nt) ((uint4 *) s_rec)[i] = make_uint4(0, 0, 0, 0);
-        m4_mbar_wait(&s_bar[0], 0);
         m4_mbar_wait(&s_bar[1], 0);
     }
     __syncthreads();
@@ -217,7 +253,8 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
 #pragma unroll 1
     for (int i = 0; i < a.rpw; i++) {
         const int rl = i * nw + warp, row = rowbase + rl;
-        const uint8_t * wrow = s_w + (size_t) rl * a.stride;
+        const uint8_t * wrow = IS8 ? s_w + (size_t) rl * a.stride : s_dec + (size_t) rl * K;   // codes [g][l][i]
+        const float * dwr = s_dw + (size_t) rl * nb, * mwr = s_mw + (size_t) rl * nb;
         // the row owner's bias / residual are in flight while the dots run
         float pbias = 0.0f, presid[TN / 4];
 #pragma unroll
@@ -235,31 +272,10 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
         for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
 #pragma unroll 2
         for (int g = 0; g < ng; g++) {
-            uint32_t wq[4];
-            if (IS8) {
-                const uint4 w = *(const uint4 *) (wrow + ((g * 2 + c) * 4 + j) * 16);
-                wq[0] = w.x; wq[1] = w.y; wq[2] = w.z; wq[3] = w.w;
-            } else {
-                const uint4 w = *(const uint4 *) (wrow + (g * 4 + j) * 16);
-                const int sh = 4 * c;
-                wq[0] = (w.x >> sh) & 0x0F0F0F0Fu; wq[1] = (w.y >> sh) & 0x0F0F0F0Fu;
-                wq[2] = (w.z >> sh) & 0x0F0F0F0Fu; wq[3] = (w.w >> sh) & 0x0F0F0F0Fu;
-                if (HASQH) {
-                    const uint32_t qh = *(const uint32_t *) (wrow + a.off_qh + g * 16 + j * 4) >> sh;
-                    wq[0] |= bg_spread4(qh & 0xFu);         wq[1] |= bg_spread4((qh >> 8) & 0xFu);
-                    wq[2] |= bg_spread4((qh >> 16) & 0xFu); wq[3] |= bg_spread4((qh >> 24) & 0xFu);
-                }
-            }
-            const uint2 dh = *(const uint2 *) (wrow + a.off_d + g * 8);
-            float dw[4];
-            dw[0] = bg_h2f((uint16_t) (dh.x & 0xFFFF)); dw[1] = bg_h2f((uint16_t) (dh.x >> 16));
-            dw[2] = bg_h2f((uint16_t) (dh.y & 0xFFFF)); dw[3] = bg_h2f((uint16_t) (dh.y >> 16));
-            float mw[4] = { 0.f, 0.f, 0.f, 0.f };
-            if (HASM && l == 0) {
-                const uint2 mh = *(const uint2 *) (wrow + a.off_m + g * 8);
-                mw[0] = bg_h2f((uint16_t) (mh.x & 0xFFFF)); mw[1] = bg_h2f((uint16_t) (mh.x >> 16));
-                mw[2] = bg_h2f((uint16_t) (mh.y & 0xFFFF)); mw[3] = bg_h2f((uint16_t) (mh.y >> 16));
-            }
+            const uint4 wq = *(const uint4 *) (wrow + (g * 8 + l) * 16);
+            const float4 dw = *(const float4 *) (dwr + g * 4);
+            float4 mw = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HASM && l == 0) mw = *(const float4 *) (mwr + g * 4);
 #pragma unroll
             for (int r = 0; r < TN / 4; r++) {
                 const uint8_t * rec = rec0 + (size_t) (r * 4) * a.act_bytes;
@@ -268,15 +284,15 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
                 if (HASOFF) nv = *(const int4 *) (rec + a.off_n + (g * 8 + l) * 16);
                 const float4 da = *(const float4 *) (rec + a.off_dd + g * 16);
                 float cacc = acc[r];
-                cacc = fmaf(__fmul_rn(dw[0], da.x), (float) __dp4a((int) wq[0], (int) av.x, nv.x), cacc);
-                cacc = fmaf(__fmul_rn(dw[1], da.y), (float) __dp4a((int) wq[1], (int) av.y, nv.y), cacc);
-                cacc = fmaf(__fmul_rn(dw[2], da.z), (float) __dp4a((int) wq[2], (int) av.z, nv.z), cacc);
-                cacc = fmaf(__fmul_rn(dw[3], da.w), (float) __dp4a((int) wq[3], (int) av.w, nv.w), cacc);
+                cacc = fmaf(__fmul_rn(dw.x, da.x), (float) __dp4a((int) wq.x, (int) av.x, nv.x), cacc);
+                cacc = fmaf(__fmul_rn(dw.y, da.y), (float) __dp4a((int) wq.y, (int) av.y, nv.y), cacc);
+                cacc = fmaf(__fmul_rn(dw.z, da.z), (float) __dp4a((int) wq.z, (int) av.z, nv.z), cacc);
+                cacc = fmaf(__fmul_rn(dw.w, da.w), (float) __dp4a((int) wq.w, (int) av.w, nv.w), cacc);
                 acc[r] = cacc;
                 if (HASM && l == 0) {
                     const float4 sa = *(const float4 *) (rec + a.off_s + g * 16);
                     float sm = summ[r];
-                    sm = fmaf(mw[0], sa.x, sm); sm = fmaf(mw[1], sa.y, sm); sm = fmaf(mw[2], sa.z, sm); sm = fmaf(mw[3], sa.w, sm);
+                    sm = fmaf(mw.x, sa.x, sm); sm = fmaf(mw.y, sa.y, sm); sm = fmaf(mw.z, sa.z, sm); sm = fmaf(mw.w, sa.w, sm);
                     summ[r] = sm;
                 }
             }
