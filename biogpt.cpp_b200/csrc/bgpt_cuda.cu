@@ -108,7 +108,7 @@ struct bgpt_model {
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
-    int sk_pdl_trig = 1, sk_tn_proj = 4, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
+    int sk_pdl_trig = 0, sk_tn_proj = 4, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };

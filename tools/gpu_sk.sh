@@ -34,7 +34,10 @@ skips)
 launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_streams.csv \
       python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 2 --n-past 511 --reps 1 > $OUT/launches_streams.log 2>&1; echo "launches rc=$?"
-  python tools/launch_summary.py $OUT/launches_streams.csv | tee $OUT/launches_streams_summary.txt ;;
+  python tools/launch_summary.py $OUT/launches_streams.csv | tee $OUT/launches_streams_summary.txt
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_sk|k_embed|k_act|k_gemv" -c 400 --csv --log-file $OUT/launches_prompt8.csv \
+      python tools/profile_prompt.py --ftype q8_0 --n 8 --n-past 512 --reps 2 > $OUT/launches_prompt8.log 2>&1; echo "launches prompt rc=$?"
+  python tools/launch_summary.py $OUT/launches_prompt8.csv | tee $OUT/launches_prompt8_summary.txt ;;
 full)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sk_mm -s 6 -c 5 -f -o $OUT/sk_mm_full \
       python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 2 --n-past 511 --reps 1 > $OUT/sk_mm_full.log 2>&1; echo "full rc=$?"
