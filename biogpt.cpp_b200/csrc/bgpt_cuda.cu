@@ -954,13 +954,13 @@ static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop) {
 
 // one token at n_past on the persistent kernel.  token source: d_tok (device) or the previous
 // launch's argmax candidates (use_cand).  Asynchronous on the model's stream.
-static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot) {
+static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot, int tok_imm = 0) {
     if (m->mega4_ok && m->decode_path == 1) {
         M4Params P = m->m4;
         MegaParams & q = P.b;
         q.kcache = m->kcache; q.vcache = m->vcache; q.logits = m->logits;
         q.x = m->x; q.x1 = m->x1; q.q = m->q; q.att = m->att; q.hff = m->hff;
-        q.tok = d_tok; q.use_cand = use_cand; q.idlog = m->d_idlog; q.log_slot = log_slot; q.n_past = n_past;
+        q.tok = d_tok; q.use_cand = use_cand; q.tok_imm = tok_imm; q.idlog = m->d_idlog; q.log_slot = log_slot; q.n_past = n_past;
         if (++m->m4_tag >= (1u << 26)) m->m4_tag = 1;        // 0 is the "never written" tag of a fresh buffer
         P.tag = m->m4_tag << 6;
         void * args[] = { &P };
@@ -971,7 +971,7 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
     MegaParams p = m->mp;
     p.kcache = m->kcache; p.vcache = m->vcache;
     p.x = m->x; p.x1 = m->x1; p.q = m->q; p.att = m->att; p.hff = m->hff; p.logits = m->logits;
-    p.tok = d_tok; p.use_cand = use_cand; p.idlog = m->d_idlog; p.log_slot = log_slot; p.n_past = n_past;
+    p.tok = d_tok; p.use_cand = use_cand; p.tok_imm = tok_imm; p.idlog = m->d_idlog; p.log_slot = log_slot; p.n_past = n_past;
     p.epoch0 = m->bar_epoch;
     m->bar_epoch += (unsigned long long) 5 * m->n_layer * m->mega_grid;
     void * args[] = { &p };
@@ -1048,10 +1048,13 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
     memcpy(m->h_tokens, tokens, (size_t) n * sizeof(int));
     m->h_st->n_past = n_past; m->h_st->step = 0; m->h_st->pad0 = m->h_st->pad1 = 0;
     CK(cudaEventRecord(m->ev0, s));
-    CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
-    if (n == 1 && use_mega(m)) { RET(launch_mega(m, m->d_tokens, 0, n_past, -1)); }
-    else RET(forward(m, m->d_tokens, n, 0));
+    if (n == 1 && use_mega(m)) {                     // token id and position travel in the kernel parameters: no host-to-device copy
+        RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0]));
+    } else {
+        CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+        RET(forward(m, m->d_tokens, n, 0));
+    }
     CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));

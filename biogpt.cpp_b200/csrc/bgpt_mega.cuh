@@ -61,7 +61,8 @@ struct MegaParams {
     uint8_t * rec_att; uint8_t * rec_hff;               // activation records published by their producers
     unsigned long long * flags; unsigned long long epoch0;   // grid barrier counter and its value at launch
     const int * tok;                                    // device: input token id (use_cand == 0)
-    int use_cand; float * cand_val; int * cand_idx; int n_cand;   // argmax candidates of the previous launch
+    int use_cand; float * cand_val; int * cand_idx; int n_cand;   // 1: argmax over the candidates of the previous launch
+    int tok_imm;                                        // use_cand == 2: the input token id travels in the kernel parameters
     int * idlog; int log_slot;                          // idlog[log_slot] = input token when log_slot >= 0
     int n_past;
     int attn_parts;                                     // CTAs per head in the attention phase (column split)
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
     // ---- input token: given, or argmax over the candidates the previous launch left
     if (tid < 32) {
         int tok;
-        if (p.use_cand) {
+        if (p.use_cand == 1) {
             float best = -INFINITY; int bi = 0x7fffffff;
             for (int i = tid; i < p.n_cand; i += 32) {
                 const float v = __ldcg(p.cand_val + i); const int ix = __ldcg(p.cand_idx + i);
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
                 if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
             }
             tok = bi == 0x7fffffff ? 0 : bi;
-        } else tok = __ldcg(p.tok);
+        } else tok = p.use_cand == 2 ? p.tok_imm : __ldcg(p.tok);
         if (tid == 0) {
             s_tok = tok;
             if (blockIdx.x == 0 && p.log_slot >= 0) p.idlog[p.log_slot] = tok;

@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
     // ---- input token: given, or argmax over the candidates the previous launch left
     if (tid < 32) {
         int tok;
-        if (p.use_cand) {
+        if (p.use_cand == 1) {
             float best = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 1
             for (int i = tid; i < p.n_cand; i += 32) {
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(M4_NT, 1) k_mega4(const __grid_constant__ M4Pa
                 if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
             }
             tok = bi == 0x7fffffff ? 0 : bi;
-        } else tok = __ldcg(p.tok);
+        } else tok = p.use_cand == 2 ? p.tok_imm : __ldcg(p.tok);
         if (tid == 0) {
             s_tok = tok;
             if (cta == 0 && p.log_slot >= 0) p.idlog[p.log_slot] = tok;

@@ -1,41 +1,33 @@
 // bgpt_skinny.cuh -- fused schedule for SKINNY batches (2..31 token rows) of the quantised formats
-// at BioGPT-base layer shapes (d_model 1024, 16 heads of 64, d_ff a multiple of 1024): the
-// reference's own prompt chunking (n_batch = 8, BASELINE configs[2]) and lock-step streams
-// (8 sequences per GPU, configs[3]).
+// at BioGPT-base layer shapes (d_model 1024, 16 heads of 64, d_ff 4096): the reference's own prompt
+// chunking (n_batch = 8, BASELINE configs[2]) and lock-step streams (8 sequences per GPU, configs[3]).
 //
-// The per-operator schedule (bgpt_kernels.cuh) spends 9 launches per layer, and its GEMV keeps
-// 4 threads on a row walking K with dependent loads: 10-17 us per kernel on 16-128 CTAs, 2.8 ms
-// per 8-row step.  Here a layer is 5 launches, every one of them wide:
+// The per-operator schedule (bgpt_kernels.cuh) spends 9 launches per layer, its GEMV keeps 4 threads
+// on a row walking K with dependent loads, and its LayerNorm / quantise kernels run on 8 CTAs: 10-17 us
+// per kernel, 2.8 ms per 8-row step.  Here a layer is 7 launches, every one of them wide:
 //
-//   k_sk_mm  qkv   : LayerNorm0 + quantise in the prologue (each CTA redoes the <= 8 rows: 32 KB
-//                    from L2, one warp per row, no block-wide step), 3072 stacked rows, one warp
-//                    per weight row; epilogue bias, q scale, KV append          (384 CTAs)
-//   k_sk_attn      : one (head, row) per CTA of 1024 threads, 16 K rows in flight per warp, transposing butterfly
-//                    for the reduce trees, V with 16 rows in flight per thread; the 64 outputs leave
-//                    as two quantised blocks of out_proj's activation record     (16 x rows CTAs)
-//   k_sk_mm  o     : records staged from global; bias + residual                 (128 CTAs)
-//   k_sk_mm  fc1   : LayerNorm1 prologue, 32 consecutive rows per CTA = one block of fc2's input;
-//                    bias + fp16-table GELU + quantise in the epilogue           (128 CTAs)
-//   k_sk_mm  fc2   : K = 4096 in four 1024-wide chunks; bias + residual          (128 CTAs)
-//   k_sk_mm lm_head: final LayerNorm prologue, 32 rows per CTA                   (1325 CTAs)
+//   k_sk_ln        : LayerNorm0 + quantise, one token row per CTA                   (rows CTAs)
+//   k_sk_mm  qkv   : 3072 stacked rows, one warp per weight row, 8 token rows per warp; epilogue bias,
+//                    q scale, KV append; prefetches the cached K/V rows of the layer into L2    (384 CTAs)
+//   k_sk_attn      : one (head, row) per CTA of 1024 threads, 16 K rows in flight per warp, transposing
+//                    butterfly for the reduce trees, V with 16 rows in flight per thread; the 64 outputs
+//                    leave as two quantised blocks of out_proj's activation record  (16 x rows CTAs)
+//   k_sk_mm  o     : 4-row token tiles; bias + residual                             (128 x 2 CTAs)
+//   k_sk_ln        : LayerNorm1 + quantise
+//   k_sk_mm  fc1   : 32 consecutive rows per CTA (16 warps x 2) = one block of fc2's input; bias +
+//                    fp16-table GELU (one batch of look-ups) + quantise in the epilogue (128 x 2 CTAs)
+//   k_sk_mm  fc2   : K = 4096; bias + residual                                      (128 x 2 CTAs)
+//   k_sk_ln + k_sk_mm lm_head (lock-step streams: every row has logits)              (1325 CTAs)
 //
-// Dot products (same bits as k_gemv_q and the persistent kernels: the 8 running sums of
-// ggml_vec_dot_q*_q8_*, acc_l = fma(d_w d_a, (float) isum_l, acc_l) in block order, hsum_float_8):
-// a warp owns a weight row.  Phase A: lane (g, j) turns its 16-byte weight word -- 4 blocks x the
-// 4-element groups of sums j and j+4 -- into 8 exact integer dots per token row (dp4a) and parks them,
-// with the 4 scale products, in a warp-private shared scratch.  Phase B: lane (token, l) walks sum l
-// of its token over the 32 blocks in order.  4 token rows per round (32 chains = 32 lanes), two rounds
-// for 8 rows; the next chunk's weight words are already in registers (1-deep prefetch), and the first
-// chunk is fetched BEFORE griddepcontrol.wait, i.e. while the previous kernel of the chain is still
-// running (programmatic dependent launch): weights never wait for activations.
+// Dot products keep the bits of k_gemv_q and the persistent kernels -- the 8 running sums of
+// ggml_vec_dot_q*_q8_*, acc_l = fma(d_w d_a, (float) isum_l, acc_l) in block order, hsum_float_8 --
+// with lane = (token, running sum): see k_sk_mm.  The kernels are chained by programmatic dependent
+// launch: everything that touches only weights (tile fetch by TMA bulk copy, decode) sits before
+// griddepcontrol.wait and overlaps the tail of the previous kernel; one CUDA graph per (rows, mode).
 #pragma once
 #include "bgpt_kernels.cuh"
 #include "bgpt_mega4.cuh"      // mbarrier / bulk-copy helpers
 
-#define SK_NT 256
-#define SK_NW 8
-#define SK_PS 36                                   // floats between two chains of the scratch (bank spread)
-#define SK_SCR (32 * SK_PS + 4 * SK_PS + 32)       // floats of scratch per warp: products, scales, mins
 #define SK_D 1024
 #define SK_DK 64
 #define SK_ANT 1024                                // threads of the attention kernel
