@@ -31,6 +31,10 @@ skips)
     env $v BGPT_SK_SKIP=$k timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 2
   done; done > $OUT/skips.log 2>&1
   cat $OUT/skips.log ;;
+nstreams)
+  for S in 4 16 24; do timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 64; timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 32 --n-past 480; done > $OUT/nstreams.log 2>&1
+  for ft in q4_0 q8_0; do timeout 300 python tools/streams_bench.py --ftype $ft --streams 8 --steps 64; done >> $OUT/nstreams.log 2>&1
+  cat $OUT/nstreams.log ;;
 launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_streams.csv \
       python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 2 --n-past 511 --reps 1 > $OUT/launches_streams.log 2>&1; echo "launches rc=$?"
