@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 4) k_sk_ln(const __grid_constant__ SkLnAr
 // and one more brings the token records once that kernel has finished.  Lanes of different tokens read the same weight
 // word (broadcast), a token's eight lanes read 128 consecutive bytes of its record: no bank conflicts.
 // grid = (ceil(M / (nw * rpw)), ceil((n - tok0) / TN)), block = 32 * nw,
-// dynamic smem = TN * act_bytes + nw * rpw * (stride + (Q8_0 ? 0 : K) + K / 32 * 4 * (1 + has minima))
+// dynamic smem = TN * (act_bytes + (TN == 8 ? 64 : 0)) + nw * rpw * (stride + (Q8_0 ? 0 : K) + K / 32 * 4 * (1 + has minima))
 // ---------------------------------------------------------------------------------------------
 template <int FMT, int TN>
 __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs a) {
@@ -158,14 +158,17 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = blockDim.x, nw = nt >> 5;
     const int rows_cta = nw * a.rpw;
     const int K = a.npass * 1024, nb = K >> 5;
-    uint8_t * s_rec = sk_smem;                                                   // [TN][act_bytes] token records
-    uint8_t * s_w = s_rec + (size_t) TN * a.act_bytes;                           // [rows_cta][stride] weight rows as they lie in HBM
+    const int rec_stride = a.act_bytes + (TN == 8 ? 64 : 0);                     // 8-row tiles: two tokens share a quarter-warp, +64 bytes keeps them on different banks
+    uint8_t * s_rec = sk_smem;                                                   // [TN][rec_stride] token records
+    uint8_t * s_w = s_rec + (size_t) TN * rec_stride;                            // [rows_cta][stride] weight rows as they lie in HBM
     uint8_t * s_dec = s_w + (size_t) rows_cta * a.stride;                        // [rows_cta][K] int8 codes [g][l][i] (Q8_0: the raw rows already are)
     float * s_dw = (float *) (s_dec + (IS8 ? 0 : (size_t) rows_cta * K));        // [rows_cta][nb] block scales as f32
     float * s_mw = s_dw + (size_t) rows_cta * nb;                                // [rows_cta][nb] block minima as f32 (Q4_1 / Q5_1)
     const int tokbase = a.tok0 + blockIdx.y * TN;
     const int rowbase = blockIdx.x * rows_cta;
-    const int tq = lane >> 3, l = lane & 7;
+    // TN = 4: lane = (token tq, running sum l), one chain per lane.  TN = 8: lane = (token tq, pair l): running sums l and l + 4,
+    // two chains per lane that share the scale product -- per 8 tokens less than half the instructions of two 4-token tiles.
+    const int tq = TN == 8 ? lane >> 2 : lane >> 3, l = TN == 8 ? (lane & 3) : (lane & 7);
     auto mat_of = [&](int row) -> int { return row >= 2 * a.rows_per ? 2 : (row >= a.rows_per ? 1 : 0); };
     // ---- everything that does not depend on the previous kernel: the weight tile, n_past, K/V rows towards the L2
     if (tid == 0) {
@@ -227,97 +230,96 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
         }
     }
     sk_pdl_wait();                                             // from here on the previous kernel's results are visible
-    // ---- token records: consecutive records are contiguous, ONE bulk copy
+    // ---- token records: bulk copies (TMA); 4-row tiles: consecutive records are contiguous, one copy
     {
         int nv = a.n - tokbase; nv = nv > TN ? TN : nv;
         const uint32_t bytes = (uint32_t) nv * (uint32_t) a.act_bytes;
         if (tid == 0) {
             m4_mbar_expect(&s_bar[1], bytes);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(m4_s32(s_rec)), "l"(a.act + (size_t) tokbase * a.act_bytes), "r"(bytes), "r"(m4_s32(&s_bar[1])) : "memory");
+            const int ncopy = TN == 8 ? nv : 1;
+            const uint32_t each = TN == 8 ? (uint32_t) a.act_bytes : bytes;
+            for (int t = 0; t < ncopy; t++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(m4_s32(s_rec + (size_t) t * rec_stride)), "l"(a.act + (size_t) (tokbase + t) * a.act_bytes), "r"(each), "r"(m4_s32(&s_bar[1])) : "memory");
         }
-        for (int i = (int) (bytes >> 4) + tid; i < TN * (a.act_bytes >> 4); i += nt) ((uint4 *) s_rec)[i] = make_uint4(0, 0, 0, 0);
+        const int v16 = a.act_bytes >> 4;
+        for (int i = nv * v16 + tid; i < TN * v16; i += nt) { const int t = i / v16; ((uint4 *) (s_rec + (size_t) t * rec_stride))[i - t * v16] = make_uint4(0, 0, 0, 0); }
         m4_mbar_wait(&s_bar[1], 0);
     }
     __syncthreads();
     const int ng = 8 * a.npass;                                // groups of 4 blocks in a row
-    const uint8_t * rec0 = s_rec + (size_t) tq * a.act_bytes;
+    const uint8_t * rec = s_rec + (size_t) tq * rec_stride;
 #pragma unroll 1
     for (int i = 0; i < a.rpw; i++) {
         const int rl = i * nw + warp, row = rowbase + rl;
-        const uint8_t * wrow = IS8 ? s_w + (size_t) rl * a.stride : s_dec + (size_t) rl * K;   // codes [g][l][i]
+        const uint8_t * wrow = IS8 ? s_w + (size_t) rl * a.stride : s_dec + (size_t) rl * K;   // codes [g][sum][i]
         const float * dwr = s_dw + (size_t) rl * nb, * mwr = s_mw + (size_t) rl * nb;
+        const int tok = tokbase + tq;
+        const bool owner = l == 0 && row < a.M && tok < a.n;
         // the row owner's bias / residual are in flight while the dots run
-        float pbias = 0.0f, presid[TN / 4];
-#pragma unroll
-        for (int r = 0; r < TN / 4; r++) presid[r] = 0.0f;
-        if (l == 0 && row < a.M) {
+        float pbias = 0.0f, presid = 0.0f;
+        if (owner) {
             if (a.epi == SK_EPI_QKV) { const int mat = mat_of(row); pbias = a.bias[mat][row - mat * a.rows_per]; }
             else if (a.bias[0]) pbias = a.bias[0][row];
-            if (a.epi == SK_EPI_RESID) {
-#pragma unroll
-                for (int r = 0; r < TN / 4; r++) { const int tok = tokbase + r * 4 + tq; if (tok < a.n) presid[r] = __ldcg(a.resid + (size_t) tok * a.ld_resid + row); }
-            }
+            if (a.epi == SK_EPI_RESID) presid = __ldcg(a.resid + (size_t) tok * a.ld_resid + row);
         }
-        float acc[TN / 4], summ[TN / 4];
-#pragma unroll
-        for (int r = 0; r < TN / 4; r++) { acc[r] = 0.0f; summ[r] = 0.0f; }
+        float acc0 = 0.0f, acc1 = 0.0f, summ = 0.0f;
 #pragma unroll 2
         for (int g = 0; g < ng; g++) {
-            const uint4 wq = *(const uint4 *) (wrow + (g * 8 + l) * 16);
             const float4 dw = *(const float4 *) (dwr + g * 4);
-            float4 mw = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (HASM && l == 0) mw = *(const float4 *) (mwr + g * 4);
-#pragma unroll
-            for (int r = 0; r < TN / 4; r++) {
-                const uint8_t * rec = rec0 + (size_t) (r * 4) * a.act_bytes;
+            const float4 da = *(const float4 *) (rec + a.off_dd + g * 16);
+            const float sx = __fmul_rn(dw.x, da.x), sy = __fmul_rn(dw.y, da.y), sz = __fmul_rn(dw.z, da.z), sw = __fmul_rn(dw.w, da.w);
+            {
+                const uint4 wq = *(const uint4 *) (wrow + (g * 8 + l) * 16);
                 const uint4 av = *(const uint4 *) (rec + (g * 8 + l) * 16);
                 int4 nv = make_int4(0, 0, 0, 0);
                 if (HASOFF) nv = *(const int4 *) (rec + a.off_n + (g * 8 + l) * 16);
-                const float4 da = *(const float4 *) (rec + a.off_dd + g * 16);
-                float cacc = acc[r];
-                cacc = fmaf(__fmul_rn(dw.x, da.x), (float) __dp4a((int) wq.x, (int) av.x, nv.x), cacc);
-                cacc = fmaf(__fmul_rn(dw.y, da.y), (float) __dp4a((int) wq.y, (int) av.y, nv.y), cacc);
-                cacc = fmaf(__fmul_rn(dw.z, da.z), (float) __dp4a((int) wq.z, (int) av.z, nv.z), cacc);
-                cacc = fmaf(__fmul_rn(dw.w, da.w), (float) __dp4a((int) wq.w, (int) av.w, nv.w), cacc);
-                acc[r] = cacc;
-                if (HASM && l == 0) {
-                    const float4 sa = *(const float4 *) (rec + a.off_s + g * 16);
-                    float sm = summ[r];
-                    sm = fmaf(mw.x, sa.x, sm); sm = fmaf(mw.y, sa.y, sm); sm = fmaf(mw.z, sa.z, sm); sm = fmaf(mw.w, sa.w, sm);
-                    summ[r] = sm;
-                }
+                acc0 = fmaf(sx, (float) __dp4a((int) wq.x, (int) av.x, nv.x), acc0);
+                acc0 = fmaf(sy, (float) __dp4a((int) wq.y, (int) av.y, nv.y), acc0);
+                acc0 = fmaf(sz, (float) __dp4a((int) wq.z, (int) av.z, nv.z), acc0);
+                acc0 = fmaf(sw, (float) __dp4a((int) wq.w, (int) av.w, nv.w), acc0);
+            }
+            if (TN == 8) {
+                const uint4 wq = *(const uint4 *) (wrow + (g * 8 + l + 4) * 16);
+                const uint4 av = *(const uint4 *) (rec + (g * 8 + l + 4) * 16);
+                int4 nv = make_int4(0, 0, 0, 0);
+                if (HASOFF) nv = *(const int4 *) (rec + a.off_n + (g * 8 + l + 4) * 16);
+                acc1 = fmaf(sx, (float) __dp4a((int) wq.x, (int) av.x, nv.x), acc1);
+                acc1 = fmaf(sy, (float) __dp4a((int) wq.y, (int) av.y, nv.y), acc1);
+                acc1 = fmaf(sz, (float) __dp4a((int) wq.z, (int) av.z, nv.z), acc1);
+                acc1 = fmaf(sw, (float) __dp4a((int) wq.w, (int) av.w, nv.w), acc1);
+            }
+            if (HASM && l == 0) {
+                const float4 mw = *(const float4 *) (mwr + g * 4);
+                const float4 sa = *(const float4 *) (rec + a.off_s + g * 16);
+                summ = fmaf(mw.x, sa.x, summ); summ = fmaf(mw.y, sa.y, summ); summ = fmaf(mw.z, sa.z, summ); summ = fmaf(mw.w, sa.w, summ);
             }
         }
-#pragma unroll
-        for (int r = 0; r < TN / 4; r++) {
-            // hsum_float_8: (a_l + a_{l+4}), then the pairs 2 apart, then 1 apart (ggml.c:611-617)
-            float v = __fadd_rn(acc[r], __shfl_xor_sync(FULLMASK, acc[r], 4));
-            v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 2));
-            v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 1));
-            if (HASM) v = __fadd_rn(v, summ[r]);
-            const int tok = tokbase + r * 4 + tq;
-            if (l == 0 && row < a.M && tok < a.n) {
-                switch (a.epi) {
-                case SK_EPI_STORE:
-                    a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(pbias, v) : v;
-                    break;
-                case SK_EPI_QKV: {
-                    const int mat = mat_of(row), rr = row - mat * a.rows_per;
-                    const float t = __fadd_rn(pbias, v);
-                    if (mat == 0) a.out[(size_t) tok * a.ld_out + rr] = __fmul_rn(t, a.qscale);
-                    else {
-                        int stream, pos, T; bg_row_info(a.mode, a.n, n_past, tok, stream, pos, T);
-                        (mat == 1 ? a.kcache : a.vcache)[(size_t) stream * a.stream_stride + (size_t) pos * a.rows_per + rr] = t;
-                    }
-                    break; }
-                case SK_EPI_RESID:
-                    a.out[(size_t) tok * a.ld_out + row] = __fadd_rn(__fadd_rn(v, pbias), presid[r]);
-                    break;
-                default:                                       // GELU input; the table look-ups run as one batch after the loop
-                    s_g[(r * 4 + tq) * 32 + rl] = __fadd_rn(pbias, v);
-                    break;
+        // hsum_float_8: (a_l + a_{l+4}), then the pairs 2 apart, then 1 apart (ggml.c:611-617)
+        float v = TN == 8 ? __fadd_rn(acc0, acc1) : __fadd_rn(acc0, __shfl_xor_sync(FULLMASK, acc0, 4));
+        v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 2));
+        v = __fadd_rn(v, __shfl_xor_sync(FULLMASK, v, 1));
+        if (HASM) v = __fadd_rn(v, summ);
+        if (owner) {
+            switch (a.epi) {
+            case SK_EPI_STORE:
+                a.out[(size_t) tok * a.ld_out + row] = a.bias[0] ? __fadd_rn(pbias, v) : v;
+                break;
+            case SK_EPI_QKV: {
+                const int mat = mat_of(row), rr = row - mat * a.rows_per;
+                const float t = __fadd_rn(pbias, v);
+                if (mat == 0) a.out[(size_t) tok * a.ld_out + rr] = __fmul_rn(t, a.qscale);
+                else {
+                    int stream, pos, T; bg_row_info(a.mode, a.n, n_past, tok, stream, pos, T);
+                    (mat == 1 ? a.kcache : a.vcache)[(size_t) stream * a.stream_stride + (size_t) pos * a.rows_per + rr] = t;
                 }
+                break; }
+            case SK_EPI_RESID:
+                a.out[(size_t) tok * a.ld_out + row] = __fadd_rn(__fadd_rn(v, pbias), presid);
+                break;
+            default:                                           // GELU input; the table look-ups run as one batch after the loop
+                s_g[tq * 32 + rl] = __fadd_rn(pbias, v);
+                break;
             }
         }
     }
@@ -327,11 +329,11 @@ __global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs
         for (int i = tid; i < TN * 32; i += nt) s_g[i] = bg_h2f(a.gelu[bg_f2h(s_g[i])]);
         __syncthreads();
         if (warp < TN) {
-            const int tok = tokbase + warp;
-            const float4 v = *(const float4 *) (s_g + warp * 32 + 4 * l);
+            const int tok = tokbase + warp, l8 = lane & 7;
+            const float4 v = *(const float4 *) (s_g + warp * 32 + 4 * l8);
             const bool wr = tok < a.n && lane < 8;
-            uint8_t * rec = a.act_out + (size_t) (tok < a.n ? tok : 0) * a.out_bytes;
-            sk_quant_block<FMT>(v, blockIdx.x, l, rec, a.out_off_n, a.out_off_d, a.out_off_s, a.code_off, wr);
+            uint8_t * orec = a.act_out + (size_t) (tok < a.n ? tok : 0) * a.out_bytes;
+            sk_quant_block<FMT>(v, blockIdx.x, l8, orec, a.out_off_n, a.out_off_d, a.out_off_s, a.code_off, wr);
         }
     }
 }

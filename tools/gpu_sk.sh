@@ -16,7 +16,7 @@ alltests)
   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"
   tail -20 $OUT/pytest_gpu.log ;;
 perf)
-  for v in "X=0" "BGPT_SK_PDL_TRIG=0" "BGPT_PDL=0" "BGPT_SK_TN_PROJ=8" "BGPT_SK_FC1_NW=8" "BGPT_SK_PDL_TRIG=0 BGPT_SK_TN_PROJ=8"; do
+  for v in "X=0" "BGPT_SK_TN_PROJ=4" "BGPT_SK_TN_PROJ=4 BGPT_SK_TN_QKV=4" "BGPT_SK_FC1_NW=8" "BGPT_SK_PDL_TRIG=1" "BGPT_PDL=0"; do
     echo "== variant: ${v:-default}"
     env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64
     env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 1
@@ -32,7 +32,7 @@ skips)
   done; done > $OUT/skips.log 2>&1
   cat $OUT/skips.log ;;
 nstreams)
-  for S in 4 16 24; do timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 64; timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 32 --n-past 480; done > $OUT/nstreams.log 2>&1
+  for S in 2 4 16 24; do timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 64; timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 32 --n-past 480; done > $OUT/nstreams.log 2>&1
   for ft in q4_0 q8_0; do timeout 300 python tools/streams_bench.py --ftype $ft --streams 8 --steps 64; done >> $OUT/nstreams.log 2>&1
   cat $OUT/nstreams.log ;;
 launches)
