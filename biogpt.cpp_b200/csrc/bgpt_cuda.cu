@@ -108,7 +108,7 @@ struct bgpt_model {
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
-    int sk_pdl_trig = 0, sk_tn_proj = 8, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
+    int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -338,9 +338,9 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_PDL")) m->use_pdl = atoi(getenv("BGPT_PDL")) != 0;
     if (getenv("BGPT_BATCH_PATH")) m->batch_path = atoi(getenv("BGPT_BATCH_PATH")) != 0;
     if (getenv("BGPT_SK_PDL_TRIG")) m->sk_pdl_trig = atoi(getenv("BGPT_SK_PDL_TRIG")) != 0;
-    if (getenv("BGPT_SK_TN_PROJ")) m->sk_tn_proj = atoi(getenv("BGPT_SK_TN_PROJ")) == 8 ? 8 : 4;
+    if (getenv("BGPT_SK_TN_PROJ")) m->sk_tn_proj = atoi(getenv("BGPT_SK_TN_PROJ")) == 8 ? 8 : (atoi(getenv("BGPT_SK_TN_PROJ")) == 4 ? 4 : 0);
     if (getenv("BGPT_SK_TN_QKV")) m->sk_tn_qkv = atoi(getenv("BGPT_SK_TN_QKV")) == 4 ? 4 : 8;
-    if (getenv("BGPT_SK_FC1_NW")) m->sk_fc1_nw = atoi(getenv("BGPT_SK_FC1_NW")) == 8 ? 8 : 16;
+    if (getenv("BGPT_SK_FC1_NW")) { const int v = atoi(getenv("BGPT_SK_FC1_NW")); m->sk_fc1_nw = v == 8 ? 8 : (v == 32 ? 32 : 16); }
     if (getenv("BGPT_SK_SKIP")) m->sk_skip = atoi(getenv("BGPT_SK_SKIP"));
     if (getenv("BGPT_SK_KVPF")) m->sk_kv_prefetch = atoi(getenv("BGPT_SK_KVPF")) != 0;
     RET(mega_setup(m));
@@ -625,7 +625,11 @@ static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int n
     a.pdl_trig = m->sk_pdl_trig;
     if (nmat > 1 && a.rows_per % (nw * rpw)) return fail(BGPT_E_UNSUPPORTED, "skinny matmul: %d rows per CTA do not divide %d", nw * rpw, a.rows_per);
     // 8-row tiles: lane = (token, pair of running sums); 4-row tiles (up to 4 rows, or BGPT_SK_TN_PROJ / _QKV = 4): lane = (token, sum)
-    const int cnt = n - tok0, TN = (cnt <= 4 || tn_pref == 4) ? 4 : 8;
+    // tn_pref 0 = automatic: up to 8 rows the 1024..4096-row kernels are latency-bound and 4-row tiles double their warps; beyond,
+    // instruction issue bounds them and the 8-row mapping needs less than half the instructions
+    const int cnt = n - tok0;
+    if (tn_pref == 0) tn_pref = cnt <= 8 ? 4 : 8;
+    const int TN = (cnt <= 4 || tn_pref == 4) ? 4 : 8;
     dim3 grid((a.M + nw * rpw - 1) / (nw * rpw), (cnt + TN - 1) / TN);
     const bool hasm = L.off_m >= 0, is8 = L.type == BG_Q8_0;
     const size_t smem = (size_t) TN * (A.bytes + (TN == 8 ? 64 : 0)) + (size_t) nw * rpw * ((size_t) L.stride + (is8 ? 0 : L.K) + (size_t) (L.K / 32) * 4 * (hasm ? 2 : 1));

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256, 4) k_sk_ln(const __grid_constant__ SkLnAr
 // dynamic smem = TN * (act_bytes + (TN == 8 ? 64 : 0)) + nw * rpw * (stride + (Q8_0 ? 0 : K) + K / 32 * 4 * (1 + has minima))
 // ---------------------------------------------------------------------------------------------
 template <int FMT, int TN>
-__global__ void __launch_bounds__(512, 2) k_sk_mm(const __grid_constant__ SkArgs a) {
+__global__ void __launch_bounds__(1024, 1) k_sk_mm(const __grid_constant__ SkArgs a) {       // 64 registers: 2 x 512 or 4 x 256 threads per SM as well
     constexpr bool IS8    = (FMT == BG_Q8_0);
     constexpr bool HASQH  = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
     constexpr bool HASM   = (FMT == BG_Q4_1 || FMT == BG_Q5_1);

@@ -16,10 +16,10 @@ alltests)
   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"
   tail -20 $OUT/pytest_gpu.log ;;
 perf)
-  for v in "X=0" "BGPT_SK_TN_PROJ=4" "BGPT_SK_TN_PROJ=4 BGPT_SK_TN_QKV=4" "BGPT_SK_FC1_NW=8" "BGPT_SK_PDL_TRIG=1" "BGPT_PDL=0"; do
+  for v in "X=0" "BGPT_SK_FC1_NW=32" "BGPT_SK_TN_PROJ=8" "BGPT_SK_TN_PROJ=8 BGPT_SK_FC1_NW=32" "X=1"; do
     echo "== variant: ${v:-default}"
     env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64
-    env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 1
+    env $v timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 3
     env $v timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8
   done > $OUT/perf.log 2>&1
   cat $OUT/perf.log ;;
