@@ -31,6 +31,9 @@ skips)
     env $v BGPT_SK_SKIP=$k timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 32 --n-past 480 --reps 2
   done; done > $OUT/skips.log 2>&1
   cat $OUT/skips.log ;;
+nograph)
+  BGPT_GRAPH=0 timeout 600 python tools/skinny_check.py --ftypes q4_0,q5_1 > $OUT/check_nograph.log 2>&1; echo "nograph rc=$?"; tail -2 $OUT/check_nograph.log
+  BGPT_PDL=0 timeout 600 python tools/skinny_check.py --ftypes q4_1,q8_0 > $OUT/check_nopdl.log 2>&1; echo "nopdl rc=$?"; tail -2 $OUT/check_nopdl.log ;;
 nstreams)
   for S in 2 4 16 24; do timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 64; timeout 300 python tools/streams_bench.py --ftype q5_1 --streams $S --steps 32 --n-past 480; done > $OUT/nstreams.log 2>&1
   for ft in q4_0 q8_0; do timeout 300 python tools/streams_bench.py --ftype $ft --streams 8 --steps 64; done >> $OUT/nstreams.log 2>&1
