@@ -133,16 +133,18 @@ __global__ void __launch_bounds__(256, 4) k_sk_ln(const __grid_constant__ SkLnAr
 // ---------------------------------------------------------------------------------------------
 // k_sk_mm: y[tok][row] = dot(W[row], record[tok]) + epilogue, one warp per weight row.
 //
-// lane = (tq = lane / 8, l = lane % 8): the lane owns running sum l of token tq (TN = 8: of tokens tq and tq + 4) from
-// the first block of the row to the last -- integer dot (dp4a), conversion, scale product and the fma, in block order;
-// nothing is exchanged between lanes until hsum_float_8 at the end of the row.  The lane's operands of four
-// consecutive blocks are one 16-byte word each, by construction of the layouts in bgpt_layout.h:
-//   weights  [g][j][i]: word j = l % 4 of group g; sums 0..3 take the low nibbles, 4..7 the high ones (Q8_0: word c = l / 4)
-//   records  aq[g][l][i], an[g][l][i] (-offset * sum of the 4 codes), ad[blk], as[blk]
+// 4-row tiles: lane = (tq = lane / 8, l = lane % 8) owns running sum l of token tq.  8-row tiles: lane = (tq = lane / 4,
+// l = lane % 4) owns the PAIR of running sums l and l + 4 of token tq (two chains sharing the scale product).  The lane
+// walks its sums from the first block of the row to the last -- integer dot (dp4a), conversion, scale product and the
+// fma, in block order; nothing is exchanged between lanes until hsum_float_8 at the end of the row.  The lane's operands
+// of four consecutive blocks are one 16-byte word each, by construction of the layouts in bgpt_layout.h:
+//   weights  decoded once per CTA to int8 codes [g][sum][i] (Q8_0 rows already are), scales / minima to f32 [blk]
+//   records  aq[g][sum][i], an[g][sum][i] (-offset * sum of the 4 codes), ad[blk], as[blk]
 // The CTA's weight rows are contiguous in HBM: ONE bulk copy (TMA) brings the whole tile into shared memory, issued
 // before griddepcontrol.wait -- the weights are in flight while the previous kernel of the chain is still running --
-// and one more brings the token records once that kernel has finished.  Lanes of different tokens read the same weight
-// word (broadcast), a token's eight lanes read 128 consecutive bytes of its record: no bank conflicts.
+// and more bring the token records once that kernel has finished.  Lanes of different tokens read the same weight
+// word (broadcast), a token's lanes read consecutive 16-byte words of its record, records of an 8-row tile sit 64 bytes apart
+// modulo the bank period: no bank conflicts.
 // grid = (ceil(M / (nw * rpw)), ceil((n - tok0) / TN)), block = 32 * nw,
 // dynamic smem = TN * (act_bytes + (TN == 8 ? 64 : 0)) + nw * rpw * (stride + (Q8_0 ? 0 : K) + K / 32 * 4 * (1 + has minima))
 // ---------------------------------------------------------------------------------------------
