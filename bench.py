@@ -43,6 +43,25 @@ METRIC = "tokens/sec BioGPT-base Q4_0 decode"
 UNIT = "tokens/s"
 
 
+# stdout carries exactly ONE json line: libraries that print to file descriptor 1 (NCCL's version banner, the reference's
+# loader) are sent to stderr for the whole run, and the line is written to the saved descriptor at the end
+_REAL_STDOUT = None
+
+
+def capture_stdout() -> None:
+    """called first thing in main() (not at import: tools/ import this module for model_path)"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def model_path(ftype: str) -> str:
     """synthetic BioGPT-base `.bin` (written once per machine; ~7 s f32 synth + ~7 s quantise)"""
     os.makedirs(MODEL_DIR, exist_ok=True)
@@ -221,10 +240,11 @@ def run_reference_arm(args):
                        "seq": args.seq, "l2": "weights (194 MB+) exceed any CPU cache"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -379,7 +399,7 @@ def main():
                        "parity": "logits bit-identical to the reference CPU path (tests/test_gpu_eval.py)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "other_configs": extras}
-    print(json.dumps(line), flush=True)
+    emit(line)
     M.close()
     if dist is not None:
         dist.destroy_process_group()
