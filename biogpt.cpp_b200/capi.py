@@ -197,7 +197,7 @@ class Model:
         _check(lib().bgpt_cuda_set_decode_path(self.h, path), "set_decode_path")
 
     def set_batch_path(self, path: int):
-        """1: fused skinny-batch schedule for 2..31 rows where it applies (default), 0: per-operator kernels"""
+        """1: fused skinny-batch schedule for 2..111 rows where it applies (default), 0: per-operator kernels"""
         _check(lib().bgpt_cuda_set_batch_path(self.h, path), "set_batch_path")
 
     def read_buffer(self, which: int, rows: int) -> np.ndarray:

@@ -108,7 +108,8 @@ struct bgpt_model {
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
-    int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
+    int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;
+    int sk_max_rows = 112;                                // measured crossover with the tcgen05 batch matmul path: 96 rows 53.5 vs 61.2 ms, 128 rows 50.9 vs 44.2 ms per 1024 Q8_0 prompt tokens (BGPT_SK_MAX_ROWS)   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -343,6 +344,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_FC1_NW")) { const int v = atoi(getenv("BGPT_SK_FC1_NW")); m->sk_fc1_nw = v == 8 ? 8 : (v == 32 ? 32 : 16); }
     if (getenv("BGPT_SK_SKIP")) m->sk_skip = atoi(getenv("BGPT_SK_SKIP"));
     if (getenv("BGPT_SK_KVPF")) m->sk_kv_prefetch = atoi(getenv("BGPT_SK_KVPF")) != 0;
+    if (getenv("BGPT_SK_MAX_ROWS")) m->sk_max_rows = std::max(2, atoi(getenv("BGPT_SK_MAX_ROWS")));
     RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
@@ -566,7 +568,7 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
 // ------------------------------------------------------------------------------------------
 static bool skinny_ok(const bgpt_model * m, int n) {
     return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff == 4096 &&
-           m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < tc_min_rows();
+           m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < (m->tc_ok && tc_min_rows() < (1 << 30) ? m->sk_max_rows : (1 << 30));
 }
 static void sk_init_attrs() {
     static bool done = false;

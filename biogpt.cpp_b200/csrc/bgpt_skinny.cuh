@@ -1,4 +1,4 @@
-// bgpt_skinny.cuh -- fused schedule for SKINNY batches (2..31 token rows) of the quantised formats
+// bgpt_skinny.cuh -- fused schedule for SKINNY batches (2..111 token rows) of the quantised formats
 // at BioGPT-base layer shapes (d_model 1024, 16 heads of 64, d_ff 4096): the reference's own prompt
 // chunking (n_batch = 8, BASELINE configs[2]) and lock-step streams (8 sequences per GPU, configs[3]).
 //

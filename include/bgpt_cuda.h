@@ -113,7 +113,7 @@ int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int
  * used for n > 1 and for lock-step streams).  All produce identical bits; tests compare them. */
 int bgpt_cuda_set_decode_path(bgpt_model * m, int path);
 int bgpt_cuda_get_decode_path(const bgpt_model * m);
-/* Which schedule evaluates skinny batches (2 <= n < 32 token rows: prompt chunks of the reference's
+/* Which schedule evaluates skinny batches (2 <= n < 112 token rows: prompt chunks of the reference's
  * n_batch = 8 and lock-step streams): 1 = the fused schedule of csrc/bgpt_skinny.cuh (default where
  * it applies: quantised weights at BioGPT-base layer shapes; 5 launches per layer, LayerNorm /
  * quantise / GELU folded into the matmul kernels, programmatic dependent launch), 0 = one kernel

@@ -179,7 +179,7 @@ def test_generation4_kernel_equals_oracle_and_generation3(checkers, capi, zoo, f
 
 @pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftype):
-    """BioGPT-base layer shapes, 2..31 token rows: the fused skinny-batch schedule (csrc/bgpt_skinny.cuh: LayerNorm /
+    """BioGPT-base layer shapes, 2..111 token rows: the fused skinny-batch schedule (csrc/bgpt_skinny.cuh: LayerNorm /
     quantise / GELU folded into warp-per-row matmul kernels, attention with a quantising epilogue, programmatic dependent
     launch).  Un-masked prompt batches of every tile shape (4- and 8-row tiles, two tiles, ragged last tile) at T across
     the 32-wide boundary, both scalar tails, T > 512 and the end of the context must give the oracle's bits and the
@@ -187,8 +187,8 @@ def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftyp
     hp = gf.NARROW
     p = zoo.path("narrow", ftype)
     O = checkers.Oracle(p)
-    M = capi.Model.load(p, max_batch=32)
-    assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(32) == 0, capi.last_error()
+    M = capi.Model.load(p, max_batch=128)
+    assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(111) == 1 and M.batch_path(112) == 0, capi.last_error()
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=55)
     sizes = [8, 8, 5, 2, 3, 4, 7, 16, 9, 1, 8, 31, 8, 6]             # 116 positions: T = 8, 16, 21, 23, 26, 30, 37, 53, 62, 63, 71, 102, ...
     sched, pos = [], 0
@@ -196,7 +196,7 @@ def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftyp
         sched.append((pos, n)); pos += n
     while pos < 500:
         sched.append((pos, 24)); pos += 24                              # 3 tiles of 8
-    for n in (8, 8, 8, 3, 8, 8):
+    for n in (8, 8, 8, 3, 8, 8, 40, 64, 100, 111):                      # many tiles per launch: the range the tensor-core path used to serve
         sched.append((pos, n)); pos += n
     while pos < 1000:
         sched.append((pos, 16)); pos += 16
