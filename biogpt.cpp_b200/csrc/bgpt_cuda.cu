@@ -109,6 +109,8 @@ struct bgpt_model {
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
     int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;
+    int sk_fc1_split = 0;                                 // 1: fc1 as plain 8-row CTAs + k_sk_gq (BGPT_SK_FC1_SPLIT)
+    int sk_tn_fc1 = 0;                                    // 0: follow sk_tn_proj (BGPT_SK_TN_FC1)
     int sk_max_rows = 112;                                // measured crossover with the tcgen05 batch matmul path: 96 rows 53.5 vs 61.2 ms, 128 rows 50.9 vs 44.2 ms per 1024 Q8_0 prompt tokens (BGPT_SK_MAX_ROWS)   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
@@ -344,6 +346,8 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_FC1_NW")) { const int v = atoi(getenv("BGPT_SK_FC1_NW")); m->sk_fc1_nw = v == 8 ? 8 : (v == 32 ? 32 : 16); }
     if (getenv("BGPT_SK_SKIP")) m->sk_skip = atoi(getenv("BGPT_SK_SKIP"));
     if (getenv("BGPT_SK_KVPF")) m->sk_kv_prefetch = atoi(getenv("BGPT_SK_KVPF")) != 0;
+    if (getenv("BGPT_SK_TN_FC1")) { const int v = atoi(getenv("BGPT_SK_TN_FC1")); m->sk_tn_fc1 = v == 8 ? 8 : (v == 4 ? 4 : 0); }
+    if (getenv("BGPT_SK_FC1_SPLIT")) m->sk_fc1_split = atoi(getenv("BGPT_SK_FC1_SPLIT")) != 0;
     if (getenv("BGPT_SK_MAX_ROWS")) m->sk_max_rows = std::max(2, atoi(getenv("BGPT_SK_MAX_ROWS")));
     RET(mega_setup(m));
     m->finalized = true;
@@ -594,6 +598,14 @@ static const void * sk_ln_fn_of(int wtype) {
     }
     return nullptr;
 }
+static const void * sk_gq_fn_of(int wtype) {
+    switch (wtype) {
+        case BG_Q4_0: return (const void *) k_sk_gq<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_gq<BG_Q4_1>;
+        case BG_Q5_0: return (const void *) k_sk_gq<BG_Q5_0>; case BG_Q5_1: return (const void *) k_sk_gq<BG_Q5_1>;
+        case BG_Q8_0: return (const void *) k_sk_gq<BG_Q8_0>;
+    }
+    return nullptr;
+}
 static const void * sk_attn_fn_of(int wtype) {
     switch (wtype) {
         case BG_Q4_0: return (const void *) k_sk_attn<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_attn<BG_Q4_1>;
@@ -691,9 +703,19 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             SkArgs a{};
             const DevTensor * W[3] = { L.fc1_w, nullptr, nullptr };
             RET(sk_ln(m, a, m->x1, L.ln1_w, L.ln1_b, n));
-            a.epi = SK_EPI_GELUQ; a.bias[0] = (const float *) L.fc1_b->ptr; a.gelu = m->gelu_tab;
-            a.act_out = m->act_ff; a.out_bytes = m->A_ff.bytes; a.out_off_n = m->A_ff.off_n; a.out_off_d = m->A_ff.off_d; a.out_off_s = m->A_ff.off_s;
-            if (!(skip & 8)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, m->sk_fc1_nw, 32 / m->sk_fc1_nw, m->sk_tn_proj));
+            a.bias[0] = (const float *) L.fc1_b->ptr;
+            if (m->sk_fc1_split) {                               // BGPT_SK_FC1_SPLIT=1: plain 8-row CTAs + a stand-alone GELU / quantise kernel
+                a.epi = SK_EPI_STORE; a.out = m->hff; a.ld_out = ff;
+                if (!(skip & 8)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, 8, 1, m->sk_tn_qkv));
+                SkGqArgs g{};
+                g.hin = m->hff; g.ld_in = ff; g.gelu = m->gelu_tab; g.act = m->act_ff; g.act_bytes = m->A_ff.bytes;
+                g.off_n = m->A_ff.off_n; g.off_d = m->A_ff.off_d; g.off_s = m->A_ff.off_s; g.code_off = bg_code_offset(wt); g.pdl_trig = m->sk_pdl_trig;
+                if (!(skip & 8)) RET(sk_launch(m, sk_gq_fn_of(wt), dim3(ff / 1024, n), 256, 0, &g));
+            } else {
+                a.epi = SK_EPI_GELUQ; a.gelu = m->gelu_tab;
+                a.act_out = m->act_ff; a.out_bytes = m->A_ff.bytes; a.out_off_n = m->A_ff.off_n; a.out_off_d = m->A_ff.off_d; a.out_off_s = m->A_ff.off_s;
+                if (!(skip & 8)) RET(sk_mm(m, a, W, 1, m->A_d, n, 0, m->sk_fc1_nw, 32 / m->sk_fc1_nw, m->sk_tn_fc1 ? m->sk_tn_fc1 : m->sk_tn_proj));
+            }
         }
         {   // fc2 + bias + residual                                 biogpt.cpp:790-795
             SkArgs a{};

@@ -130,6 +130,26 @@ __global__ void __launch_bounds__(256, 4) k_sk_ln(const __grid_constant__ SkLnAr
     sk_quant_block<FMT>(y, tid >> 3, tid & 7, a.act + (size_t) row * a.act_bytes, a.off_n, a.off_d, a.off_s, a.code_off, true);
 }
 
+// ---- stand-alone GELU + quantise of fc1's output (alternative to the quantising epilogue of k_sk_mm, BGPT_SK_FC1_SPLIT=1):
+// grid = (d_ff / 1024, rows), block = 256; thread t: elements 4t..4t+3 of the 1024-wide slice = block t/8, word t%8
+struct SkGqArgs {
+    const float * hin; int ld_in; const uint16_t * gelu;
+    uint8_t * act; int act_bytes, off_n, off_d, off_s, code_off;
+    int pdl_trig;
+};
+template <int FMT>
+__global__ void __launch_bounds__(256, 4) k_sk_gq(const __grid_constant__ SkGqArgs a) {
+    const int tid = threadIdx.x, row = blockIdx.y;
+    if (a.pdl_trig == 0) sk_pdl_launch_dependents();
+    sk_pdl_wait();
+    const float4 v = __ldcg((const float4 *) (a.hin + (size_t) row * a.ld_in + blockIdx.x * 1024) + tid);
+    float4 y;
+    y.x = bg_h2f(a.gelu[bg_f2h(v.x)]); y.y = bg_h2f(a.gelu[bg_f2h(v.y)]);
+    y.z = bg_h2f(a.gelu[bg_f2h(v.z)]); y.w = bg_h2f(a.gelu[bg_f2h(v.w)]);
+    if (a.pdl_trig == 1) sk_pdl_launch_dependents();
+    sk_quant_block<FMT>(y, blockIdx.x * 32 + (tid >> 3), tid & 7, a.act + (size_t) row * a.act_bytes, a.off_n, a.off_d, a.off_s, a.code_off, true);
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_sk_mm: y[tok][row] = dot(W[row], record[tok]) + epilogue, one warp per weight row.
 //
