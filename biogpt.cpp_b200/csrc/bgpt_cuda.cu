@@ -109,7 +109,7 @@ struct bgpt_model {
     int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
     int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;
-    int sk_fc1_split = 0;                                 // 1: fc1 as plain 8-row CTAs + k_sk_gq (BGPT_SK_FC1_SPLIT)
+    int sk_fc1_split = 1;                                 // 1: fc1 as plain 8-row CTAs + k_sk_gq (8 Q5_1 streams 979 -> 943 us per step, prompt unchanged), 0: quantising epilogue (BGPT_SK_FC1_SPLIT)
     int sk_tn_fc1 = 0;                                    // 0: follow sk_tn_proj (BGPT_SK_TN_FC1)
     int sk_max_rows = 112;                                // measured crossover with the tcgen05 batch matmul path: 96 rows 53.5 vs 61.2 ms, 128 rows 50.9 vs 44.2 ms per 1024 Q8_0 prompt tokens (BGPT_SK_MAX_ROWS)   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;

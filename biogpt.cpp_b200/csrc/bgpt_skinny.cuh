@@ -4,7 +4,7 @@
 //
 // The per-operator schedule (bgpt_kernels.cuh) spends 9 launches per layer, its GEMV keeps 4 threads
 // on a row walking K with dependent loads, and its LayerNorm / quantise kernels run on 8 CTAs: 10-17 us
-// per kernel, 2.8 ms per 8-row step.  Here a layer is 7 launches, every one of them wide:
+// per kernel, 2.8 ms per 8-row step.  Here a layer is 8 launches, every one of them wide:
 //
 //   k_sk_ln        : LayerNorm0 + quantise, one token row per CTA                   (rows CTAs)
 //   k_sk_mm  qkv   : 3072 stacked rows, one warp per weight row, 8 token rows per warp; epilogue bias,
@@ -14,8 +14,10 @@
 //                    leave as two quantised blocks of out_proj's activation record  (16 x rows CTAs)
 //   k_sk_mm  o     : 4-row token tiles; bias + residual                             (128 x 2 CTAs)
 //   k_sk_ln        : LayerNorm1 + quantise
-//   k_sk_mm  fc1   : 32 consecutive rows per CTA (16 warps x 2) = one block of fc2's input; bias +
-//                    fp16-table GELU (one batch of look-ups) + quantise in the epilogue (128 x 2 CTAs)
+//   k_sk_mm  fc1   : 4096 rows, 8-row tiles; bias -> f32                              (512 CTAs)
+//   k_sk_gq        : fp16-table GELU + quantise -> fc2's activation record            (4 x rows CTAs)
+//                    (BGPT_SK_FC1_SPLIT=0: 32 consecutive rows per CTA = one block of fc2's input, GELU +
+//                    quantise in the matmul's epilogue instead)
 //   k_sk_mm  fc2   : K = 4096; bias + residual                                      (128 x 2 CTAs)
 //   k_sk_ln + k_sk_mm lm_head (lock-step streams: every row has logits)              (1325 CTAs)
 //
