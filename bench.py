@@ -221,6 +221,66 @@ def side_configs(capi, device: int, seq: int):
     return out
 
 
+def run_streams_workload(args, capi, dist, barrier, rank, local_rank, world):
+    """BASELINE.json configs[3]: S independent Q5_1 sequences per GPU decoded in lock step (every weight read serves the S rows; each
+    stream has its own F32 KV cache), the model replicated on every rank, no collective on the data path.  One step = one pass over
+    the context (seq tokens per stream).  value = all ranks' tokens / max-over-ranks device time (CUDA events inside each call)."""
+    ftype = "q5_1" if args.ftype == "q4_0" else args.ftype          # the config names Q5_1; --ftype overrides
+    S, seq = args.streams, args.seq
+    if rank == 0:
+        model_path(ftype)
+    if dist is not None:
+        dist.barrier()
+    M = capi.Model.load(model_path(ftype), device=local_rank, max_batch=S)
+    M.set_streams(S)
+    first = gf.synth_tokens(S, gf.BASE.n_vocab, seed=9 + rank).astype(np.int32)
+
+    def one_pass():
+        cur = first.copy(); ms = 0.0
+        for p in range(seq):
+            logits = M.eval_streams(cur, p)
+            ms += M.last_eval_ms
+            cur = np.argmax(logits, axis=1).astype(np.int32)
+        return ms
+    for _ in range(max(1, args.warmup)):
+        one_pass()
+    sampler = ClockSampler(local_rank).start()
+    barrier()
+    l0 = M.launch_count
+    t0 = time.perf_counter()
+    ms_total = sum(one_pass() for _ in range(args.steps))
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = (M.launch_count - l0) / args.steps
+    clocks = sampler.stop()
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_total, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, wall = float(t[0].item()), float(t[1].item())
+    M.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    nbytes = sum(bytes_per_token(ftype, p) + (S - 1) * (196_608 * (p + 1) + 196_608 + 169_536 + 2 * 768) for p in range(seq))
+    step_ms = ms_total / args.steps
+    achieved = nbytes / (step_ms / 1e3) / 1e9
+    emit({"metric": "tokens/sec BioGPT-base Q5_1 decode, lock-step streams", "value": world * S * seq * args.steps / (ms_total / 1e3), "unit": UNIT,
+          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "int8*int8->f32 (Q8_1 activations), f32 KV", "data": "synthetic",
+          "config": {"workload": f"BioGPT-base {ftype}, {S} lock-step streams per GPU x {world} GPUs, seq 1->{seq} (BASELINE.json configs[3])",
+                     "ftype": ftype, "seq": seq, "streams_per_gpu": S, "parallelism": f"replicas x{world}",
+                     "l2": "inputs larger than L2: every step streams the full weight set and S KV caches"},
+          "clocks": clocks,
+          "e2e": {"value": world * S * seq * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": seq * (4 * S + 16), "d2h_bytes_per_step": seq * S * 42384 * 4},
+          "gpu_launches": launches,
+          "roofline": {"bound": "hbm", "kernel": "fused skinny-batch schedule (k_sk_mm / k_sk_attn / k_sk_ln / k_sk_gq), per GPU", "achieved": achieved,
+                       "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None},
+          "cpu_baseline": None})
+
+
 def run_reference_arm(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -255,6 +315,10 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="decode", choices=["decode", "streams"],
+                    help="decode: BASELINE configs[1] (the headline, default); streams: configs[3] -- `--streams` lock-step Q5_1 sequences per GPU, "
+                         "replicated over the ranks (64 streams on 8 GPUs)")
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE.json configs[2] / configs[3] side measurements")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -281,16 +345,20 @@ def main():
         if rank == 0:
             model_path(args.ftype)
         dist.barrier()
-    path = model_path(args.ftype)
-    M = capi.Model.load(path, device=local_rank, max_batch=8)
-    seq = args.seq
-    first_token = 2
-
     def barrier():
         if dist is not None:
             import torch
             torch.cuda.synchronize()
             dist.barrier()
+
+    if args.workload == "streams":
+        run_streams_workload(args, capi, dist, barrier, rank, local_rank, world)
+        return
+
+    path = model_path(args.ftype)
+    M = capi.Model.load(path, device=local_rank, max_batch=8)
+    seq = args.seq
+    first_token = 2
 
     # ---- warm-up
     for _ in range(args.warmup):
