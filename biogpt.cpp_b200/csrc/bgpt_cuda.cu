@@ -11,6 +11,9 @@
 //                                                           biogpt.cpp:688-796
 //   act(LN) -> gemv(lm_head) on the last row only           biogpt.cpp:798-803, 844
 //
+// Quantised models at BioGPT-base layer shapes do not use that schedule for the common cases: single-token steps run on one
+// persistent kernel (bgpt_mega4.cuh / bgpt_mega.cuh), 2..111-row evals on the fused skinny-batch schedule (bgpt_skinny.cuh).
+//
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
 #include "../../include/bgpt_cuda.h"
 #include "bgpt_kernels.cuh"
@@ -568,7 +571,7 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
 
 
 // ------------------------------------------------------------------------------------------
-// fused skinny-batch schedule (bgpt_skinny.cuh): 5 launches per layer, programmatic dependent launch
+// fused skinny-batch schedule (bgpt_skinny.cuh): 8 wide launches per layer chained by programmatic dependent launch
 // ------------------------------------------------------------------------------------------
 static bool skinny_ok(const bgpt_model * m, int n) {
     return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff == 4096 &&
