@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_barrier_bench", "bgpt_cuda_debug_icache_bench", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_debug_quantize_bench", "bgpt_cuda_debug_gemm_bench", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -83,10 +83,7 @@ def lib():
     L.bgpt_cuda_debug_read_prof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bgpt_cuda_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bgpt_cuda_op_quantize_weights.argtypes = [C.c_int, _f32p, C.c_longlong, _u8p]
-    L.bgpt_cuda_debug_quantize_bench.argtypes = [C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_float)]
-    L.bgpt_cuda_debug_icache_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
-    L.bgpt_cuda_debug_barrier_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
-    L.bgpt_cuda_debug_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.bgpt_cuda_get_eval_path.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
     L.bgpt_cuda_hparams.restype = None
@@ -107,6 +104,27 @@ def lib():
     L.bgpt_cuda_op_dequantize.argtypes = [C.c_int, _u8p, _f32p, C.c_int, C.c_int]
     _lib = L
     return L
+
+
+_tools = None
+
+
+def tools_lib():
+    """libbgpt_cuda_tools.so (`make -C biogpt.cpp_b200/csrc tools`): the design micro-benchmarks of
+    include/bgpt_cuda_tools.h.  Not part of the product library; only tools/*_bench.py load it."""
+    global _tools
+    if _tools is None:
+        p = os.path.join(HERE, "csrc", "libbgpt_cuda_tools.so")
+        if not os.path.exists(p):
+            raise BgptError(f"{p} is missing: build it with `make -C biogpt.cpp_b200/csrc tools`")
+        T = C.CDLL(p)
+        T.bgpt_cuda_last_error.restype = C.c_char_p
+        T.bgpt_cuda_debug_quantize_bench.argtypes = [C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_float)]
+        T.bgpt_cuda_debug_icache_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        T.bgpt_cuda_debug_barrier_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        T.bgpt_cuda_debug_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        _tools = T
+    return _tools
 
 
 def _check(rc: int, what: str):
@@ -211,6 +229,11 @@ class Model:
     def batch_path(self, n_rows: int) -> int:
         return int(lib().bgpt_cuda_get_batch_path(self.h, n_rows))
 
+    def eval_path(self, n_rows: int) -> int:
+        """3 persistent decode kernel, 1 fused skinny-batch schedule, 0 per-operator exact SIMT, 2 per-operator with the
+        tcgen05 matmul (the only one that is tolerance-close instead of bit-identical)"""
+        return int(lib().bgpt_cuda_get_eval_path(self.h, n_rows))
+
     @property
     def decode_path(self) -> int:
         return int(lib().bgpt_cuda_get_decode_path(self.h))
@@ -302,7 +325,8 @@ def op_quantize_weights(ggml_type: int, x: np.ndarray) -> np.ndarray:
 def quantize_bench(ggml_type: int, n: int, iters: int = 10) -> float:
     """microseconds per launch of the device quantiser over n weights (device-resident)"""
     us = C.c_float(0)
-    _check(lib().bgpt_cuda_debug_quantize_bench(ggml_type, n, iters, C.byref(us)), "quantize_bench")
+    if tools_lib().bgpt_cuda_debug_quantize_bench(ggml_type, n, iters, C.byref(us)) != 0:
+        raise BgptError("quantize_bench: " + tools_lib().bgpt_cuda_last_error().decode())
     return float(us.value)
 
 

@@ -16,13 +16,19 @@
 //
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
 #include "../../include/bgpt_cuda.h"
+#ifdef BGPT_BENCH_TOOLS
+#include "../../include/bgpt_cuda_tools.h"
+#endif
 #include "bgpt_kernels.cuh"
 #include "bgpt_mega.cuh"
 #include "bgpt_mega4.cuh"
-#include "bgpt_barbench.cuh"
+#ifdef BGPT_BENCH_TOOLS
+#include "bgpt_barbench.cuh"      // micro-benchmarks: only in libbgpt_cuda_tools.so (make tools), never in the product library
+#endif
 #include "bgpt_tc.cuh"
 #include "bgpt_quant.cuh"
 #include "bgpt_skinny.cuh"
+#include "bgpt_tu.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -85,7 +91,7 @@ struct bgpt_model {
     DevState * st = nullptr;
     // arena for `cap` token rows
     int cap = 0;
-    int * d_tokens = nullptr; int * d_idlog = nullptr; int idlog_cap = 0;
+    int * d_tokens = nullptr; int * d_idlog = nullptr; int * h_idlog = nullptr; int idlog_cap = 0;   // h_idlog: pinned, idlog_cap ints
     float *x = nullptr, *x1 = nullptr, *q = nullptr, *att = nullptr, *hff = nullptr, *logits = nullptr;
     uint8_t *act_d = nullptr, *act_ff = nullptr;
     ActLayout A_d{}, A_ff{};
@@ -208,6 +214,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
     cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch); cudaFree(m->d_trace);
     if (m->h_st) cudaFreeHost(m->h_st);
+    if (m->h_idlog) cudaFreeHost(m->h_idlog);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -297,10 +304,17 @@ static DevTensor * find(bgpt_model * m, const std::string & n) {
 template <typename K> static void allow_big_smem(K kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
+// cudaFuncSetAttribute is per device (context): remember which devices have been initialised, not "done once per process"
+static bool first_use_on_current_device(unsigned long long & mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    if (mask & (1ULL << dev)) return false;
+    mask |= 1ULL << dev;
+    return true;
+}
 static void init_kernel_attrs() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static unsigned long long done = 0;
+    if (!first_use_on_current_device(done)) return;
 #define ATTR_Q(F) allow_big_smem(k_gemv_q<F, 1>); allow_big_smem(k_gemv_q<F, 2>); allow_big_smem(k_gemv_q<F, 4>); allow_big_smem(k_gemv_q<F, 8>);
 #define ATTR_F(F) allow_big_smem(k_gemv_f<F, 1>); allow_big_smem(k_gemv_f<F, 2>); allow_big_smem(k_gemv_f<F, 4>); allow_big_smem(k_gemv_f<F, 8>);
     ATTR_Q(BG_Q4_0) ATTR_Q(BG_Q4_1) ATTR_Q(BG_Q5_0) ATTR_Q(BG_Q5_1) ATTR_Q(BG_Q8_0) ATTR_F(BG_F16) ATTR_F(BG_F32)
@@ -433,21 +447,16 @@ static int tc_min_rows() {
     static int v = -1;
     if (v < 0) {
         const char * e = getenv("BGPT_TC"); const char * r = getenv("BGPT_TC_MIN_ROWS");
-        v = (e && atoi(e) == 0) ? (1 << 30) : (r ? std::max(1, atoi(r)) : 32);
+        v = (e && atoi(e) == 0) ? (1 << 30) : (r ? std::max(1, atoi(r)) : 112);   // every smaller batch stays on the exact-order kernels, whatever the model shape
     }
     return v;
 }
 static size_t tc_smem_bytes() { return std::max(sizeof(TcShared) + 128, (size_t) 120 * 1024); }   // >= half the SM: one CTA (512 TMEM columns) per SM
 static void tc_init_attrs() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static unsigned long long done = 0;
+    if (!first_use_on_current_device(done)) return;
     const int sm = (int) tc_smem_bytes();
-    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q4_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q5_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q5_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(k_gemm_tc_q<BG_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    for (int t : { BG_Q4_0, BG_Q4_1, BG_Q5_0, BG_Q5_1, BG_Q8_0 }) cudaFuncSetAttribute(bgpt_k_gemm_tc_fn(t), cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaGetLastError();
 }
 static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
@@ -462,14 +471,10 @@ static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * cons
     a.n = n; a.tok0 = tok0; a.epi = epi;
     dim3 grid((a.M + TC_ROWS - 1) / TC_ROWS, (n - tok0 + TC_TOK - 1) / TC_TOK);
     const size_t smem = tc_smem_bytes();
-    switch (L.type) {
-        case BG_Q4_0: k_gemm_tc_q<BG_Q4_0><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case BG_Q4_1: k_gemm_tc_q<BG_Q4_1><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case BG_Q5_0: k_gemm_tc_q<BG_Q5_0><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case BG_Q5_1: k_gemm_tc_q<BG_Q5_1><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case BG_Q8_0: k_gemm_tc_q<BG_Q8_0><<<grid, TC_THREADS, smem, s>>>(a); break;
-        default: return fail(BGPT_E_UNSUPPORTED, "tensor-core matmul: type %d", L.type);
-    }
+    const void * fn = bgpt_k_gemm_tc_fn(L.type);
+    if (!fn) return fail(BGPT_E_UNSUPPORTED, "tensor-core matmul: type %d", L.type);
+    void * args[] = { &a };
+    CK(cudaLaunchKernel(fn, grid, dim3(TC_THREADS), args, smem, s));
     if (m) m->launches++;
     CK(cudaGetLastError());
     return BGPT_OK;
@@ -578,44 +583,11 @@ static bool skinny_ok(const bgpt_model * m, int n) {
            m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < (m->tc_ok && tc_min_rows() < (1 << 30) ? m->sk_max_rows : (1 << 30));
 }
 static void sk_init_attrs() {
-    static bool done = false;
-    if (done) return;
-    done = true;
-#define ATTR_SK(F) allow_big_smem(k_sk_mm<F, 4>); allow_big_smem(k_sk_mm<F, 8>);
-    ATTR_SK(BG_Q4_0) ATTR_SK(BG_Q4_1) ATTR_SK(BG_Q5_0) ATTR_SK(BG_Q5_1) ATTR_SK(BG_Q8_0)
+    static unsigned long long done = 0;
+    if (!first_use_on_current_device(done)) return;
+    for (int t : { BG_Q4_0, BG_Q4_1, BG_Q5_0, BG_Q5_1, BG_Q8_0 }) for (int tn : { 4, 8 })
+        cudaFuncSetAttribute(bgpt_k_sk_mm_fn(t, tn), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaGetLastError();
-}
-template <int FMT> static const void * sk_mm_fn(int TN) { return TN == 4 ? (const void *) k_sk_mm<FMT, 4> : (const void *) k_sk_mm<FMT, 8>; }
-static const void * sk_mm_fn_of(int wtype, int TN) {
-    switch (wtype) {
-        case BG_Q4_0: return sk_mm_fn<BG_Q4_0>(TN); case BG_Q4_1: return sk_mm_fn<BG_Q4_1>(TN); case BG_Q5_0: return sk_mm_fn<BG_Q5_0>(TN);
-        case BG_Q5_1: return sk_mm_fn<BG_Q5_1>(TN); case BG_Q8_0: return sk_mm_fn<BG_Q8_0>(TN);
-    }
-    return nullptr;
-}
-static const void * sk_ln_fn_of(int wtype) {
-    switch (wtype) {
-        case BG_Q4_0: return (const void *) k_sk_ln<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_ln<BG_Q4_1>;
-        case BG_Q5_0: return (const void *) k_sk_ln<BG_Q5_0>; case BG_Q5_1: return (const void *) k_sk_ln<BG_Q5_1>;
-        case BG_Q8_0: return (const void *) k_sk_ln<BG_Q8_0>;
-    }
-    return nullptr;
-}
-static const void * sk_gq_fn_of(int wtype) {
-    switch (wtype) {
-        case BG_Q4_0: return (const void *) k_sk_gq<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_gq<BG_Q4_1>;
-        case BG_Q5_0: return (const void *) k_sk_gq<BG_Q5_0>; case BG_Q5_1: return (const void *) k_sk_gq<BG_Q5_1>;
-        case BG_Q8_0: return (const void *) k_sk_gq<BG_Q8_0>;
-    }
-    return nullptr;
-}
-static const void * sk_attn_fn_of(int wtype) {
-    switch (wtype) {
-        case BG_Q4_0: return (const void *) k_sk_attn<BG_Q4_0>; case BG_Q4_1: return (const void *) k_sk_attn<BG_Q4_1>;
-        case BG_Q5_0: return (const void *) k_sk_attn<BG_Q5_0>; case BG_Q5_1: return (const void *) k_sk_attn<BG_Q5_1>;
-        case BG_Q8_0: return (const void *) k_sk_attn<BG_Q8_0>;
-    }
-    return nullptr;
 }
 // launch with the programmatic-stream-serialisation attribute: the kernel may start while its predecessor in the stream is
 // still running and blocks at griddepcontrol.wait (everything before that point touches weights only)
@@ -650,7 +622,7 @@ static int sk_mm(bgpt_model * m, SkArgs & a, const DevTensor * const W[3], int n
     dim3 grid((a.M + nw * rpw - 1) / (nw * rpw), (cnt + TN - 1) / TN);
     const bool hasm = L.off_m >= 0, is8 = L.type == BG_Q8_0;
     const size_t smem = (size_t) TN * (A.bytes + (TN == 8 ? 64 : 0)) + (size_t) nw * rpw * ((size_t) L.stride + (is8 ? 0 : L.K) + (size_t) (L.K / 32) * 4 * (hasm ? 2 : 1));
-    return sk_launch(m, sk_mm_fn_of(m->wtype, TN), grid, nw * 32, smem, &a);
+    return sk_launch(m, bgpt_k_sk_mm_fn(m->wtype, TN), grid, nw * 32, smem, &a);
 }
 
 // LayerNorm + quantise of n rows into the d_model-wide activation records (k_sk_ln)
@@ -661,7 +633,7 @@ static int sk_ln(bgpt_model * m, SkArgs & a, const float * x, const DevTensor * 
     l.xin = x; l.ld_in = m->d_model; l.lnw = (const float *) w->ptr; l.lnb = (const float *) b->ptr; l.eps = 1e-5f;   // NORM_EPS, biogpt.cpp:24
     l.act = m->act_d; l.act_bytes = m->A_d.bytes; l.off_n = m->A_d.off_n; l.off_d = m->A_d.off_d; l.off_s = m->A_d.off_s;
     l.code_off = bg_code_offset(m->wtype); l.pdl_trig = m->sk_pdl_trig;
-    return sk_launch(m, sk_ln_fn_of(m->wtype), dim3(n), 256, 0, &l);
+    return sk_launch(m, bgpt_k_sk_ln_fn(m->wtype), dim3(n), 256, 0, &l);
 }
 
 static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, int mode) {
@@ -693,7 +665,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
             a.q = m->q; a.ld_q = d; a.kcache = kc; a.vcache = vc; a.stream_stride = m->stream_stride;
             a.act = m->act_d; a.act_bytes = m->A_d.bytes; a.off_n = m->A_d.off_n; a.off_d = m->A_d.off_d; a.off_s = m->A_d.off_s;
             a.code_off = bg_code_offset(wt); a.n = n; a.mode = mode; a.st = m->st; a.exp_tab = m->exp_tab;
-            if (!(skip & 2)) RET(sk_launch(m, sk_attn_fn_of(wt), dim3(m->n_head, n), SK_ANT, 0, &a));
+            if (!(skip & 2)) RET(sk_launch(m, bgpt_k_sk_attn_fn(wt), dim3(m->n_head, n), SK_ANT, 0, &a));
         }
         {   // out_proj + bias + residual                            biogpt.cpp:767-772
             SkArgs a{};
@@ -713,7 +685,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
                 SkGqArgs g{};
                 g.hin = m->hff; g.ld_in = ff; g.gelu = m->gelu_tab; g.act = m->act_ff; g.act_bytes = m->A_ff.bytes;
                 g.off_n = m->A_ff.off_n; g.off_d = m->A_ff.off_d; g.off_s = m->A_ff.off_s; g.code_off = bg_code_offset(wt); g.pdl_trig = m->sk_pdl_trig;
-                if (!(skip & 8)) RET(sk_launch(m, sk_gq_fn_of(wt), dim3(ff / 1024, n), 256, 0, &g));
+                if (!(skip & 8)) RET(sk_launch(m, bgpt_k_sk_gq_fn(wt), dim3(ff / 1024, n), 256, 0, &g));
             } else {
                 a.epi = SK_EPI_GELUQ; a.gelu = m->gelu_tab;
                 a.act_out = m->act_ff; a.out_bytes = m->A_ff.bytes; a.out_off_n = m->A_ff.off_n; a.out_off_d = m->A_ff.off_d; a.out_off_s = m->A_ff.off_s;
@@ -811,33 +783,24 @@ extern "C" long long bgpt_cuda_debug_read_buffer(bgpt_model * m, int which, int 
     return (long long) bytes;
 }
 extern "C" int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows) { return m && skinny_ok(m, n_rows) ? 1 : 0; }
+static bool use_mega(const bgpt_model * m);
+// which schedule an eval of n_rows token rows takes: 3 persistent decode kernel, 1 fused skinny-batch schedule (exact), 2 per-operator
+// schedule with the tcgen05 matmul (tolerance-close), 0 per-operator schedule with the exact-order SIMT matmul
+extern "C" int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows) {
+    if (!m || n_rows < 1) return -1;
+    if (n_rows == 1 && use_mega(m)) return 3;
+    if (skinny_ok(m, n_rows)) return 1;
+    if (bg_is_quant(m->wtype) && m->tc_ok && n_rows >= tc_min_rows()) return 2;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // persistent decode kernel: host side
 // ------------------------------------------------------------------------------------------
-template <int FMT> static const void * mega_fn_dk(int dk) {
-    switch (dk) {   // head dims the persistent kernel is instantiated for; others use the per-op kernels
-        case 16:  return (const void *) k_mega<FMT, 16>;
-        case 64:  return (const void *) k_mega<FMT, 64>;
-    }
-    return nullptr;
-}
-static const void * mega_fn(int wtype, int dk) {
-    switch (wtype) {
-        case BG_Q4_0: return mega_fn_dk<BG_Q4_0>(dk);
-        case BG_Q4_1: return mega_fn_dk<BG_Q4_1>(dk);
-        case BG_Q5_0: return mega_fn_dk<BG_Q5_0>(dk);
-        case BG_Q5_1: return mega_fn_dk<BG_Q5_1>(dk);
-        case BG_Q8_0: return mega_fn_dk<BG_Q8_0>(dk);
-        case BG_F16:  return mega_fn_dk<BG_F16>(dk);
-    }
-    return nullptr;   // F32 weights: per-op kernels only
-}
-
 static int mega_setup(bgpt_model * m) {
     m->mega_ok = false;
     const int dk = m->d_model / m->n_head;
-    const void * fn = mega_fn(m->wtype, dk);
+    const void * fn = bgpt_k_mega_fn(m->wtype, dk);
     if (!fn) return BGPT_OK;
     MegaParams & p = m->mp;
     p.d = m->d_model; p.ff = m->d_ff; p.n_head = m->n_head; p.dk = dk; p.n_layer = m->n_layer; p.n_vocab = m->n_vocab;
@@ -915,21 +878,9 @@ static int mega_setup(bgpt_model * m) {
 }
 
 // generation 4: quantised weights at BioGPT-base shapes only (everything else stays on k_mega)
-// prof: the instantiation with clock stamps (BGPT_MEGA_PROF); the production kernel carries none of that code --
-// the per-layer loop has to stay inside the SM's instruction cache (profiles/README.md)
-static const void * mega4_fn(int wtype, bool prof) {
-    switch (wtype) {
-        case BG_Q4_0: return prof ? (const void *) k_mega4<BG_Q4_0, true> : (const void *) k_mega4<BG_Q4_0, false>;
-        case BG_Q4_1: return prof ? (const void *) k_mega4<BG_Q4_1, true> : (const void *) k_mega4<BG_Q4_1, false>;
-        case BG_Q5_0: return prof ? (const void *) k_mega4<BG_Q5_0, true> : (const void *) k_mega4<BG_Q5_0, false>;
-        case BG_Q5_1: return prof ? (const void *) k_mega4<BG_Q5_1, true> : (const void *) k_mega4<BG_Q5_1, false>;
-        case BG_Q8_0: return prof ? (const void *) k_mega4<BG_Q8_0, true> : (const void *) k_mega4<BG_Q8_0, false>;
-    }
-    return nullptr;
-}
 static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     m->mega4_ok = false;
-    const void * fn = mega4_fn(m->wtype, m->d_prof != nullptr);
+    const void * fn = bgpt_k_mega4_fn(m->wtype, m->d_prof != nullptr);
     const int nC = m->mega_grid;
     static_assert(sizeof(M4Params) <= 4096, "M4Params must fit the 4 KB kernel parameter space");
     if (!fn || m->n_layer > M4_MAXL || m->d_model != M4_D || m->d_ff != M4_FF || m->n_head != M4_NH || m->n_positions > 1024 || nC < M4_NB_F) return BGPT_OK;
@@ -995,7 +946,7 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
         if (++m->m4_tag >= (1u << 26)) m->m4_tag = 1;        // 0 is the "never written" tag of a fresh buffer
         P.tag = m->m4_tag << 6;
         void * args[] = { &P };
-        CK(cudaLaunchCooperativeKernel(mega4_fn(m->wtype, m->d_trace != nullptr), dim3(m->mega_grid), dim3(M4_NT), args, (size_t) P.sm_total, m->stream));
+        CK(cudaLaunchCooperativeKernel(bgpt_k_mega4_fn(m->wtype, m->d_trace != nullptr), dim3(m->mega_grid), dim3(M4_NT), args, (size_t) P.sm_total, m->stream));
         m->launches++;
         return BGPT_OK;
     }
@@ -1006,7 +957,7 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
     p.epoch0 = m->bar_epoch;
     m->bar_epoch += (unsigned long long) 5 * m->n_layer * m->mega_grid;
     void * args[] = { &p };
-    const void * fn = mega_fn(m->wtype, m->d_model / m->n_head);
+    const void * fn = bgpt_k_mega_fn(m->wtype, m->d_model / m->n_head);
     CK(cudaLaunchCooperativeKernel(fn, dim3(m->mega_grid), dim3(MEGA_NT), args, (size_t) p.sm_total, m->stream));
     m->launches++;
     return BGPT_OK;
@@ -1125,7 +1076,10 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
     cudaStream_t s = m->stream;
     if (n_steps > m->idlog_cap) {
         cudaFree(m->d_idlog); m->d_idlog = nullptr;
+        if (m->h_idlog) cudaFreeHost(m->h_idlog);
+        m->h_idlog = nullptr; m->idlog_cap = 0;
         CK(cudaMalloc(&m->d_idlog, (size_t) n_steps * sizeof(int)));
+        CK(cudaMallocHost(&m->h_idlog, (size_t) n_steps * sizeof(int)));
         m->idlog_cap = n_steps;
     }
     CK(cudaStreamSynchronize(s));
@@ -1136,7 +1090,11 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
     CK(cudaEventRecord(m->ev0, s));
     if (use_mega(m)) {
         for (int i = 0; i < n_steps; i++) RET(launch_mega(m, m->d_tokens, i > 0, n_past + i, i - 1));
-        k_mega_pick<<<1, 32, 0, s>>>(m->d_cand_val, m->d_cand_idx, m->mega_grid, m->d_idlog, n_steps - 1, m->d_tokens);
+        {
+            int slot = n_steps - 1, n_cand = m->mega_grid;
+            void * pargs[] = { &m->d_cand_val, &m->d_cand_idx, &n_cand, &m->d_idlog, &slot, &m->d_tokens };
+            CK(cudaLaunchKernel(bgpt_k_mega_pick_fn(), dim3(1), dim3(32), pargs, 0, s));
+        }
         m->launches++;
         CK(cudaGetLastError());
     } else {
@@ -1148,10 +1106,10 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
         }
     }
     CK(cudaEventRecord(m->ev1, s));
-    CK(cudaMemcpyAsync(m->h_logits, m->d_idlog, (size_t) n_steps * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(m->h_idlog, m->d_idlog, (size_t) n_steps * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
-    memcpy(ids_out, m->h_logits, (size_t) n_steps * sizeof(int));
+    memcpy(ids_out, m->h_idlog, (size_t) n_steps * sizeof(int));
     if (ms_out) *ms_out = m->last_ms;
     return BGPT_OK;
 }
@@ -1302,6 +1260,7 @@ extern "C" int bgpt_cuda_op_dequantize(int type, const void * w, float * y, int 
     return BGPT_OK;
 }
 
+#ifdef BGPT_BENCH_TOOLS
 // debug: microseconds per grid barrier for variant `v` (bgpt_barbench.cuh); with_load adds one
 // dependent L2 load after each barrier
 extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, float * us_per_barrier) {
@@ -1341,6 +1300,8 @@ extern "C" int bgpt_cuda_debug_barrier_bench(int v, int iters, int with_load, fl
     return BGPT_OK;
 }
 
+#endif  // BGPT_BENCH_TOOLS
+
 // ---- device weight quantiser (bgpt_quant.cuh): f32 -> Qx file blocks, the reference's quantize_row_q*_reference bits
 static int launch_quantize(int type, const float * d_x, long long nblocks, uint8_t * d_out, cudaStream_t s) {
     static int n_sm = 0;
@@ -1370,6 +1331,7 @@ extern "C" int bgpt_cuda_op_quantize_weights(int type, const float * x, long lon
     CK(cudaMemcpy(out, dout.p, ob, cudaMemcpyDeviceToHost));
     return BGPT_OK;
 }
+#ifdef BGPT_BENCH_TOOLS
 // debug: device-resident timing of the quantiser over n synthetic weights; us_out = microseconds per launch (best of 5)
 extern "C" int bgpt_cuda_debug_quantize_bench(int type, long long n, int iters, float * us_out) {
     RET(need_device());
@@ -1422,6 +1384,8 @@ extern "C" int bgpt_cuda_debug_icache_bench(int kb, int iters, int nwarps, float
     return BGPT_OK;
 }
 
+#endif  // BGPT_BENCH_TOOLS
+
 // y = W . x through the tcgen05 path regardless of n (parity tests; quantised types only)
 extern "C" int bgpt_cuda_op_mul_mat_tc(int type, const void * w, const float * x, float * y, int k, int rows, int n) {
     RET(need_device());
@@ -1443,6 +1407,7 @@ extern "C" int bgpt_cuda_op_mul_mat_tc(int type, const void * w, const float * x
     return BGPT_OK;
 }
 
+#ifdef BGPT_BENCH_TOOLS
 // debug: device time of `iters` back-to-back matmuls y[n][rows] = W[rows][k] . x[n][k] on synthetic
 // data; path 0 = exact-order SIMT kernels, 1 = tcgen05.  ms_out = milliseconds per matmul.
 extern "C" int bgpt_cuda_debug_gemm_bench(int type, int k, int rows, int n, int iters, int path, float * ms_out) {
@@ -1484,3 +1449,4 @@ extern "C" int bgpt_cuda_debug_gemm_bench(int type, int k, int rows, int n, int 
     *ms_out = ms / iters;
     return BGPT_OK;
 }
+#endif  // BGPT_BENCH_TOOLS

@@ -94,7 +94,7 @@ __device__ __forceinline__ float bg_dequant_elem(int type, const uint8_t * row, 
     }
 }
 
-__global__ void k_embed(const uint8_t * __restrict__ tokW, const uint8_t * __restrict__ posW, int type,
+static __global__ void k_embed(const uint8_t * __restrict__ tokW, const uint8_t * __restrict__ posW, int type,
                         const int * __restrict__ toks, const DevState * __restrict__ st, int mode, int n,
                         int d, int n_vocab, int n_pos_rows, float scale, float * __restrict__ x) {
     const int row = blockIdx.x;
@@ -110,7 +110,7 @@ __global__ void k_embed(const uint8_t * __restrict__ tokW, const uint8_t * __res
     }
 }
 
-__global__ void k_dequant_rows(const uint8_t * __restrict__ W, int type, int K, float * __restrict__ y) {
+static __global__ void k_dequant_rows(const uint8_t * __restrict__ W, int type, int K, float * __restrict__ y) {
     const size_t rb = (size_t) K / (bg_is_quant(type) ? 32 : 1) * (type == BG_F32 ? 4 : type == BG_F16 ? 2 : type == BG_Q4_0 ? 18 : type == BG_Q4_1 ? 20 : type == BG_Q5_0 ? 22 : type == BG_Q5_1 ? 24 : 34);
     const uint8_t * r = W + rb * blockIdx.x;
     for (int c = threadIdx.x; c < K; c += blockDim.x) y[(size_t) blockIdx.x * K + c] = bg_dequant_elem(type, r, c);
@@ -279,7 +279,7 @@ __device__ __forceinline__ void bg_row_to_record(const float * srow, int K, int 
     }
 }
 
-__global__ void __launch_bounds__(256) k_act(ActArgs a) {
+static __global__ void __launch_bounds__(256) k_act(ActArgs a) {
     extern __shared__ __align__(16) float srow[];
     __shared__ double sd[32];
     const int row = blockIdx.x, tid = threadIdx.x, K = a.K;
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(256) k_attn(AttnArgs a) {
 // grid = (n_head, ceil(n / AT_R)), block = 256, dynamic smem = AT_R * (Tpad + 64) floats. d_kv = 64.
 // ---------------------------------------------------------------------------------------------
 #define AT_R 16
-__global__ void __launch_bounds__(256) k_attn_tile(AttnArgs a) {
+static __global__ void __launch_bounds__(256) k_attn_tile(AttnArgs a) {
     constexpr int DK = 64, NW = 8;
     extern __shared__ __align__(16) float s_at[];
     const int h = blockIdx.x, r0 = blockIdx.y * AT_R, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -791,13 +791,13 @@ __global__ void __launch_bounds__(256) k_attn_tile(AttnArgs a) {
 }
 
 // fp16-table GELU as a stand-alone op (unit tests); the eval fuses it into the fc1 epilogue
-__global__ void k_gelu(const float * __restrict__ x, float * __restrict__ y, int n, const uint16_t * __restrict__ tab) {
+static __global__ void k_gelu(const float * __restrict__ x, float * __restrict__ y, int n, const uint16_t * __restrict__ tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = bg_h2f(tab[bg_f2h(x[i])]);
 }
 
 // convert an activation record back to the reference's block_q8_0 / block_q8_1 / fp16 bytes
-__global__ void k_act_export(const uint8_t * __restrict__ rec, int wtype, int K, int off_d, int off_s, uint8_t * __restrict__ out) {
+static __global__ void k_act_export(const uint8_t * __restrict__ rec, int wtype, int K, int off_d, int off_s, uint8_t * __restrict__ out) {
     const int kind = bg_act_kind(wtype);
     const int nb = K >> 5;
     if (kind == ACT_F16) {
@@ -839,7 +839,7 @@ __global__ void k_act_export(const uint8_t * __restrict__ rec, int wtype, int K,
 
 // greedy sampling on the device: argmax (first index wins), log the id, feed it back and
 // advance n_past -- lets a whole decode loop run without the host (bgpt_cuda_decode_greedy)
-__global__ void __launch_bounds__(1024) k_argmax_advance(const float * __restrict__ logits, int n_vocab,
+static __global__ void __launch_bounds__(1024) k_argmax_advance(const float * __restrict__ logits, int n_vocab,
                                                          int * __restrict__ next_tok, int * __restrict__ id_log,
                                                          DevState * st, int n_advance) {
     __shared__ float sv[32]; __shared__ int si[32];

@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(MEGA_NT, 1) k_mega(MegaParams p) {
 }
 
 // reduces the candidates of the last launch of a greedy loop into the id log
-__global__ void k_mega_pick(const float * __restrict__ cand_val, const int * __restrict__ cand_idx, int n_cand,
+static __global__ void k_mega_pick(const float * __restrict__ cand_val, const int * __restrict__ cand_idx, int n_cand,
                             int * __restrict__ idlog, int slot, int * __restrict__ next_tok) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         float best = -INFINITY; int bi = 0x7fffffff;

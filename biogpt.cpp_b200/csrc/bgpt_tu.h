@@ -1,0 +1,13 @@
+// bgpt_tu.h -- kernel entry points by translation unit.  The persistent decode kernels, the skinny-batch schedule and the
+// tensor-core matmul are each instantiated in their own .cu file (tu_*.cu) so that the library builds in parallel and a
+// change to one schedule recompiles one file; bgpt_cuda.cu launches them through these pointers (cudaLaunchKernelExC /
+// cudaLaunchCooperativeKernel).  nullptr = no instantiation for that format / shape.
+#pragma once
+const void * bgpt_k_mega_fn(int wtype, int dk);                 // tu_mega3.cu : k_mega<FMT, DK>
+const void * bgpt_k_mega_pick_fn();                             // tu_mega3.cu : k_mega_pick
+const void * bgpt_k_mega4_fn(int wtype, bool prof);             // tu_mega4.cu : k_mega4<FMT, PROF>
+const void * bgpt_k_sk_mm_fn(int wtype, int TN);                // tu_skinny.cu: k_sk_mm<FMT, TN>
+const void * bgpt_k_sk_ln_fn(int wtype);
+const void * bgpt_k_sk_gq_fn(int wtype);
+const void * bgpt_k_sk_attn_fn(int wtype);
+const void * bgpt_k_gemm_tc_fn(int wtype);                      // tu_tc.cu    : k_gemm_tc_q<FMT>

@@ -121,6 +121,11 @@ int bgpt_cuda_get_decode_path(const bgpt_model * m);
  * on the fused schedule. */
 int bgpt_cuda_set_batch_path(bgpt_model * m, int path);
 int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows);
+/* Which schedule an eval of n_rows token rows takes on this model: 3 = persistent decode kernel (n_rows == 1), 1 = fused
+ * skinny-batch schedule, 0 = per-operator schedule with the exact-order SIMT matmul -- these three give the reference's bits --
+ * 2 = per-operator schedule with the tcgen05 matmul (quantised weights, 112+ rows; BGPT_TC_MIN_ROWS / BGPT_TC=0): exact
+ * integer block dots but one f32 term per block, so logits are tolerance-close, not bit-identical (csrc/bgpt_tc.cuh). */
+int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows);
 /* debug: copy one of the eval arena's buffers as the last eval left it (0 x, 1 x1, 2 q, 3 the d_model-wide activation
  * records, 4 the d_ff-wide activation records; `rows` token rows) to HOST memory; returns the bytes copied, -1 on error.
  * tools/skinny_check.py uses it to localise a mismatch between the two batch schedules. */
@@ -134,18 +139,10 @@ int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);
  * {globaltimer ns, clock64} pairs taken at the start and the end of the launch, which put the
  * per-SM clocks on one time axis.  Returns the number of entries copied (0: off / cap too small). */
 int bgpt_cuda_debug_read_trace(bgpt_model * m, long long * out, int cap, int * n_cta, int * per_cta);
-/* debug: microseconds per grid-wide barrier for the candidate implementations in
- * csrc/bgpt_barbench.cuh (one CTA per SM, `iters` back-to-back barriers). */
 /* f32 -> Q4_0/Q4_1/Q5_0/Q5_1/Q8_0 blocks in the file layout, on the device; bit-identical to the reference's
  * quantize_row_q*_reference as its `quantize` tool runs them (ggml.c:892-1094, biogpt.cpp:459-621).  `type` is a
  * ggml_type; n (a multiple of 32) host floats in, n/32 blocks out. */
 int bgpt_cuda_op_quantize_weights(int type, const float * x, long long n, uint8_t * out);
-int bgpt_cuda_debug_quantize_bench(int type, long long n, int iters, float * us_per_launch);
-int bgpt_cuda_debug_icache_bench(int kb, int iters, int nwarps, float * cycles_per_iter);
-int bgpt_cuda_debug_barrier_bench(int variant, int iters, int with_load, float * us_per_barrier);
-/* debug: milliseconds per matmul y[n][rows] = W[rows][k].x[n][k] (synthetic data, device
- * resident, `iters` back-to-back launches); path 0 = exact-order SIMT kernels, 1 = tcgen05. */
-int bgpt_cuda_debug_gemm_bench(int ggml_type, int k, int rows, int n, int iters, int path, float * ms_out);
 
 /* multi-stream state: `n_streams` independent sequences, each with its own KV cache
  * (SURVEY 8(d) config 4).  Stream 0 always exists. */

@@ -238,6 +238,139 @@ def test_skinny_lockstep_streams_equal_single_stream(capi, zoo, ftype):
         M.close()
 
 
+def _fast_checker(checkers, path, n_batch=8):
+    """the unmodified reference on all host threads (AVX2) where oracle/_ref was built, else the plain-C restatement;
+    tests/test_oracle_vs_ref.py pins the two to each other bit for bit"""
+    return checkers.Ref(path, n_batch=n_batch) if checkers.have_ref() else checkers.Oracle(path)
+
+
+def _top5(v):
+    return set(np.argsort(-v, kind="stable")[:5].tolist())
+
+
+# north_star gate for the one schedule that is not bit-identical (tcgen05 matmul, 112+ rows): argmax-identical ids, top-5
+# set equality, and a max-abs logit bound.  The bound is stated here: 2e-2 absolute on logits whose spread (max - min) is
+# ~10 -- the measured deviation is printed by the test and recorded in profiles/README.md.
+TC_LOGIT_TOL = 2e-2
+
+
+@pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_tensor_core_prompt_meets_north_star_gate(checkers, capi, zoo, ftype):
+    """whole evals of 112 / 128 / 256 / 1024 rows (BioGPT-base layer shapes, 2 layers) on the per-operator schedule with the
+    tcgen05 matmul -- the DEFAULT path for quantised prompts of 112+ rows -- against the reference: same argmax, same top-5
+    set, max|dlogit| <= TC_LOGIT_TOL, and a 24-token greedy continuation (persistent kernel on the KV cache the tensor-core
+    pass wrote) with identical ids"""
+    hp = gf.NARROW
+    p = zoo.path("narrow", ftype)
+    toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=808)
+    worst = 0.0
+    for rows in (112, 128, 256, 1024):
+        R = _fast_checker(checkers, p, n_batch=rows)
+        M = capi.Model.load(p, max_batch=rows)
+        assert M.eval_path(rows) == 2 and M.eval_path(111) == 1 and M.eval_path(1) == 3, capi.last_error()
+        want = R.eval(toks[:rows], 0)
+        got = M.eval(toks[:rows], 0)
+        err = float(np.abs(got - want).max())
+        worst = max(worst, err)
+        assert int(np.argmax(got)) == int(np.argmax(want)), f"{ftype} rows={rows}: argmax differs (max|d|={err:.3e})"
+        assert _top5(got) == _top5(want), f"{ftype} rows={rows}: top-5 sets differ (max|d|={err:.3e})"
+        assert err <= TC_LOGIT_TOL, f"{ftype} rows={rows}: max|dlogit|={err:.3e} > {TC_LOGIT_TOL}"
+        if rows < hp.n_positions:
+            steps = 24
+            tok_r, tok_m, ids_r, ids_m = int(np.argmax(want)), int(np.argmax(got)), [], []
+            for i in range(steps):
+                lr = R.eval(np.array([tok_r], np.int32), rows + i); tok_r = int(np.argmax(lr)); ids_r.append(tok_r)
+                lm = M.eval(np.array([tok_m], np.int32), rows + i); tok_m = int(np.argmax(lm)); ids_m.append(tok_m)
+                assert _top5(lm) == _top5(lr), f"{ftype} rows={rows}: top-5 sets differ at continuation step {i}"
+            assert ids_m == ids_r, f"{ftype} rows={rows}: greedy continuation differs"
+        R.close(); M.close()
+    print(f"tcgen05 prompt path {ftype}: worst max|dlogit| = {worst:.3e}")
+
+
+@pytest.mark.parametrize("ftype,rows", [("q4_0", 128), ("q8_0", 1024)])
+def test_tensor_core_prompt_gate_base_model(checkers, capi, zoo, ftype, rows):
+    """the same gate on the full 24-layer, 42384-row-vocabulary model"""
+    hp = gf.BASE
+    p = zoo.path("base", ftype)
+    toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=909)
+    R = _fast_checker(checkers, p, n_batch=rows)
+    M = capi.Model.load(p, max_batch=rows)
+    assert M.eval_path(rows) == 2
+    want = R.eval(toks[:rows], 0)
+    got = M.eval(toks[:rows], 0)
+    err = float(np.abs(got - want).max())
+    print(f"tcgen05 prompt path base/{ftype} rows={rows}: max|dlogit| = {err:.3e}")
+    assert int(np.argmax(got)) == int(np.argmax(want)), f"argmax differs (max|d|={err:.3e})"
+    assert _top5(got) == _top5(want), f"top-5 sets differ (max|d|={err:.3e})"
+    assert err <= TC_LOGIT_TOL, f"max|dlogit|={err:.3e} > {TC_LOGIT_TOL}"
+    R.close(); M.close()
+
+
+def test_base_model_headline_greedy_over_whole_context(checkers, capi, zoo):
+    """BASELINE configs[1] itself: 24 layers, vocabulary 42384, Q4_0, one token at a time from n_past 0 to 1023 on the
+    persistent decode kernel (device-side greedy loop), against the reference's own greedy loop (biogpt.cpp:812-847 +
+    top_k = 1 sampling): all 1024 ids identical; logits bit-identical where sampled (first steps, the 32-wide boundaries,
+    the second K pass, the end of the context)"""
+    hp = gf.BASE
+    p = zoo.path("base", "q4_0")
+    R = _fast_checker(checkers, p)
+    M = capi.Model.load(p)
+    assert M.eval_path(1) == 3 and M.decode_generation >= 4, capi.last_error()
+    n = hp.n_positions
+    ids, _ = M.decode_greedy(2, 0, n)
+    probe = {0, 1, 2, 30, 31, 32, 33, 63, 64, 255, 256, 511, 512, 513, 767, 1021, 1022, 1023}
+    want_ids, want_logits, tok = [], {}, 2
+    for i in range(n):
+        l = R.eval(np.array([tok], np.int32), i)
+        if i in probe:
+            want_logits[i] = (tok, l.copy())
+        tok = int(np.argmax(l)); want_ids.append(tok)
+    first_bad = next((i for i in range(n) if ids[i] != want_ids[i]), None)
+    assert first_bad is None, f"greedy ids fork at step {first_bad}: {ids[first_bad]} vs {want_ids[first_bad]}"
+    for i in sorted(probe):                      # the device cache holds this very sequence: re-evaluating position i is idempotent
+        tok_i, wl = want_logits[i]
+        got = M.eval(np.array([tok_i], np.int32), i)
+        assert np.array_equal(_bits(got), _bits(wl)), _diff(f"base q4_0 n_past={i}", got, wl)
+    R.close(); M.close()
+
+
+@pytest.mark.parametrize("ftype", ["q4_1", "q5_0", "q5_1", "q8_0", "f16", "f32"])
+def test_base_model_64_token_continuation(checkers, capi, zoo, ftype):
+    """SURVEY 8(d) parity gate on the full-size model for every other format: an 8-token un-masked prompt batch, then a
+    64-token greedy continuation -- ids identical, top-5 sets identical, and (stronger) logits bit-identical at every step"""
+    hp = gf.BASE
+    p = zoo.path("base", ftype)
+    R = _fast_checker(checkers, p)
+    M = capi.Model.load(p)
+    prompt = gf.synth_tokens(8, hp.n_vocab, seed=17)
+    want = R.eval(prompt, 0); got = M.eval(prompt, 0)
+    assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} prompt", got, want)
+    first = int(np.argmax(want))
+    ids, _ = M.decode_greedy(first, 8, 64)
+    tok, want_ids = first, []
+    for i in range(64):
+        l = R.eval(np.array([tok], np.int32), 8 + i)
+        g = M.eval(np.array([tok], np.int32), 8 + i)
+        assert _top5(g) == _top5(l), (ftype, i)
+        assert np.array_equal(_bits(g), _bits(l)), _diff(f"{ftype} continuation step {i}", g, l)
+        tok = int(np.argmax(l)); want_ids.append(tok)
+    assert ids.tolist() == want_ids
+    R.close(); M.close()
+
+
+def test_eval_path_map(capi, zoo):
+    """which schedule a (model, rows) pair takes: only quantised evals of 112+ rows leave the bit-exact kernels"""
+    M = capi.Model.load(zoo.path("narrow", "q5_1"), max_batch=128)
+    assert [M.eval_path(n) for n in (1, 2, 8, 111, 112, 128)] == [3, 1, 1, 1, 2, 2]
+    M.close()
+    M = capi.Model.load(zoo.path("small", "q4_0"), max_batch=128)          # not BioGPT-base layer shapes: no skinny schedule
+    assert [M.eval_path(n) for n in (1, 2, 32, 111, 112)] == [3, 0, 0, 0, 2]
+    M.close()
+    M = capi.Model.load(zoo.path("small", "f16"), max_batch=128)           # F16 never uses the integer tensor-core matmul
+    assert [M.eval_path(n) for n in (1, 8, 112)] == [3, 0, 0]
+    M.close()
+
+
 def test_persistent_kernel_long_context(checkers, capi, zoo):
     """prompt in un-masked batches of 8 (per-op kernels), then persistent-kernel decode near the end
     of the context"""

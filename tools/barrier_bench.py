@@ -11,7 +11,7 @@ names = ["counter+poll counter", "counter+flag(last arriver)", "per-CTA flags, 1
 for v, n in enumerate(names):
     for wl in (0, 1):
         us = C.c_float(0)
-        rc = capi.lib().bgpt_cuda_debug_barrier_bench(v, 2000, wl, C.byref(us))
+        rc = capi.tools_lib().bgpt_cuda_debug_barrier_bench(v, 2000, wl, C.byref(us))
         print(f"variant {v} ({n}){' + dependent L2 load' if wl else ''}: {us.value:.3f} us/barrier" if rc == 0 else capi.last_error())
 
 xn = ["exchange: ld.volatile, 8 replicas, 512 pollers (generation-4 kernel)", "exchange: ld.relaxed.gpu, 8 replicas, 512 pollers", "exchange: ld.acquire.gpu, 8 replicas, 512 pollers",
@@ -20,18 +20,18 @@ xn = ["exchange: ld.volatile, 8 replicas, 512 pollers (generation-4 kernel)", "e
 for i, n in enumerate(xn):
     for sl in (0, 100):
         us = C.c_float(0)
-        rc = capi.lib().bgpt_cuda_debug_barrier_bench(7 + i, 2000, sl, C.byref(us))
+        rc = capi.tools_lib().bgpt_cuda_debug_barrier_bench(7 + i, 2000, sl, C.byref(us))
         print(f"variant {7 + i} ({n}){', nanosleep(100) back-off' if sl else ''}: {us.value:.3f} us/exchange" if rc == 0 else capi.last_error())
 for i, n in enumerate(["ld.volatile", "ld.relaxed.gpu", "ld.acquire.gpu"]):
     for peer in (1, 2, 75, 147):
         us = C.c_float(0)
-        rc = capi.lib().bgpt_cuda_debug_barrier_bench(15 + i, 2000, peer, C.byref(us))
+        rc = capi.tools_lib().bgpt_cuda_debug_barrier_bench(15 + i, 2000, peer, C.byref(us))
         print(f"ping-pong CTA 0 <-> CTA {peer} ({n}): {us.value * 500:.0f} ns one way" if rc == 0 else capi.last_error())
 
 for v, n in [(18, "exchange: ld.volatile, 16 replicas"), (19, "exchange: ld.volatile, 32 replicas"), (20, "exchange: ld.global.cg, 8 replicas"),
              (21, "packed exchange {3 x f32, tag} 16-byte units, 8 replicas, 384 pollers"), (22, "packed exchange, 16 replicas"), (23, "packed exchange, 1 replica")]:
     us = C.c_float(0)
-    rc = capi.lib().bgpt_cuda_debug_barrier_bench(v, 2000, 0, C.byref(us))
+    rc = capi.tools_lib().bgpt_cuda_debug_barrier_bench(v, 2000, 0, C.byref(us))
     print(f"variant {v} ({n}): {us.value:.3f} us/exchange" if rc == 0 else capi.last_error())
 
 for v, n in [(24, "producer: lane 28 of warps < rows, 8 sequential stores"), (25, "producer: threads 8*row, 8 sequential stores"),
@@ -39,5 +39,5 @@ for v, n in [(24, "producer: lane 28 of warps < rows, 8 sequential stores"), (25
              (28, "producer: gather + sync, warp r writes replica r")]:
     for rep in range(2):
         us = C.c_float(0)
-        rc = capi.lib().bgpt_cuda_debug_barrier_bench(v, 2000, 0, C.byref(us))
+        rc = capi.tools_lib().bgpt_cuda_debug_barrier_bench(v, 2000, 0, C.byref(us))
         print(f"variant {v} ({n}): {us.value:.3f} us/exchange" if rc == 0 else capi.last_error())

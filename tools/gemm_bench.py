@@ -21,7 +21,7 @@ for tn in a.types.split(","):
             for path in (0, 1):
                 ms = C.c_float(0)
                 iters = max(3, min(50, int(2e10 / (2.0 * k * rows * n + 1))))
-                rc = capi.lib().bgpt_cuda_debug_gemm_bench(T[tn], k, rows, n, iters, path, C.byref(ms))
+                rc = capi.tools_lib().bgpt_cuda_debug_gemm_bench(T[tn], k, rows, n, iters, path, C.byref(ms))
                 out.append((ms.value, 2.0 * k * rows * n / (ms.value * 1e-3) / 1e12) if rc == 0 else None)
             f = lambda o: f"{o[0] * 1e3:9.1f} us {o[1]:8.2f} TFLOP/s" if o else "      n/a"
             print(f"{tn:5s} K={k:5d} rows={rows:5d} n={n:5d}  simt-exact {f(out[0])}   tcgen05 {f(out[1])}")
