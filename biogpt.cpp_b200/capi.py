@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -84,6 +84,7 @@ def lib():
     L.bgpt_cuda_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bgpt_cuda_op_quantize_weights.argtypes = [C.c_int, _f32p, C.c_longlong, _u8p]
     L.bgpt_cuda_get_eval_path.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_set_tc_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
     L.bgpt_cuda_hparams.restype = None
@@ -228,6 +229,10 @@ class Model:
 
     def batch_path(self, n_rows: int) -> int:
         return int(lib().bgpt_cuda_get_batch_path(self.h, n_rows))
+
+    def set_tc_min_rows(self, rows: int):
+        """opt in to the tolerance-close integer tcgen05 matmul for quantised evals of `rows`+ rows (0 = off, the default)"""
+        _check(lib().bgpt_cuda_set_tc_min_rows(self.h, rows), "set_tc_min_rows")
 
     def eval_path(self, n_rows: int) -> int:
         """3 persistent decode kernel, 1 fused skinny-batch schedule, 0 per-operator exact SIMT, 2 per-operator with the

@@ -102,7 +102,9 @@ struct bgpt_model {
     uint64_t launches = 0;
     size_t weight_bytes = 0;
     // persistent decode kernel (bgpt_mega.cuh)
-    bool tc_ok = true;                                   // tcgen05 batch matmul allowed (BGPT_TC=0 disables)
+    // the integer tcgen05 batch matmul (bgpt_tc.cuh) is tolerance-close, not bit-identical: OFF unless asked for
+    // (BGPT_TC_MIN_ROWS=<rows> or bgpt_cuda_set_tc_min_rows); evals of that many token rows then leave the exact kernels
+    int tc_min_rows = 1 << 30;
     bool mega_ok = false; int decode_path = 1;          // 1: k_mega for n == 1, 0: per-op kernels
     MegaParams mp{}; MegaLayer * d_mega_layers = nullptr; std::vector<MegaLayer> h_mega_layers;
     unsigned long long * d_bar = nullptr; unsigned long long bar_epoch = 0;
@@ -120,7 +122,7 @@ struct bgpt_model {
     int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;
     int sk_fc1_split = 1;                                 // 1: fc1 as plain 8-row CTAs + k_sk_gq (8 Q5_1 streams 979 -> 943 us per step, prompt unchanged), 0: quantising epilogue (BGPT_SK_FC1_SPLIT)
     int sk_tn_fc1 = 0;                                    // 0: follow sk_tn_proj (BGPT_SK_TN_FC1)
-    int sk_max_rows = 112;                                // measured crossover with the tcgen05 batch matmul path: 96 rows 53.5 vs 61.2 ms, 128 rows 50.9 vs 44.2 ms per 1024 Q8_0 prompt tokens (BGPT_SK_MAX_ROWS)   // tuning knobs of that schedule (BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF)
+    // tuning knobs of that schedule: BGPT_SK_PDL_TRIG, BGPT_SK_TN_PROJ, BGPT_SK_TN_QKV, BGPT_SK_FC1_NW, BGPT_SK_SKIP, BGPT_SK_KVPF
     float * taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; bool taps_armed = false;
     float * d_taps[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 };
@@ -365,7 +367,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_KVPF")) m->sk_kv_prefetch = atoi(getenv("BGPT_SK_KVPF")) != 0;
     if (getenv("BGPT_SK_TN_FC1")) { const int v = atoi(getenv("BGPT_SK_TN_FC1")); m->sk_tn_fc1 = v == 8 ? 8 : (v == 4 ? 4 : 0); }
     if (getenv("BGPT_SK_FC1_SPLIT")) m->sk_fc1_split = atoi(getenv("BGPT_SK_FC1_SPLIT")) != 0;
-    if (getenv("BGPT_SK_MAX_ROWS")) m->sk_max_rows = std::max(2, atoi(getenv("BGPT_SK_MAX_ROWS")));
+    if (getenv("BGPT_TC_MIN_ROWS")) { const int v = atoi(getenv("BGPT_TC_MIN_ROWS")); m->tc_min_rows = v > 0 ? std::max(2, v) : (1 << 30); }
     RET(mega_setup(m));
     m->finalized = true;
     return BGPT_OK;
@@ -404,7 +406,6 @@ template <int FMT> static void launch_gemv_f_tn(int TN, dim3 grid, int threads, 
     }
 }
 
-static int tc_min_rows();
 static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
                           int n, int tok0, const Epi & epi);
 
@@ -419,7 +420,7 @@ static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W
     a.act = act; a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s;
     a.n = n; a.tok0 = tok0; a.epi = epi;
     const int cnt = n - tok0;
-    if (bg_is_quant(L.type) && cnt >= tc_min_rows() && m && m->tc_ok) return launch_gemm_tc(m, s, W, nmat, act, A, n, tok0, epi);
+    if (bg_is_quant(L.type) && m && cnt >= m->tc_min_rows) return launch_gemm_tc(m, s, W, nmat, act, A, n, tok0, epi);
     const int TN = cnt <= 1 ? 1 : cnt == 2 ? 2 : cnt <= 4 ? 4 : 8;
     const int gy = (cnt + TN - 1) / TN;
     const size_t smem = (size_t) TN * A.bytes;
@@ -443,14 +444,6 @@ static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W
 }
 
 // ---- tensor-core (tcgen05) batch matmul for the quantised formats, bgpt_tc.cuh
-static int tc_min_rows() {
-    static int v = -1;
-    if (v < 0) {
-        const char * e = getenv("BGPT_TC"); const char * r = getenv("BGPT_TC_MIN_ROWS");
-        v = (e && atoi(e) == 0) ? (1 << 30) : (r ? std::max(1, atoi(r)) : 112);   // every smaller batch stays on the exact-order kernels, whatever the model shape
-    }
-    return v;
-}
 static size_t tc_smem_bytes() { return std::max(sizeof(TcShared) + 128, (size_t) 120 * 1024); }   // >= half the SM: one CTA (512 TMEM columns) per SM
 static void tc_init_attrs() {
     static unsigned long long done = 0;
@@ -580,7 +573,7 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
 // ------------------------------------------------------------------------------------------
 static bool skinny_ok(const bgpt_model * m, int n) {
     return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff == 4096 &&
-           m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < (m->tc_ok && tc_min_rows() < (1 << 30) ? m->sk_max_rows : (1 << 30));
+           m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < m->tc_min_rows;
 }
 static void sk_init_attrs() {
     static unsigned long long done = 0;
@@ -782,6 +775,14 @@ extern "C" long long bgpt_cuda_debug_read_buffer(bgpt_model * m, int which, int 
         cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { fail(BGPT_E_CUDA, "debug_read_buffer: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
     return (long long) bytes;
 }
+extern "C" int bgpt_cuda_set_tc_min_rows(bgpt_model * m, int rows) {
+    if (!m || rows < 0) return fail(BGPT_E_ARG, "set_tc_min_rows: bad arguments");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    drop_graphs(m);
+    m->tc_min_rows = rows == 0 ? (1 << 30) : std::max(2, rows);
+    return BGPT_OK;
+}
 extern "C" int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows) { return m && skinny_ok(m, n_rows) ? 1 : 0; }
 static bool use_mega(const bgpt_model * m);
 // which schedule an eval of n_rows token rows takes: 3 persistent decode kernel, 1 fused skinny-batch schedule (exact), 2 per-operator
@@ -790,7 +791,7 @@ extern "C" int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows) {
     if (!m || n_rows < 1) return -1;
     if (n_rows == 1 && use_mega(m)) return 3;
     if (skinny_ok(m, n_rows)) return 1;
-    if (bg_is_quant(m->wtype) && m->tc_ok && n_rows >= tc_min_rows()) return 2;
+    if (bg_is_quant(m->wtype) && n_rows >= m->tc_min_rows) return 2;
     return 0;
 }
 
@@ -1434,7 +1435,7 @@ extern "C" int bgpt_cuda_debug_gemm_bench(int type, int k, int rows, int n, int 
     RET(launch_act(nullptr, 0, dx.as<float>(), k, nullptr, nullptr, k, type, da.as<uint8_t>(), A, n, nullptr, 0));
     const DevTensor * W[3] = { &t, nullptr, nullptr };
     Epi e = make_epi(EPI_STORE, nullptr, dy.as<float>(), rows);
-    bgpt_model fake{}; fake.tc_ok = false;
+    bgpt_model fake{};
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; rep++) {
         if (rep == 1) CK(cudaEventRecord(e0));

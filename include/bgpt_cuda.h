@@ -122,10 +122,13 @@ int bgpt_cuda_get_decode_path(const bgpt_model * m);
 int bgpt_cuda_set_batch_path(bgpt_model * m, int path);
 int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows);
 /* Which schedule an eval of n_rows token rows takes on this model: 3 = persistent decode kernel (n_rows == 1), 1 = fused
- * skinny-batch schedule, 0 = per-operator schedule with the exact-order SIMT matmul -- these three give the reference's bits --
- * 2 = per-operator schedule with the tcgen05 matmul (quantised weights, 112+ rows; BGPT_TC_MIN_ROWS / BGPT_TC=0): exact
- * integer block dots but one f32 term per block, so logits are tolerance-close, not bit-identical (csrc/bgpt_tc.cuh). */
+ * skinny-batch schedule, 0 = per-operator schedule with the exact-order SIMT matmul -- these three give the reference's bits
+ * and are the only ones used by default -- 2 = per-operator schedule with the integer tcgen05 matmul of csrc/bgpt_tc.cuh
+ * (exact integer block dots but one f32 term per block: logits drift by ~5e-2, see tests/test_gpu_eval.py), which is OFF
+ * unless enabled with bgpt_cuda_set_tc_min_rows / BGPT_TC_MIN_ROWS. */
 int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows);
+/* opt in to the tolerance-close integer tcgen05 matmul for quantised evals of `rows`+ token rows (0 = off, the default) */
+int bgpt_cuda_set_tc_min_rows(bgpt_model * m, int rows);
 /* debug: copy one of the eval arena's buffers as the last eval left it (0 x, 1 x1, 2 q, 3 the d_model-wide activation
  * records, 4 the d_ff-wide activation records; `rows` token rows) to HOST memory; returns the bytes copied, -1 on error.
  * tools/skinny_check.py uses it to localise a mismatch between the two batch schedules. */

@@ -188,7 +188,7 @@ def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftyp
     p = zoo.path("narrow", ftype)
     O = checkers.Oracle(p)
     M = capi.Model.load(p, max_batch=128)
-    assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(111) == 1 and M.batch_path(112) == 0, capi.last_error()
+    assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(111) == 1 and M.batch_path(112) == 1, capi.last_error()
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=55)
     sizes = [8, 8, 5, 2, 3, 4, 7, 16, 9, 1, 8, 31, 8, 6]             # 116 positions: T = 8, 16, 21, 23, 26, 30, 37, 53, 62, 63, 71, 102, ...
     sched, pos = [], 0
@@ -211,8 +211,6 @@ def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftyp
     M.set_batch_path(0)
     assert M.batch_path(8) == 0
     for (pos, n), ref in zip(sched, got_fused):
-        if n >= 32:       # the per-operator schedule runs 32+ rows on the tcgen05 matmul (one f32 term per block: close, not identical --
-            continue      # tests/test_gpu_ops.py carries its tolerance); skipping keeps the cache rows of the fused pass, which are the oracle's
         got = M.eval(toks[pos:pos + n], pos)
         assert np.array_equal(_bits(got), _bits(ref)), (ftype, pos, n)
     O.close(); M.close()
@@ -248,62 +246,72 @@ def _top5(v):
     return set(np.argsort(-v, kind="stable")[:5].tolist())
 
 
-# north_star gate for the one schedule that is not bit-identical (tcgen05 matmul, 112+ rows): argmax-identical ids, top-5
-# set equality, and a max-abs logit bound.  The bound is stated here: 2e-2 absolute on logits whose spread (max - min) is
-# ~10 -- the measured deviation is printed by the test and recorded in profiles/README.md.
-TC_LOGIT_TOL = 2e-2
-
-
 @pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
-def test_tensor_core_prompt_meets_north_star_gate(checkers, capi, zoo, ftype):
-    """whole evals of 112 / 128 / 256 / 1024 rows (BioGPT-base layer shapes, 2 layers) on the per-operator schedule with the
-    tcgen05 matmul -- the DEFAULT path for quantised prompts of 112+ rows -- against the reference: same argmax, same top-5
-    set, max|dlogit| <= TC_LOGIT_TOL, and a 24-token greedy continuation (persistent kernel on the KV cache the tensor-core
-    pass wrote) with identical ids"""
+def test_large_prompt_batches_are_bit_exact(checkers, capi, zoo, ftype):
+    """whole evals of 112 / 128 / 256 / 1024 rows (BioGPT-base layer shapes, 2 layers): the DEFAULT path for large quantised
+    prompt batches is the exact-order skinny-batch schedule -- logits bit-identical to the reference, and a 24-token greedy
+    continuation on the KV cache that pass wrote gives identical ids and bit-identical logits"""
     hp = gf.NARROW
     p = zoo.path("narrow", ftype)
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=808)
-    worst = 0.0
     for rows in (112, 128, 256, 1024):
         R = _fast_checker(checkers, p, n_batch=rows)
         M = capi.Model.load(p, max_batch=rows)
-        assert M.eval_path(rows) == 2 and M.eval_path(111) == 1 and M.eval_path(1) == 3, capi.last_error()
+        assert M.eval_path(rows) == 1 and M.eval_path(1) == 3, capi.last_error()
         want = R.eval(toks[:rows], 0)
         got = M.eval(toks[:rows], 0)
-        err = float(np.abs(got - want).max())
-        worst = max(worst, err)
-        assert int(np.argmax(got)) == int(np.argmax(want)), f"{ftype} rows={rows}: argmax differs (max|d|={err:.3e})"
-        assert _top5(got) == _top5(want), f"{ftype} rows={rows}: top-5 sets differ (max|d|={err:.3e})"
-        assert err <= TC_LOGIT_TOL, f"{ftype} rows={rows}: max|dlogit|={err:.3e} > {TC_LOGIT_TOL}"
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} rows={rows}", got, want)
         if rows < hp.n_positions:
-            steps = 24
-            tok_r, tok_m, ids_r, ids_m = int(np.argmax(want)), int(np.argmax(got)), [], []
-            for i in range(steps):
-                lr = R.eval(np.array([tok_r], np.int32), rows + i); tok_r = int(np.argmax(lr)); ids_r.append(tok_r)
-                lm = M.eval(np.array([tok_m], np.int32), rows + i); tok_m = int(np.argmax(lm)); ids_m.append(tok_m)
-                assert _top5(lm) == _top5(lr), f"{ftype} rows={rows}: top-5 sets differ at continuation step {i}"
-            assert ids_m == ids_r, f"{ftype} rows={rows}: greedy continuation differs"
+            tok = int(np.argmax(want))
+            for i in range(24):
+                lr = R.eval(np.array([tok], np.int32), rows + i)
+                lm = M.eval(np.array([tok], np.int32), rows + i)
+                assert np.array_equal(_bits(lm), _bits(lr)), _diff(f"{ftype} rows={rows} continuation step {i}", lm, lr)
+                tok = int(np.argmax(lr))
         R.close(); M.close()
-    print(f"tcgen05 prompt path {ftype}: worst max|dlogit| = {worst:.3e}")
 
 
 @pytest.mark.parametrize("ftype,rows", [("q4_0", 128), ("q8_0", 1024)])
-def test_tensor_core_prompt_gate_base_model(checkers, capi, zoo, ftype, rows):
-    """the same gate on the full 24-layer, 42384-row-vocabulary model"""
+def test_large_prompt_batch_base_model_bit_exact(checkers, capi, zoo, ftype, rows):
+    """the same on the full 24-layer, 42384-row-vocabulary model"""
     hp = gf.BASE
     p = zoo.path("base", ftype)
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=909)
     R = _fast_checker(checkers, p, n_batch=rows)
     M = capi.Model.load(p, max_batch=rows)
-    assert M.eval_path(rows) == 2
+    assert M.eval_path(rows) == 1
     want = R.eval(toks[:rows], 0)
     got = M.eval(toks[:rows], 0)
-    err = float(np.abs(got - want).max())
-    print(f"tcgen05 prompt path base/{ftype} rows={rows}: max|dlogit| = {err:.3e}")
-    assert int(np.argmax(got)) == int(np.argmax(want)), f"argmax differs (max|d|={err:.3e})"
-    assert _top5(got) == _top5(want), f"top-5 sets differ (max|d|={err:.3e})"
-    assert err <= TC_LOGIT_TOL, f"max|dlogit|={err:.3e} > {TC_LOGIT_TOL}"
+    assert np.array_equal(_bits(got), _bits(want)), _diff(f"base {ftype} rows={rows}", got, want)
     R.close(); M.close()
+
+
+# The integer tcgen05 matmul (csrc/bgpt_tc.cuh) adds ONE f32 term per 32-block instead of the reference's 8 running sums.
+# Each matmul is within 3e-5 relative (tests/test_gpu_ops.py) but activations are re-quantised to int8 in front of every
+# matmul, so the drift compounds: measured max|dlogit| 1.7e-2 (2 layers) .. 5.3e-2 (24 layers) on logits of spread ~4, and
+# top-5 sets of a flat synthetic distribution are not stable.  That fails the north_star gate for Qx, so the path is OPT-IN
+# (bgpt_cuda_set_tc_min_rows) and this test only pins its documented envelope: same argmax, max|dlogit| <= 1e-1.
+TC_LOGIT_TOL = 1e-1
+
+
+@pytest.mark.parametrize("ftype", ["q4_0", "q5_1", "q8_0"])
+def test_opt_in_integer_tensor_core_path_envelope(checkers, capi, zoo, ftype):
+    hp = gf.NARROW
+    p = zoo.path("narrow", ftype)
+    toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=808)
+    for rows in (128, 1024):
+        R = _fast_checker(checkers, p, n_batch=rows)
+        M = capi.Model.load(p, max_batch=rows)
+        M.set_tc_min_rows(112)
+        assert M.eval_path(rows) == 2 and M.eval_path(111) == 1
+        want = R.eval(toks[:rows], 0)
+        got = M.eval(toks[:rows], 0)
+        err = float(np.abs(got - want).max())
+        print(f"opt-in integer tcgen05 path {ftype} rows={rows}: max|dlogit| = {err:.3e}")
+        assert int(np.argmax(got)) == int(np.argmax(want)) and err <= TC_LOGIT_TOL, f"{ftype} rows={rows}: max|dlogit|={err:.3e}"
+        M.set_tc_min_rows(0)
+        assert M.eval_path(rows) == 1
+        R.close(); M.close()
 
 
 def test_base_model_headline_greedy_over_whole_context(checkers, capi, zoo):
@@ -361,10 +369,12 @@ def test_base_model_64_token_continuation(checkers, capi, zoo, ftype):
 def test_eval_path_map(capi, zoo):
     """which schedule a (model, rows) pair takes: only quantised evals of 112+ rows leave the bit-exact kernels"""
     M = capi.Model.load(zoo.path("narrow", "q5_1"), max_batch=128)
-    assert [M.eval_path(n) for n in (1, 2, 8, 111, 112, 128)] == [3, 1, 1, 1, 2, 2]
+    assert [M.eval_path(n) for n in (1, 2, 8, 111, 112, 128, 1024)] == [3, 1, 1, 1, 1, 1, 1]
+    M.set_tc_min_rows(112)
+    assert [M.eval_path(n) for n in (1, 8, 111, 112, 128)] == [3, 1, 1, 2, 2]
     M.close()
     M = capi.Model.load(zoo.path("small", "q4_0"), max_batch=128)          # not BioGPT-base layer shapes: no skinny schedule
-    assert [M.eval_path(n) for n in (1, 2, 32, 111, 112)] == [3, 0, 0, 0, 2]
+    assert [M.eval_path(n) for n in (1, 2, 32, 111, 112)] == [3, 0, 0, 0, 0]
     M.close()
     M = capi.Model.load(zoo.path("small", "f16"), max_batch=128)           # F16 never uses the integer tensor-core matmul
     assert [M.eval_path(n) for n in (1, 8, 112)] == [3, 0, 0]

@@ -11,6 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <cstring>
+#include <time.h>
+#include <unistd.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); exit(1); } } while (0)
 #define NT 512
@@ -173,7 +176,23 @@ static double med_cycles(const long long * d_cyc, int n) {
 }
 static int aborted() { int v = 0; CK(cudaMemcpyFromSymbol(&v, g_abort, sizeof v)); if (v) { int z = 0; CK(cudaMemcpyToSymbol(g_abort, &z, sizeof z)); } return v; }
 
-int main() {
+// run one kernel with a host-side deadline: a kernel that is still running after 8 s is reported and the process exits
+// (destroying the context is the only way to stop it)
+static cudaError_t sync_with_deadline(const char * what) {
+    cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); CK(cudaEventRecord(ev, 0));
+    for (int ms = 0; ms < 8000; ms += 5) {
+        cudaError_t e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady) { cudaEventDestroy(ev); return e; }
+        struct timespec ts = { 0, 5000000 }; nanosleep(&ts, nullptr);
+    }
+    printf("HUNG: %s did not finish within 8 s -- exiting\n", what); fflush(stdout);
+    _exit(3);
+}
+
+int main(int argc, char ** argv) {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
+    const char * only = argc > 1 ? argv[1] : "";          // "", "T1", "T2", "T3", "T4", "T5"
+    auto want = [&](const char * t) { return !only[0] || !strcmp(only, t); };
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
     const double ghz = khz / 1e6;
@@ -202,25 +221,25 @@ int main() {
     }
     const int iters = 2000;
     // ---- T2: cluster barrier
-    for (int CL : {2, 4, 8}) {
+    if (want("T2")) for (int CL : {2, 4, 8}) {
         if (maxcl[CL] <= 0) continue;
         int it = iters; void * args[] = { &it, &d_cyc };
         const int grid = maxcl[CL] * CL;
         cudaError_t e = launch((const void *) k_clsync, grid, CL, 0, args, false);
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = sync_with_deadline("kernel");
         printf("T2 barrier.cluster arrive+wait, cluster %d, grid %d: %.0f cycles = %.0f ns per barrier (%s)\n", CL, grid, med_cycles(d_cyc, grid) / iters,
                med_cycles(d_cyc, grid) / iters / ghz, cudaGetErrorString(e));
     }
     // ---- T5: cluster + cooperative attribute together
-    {
+    if (want("T5")) {
         int it = 10; void * args[] = { &it, &d_cyc };
         cudaError_t e = launch((const void *) k_clsync, std::max(1, maxcl[8]) * 8, 8, 0, args, true);
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = sync_with_deadline("kernel");
         printf("T5 cluster 8 + cooperative launch attribute: %s\n", cudaGetErrorString(e));
         cudaGetLastError();
     }
     // ---- T3: DSMEM all-gather
-    for (int CL : {2, 4, 8}) {
+    if (want("T3")) for (int CL : {2, 4, 8}) {
         if (maxcl[CL] <= 0) continue;
         for (int words : {8, 16, 64, 128}) {
             int it = iters, cl = CL, w = words; void * args[] = { &cl, &w, &it, &d_cyc, &d_sink };
@@ -228,19 +247,19 @@ int main() {
             CK(cudaFuncSetAttribute((const void *) k_allgather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             const int grid = maxcl[CL] * CL;
             cudaError_t e = launch((const void *) k_allgather, grid, CL, std::max(smem, (size_t) 200 * 1024), args, false);
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e == cudaSuccess) e = sync_with_deadline("kernel");
             const int ab = aborted();
             printf("T3 DSMEM all-gather, cluster %d, %4d B per source, grid %d: %.0f cycles = %.0f ns per round%s (%s)\n", CL, words * 8, grid,
                    med_cycles(d_cyc, grid) / iters, med_cycles(d_cyc, grid) / iters / ghz, ab ? " TIMEOUT" : "", cudaGetErrorString(e));
         }
     }
     // ---- T4: L2 exchange, direct vs cluster-forwarded
-    for (int R : {8, 16}) {
+    if (want("T4")) for (int R : {8, 16}) {
         for (int grid0 : {148, 128}) {
             int it = iters, cl = 1, r = R; void * args[] = { &cl, &r, &d_x, &it, &d_cyc, &d_sink };
             CK(cudaMemset(d_x, 0, 2 * 32 * 1024 * sizeof(unsigned long long)));
             cudaError_t e = launch((const void *) k_xch<0>, grid0, 1, 0, args, true);
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e == cudaSuccess) e = sync_with_deadline("kernel");
             const int ab = aborted();
             printf("T4 L2 exchange, every CTA polls 8 KB, R=%d, grid %d (no clusters): %.0f ns per exchange%s (%s)\n", R, grid0, med_cycles(d_cyc, grid0) / iters / ghz,
                    ab ? " TIMEOUT" : "", cudaGetErrorString(e));
@@ -252,7 +271,7 @@ int main() {
                 int it = iters, cl = CL, r = R; void * args[] = { &cl, &r, &d_x, &it, &d_cyc, &d_sink };
                 CK(cudaMemset(d_x, 0, 2 * 32 * 1024 * sizeof(unsigned long long)));
                 cudaError_t e = launch(mode ? (const void *) k_xch<1> : (const void *) k_xch<0>, grid, CL, 0, args, false);
-                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+                if (e == cudaSuccess) e = sync_with_deadline("kernel");
                 const int ab = aborted();
                 printf("T4 L2 exchange, %s, R=%d, cluster %d, grid %d: %.0f ns per exchange%s (%s)\n", mode ? "rank polls 1/CL and forwards by DSMEM" : "every CTA polls 8 KB",
                        R, CL, grid, med_cycles(d_cyc, grid) / iters / ghz, ab ? " TIMEOUT" : "", cudaGetErrorString(e));

@@ -1,0 +1,29 @@
+#!/bin/bash
+# round-2 GPU visits: bash tools/gpu_r2.sh <tag> <stages...>
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+for st in "$@"; do
+case $st in
+probe)
+  for t in T1 T2 T5 T3 T4; do timeout 40 tools/_build/cluster_probe $t >> $OUT/cluster_probe.log 2>&1; echo "probe $t rc=$?" >> $OUT/cluster_probe.log; done; cat $OUT/cluster_probe.log ;;
+tests)
+  timeout 2400 python -m pytest tests -m gpu -q --maxfail=12 -s > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+  grep -E "passed|failed|FAILED|Error|max\|d|tcgen05 prompt" $OUT/pytest_gpu.log | tail -40 ;;
+newtests)
+  timeout 1800 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=12 -s -k "tensor_core or base_model or eval_path" > $OUT/pytest_new.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_new.log
+  grep -E "passed|failed|FAILED|Error|max\|d|tcgen05 prompt" $OUT/pytest_new.log | tail -40 ;;
+smoke)
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
+  tail -5 $OUT/smoke.log ;;
+bench)
+  timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+  cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
+trace5)
+  for np in 4 511 1020; do BGPT_MEGA_PROF=1 timeout 200 python tools/trace_decode.py --n-past $np; done > $OUT/trace.log 2>&1; grep -v "Warning\|nanm\|return np" $OUT/trace.log | head -150 ;;
+decode)
+  for ft in ${FTYPES:-q4_0}; do for np in 0 511 1023; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
+  cat $OUT/decode.log ;;
+esac
+done
