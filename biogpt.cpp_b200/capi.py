@@ -212,7 +212,7 @@ class Model:
         return out
 
     def set_decode_path(self, path: int):
-        """1: persistent kernel per token (default), 0: one kernel per fused operator"""
+        """1: persistent kernel per token, newest generation (default); 3: generation 4; 2: generation 3; 0: one kernel per fused operator"""
         _check(lib().bgpt_cuda_set_decode_path(self.h, path), "set_decode_path")
 
     def set_batch_path(self, path: int):
@@ -245,7 +245,7 @@ class Model:
 
     @property
     def decode_generation(self) -> int:
-        """4 / 3: persistent-kernel generation used for single-token steps; 0: per-operator kernels"""
+        """5 / 4 / 3: persistent-kernel generation used for single-token steps; 0: per-operator kernels"""
         return int(lib().bgpt_cuda_decode_kernel_generation(self.h))
 
     def read_prof(self):

@@ -22,6 +22,7 @@
 #include "bgpt_kernels.cuh"
 #include "bgpt_mega.cuh"
 #include "bgpt_mega4.cuh"
+#include "bgpt_mega5.cuh"
 #ifdef BGPT_BENCH_TOOLS
 #include "bgpt_barbench.cuh"      // micro-benchmarks: only in libbgpt_cuda_tools.so (make tools), never in the product library
 #endif
@@ -114,6 +115,10 @@ struct bgpt_model {
     // generation-4 persistent kernel (bgpt_mega4.cuh): tagged-word exchange, no grid barrier
     bool mega4_ok = false; M4Params m4{}; unsigned long long * d_xch = nullptr; unsigned int m4_tag = 0;
     long long * d_trace = nullptr; size_t trace_n = 0;
+    // generation-5 persistent kernel (bgpt_mega5.cuh): clusters of 4, one attention head per cluster, DSMEM exchange inside the head
+    bool mega5_ok = false; M5Params m5{}; unsigned long long * d_xch5 = nullptr; unsigned int m5_tag = 0;
+    int * d_err5 = nullptr; int * h_err5 = nullptr; long long * d_trace5 = nullptr; size_t trace5_n = 0;
+    int mega_gen_pref = 5;                               // highest generation allowed (BGPT_MEGA_V / bgpt_cuda_set_decode_path)
     // per-operator schedule replayed as a CUDA graph, one per (rows, mode, token buffer): every kernel reads n_past from m->st
     struct FwdGraph { cudaGraphExec_t exec; uint64_t launches; };
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
@@ -215,6 +220,8 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     free_arena(m);
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
     cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch); cudaFree(m->d_trace);
+    cudaFree(m->d_xch5); cudaFree(m->d_err5); cudaFree(m->d_trace5);
+    if (m->h_err5) cudaFreeHost(m->h_err5);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
     if (m->ev0) cudaEventDestroy(m->ev0);
@@ -327,6 +334,7 @@ static void init_kernel_attrs() {
 
 static int mega_setup(bgpt_model * m);
 static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop);
+static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop);
 
 extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (!m) return fail(BGPT_E_ARG, "finalize: NULL model");
@@ -875,6 +883,7 @@ static int mega_setup(bgpt_model * m) {
     const char * e = getenv("BGPT_DECODE_PATH");
     if (e) m->decode_path = atoi(e);
     if (m->mega_ok) RET(mega4_setup(m, prop));
+    if (m->mega_ok) RET(mega5_setup(m, prop));
     return BGPT_OK;
 }
 
@@ -935,10 +944,113 @@ static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     return BGPT_OK;
 }
 
+// generation 5: quantised weights at BioGPT-base shapes on a device that co-schedules 32 clusters of 4 CTAs (bgpt_mega5.cuh)
+static int launch_cluster_kernel(const void * fn, int grid, int threads, int cluster, size_t smem, cudaStream_t s, void ** args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;       // all CTAs co-resident: they spin on each other's words
+    cfg.attrs = at; cfg.numAttrs = 2;
+    CK(cudaLaunchKernelExC(&cfg, fn, args));
+    return BGPT_OK;
+}
+static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
+    m->mega5_ok = false;
+    const bool prof = m->d_prof != nullptr;
+    const void * fn = bgpt_k_mega5_fn(m->wtype, prof);
+    static_assert(sizeof(M5Params) <= 4096, "M5Params must fit the 4 KB kernel parameter space");
+    if (!fn || m->n_layer > M5_MAXL || m->d_model != M5_D || m->d_ff != M5_FF || m->n_head != M5_NH || m->n_positions > 1024 ||
+        prop.multiProcessorCount < M5_NC || m->n_vocab < M5_NC) return BGPT_OK;
+    M5Params & P = m->m5;
+    P.b = m->mp;
+    for (int i = 0; i < m->n_layer; i++) P.layers[i] = m->h_mega_layers[i];
+    auto al = [](int x) { return (x + 127) & ~127; };
+    const int sd = P.b.stride_d, sf = P.b.stride_f;
+    const int fixed = al(P.b.actb_d) + al(P.b.actb_f) + 2 * al(M5_D * 4) + al(m->n_positions * 4) + al(32 * M5_HR * 4) + al(31 * M5_HR * 4);
+    const int lim = (int) prop.sharedMemPerBlockOptin - 2048;             // static shared memory + margin
+    P.lmrt = 64; P.nslot = M4_NSLOT;
+    auto slot_for = [&](int lmrt) { return al(std::max(std::max(32 * sd, 8 * sf), std::max(3 * M5_HR, lmrt) * sd)); };
+    if (P.nslot * slot_for(64) + fixed > lim) P.lmrt = 32;
+    P.slot_bytes = slot_for(P.lmrt);
+    while (P.nslot > 2 && P.nslot * P.slot_bytes + fixed > lim) P.nslot--;
+    if (P.nslot * P.slot_bytes + fixed > lim) return BGPT_OK;
+    if (getenv("BGPT_M5_LMRT")) { const int v = atoi(getenv("BGPT_M5_LMRT")); if ((v == 32 || v == 64) && v <= P.lmrt) { P.lmrt = v; P.slot_bytes = slot_for(v); } }
+    int o = 0;
+    P.sm_w = o; o += P.nslot * P.slot_bytes;
+    P.sm_rec0 = o; o += al(P.b.actb_d);
+    P.sm_rec1 = o; o += al(P.b.actb_f);
+    P.sm_x = o; o += al(M5_D * 4);
+    P.sm_x1 = o; o += al(M5_D * 4);
+    P.sm_sc = o; o += al(m->n_positions * 4);
+    P.sm_red = o; o += al(32 * M5_HR * 4);
+    P.sm_tail = o; o += al(31 * M5_HR * 4);
+    P.sm_total = o;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sm_total));
+    {   // 32 clusters of 4 must be co-resident
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(M5_NC); cfg.blockDim = dim3(M5_NT); cfg.dynamicSmemBytes = (size_t) P.sm_total;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = M5_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl * M5_CL < M5_NC) { cudaGetLastError(); return BGPT_OK; }
+    }
+    const size_t xb = (size_t) 2 * M5_LW * sizeof(unsigned long long);
+    CK(cudaMalloc(&m->d_xch5, xb)); CK(cudaMemset(m->d_xch5, 0, xb));
+    CK(cudaMalloc(&m->d_err5, sizeof(int))); CK(cudaMemset(m->d_err5, 0, sizeof(int)));
+    CK(cudaMallocHost(&m->h_err5, sizeof(int))); *m->h_err5 = 0;
+    P.xch = m->d_xch5; P.err = m->d_err5;
+    P.trace = nullptr; P.prof_n = (m->n_layer + 1) * 5 * M5_PK;
+    if (prof) {
+        m->trace5_n = (size_t) M5_NC * P.prof_n + 4 * (size_t) M5_NC;
+        CK(cudaMalloc(&m->d_trace5, m->trace5_n * sizeof(long long))); CK(cudaMemset(m->d_trace5, 0, m->trace5_n * sizeof(long long)));
+        P.trace = m->d_trace5;
+    }
+    m->m5_tag = 0;
+    const char * e3 = getenv("BGPT_MEGA_V");
+    if (e3 && atoi(e3) >= 3 && atoi(e3) <= 5) m->mega_gen_pref = atoi(e3);
+    m->mega5_ok = true;
+    return BGPT_OK;
+}
+static int mega_generation(const bgpt_model * m) {
+    if (!m->mega_ok || m->decode_path < 1) return 0;
+    if (m->decode_path == 2) return 3;
+    if (m->decode_path == 3) return m->mega4_ok ? 4 : 3;
+    if (m->mega5_ok && m->mega_gen_pref >= 5) return 5;
+    if (m->mega4_ok && m->mega_gen_pref >= 4) return 4;
+    return 3;
+}
+// a watchdog code left by the generation-5 kernel (checked after the stream has been synchronised)
+static int check_mega5_error(bgpt_model * m) {
+    if (!m->mega5_ok) return BGPT_OK;
+    int code = 0;
+    CK(cudaMemcpy(&code, m->d_err5, sizeof(int), cudaMemcpyDeviceToHost));
+    if (code == 0) return BGPT_OK;
+    CK(cudaMemset(m->d_err5, 0, sizeof(int)));
+    return fail(BGPT_E_CUDA, "persistent decode kernel (generation 5): a wait timed out -- stage %d, layer %d, wait %d; results are invalid",
+                code >> 16, (code >> 8) & 0xff, code & 0xff);
+}
+
 // one token at n_past on the persistent kernel.  token source: d_tok (device) or the previous
 // launch's argmax candidates (use_cand).  Asynchronous on the model's stream.
 static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot, int tok_imm = 0) {
-    if (m->mega4_ok && m->decode_path == 1) {
+    const int gen = mega_generation(m);
+    if (gen == 5) {
+        M5Params P = m->m5;
+        MegaParams & q = P.b;
+        q.kcache = m->kcache; q.vcache = m->vcache; q.logits = m->logits;
+        q.x = m->x; q.x1 = m->x1; q.q = m->q; q.att = m->att; q.hff = m->hff;
+        q.tok = d_tok; q.use_cand = use_cand; q.tok_imm = tok_imm; q.idlog = m->d_idlog; q.log_slot = log_slot; q.n_past = n_past;
+        q.n_cand = M5_NC;
+        if (++m->m5_tag >= (1u << 26)) m->m5_tag = 1;        // 0 is the "never written" tag of a fresh buffer
+        P.tag = m->m5_tag << 6;
+        void * args[] = { &P };
+        RET(launch_cluster_kernel(bgpt_k_mega5_fn(m->wtype, m->d_trace5 != nullptr), M5_NC, M5_NT, M5_CL, (size_t) P.sm_total, m->stream, args));
+        m->launches++;
+        return BGPT_OK;
+    }
+    if (gen == 4) {
         M4Params P = m->m4;
         MegaParams & q = P.b;
         q.kcache = m->kcache; q.vcache = m->vcache; q.logits = m->logits;
@@ -966,7 +1078,7 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
 static bool use_mega(const bgpt_model * m) { return m->mega_ok && m->decode_path >= 1 && !m->taps_armed; }
 
 extern "C" int bgpt_cuda_set_decode_path(bgpt_model * m, int path) {
-    if (!m || path < 0 || path > 2) return fail(BGPT_E_ARG, "set_decode_path: path must be 0 (per-op kernels), 1 (persistent kernel) or 2 (persistent kernel with grid barriers)");
+    if (!m || path < 0 || path > 3) return fail(BGPT_E_ARG, "set_decode_path: path must be 0 (per-op kernels), 1 (persistent kernel, newest generation), 2 (generation 3: grid barriers) or 3 (generation 4)");
     if (path >= 1 && !m->mega_ok) return fail(BGPT_E_UNSUPPORTED, "set_decode_path: the persistent kernel is not available for this model/device");
     m->decode_path = path;
     return BGPT_OK;
@@ -978,25 +1090,27 @@ extern "C" int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int ca
     const int n = cap < m->prof_n ? cap : m->prof_n;
     cudaStreamSynchronize(m->stream);
     const long long * src = m->d_prof;
-    if (m->mega4_ok && m->decode_path == 1) return 0;      // generation 4 records every CTA: bgpt_cuda_debug_read_trace
+    if (mega_generation(m) >= 4) return 0;                  // generations 4 and 5 record every CTA: bgpt_cuda_debug_read_trace
     if (cudaMemcpy(out, src, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
 }
 // debug: generation-4 kernel, stamps of EVERY CTA: [n_cta][prof_n] then [n_cta][4] = {globaltimer ns, clock64} at the
 // start and at the end of the launch (clock64 is per SM; the pairs put all CTAs on one time axis)
 extern "C" int bgpt_cuda_debug_read_trace(bgpt_model * m, long long * out, int cap, int * n_cta, int * per_cta) {
-    if (!m || !m->d_trace || !out) return 0;
-    if ((size_t) cap < m->trace_n) return 0;
+    if (!m || !out) return 0;
+    const bool g5 = mega_generation(m) == 5;
+    const long long * src = g5 ? m->d_trace5 : m->d_trace;
+    const size_t n = g5 ? m->trace5_n : m->trace_n;
+    if (!src || (size_t) cap < n) return 0;
     cudaStreamSynchronize(m->stream);
-    if (cudaMemcpy(out, m->d_trace, m->trace_n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-    if (n_cta) *n_cta = m->mega_grid;
-    if (per_cta) *per_cta = m->m4.prof_n;
-    return (int) m->trace_n;
+    if (cudaMemcpy(out, src, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (n_cta) *n_cta = g5 ? M5_NC : m->mega_grid;
+    if (per_cta) *per_cta = g5 ? m->m5.prof_n : m->m4.prof_n;
+    return (int) n;
 }
 extern "C" int bgpt_cuda_get_decode_path(const bgpt_model * m) { return m && m->mega_ok && m->decode_path >= 1 ? m->decode_path : 0; }
 extern "C" int bgpt_cuda_decode_kernel_generation(const bgpt_model * m) {
-    if (!m || !m->mega_ok || m->decode_path < 1) return 0;
-    return (m->mega4_ok && m->decode_path == 1) ? 4 : 3;
+    return m ? mega_generation(m) : 0;
 }
 
 static int check_eval_args(bgpt_model * m, int n, int n_past, int rows_of_stream) {
@@ -1042,6 +1156,7 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    if (n == 1 && use_mega(m) && mega_generation(m) == 5) RET(check_mega5_error(m));
     memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
     RET(fetch_taps(m, n));
     return BGPT_OK;
@@ -1092,7 +1207,7 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
     if (use_mega(m)) {
         for (int i = 0; i < n_steps; i++) RET(launch_mega(m, m->d_tokens, i > 0, n_past + i, i - 1));
         {
-            int slot = n_steps - 1, n_cand = m->mega_grid;
+            int slot = n_steps - 1, n_cand = mega_generation(m) == 5 ? M5_NC : m->mega_grid;
             void * pargs[] = { &m->d_cand_val, &m->d_cand_idx, &n_cand, &m->d_idlog, &slot, &m->d_tokens };
             CK(cudaLaunchKernel(bgpt_k_mega_pick_fn(), dim3(1), dim3(32), pargs, 0, s));
         }
@@ -1110,6 +1225,7 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
     CK(cudaMemcpyAsync(m->h_idlog, m->d_idlog, (size_t) n_steps * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    if (use_mega(m) && mega_generation(m) == 5) RET(check_mega5_error(m));
     memcpy(ids_out, m->h_idlog, (size_t) n_steps * sizeof(int));
     if (ms_out) *ms_out = m->last_ms;
     return BGPT_OK;

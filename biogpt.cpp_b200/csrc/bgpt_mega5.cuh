@@ -1,0 +1,669 @@
+// bgpt_mega5.cuh -- persistent decode kernel, generation 5 (quantised weights, BioGPT-base shapes: d_model 1024, 16 heads of 64,
+// d_ff 4096, n_positions <= 1024).  One launch per token; 128 CTAs of 512 threads in 32 thread-block CLUSTERS of 4.
+//
+// Generation 4 (bgpt_mega4.cuh) removed the grid barriers; its trace (profiles/r1_mega4_trace.log) shows what was left of the
+// 18 us per layer: five all-to-all exchanges through L2 (~0.9 us each), dot products that were instruction-issue bound (a relay
+// of the 8 running sums along the lanes executed 8 predicated steps: 0.9 us for 2 rows per warp), and an attention stage whose
+// 32 CTAs each scored every cached position.  Generation 5 changes the decomposition (measurements behind the choices:
+// tools/cluster_probe.cu, profiles/r2_cluster_probe.log):
+//
+//  1. One attention head = one cluster of 4 CTAs (clusters 0..15; 15 clusters of 8 is all a B200 co-schedules at one CTA per SM,
+//     33 clusters of 4 fit).  The CTAs of cluster h compute the q, k, v rows of head h (16 rows of each per CTA) and its
+//     attention; q and the new k travel to the 4 CTAs of the cluster through DISTRIBUTED SHARED MEMORY (st.shared::cluster +
+//     barrier.cluster, 0.24 us) instead of L2 tagged words (~0.9 us); the T scores are computed once (T/4 per CTA; generation
+//     4: T per CTA) and all-gathered the same way; every CTA reduces V for its own 16 columns, whose new row it computed itself.
+//     Four exchanges through L2 per layer remain (attention output, x1, the GELU blocks, x); they are inherent: every CTA's next
+//     dot product needs the whole vector.  128 CTAs instead of 148: an all-to-all exchange is faster with fewer pollers (1.17
+//     against 1.68 us per round in the probe) and every stage divides evenly (8 rows, one fc1 block per CTA).
+//  2. Dot products in chain order with no relay: lane (row, l) of a warp owns running sum l of one weight row (4 rows per warp)
+//     and walks the 32 (128) blocks in order -- dp4a, int -> float, fma -- straight from the shared-memory weight tile; the only
+//     cross-lane step is hsum_float_8 (3 shuffles).  ~230 instructions per lane for K = 1024 against ~450 for the relay.
+//  3. Every wait carries a watchdog: a lost signal ends the launch with an error code instead of hanging the GPU.
+//
+//  stage (per layer)           CTAs, rows                         consumes                       publishes
+//  P1 LN0 + q,k,v              0..63, 16 + 16 + 16 rows of a head  E5[l-1] x (L2)                 q, k -> cluster (DSMEM); k, v -> KV cache
+//  P2 attention                0..63, T/4 scores + 16 V columns    q, k, scores (DSMEM)           E2: 16 f32 attention outputs (L2, R replicas)
+//  P3 out_proj + bias + res    all, 8 rows                         E2 (every CTA quantises it)    E3: x1 (L2)
+//  P4 LN1 + fc1 + bias + GELU  all, 32 rows = one block            E3                             E4: one quantised block (L2)
+//  P5 fc2 + bias + residual    all, 8 rows (K = 4096)              E4                             E5: x (L2)
+//  final LN + lm_head          all, 331-332 rows in tiles          E5[L-1]                        logits, per-CTA argmax candidate
+//
+// Arithmetic: identical to generations 3 and 4 and to the reference (bgpt_cuda.cu, "lane order"); tests/test_gpu_eval.py compares
+// the three generations with each other and with the oracle bit for bit.
+#pragma once
+#include "bgpt_mega4.cuh"
+
+#define M5_NT 512
+#define M5_NW (M5_NT / 32)
+#define M5_CL 4               // CTAs per cluster; clusters 0..15 own one attention head each
+#define M5_NC 128             // CTAs per launch (32 clusters)
+#define M5_HC (M5_NH * M5_CL) // CTAs 0..63 run P1 / P2
+#define M5_HR (M5_DK / M5_CL) // q (k, v) rows = attention columns per head CTA: 16
+#define M5_R 8                // replicas of an L2 exchange buffer
+#define M5_D 1024
+#define M5_FF 4096
+#define M5_DK 64
+#define M5_NH 16
+#define M5_NB_F (M5_FF / 32)
+// L2 exchange words per layer parity
+#define M5_E2 0
+#define M5_E3 (M5_E2 + M5_R * M5_D)
+#define M5_E4 (M5_E3 + M5_R * M5_D)
+#define M5_E5 (M5_E4 + M5_R * M5_NB_F * 10)
+#define M5_LW (M5_E5 + M5_R * M5_D)
+#define M5_MAXL 24
+#define M5_PK 12              // trace stamps per (layer, stage)
+#define M5_WATCHDOG 300000000LL   // cycles (~0.15 s) before a wait gives up
+
+struct M5Params {
+    MegaParams b;
+    MegaLayer layers[M5_MAXL];
+    unsigned long long * xch;      // [2][M5_LW] tagged words (layer parity)
+    unsigned int tag;              // launch serial << 6 (never 0); a word's tag = tag | (layer + 1)
+    int * err;                     // device: 0, or the code of the first wait that timed out (stage << 16 | layer << 8 | 1)
+    long long * trace;             // BGPT_MEGA_PROF: [nC][prof_n] clock64 stamps, then [nC][4] clock calibration
+    int prof_n;
+    int nslot, slot_bytes, lmrt;   // weight ring: slots, bytes per slot, lm_head rows per tile (32 or 64)
+    int sm_w, sm_rec0, sm_rec1, sm_x, sm_x1, sm_sc, sm_red, sm_tail, sm_total;
+};
+
+// ---- cluster / DSMEM -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t m5_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t m5_mapa(uint32_t addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ void m5_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void m5_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void m5_cluster_wait()   { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// the same 32-bit value to the same shared-memory offset in all M5_CL CTAs of the cluster (visible after the next cluster barrier)
+__device__ __forceinline__ void m5_bcast32(const void * local_dst, uint32_t v) {
+    const uint32_t la = m4_s32(local_dst);
+#pragma unroll
+    for (uint32_t r = 0; r < M5_CL; r++) asm volatile("st.shared::cluster.b32 [%0], %1;" :: "r"(m5_mapa(la, r)), "r"(v) : "memory");
+}
+
+// ---- waits with a watchdog ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool m5_give_up(int * err, int code, long long t0) {
+    if (*(volatile int *) err != 0) return true;
+    if (clock64() - t0 > M5_WATCHDOG) { atomicCAS(err, 0, code); return true; }
+    return false;
+}
+__device__ __forceinline__ void m5_poll2(const unsigned long long * p, uint32_t tag, uint32_t & a, uint32_t & b, int * err, int code) {
+    unsigned long long w0, w1;
+    unsigned spins = 0; long long t0 = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+        if ((uint32_t) (w0 >> 32) == tag && (uint32_t) (w1 >> 32) == tag) break;
+        if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, code, t0)) break; }
+    }
+    a = (uint32_t) w0; b = (uint32_t) w1;
+}
+__device__ __forceinline__ void m5_mbar_wait(uint64_t * bar, uint32_t parity, int * err, int code) {
+    uint32_t done; unsigned spins = 0; long long t0 = 0;
+    const uint32_t a = m4_s32(bar);
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        if ((++spins & 63u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, code, t0)) break; }
+    }
+}
+
+// ---- activation quantiser on registers: thread t owns elements 2t, 2t+1 of a 1024-wide row ----------------------------------
+// (ggml.c:1166-1203, 1403-1450: d = amax / 127, id = 127 / amax, round to nearest even; Q8_0 rounds d through fp16.)
+// Writes the int8 words [g][l][i], the folded code offsets, d and s of the record.  Ends WITHOUT a barrier.
+template <int FMT>
+__device__ __forceinline__ void m5_quant_pair(float y0, float y1, uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
+    constexpr bool Q81 = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    constexpr bool HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
+    const int tid = threadIdx.x;
+    float amax = fmaxf(fabsf(y0), fabsf(y1));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 2));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 4));
+    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 8));
+    const float d  = __fdiv_rn(amax, 127.0f);
+    const float id = (amax != 0.0f) ? __fdiv_rn(127.0f, amax) : 0.0f;
+    const int q0 = __float2int_rn(__fmul_rn(y0, id)), q1 = __float2int_rn(__fmul_rn(y1, id));
+    const uint32_t hw = ((uint32_t) q0 & 0xFFu) | (((uint32_t) q1 & 0xFFu) << 8);
+    const int ps = q0 + q1;
+    const uint32_t hw_p = __shfl_xor_sync(FULLMASK, hw, 1);
+    const int ps_p = __shfl_xor_sync(FULLMASK, ps, 1);
+    const int b = tid >> 4, g = b >> 2, i = b & 3;
+    if ((tid & 1) == 0) {
+        const int l = (tid & 15) >> 1;
+        ((uint32_t *) rec)[(g * 8 + l) * 4 + i] = hw | (hw_p << 16);
+        if (HASOFF) ((int *) (rec + off_n))[(g * 8 + l) * 4 + i] = -code_off * (ps + ps_p);
+    }
+    if (Q81) {
+        int stot = ps;
+        stot += __shfl_xor_sync(FULLMASK, stot, 1);
+        stot += __shfl_xor_sync(FULLMASK, stot, 2);
+        stot += __shfl_xor_sync(FULLMASK, stot, 4);
+        stot += __shfl_xor_sync(FULLMASK, stot, 8);
+        if ((tid & 15) == 0) { ((float *) (rec + off_d))[b] = d; ((float *) (rec + off_s))[b] = __fmul_rn(d, (float) stot); }
+    } else if ((tid & 15) == 0) { ((float *) (rec + off_d))[b] = bg_h2f(bg_f2h(d)); ((float *) (rec + off_s))[b] = 0.0f; }
+}
+
+// LayerNorm + affine on registers (ggml.c:11403-11420 then mul, add): same operations as m4_ln_quant; the double sums are
+// combined in a parallel order.  Two block barriers inside.
+__device__ __forceinline__ void m5_layer_norm(float v0, float v1, float2 lw, float2 lb, float eps, double * sredA, double * sredB, float & y0, float & y1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double s = m4_warp_sum_f64((double) v0 + (double) v1);
+    if (lane == 0) sredA[warp] = s;
+    __syncthreads();
+    const float mean = (float) (m4_tree16(sredA) * (1.0 / M5_D));
+    const float e0 = __fsub_rn(v0, mean), e1 = __fsub_rn(v1, mean);
+    const double s2 = m4_warp_sum_f64((double) __fmul_rn(e0, e0) + (double) __fmul_rn(e1, e1));
+    if (lane == 0) sredB[warp] = s2;
+    __syncthreads();
+    const float variance = (float) (m4_tree16(sredB) * (1.0 / M5_D));
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
+    y0 = __fadd_rn(__fmul_rn(lw.x, __fmul_rn(e0, scale)), lb.x);
+    y1 = __fadd_rn(__fmul_rn(lw.y, __fmul_rn(e1, scale)), lb.y);
+}
+
+// ---- one weight row x the activation record, running sum l of the row in this lane -----------------------------------------------
+// The reference (AVX2: ggml.c:2518-2541, 2824-2857, 3071-3093, 3386-3411, 3597-3618) keeps 8 running sums per row: sum l takes the
+// elements 4l..4l+3 of every 32-block, acc_l = fma(d_w * d_a, (float) isum_l, acc_l) in block order; Q4_1 / Q5_1 add the chain
+// summs = fma(m_w, s_a, summs); the result is hsum_float_8 (+ summs).  Lanes 8q..8q+7 of a warp hold the 8 sums of one row; every
+// lane of the warp must call (shuffles); the finished dot is in all 8 lanes of the row.
+template <int FMT, int G>
+__device__ __forceinline__ float m5_row_dot(const uint8_t * wrow, const uint8_t * rec, const M4MM & D) {
+    constexpr bool IS8    = (FMT == BG_Q8_0);
+    constexpr bool HASQH  = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM   = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    constexpr bool HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
+    const int l = threadIdx.x & 7, j = l & 3, hi = l >> 2, sh = hi * 4;
+    float acc = 0.0f, summ = 0.0f;
+#pragma unroll 4
+    for (int g = 0; g < G; g++) {
+        const uint4 wq = IS8 ? *(const uint4 *) (wrow + ((g * 2 + hi) * 4 + j) * 16) : *(const uint4 *) (wrow + (g * 4 + j) * 16);
+        uint32_t qh = 0;
+        if (HASQH) qh = *(const uint32_t *) (wrow + D.off_qh + (g * 4 + j) * 4);
+        const uint4 aw = *(const uint4 *) (rec + (g * 8 + l) * 16);
+        int4 an = make_int4(0, 0, 0, 0);
+        if (HASOFF) an = *(const int4 *) (rec + D.off_n + (g * 8 + l) * 16);
+        const uint2 dh = *(const uint2 *) (wrow + D.off_d + g * 8);
+        const float4 da = *(const float4 *) (rec + D.off_dd + g * 16);
+        const uint32_t ww[4] = { wq.x, wq.y, wq.z, wq.w }, aa[4] = { aw.x, aw.y, aw.z, aw.w };
+        const int nn[4] = { an.x, an.y, an.z, an.w };
+        const float dd[4] = { da.x, da.y, da.z, da.w };
+        const uint16_t dw[4] = { (uint16_t) (dh.x & 0xFFFF), (uint16_t) (dh.x >> 16), (uint16_t) (dh.y & 0xFFFF), (uint16_t) (dh.y >> 16) };
+        uint16_t mw[4] = { 0, 0, 0, 0 }; float ss[4] = { 0.f, 0.f, 0.f, 0.f };
+        if (HASM) {
+            const uint2 mh = *(const uint2 *) (wrow + D.off_m + g * 8);
+            const float4 sa = *(const float4 *) (rec + D.off_s + g * 16);
+            mw[0] = (uint16_t) (mh.x & 0xFFFF); mw[1] = (uint16_t) (mh.x >> 16); mw[2] = (uint16_t) (mh.y & 0xFFFF); mw[3] = (uint16_t) (mh.y >> 16);
+            ss[0] = sa.x; ss[1] = sa.y; ss[2] = sa.z; ss[3] = sa.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t code;
+            if (IS8) code = ww[i];
+            else {
+                code = (ww[i] >> sh) & 0x0F0F0F0Fu;
+                if (HASQH) code |= bg_spread4((qh >> (8 * i + sh)) & 0xFu);
+            }
+            const float p = (float) __dp4a((int) code, (int) aa[i], nn[i]);
+            const float s = __fmul_rn(bg_h2f(dw[i]), dd[i]);
+            acc = fmaf(s, p, acc);
+            if (HASM) summ = fmaf(bg_h2f(mw[i]), ss[i], summ);
+        }
+    }
+    float r = __fadd_rn(acc, __shfl_xor_sync(FULLMASK, acc, 4));
+    r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 1));
+    if (HASM) r = __fadd_rn(r, summ);
+    return r;
+}
+
+// scatter one exchange word (block b, word k) into a quantised record, with the folded code offset
+__device__ __forceinline__ void m5_scatter_word(uint8_t * rec, int off_n, int off_d, int off_s, int code_off, int w, uint32_t v) {
+    const int b = w / 10, k = w - b * 10;
+    if (k < 8) {
+        const int g = b >> 2, i = b & 3;
+        ((uint32_t *) rec)[(g * 8 + k) * 4 + i] = v;
+        if (code_off) ((int *) (rec + off_n))[(g * 8 + k) * 4 + i] = -code_off * __dp4a((int) v, 0x01010101, 0);
+    } else if (k == 8) ((float *) (rec + off_d))[b] = __uint_as_float(v);
+    else               ((float *) (rec + off_s))[b] = __uint_as_float(v);
+}
+
+#define M5PROF(ph, k) do { if (PROF && P.trace && threadIdx.x == 0) P.trace[(size_t) blockIdx.x * P.prof_n + (l * 5 + (ph)) * M5_PK + (k)] = clock64(); } while (0)
+
+template <int FMT, bool PROF>
+__global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Params P) {
+    const MegaParams & p = P.b;
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar[M4_NSLOT];               // weight ring
+    __shared__ double sredA[M5_NW], sredB[M5_NW];
+    __shared__ float sredF[M5_NW];
+    __shared__ __align__(16) float s_blk[32];
+    __shared__ __align__(16) float s_q[M5_DK], s_kn[M5_DK];        // q and the new k row of this head: written by the 4 CTAs of the cluster
+    __shared__ __align__(16) float s_vn[M5_HR];                    // new v values of this CTA's 16 columns
+    __shared__ float s_cv[M5_NW]; __shared__ int s_ci[M5_NW];
+    __shared__ int s_tok;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const bool is_head = cta < M5_HC;                              // clusters 0..15: one attention head each
+    const int head = cta >> 2;
+    const int rank = (int) m5_cluster_rank();                      // == cta & 3 for a 1-D cluster of 4
+    const uint32_t tag0 = P.tag;
+    int * const err = P.err;
+    uint8_t * s_w = smem + P.sm_w;
+    uint8_t * rec0 = smem + P.sm_rec0;
+    uint8_t * rec1 = smem + P.sm_rec1;
+    float * s_x = (float *) (smem + P.sm_x);
+    float * s_x1 = (float *) (smem + P.sm_x1);
+    float * sc = (float *) (smem + P.sm_sc);                       // [n_positions] scores / probabilities of this head
+    float * red = (float *) (smem + P.sm_red);                     // [32][16]
+    float * tailv = (float *) (smem + P.sm_tail);                  // [31][16]
+
+    const int n_pos = p.n_positions;
+    const int o0 = cta * 8;                                        // out_proj / fc2 rows
+    const int hrow0 = (head & (M5_NH - 1)) * M5_DK + rank * M5_HR; // first of this CTA's 16 q / k / v rows (= its 16 attention columns)
+    const unsigned uC = (unsigned) M5_NC, uc = (unsigned) cta;
+    const int v0 = (int) ((uc * (unsigned) p.n_vocab) / uC), v1 = (int) (((uc + 1u) * (unsigned) p.n_vocab) / uC);
+    const int n_lm = (v1 - v0 + P.lmrt - 1) / P.lmrt;
+    const int n_lt = 4 * p.n_layer;
+    const int n_tiles = n_lt + n_lm;
+    const int rep = cta % M5_R;
+
+    // ---- weight ring: tile n = layer n>>2, stage n&3 (P1, P3, P4, P5), then the lm_head tiles
+    struct TileSrc { const uint8_t * s0, * s1, * s2; uint32_t b0, b1, b2; };
+    auto describe_tile = [&](int n) -> TileSrc {
+        TileSrc t{nullptr, nullptr, nullptr, 0u, 0u, 0u};
+        if (n >= n_tiles) return t;
+        if (n < n_lt) {
+            const MegaLayer & L = P.layers[n >> 2];
+            const int k = n & 3;
+            if (k == 0) {
+                if (is_head) {
+                    const size_t off = (size_t) hrow0 * p.stride_d;
+                    t.s0 = L.q_w + off; t.s1 = L.k_w + off; t.s2 = L.v_w + off;
+                    t.b0 = t.b1 = t.b2 = (uint32_t) M5_HR * (uint32_t) p.stride_d;
+                }
+            } else if (k == 1) { t.s0 = L.o_w + (size_t) o0 * p.stride_d; t.b0 = 8u * (uint32_t) p.stride_d; }
+            else if (k == 2)   { t.s0 = L.fc1_w + (size_t) cta * 32 * p.stride_d; t.b0 = 32u * (uint32_t) p.stride_d; }
+            else               { t.s0 = L.fc2_w + (size_t) o0 * p.stride_f; t.b0 = 8u * (uint32_t) p.stride_f; }
+        } else {
+            const int r = v0 + (n - n_lt) * P.lmrt;
+            t.s0 = p.lm_head + (size_t) r * p.stride_d; t.b0 = (uint32_t) min(P.lmrt, v1 - r) * (uint32_t) p.stride_d;
+        }
+        return t;
+    };
+    const uint64_t pol_w = m4_policy_evict_first();
+    auto fire_tile = [&](int n, const TileSrc & t) {
+        if (t.b0 == 0) return;
+        const int slot = n % P.nslot;
+        uint8_t * dst = s_w + (size_t) slot * P.slot_bytes;
+        m4_mbar_expect(&mbar[slot], t.b0 + t.b1 + t.b2);
+        m4_bulk_g2s(dst, t.s0, t.b0, &mbar[slot], pol_w);
+        if (t.b1) m4_bulk_g2s(dst + t.b0, t.s1, t.b1, &mbar[slot], pol_w);
+        if (t.b2) m4_bulk_g2s(dst + t.b0 + t.b1, t.s2, t.b2, &mbar[slot], pol_w);
+    };
+    constexpr int ISSUER = M5_NT - 32;
+    uint32_t wphase = 0;
+    if (tid == 0) {
+        for (int i = 0; i < P.nslot; i++) m4_mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == ISSUER) {
+#pragma unroll 1
+        for (int n = 0; n < P.nslot - 1; n++) fire_tile(n, describe_tile(n));
+    }
+
+    const int pos = p.n_past, T = p.n_past + 1;
+    // L2 prefetch of the K/V lines this head reads in layer Ln (2 lines per position and tensor, spread over the cluster) and of
+    // Ln's small f32 vectors
+    auto prefetch_layer = [&](int Ln) {
+        if (Ln >= p.n_layer) return;
+        if (is_head) {
+            const int pr = rank * 512 + tid;
+            const int t = pr >> 1, half = pr & 1;
+            if (t < p.n_past) {
+                const size_t o = (size_t) Ln * n_pos * M5_D + (size_t) t * M5_D + head * M5_DK + half * 32;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p.kcache + o));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p.vcache + o));
+            }
+        }
+        const int who = M5_NC - 1 - cta;                           // 10 vectors of <= 16 KB, one CTA each
+        if (who < 10) {
+            const float * const * vecs = (const float * const *) &P.layers[Ln].q_b;     // q_b .. fc2_b: 10 consecutive pointers
+            const unsigned bytes = (who == 8 ? M5_FF : M5_D) * 4u;                      // fc1_b is the 9th
+#pragma unroll 1
+            for (unsigned off = tid * 128u; off < bytes; off += M5_NT * 128u)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"((const uint8_t *) vecs[who] + off));
+        }
+    };
+    prefetch_layer(0);
+    if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) M5_NC * P.prof_n + 4 * cta);
+
+    // ---- input token: given, or argmax over the candidates the previous launch left
+    if (tid < 32) {
+        int tok;
+        if (p.use_cand == 1) {
+            float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
+            for (int i = tid; i < p.n_cand; i += 32) {
+                const float v = __ldcg(p.cand_val + i); const int ix = __ldcg(p.cand_idx + i);
+                if (v > best || (v == best && ix < bi)) { best = v; bi = ix; }
+            }
+#pragma unroll 1
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULLMASK, best, o); const int oi = __shfl_xor_sync(FULLMASK, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            tok = bi == 0x7fffffff ? 0 : bi;
+        } else tok = p.use_cand == 2 ? p.tok_imm : __ldcg(p.tok);
+        if (tid == 0) {
+            s_tok = tok;
+            if (cta == 0 && p.log_slot >= 0) p.idlog[p.log_slot] = tok;
+        }
+    }
+    // every CTA of the cluster is running (its shared memory exists) before anyone stores into a peer; also publishes s_tok
+    m5_cluster_sync();
+    // ---- embedding: every CTA, elements 2t, 2t+1 in registers
+    float xa, xb;
+    {
+        int tok = s_tok; tok = tok < 0 ? 0 : (tok >= p.n_vocab ? p.n_vocab - 1 : tok);
+        int prow = p.n_past + 2; prow = prow >= p.n_pos_rows ? p.n_pos_rows - 1 : prow;
+        const size_t rb = bg_file_row_bytes(FMT, M5_D);
+        const uint8_t * tr = p.embed_tok + rb * (size_t) tok;
+        const uint8_t * pr = p.embed_pos + rb * (size_t) prow;
+        xa = __fadd_rn(__fmul_rn(bg_dequant_elem(FMT, tr, 2 * tid), p.emb_scale), bg_dequant_elem(FMT, pr, 2 * tid));
+        xb = __fadd_rn(__fmul_rn(bg_dequant_elem(FMT, tr, 2 * tid + 1), p.emb_scale), bg_dequant_elem(FMT, pr, 2 * tid + 1));
+    }
+
+    float best = -INFINITY; int bi = 0x7fffffff;                  // lm_head argmax of this thread's rows
+#pragma unroll 1
+    for (int tn = 0; tn < n_tiles; tn++) {
+        const bool lm = tn >= n_lt;
+        const int kind = lm ? 4 : (tn & 3);                        // 0 P1 (+ attention), 1 P3, 2 P4, 3 P5, 4 lm_head
+        const int l = lm ? p.n_layer : (tn >> 2);
+        const MegaLayer & L = P.layers[lm ? 0 : l];
+        const int lx = lm ? p.n_layer - 1 : l;                     // layer whose exchange buffer (parity) and tag this tile uses
+        unsigned long long * X = P.xch + (size_t) (lx & 1) * M5_LW;
+        const uint32_t tag = tag0 | (uint32_t) (lx + 1);
+        const int wcode = ((kind + 1) << 16) | (lx << 8);          // watchdog code of this tile's waits
+        float * kc = p.kcache + (size_t) (lm ? 0 : l) * n_pos * M5_D;
+        float * vc = p.vcache + (size_t) (lm ? 0 : l) * n_pos * M5_D;
+        const int phs = kind == 0 ? 0 : kind + 1;                  // trace slot (1 = attention)
+        if (!lm || tn == n_lt) M5PROF(lm ? 0 : phs, 0);
+        if (kind == 0) prefetch_layer(l + 1);
+        // the ring slot of tile tn-1 is free after this tile's barrier: its next tenant is tile tn-1+nslot
+        TileSrc nxt{nullptr, nullptr, nullptr, 0u, 0u, 0u};
+        if (tid == ISSUER) nxt = describe_tile(tn - 1 + P.nslot);
+        // ---- rows of this tile: warp w, lanes 8q..8q+7 -> local row 4w + q
+        int rbase, rt;
+        if (kind == 0)      { rbase = 0; rt = is_head ? 3 * M5_HR : 0; }
+        else if (kind == 2) { rbase = cta * 32; rt = 32; }
+        else if (kind == 4) { rbase = v0 + (tn - n_lt) * P.lmrt; rt = min(P.lmrt, v1 - rbase); }
+        else                { rbase = o0; rt = 8; }
+        const bool Kff = kind == 3;
+        M4MM D;
+        D.G = Kff ? p.Gf : p.Gd; D.gsh = Kff ? 5 : 3; D.stride = Kff ? p.stride_f : p.stride_d;
+        D.off_qh = Kff ? p.offqh_f : p.offqh_d; D.off_d = Kff ? p.offd_f : p.offd_d; D.off_m = Kff ? p.offm_f : p.offm_d;
+        D.off_n = Kff ? p.offn_f : p.offn_d; D.off_dd = Kff ? p.offdd_f : p.offdd_d; D.off_s = Kff ? p.offs_f : p.offs_d;
+        uint8_t * rec = (kind & 1) ? rec1 : rec0;
+        const int myrow = 4 * warp + (lane >> 3);
+        const bool owner = (lane & 7) == 0 && myrow < rt;
+        // ---- row owners fetch their bias before anything can stall
+        float bias = 0.f;
+        if (owner && kind != 4) {
+            if (kind == 0) { const int mat = myrow >> 4; bias = (mat == 0 ? L.q_b : mat == 1 ? L.k_b : L.v_b)[hrow0 + (myrow & 15)]; }
+            else bias = (kind == 1 ? L.o_b : (kind == 2 ? L.fc1_b : L.fc2_b))[rbase + myrow];
+        }
+        // ---- inputs of the tile -> activation record in shared memory
+        if (kind == 0 && !is_head) {
+            // clusters 16..31 have no q, k, v rows: they only need x at their 8 out_proj rows (the residual of P3)
+            if (tn > 0 && tid < 4) {
+                const unsigned long long * src = P.xch + (size_t) ((l - 1) & 1) * M5_LW + M5_E5 + (size_t) rep * M5_D + o0 + 2 * tid;
+                uint32_t a, b;
+                m5_poll2(src, tag - 1, a, b, err, wcode | 1);
+                *(float2 *) (s_x + o0 + 2 * tid) = make_float2(__uint_as_float(a), __uint_as_float(b));
+            } else if (tn == 0) *(float2 *) (s_x + 2 * tid) = make_float2(xa, xb);
+        } else if (kind < 3 || tn == n_lt) {
+            const bool ln = kind != 1;
+            float2 lw = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+            if (ln) {
+                const float * lnw = kind == 0 ? L.ln0_w : (kind == 2 ? L.ln1_w : p.lnf_w);
+                const float * lnb = kind == 0 ? L.ln0_b : (kind == 2 ? L.ln1_b : p.lnf_b);
+                lw = *(const float2 *) (lnw + 2 * tid); lb = *(const float2 *) (lnb + 2 * tid);
+            }
+            float va = xa, vb = xb;
+            if (tn > 0) {
+                const unsigned long long * src;
+                uint32_t want = tag;
+                if (kind == 0) { src = P.xch + (size_t) ((l - 1) & 1) * M5_LW + M5_E5; want = tag - 1; }
+                else if (kind == 1) src = X + M5_E2;
+                else if (kind == 2) src = X + M5_E3;
+                else src = X + M5_E5;
+                uint32_t a, b;
+                m5_poll2(src + (size_t) rep * M5_D + 2 * tid, want, a, b, err, wcode | 1);
+                va = __uint_as_float(a); vb = __uint_as_float(b);
+            }
+            M5PROF(phs, 3);
+            if (kind == 0) *(float2 *) (s_x + 2 * tid) = make_float2(va, vb);
+            if (kind == 2) *(float2 *) (s_x1 + 2 * tid) = make_float2(va, vb);
+            float y0 = va, y1 = vb;
+            if (ln) m5_layer_norm(va, vb, lw, lb, p.eps, sredA, sredB, y0, y1);
+            M5PROF(phs, 4);
+            m5_quant_pair<FMT>(y0, y1, rec, D.off_n, D.off_dd, D.off_s, p.code_off);
+            M5PROF(phs, 5);
+        } else if (kind == 3) {
+            const int nw10 = M5_NB_F * 10;                         // 1280 words: <= 2 units of two words per thread, both loads in flight
+            const unsigned long long * src = X + M5_E4 + (size_t) rep * nw10;
+            if (2 * tid < nw10) {
+                const bool two = 2 * (tid + M5_NT) < nw10;
+                const unsigned long long * pa = src + 2 * tid, * pb = src + 2 * (two ? tid + M5_NT : tid);
+                unsigned long long a0, a1, b0, b1;
+                unsigned spins = 0; long long t0 = 0;
+                for (;;) {
+                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(pa) : "memory");
+                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(b0), "=l"(b1) : "l"(pb) : "memory");
+                    if ((uint32_t) (a0 >> 32) == tag && (uint32_t) (a1 >> 32) == tag && (uint32_t) (b0 >> 32) == tag && (uint32_t) (b1 >> 32) == tag) break;
+                    if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, wcode | 1, t0)) break; }
+                }
+                m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * tid, (uint32_t) a0);
+                m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * tid + 1, (uint32_t) a1);
+                if (two) {
+                    m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * (tid + M5_NT), (uint32_t) b0);
+                    m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * (tid + M5_NT) + 1, (uint32_t) b1);
+                }
+            }
+            M5PROF(phs, 3);
+        }
+        // ---- weights of the tile
+        const int slot = tn % P.nslot;
+        const uint8_t * wt = s_w + (size_t) slot * P.slot_bytes;
+        if (rt > 0) {
+            m5_mbar_wait(&mbar[slot], (wphase >> slot) & 1u, err, wcode | 2);
+            wphase ^= 1u << slot;
+        }
+        __syncthreads();                                           // record complete; previous tile's shared scratch free
+        if (tid == ISSUER) fire_tile(tn - 1 + P.nslot, nxt);
+        M5PROF(lm ? 0 : phs, 1);
+        // ---- dot products: 4 rows per warp, lane = (row, running sum)
+        float dot = 0.f;
+        if (4 * warp < rt) {
+            const uint8_t * wrow = wt + (size_t) min(myrow, rt - 1) * D.stride;
+            dot = Kff ? m5_row_dot<FMT, M5_FF / 128>(wrow, rec, D) : m5_row_dot<FMT, M5_D / 128>(wrow, rec, D);
+        }
+        if (!lm) M5PROF(phs, 10);
+        // ---- epilogues
+        if (kind == 0) {
+            if (owner) {
+                const int mat = myrow >> 4, idx = myrow & 15;
+                float t = __fadd_rn(bias, dot);
+                if (mat == 0) { t = __fmul_rn(t, p.qscale); m5_bcast32(&s_q[rank * M5_HR + idx], __float_as_uint(t)); }
+                else if (mat == 1) { kc[(size_t) pos * M5_D + hrow0 + idx] = t; m5_bcast32(&s_kn[rank * M5_HR + idx], __float_as_uint(t)); }
+                else { vc[(size_t) pos * M5_D + hrow0 + idx] = t; s_vn[idx] = t; }
+            }
+        } else if (kind == 1 || kind == 3) {
+            if (4 * warp < rt) {                                   // warps 0, 1: four finished rows each, in lanes 0, 8, 16, 24
+                float v = 0.f;
+                if (owner) v = kind == 1 ? __fadd_rn(__fadd_rn(dot, bias), s_x[rbase + myrow]) : __fadd_rn(__fadd_rn(bias, dot), s_x1[rbase + myrow]);
+                const float mine = __shfl_sync(FULLMASK, v, 8 * (lane & 3));
+                unsigned long long * dst = X + (kind == 1 ? M5_E3 : M5_E5) + rbase + 4 * warp + (lane & 3);
+                m4_put(dst + (size_t) (lane >> 2) * M5_D, __float_as_uint(mine), tag);     // lane = (replica, row): 8 replicas x 4 rows
+            }
+        } else if (kind == 2) {
+            if (owner) s_blk[myrow] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dot))]);
+            __syncthreads();
+            if (tid < 32) m4_quant_publish<FMT>(s_blk, X + M5_E4 + (size_t) cta * 10, M5_NB_F * 10, tag);
+        } else {
+            if (owner) {
+                const int r_own = rbase + myrow;
+                p.logits[r_own] = dot;
+                if (dot > best || (dot == best && r_own < bi)) { best = dot; bi = r_own; }
+            }
+        }
+        if (!lm) M5PROF(phs, 2);
+        // ================= attention: cluster `head`; this CTA scores T/4 positions and reduces V for its 16 columns =================
+        if (kind == 0 && is_head) {
+            m5_cluster_arrive();                                   // q, k of this CTA stored into the 4 CTAs of the cluster
+            const float * Kb = kc + head * M5_DK;
+            const float * Vb = vc + hrow0;
+            // K rows of this warp: positions 512 pass + 32 warp + 8 rank + u, u < 8 (all but the new row are in the cache already)
+            const int tb0 = 32 * warp + 8 * rank;
+            float kr[8][2];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int t = tb0 + u;
+                kr[u][0] = (t < T - 1) ? __ldcg(Kb + (size_t) t * M5_D + lane) : 0.0f;
+                kr[u][1] = (t < T - 1) ? __ldcg(Kb + (size_t) t * M5_D + 32 + lane) : 0.0f;
+            }
+            m5_cluster_wait();
+            M5PROF(1, 3);
+            const float q0 = s_q[lane], q1 = s_q[32 + lane];
+            const float kn0 = s_kn[lane], kn1 = s_kn[32 + lane];
+#pragma unroll 1
+            for (int tb = tb0; tb < T; tb += 512) {
+                if (tb != tb0) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int t = tb + u;
+                        kr[u][0] = (t < T - 1) ? __ldcg(Kb + (size_t) t * M5_D + lane) : 0.0f;
+                        kr[u][1] = (t < T - 1) ? __ldcg(Kb + (size_t) t * M5_D + 32 + lane) : 0.0f;
+                    }
+                }
+                float s[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const bool isnew = (tb + u) == T - 1;
+                    float a = 0.0f;
+                    a = fmaf(isnew ? kn0 : kr[u][0], q0, a); a = fmaf(isnew ? kn1 : kr[u][1], q1, a);
+                    s[u] = a;
+                }
+                // 8 reduce trees (xor 16, 8, 4, 1, 2: GGML_F32x8_REDUCE) -- the first three levels as a transposing butterfly
+                float a4[4], a2[2];
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const float mine = b4 ? s[4 + i] : s[i], send = b4 ? s[i] : s[4 + i]; a4[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 16)); }
+#pragma unroll
+                for (int i = 0; i < 2; i++) { const float mine = b3 ? a4[2 + i] : a4[i], send = b3 ? a4[i] : a4[2 + i]; a2[i] = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 8)); }
+                const float mine = b2 ? a2[1] : a2[0], send = b2 ? a2[0] : a2[1];
+                float dotv = __fadd_rn(mine, __shfl_xor_sync(FULLMASK, send, 4));
+                dotv = __fadd_rn(dotv, __shfl_xor_sync(FULLMASK, dotv, 1));
+                dotv = __fadd_rn(dotv, __shfl_xor_sync(FULLMASK, dotv, 2));
+                const int u = (b4 ? 4 : 0) | (b3 ? 2 : 0) | (b2 ? 1 : 0);
+                const int t = tb + u;
+                if (t < T && (lane & 3) == 0) m5_bcast32(&sc[t], __float_as_uint(dotv));
+            }
+            m5_cluster_arrive();                                   // this CTA's scores stored into the 4 CTAs of the cluster
+            // V rows: unit (r32 = t % 32, column c), all 512 threads, up to 32 loads in flight while the scores travel
+            const int np = T & ~31;
+            const int vr = tid >> 4, vcn = tid & 15;
+            float vv[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const int t = 32 * k + vr;
+                vv[k] = (t < np && t != T - 1) ? __ldcg(Vb + (size_t) t * M5_D + vcn) : 0.0f;
+            }
+            if (np + vr < T - 1) tailv[tid] = __ldcg(Vb + (size_t) (np + vr) * M5_D + vcn);        // tail rows np .. T-2 (at most 30)
+            m5_cluster_wait();
+            M5PROF(1, 5);
+            // softmax over sc[0..T): max, fp16-table exp, sum in double (exact for fp16 values), scale (ggml.c:12955-12974)
+            {
+                const float x0 = tid < T ? sc[tid] : -INFINITY, x1 = tid + M5_NT < T ? sc[tid + M5_NT] : -INFINITY;
+                float mx = fmaxf(x0, x1);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
+                if (lane == 0) sredF[warp] = mx;
+                __syncthreads();
+                mx = sredF[lane & 15];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
+                float e0 = 0.f, e1 = 0.f;
+                if (tid < T) e0 = bg_h2f(p.exp_tab[bg_f2h(__fsub_rn(x0, mx))]);
+                if (tid + M5_NT < T) e1 = bg_h2f(p.exp_tab[bg_f2h(__fsub_rn(x1, mx))]);
+                const double sm = m4_warp_sum_f64((double) e0 + (double) e1);
+                if (lane == 0) sredA[warp] = sm;
+                __syncthreads();
+                const float inv = (float) (1.0 / m4_tree16(sredA));
+                if (tid < T) sc[tid] = __fmul_rn(e0, inv);
+                if (tid + M5_NT < T) sc[tid + M5_NT] = __fmul_rn(e1, inv);
+            }
+            __syncthreads();                                       // probabilities, s_vn and tailv visible to everyone
+            M5PROF(1, 4);
+            // V: running sum r32 of column c over t = r32, r32 + 32, ... < np (ggml_vec_dot_f32's 32 lanes, ggml.c:2372-2407)
+            {
+                const float vnew = s_vn[vcn];
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    const int t = 32 * k + vr;
+                    if (t < np) acc = fmaf((t == T - 1) ? vnew : vv[k], sc[t], acc);
+                }
+                red[vr * M5_HR + vcn] = acc;
+            }
+            __syncthreads();
+            if (tid < 32) {
+                float sumf = 0.f;
+                if (tid < M5_HR) {
+                    float x0[8];
+#pragma unroll
+                    for (int l8 = 0; l8 < 8; l8++) {
+                        const float a02 = __fadd_rn(red[(0 * 8 + l8) * M5_HR + tid], red[(2 * 8 + l8) * M5_HR + tid]);
+                        const float a13 = __fadd_rn(red[(1 * 8 + l8) * M5_HR + tid], red[(3 * 8 + l8) * M5_HR + tid]);
+                        x0[l8] = __fadd_rn(a02, a13);
+                    }
+                    const float t0 = __fadd_rn(x0[0], x0[4]), t1 = __fadd_rn(x0[1], x0[5]);
+                    const float t2 = __fadd_rn(x0[2], x0[6]), t3 = __fadd_rn(x0[3], x0[7]);
+                    sumf = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+                    // the as-built scalar tail of ggml_vec_dot_f32: products unfused in groups of 4, then <= 3 fused
+                    const int nv = np + ((T - np) & ~3);
+                    int t = np;
+#pragma unroll 1
+                    for (; t < nv; t++) sumf = __fadd_rn(sumf, __fmul_rn((t == T - 1) ? s_vn[tid] : tailv[(t - np) * M5_HR + tid], sc[t]));
+#pragma unroll 1
+                    for (; t < T;  t++) sumf = fmaf((t == T - 1) ? s_vn[tid] : tailv[(t - np) * M5_HR + tid], sc[t], sumf);
+                }
+                // lane = (replica, column): 16 columns x 8 replicas, 4 stores per lane
+                const float mine = __shfl_sync(FULLMASK, sumf, lane & 15);
+                unsigned long long * dst = X + M5_E2 + hrow0 + (lane & 15);
+#pragma unroll
+                for (int r = lane >> 4; r < M5_R; r += 2) m4_put(dst + (size_t) r * M5_D, __float_as_uint(mine), tag);
+            }
+            M5PROF(1, 2);
+        }
+    }
+    // per-CTA argmax candidate (first index wins ties) for the next launch's prologue
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULLMASK, best, o); const int oi = __shfl_xor_sync(FULLMASK, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { s_cv[warp] = best; s_ci[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 1; i < M5_NW; i++) if (s_cv[i] > best || (s_cv[i] == best && s_ci[i] < bi)) { best = s_cv[i]; bi = s_ci[i]; }
+        p.cand_val[cta] = best; p.cand_idx[cta] = bi;
+    }
+    { const int l = p.n_layer; M5PROF(0, 2); }
+    if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) M5_NC * P.prof_n + 4 * cta + 2);
+}

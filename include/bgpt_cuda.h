@@ -106,11 +106,11 @@ int bgpt_cuda_synchronize(bgpt_model * m);
 int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int n_steps,
                             int32_t * ids_out, float * ms_out);
 
-/* Which schedule evaluates single-token steps (n == 1): 1 = one persistent kernel per token
- * (default when available: generation 4 -- tagged-word exchange, csrc/bgpt_mega4.cuh -- for
- * quantised weights at BioGPT-base shapes, else generation 3), 2 = the generation-3 persistent
- * kernel with grid barriers (csrc/bgpt_mega.cuh), 0 = one kernel per fused operator (the schedule
- * used for n > 1 and for lock-step streams).  All produce identical bits; tests compare them. */
+/* Which schedule evaluates single-token steps (n == 1): 1 = one persistent kernel per token, newest generation available
+ * (default: generation 5 -- thread-block clusters, one attention head per cluster, csrc/bgpt_mega5.cuh -- for quantised
+ * weights at BioGPT-base shapes, else generation 3), 3 = generation 4 (tagged-word exchange without clusters,
+ * csrc/bgpt_mega4.cuh), 2 = generation 3 (grid barriers, csrc/bgpt_mega.cuh; every format and shape), 0 = one kernel per
+ * fused operator.  All produce identical bits; tests compare them.  BGPT_MEGA_V=3|4 caps the generation at load time. */
 int bgpt_cuda_set_decode_path(bgpt_model * m, int path);
 int bgpt_cuda_get_decode_path(const bgpt_model * m);
 /* Which schedule evaluates skinny batches (2 <= n < 112 token rows: prompt chunks of the reference's
@@ -133,7 +133,7 @@ int bgpt_cuda_set_tc_min_rows(bgpt_model * m, int rows);
  * records, 4 the d_ff-wide activation records; `rows` token rows) to HOST memory; returns the bytes copied, -1 on error.
  * tools/skinny_check.py uses it to localise a mismatch between the two batch schedules. */
 long long bgpt_cuda_debug_read_buffer(bgpt_model * m, int which, int rows, void * out, long long cap_bytes);
-/* 4 or 3: the persistent-kernel generation single-token steps run on; 0: per-operator kernels */
+/* 5, 4 or 3: the persistent-kernel generation single-token steps run on; 0: per-operator kernels */
 int bgpt_cuda_decode_kernel_generation(const bgpt_model * m);
 /* debug (env BGPT_MEGA_PROF=1 at load): per-phase clock64 stamps of CTA 0 of the last
  * persistent-kernel launch; returns the number of entries copied (0 when profiling is off). */

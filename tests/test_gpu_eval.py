@@ -136,44 +136,45 @@ def test_persistent_kernel_equals_oracle_and_per_op_path(checkers, capi, zoo, si
 
 
 @pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
-def test_generation4_kernel_equals_oracle_and_generation3(checkers, capi, zoo, ftype):
-    """BioGPT-base layer shapes: single-token steps run on the generation-4 persistent kernel
-    (tagged-word exchange, TMA weight ring).  Bits must equal the oracle's and the generation-3
-    kernel's at every position class: T = 1, the 32-wide boundary and both scalar tails, the
-    second K pass (T > 512) and the end of the context; the vocabulary (3001 rows) leaves ragged
-    lm_head tiles."""
+def test_persistent_generations_equal_oracle_and_each_other(checkers, capi, zoo, ftype):
+    """BioGPT-base layer shapes: single-token steps run on the generation-5 persistent kernel (clusters of 4 CTAs, one
+    attention head per cluster, DSMEM exchange inside the head, chain-order dot products, TMA weight ring).  Bits must equal
+    the oracle's, generation 4's (tagged-word exchange, no clusters) and generation 3's (grid barriers) at every position
+    class: T = 1, the 32-wide boundary and both scalar tails, the second K pass (T > 512) and the end of the context; the
+    vocabulary (3001 rows) leaves ragged lm_head tiles."""
     hp = gf.NARROW
     p = zoo.path("narrow", ftype)
     O = checkers.Oracle(p)
     M = capi.Model.load(p, max_batch=64)
-    assert M.decode_generation == 4, "generation-4 kernel not selected: " + capi.last_error()
+    assert M.decode_generation == 5, "generation-5 kernel not selected: " + capi.last_error()
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=77)
     windows = [(0, 70), (500, 531), (990, 1024)]
     pos = 0
-    got4 = {}
+    got5 = {}
     for lo, hi in windows:
-        while pos < lo:                                   # fill the cache with un-masked prompt batches (per-op kernels)
-            n = min(16, lo - pos)                          # <= 16 rows: the exact SIMT matmul path
+        while pos < lo:                                   # fill the cache with un-masked prompt batches (skinny-batch schedule)
+            n = min(16, lo - pos)
             want = O.eval(toks[pos:pos + n], pos); got = M.eval(toks[pos:pos + n], pos)
             assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} prompt at {pos}", got, want)
             pos += n
         for i in range(lo, hi):
             want = O.eval(toks[i:i + 1], i)
             got = M.eval(toks[i:i + 1], i)
-            assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} generation 4 at n_past={i}", got, want)
-            got4[i] = got
+            assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} generation 5 at n_past={i}", got, want)
+            got5[i] = got
         pos = hi
-    M.set_decode_path(2)
-    assert M.decode_generation == 3
-    for lo, hi in windows:
-        for i in range(lo, hi):                           # the cache rows are already there: same evals again
-            got = M.eval(toks[i:i + 1], i)
-            assert np.array_equal(_bits(got), _bits(got4[i])), (ftype, i)
-    M.set_decode_path(1)
-    ids4, _ = M.decode_greedy(int(toks[0]), 0, 40)
-    M.set_decode_path(2)
-    ids3, _ = M.decode_greedy(int(toks[0]), 0, 40)
-    assert ids4.tolist() == ids3.tolist()
+    for path, gen in ((3, 4), (2, 3)):
+        M.set_decode_path(path)
+        assert M.decode_generation == gen
+        for lo, hi in windows:
+            for i in range(lo, hi):                       # the cache rows are already there: same evals again
+                got = M.eval(toks[i:i + 1], i)
+                assert np.array_equal(_bits(got), _bits(got5[i])), (ftype, gen, i)
+    ids = {}
+    for path in (1, 3, 2):
+        M.set_decode_path(path)
+        ids[path], _ = M.decode_greedy(int(toks[0]), 0, 40)
+    assert ids[1].tolist() == ids[3].tolist() == ids[2].tolist()
     O.close(); M.close()
 
 

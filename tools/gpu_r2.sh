@@ -14,6 +14,12 @@ tests)
 newtests)
   timeout 1800 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=12 -s -k "tensor_core or base_model or eval_path" > $OUT/pytest_new.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_new.log
   grep -E "passed|failed|FAILED|Error|max\|d|tcgen05 prompt" $OUT/pytest_new.log | tail -40 ;;
+gen5)
+  timeout 900 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=3 -x -k "persistent_generations" > $OUT/pytest_gen5.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gen5.log
+  grep -E "passed|failed|FAILED|Error|differ|timed out" $OUT/pytest_gen5.log | tail -20 ;;
+headline)
+  timeout 900 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=3 -x -k "base_model_headline or base_model_64" > $OUT/pytest_headline.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_headline.log
+  grep -E "passed|failed|FAILED|Error|differ|timed out" $OUT/pytest_headline.log | tail -20 ;;
 smoke)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
   tail -5 $OUT/smoke.log ;;
@@ -21,7 +27,7 @@ bench)
   timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
   cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
 trace5)
-  for np in 4 511 1020; do BGPT_MEGA_PROF=1 timeout 200 python tools/trace_decode.py --n-past $np; done > $OUT/trace.log 2>&1; grep -v "Warning\|nanm\|return np" $OUT/trace.log | head -150 ;;
+  for np in 4 507 1015; do BGPT_MEGA_PROF=1 timeout 200 python tools/trace_decode5.py --n-past $np; done > $OUT/trace.log 2>&1; grep -v "Warning\|nanm\|return np" $OUT/trace.log | head -150 ;;
 decode)
   for ft in ${FTYPES:-q4_0}; do for np in 0 511 1023; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
   cat $OUT/decode.log ;;
