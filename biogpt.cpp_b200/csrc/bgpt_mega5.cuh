@@ -148,17 +148,24 @@ __device__ __forceinline__ void m5_quant_pair(float y0, float y1, uint8_t * rec,
 
 // LayerNorm + affine on registers (ggml.c:11403-11420 then mul, add): same operations as m4_ln_quant; the double sums are
 // combined in a parallel order.  Two block barriers inside.
-__device__ __forceinline__ void m5_layer_norm(float v0, float v1, float2 lw, float2 lb, float eps, double * sredA, double * sredB, float & y0, float & y1) {
+template <bool PROF>
+__device__ __forceinline__ void m5_layer_norm(float v0, float v1, float2 lw, float2 lb, float eps, double * sredA, double * sredB, float & y0, float & y1,
+                                              long long * stamp /* PROF: this CTA's stamps of the current (layer, stage), or nullptr */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool st = PROF && stamp && threadIdx.x == 0;
     const double s = m4_warp_sum_f64((double) v0 + (double) v1);
     if (lane == 0) sredA[warp] = s;
+    if (st) stamp[7] = clock64();
     __syncthreads();
     const float mean = (float) (m4_tree16(sredA) * (1.0 / M5_D));
     const float e0 = __fsub_rn(v0, mean), e1 = __fsub_rn(v1, mean);
+    if (st) stamp[8] = clock64();
     const double s2 = m4_warp_sum_f64((double) __fmul_rn(e0, e0) + (double) __fmul_rn(e1, e1));
     if (lane == 0) sredB[warp] = s2;
+    if (st) stamp[9] = clock64();
     __syncthreads();
     const float variance = (float) (m4_tree16(sredB) * (1.0 / M5_D));
+    if (st) stamp[11] = clock64();
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
     y0 = __fadd_rn(__fmul_rn(lw.x, __fmul_rn(e0, scale)), lb.x);
     y1 = __fadd_rn(__fmul_rn(lw.y, __fmul_rn(e1, scale)), lb.y);
@@ -217,6 +224,107 @@ __device__ __forceinline__ float m5_row_dot(const uint8_t * wrow, const uint8_t 
     r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 1));
     if (HASM) r = __fadd_rn(r, summ);
     return r;
+}
+
+// ---- one weight row per warp, K split over the four quarter-warps ("relay") ---------------------------------------------------
+// For the stages with few rows per CTA (out_proj, fc1, fc2: 8 / 32 / 8 rows) the 4-rows-per-warp mapping above leaves most of the
+// SM idle and one lane walks all K/32 blocks.  Here lane (kq = lane >> 3, l = lane & 7) does the integer work of running sum l for
+// the blocks of quarter kq only (K/128 blocks), all in registers and all four quarters at once; then the sums are continued in
+// block order by handing acc from quarter to quarter (3 shuffles): quarter 0 walks its blocks, quarter 1 continues, ...  The scale
+// products d_w * d_a are computed once per block (one lane each) and distributed by shuffles instead of 8 times.  Same operations
+// in the same order as m5_row_dot.  The finished dot (hsum_float_8 + summs) is in lanes 24..31.
+// SUMM: continue the Q4_1 / Q5_1 `summs` chain in the same lanes (K = 1024); for K = 4096 that would need 64 more registers, so a
+// helper warp walks it (m5_summs_chain) and the caller adds the two parts.
+template <int FMT, int G, bool SUMM>          // G = K / 128 groups of 4 blocks in the row; a quarter owns G / 4 groups
+__device__ __forceinline__ float m5_row_dot_relay(const uint8_t * wrow, const uint8_t * rec, const M4MM & D) {
+    constexpr bool IS8    = (FMT == BG_Q8_0);
+    constexpr bool HASQH  = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM   = SUMM && (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    constexpr bool HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
+    constexpr int GQ = G / 4, NBQ = GQ * 4;                      // groups / blocks per quarter: 2 / 8 (K = 1024), 8 / 32 (K = 4096)
+    constexpr int SPL = NBQ / 8;                                 // scale products per lane: 1 or 4
+    const int lane = threadIdx.x & 31, kq = lane >> 3, l = lane & 7, j = l & 3, hi = l >> 2, sh = hi * 4;
+    // scale products of this quarter's blocks, one lane each: lane l owns blocks kq * NBQ + SPL * l .. + SPL - 1
+    float sprod[SPL], mval[SPL], sval[SPL];
+#pragma unroll
+    for (int e = 0; e < SPL; e++) {
+        const int b = kq * NBQ + SPL * l + e;
+        sprod[e] = __fmul_rn(bg_h2f(*(const uint16_t *) (wrow + D.off_d + b * 2)), *(const float *) (rec + D.off_dd + b * 4));
+        mval[e] = 0.f; sval[e] = 0.f;
+        if (HASM) { mval[e] = bg_h2f(*(const uint16_t *) (wrow + D.off_m + b * 2)); sval[e] = *(const float *) (rec + D.off_s + b * 4); }
+    }
+    // integer dots of this lane's running sum over the quarter's blocks
+    float pv[NBQ];
+#pragma unroll
+    for (int gg = 0; gg < GQ; gg++) {
+        const int g = kq * GQ + gg;
+        const uint4 wq = IS8 ? *(const uint4 *) (wrow + ((g * 2 + hi) * 4 + j) * 16) : *(const uint4 *) (wrow + (g * 4 + j) * 16);
+        uint32_t qh = 0;
+        if (HASQH) qh = *(const uint32_t *) (wrow + D.off_qh + (g * 4 + j) * 4);
+        const uint4 aw = *(const uint4 *) (rec + (g * 8 + l) * 16);
+        int4 an = make_int4(0, 0, 0, 0);
+        if (HASOFF) an = *(const int4 *) (rec + D.off_n + (g * 8 + l) * 16);
+        const uint32_t ww[4] = { wq.x, wq.y, wq.z, wq.w }, aa[4] = { aw.x, aw.y, aw.z, aw.w };
+        const int nn[4] = { an.x, an.y, an.z, an.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t code;
+            if (IS8) code = ww[i];
+            else {
+                code = (ww[i] >> sh) & 0x0F0F0F0Fu;
+                if (HASQH) code |= bg_spread4((qh >> (8 * i + sh)) & 0xFu);
+            }
+            pv[gg * 4 + i] = (float) __dp4a((int) code, (int) aa[i], nn[i]);
+        }
+    }
+    // every lane collects the scale products of its quarter: block b of the quarter lives in lane (kq, b / SPL), register b % SPL
+    float sq[NBQ], mq[HASM ? NBQ : 1], aq[HASM ? NBQ : 1];
+#pragma unroll
+    for (int b = 0; b < NBQ; b++) {
+        const int src = (lane & 24) + b / SPL;
+        sq[b] = __shfl_sync(FULLMASK, sprod[b % SPL], src);
+        if (HASM) { mq[b] = __shfl_sync(FULLMASK, mval[b % SPL], src); aq[b] = __shfl_sync(FULLMASK, sval[b % SPL], src); }
+    }
+    // the chains in block order: quarter 0 first, its sums handed to quarter 1, ...
+    float acc = 0.0f, summ = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (q > 0) {
+            const float ia = __shfl_up_sync(FULLMASK, acc, 8);
+            float im = 0.f;
+            if (HASM) im = __shfl_up_sync(FULLMASK, summ, 8);
+            if (kq == q) { acc = ia; summ = im; }
+        }
+        if (kq == q) {
+#pragma unroll
+            for (int b = 0; b < NBQ; b++) { acc = fmaf(sq[b], pv[b], acc); if (HASM) summ = fmaf(mq[b], aq[b], summ); }
+        }
+    }
+    float r = __fadd_rn(acc, __shfl_xor_sync(FULLMASK, acc, 4));
+    r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 1));
+    if (HASM) r = __fadd_rn(r, summ);
+    return r;                                                     // valid in lanes 24..31
+}
+
+// the Q4_1 / Q5_1 `summs` chain of one K = 4096 row, summs = fma(m_w[b], s_a[b], summs) over the 128 blocks in order
+// (ggml.c:2824-2857, 3386-3411), walked by a helper warp while the row's owner warp does the relay: lane i loads blocks 4i..4i+3;
+// the values travel to lane 0 by shuffles and lane 0 runs the 128 dependent fmas.  Returned in every lane.
+__device__ __forceinline__ float m5_summs_chain(const uint8_t * wrow, const uint8_t * rec, const M4MM & D) {
+    const int lane = threadIdx.x & 31;
+    const uint2 mh = *(const uint2 *) (wrow + D.off_m + lane * 8);
+    const float4 sa = *(const float4 *) (rec + D.off_s + lane * 16);
+    const float m0 = bg_h2f((uint16_t) (mh.x & 0xFFFF)), m1 = bg_h2f((uint16_t) (mh.x >> 16));
+    const float m2 = bg_h2f((uint16_t) (mh.y & 0xFFFF)), m3 = bg_h2f((uint16_t) (mh.y >> 16));
+    float summ = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        summ = fmaf(__shfl_sync(FULLMASK, m0, i), __shfl_sync(FULLMASK, sa.x, i), summ);
+        summ = fmaf(__shfl_sync(FULLMASK, m1, i), __shfl_sync(FULLMASK, sa.y, i), summ);
+        summ = fmaf(__shfl_sync(FULLMASK, m2, i), __shfl_sync(FULLMASK, sa.z, i), summ);
+        summ = fmaf(__shfl_sync(FULLMASK, m3, i), __shfl_sync(FULLMASK, sa.w, i), summ);
+    }
+    return summ;
 }
 
 // scatter one exchange word (block b, word k) into a quantised record, with the folded code offset
@@ -408,14 +516,16 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         D.off_qh = Kff ? p.offqh_f : p.offqh_d; D.off_d = Kff ? p.offd_f : p.offd_d; D.off_m = Kff ? p.offm_f : p.offm_d;
         D.off_n = Kff ? p.offn_f : p.offn_d; D.off_dd = Kff ? p.offdd_f : p.offdd_d; D.off_s = Kff ? p.offs_f : p.offs_d;
         uint8_t * rec = (kind & 1) ? rec1 : rec0;
+        // direct mapping (P1, lm_head): warp w, lanes 8q..8q+7 -> local row 4w + q, finished in lane 8q.  Relay mapping (P3, P4, P5): one
+        // row per warp (P4: rows w and w + 16), finished in lane 24; P3 / P5 results are gathered and published by warp 0.
+        const bool relay = kind >= 1 && kind <= 3;
         const int myrow = 4 * warp + (lane >> 3);
-        const bool owner = (lane & 7) == 0 && myrow < rt;
-        // ---- row owners fetch their bias before anything can stall
-        float bias = 0.f;
-        if (owner && kind != 4) {
-            if (kind == 0) { const int mat = myrow >> 4; bias = (mat == 0 ? L.q_b : mat == 1 ? L.k_b : L.v_b)[hrow0 + (myrow & 15)]; }
-            else bias = (kind == 1 ? L.o_b : (kind == 2 ? L.fc1_b : L.fc2_b))[rbase + myrow];
-        }
+        const bool owner = !relay && (lane & 7) == 0 && myrow < rt;
+        // ---- whoever finishes a row fetches its bias before anything can stall
+        float bias = 0.f, bias2 = 0.f;
+        if (kind == 0) { if (owner) { const int mat = myrow >> 4; bias = (mat == 0 ? L.q_b : mat == 1 ? L.k_b : L.v_b)[hrow0 + (myrow & 15)]; } }
+        else if (kind == 2) { if (lane == 24) { bias = L.fc1_b[rbase + warp]; bias2 = L.fc1_b[rbase + warp + 16]; } }
+        else if (relay) { if (warp == 0 && lane < 8) bias = (kind == 1 ? L.o_b : L.fc2_b)[rbase + lane]; }
         // ---- inputs of the tile -> activation record in shared memory
         if (kind == 0 && !is_head) {
             // clusters 16..31 have no q, k, v rows: they only need x at their 8 out_proj rows (the residual of P3)
@@ -449,7 +559,8 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             if (kind == 0) *(float2 *) (s_x + 2 * tid) = make_float2(va, vb);
             if (kind == 2) *(float2 *) (s_x1 + 2 * tid) = make_float2(va, vb);
             float y0 = va, y1 = vb;
-            if (ln) m5_layer_norm(va, vb, lw, lb, p.eps, sredA, sredB, y0, y1);
+            if (ln) m5_layer_norm<PROF>(va, vb, lw, lb, p.eps, sredA, sredB, y0, y1,
+                                        PROF && P.trace ? P.trace + (size_t) cta * P.prof_n + (l * 5 + (lm ? 0 : phs)) * M5_PK : nullptr);
             M5PROF(phs, 4);
             m5_quant_pair<FMT>(y0, y1, rec, D.off_n, D.off_dd, D.off_s, p.code_off);
             M5PROF(phs, 5);
@@ -480,17 +591,28 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         const int slot = tn % P.nslot;
         const uint8_t * wt = s_w + (size_t) slot * P.slot_bytes;
         if (rt > 0) {
-            m5_mbar_wait(&mbar[slot], (wphase >> slot) & 1u, err, wcode | 2);
+            // ONE thread waits for the bulk copies (16 warps testing the same mbarrier serialise: ~500 cycles); the block barrier
+            // below hands the completed phase to everyone
+            if (tid == 0) m5_mbar_wait(&mbar[slot], (wphase >> slot) & 1u, err, wcode | 2);
             wphase ^= 1u << slot;
         }
-        __syncthreads();                                           // record complete; previous tile's shared scratch free
+        M5PROF(phs, 6);
+        __syncthreads();                                           // record and weights complete; previous tile's shared scratch free
         if (tid == ISSUER) fire_tile(tn - 1 + P.nslot, nxt);
         M5PROF(lm ? 0 : phs, 1);
-        // ---- dot products: 4 rows per warp, lane = (row, running sum)
-        float dot = 0.f;
-        if (4 * warp < rt) {
-            const uint8_t * wrow = wt + (size_t) min(myrow, rt - 1) * D.stride;
-            dot = Kff ? m5_row_dot<FMT, M5_FF / 128>(wrow, rec, D) : m5_row_dot<FMT, M5_D / 128>(wrow, rec, D);
+        // ---- dot products
+        constexpr bool HASMF = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+        float dot = 0.f, dot2 = 0.f;
+        if (!relay) {
+            if (4 * warp < rt) dot = m5_row_dot<FMT, M5_D / 128>(wt + (size_t) min(myrow, rt - 1) * D.stride, rec, D);
+        } else if (kind == 2) {
+            dot  = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) warp * D.stride, rec, D);
+            dot2 = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) (warp + 16) * D.stride, rec, D);
+        } else if (kind == 1) {
+            if (warp < 8) dot = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) warp * D.stride, rec, D);
+        } else {
+            if (warp < 8) dot = m5_row_dot_relay<FMT, M5_FF / 128, false>(wt + (size_t) warp * D.stride, rec, D);
+            else if (HASMF) dot = m5_summs_chain(wt + (size_t) (warp - 8) * D.stride, rec, D);     // the row's summs chain, on an idle warp
         }
         if (!lm) M5PROF(phs, 10);
         // ---- epilogues
@@ -503,15 +625,27 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 else { vc[(size_t) pos * M5_D + hrow0 + idx] = t; s_vn[idx] = t; }
             }
         } else if (kind == 1 || kind == 3) {
-            if (4 * warp < rt) {                                   // warps 0, 1: four finished rows each, in lanes 0, 8, 16, 24
+            // gather the 8 rows; warp 0 finishes them (bias, residual) and writes 8 rows x 8 replicas as consecutive words
+            if (warp < 8) { if (lane == 24) s_blk[warp] = dot; }
+            else if (kind == 3 && HASMF && lane == 0) s_blk[warp] = dot;
+            __syncthreads();
+            if (warp == 0) {
                 float v = 0.f;
-                if (owner) v = kind == 1 ? __fadd_rn(__fadd_rn(dot, bias), s_x[rbase + myrow]) : __fadd_rn(__fadd_rn(bias, dot), s_x1[rbase + myrow]);
-                const float mine = __shfl_sync(FULLMASK, v, 8 * (lane & 3));
-                unsigned long long * dst = X + (kind == 1 ? M5_E3 : M5_E5) + rbase + 4 * warp + (lane & 3);
-                m4_put(dst + (size_t) (lane >> 2) * M5_D, __float_as_uint(mine), tag);     // lane = (replica, row): 8 replicas x 4 rows
+                if (lane < 8) {
+                    float d = s_blk[lane];
+                    if (kind == 3 && HASMF) d = __fadd_rn(d, s_blk[8 + lane]);
+                    v = kind == 1 ? __fadd_rn(__fadd_rn(d, bias), s_x[rbase + lane]) : __fadd_rn(__fadd_rn(bias, d), s_x1[rbase + lane]);
+                }
+                const float mine = __shfl_sync(FULLMASK, v, lane & 7);
+                unsigned long long * dst = X + (kind == 1 ? M5_E3 : M5_E5) + rbase + (lane & 7);
+                m4_put(dst + (size_t) (lane >> 3) * M5_D, __float_as_uint(mine), tag);
+                m4_put(dst + (size_t) ((lane >> 3) + 4) * M5_D, __float_as_uint(mine), tag);
             }
         } else if (kind == 2) {
-            if (owner) s_blk[myrow] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dot))]);
+            if (lane == 24) {
+                s_blk[warp] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dot))]);
+                s_blk[warp + 16] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias2, dot2))]);
+            }
             __syncthreads();
             if (tid < 32) m4_quant_publish<FMT>(s_blk, X + M5_E4 + (size_t) cta * 10, M5_NB_F * 10, tag);
         } else {

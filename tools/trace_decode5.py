@@ -64,7 +64,11 @@ C = st.astype(np.float64); C[~valid] = np.nan
 def dur(a_, b_):
     return np.nanmean(C[:, 1:L, b_[0], b_[1]] - C[:, 1:L, a_[0], a_[1]], axis=1)
 with np.errstate(all="ignore"):
-    for nme, a_, b_ in [("P1 polled -> LayerNorm done", (0, 3), (0, 4)), ("P1 LayerNorm -> quantised", (0, 4), (0, 5)), ("P1 quantised -> ready", (0, 5), (0, 1)),
+    for nme, a_, b_ in [("P1 LN: polled -> before sync 1", (0, 3), (0, 7)), ("P1 LN: sync 1 -> mean known", (0, 7), (0, 8)), ("P1 LN: mean -> before sync 2", (0, 8), (0, 9)),
+                        ("P1 LN: sync 2 -> variance known", (0, 9), (0, 11)), ("P1 LN: variance -> y", (0, 11), (0, 4)),
+                        ("P1 quantised -> weights waited", (0, 5), (0, 6)), ("P1 weights waited -> ready", (0, 6), (0, 1)),
+                        ("P3 quantised -> weights waited", (2, 5), (2, 6)), ("P3 weights waited -> ready", (2, 6), (2, 1)),
+                        ("P1 polled -> LayerNorm done", (0, 3), (0, 4)), ("P1 LayerNorm -> quantised", (0, 4), (0, 5)), ("P1 quantised -> ready", (0, 5), (0, 1)),
                         ("P1 ready -> dots", (0, 1), (0, 10)), ("P1 dots -> stored", (0, 10), (0, 2)), ("P1 stored -> q,k arrived", (0, 2), (1, 3)),
                         ("att q,k -> scores arrived", (1, 3), (1, 5)), ("att scores -> softmax", (1, 5), (1, 4)), ("att softmax -> published", (1, 4), (1, 2)),
                         ("P3 polled -> quantised", (2, 3), (2, 5)), ("P3 quantised -> ready", (2, 5), (2, 1)), ("P3 ready -> dots", (2, 1), (2, 10)), ("P3 dots -> published", (2, 10), (2, 2)),
