@@ -917,7 +917,7 @@ static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     P.sm_m = o; o += s_bytes;
     P.sm_x = o; o += al(M4_D * 4);
     P.sm_x1 = o; o += al(M4_D * 4);
-    P.sm_sc = o; o += al(m->n_positions * 4);
+    P.sm_sc = o; o += al(1024 * 4);
     P.sm_red = o; o += al(32 * 32 * 4);
     P.sm_tail = o; o += al(31 * 32 * 4);
     P.sm_total = o;
@@ -967,7 +967,7 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     for (int i = 0; i < m->n_layer; i++) P.layers[i] = m->h_mega_layers[i];
     auto al = [](int x) { return (x + 127) & ~127; };
     const int sd = P.b.stride_d, sf = P.b.stride_f;
-    const int fixed = al(P.b.actb_d) + al(P.b.actb_f) + 2 * al(M5_D * 4) + al(m->n_positions * 4) + al(32 * M5_HR * 4) + al(31 * M5_HR * 4);
+    const int fixed = al(P.b.actb_d) + al(P.b.actb_f) + 2 * al(M5_D * 4) + al(1024 * 4) + al(32 * M5_HR * 4) + al(31 * M5_HR * 4);
     const int lim = (int) prop.sharedMemPerBlockOptin - 2048;             // static shared memory + margin
     P.lmrt = 64; P.nslot = M4_NSLOT;
     auto slot_for = [&](int lmrt) { return al(std::max(std::max(32 * sd, 8 * sf), std::max(3 * M5_HR, lmrt) * sd)); };
@@ -982,7 +982,7 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     P.sm_rec1 = o; o += al(P.b.actb_f);
     P.sm_x = o; o += al(M5_D * 4);
     P.sm_x1 = o; o += al(M5_D * 4);
-    P.sm_sc = o; o += al(m->n_positions * 4);
+    P.sm_sc = o; o += al(1024 * 4);
     P.sm_red = o; o += al(32 * M5_HR * 4);
     P.sm_tail = o; o += al(31 * M5_HR * 4);
     P.sm_total = o;

@@ -110,65 +110,97 @@ __device__ __forceinline__ void m5_mbar_wait(uint64_t * bar, uint32_t parity, in
     }
 }
 
-// ---- activation quantiser on registers: thread t owns elements 2t, 2t+1 of a 1024-wide row ----------------------------------
-// (ggml.c:1166-1203, 1403-1450: d = amax / 127, id = 127 / amax, round to nearest even; Q8_0 rounds d through fp16.)
+// ---- the "prep" stage runs on 4 warps ---------------------------------------------------------------------------------------------
+// With 16 warps per SM every instruction that all warps execute costs ~5 issue cycles (4 warps per scheduler), and a LayerNorm over
+// 1024 values is almost all per-thread overhead (shuffle rounds, the cross-warp sum, a division and a square root): 2 elements per
+// thread on 512 threads measured 2480 cycles.  128 threads x 8 elements issue a quarter of the instructions; the other 12 warps wait
+// at the block barrier that follows and cost nothing.
+#define M5_PT 128             // threads of the prep stage
+__device__ __forceinline__ void m5_bar_prep() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// poll 8 consecutive tagged words (64 bytes) until all carry `tag`
+__device__ __forceinline__ void m5_poll8(const unsigned long long * p, uint32_t tag, float (&v)[8], int * err, int code) {
+    unsigned long long w[8];
+    unsigned spins = 0; long long t0 = 0;
+    for (;;) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[2 * i]), "=l"(w[2 * i + 1]) : "l"(p + 2 * i) : "memory");
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) ok = ok && (uint32_t) (w[i] >> 32) == tag;
+        if (ok) break;
+        if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, code, t0)) break; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float((uint32_t) w[i]);
+}
+
+// activation quantiser (ggml.c:1166-1203, 1403-1450: d = amax / 127, id = 127 / amax, round to nearest even; Q8_0 rounds d through
+// fp16): thread t < 128 owns elements 8t..8t+7 = the 4-byte groups l = 2 (t & 3), 2 (t & 3) + 1 of block t >> 2.
 // Writes the int8 words [g][l][i], the folded code offsets, d and s of the record.  Ends WITHOUT a barrier.
 template <int FMT>
-__device__ __forceinline__ void m5_quant_pair(float y0, float y1, uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
+__device__ __forceinline__ void m5_quant8(const float (&y)[8], uint8_t * rec, int off_n, int off_d, int off_s, int code_off) {
     constexpr bool Q81 = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
     constexpr bool HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
     const int tid = threadIdx.x;
-    float amax = fmaxf(fabsf(y0), fabsf(y1));
+    float amax = fmaxf(fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3]))), fmaxf(fmaxf(fabsf(y[4]), fabsf(y[5])), fmaxf(fabsf(y[6]), fabsf(y[7]))));
     amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 1));
     amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 2));
-    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 4));
-    amax = fmaxf(amax, __shfl_xor_sync(FULLMASK, amax, 8));
     const float d  = __fdiv_rn(amax, 127.0f);
     const float id = (amax != 0.0f) ? __fdiv_rn(127.0f, amax) : 0.0f;
-    const int q0 = __float2int_rn(__fmul_rn(y0, id)), q1 = __float2int_rn(__fmul_rn(y1, id));
-    const uint32_t hw = ((uint32_t) q0 & 0xFFu) | (((uint32_t) q1 & 0xFFu) << 8);
-    const int ps = q0 + q1;
-    const uint32_t hw_p = __shfl_xor_sync(FULLMASK, hw, 1);
-    const int ps_p = __shfl_xor_sync(FULLMASK, ps, 1);
-    const int b = tid >> 4, g = b >> 2, i = b & 3;
-    if ((tid & 1) == 0) {
-        const int l = (tid & 15) >> 1;
-        ((uint32_t *) rec)[(g * 8 + l) * 4 + i] = hw | (hw_p << 16);
-        if (HASOFF) ((int *) (rec + off_n))[(g * 8 + l) * 4 + i] = -code_off * (ps + ps_p);
+    int q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = __float2int_rn(__fmul_rn(y[i], id));
+    const uint32_t w0 = ((uint32_t) q[0] & 0xFFu) | (((uint32_t) q[1] & 0xFFu) << 8) | (((uint32_t) q[2] & 0xFFu) << 16) | (((uint32_t) q[3] & 0xFFu) << 24);
+    const uint32_t w1 = ((uint32_t) q[4] & 0xFFu) | (((uint32_t) q[5] & 0xFFu) << 8) | (((uint32_t) q[6] & 0xFFu) << 16) | (((uint32_t) q[7] & 0xFFu) << 24);
+    const int s0 = (q[0] + q[1]) + (q[2] + q[3]), s1 = (q[4] + q[5]) + (q[6] + q[7]);
+    const int b = tid >> 2, g = b >> 2, i = b & 3, l0 = 2 * (tid & 3);
+    ((uint32_t *) rec)[(g * 8 + l0) * 4 + i] = w0;
+    ((uint32_t *) rec)[(g * 8 + l0 + 1) * 4 + i] = w1;
+    if (HASOFF) {
+        ((int *) (rec + off_n))[(g * 8 + l0) * 4 + i] = -code_off * s0;
+        ((int *) (rec + off_n))[(g * 8 + l0 + 1) * 4 + i] = -code_off * s1;
     }
     if (Q81) {
-        int stot = ps;
+        int stot = s0 + s1;
         stot += __shfl_xor_sync(FULLMASK, stot, 1);
         stot += __shfl_xor_sync(FULLMASK, stot, 2);
-        stot += __shfl_xor_sync(FULLMASK, stot, 4);
-        stot += __shfl_xor_sync(FULLMASK, stot, 8);
-        if ((tid & 15) == 0) { ((float *) (rec + off_d))[b] = d; ((float *) (rec + off_s))[b] = __fmul_rn(d, (float) stot); }
-    } else if ((tid & 15) == 0) { ((float *) (rec + off_d))[b] = bg_h2f(bg_f2h(d)); ((float *) (rec + off_s))[b] = 0.0f; }
+        if ((tid & 3) == 0) { ((float *) (rec + off_d))[b] = d; ((float *) (rec + off_s))[b] = __fmul_rn(d, (float) stot); }
+    } else if ((tid & 3) == 0) { ((float *) (rec + off_d))[b] = bg_h2f(bg_f2h(d)); ((float *) (rec + off_s))[b] = 0.0f; }
 }
 
-// LayerNorm + affine on registers (ggml.c:11403-11420 then mul, add): same operations as m4_ln_quant; the double sums are
-// combined in a parallel order.  Two block barriers inside.
+// LayerNorm + affine on registers (ggml.c:11403-11420 then mul, add), 8 elements per thread on 128 threads; the double sums are
+// combined in a parallel order.  Two named barriers (prep threads only) inside.
 template <bool PROF>
-__device__ __forceinline__ void m5_layer_norm(float v0, float v1, float2 lw, float2 lb, float eps, double * sredA, double * sredB, float & y0, float & y1,
-                                              long long * stamp /* PROF: this CTA's stamps of the current (layer, stage), or nullptr */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool st = PROF && stamp && threadIdx.x == 0;
-    const double s = m4_warp_sum_f64((double) v0 + (double) v1);
+__device__ __forceinline__ void m5_layer_norm8(const float (&v)[8], const float * lnw, const float * lnb, float eps, double * sredA, double * sredB, float (&y)[8],
+                                               long long * stamp /* PROF: this CTA's stamps of the current (layer, stage), or nullptr */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool st = PROF && stamp && tid == 0;
+    const float4 lw0 = *(const float4 *) (lnw + 8 * tid), lw1 = *(const float4 *) (lnw + 8 * tid + 4);
+    const float4 lb0 = *(const float4 *) (lnb + 8 * tid), lb1 = *(const float4 *) (lnb + 8 * tid + 4);
+    double s = (((double) v[0] + (double) v[1]) + ((double) v[2] + (double) v[3])) + (((double) v[4] + (double) v[5]) + ((double) v[6] + (double) v[7]));
+    s = m4_warp_sum_f64(s);
     if (lane == 0) sredA[warp] = s;
     if (st) stamp[7] = clock64();
-    __syncthreads();
-    const float mean = (float) (m4_tree16(sredA) * (1.0 / M5_D));
-    const float e0 = __fsub_rn(v0, mean), e1 = __fsub_rn(v1, mean);
+    m5_bar_prep();
+    const float mean = (float) (((sredA[0] + sredA[1]) + (sredA[2] + sredA[3])) * (1.0 / M5_D));
     if (st) stamp[8] = clock64();
-    const double s2 = m4_warp_sum_f64((double) __fmul_rn(e0, e0) + (double) __fmul_rn(e1, e1));
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = __fsub_rn(v[i], mean);
+    double s2 = (((double) __fmul_rn(e[0], e[0]) + (double) __fmul_rn(e[1], e[1])) + ((double) __fmul_rn(e[2], e[2]) + (double) __fmul_rn(e[3], e[3]))) +
+                (((double) __fmul_rn(e[4], e[4]) + (double) __fmul_rn(e[5], e[5])) + ((double) __fmul_rn(e[6], e[6]) + (double) __fmul_rn(e[7], e[7])));
+    s2 = m4_warp_sum_f64(s2);
     if (lane == 0) sredB[warp] = s2;
     if (st) stamp[9] = clock64();
-    __syncthreads();
-    const float variance = (float) (m4_tree16(sredB) * (1.0 / M5_D));
+    m5_bar_prep();
+    const float variance = (float) (((sredB[0] + sredB[1]) + (sredB[2] + sredB[3])) * (1.0 / M5_D));
     if (st) stamp[11] = clock64();
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, eps)));
-    y0 = __fadd_rn(__fmul_rn(lw.x, __fmul_rn(e0, scale)), lb.x);
-    y1 = __fadd_rn(__fmul_rn(lw.y, __fmul_rn(e1, scale)), lb.y);
+    const float lw[8] = { lw0.x, lw0.y, lw0.z, lw0.w, lw1.x, lw1.y, lw1.z, lw1.w }, lb[8] = { lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w };
+#pragma unroll
+    for (int i = 0; i < 8; i++) y[i] = __fadd_rn(__fmul_rn(lw[i], __fmul_rn(e[i], scale)), lb[i]);
 }
 
 // ---- one weight row x the activation record, running sum l of the row in this lane -----------------------------------------------
@@ -347,6 +379,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     __shared__ __align__(8) uint64_t mbar[M4_NSLOT];               // weight ring
     __shared__ double sredA[M5_NW], sredB[M5_NW];
     __shared__ float sredF[M5_NW];
+    __shared__ unsigned long long s_isum[4];
     __shared__ __align__(16) float s_blk[32];
     __shared__ __align__(16) float s_q[M5_DK], s_kn[M5_DK];        // q and the new k row of this head: written by the 4 CTAs of the cluster
     __shared__ __align__(16) float s_vn[M5_HR];                    // new v values of this CTA's 16 columns
@@ -473,16 +506,16 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     }
     // every CTA of the cluster is running (its shared memory exists) before anyone stores into a peer; also publishes s_tok
     m5_cluster_sync();
-    // ---- embedding: every CTA, elements 2t, 2t+1 in registers
-    float xa, xb;
-    {
+    // ---- embedding: every CTA, 8 elements per prep thread, into s_x (read back by the first tile)
+    if (tid < M5_PT) {
         int tok = s_tok; tok = tok < 0 ? 0 : (tok >= p.n_vocab ? p.n_vocab - 1 : tok);
         int prow = p.n_past + 2; prow = prow >= p.n_pos_rows ? p.n_pos_rows - 1 : prow;
         const size_t rb = bg_file_row_bytes(FMT, M5_D);
         const uint8_t * tr = p.embed_tok + rb * (size_t) tok;
         const uint8_t * pr = p.embed_pos + rb * (size_t) prow;
-        xa = __fadd_rn(__fmul_rn(bg_dequant_elem(FMT, tr, 2 * tid), p.emb_scale), bg_dequant_elem(FMT, pr, 2 * tid));
-        xb = __fadd_rn(__fmul_rn(bg_dequant_elem(FMT, tr, 2 * tid + 1), p.emb_scale), bg_dequant_elem(FMT, pr, 2 * tid + 1));
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            s_x[8 * tid + i] = __fadd_rn(__fmul_rn(bg_dequant_elem(FMT, tr, 8 * tid + i), p.emb_scale), bg_dequant_elem(FMT, pr, 8 * tid + i));
     }
 
     float best = -INFINITY; int bi = 0x7fffffff;                  // lm_head argmax of this thread's rows
@@ -516,17 +549,17 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         D.off_qh = Kff ? p.offqh_f : p.offqh_d; D.off_d = Kff ? p.offd_f : p.offd_d; D.off_m = Kff ? p.offm_f : p.offm_d;
         D.off_n = Kff ? p.offn_f : p.offn_d; D.off_dd = Kff ? p.offdd_f : p.offdd_d; D.off_s = Kff ? p.offs_f : p.offs_d;
         uint8_t * rec = (kind & 1) ? rec1 : rec0;
-        // direct mapping (P1, lm_head): warp w, lanes 8q..8q+7 -> local row 4w + q, finished in lane 8q.  Relay mapping (P3, P4, P5): one
-        // row per warp (P4: rows w and w + 16), finished in lane 24; P3 / P5 results are gathered and published by warp 0.
-        const bool relay = kind >= 1 && kind <= 3;
+        // direct mapping (P1, P4, lm_head): warp w, lanes 8q..8q+7 -> local row 4w + q, finished in lane 8q.  Relay mapping (P3, P5): one
+        // row per warp, finished in lane 24; the 8 results are gathered and published by warp 0.
+        const bool relay = kind == 1 || kind == 3;
         const int myrow = 4 * warp + (lane >> 3);
         const bool owner = !relay && (lane & 7) == 0 && myrow < rt;
         // ---- whoever finishes a row fetches its bias before anything can stall
-        float bias = 0.f, bias2 = 0.f;
+        float bias = 0.f;
         if (kind == 0) { if (owner) { const int mat = myrow >> 4; bias = (mat == 0 ? L.q_b : mat == 1 ? L.k_b : L.v_b)[hrow0 + (myrow & 15)]; } }
-        else if (kind == 2) { if (lane == 24) { bias = L.fc1_b[rbase + warp]; bias2 = L.fc1_b[rbase + warp + 16]; } }
+        else if (kind == 2) { if (owner) bias = L.fc1_b[rbase + myrow]; }
         else if (relay) { if (warp == 0 && lane < 8) bias = (kind == 1 ? L.o_b : L.fc2_b)[rbase + lane]; }
-        // ---- inputs of the tile -> activation record in shared memory
+        // ---- inputs of the tile -> activation record in shared memory (4 warps; everyone else goes straight to the barrier)
         if (kind == 0 && !is_head) {
             // clusters 16..31 have no q, k, v rows: they only need x at their 8 out_proj rows (the residual of P3)
             if (tn > 0 && tid < 4) {
@@ -534,56 +567,68 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 uint32_t a, b;
                 m5_poll2(src, tag - 1, a, b, err, wcode | 1);
                 *(float2 *) (s_x + o0 + 2 * tid) = make_float2(__uint_as_float(a), __uint_as_float(b));
-            } else if (tn == 0) *(float2 *) (s_x + 2 * tid) = make_float2(xa, xb);
+            }
         } else if (kind < 3 || tn == n_lt) {
-            const bool ln = kind != 1;
-            float2 lw = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-            if (ln) {
-                const float * lnw = kind == 0 ? L.ln0_w : (kind == 2 ? L.ln1_w : p.lnf_w);
-                const float * lnb = kind == 0 ? L.ln0_b : (kind == 2 ? L.ln1_b : p.lnf_b);
-                lw = *(const float2 *) (lnw + 2 * tid); lb = *(const float2 *) (lnb + 2 * tid);
+            if (tid < M5_PT) {
+                const bool ln = kind != 1;
+                float v[8];
+                if (tn > 0) {
+                    const unsigned long long * src;
+                    uint32_t want = tag;
+                    if (kind == 0) { src = P.xch + (size_t) ((l - 1) & 1) * M5_LW + M5_E5; want = tag - 1; }
+                    else if (kind == 1) src = X + M5_E2;
+                    else if (kind == 2) src = X + M5_E3;
+                    else src = X + M5_E5;
+                    m5_poll8(src + (size_t) rep * M5_D + 8 * tid, want, v, err, wcode | 1);
+                } else {
+                    const float4 a = *(const float4 *) (s_x + 8 * tid), b = *(const float4 *) (s_x + 8 * tid + 4);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                }
+                M5PROF(phs, 3);
+                if ((kind == 0 && tn > 0) || kind == 2) {
+                    float * dstx = kind == 0 ? s_x : s_x1;
+                    *(float4 *) (dstx + 8 * tid) = make_float4(v[0], v[1], v[2], v[3]);
+                    *(float4 *) (dstx + 8 * tid + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                float y[8];
+                if (ln) {
+                    const float * lnw = kind == 0 ? L.ln0_w : (kind == 2 ? L.ln1_w : p.lnf_w);
+                    const float * lnb = kind == 0 ? L.ln0_b : (kind == 2 ? L.ln1_b : p.lnf_b);
+                    m5_layer_norm8<PROF>(v, lnw, lnb, p.eps, sredA, sredB, y,
+                                         PROF && P.trace ? P.trace + (size_t) cta * P.prof_n + (l * 5 + (lm ? 0 : phs)) * M5_PK : nullptr);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) y[i] = v[i];
+                }
+                M5PROF(phs, 4);
+                m5_quant8<FMT>(y, rec, D.off_n, D.off_dd, D.off_s, p.code_off);
+                M5PROF(phs, 5);
             }
-            float va = xa, vb = xb;
-            if (tn > 0) {
-                const unsigned long long * src;
-                uint32_t want = tag;
-                if (kind == 0) { src = P.xch + (size_t) ((l - 1) & 1) * M5_LW + M5_E5; want = tag - 1; }
-                else if (kind == 1) src = X + M5_E2;
-                else if (kind == 2) src = X + M5_E3;
-                else src = X + M5_E5;
-                uint32_t a, b;
-                m5_poll2(src + (size_t) rep * M5_D + 2 * tid, want, a, b, err, wcode | 1);
-                va = __uint_as_float(a); vb = __uint_as_float(b);
-            }
-            M5PROF(phs, 3);
-            if (kind == 0) *(float2 *) (s_x + 2 * tid) = make_float2(va, vb);
-            if (kind == 2) *(float2 *) (s_x1 + 2 * tid) = make_float2(va, vb);
-            float y0 = va, y1 = vb;
-            if (ln) m5_layer_norm<PROF>(va, vb, lw, lb, p.eps, sredA, sredB, y0, y1,
-                                        PROF && P.trace ? P.trace + (size_t) cta * P.prof_n + (l * 5 + (lm ? 0 : phs)) * M5_PK : nullptr);
-            M5PROF(phs, 4);
-            m5_quant_pair<FMT>(y0, y1, rec, D.off_n, D.off_dd, D.off_s, p.code_off);
-            M5PROF(phs, 5);
         } else if (kind == 3) {
-            const int nw10 = M5_NB_F * 10;                         // 1280 words: <= 2 units of two words per thread, both loads in flight
-            const unsigned long long * src = X + M5_E4 + (size_t) rep * nw10;
-            if (2 * tid < nw10) {
-                const bool two = 2 * (tid + M5_NT) < nw10;
-                const unsigned long long * pa = src + 2 * tid, * pb = src + 2 * (two ? tid + M5_NT : tid);
-                unsigned long long a0, a1, b0, b1;
+            // 128 blocks x 10 words: prep thread t polls block t (5 loads in flight) and scatters it into the K = 4096 record
+            if (tid < M5_PT) {
+                const unsigned long long * src = X + M5_E4 + (size_t) rep * (M5_NB_F * 10) + (size_t) tid * 10;
+                unsigned long long w[10];
                 unsigned spins = 0; long long t0 = 0;
                 for (;;) {
-                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(pa) : "memory");
-                    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(b0), "=l"(b1) : "l"(pb) : "memory");
-                    if ((uint32_t) (a0 >> 32) == tag && (uint32_t) (a1 >> 32) == tag && (uint32_t) (b0 >> 32) == tag && (uint32_t) (b1 >> 32) == tag) break;
+#pragma unroll
+                    for (int i = 0; i < 5; i++)
+                        asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[2 * i]), "=l"(w[2 * i + 1]) : "l"(src + 2 * i) : "memory");
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < 10; i++) ok = ok && (uint32_t) (w[i] >> 32) == tag;
+                    if (ok) break;
                     if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, wcode | 1, t0)) break; }
                 }
-                m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * tid, (uint32_t) a0);
-                m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * tid + 1, (uint32_t) a1);
-                if (two) {
-                    m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * (tid + M5_NT), (uint32_t) b0);
-                    m5_scatter_word(rec, D.off_n, D.off_dd, D.off_s, p.code_off, 2 * (tid + M5_NT) + 1, (uint32_t) b1);
+                const int b = tid, g = b >> 2, i = b & 3;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t v = (uint32_t) w[k];
+                    ((uint32_t *) rec)[(g * 8 + k) * 4 + i] = v;
+                    if (p.code_off) ((int *) (rec + D.off_n))[(g * 8 + k) * 4 + i] = -p.code_off * __dp4a((int) v, 0x01010101, 0);
                 }
+                ((float *) (rec + D.off_dd))[b] = __uint_as_float((uint32_t) w[8]);
+                ((float *) (rec + D.off_s))[b] = __uint_as_float((uint32_t) w[9]);
             }
             M5PROF(phs, 3);
         }
@@ -602,12 +647,9 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         M5PROF(lm ? 0 : phs, 1);
         // ---- dot products
         constexpr bool HASMF = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
-        float dot = 0.f, dot2 = 0.f;
+        float dot = 0.f;
         if (!relay) {
             if (4 * warp < rt) dot = m5_row_dot<FMT, M5_D / 128>(wt + (size_t) min(myrow, rt - 1) * D.stride, rec, D);
-        } else if (kind == 2) {
-            dot  = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) warp * D.stride, rec, D);
-            dot2 = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) (warp + 16) * D.stride, rec, D);
         } else if (kind == 1) {
             if (warp < 8) dot = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) warp * D.stride, rec, D);
         } else {
@@ -642,10 +684,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 m4_put(dst + (size_t) ((lane >> 3) + 4) * M5_D, __float_as_uint(mine), tag);
             }
         } else if (kind == 2) {
-            if (lane == 24) {
-                s_blk[warp] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dot))]);
-                s_blk[warp + 16] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias2, dot2))]);
-            }
+            if (owner) s_blk[myrow] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dot))]);
             __syncthreads();
             if (tid < 32) m4_quant_publish<FMT>(s_blk, X + M5_E4 + (size_t) cta * 10, M5_NB_F * 10, tag);
         } else {
@@ -714,32 +753,45 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             float vv[32];
 #pragma unroll
             for (int k = 0; k < 32; k++) {
+                if (32 * k >= np) break;                           // CTA-uniform: nothing is issued for positions that do not exist
                 const int t = 32 * k + vr;
-                vv[k] = (t < np && t != T - 1) ? __ldcg(Vb + (size_t) t * M5_D + vcn) : 0.0f;
+                vv[k] = (t != T - 1) ? __ldcg(Vb + (size_t) t * M5_D + vcn) : 0.0f;
             }
             if (np + vr < T - 1) tailv[tid] = __ldcg(Vb + (size_t) (np + vr) * M5_D + vcn);        // tail rows np .. T-2 (at most 30)
             m5_cluster_wait();
             M5PROF(1, 5);
-            // softmax over sc[0..T): max, fp16-table exp, sum in double (exact for fp16 values), scale (ggml.c:12955-12974)
-            {
-                const float x0 = tid < T ? sc[tid] : -INFINITY, x1 = tid + M5_NT < T ? sc[tid + M5_NT] : -INFINITY;
-                float mx = fmaxf(x0, x1);
+            // softmax over sc[0..T) on 4 warps, 8 scores per thread: max, fp16-table exp, sum, scale (ggml.c:12955-12974).  The reference
+            // adds the fp16-valued exponentials in double; they are multiples of 2^-24 not above 1, so the sum is exact in any order --
+            // here as integers (two warp-wide redux.add instead of ten 64-bit shuffles), converted to double once.
+            if (tid < M5_PT) {
+                const float4 xa4 = *(const float4 *) (sc + 8 * tid), xb4 = *(const float4 *) (sc + 8 * tid + 4);
+                float x[8] = { xa4.x, xa4.y, xa4.z, xa4.w, xb4.x, xb4.y, xb4.z, xb4.w };
+                float mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { if (8 * tid + i >= T) x[i] = -INFINITY; mx = fmaxf(mx, x[i]); }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
                 if (lane == 0) sredF[warp] = mx;
-                __syncthreads();
-                mx = sredF[lane & 15];
+                m5_bar_prep();
+                mx = fmaxf(fmaxf(sredF[0], sredF[1]), fmaxf(sredF[2], sredF[3]));
+                float e[8];
+                unsigned lo = 0, hi = 0;
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
-                float e0 = 0.f, e1 = 0.f;
-                if (tid < T) e0 = bg_h2f(p.exp_tab[bg_f2h(__fsub_rn(x0, mx))]);
-                if (tid + M5_NT < T) e1 = bg_h2f(p.exp_tab[bg_f2h(__fsub_rn(x1, mx))]);
-                const double sm = m4_warp_sum_f64((double) e0 + (double) e1);
-                if (lane == 0) sredA[warp] = sm;
-                __syncthreads();
-                const float inv = (float) (1.0 / m4_tree16(sredA));
-                if (tid < T) sc[tid] = __fmul_rn(e0, inv);
-                if (tid + M5_NT < T) sc[tid + M5_NT] = __fmul_rn(e1, inv);
+                for (int i = 0; i < 8; i++) {
+                    e[i] = 0.f;
+                    if (8 * tid + i < T) {
+                        e[i] = bg_h2f(p.exp_tab[bg_f2h(__fsub_rn(x[i], mx))]);
+                        const unsigned u = __float2uint_rn(__fmul_rn(e[i], 16777216.0f));       // exact: fp16 values are multiples of 2^-24
+                        lo += u & 0xFFFFu; hi += u >> 16;
+                    }
+                }
+                lo = __reduce_add_sync(FULLMASK, lo); hi = __reduce_add_sync(FULLMASK, hi);
+                if (lane == 0) s_isum[warp] = ((unsigned long long) hi << 16) + lo;
+                m5_bar_prep();
+                const unsigned long long tot = (s_isum[0] + s_isum[1]) + (s_isum[2] + s_isum[3]);
+                const float inv = (float) (1.0 / ((double) (long long) tot * (1.0 / 16777216.0)));
+#pragma unroll
+                for (int i = 0; i < 8; i++) if (8 * tid + i < T) sc[8 * tid + i] = __fmul_rn(e[i], inv);
             }
             __syncthreads();                                       // probabilities, s_vn and tailv visible to everyone
             M5PROF(1, 4);
@@ -749,8 +801,9 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 float acc = 0.f;
 #pragma unroll
                 for (int k = 0; k < 32; k++) {
+                    if (32 * k >= np) break;
                     const int t = 32 * k + vr;
-                    if (t < np) acc = fmaf((t == T - 1) ? vnew : vv[k], sc[t], acc);
+                    acc = fmaf((t == T - 1) ? vnew : vv[k], sc[t], acc);
                 }
                 red[vr * M5_HR + vcn] = acc;
             }
@@ -771,7 +824,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                     // the as-built scalar tail of ggml_vec_dot_f32: products unfused in groups of 4, then <= 3 fused
                     const int nv = np + ((T - np) & ~3);
                     int t = np;
-#pragma unroll 1
+#pragma unroll 4
                     for (; t < nv; t++) sumf = __fadd_rn(sumf, __fmul_rn((t == T - 1) ? s_vn[tid] : tailv[(t - np) * M5_HR + tid], sc[t]));
 #pragma unroll 1
                     for (; t < T;  t++) sumf = fmaf((t == T - 1) ? s_vn[tid] : tailv[(t - np) * M5_HR + tid], sc[t], sumf);
