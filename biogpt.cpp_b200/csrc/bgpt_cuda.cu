@@ -967,15 +967,22 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     for (int i = 0; i < m->n_layer; i++) P.layers[i] = m->h_mega_layers[i];
     auto al = [](int x) { return (x + 127) & ~127; };
     const int sd = P.b.stride_d, sf = P.b.stride_f;
-    const int fixed = al(P.b.actb_d) + al(P.b.actb_f) + 2 * al(M5_D * 4) + al(1024 * 4) + al(32 * M5_HR * 4) + al(31 * M5_HR * 4);
+    const int base = al(P.b.actb_d) + al(P.b.actb_f) + 2 * al(M5_D * 4) + al(1024 * 4) + al(32 * M5_HR * 4) + al(31 * M5_HR * 4);
+    const int hasm = (m->wtype == BG_Q4_1 || m->wtype == BG_Q5_1) ? 2 : 1;
+    const int scratch = al(8 * 8 * M5_PS * 4) + al(hasm * 8 * M5_NB_F * 4);      // fc2 two-phase: block products + scale products (+ minima)
     const int lim = (int) prop.sharedMemPerBlockOptin - 2048;             // static shared memory + margin
-    P.lmrt = 64; P.nslot = M4_NSLOT;
     auto slot_for = [&](int lmrt) { return al(std::max(std::max(32 * sd, 8 * sf), std::max(3 * M5_HR, lmrt) * sd)); };
-    if (P.nslot * slot_for(64) + fixed > lim) P.lmrt = 32;
+    // preference: 4 ring slots; then the fc2 scratch (relay otherwise); then 64-row lm_head tiles
+    bool use_scratch = !(getenv("BGPT_M5_FC2") && atoi(getenv("BGPT_M5_FC2")) == 0);
+    P.nslot = M4_NSLOT; P.lmrt = 64;
+    auto total = [&]() { return P.nslot * slot_for(P.lmrt) + base + (use_scratch ? scratch : 0); };
+    if (total() > lim) P.lmrt = 32;
+    if (total() > lim && P.nslot > 3) P.nslot = 3;
+    if (total() > lim) use_scratch = false;
+    while (P.nslot > 2 && total() > lim) P.nslot--;
+    if (total() > lim) return BGPT_OK;
+    if (getenv("BGPT_M5_LMRT")) { const int v = atoi(getenv("BGPT_M5_LMRT")); if ((v == 32 || v == 64) && v <= P.lmrt) P.lmrt = v; }
     P.slot_bytes = slot_for(P.lmrt);
-    while (P.nslot > 2 && P.nslot * P.slot_bytes + fixed > lim) P.nslot--;
-    if (P.nslot * P.slot_bytes + fixed > lim) return BGPT_OK;
-    if (getenv("BGPT_M5_LMRT")) { const int v = atoi(getenv("BGPT_M5_LMRT")); if ((v == 32 || v == 64) && v <= P.lmrt) { P.lmrt = v; P.slot_bytes = slot_for(v); } }
     int o = 0;
     P.sm_w = o; o += P.nslot * P.slot_bytes;
     P.sm_rec0 = o; o += al(P.b.actb_d);
@@ -985,6 +992,8 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     P.sm_sc = o; o += al(1024 * 4);
     P.sm_red = o; o += al(32 * M5_HR * 4);
     P.sm_tail = o; o += al(31 * M5_HR * 4);
+    P.sm_p = P.sm_s = -1;
+    if (use_scratch) { P.sm_p = o; o += al(8 * 8 * M5_PS * 4); P.sm_s = o; o += al(hasm * 8 * M5_NB_F * 4); }
     P.sm_total = o;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sm_total));
     {   // 32 clusters of 4 must be co-resident

@@ -64,7 +64,7 @@ struct M5Params {
     long long * trace;             // BGPT_MEGA_PROF: [nC][prof_n] clock64 stamps, then [nC][4] clock calibration
     int prof_n;
     int nslot, slot_bytes, lmrt;   // weight ring: slots, bytes per slot, lm_head rows per tile (32 or 64)
-    int sm_w, sm_rec0, sm_rec1, sm_x, sm_x1, sm_sc, sm_red, sm_tail, sm_total;
+    int sm_w, sm_rec0, sm_rec1, sm_x, sm_x1, sm_sc, sm_red, sm_tail, sm_p, sm_s, sm_total;   // sm_p < 0: no fc2 scratch (relay instead)
 };
 
 // ---- cluster / DSMEM -------------------------------------------------------------------------------------------------------
@@ -116,6 +116,7 @@ __device__ __forceinline__ void m5_mbar_wait(uint64_t * bar, uint32_t parity, in
 // thread on 512 threads measured 2480 cycles.  128 threads x 8 elements issue a quarter of the instructions; the other 12 warps wait
 // at the block barrier that follows and cost nothing.
 #define M5_PT 128             // threads of the prep stage
+#define M5_PS (M5_NB_F + 4)    // padded row of the fc2 product scratch (floats): conflict-free float4 stores
 __device__ __forceinline__ void m5_bar_prep() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // poll 8 consecutive tagged words (64 bytes) until all carry `tag`
@@ -400,6 +401,8 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     float * sc = (float *) (smem + P.sm_sc);                       // [n_positions] scores / probabilities of this head
     float * red = (float *) (smem + P.sm_red);                     // [32][16]
     float * tailv = (float *) (smem + P.sm_tail);                  // [31][16]
+    float * s_p = (float *) (smem + (P.sm_p < 0 ? 0 : P.sm_p));    // fc2: [8 rows][8 sums][M5_PS] block products
+    float * s_s = (float *) (smem + (P.sm_s < 0 ? 0 : P.sm_s));    // fc2: [8 rows][128] scale products, then [8][128] minima (Q4_1 / Q5_1)
 
     const int n_pos = p.n_positions;
     const int o0 = cta * 8;                                        // out_proj / fc2 rows
@@ -652,9 +655,74 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             if (4 * warp < rt) dot = m5_row_dot<FMT, M5_D / 128>(wt + (size_t) min(myrow, rt - 1) * D.stride, rec, D);
         } else if (kind == 1) {
             if (warp < 8) dot = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) warp * D.stride, rec, D);
-        } else {
+        } else if (P.sm_p < 0) {
             if (warp < 8) dot = m5_row_dot_relay<FMT, M5_FF / 128, false>(wt + (size_t) warp * D.stride, rec, D);
             else if (HASMF) dot = m5_summs_chain(wt + (size_t) (warp - 8) * D.stride, rec, D);     // the row's summs chain, on an idle warp
+        } else {
+            // fc2, K = 4096, 8 rows: the chain of 128 dependent fmas per running sum is the floor (512 cycles); everything else is
+            // spread over all 16 warps first.  Phase A: thread (g = group of 4 blocks, l) does the integer dots of rows r0, r0+2, r0+4,
+            // r0+6 (its activation words stay in registers) and writes (float) isum as float4 per row; 2 scale products per thread.
+            {
+                constexpr bool IS8 = (FMT == BG_Q8_0), HASQH = (FMT == BG_Q5_0 || FMT == BG_Q5_1), HASOFF = (FMT == BG_Q4_0 || FMT == BG_Q5_0);
+                const int l = tid & 7, g = (tid >> 3) & 31, r0 = tid >> 8, j = l & 3, hi = l >> 2, sh = hi * 4;
+                const uint4 aw = *(const uint4 *) (rec + (g * 8 + l) * 16);
+                int4 an = make_int4(0, 0, 0, 0);
+                if (HASOFF) an = *(const int4 *) (rec + D.off_n + (g * 8 + l) * 16);
+                const uint32_t aa[4] = { aw.x, aw.y, aw.z, aw.w };
+                const int nn[4] = { an.x, an.y, an.z, an.w };
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) {
+                    const int row = r0 + 2 * rr;
+                    const uint8_t * wrow = wt + (size_t) row * D.stride;
+                    const uint4 wq = IS8 ? *(const uint4 *) (wrow + ((g * 2 + hi) * 4 + j) * 16) : *(const uint4 *) (wrow + (g * 4 + j) * 16);
+                    uint32_t qh = 0;
+                    if (HASQH) qh = *(const uint32_t *) (wrow + D.off_qh + (g * 4 + j) * 4);
+                    const uint32_t ww[4] = { wq.x, wq.y, wq.z, wq.w };
+                    float pv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        uint32_t code;
+                        if (IS8) code = ww[i];
+                        else {
+                            code = (ww[i] >> sh) & 0x0F0F0F0Fu;
+                            if (HASQH) code |= bg_spread4((qh >> (8 * i + sh)) & 0xFu);
+                        }
+                        pv[i] = (float) __dp4a((int) code, (int) aa[i], nn[i]);
+                    }
+                    *(float4 *) (s_p + (size_t) (row * 8 + l) * M5_PS + 4 * g) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int b = tid & 127, row = (tid >> 7) + 4 * e;
+                    const uint8_t * wrow = wt + (size_t) row * D.stride;
+                    s_s[row * M5_NB_F + b] = __fmul_rn(bg_h2f(*(const uint16_t *) (wrow + D.off_d + b * 2)), *(const float *) (rec + D.off_dd + b * 4));
+                    if (HASMF) s_s[(8 + row) * M5_NB_F + b] = bg_h2f(*(const uint16_t *) (wrow + D.off_m + b * 2));
+                }
+            }
+            __syncthreads();
+            // Phase B: warps 0, 1, lane = (row, running sum): the chains in block order (+ summs), then hsum_float_8
+            if (warp < 2) {
+                const int row = 4 * warp + (lane >> 3), l = lane & 7;
+                const float * pp = s_p + (size_t) (row * 8 + l) * M5_PS;
+                const float * ss = s_s + row * M5_NB_F;
+                float acc = 0.f, summ = 0.f;
+#pragma unroll 8
+                for (int g = 0; g < M5_NB_F / 4; g++) {
+                    const float4 pv = *(const float4 *) (pp + 4 * g);
+                    const float4 sv = *(const float4 *) (ss + 4 * g);
+                    acc = fmaf(sv.x, pv.x, acc); acc = fmaf(sv.y, pv.y, acc); acc = fmaf(sv.z, pv.z, acc); acc = fmaf(sv.w, pv.w, acc);
+                    if (HASMF) {
+                        const float4 mv = *(const float4 *) (ss + 8 * M5_NB_F + 4 * g);
+                        const float4 sa = *(const float4 *) (rec + D.off_s + g * 16);
+                        summ = fmaf(mv.x, sa.x, summ); summ = fmaf(mv.y, sa.y, summ); summ = fmaf(mv.z, sa.z, summ); summ = fmaf(mv.w, sa.w, summ);
+                    }
+                }
+                float r = __fadd_rn(acc, __shfl_xor_sync(FULLMASK, acc, 4));
+                r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 2));
+                r = __fadd_rn(r, __shfl_xor_sync(FULLMASK, r, 1));
+                if (HASMF) r = __fadd_rn(r, summ);
+                dot = r;
+            }
         }
         if (!lm) M5PROF(phs, 10);
         // ---- epilogues
@@ -668,14 +736,16 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             }
         } else if (kind == 1 || kind == 3) {
             // gather the 8 rows; warp 0 finishes them (bias, residual) and writes 8 rows x 8 replicas as consecutive words
-            if (warp < 8) { if (lane == 24) s_blk[warp] = dot; }
+            const bool two_phase = kind == 3 && P.sm_p >= 0;
+            if (two_phase) { if (warp < 2 && (lane & 7) == 0) s_blk[4 * warp + (lane >> 3)] = dot; }
+            else if (warp < 8) { if (lane == 24) s_blk[warp] = dot; }
             else if (kind == 3 && HASMF && lane == 0) s_blk[warp] = dot;
             __syncthreads();
             if (warp == 0) {
                 float v = 0.f;
                 if (lane < 8) {
                     float d = s_blk[lane];
-                    if (kind == 3 && HASMF) d = __fadd_rn(d, s_blk[8 + lane]);
+                    if (kind == 3 && HASMF && !two_phase) d = __fadd_rn(d, s_blk[8 + lane]);
                     v = kind == 1 ? __fadd_rn(__fadd_rn(d, bias), s_x[rbase + lane]) : __fadd_rn(__fadd_rn(bias, d), s_x1[rbase + lane]);
                 }
                 const float mine = __shfl_sync(FULLMASK, v, lane & 7);
