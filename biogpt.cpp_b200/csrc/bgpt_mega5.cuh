@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         const int wcode = ((kind + 1) << 16) | (lx << 8);          // watchdog code of this tile's waits
         float * kc = p.kcache + (size_t) (lm ? 0 : l) * n_pos * M5_D;
         float * vc = p.vcache + (size_t) (lm ? 0 : l) * n_pos * M5_D;
-        const int phs = kind == 0 ? 0 : kind + 1;                  // trace slot (1 = attention)
+        const int phs = (kind == 0 || lm) ? 0 : kind + 1;         // trace slot (1 = attention; the lm_head tiles use slot 0 of "layer" n_layer)
         if (!lm || tn == n_lt) M5PROF(lm ? 0 : phs, 0);
         if (kind == 0) prefetch_layer(l + 1);
         // the ring slot of tile tn-1 is free after this tile's barrier: its next tenant is tile tn-1+nslot
@@ -562,6 +562,14 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         if (kind == 0) { if (owner) { const int mat = myrow >> 4; bias = (mat == 0 ? L.q_b : mat == 1 ? L.k_b : L.v_b)[hrow0 + (myrow & 15)]; } }
         else if (kind == 2) { if (owner) bias = L.fc1_b[rbase + myrow]; }
         else if (relay) { if (warp == 0 && lane < 8) bias = (kind == 1 ? L.o_b : L.fc2_b)[rbase + lane]; }
+        // ---- weights of the tile: ONE thread of a warp that idles during the prep stage waits for the bulk copies (they were issued
+        //      three tiles ago); the block barrier below hands the completed phase to everyone
+        const int slot = tn % P.nslot;
+        const uint8_t * wt = s_w + (size_t) slot * P.slot_bytes;
+        if (rt > 0) {
+            if (tid == M5_PT) m5_mbar_wait(&mbar[slot], (wphase >> slot) & 1u, err, wcode | 2);
+            wphase ^= 1u << slot;
+        }
         // ---- inputs of the tile -> activation record in shared memory (4 warps; everyone else goes straight to the barrier)
         if (kind == 0 && !is_head) {
             // clusters 16..31 have no q, k, v rows: they only need x at their 8 out_proj rows (the residual of P3)
@@ -634,15 +642,6 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 ((float *) (rec + D.off_s))[b] = __uint_as_float((uint32_t) w[9]);
             }
             M5PROF(phs, 3);
-        }
-        // ---- weights of the tile
-        const int slot = tn % P.nslot;
-        const uint8_t * wt = s_w + (size_t) slot * P.slot_bytes;
-        if (rt > 0) {
-            // ONE thread waits for the bulk copies (16 warps testing the same mbarrier serialise: ~500 cycles); the block barrier
-            // below hands the completed phase to everyone
-            if (tid == 0) m5_mbar_wait(&mbar[slot], (wphase >> slot) & 1u, err, wcode | 2);
-            wphase ^= 1u << slot;
         }
         M5PROF(phs, 6);
         __syncthreads();                                           // record and weights complete; previous tile's shared scratch free
