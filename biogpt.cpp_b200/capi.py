@@ -29,8 +29,8 @@ SYMBOLS = [
     "bgpt_cuda_last_error", "bgpt_cuda_device_count", "bgpt_cuda_version",
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
-    "bgpt_cuda_eval", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams",
+    "bgpt_cuda_eval", "bgpt_cuda_eval_topk", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -67,6 +67,8 @@ def lib():
     L.bgpt_cuda_model_free.restype = None
     L.bgpt_cuda_model_free.argtypes = [C.c_void_p]
     L.bgpt_cuda_eval.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, _f32p]
+    L.bgpt_cuda_eval_topk.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _f32p, _i32p,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     L.bgpt_cuda_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.bgpt_cuda_logits_device.restype = C.c_void_p
     L.bgpt_cuda_logits_device.argtypes = [C.c_void_p]
@@ -87,6 +89,7 @@ def lib():
     L.bgpt_cuda_set_tc_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
+    L.bgpt_cuda_decode_greedy_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.POINTER(C.c_float)]
     L.bgpt_cuda_hparams.restype = None
     L.bgpt_cuda_hparams.argtypes = [C.c_void_p, _i32p]
     L.bgpt_cuda_weight_bytes.restype = C.c_size_t
@@ -204,6 +207,17 @@ class Model:
         _check(lib().bgpt_cuda_eval(self.h, t, len(t), n_past, out), "eval")
         return (out, bufs) if taps else out
 
+    def eval_topk(self, tokens: Sequence[int], n_past: int, k: int, fallback: bool = True):
+        """(vals[K], ids[K], exact, full_logits_or_None): the K largest logits of the eval's last row, selected on the device"""
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        vals = np.zeros(k, dtype=np.float32)
+        ids = np.zeros(k, dtype=np.int32)
+        n_out, exact = C.c_int(0), C.c_int(0)
+        full = np.empty(self.n_vocab, dtype=np.float32) if fallback else None
+        _check(lib().bgpt_cuda_eval_topk(self.h, t, len(t), n_past, k, vals, ids, C.byref(n_out), C.byref(exact),
+                                         full.ctypes.data if fallback else None), "eval_topk")
+        return vals[:n_out.value], ids[:n_out.value], bool(exact.value), (full if fallback and not exact.value else None)
+
     def eval_streams(self, tokens: Sequence[int], n_past: int, fetch: bool = True) -> Optional[np.ndarray]:
         t = np.ascontiguousarray(tokens, dtype=np.int32)
         out = np.empty((len(t), self.n_vocab), dtype=np.float32) if fetch else None
@@ -266,6 +280,15 @@ class Model:
 
     def set_streams(self, n: int):
         _check(lib().bgpt_cuda_set_streams(self.h, n), "set_streams")
+
+    def decode_greedy_streams(self, first_tokens: Sequence[int], n_past: int, n_steps: int):
+        """(ids [n_steps][n_streams], device ms): lock-step greedy decode of the streams, entirely on the device"""
+        t = np.ascontiguousarray(first_tokens, dtype=np.int32)
+        ids = np.zeros((n_steps, len(t)), dtype=np.int32)
+        ms = C.c_float(0)
+        _check(lib().bgpt_cuda_decode_greedy_streams(self.h, t, len(t), n_past, n_steps, ids.reshape(-1), C.byref(ms)),
+               "decode_greedy_streams")
+        return ids, float(ms.value)
 
     def decode_greedy(self, first_token: int, n_past: int, n_steps: int):
         ids = np.zeros(n_steps, dtype=np.int32)

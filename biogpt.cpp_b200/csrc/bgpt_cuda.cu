@@ -28,6 +28,7 @@
 #endif
 #include "bgpt_tc.cuh"
 #include "bgpt_quant.cuh"
+#include "bgpt_topk.cuh"
 #include "bgpt_skinny.cuh"
 #include "bgpt_tu.h"
 
@@ -92,7 +93,8 @@ struct bgpt_model {
     DevState * st = nullptr;
     // arena for `cap` token rows
     int cap = 0;
-    int * d_tokens = nullptr; int * d_idlog = nullptr; int * h_idlog = nullptr; int idlog_cap = 0;   // h_idlog: pinned, idlog_cap ints
+    int * d_tokens = nullptr; int * d_idlog = nullptr; int * h_idlog = nullptr; int idlog_cap = 0;
+    uint8_t * d_topk = nullptr; uint8_t * h_topk = nullptr;      // [TOPK_MAXK floats | TOPK_MAXK ints | 2 ints], device and pinned host   // h_idlog: pinned, idlog_cap ints
     float *x = nullptr, *x1 = nullptr, *q = nullptr, *att = nullptr, *hff = nullptr, *logits = nullptr;
     uint8_t *act_d = nullptr, *act_ff = nullptr;
     ActLayout A_d{}, A_ff{};
@@ -224,6 +226,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     if (m->h_err5) cudaFreeHost(m->h_err5);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
+    cudaFree(m->d_topk); if (m->h_topk) cudaFreeHost(m->h_topk);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -1171,6 +1174,52 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
     return BGPT_OK;
 }
 
+// eval + the K largest logits of the last row, for the sampler (bgpt_topk.cuh).  Host buffers: tokens in; vals / ids (K entries,
+// logit descending) and *exact out.  *exact = 0 means equal values make std::partial_sort's choice / order ambiguous: then (and
+// only then) the full logit row is copied to logits_fallback (n_vocab floats, may be NULL) so the caller can run the reference's
+// sampler on it.  8 K + 8 bytes cross PCIe per token instead of 4 n_vocab.
+extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
+                                   float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback) {
+    RET(check_eval_args(m, n, n_past, n));
+    if (!tokens || !vals || !ids || !n_out || !exact || k < 1) return fail(BGPT_E_ARG, "eval_topk: bad arguments");
+    if (k > TOPK_MAXK) return fail(BGPT_E_ARG, "eval_topk: k=%d exceeds %d; use bgpt_cuda_eval and sample on the host", k, TOPK_MAXK);
+    CK(cudaSetDevice(m->device));
+    RET(ensure_arena(m, n));
+    const size_t tk_bytes = (size_t) TOPK_MAXK * 8 + 8;
+    if (!m->d_topk) {
+        CK(cudaMalloc(&m->d_topk, tk_bytes)); CK(cudaMallocHost(&m->h_topk, tk_bytes));
+        cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaGetLastError();
+    }
+    cudaStream_t s = m->stream;
+    memcpy(m->h_tokens, tokens, (size_t) n * sizeof(int));
+    m->h_st->n_past = n_past; m->h_st->step = 0; m->h_st->pad0 = m->h_st->pad1 = 0;
+    CK(cudaEventRecord(m->ev0, s));
+    const bool mega = n == 1 && use_mega(m);
+    if (mega) { RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0])); }
+    else {
+        CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+        RET(forward(m, m->d_tokens, n, 0));
+    }
+    const int staged = (size_t) m->n_vocab * 4 <= (size_t) 200 * 1024;
+    float * dv = (float *) m->d_topk; int * di = (int *) (m->d_topk + TOPK_MAXK * 4); int * dinfo = (int *) (m->d_topk + TOPK_MAXK * 8);
+    k_topk<<<1, TOPK_NT, staged ? (size_t) m->n_vocab * 4 : 0, s>>>(m->logits, m->n_vocab, k, staged, dv, di, dinfo);
+    m->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m->h_topk, m->d_topk, tk_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(m->ev1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    if (mega && mega_generation(m) == 5) RET(check_mega5_error(m));
+    const int * hinfo = (const int *) (m->h_topk + TOPK_MAXK * 8);
+    *n_out = hinfo[0]; *exact = hinfo[1];
+    memcpy(vals, m->h_topk, (size_t) hinfo[0] * 4);
+    memcpy(ids, m->h_topk + TOPK_MAXK * 4, (size_t) hinfo[0] * 4);
+    if (!hinfo[1] && logits_fallback) CK(cudaMemcpy(logits_fallback, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
 extern "C" int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, int n, int n_past) {
     RET(check_eval_args(m, n, n_past, n));
     if (!d_tokens) return fail(BGPT_E_ARG, "eval_device: NULL tokens");
@@ -1267,6 +1316,48 @@ extern "C" int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, in
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     if (logits_out) memcpy(logits_out, m->h_logits, (size_t) n_streams * m->n_vocab * 4);
+    return BGPT_OK;
+}
+
+// Greedy decode of S lock-step streams entirely on the device (config 4 as a serving loop): every step is one forward pass
+// over the S rows (weights read once per step), S argmax blocks that feed the ids back, and a counter bump -- no host round trip
+// until the end.  ids_out (HOST) = [n_steps][n_streams].
+extern "C" int bgpt_cuda_decode_greedy_streams(bgpt_model * m, const int32_t * first_tokens, int n_streams, int n_past, int n_steps,
+                                               int32_t * ids_out, float * ms_out) {
+    RET(check_eval_args(m, n_streams, n_past, n_steps));
+    if (!first_tokens || !ids_out || n_steps < 1) return fail(BGPT_E_ARG, "decode_greedy_streams: bad arguments");
+    if (n_streams > m->n_streams) return fail(BGPT_E_ARG, "decode_greedy_streams: %d streams requested, %d allocated (bgpt_cuda_set_streams)", n_streams, m->n_streams);
+    CK(cudaSetDevice(m->device));
+    RET(ensure_arena(m, n_streams));
+    cudaStream_t s = m->stream;
+    const int need = n_steps * n_streams;
+    if (need > m->idlog_cap) {
+        cudaFree(m->d_idlog); m->d_idlog = nullptr;
+        if (m->h_idlog) cudaFreeHost(m->h_idlog);
+        m->h_idlog = nullptr; m->idlog_cap = 0;
+        CK(cudaMalloc(&m->d_idlog, (size_t) need * sizeof(int)));
+        CK(cudaMallocHost(&m->h_idlog, (size_t) need * sizeof(int)));
+        m->idlog_cap = need;
+    }
+    CK(cudaStreamSynchronize(s));
+    memcpy(m->h_tokens, first_tokens, (size_t) n_streams * sizeof(int));
+    m->h_st->n_past = n_past; m->h_st->step = 0;
+    CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n_streams * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(m->ev0, s));
+    for (int i = 0; i < n_steps; i++) {
+        RET(forward(m, m->d_tokens, n_streams, 1));
+        k_argmax_rows<<<n_streams, 1024, 0, s>>>(m->logits, m->n_vocab, m->d_tokens, m->d_idlog, m->st, n_streams);
+        k_streams_advance<<<1, 1, 0, s>>>(m->st);
+        m->launches += 2;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(m->ev1, s));
+    CK(cudaMemcpyAsync(m->h_idlog, m->d_idlog, (size_t) need * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    memcpy(ids_out, m->h_idlog, (size_t) need * sizeof(int));
+    if (ms_out) *ms_out = m->last_ms;
     return BGPT_OK;
 }
 

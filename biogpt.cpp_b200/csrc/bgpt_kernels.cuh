@@ -865,3 +865,33 @@ static __global__ void __launch_bounds__(1024) k_argmax_advance(const float * __
         st->n_past += n_advance;
     }
 }
+
+
+// the same for S lock-step streams: block s takes the argmax of logit row s (first index wins), feeds it back as stream s's next
+// token and logs it at id_log[step * S + s]; k_streams_advance then moves the step counter and n_past (one tiny launch: the S
+// blocks of k_argmax_rows read st->step, so it must not change under them)
+static __global__ void __launch_bounds__(1024) k_argmax_rows(const float * __restrict__ logits, int n_vocab, int * __restrict__ next_tok,
+                                                             int * __restrict__ id_log, const DevState * __restrict__ st, int n_streams) {
+    __shared__ float sv[32]; __shared__ int si[32];
+    const float * row = logits + (size_t) blockIdx.x * n_vocab;
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
+        const float v = row[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULLMASK, best, o); const int oi = __shfl_xor_sync(FULLMASK, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int) (blockDim.x >> 5); w++)
+            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+        if (bi == 0x7fffffff) bi = 0;
+        next_tok[blockIdx.x] = bi;
+        id_log[(size_t) st->step * n_streams + blockIdx.x] = bi;
+    }
+}
+static __global__ void k_streams_advance(DevState * st) { st->step += 1; st->n_past += 1; }

@@ -1,0 +1,100 @@
+// bgpt_topk.cuh -- the K largest logits on the device, for biogpt_sample_top_k_top_p (biogpt.cpp:908-980).
+//
+// The reference sorts all n_vocab (logit / temp, id) pairs with std::partial_sort, keeps top_k (default 40), and draws from their
+// softmax with std::discrete_distribution on std::mt19937.  Only the top_k pairs influence the draw, so the device returns exactly
+// those -- K (logit, id) pairs sorted by logit descending, 8 K bytes instead of 4 n_vocab -- and the host runs the reference's
+// double-precision softmax / top-p / RNG draw on them unchanged (host/biogpt_b200.cpp).  partial_sort leaves the order of EQUAL
+// values unspecified: when the K-th value is tied with the (K+1)-th, or two of the K values are equal, the kernel says so
+// (info[1] = 0) and the caller falls back to the full-logit path, so the drawn id is the reference's in every case.
+//
+// One CTA: the keys (order-preserving uint32 images of the floats) are staged in shared memory once (170 KB for 42384 logits),
+// the K-th largest key is found by a 4-pass radix select on 8-bit digits, the <= K survivors are ranked by counting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TOPK_NT 1024
+#define TOPK_MAXK 128
+
+__device__ __forceinline__ uint32_t topk_key(float f) {            // ascending float order -> ascending uint32 order
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// out_val / out_idx: K entries; info[0] = entries written (min(K, n)), info[1] = 1 if the selection and its order are unambiguous
+static __global__ void __launch_bounds__(TOPK_NT) k_topk(const float * __restrict__ logits, int n, int k, int staged,
+                                                          float * __restrict__ out_val, int * __restrict__ out_idx, int * __restrict__ info) {
+    extern __shared__ uint32_t s_keys[];                            // n keys when `staged`
+    __shared__ unsigned hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    __shared__ unsigned s_cnt, s_eq;
+    __shared__ uint32_t c_key[TOPK_MAXK]; __shared__ int c_idx[TOPK_MAXK];
+    __shared__ int s_dup;
+    const int tid = threadIdx.x;
+    if (k > n) k = n;
+    if (k > TOPK_MAXK) k = TOPK_MAXK;
+    if (staged) for (int i = tid; i < n; i += TOPK_NT) s_keys[i] = topk_key(logits[i]);
+    if (tid == 0) { s_prefix = 0u; s_remaining = (uint32_t) k; s_cnt = 0u; s_eq = 0u; s_dup = 0; }
+    __syncthreads();
+    uint32_t mask = 0u;
+    for (int pass = 3; pass >= 0; pass--) {
+        for (int b = tid; b < 256; b += TOPK_NT) hist[b] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        for (int i = tid; i < n; i += TOPK_NT) {
+            const uint32_t u = staged ? s_keys[i] : topk_key(logits[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {                                             // the digit of the remaining-th largest key among the survivors
+            uint32_t need = s_remaining, c = 0u; int bin = 0;
+            for (int b = 255; b >= 0; b--) { if (c + hist[b] >= need) { bin = b; break; } c += hist[b]; }
+            s_remaining = need - c;
+            s_prefix = prefix | ((uint32_t) bin << (8 * pass));
+        }
+        mask |= 0xFFu << (8 * pass);
+        __syncthreads();
+    }
+    const uint32_t thr = s_prefix;                                  // the K-th largest key; s_remaining of the keys equal to it are needed
+    const uint32_t need_eq = s_remaining;
+    for (int i = tid; i < n; i += TOPK_NT) {
+        const uint32_t u = staged ? s_keys[i] : topk_key(logits[i]);
+        if (u > thr) { const unsigned p = atomicAdd(&s_cnt, 1u); if (p < TOPK_MAXK) { c_key[p] = u; c_idx[p] = i; } }
+        else if (u == thr) atomicAdd(&s_eq, 1u);
+    }
+    __syncthreads();
+    const unsigned n_gt = s_cnt;                                    // = k - need_eq
+    // the keys equal to the threshold: lowest indices first (any choice is flagged when there are more than needed)
+    if (tid == 0) s_cnt = n_gt;
+    __syncthreads();
+    if (s_eq <= need_eq) {
+        for (int i = tid; i < n; i += TOPK_NT) {
+            const uint32_t u = staged ? s_keys[i] : topk_key(logits[i]);
+            if (u == thr) { const unsigned p = atomicAdd(&s_cnt, 1u); if (p < TOPK_MAXK) { c_key[p] = u; c_idx[p] = i; } }
+        }
+    } else if (tid == 0) {
+        unsigned got = 0;
+        for (int i = 0; i < n && got < need_eq; i++) {
+            const uint32_t u = staged ? s_keys[i] : topk_key(logits[i]);
+            if (u == thr) { c_key[n_gt + got] = u; c_idx[n_gt + got] = i; got++; }
+        }
+        s_dup = 1;                                                  // boundary tie: which of the equal values partial_sort keeps is unspecified
+    }
+    __syncthreads();
+    // rank by counting: key descending, index ascending among equals (equal keys are flagged)
+    if (tid < k) {
+        const uint32_t mk = c_key[tid]; const int mi = c_idx[tid];
+        int rank = 0;
+        for (int j = 0; j < k; j++) {
+            const uint32_t ok = c_key[j];
+            if (ok > mk || (ok == mk && c_idx[j] < mi)) rank++;
+            if (j != tid && ok == mk) s_dup = 1;
+        }
+        const uint32_t u = mk;
+        const uint32_t bits = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+        out_val[rank] = __uint_as_float(bits);
+        out_idx[rank] = mi;
+    }
+    __syncthreads();
+    if (tid == 0) { info[0] = k; info[1] = s_dup ? 0 : 1; }
+}

@@ -129,5 +129,12 @@ std::string    gpt_decode(std::vector<std::string> & tokens, const std::string &
 
 biogpt_vocab::id biogpt_sample_top_k_top_p(const biogpt_vocab & vocab, const float * logits, int top_k, double top_p, double temp, std::mt19937 & rng);
 
+// EXTENSION (not in the reference): biogpt_eval immediately followed by biogpt_sample_top_k_top_p on its logits, with the top_k
+// selection done on the device -- the returned id is the one the two reference calls would return (same RNG draw), but only
+// top_k (logit, id) pairs cross PCIe instead of the n_vocab logits.  Falls back to the two calls when
+// top_k > 128 or when equal logits make std::partial_sort's choice ambiguous.  Returns -1 on error.
+biogpt_vocab::id biogpt_eval_sample(const biogpt_model & model, const biogpt_vocab & vocab, const token_sequence & embed_inp,
+                                    const int n_past, int top_k, double top_p, double temp, std::mt19937 & rng);
+
 bool biogpt_params_parse(int argc, char ** argv, biogpt_params & params);
 void biogpt_print_usage(char ** argv, const biogpt_params & params);

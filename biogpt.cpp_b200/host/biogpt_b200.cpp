@@ -37,6 +37,9 @@ struct ggml_backend_buffer { size_t size = 0; };
 struct ggml_cgraph { int n_tokens = 0; int n_past = 0; size_t arena_bytes = 0; };
 struct ggml_allocr { bool measure = false; size_t last_size = 0; };
 
+// the device engine behind a loaded model (replicas.cpp drives it directly for multi-stream calls)
+bgpt_model * bgpt_host_engine_of(const biogpt_model & model) { return model.ctx ? model.ctx->engine : nullptr; }
+
 static std::chrono::steady_clock::time_point g_t0;
 
 extern "C" {
@@ -348,17 +351,8 @@ std::string gpt_decode(std::vector<std::string> & tokens, const std::string & la
 // ------------------------------------------------------------------------------------------------
 // sampler: identical draw to the reference for the same rng state (std::discrete_distribution)
 // ------------------------------------------------------------------------------------------------
-biogpt_vocab::id biogpt_sample_top_k_top_p(const biogpt_vocab & vocab, const float * logits, int top_k, double top_p, double temp, std::mt19937 & rng) {
-    const int n_logits = (int) vocab.id_to_token.size();
-    top_k = std::max(1, std::min(top_k, n_logits));
-    std::vector<std::pair<double, biogpt_vocab::id>> cand;
-    cand.reserve(n_logits);
-    const double inv_temp = 1.0 / temp;
-    for (int i = 0; i < n_logits; i++) cand.emplace_back(logits[i] * inv_temp, i);
-    std::partial_sort(cand.begin(), cand.begin() + top_k, cand.end(),
-                      [](const std::pair<double, biogpt_vocab::id> & a, const std::pair<double, biogpt_vocab::id> & b) { return a.first > b.first; });
-    cand.resize(top_k);
-
+// softmax over the sorted candidates, top-p cut and the draw: the tail of the reference function, shared by both entry points
+static biogpt_vocab::id draw_from_sorted(std::vector<std::pair<double, biogpt_vocab::id>> & cand, int top_k, double top_p, std::mt19937 & rng) {
     double maxl = -INFINITY;
     for (const auto & c : cand) maxl = std::max(maxl, c.first);
     std::vector<double> probs;
@@ -378,6 +372,42 @@ biogpt_vocab::id biogpt_sample_top_k_top_p(const biogpt_vocab & vocab, const flo
     }
     std::discrete_distribution<> dist(probs.begin(), probs.end());
     return cand[dist(rng)].second;
+}
+
+biogpt_vocab::id biogpt_sample_top_k_top_p(const biogpt_vocab & vocab, const float * logits, int top_k, double top_p, double temp, std::mt19937 & rng) {
+    const int n_logits = (int) vocab.id_to_token.size();
+    top_k = std::max(1, std::min(top_k, n_logits));
+    std::vector<std::pair<double, biogpt_vocab::id>> cand;
+    cand.reserve(n_logits);
+    const double inv_temp = 1.0 / temp;
+    for (int i = 0; i < n_logits; i++) cand.emplace_back(logits[i] * inv_temp, i);
+    std::partial_sort(cand.begin(), cand.begin() + top_k, cand.end(),
+                      [](const std::pair<double, biogpt_vocab::id> & a, const std::pair<double, biogpt_vocab::id> & b) { return a.first > b.first; });
+    cand.resize(top_k);
+    return draw_from_sorted(cand, top_k, top_p, rng);
+}
+
+biogpt_vocab::id biogpt_eval_sample(const biogpt_model & model, const biogpt_vocab & vocab, const token_sequence & embed_inp,
+                                    const int n_past, int top_k, double top_p, double temp, std::mt19937 & rng) {
+    if (!model.ctx || !model.ctx->engine || embed_inp.empty()) return -1;
+    const int n_vocab = model.hparams.n_vocab;
+    top_k = std::max(1, std::min(top_k, n_vocab));
+    static thread_local std::vector<float> full;
+    if (top_k > 128 || !(temp > 0.0)) {                            // outside the device selector's range: the reference's two calls
+        if (!biogpt_eval(model, embed_inp, full, nullptr, n_past, 0)) return -1;
+        return biogpt_sample_top_k_top_p(vocab, full.data(), top_k, top_p, temp, rng);
+    }
+    float vals[128]; int32_t ids[128]; int n_out = 0, exact = 0;
+    full.resize(n_vocab);
+    const int rc = bgpt_cuda_eval_topk(model.ctx->engine, embed_inp.data(), (int) embed_inp.size(), n_past, top_k, vals, ids, &n_out, &exact, full.data());
+    if (rc != BGPT_OK) { fprintf(stderr, "%s: %s\n", __func__, bgpt_cuda_last_error()); return -1; }
+    if (!exact) return biogpt_sample_top_k_top_p(vocab, full.data(), top_k, top_p, temp, rng);      // tied logits: the full path decides
+    // the device returned the top_k pairs by logit descending; logit * (1 / temp) in double keeps that order (temp > 0)
+    std::vector<std::pair<double, biogpt_vocab::id>> cand;
+    cand.reserve(n_out);
+    const double inv_temp = 1.0 / temp;
+    for (int i = 0; i < n_out; i++) cand.emplace_back(vals[i] * inv_temp, ids[i]);
+    return draw_from_sorted(cand, n_out, top_p, rng);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -72,6 +72,12 @@ int bgpt_host_eval(void * h, const int32_t * tokens, int n, int n_past, float * 
     memcpy(logits_out, s->logits.data(), s->logits.size() * sizeof(float));
     return 0;
 }
+// biogpt_eval_sample (device top-k + host draw): the id biogpt_eval + biogpt_sample_top_k_top_p would return
+int bgpt_host_eval_sample(void * h, const int32_t * tokens, int n, int n_past, int top_k, double top_p, double temp, uint32_t seed) {
+    Session * s = (Session *) h;
+    std::mt19937 rng(seed);
+    return biogpt_eval_sample(s->model, s->vocab, token_sequence(tokens, tokens + n), n_past, top_k, top_p, temp, rng);
+}
 int bgpt_host_tokenize(void * h, const char * text, int32_t * out, int cap) {
     Session * s = (Session *) h;
     const token_sequence ids = gpt_tokenize(s->vocab, text, "en");

@@ -98,6 +98,15 @@ int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, int n, int n
 const float * bgpt_cuda_logits_device(bgpt_model * m);
 int bgpt_cuda_synchronize(bgpt_model * m);
 
+/* biogpt_eval + the K largest logits of the returned row, selected on the device (csrc/bgpt_topk.cuh), for
+ * biogpt_sample_top_k_top_p (biogpt.cpp:908-980): only the top_k (logit, id) pairs influence the reference's draw, so 8 K + 8
+ * bytes cross PCIe per token instead of 4 n_vocab.  vals / ids (HOST, K entries) are sorted by logit descending; *n_out =
+ * min(K, n_vocab).  *exact = 0 when equal values make std::partial_sort's selection or order ambiguous -- then the whole logit row
+ * is copied to logits_fallback (HOST, n_vocab floats; may be NULL) and the caller runs the reference's sampler on it, so the
+ * drawn id is the reference's in every case.  K <= 128. */
+int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
+                        float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback);
+
 /* Greedy decode entirely on the device: starting from `first_token` at position n_past,
  * run `n_steps` evals of one token each, feeding argmax(logits) back in (first index wins
  * ties, like std::partial_sort with top_k = 1 in biogpt_sample_top_k_top_p,
@@ -154,6 +163,11 @@ int bgpt_cuda_set_streams(bgpt_model * m, int n_streams);
  * on the HOST (may be NULL to leave them on the device). */
 int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, int n_streams, int n_past,
                            float * logits_out);
+
+/* greedy decode of n_streams lock-step streams entirely on the device: n_steps forward passes over the n_streams rows, per-row
+ * argmax fed back on the device, one synchronisation at the end.  ids_out (HOST) = [n_steps][n_streams]; ms_out = device time. */
+int bgpt_cuda_decode_greedy_streams(bgpt_model * m, const int32_t * first_tokens, int n_streams, int n_past, int n_steps,
+                                    int32_t * ids_out, float * ms_out);
 
 /* ---- introspection ---------------------------------------------------------------------- */
 void   bgpt_cuda_hparams(const bgpt_model * m, int32_t out7[7]);

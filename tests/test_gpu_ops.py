@@ -195,3 +195,22 @@ def test_quantize_weights_equals_reference_quantiser(capi, name):
         want = gf.QUANTIZERS[t](x)
         bad = np.flatnonzero(got != want)
         assert bad.size == 0, f"{name} case {i}: {bad.size}/{got.size} bytes differ, first at {bad[:8]} (block {bad[0] // gf.TYPE_SIZE[t]})"
+
+
+def test_device_topk_selects_what_partial_sort_selects(capi, zoo):
+    """bgpt_cuda_eval_topk: K (logit, id) pairs sorted by logit descending == the K best of the full logit row (stable order is
+    irrelevant: ties are flagged `exact = False` and come with the full row)"""
+    M = capi.Model.load(zoo.path("small", "q8_0"))
+    toks = gf.synth_tokens(12, gf.SMALL.n_vocab, seed=3)
+    for t, n_past in ((toks[:8], 0), (toks[8:9], 8), (toks[9:10], 9)):
+        full = M.eval(t, n_past)
+        for k in (1, 5, 40, 128):
+            vals, ids, exact, fb = M.eval_topk(t, n_past, k)
+            order = np.argsort(-full, kind="stable")[:k]
+            if exact:
+                assert ids.tolist() == order.tolist() and np.array_equal(vals.view(np.uint32), full[order].view(np.uint32)), (n_past, k)
+                assert fb is None
+            else:                                          # equal logits somewhere in the top K: the full row must have come along
+                assert fb is not None and np.array_equal(fb.view(np.uint32), full.view(np.uint32))
+            assert np.array_equal(np.sort(vals)[::-1], vals)
+    M.close()

@@ -28,6 +28,7 @@ def host():
     L.bgpt_host_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
     L.bgpt_host_close.argtypes = [C.c_void_p]
     L.bgpt_host_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint32]
+    L.bgpt_host_eval_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint32]
     return L
 
 
@@ -130,3 +131,30 @@ def test_cpp_api_eval_matches_oracle(host, checkers, zoo, ftype):
     n = host.bgpt_host_tokenize(h, b"a b c", ids.ctypes.data, 16)
     assert ids[:n].tolist() == [2, 4, 5, 6]          # "a b c" -> 2 4 5 6
     host.bgpt_host_close(h); O.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,ftype", [("small", "q4_0"), ("narrow", "q5_1"), ("small", "f16")])
+def test_device_topk_sampler_draws_the_reference_id(host, checkers, zoo, size, ftype):
+    """biogpt_eval_sample (top_k selection on the device, csrc/bgpt_topk.cuh; softmax / top-p / mt19937 draw on the host) returns the
+    id that the reference's biogpt_sample_top_k_top_p (biogpt.cpp:908-980) draws from the full logits: 20 seeds x the 4 settings of
+    test_sampler_draw_identical_to_reference, on a prompt batch and on decode steps"""
+    if not checkers.have_ref():
+        pytest.skip("reference build not available")
+    hp = {"small": gf.SMALL, "narrow": gf.NARROW}[size]
+    p = zoo.path(size, ftype)
+    h = host.bgpt_host_open(p.encode(), 8)
+    assert h
+    R = checkers.Ref(p)
+    toks = gf.synth_tokens(16, hp.n_vocab, seed=5)
+    logits = np.zeros(hp.n_vocab, np.float32)
+    evals = [(toks[:8], 0)] + [(toks[8 + i:9 + i], 8 + i) for i in range(4)]
+    for t, n_past in evals:
+        t = np.ascontiguousarray(t)
+        assert host.bgpt_host_eval(h, t.ctypes.data, len(t), n_past, logits.ctypes.data) == 0
+        for seed in range(20):
+            for top_k, top_p, temp in ((1, 1.0, 1.0), (40, 0.9, 0.9), (5, 0.5, 1.3), (128, 1.0, 0.7)):
+                want = R.sample(logits, top_k, top_p, temp, seed)
+                got = host.bgpt_host_eval_sample(h, t.ctypes.data, len(t), n_past, top_k, top_p, temp, seed)
+                assert got == want, (n_past, seed, top_k, top_p, temp)
+    host.bgpt_host_close(h); R.close()
