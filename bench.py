@@ -6,8 +6,9 @@ decode over the whole context (n_past 0 -> seq-1), synthetic weights at the true
 (seed 1234), greedy sampling.  One "step" = one such sequence (seq tokens).
 
   value     device-resident: ids fed back on the GPU (bgpt_cuda_decode_greedy), CUDA events
-  e2e       the reference-facing call per token: bgpt_cuda_eval with HOST buffers (ids H2D,
-            42384 logits D2H inside the call) + host argmax, wall clock around the loop
+  e2e       the reference-facing call per token with HOST buffers: bgpt_cuda_eval_topk (token id H2D, the
+            top-40 (logit, id) pairs D2H -- what biogpt_sample_top_k_top_p needs) + the host's pick,
+            wall clock around the loop
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured
             HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, built from /root/reference by
@@ -131,44 +132,74 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def cpu_reference_tokens_per_s(ftype: str, seq: int, budget_s: float, threads: int):
-    """the reference's own biogpt_eval on the host cores, sampled at evenly spaced positions of
-    the same decode workload; returns (tokens/s, description, kind)."""
+def workload_config(ftype: str, seq: int, world: int) -> dict:
+    """the SAME dict for both arms (the driver compares them)"""
+    return {"workload": f"BioGPT-base {ftype} decode, batch 1, seq 1->{seq} (BASELINE.json configs[1])",
+            "ftype": ftype, "seq": seq, "streams_per_gpu": 1, "parallelism": f"replicas x{world}",
+            "l2": "inputs larger than L2: every token streams the full weight set (+KV) through the cache",
+            "parity": "logits bit-identical to the reference CPU path (tests/test_gpu_eval.py)"}
+
+
+_REF_CACHE = {}
+
+
+def _ref_handle(ftype: str, threads: int):
+    """the reference (oracle/_ref: the UNMODIFIED sources, oracle/Makefile) or, where it was not built, the C port"""
     import ref
-    path = model_path(ftype)
+    if ftype not in _REF_CACHE:
+        path = model_path(ftype)
+        _REF_CACHE[ftype] = (ref.Ref(path, n_batch=8, n_threads=threads), "reference") if ref.have_ref() else (ref.Oracle(path), "port")
+    R, kind = _REF_CACHE[ftype]
+    if kind == "reference":
+        R.n_threads = threads
+    return R, kind
+
+
+def _ref_time(R, kind, tok, p, reps) -> float:
+    if kind == "reference":
+        return R.time_eval_us(tok, p, reps) / 1e6
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        R.eval(tok, p)
+    return time.perf_counter() - t0
+
+
+def best_reference_threads(ftype: str, seq: int):
+    """ggml's spin-barrier pool is sensitive to oversubscription: try 4 (the reference's default -t), 8, 16 and nproc threads on a
+    short sample at mid-context and keep the fastest (`-t nproc` and `-t 4`)."""
+    nproc = os.cpu_count() or 1
+    cands = sorted({t for t in (4, 8, 16, nproc) if 1 <= t <= nproc})
+    tok = np.array([1234], dtype=np.int32)
+    res = {}
+    for t in cands:
+        R, kind = _ref_handle(ftype, t)
+        if kind != "reference":
+            return 1, {1: None}
+        _ref_time(R, kind, tok, seq // 2, 2)
+        res[t] = 8 / _ref_time(R, kind, tok, seq // 2, 8)
+    best = max(res, key=res.get)
+    return best, {k: round(v, 1) for k, v in res.items()}
+
+
+def cpu_reference_tokens_per_s(ftype: str, seq: int, budget_s: float, threads: int):
+    """the reference's own biogpt_eval on the host cores, sampled at evenly spaced positions of the same decode workload;
+    returns (tokens/s, description, kind, seconds actually spent)."""
     positions = [int(round(x)) for x in np.linspace(0, seq - 1, 9)]
     tok = np.array([1234], dtype=np.int32)
-    if ref.have_ref():
-        R = ref.Ref(path, n_batch=8, n_threads=threads)
-        kind = "reference"
-
-        def run(p, reps):
-            return R.time_eval_us(tok, p, reps) / 1e6
-    else:
-        R = ref.Oracle(path)
-        kind = "port"
-
-        def run(p, reps):
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                R.eval(tok, p)
-            return time.perf_counter() - t0
-    run(0, 2)  # warm-up (page in the weights, spin up threads)
+    R, kind = _ref_handle(ftype, threads)
+    _ref_time(R, kind, tok, 0, 2)  # warm-up (page in the weights, spin up threads)
+    first = _ref_time(R, kind, tok, positions[len(positions) // 2], 1)
+    reps = min(256, max(1, int(budget_s / max(first, 1e-4) / len(positions))))
     per_tok = []
     t_spent = 0.0
-    reps = 1
-    first = run(positions[len(positions) // 2], 1)
-    reps = max(1, int(budget_s / max(first, 1e-4) / len(positions)))
-    reps = min(reps, 256)
     for p in positions:
-        dt = run(p, reps)
+        dt = _ref_time(R, kind, tok, p, reps)
         per_tok.append(dt / reps)
         t_spent += dt
-    R.close()
     tps = 1.0 / float(np.mean(per_tok))
     sample = (f"{reps} evals of N=1 at each n_past in {positions} ({len(positions) * reps} tokens, "
               f"{t_spent:.1f} s), tokens/s = 1/mean(time per token)")
-    return tps, sample, kind
+    return tps, sample, kind, t_spent
 
 
 def side_configs(capi, device: int, seq: int):
@@ -193,32 +224,97 @@ def side_configs(capi, device: int, seq: int):
         "workload": f"BioGPT-base Q8_0, {seq} prompt tokens in {seq // 8} un-masked evals of 8 rows (BASELINE.json configs[2])",
         "tokens_per_s": seq / (ms / 1e3), "tokens_per_s_host_buffers_wall": seq / wall, "ms_total": ms, "tflops": flops / (ms / 1e3) / 1e12,
         "roofline": {"bound": "hbm", "achieved": nbytes / (ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": nbytes / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "note": "AI ~ 15 FLOP/B at 8 rows: HBM-bound by SURVEY 8(d)"},
+                     "frac": nbytes / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "note": "AI ~ 15 FLOP/B at 8 rows: HBM-bound by SURVEY 8(d)",
+                     "traffic": _traffic("prompt_q8_0_n_batch_8")},
         "schedule": "fused skinny-batch" if M.batch_path(8) else "per-operator", "launches_per_eval": None}
     l0 = M.launch_count; M.eval(toks[:8], 0); out["prompt_q8_0_n_batch_8"]["launches_per_eval"] = M.launch_count - l0
     M.close()
-    # ---- configs[3]: 8 independent sequences per GPU in lock step, each with its own F32 KV cache, greedy ids on the host
+    # ---- configs[3]: 8 independent sequences per GPU in lock step, each with its own F32 KV cache.  Device-resident: the greedy loop
+    #      runs on the GPU (bgpt_cuda_decode_greedy_streams); host buffers: one bgpt_cuda_eval_streams call per step, logits D2H
     S = 8
     M = capi.Model.load(model_path("q5_1"), device=device, max_batch=S)
     M.set_streams(S)
     first = gf.synth_tokens(S, gf.BASE.n_vocab, seed=9).astype(np.int32)
-    for rep in range(2):
-        cur = first.copy(); ms = 0.0; nbytes = 0.0
-        t0 = time.perf_counter()
-        for p in range(seq):
-            logits = M.eval_streams(cur, p)
-            ms += M.last_eval_ms
-            cur = np.argmax(logits, axis=1).astype(np.int32)
-            nbytes += bytes_per_token("q5_1", p) + (S - 1) * (196_608 * (p + 1) + 196_608 + 169_536 + 2 * 768)
-        wall = time.perf_counter() - t0
+    M.decode_greedy_streams(first, 0, seq)
+    ids_dev, ms = M.decode_greedy_streams(first, 0, seq)
+    nbytes = sum(bytes_per_token("q5_1", p) + (S - 1) * (196_608 * (p + 1) + 196_608 + 169_536 + 2 * 768) for p in range(seq))
+    cur = first.copy()
+    t0 = time.perf_counter()
+    ids_host = []
+    for p in range(seq):
+        logits = M.eval_streams(cur, p)
+        cur = np.argmax(logits, axis=1).astype(np.int32)
+        ids_host.append(cur.copy())
+    wall = time.perf_counter() - t0
     out["streams_q5_1_x8"] = {
         "workload": f"BioGPT-base Q5_1, {S} lock-step streams on one GPU, seq 1->{seq} (BASELINE.json configs[3], per GPU)",
         "tokens_per_s": S * seq / (ms / 1e3), "tokens_per_s_host_buffers_wall": S * seq / wall, "us_per_step": ms * 1e3 / seq,
+        "ids_equal_host_loop": bool(np.array_equal(np.stack(ids_host), ids_dev)),
         "roofline": {"bound": "hbm", "achieved": nbytes / (ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": nbytes / (ms / 1e3) / 1e9 / pk["hbm_gbs"]},
+                     "frac": nbytes / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": _traffic("streams_q5_1_x8")},
         "schedule": "fused skinny-batch" if M.batch_path(S) else "per-operator"}
     M.close()
+    # ---- configs[0]: the reference's own CPU-runnable case -- F16, a 4-token prompt as one N = 4 batch, then 15 single-token evals
+    #      (-n 16); reported like main.cpp:160 (predict ms and ms per token), the reference on the host cores beside it
+    toks4 = gf.synth_tokens(4, gf.BASE.n_vocab, seed=1)
+    M = capi.Model.load(model_path("f16"), device=device, max_batch=8)
+
+    def run_ours():
+        t0 = time.perf_counter()
+        l = M.eval(toks4, 0); ids = [int(np.argmax(l))]
+        for i in range(15):
+            l = M.eval(np.array([ids[-1]], np.int32), 4 + i); ids.append(int(np.argmax(l)))
+        return (time.perf_counter() - t0) * 1e3, ids
+    run_ours()
+    ours_ms, ours_ids = run_ours()
+    gen_f16 = M.decode_generation
+    M.close()
+    c0 = {"workload": "BioGPT-base F16, 4-token prompt (one N = 4 batch) + 15 single-token evals, n_predict = 16 (BASELINE.json configs[0])",
+          "b200_predict_ms": ours_ms, "b200_ms_per_token": ours_ms / 19, "b200_decode_kernel_generation": gen_f16}
+    try:
+        import ref
+        if ref.have_ref():
+            threads, _ = best_reference_threads("f16", seq)
+            R, kind = _ref_handle("f16", threads)
+            best = None
+            for rep in range(3):
+                t0 = time.perf_counter()
+                l = R.eval(toks4, 0); rids = [int(np.argmax(l))]
+                for i in range(15):
+                    l = R.eval(np.array([rids[-1]], np.int32), 4 + i); rids.append(int(np.argmax(l)))
+                dt = (time.perf_counter() - t0) * 1e3
+                best = dt if best is None else min(best, dt)
+            c0.update({"reference_cpu_predict_ms": best, "reference_cpu_ms_per_token": best / 19, "reference_threads": threads,
+                       "ids_identical": rids == ours_ids})
+    except Exception as e:
+        c0["reference_error"] = repr(e)
+    out["f16_cpu_case"] = c0
+    # ---- configs[4]: format sweep at n_past 511 (single-token decode): us per token, GB/s of algorithmic bytes, fraction of peak
+    sweep = {}
+    for ft in ("f16", "q4_0", "q4_1", "q5_0", "q5_1", "q8_0"):
+        M = capi.Model.load(model_path(ft), device=device, max_batch=8)
+        M.decode_greedy(2, 496, 16)
+        _, ms = M.decode_greedy(2, 496, 32)                  # n_past 496..527, mean position 511.5
+        us = ms * 1e3 / 32
+        b = np.mean([bytes_per_token(ft, p) for p in range(496, 528)])
+        sweep[ft] = {"us_per_token": us, "gb_per_s": b / us / 1e3, "frac_of_hbm_peak": b / us / 1e3 / pk["hbm_gbs"],
+                     "decode_kernel_generation": M.decode_generation}
+        M.close()
+    out["format_sweep_n_past_511"] = {"workload": "single-token decode at n_past ~511, all six formats (BASELINE.json configs[4])", "formats": sweep}
     return out
+
+
+def _traffic(key: str):
+    """dram__bytes_read + dram__bytes_write per launch of the skinny-batch schedule's matmul kernels, from the committed
+    `ncu --set full` capture (profiles/r1_skinny_mm_ncu_summary.json: 8 Q5_1 streams at n_past 511; the matmul kernels read their
+    weight slice exactly once, e.g. fc1 = 4096 x 1024 Q5_1 rows = 3,145,728 B algorithmic against 3,211,520 B measured)"""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_skinny_mm_ncu_summary.json")))
+        return {"source": prof["source"], "config": key,
+                "launches": [{"kernel": l["kernel"], "grid": l["grid"], "dram_bytes": l["dram_bytes_read"] + l["dram_bytes_write"],
+                              "duration_us": l["duration_us"]} for l in prof["launches"]]}
+    except Exception:
+        return None
 
 
 def run_streams_workload(args, capi, dist, barrier, rank, local_rank, world):
@@ -282,23 +378,27 @@ def run_streams_workload(args, capi, dist, barrier, rank, local_rank, world):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  A "step" is a BOUNDED sample
+    of the workload (9 evenly spaced positions of the 1024-token decode, `reps` evals each); ms_per_step is the time that sample
+    really took, value = tokens/s over the sample.  Threads: best of {4, 8, 16, nproc}."""
     rank, local_rank, world = dist_env()
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    vals = []
+    threads, sweep = best_reference_threads(args.ftype, args.seq)
+    vals, secs = [], []
     sample = kind = ""
+    per_step = args.cpu_budget / max(1, args.steps + args.warmup)
     for i in range(args.warmup + args.steps):
-        tps, sample, kind = cpu_reference_tokens_per_s(args.ftype, args.seq, args.cpu_budget / max(1, args.steps), threads)
+        tps, sample, kind, spent = cpu_reference_tokens_per_s(args.ftype, args.seq, per_step, threads)
         if i >= args.warmup:
-            vals.append(tps)
+            vals.append(tps); secs.append(spent)
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * args.seq / v, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8*int8->f32 (Q8_0 activations), f32 KV", "data": "synthetic",
-            "config": {"workload": f"BioGPT-base {args.ftype} decode, batch 1, seq 1->{args.seq}", "ftype": args.ftype,
-                       "seq": args.seq, "l2": "weights (194 MB+) exceed any CPU cache"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "config": workload_config(args.ftype, args.seq, world),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": "per step: " + sample,
+                             "threads_tried_tokens_per_s": sweep, "host_cores": os.cpu_count()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -339,7 +439,6 @@ def main():
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
-        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to stdout: rank 0 prints ONE json line
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
         if rank == 0:
@@ -387,12 +486,14 @@ def main():
     # ---- e2e: the reference-facing call per token with host buffers
     e2e = None
     if not args.no_e2e:
+        TOPK = 40                                    # the reference's default top_k (biogpt.h:113)
+
         def e2e_pass():
             tok = np.array([first_token], dtype=np.int32)
             out = []
             for p in range(seq):
-                logits = M.eval(tok, p)
-                nxt = int(np.argmax(logits))
+                vals, tids, exact, full = M.eval_topk(tok, p, TOPK)      # id H2D, 40 (logit, id) pairs D2H, inside the call
+                nxt = int(tids[0]) if exact else int(np.argmax(full))     # greedy = top_k 1: the best candidate (ties: the full row decides)
                 out.append(nxt)
                 tok[0] = nxt
             return out
@@ -410,7 +511,8 @@ def main():
             dt = float(t.item())
         assert ids is None or e2e_ids == ids.tolist(), "device-side greedy ids differ from the host-sampled ids"
         e2e = {"value": world * seq * args.steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": seq * (4 + 16), "d2h_bytes_per_step": seq * M.n_vocab * 4}
+               "h2d_bytes_per_step": seq * 4, "d2h_bytes_per_step": seq * (8 * TOPK + 8),
+               "call": "bgpt_cuda_eval_topk (C ABI; what biogpt_eval_sample calls): host token in, top-40 (logit, id) pairs out"}
 
     if rank != 0:
         M.close()
@@ -427,27 +529,28 @@ def main():
     achieved = total_bytes / (step_ms / 1e3) / 1e9
     traffic = None
     try:   # dram__bytes_read+write of one k_mega launch from the committed ncu capture (profiles/)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_mega4_ncu_summary.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r2_mega5_ncu_summary.json" if M.decode_generation == 5 else "r1_mega4_ncu_summary.json")))
         if prof.get("ftype") == args.ftype:
             traffic = {"bytes_per_launch": prof["dram_bytes_per_launch"], "at_n_past": prof["n_past"],
                        "algorithmic_bytes_at_that_n_past": bytes_per_token(args.ftype, prof["n_past"]), "source": prof["source"]}
     except Exception:
         pass
     gen = M.decode_generation
-    kname = {4: "k_mega4", 3: "k_mega"}.get(gen, "per-operator kernels")
+    kname = {5: "k_mega5", 4: "k_mega4", 3: "k_mega"}.get(gen, "per-operator kernels")
     roofline = {"bound": "hbm", "kernel": f"{kname}<{args.ftype}> (persistent decode kernel, generation {gen}, 1 launch per token; mean over n_past 0..{seq - 1})",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                 "algorithmic_bytes_per_launch_mean": total_bytes / seq,
                 "us_per_launch_mean": step_ms * 1e3 / seq,
-                "note": "latency-bound: a batch-1 step is a chain of 5 all-to-all exchanges per layer through L2 (~1 us each) plus "
-                        "LayerNorm / dot / softmax latencies between them (profiles/README.md, DESIGN.md 4.2); bytes are not the limit"}
+                "note": "latency-bound: a batch-1 step is a chain of 4 all-to-all exchanges through L2 and 2 cluster exchanges per layer "
+                        "(~0.8 us each) plus LayerNorm / dot / softmax latencies between them (profiles/README.md, DESIGN.md 4.2); bytes are not the limit"}
 
     cpu = None
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        tps, sample, kind = cpu_reference_tokens_per_s(args.ftype, seq, args.cpu_budget, threads)
-        cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+        threads, sweep = best_reference_threads(args.ftype, seq)
+        tps, sample, kind, _ = cpu_reference_tokens_per_s(args.ftype, seq, args.cpu_budget, threads)
+        cpu = {"value": tps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+               "threads_tried_tokens_per_s": sweep, "host_cores": os.cpu_count()}
 
     extras = None
     if not args.no_extras:
@@ -461,10 +564,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8*int8->f32 (Q8_0 activations), f32 KV", "data": "synthetic",
-            "config": {"workload": f"BioGPT-base {args.ftype} decode, batch 1, seq 1->{seq} (BASELINE.json configs[1])",
-                       "ftype": args.ftype, "seq": seq, "streams_per_gpu": 1, "parallelism": f"replicas x{world}",
-                       "l2": "inputs larger than L2: every token streams the full 194 MB weight set (+KV) through a 126 MB L2",
-                       "parity": "logits bit-identical to the reference CPU path (tests/test_gpu_eval.py)"},
+            "config": workload_config(args.ftype, seq, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "other_configs": extras}
     emit(line)

@@ -1203,19 +1203,20 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         RET(forward(m, m->d_tokens, n, 0));
     }
     const int staged = (size_t) m->n_vocab * 4 <= (size_t) 200 * 1024;
-    float * dv = (float *) m->d_topk; int * di = (int *) (m->d_topk + TOPK_MAXK * 4); int * dinfo = (int *) (m->d_topk + TOPK_MAXK * 8);
+    // packed as [info: 2 ints][vals: k floats][ids: k ints] so that ONE copy of 8 + 8 k bytes brings everything back
+    int * dinfo = (int *) m->d_topk; float * dv = (float *) (m->d_topk + 8); int * di = (int *) (m->d_topk + 8 + (size_t) k * 4);
     k_topk<<<1, TOPK_NT, staged ? (size_t) m->n_vocab * 4 : 0, s>>>(m->logits, m->n_vocab, k, staged, dv, di, dinfo);
     m->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(m->h_topk, m->d_topk, tk_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(m->h_topk, m->d_topk, 8 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     if (mega && mega_generation(m) == 5) RET(check_mega5_error(m));
-    const int * hinfo = (const int *) (m->h_topk + TOPK_MAXK * 8);
+    const int * hinfo = (const int *) m->h_topk;
     *n_out = hinfo[0]; *exact = hinfo[1];
-    memcpy(vals, m->h_topk, (size_t) hinfo[0] * 4);
-    memcpy(ids, m->h_topk + TOPK_MAXK * 4, (size_t) hinfo[0] * 4);
+    memcpy(vals, m->h_topk + 8, (size_t) hinfo[0] * 4);
+    memcpy(ids, m->h_topk + 8 + (size_t) k * 4, (size_t) hinfo[0] * 4);
     if (!hinfo[1] && logits_fallback) CK(cudaMemcpy(logits_fallback, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost));
     return BGPT_OK;
 }

@@ -29,7 +29,7 @@ bench)
 trace5)
   for np in 4 507 1015; do BGPT_MEGA_PROF=1 timeout 200 python tools/trace_decode5.py --n-past $np; done > $OUT/trace.log 2>&1; grep -v "Warning\|nanm\|return np" $OUT/trace.log | head -150 ;;
 decode)
-  for ft in ${FTYPES:-q4_0}; do for np in 0 511 1000; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
+  for ft in ${FTYPES:-q4_0}; do for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
   cat $OUT/decode.log ;;
 esac
 done
