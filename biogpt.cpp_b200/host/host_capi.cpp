@@ -23,8 +23,11 @@ std::vector<std::string> split_lines(const char * s) {
 struct Session { biogpt_model model; biogpt_vocab vocab; ggml_allocr * allocr = nullptr; ggml_backend_buffer_t buf = nullptr; std::vector<float> logits; };
 }
 
+void bgpt_text_class_mask(int which, uint32_t out[8]);
+
 extern "C" {
 
+void bgpt_host_text_class_mask(int which, uint32_t * out8) { bgpt_text_class_mask(which, out8); }
 int bgpt_host_moses_tokenize(const char * text, char * out, int cap) { return join(moses_tokenize(text, "en"), out, cap); }
 int bgpt_host_moses_detokenize(const char * tokens_nl, char * out, int cap) {
     std::vector<std::string> v = split_lines(tokens_nl);

@@ -58,7 +58,10 @@ def test_moses_edge_cases(host):
         "Dr.", "Smith", "paid", "1,000", "dollars", ",", "e.g.", "in", "1990", "&apos;s", "."]
     buf = C.create_string_buffer(4096)
     host.bgpt_host_moses_detokenize("Hello\nWorld\n!\nIt\n&apos;s\nhow\n@-@\nto\n(\nfine\n)\n.".encode(), buf, len(buf))
-    assert buf.value.decode() == "Hello World! It's how-to (fine)."
+    # AS BUILT the reference's detokenizer neither unescapes XML entities (it drops the result of its regex_replace,
+    # mosestokenizer.cpp:386-390) nor attaches closing punctuation (its rule only matches one literal token, :419) and turns
+    # " @-@" into "-" keeping the space after it; tests/test_text.py pins 327 strings against the reference's output
+    assert buf.value.decode() == "Hello World ! It &apos;s how- to (fine ) ."
 
 
 def test_bpe_lowest_rank_merges_first(host):
