@@ -30,10 +30,10 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_topk", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
-    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
+    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_mul_mat_tcx", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
     "bgpt_cuda_op_attention", "bgpt_cuda_op_gelu", "bgpt_cuda_op_dequantize",
 ]
 
@@ -87,6 +87,7 @@ def lib():
     L.bgpt_cuda_op_quantize_weights.argtypes = [C.c_int, _f32p, C.c_longlong, _u8p]
     L.bgpt_cuda_get_eval_path.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_tc_min_rows.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_set_tcx_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
     L.bgpt_cuda_decode_greedy_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.POINTER(C.c_float)]
@@ -101,6 +102,7 @@ def lib():
     L.bgpt_cuda_set_taps.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.bgpt_cuda_op_mul_mat.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_mul_mat_tc.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+    L.bgpt_cuda_op_mul_mat_tcx.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_quantize_act.argtypes = [C.c_int, _f32p, _u8p, C.c_int]
     L.bgpt_cuda_op_norm.argtypes = [_f32p, C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float]
     L.bgpt_cuda_op_attention.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u16p]
@@ -244,6 +246,10 @@ class Model:
     def batch_path(self, n_rows: int) -> int:
         return int(lib().bgpt_cuda_get_batch_path(self.h, n_rows))
 
+    def set_tcx_min_rows(self, rows: int):
+        """bit-exact tcgen05 matmul for quantised evals of `rows`+ rows (default 128; 0 = off)"""
+        _check(lib().bgpt_cuda_set_tcx_min_rows(self.h, rows), "set_tcx_min_rows")
+
     def set_tc_min_rows(self, rows: int):
         """opt in to the tolerance-close integer tcgen05 matmul for quantised evals of `rows`+ rows (0 = off, the default)"""
         _check(lib().bgpt_cuda_set_tc_min_rows(self.h, rows), "set_tc_min_rows")
@@ -329,6 +335,15 @@ def op_mul_mat(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int) ->
     y = np.empty((n, rows), dtype=np.float32)
     _check(lib().bgpt_cuda_op_mul_mat(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
            "op_mul_mat")
+    return y
+
+
+def op_mul_mat_tcx(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, k = x.shape
+    y = np.empty((n, rows), dtype=np.float32)
+    _check(lib().bgpt_cuda_op_mul_mat_tcx(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
+           "op_mul_mat_tcx")
     return y
 
 

@@ -108,6 +108,9 @@ struct bgpt_model {
     // the integer tcgen05 batch matmul (bgpt_tc.cuh) is tolerance-close, not bit-identical: OFF unless asked for
     // (BGPT_TC_MIN_ROWS=<rows> or bgpt_cuda_set_tc_min_rows); evals of that many token rows then leave the exact kernels
     int tc_min_rows = 1 << 30;
+    // the bit-exact tcgen05 matmul (k_gemm_tc_x: the 8 running sums per row through masked activation columns) serves quantised
+    // evals of this many token rows and more on the per-operator schedule (BGPT_TCX_MIN_ROWS / bgpt_cuda_set_tcx_min_rows; 0 = off)
+    int tcx_min_rows = 128;
     bool mega_ok = false; int decode_path = 1;          // 1: k_mega for n == 1, 0: per-op kernels
     MegaParams mp{}; MegaLayer * d_mega_layers = nullptr; std::vector<MegaLayer> h_mega_layers;
     unsigned long long * d_bar = nullptr; unsigned long long bar_epoch = 0;
@@ -378,6 +381,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_KVPF")) m->sk_kv_prefetch = atoi(getenv("BGPT_SK_KVPF")) != 0;
     if (getenv("BGPT_SK_TN_FC1")) { const int v = atoi(getenv("BGPT_SK_TN_FC1")); m->sk_tn_fc1 = v == 8 ? 8 : (v == 4 ? 4 : 0); }
     if (getenv("BGPT_SK_FC1_SPLIT")) m->sk_fc1_split = atoi(getenv("BGPT_SK_FC1_SPLIT")) != 0;
+    if (getenv("BGPT_TCX_MIN_ROWS")) { const int v = atoi(getenv("BGPT_TCX_MIN_ROWS")); m->tcx_min_rows = v > 0 ? std::max(2, v) : (1 << 30); }
     if (getenv("BGPT_TC_MIN_ROWS")) { const int v = atoi(getenv("BGPT_TC_MIN_ROWS")); m->tc_min_rows = v > 0 ? std::max(2, v) : (1 << 30); }
     RET(mega_setup(m));
     m->finalized = true;
@@ -419,6 +423,8 @@ template <int FMT> static void launch_gemv_f_tn(int TN, dim3 grid, int threads, 
 
 static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
                           int n, int tok0, const Epi & epi);
+static int launch_gemm_tcx(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
+                           int n, int tok0, const Epi & epi);
 
 // y = W . act for rows tok0..n-1; W = up to 3 stacked matrices sharing one layout
 static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
@@ -432,6 +438,7 @@ static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W
     a.n = n; a.tok0 = tok0; a.epi = epi;
     const int cnt = n - tok0;
     if (bg_is_quant(L.type) && m && cnt >= m->tc_min_rows) return launch_gemm_tc(m, s, W, nmat, act, A, n, tok0, epi);
+    if (bg_is_quant(L.type) && m && cnt >= m->tcx_min_rows) return launch_gemm_tcx(m, s, W, nmat, act, A, n, tok0, epi);
     const int TN = cnt <= 1 ? 1 : cnt == 2 ? 2 : cnt <= 4 ? 4 : 8;
     const int gy = (cnt + TN - 1) / TN;
     const size_t smem = (size_t) TN * A.bytes;
@@ -476,6 +483,32 @@ static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * cons
     dim3 grid((a.M + TC_ROWS - 1) / TC_ROWS, (n - tok0 + TC_TOK - 1) / TC_TOK);
     const size_t smem = tc_smem_bytes();
     const void * fn = bgpt_k_gemm_tc_fn(L.type);
+    if (!fn) return fail(BGPT_E_UNSUPPORTED, "tensor-core matmul: type %d", L.type);
+    void * args[] = { &a };
+    CK(cudaLaunchKernel(fn, grid, dim3(TC_THREADS), args, smem, s));
+    if (m) m->launches++;
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+
+// the bit-exact tensor-core matmul (k_gemm_tc_x): tiles of 128 weight rows x 16 tokens
+static int launch_gemm_tcx(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
+                           int n, int tok0, const Epi & epi) {
+    const RowLayout & L = W[0]->L;
+    static unsigned long long done = 0;
+    const size_t smem = std::max(sizeof(TcxShared) + 128, (size_t) 120 * 1024);       // >= half the SM: one CTA (512 TMEM columns) per SM
+    if (first_use_on_current_device(done)) {
+        for (int t : { BG_Q4_0, BG_Q4_1, BG_Q5_0, BG_Q5_1, BG_Q8_0 }) cudaFuncSetAttribute(bgpt_k_gemm_tcx_fn(t), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaGetLastError();
+    }
+    GemvArgs a{};
+    for (int i = 0; i < 3; i++) a.W[i] = W[i < nmat ? i : 0]->ptr;
+    a.rows_per = (int) W[0]->ne1; a.M = a.rows_per * nmat; a.G = L.G; a.stride = L.stride;
+    a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
+    a.act = act; a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s;
+    a.n = n; a.tok0 = tok0; a.epi = epi;
+    dim3 grid((a.M + TC_ROWS - 1) / TC_ROWS, (n - tok0 + TCX_TOK - 1) / TCX_TOK);
+    const void * fn = bgpt_k_gemm_tcx_fn(L.type);
     if (!fn) return fail(BGPT_E_UNSUPPORTED, "tensor-core matmul: type %d", L.type);
     void * args[] = { &a };
     CK(cudaLaunchKernel(fn, grid, dim3(TC_THREADS), args, smem, s));
@@ -584,7 +617,7 @@ static int enqueue_forward(bgpt_model * m, const int * d_tokens, int n, int mode
 // ------------------------------------------------------------------------------------------
 static bool skinny_ok(const bgpt_model * m, int n) {
     return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff == 4096 &&
-           m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < m->tc_min_rows;
+           m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < std::min(m->tc_min_rows, m->tcx_min_rows);
 }
 static void sk_init_attrs() {
     static unsigned long long done = 0;
@@ -794,6 +827,14 @@ extern "C" int bgpt_cuda_set_tc_min_rows(bgpt_model * m, int rows) {
     m->tc_min_rows = rows == 0 ? (1 << 30) : std::max(2, rows);
     return BGPT_OK;
 }
+extern "C" int bgpt_cuda_set_tcx_min_rows(bgpt_model * m, int rows) {
+    if (!m || rows < 0) return fail(BGPT_E_ARG, "set_tcx_min_rows: bad arguments");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    drop_graphs(m);
+    m->tcx_min_rows = rows == 0 ? (1 << 30) : std::max(2, rows);
+    return BGPT_OK;
+}
 extern "C" int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows) { return m && skinny_ok(m, n_rows) ? 1 : 0; }
 static bool use_mega(const bgpt_model * m);
 // which schedule an eval of n_rows token rows takes: 3 persistent decode kernel, 1 fused skinny-batch schedule (exact), 2 per-operator
@@ -803,6 +844,7 @@ extern "C" int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows) {
     if (n_rows == 1 && use_mega(m)) return 3;
     if (skinny_ok(m, n_rows)) return 1;
     if (bg_is_quant(m->wtype) && n_rows >= m->tc_min_rows) return 2;
+    if (bg_is_quant(m->wtype) && n_rows >= m->tcx_min_rows) return 4;
     return 0;
 }
 
@@ -1603,6 +1645,27 @@ extern "C" int bgpt_cuda_debug_icache_bench(int kb, int iters, int nwarps, float
 }
 
 #endif  // BGPT_BENCH_TOOLS
+
+// y = W . x through the BIT-EXACT tcgen05 kernel regardless of n (parity tests; quantised types only)
+extern "C" int bgpt_cuda_op_mul_mat_tcx(int type, const void * w, const float * x, float * y, int k, int rows, int n) {
+    RET(need_device());
+    if (!bg_is_quant(type)) return fail(BGPT_E_UNSUPPORTED, "op_mul_mat_tcx: quantised weight types only");
+    if (!w || !x || !y || k <= 0 || k % 32 || rows <= 0 || n <= 0) return fail(BGPT_E_ARG, "op_mul_mat_tcx: bad arguments");
+    DevTensor t; t.type = type; t.ne0 = k; t.ne1 = rows;
+    RET(upload_matrix(t, type, k, rows, (const uint8_t *) w));
+    DevBuf wguard; wguard.p = t.ptr;
+    const ActLayout A = bg_act_layout(type, k);
+    DevBuf dx, da, dy;
+    RET(dx.alloc((size_t) n * k * 4)); RET(da.alloc((size_t) n * A.bytes)); RET(dy.alloc((size_t) n * rows * 4));
+    CK(cudaMemcpy(dx.p, x, (size_t) n * k * 4, cudaMemcpyHostToDevice));
+    RET(launch_act(nullptr, 0, dx.as<float>(), k, nullptr, nullptr, k, type, da.as<uint8_t>(), A, n, nullptr, 0));
+    const DevTensor * W[3] = { &t, nullptr, nullptr };
+    Epi e = make_epi(EPI_STORE, nullptr, dy.as<float>(), rows);
+    RET(launch_gemm_tcx(nullptr, 0, W, 1, da.as<uint8_t>(), A, n, 0, e));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(y, dy.p, (size_t) n * rows * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
 
 // y = W . x through the tcgen05 path regardless of n (parity tests; quantised types only)
 extern "C" int bgpt_cuda_op_mul_mat_tc(int type, const void * w, const float * x, float * y, int k, int rows, int n) {

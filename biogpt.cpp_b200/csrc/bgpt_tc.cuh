@@ -264,3 +264,196 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_q(GemvArgs a) {
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
 }
+
+// ================================================================================================================================
+// k_gemm_tc_x -- the same tensor-core matmul, BIT-EXACT: the reference's 8 running sums per row through tcgen05
+// ================================================================================================================================
+// The reference (AVX2) adds a block's 32 products in eight groups of four: isum_l = sum of elements 4l..4l+3, then
+// acc_l = fma(d_w * d_a, (float) isum_l, acc_l) per group l in block order, hsum_float_8 at the end (ggml.c:2518-2541 ...).  One
+// tcgen05.mma sums all of K = 32, so k_gemm_tc_q above can only deliver one term per block and drifts from the reference by ~5e-2
+// in the logits once activations are re-quantised 24 layers deep.  Here the ACTIVATION operand is expanded instead: token n
+// becomes eight columns (n, l), column (n, l) carrying the token's int8 codes in bytes 4l..4l+3 of the block and zeros elsewhere.
+// The MMA then produces D[row][(n, l)] = isum_l exactly (int32), i.e. all eight partial sums of 128 rows x 16 tokens per
+// instruction (M = 128, N = 128, K = 32), and the epilogue runs the reference's eight fma chains per (row, token) in block
+// order.  The tensor pipe does 8x redundant multiplications by zero; it has the room (the step is bound by the f32 epilogue:
+// 16 f32-pipe instructions per (row, token, block) -- the arithmetic the bit-exact contract prescribes).
+//
+// Tile: 128 weight rows x 16 tokens; a group of 4 blocks fills the 512 TMEM columns (4 x 128), single stage: the four MMAs of a
+// group take ~0.25 us against ~1.1 us of epilogue, so nothing is gained by splitting TMEM in two.  The zero pattern of the
+// activation operand is written once; a group only rewrites the 4-byte words that carry data.
+#define TCX_TOK 16
+#define TCX_N (TCX_TOK * 8)
+
+struct TcxShared {
+    uint8_t A[4][TC_ROWS * 32];        // [block in group][canonical K-major layout]
+    uint8_t B[4][TCX_N * 32];          // [block in group][column (n, l)][32 bytes]
+    float sw[4][TC_ROWS];              // weight scales d_w
+    float mw[4][TC_ROWS];              // weight mins   m_w   (Q4_1 / Q5_1)
+    float sa[4][TCX_TOK];              // activation scales d_a
+    float ss[4][TCX_TOK];              // activation s = d * sum(q) (Q8_1)
+    unsigned long long mbar;
+    uint32_t tmem_base;
+};
+__device__ __forceinline__ uint32_t tcx_idesc_i8() {          // D = S32, A = B = S8, both K-major, M = 128, N = 128
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (TCX_N >> 3) << 17) | ((uint32_t) (TC_ROWS >> 4) << 24);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_x(GemvArgs a) {
+    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+    TcxShared & S = *reinterpret_cast<TcxShared *>(tc_smem_raw);
+    constexpr bool IS8   = (FMT == BG_Q8_0);
+    constexpr bool HASQH = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM  = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * TC_ROWS;                 // first weight row of this tile (stacked row space)
+    const int tok0 = a.tok0 + blockIdx.y * TCX_TOK;        // first token row
+
+    if (tid == 0) { tc_mbar_init(tc_smem_u32(&S.mbar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the zero pattern of the expanded activation operand, once
+    for (int i = tid; i < (int) (sizeof(S.B) / 16); i += TC_THREADS) ((uint4 *) &S.B[0][0])[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t idesc = tcx_idesc_i8();
+
+    // ---- fill: load_group (global -> registers), store_group (unpack, registers -> shared memory)
+    const int frow = tid >> 1, fkc = tid & 1;               // weights: thread (row, kc): kc = 0 -> elements 0..15, 1 -> 16..31
+    const uint8_t * wrow;
+    {
+        int r = row0 + frow; r = r < a.M ? r : a.M - 1;
+        const int mat = r / a.rows_per;
+        wrow = a.W[mat] + (size_t) (r - mat * a.rows_per) * a.stride;
+    }
+    const int atk = tid >> 3, al = tid & 7;                 // activations: thread (token, element group l), tid < 8 * TCX_TOK
+    const bool a_thread = tid < 8 * TCX_TOK;
+    const bool a_valid = a_thread && (tok0 + atk) < a.n;
+    const uint8_t * arec = a.act + (size_t) (a_valid ? tok0 + atk : 0) * a.act_bytes;
+    uint4 wreg[4], areg; uint32_t qhreg[4]; uint2 sreg; float4 asreg;
+    auto load_group = [&](int g) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            wreg[j] = IS8 ? ldg_stream128(wrow + (size_t) ((g * 2 + fkc) * 4 + j) * 16) : ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
+            if (HASQH) qhreg[j] = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
+        }
+        sreg = make_uint2(0, 0);
+        if (fkc == 0) sreg = ldg_stream64(wrow + a.off_d + g * 8);
+        else if (HASM) sreg = ldg_stream64(wrow + a.off_m + g * 8);
+        asreg = make_float4(0.f, 0.f, 0.f, 0.f);
+        areg = make_uint4(0, 0, 0, 0);
+        if (a_valid) {
+            areg = *(const uint4 *) (arec + (size_t) (g * 8 + al) * 16);          // the codes of element group l for the 4 blocks
+            if (al == 0) asreg = *(const float4 *) (arec + a.off_dd + g * 16);
+            else if (HASM && al == 1) asreg = *(const float4 *) (arec + a.off_s + g * 16);
+        }
+    };
+    auto store_group = [&]() {
+        {
+            uint32_t out[4][4];                              // [block i][word j]
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t ww[4] = { wreg[j].x, wreg[j].y, wreg[j].z, wreg[j].w };
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t v = ww[i];
+                    if (!IS8) {
+                        v = fkc ? ((ww[i] >> 4) & 0x0F0F0F0Fu) : (ww[i] & 0x0F0F0F0Fu);
+                        if (HASQH) { const uint32_t hb = (qhreg[j] >> (8 * i)) & 0xFFu; v |= bg_spread4(fkc ? (hb >> 4) : (hb & 0xFu)); }
+                        if (FMT == BG_Q4_0) v = tc_sub8(v);
+                        if (FMT == BG_Q5_0) v = tc_sub16(v);
+                    }
+                    out[i][j] = v;
+                }
+            }
+            const int off = (frow >> 3) * 256 + fkc * 128 + (frow & 7) * 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) *(uint4 *) (&S.A[i][off]) = make_uint4(out[i][0], out[i][1], out[i][2], out[i][3]);
+            float * dst = (fkc == 0) ? &S.sw[0][0] : &S.mw[0][0];
+            if (fkc == 0 || HASM) {
+                dst[0 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.x & 0xFFFF)); dst[1 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.x >> 16));
+                dst[2 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.y & 0xFFFF)); dst[3 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.y >> 16));
+            }
+        }
+        if (a_thread) {
+            // column (n, l) = operand row n * 8 + l: 16-byte chunk l >> 2 of its 32 K bytes, word l & 3 -- everything else stays zero
+            const int off = atk * 256 + (al >> 2) * 128 + al * 16 + (al & 3) * 4;
+            *(uint32_t *) (&S.B[0][off]) = areg.x; *(uint32_t *) (&S.B[1][off]) = areg.y;
+            *(uint32_t *) (&S.B[2][off]) = areg.z; *(uint32_t *) (&S.B[3][off]) = areg.w;
+            if (al == 0) { S.sa[0][atk] = asreg.x; S.sa[1][atk] = asreg.y; S.sa[2][atk] = asreg.z; S.sa[3][atk] = asreg.w; }
+            else if (HASM && al == 1) { S.ss[0][atk] = asreg.x; S.ss[1][atk] = asreg.y; S.ss[2][atk] = asreg.z; S.ss[3][atk] = asreg.w; }
+        }
+    };
+
+    // ---- epilogue state: this thread owns row (quadrant * 32 + lane) and 8 of the 16 tokens: 8 running sums each
+    const int quad = warp & 3, chalf = warp >> 2;
+    const int erow = quad * 32 + lane;
+    float acc[8][8], summ[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) { summ[t] = 0.0f;
+#pragma unroll
+        for (int l = 0; l < 8; l++) acc[t][l] = 0.0f; }
+
+    const int G = a.G;
+    load_group(0);
+    for (int g = 0; g < G; g++) {
+        store_group();                                     // the previous group's operands and accumulators were drained
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                tc_mma_i8(tmem + (uint32_t) (i * TCX_N), tc_make_desc(tc_smem_u32(&S.A[i][0])), tc_make_desc(tc_smem_u32(&S.B[i][0])), idesc, 0u);
+            tc_commit(tc_smem_u32(&S.mbar));
+        }
+        if (g + 1 < G) load_group(g + 1);                  // in flight during the MMAs and the epilogue
+        tc_mbar_wait(tc_smem_u32(&S.mbar), (uint32_t) (g & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // the reference's chains: for every block in order, acc_l = fma(d_w * d_a, (float) isum_l, acc_l); summs = fma(m_w, s_a, summs)
+        uint32_t v[2][32];
+        const uint32_t tbase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (chalf * 64);
+        tc_ld32(tbase, v[0]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float dw = S.sw[i][erow];
+            const float mwv = HASM ? S.mw[i][erow] : 0.0f;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {                   // 32 columns = 4 tokens x 8 sums per load
+                const int k = i * 2 + h;
+                tc_ld_wait();
+                if (k < 7) tc_ld32(tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (((k + 1) >> 1) * TCX_N + chalf * 64 + ((k + 1) & 1) * 32), v[(k + 1) & 1]);
+#pragma unroll
+                for (int t4 = 0; t4 < 4; t4++) {
+                    const int t = h * 4 + t4;
+                    const float sc = __fmul_rn(dw, S.sa[i][chalf * 8 + t]);
+#pragma unroll
+                    for (int l = 0; l < 8; l++) acc[t][l] = fmaf(sc, tc_i2f(v[k & 1][t4 * 8 + l]), acc[t][l]);
+                    if (HASM) summ[t] = fmaf(mwv, S.ss[i][chalf * 8 + t], summ[t]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                   // operands, scales and TMEM are free again
+    }
+
+    // ---- hsum_float_8 (+ summs) and the fused epilogue of the matmul
+    const int r = row0 + erow;
+    if (r < a.M) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int n = tok0 + chalf * 8 + t;
+            float x = __fadd_rn(__fadd_rn(__fadd_rn(acc[t][0], acc[t][4]), __fadd_rn(acc[t][2], acc[t][6])),
+                                __fadd_rn(__fadd_rn(acc[t][1], acc[t][5]), __fadd_rn(acc[t][3], acc[t][7])));
+            if (HASM) x = __fadd_rn(x, summ[t]);
+            if (n < a.n) bg_epilogue(a.epi, n, r, x);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}

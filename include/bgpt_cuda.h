@@ -132,10 +132,15 @@ int bgpt_cuda_set_batch_path(bgpt_model * m, int path);
 int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows);
 /* Which schedule an eval of n_rows token rows takes on this model: 3 = persistent decode kernel (n_rows == 1), 1 = fused
  * skinny-batch schedule, 0 = per-operator schedule with the exact-order SIMT matmul -- these three give the reference's bits
- * and are the only ones used by default -- 2 = per-operator schedule with the integer tcgen05 matmul of csrc/bgpt_tc.cuh
+ * -- as does 4 = per-operator schedule with the bit-exact tcgen05 matmul (k_gemm_tc_x; quantised evals of 128+ rows); these four
+ * are the only ones used by default -- 2 = per-operator schedule with the one-term-per-block tcgen05 matmul of csrc/bgpt_tc.cuh
  * (exact integer block dots but one f32 term per block: logits drift by ~5e-2, see tests/test_gpu_eval.py), which is OFF
  * unless enabled with bgpt_cuda_set_tc_min_rows / BGPT_TC_MIN_ROWS. */
 int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows);
+/* the bit-exact tcgen05 matmul (csrc/bgpt_tc.cuh, k_gemm_tc_x: the reference's 8 running sums per row through masked activation
+ * columns) serves quantised evals of `rows`+ token rows on the per-operator schedule (default 128; 0 = off: the skinny-batch
+ * schedule then serves every batch size).  bgpt_cuda_get_eval_path reports 4 for it; results are the reference's bits. */
+int bgpt_cuda_set_tcx_min_rows(bgpt_model * m, int rows);
 /* opt in to the tolerance-close integer tcgen05 matmul for quantised evals of `rows`+ token rows (0 = off, the default) */
 int bgpt_cuda_set_tc_min_rows(bgpt_model * m, int rows);
 /* debug: copy one of the eval arena's buffers as the last eval left it (0 x, 1 x1, 2 q, 3 the d_model-wide activation
@@ -186,9 +191,12 @@ int    bgpt_cuda_set_taps(bgpt_model * m, float * const taps5[5]);
  * (ggml_compute_forward_mul_mat, ggml.c:11804-12013).  All pointers HOST. */
 int bgpt_cuda_op_mul_mat(int ggml_type, const void * w, const float * x, float * y,
                          int k, int rows, int n);
-/* the same product through the tcgen05 tensor-core kernel used for prompt batches
- * (csrc/bgpt_tc.cuh; quantised types only).  Exact integer block dots, f32 block accumulation
- * in block order: close to, not bit-identical with, the CPU reference (see the file header). */
+/* the same product through the BIT-EXACT tcgen05 tensor-core kernel used for prompt batches of 128+ rows (csrc/bgpt_tc.cuh,
+ * k_gemm_tc_x; quantised types only): identical bits to bgpt_cuda_op_mul_mat */
+int bgpt_cuda_op_mul_mat_tcx(int ggml_type, const void * w, const float * x, float * y,
+                             int k, int rows, int n);
+/* the same product through the opt-in one-term-per-block tcgen05 kernel (k_gemm_tc_q).  Exact integer block dots, f32 block
+ * accumulation in block order: close to, not bit-identical with, the CPU reference (see the file header). */
 int bgpt_cuda_op_mul_mat_tc(int ggml_type, const void * w, const float * x, float * y,
                             int k, int rows, int n);
 /* activation quantisers applied to src1 by mul_mat (ggml.c:1166-1249, 1403-1494, 493-510):

@@ -189,7 +189,7 @@ def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftyp
     p = zoo.path("narrow", ftype)
     O = checkers.Oracle(p)
     M = capi.Model.load(p, max_batch=128)
-    assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(111) == 1 and M.batch_path(112) == 1, capi.last_error()
+    assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(111) == 1 and M.batch_path(128) == 0, capi.last_error()
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=55)
     sizes = [8, 8, 5, 2, 3, 4, 7, 16, 9, 1, 8, 31, 8, 6]             # 116 positions: T = 8, 16, 21, 23, 26, 30, 37, 53, 62, 63, 71, 102, ...
     sched, pos = [], 0
@@ -249,19 +249,27 @@ def _top5(v):
 
 @pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_large_prompt_batches_are_bit_exact(checkers, capi, zoo, ftype):
-    """whole evals of 112 / 128 / 256 / 1024 rows (BioGPT-base layer shapes, 2 layers): the DEFAULT path for large quantised
-    prompt batches is the exact-order skinny-batch schedule -- logits bit-identical to the reference, and a 24-token greedy
-    continuation on the KV cache that pass wrote gives identical ids and bit-identical logits"""
+    """whole evals of 112 / 128 / 256 / 1024 rows (BioGPT-base layer shapes, 2 layers) on their DEFAULT paths -- the skinny-batch
+    schedule below 128 rows, the per-operator schedule with the bit-exact tcgen05 matmul (k_gemm_tc_x: the reference's 8 running
+    sums per row through masked activation columns) from 128 rows on: logits bit-identical to the reference, a 24-token greedy
+    continuation on the KV cache that pass wrote gives bit-identical logits, and the skinny-batch schedule gives the same bits
+    at every size"""
     hp = gf.NARROW
     p = zoo.path("narrow", ftype)
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=808)
     for rows in (112, 128, 256, 1024):
         R = _fast_checker(checkers, p, n_batch=rows)
         M = capi.Model.load(p, max_batch=rows)
-        assert M.eval_path(rows) == 1 and M.eval_path(1) == 3, capi.last_error()
+        assert M.eval_path(rows) == (4 if rows >= 128 else 1) and M.eval_path(1) == 3, capi.last_error()
         want = R.eval(toks[:rows], 0)
         got = M.eval(toks[:rows], 0)
-        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} rows={rows}", got, want)
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} rows={rows} (path {M.eval_path(rows)})", got, want)
+        if rows >= 128:
+            M.set_tcx_min_rows(0)
+            assert M.eval_path(rows) == 1
+            got = M.eval(toks[:rows], 0)
+            assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} rows={rows} (skinny-batch schedule)", got, want)
+            M.set_tcx_min_rows(128)
         if rows < hp.n_positions:
             tok = int(np.argmax(want))
             for i in range(24):
@@ -280,7 +288,7 @@ def test_large_prompt_batch_base_model_bit_exact(checkers, capi, zoo, ftype, row
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=909)
     R = _fast_checker(checkers, p, n_batch=rows)
     M = capi.Model.load(p, max_batch=rows)
-    assert M.eval_path(rows) == 1
+    assert M.eval_path(rows) == 4
     want = R.eval(toks[:rows], 0)
     got = M.eval(toks[:rows], 0)
     assert np.array_equal(_bits(got), _bits(want)), _diff(f"base {ftype} rows={rows}", got, want)
@@ -311,7 +319,7 @@ def test_opt_in_integer_tensor_core_path_envelope(checkers, capi, zoo, ftype):
         print(f"opt-in integer tcgen05 path {ftype} rows={rows}: max|dlogit| = {err:.3e}")
         assert int(np.argmax(got)) == int(np.argmax(want)) and err <= TC_LOGIT_TOL, f"{ftype} rows={rows}: max|dlogit|={err:.3e}"
         M.set_tc_min_rows(0)
-        assert M.eval_path(rows) == 1
+        assert M.eval_path(rows) == 4
         R.close(); M.close()
 
 
@@ -370,12 +378,14 @@ def test_base_model_64_token_continuation(checkers, capi, zoo, ftype):
 def test_eval_path_map(capi, zoo):
     """which schedule a (model, rows) pair takes: only quantised evals of 112+ rows leave the bit-exact kernels"""
     M = capi.Model.load(zoo.path("narrow", "q5_1"), max_batch=128)
-    assert [M.eval_path(n) for n in (1, 2, 8, 111, 112, 128, 1024)] == [3, 1, 1, 1, 1, 1, 1]
+    assert [M.eval_path(n) for n in (1, 2, 8, 111, 127, 128, 1024)] == [3, 1, 1, 1, 1, 4, 4]
     M.set_tc_min_rows(112)
     assert [M.eval_path(n) for n in (1, 8, 111, 112, 128)] == [3, 1, 1, 2, 2]
+    M.set_tc_min_rows(0); M.set_tcx_min_rows(0)
+    assert [M.eval_path(n) for n in (1, 8, 128, 1024)] == [3, 1, 1, 1]
     M.close()
     M = capi.Model.load(zoo.path("small", "q4_0"), max_batch=128)          # not BioGPT-base layer shapes: no skinny schedule
-    assert [M.eval_path(n) for n in (1, 2, 32, 111, 112)] == [3, 0, 0, 0, 0]
+    assert [M.eval_path(n) for n in (1, 2, 32, 127, 128)] == [3, 0, 0, 0, 4]
     M.close()
     M = capi.Model.load(zoo.path("small", "f16"), max_batch=128)           # F16 never uses the integer tensor-core matmul
     assert [M.eval_path(n) for n in (1, 8, 112)] == [3, 0, 0]

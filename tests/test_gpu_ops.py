@@ -172,6 +172,26 @@ def test_mul_mat_tensor_core(checkers, capi, name, shape):
 
 
 @pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+@pytest.mark.parametrize("shape", [(1024, 256, 64), (4096, 136, 70), (1024, 1000, 200), (128, 128, 33), (64, 8, 5), (1024, 3072, 17)])
+def test_mul_mat_tensor_core_exact(checkers, capi, name, shape):
+    """the bit-exact tcgen05 matmul (csrc/bgpt_tc.cuh, k_gemm_tc_x): every token becomes 8 masked activation columns, the MMA
+    delivers the reference's 8 four-element partial sums per block as exact int32, the epilogue runs the 8 fma chains in block order
+    -- the result must be the oracle's bits for every format, ragged rows / tokens and K = 64 .. 4096"""
+    k, rows, n = shape
+    t = TYPES[name]
+    rng = np.random.default_rng(k + rows * 3 + n + t)
+    w = (rng.standard_normal((rows, k)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    x[0, :32] = 0.0                                       # an all-zero activation block
+    wb = np.frombuffer(gf.encode_tensor(w, t), dtype=np.uint8).copy()
+    want = np.zeros((n, rows), dtype=np.float32)
+    checkers.oracle_lib().bo_mul_mat(t, wb, x, want, k, rows, n)
+    got = capi.op_mul_mat_tcx(t, wb, x, rows)
+    bad = np.flatnonzero(got.view(np.uint32).ravel() != want.view(np.uint32).ravel())
+    assert bad.size == 0, f"{name} {shape}: {bad.size}/{got.size} outputs differ, max|d|={np.abs(got - want).max():.3e}"
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_quantize_weights_equals_reference_quantiser(capi, name):
     """device f32 -> Qx blocks (csrc/bgpt_quant.cuh) == quantize_row_q*_reference as the reference's `quantize` tool
     runs it (ggml.c:892-1094).  The checker is ggml_file's numpy restatement, itself pinned to the tool's output and to

@@ -20,6 +20,14 @@ gen5)
 headline)
   timeout 900 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=3 -x -k "base_model_headline or base_model_64" > $OUT/pytest_headline.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_headline.log
   grep -E "passed|failed|FAILED|Error|differ|timed out" $OUT/pytest_headline.log | tail -20 ;;
+tcx)
+  timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q --maxfail=6 -k "tensor_core_exact or large_prompt or eval_path_map or opt_in" > $OUT/pytest_tcx.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_tcx.log
+  grep -E "passed|failed|FAILED|Error|differ|timed out" $OUT/pytest_tcx.log | tail -20 ;;
+promptsweep)
+  for ft in ${FTYPES:-q8_0}; do
+    BGPT_TCX_MIN_ROWS=0 timeout 600 python tools/prompt_bench.py --ftype $ft --n 128,256,1024 > $OUT/prompt_skinny_$ft.log 2>&1; cat $OUT/prompt_skinny_$ft.log
+    timeout 600 python tools/prompt_bench.py --ftype $ft --n 8,64,128,256,1024 > $OUT/prompt_tcx_$ft.log 2>&1; cat $OUT/prompt_tcx_$ft.log
+  done ;;
 smoke)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
   tail -5 $OUT/smoke.log ;;
