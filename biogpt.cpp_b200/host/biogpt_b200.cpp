@@ -171,11 +171,20 @@ bool biogpt_model_load(const std::string & fname, biogpt_model & model, biogpt_v
         fprintf(stderr, "%s: invalid model file '%s' (bad vocab size %d != %d)\n", __func__, fname.c_str(), n_vocab, hp.n_vocab);
         return false;
     }
+    // a corrupt or truncated file must end in `return false`, not in a multi-GB resize or a bad_alloc: sizes read from the file
+    // are checked before they are used
+    const uint32_t MAX_STR = 1u << 16;
+    if (hp.n_vocab <= 0 || hp.n_layer <= 0 || hp.n_head <= 0 || hp.n_positions <= 0 || hp.d_ff <= 0 || hp.d_model <= 0) {
+        fprintf(stderr, "%s: invalid model file '%s' (bad hyper-parameters)\n", __func__, fname.c_str());
+        return false;
+    }
     std::string word;
     for (int i = 0; i < n_vocab; i++) {
         uint32_t len = 0; read_safe(in, len);
+        if (!in.good() || len > MAX_STR) { fprintf(stderr, "%s: invalid model file '%s' (bad vocabulary entry %d)\n", __func__, fname.c_str(), i); return false; }
         word.resize(len);
         if (len) in.read(&word[0], len);
+        if (!in.good()) { fprintf(stderr, "%s: model file '%s' is truncated in the vocabulary\n", __func__, fname.c_str()); return false; }
         vocab.token_to_id[word] = i;
         vocab.id_to_token[i] = word;
     }
@@ -191,8 +200,10 @@ bool biogpt_model_load(const std::string & fname, biogpt_model & model, biogpt_v
     word_pair last_pair;
     for (int i = 0; i < n_merges; i++) {
         uint32_t len = 0; read_safe(in, len);
+        if (!in.good() || len > MAX_STR) { fprintf(stderr, "%s: invalid model file '%s' (bad merge entry %d)\n", __func__, fname.c_str(), i); return false; }
         if (len) {
             word.resize(len); in.read(&word[0], len);
+            if (!in.good()) { fprintf(stderr, "%s: model file '%s' is truncated in the merges\n", __func__, fname.c_str()); return false; }
             std::stringstream ss(word);
             ss >> last_pair.first >> last_pair.second;
         }
@@ -240,6 +251,9 @@ bool biogpt_model_load(const std::string & fname, biogpt_model & model, biogpt_v
         for (int i = 0; i < n_dims; i++) read_safe(in, ne[i]);
         std::string name(name_len, 0);
         in.read(&name[0], name_len);
+        if (!in.good() || ne[0] <= 0 || ne[1] <= 0 || (int64_t) ne[0] * ne[1] > ((int64_t) 1 << 31)) {
+            fprintf(stderr, "%s: tensor '%s' has a bad shape [%d, %d] in '%s'\n", __func__, name.c_str(), ne[0], ne[1], fname.c_str()); ggml_free(ctx); return false;
+        }
         if (ggml_type_size((ggml_type) ttype) == 0 || ttype == GGML_TYPE_Q8_1) { fprintf(stderr, "%s: tensor '%s' has unknown type %d\n", __func__, name.c_str(), ttype); ggml_free(ctx); return false; }
         const size_t nbytes = (size_t) ne[0] * ne[1] / ggml_blck_size((ggml_type) ttype) * ggml_type_size((ggml_type) ttype);
         raw.resize(nbytes);

@@ -161,3 +161,50 @@ def test_device_topk_sampler_draws_the_reference_id(host, checkers, zoo, size, f
                 got = host.bgpt_host_eval_sample(h, t.ctypes.data, len(t), n_past, top_k, top_p, temp, seed)
                 assert got == want, (n_past, seed, top_k, top_p, temp)
     host.bgpt_host_close(h); R.close()
+
+
+def test_loader_rejects_corrupt_files_without_throwing(host, zoo, model_dir):
+    """sizes read from the file are validated before use: a truncated file, an absurd vocabulary string length and a negative
+    tensor dimension all make biogpt_model_load return false (no exception, no multi-GB allocation)"""
+    import struct
+    good = open(zoo.path("tiny", "q4_0"), "rb").read()
+    cases = {
+        "truncated_vocab": good[:200],
+        "huge_vocab_len": good[:36] + struct.pack("<I", 0x7FFFFFF0) + good[40:],
+        "truncated_tensor": good[:len(good) - 1000],
+    }
+    # a negative ne[0] in the first tensor header: find the first tensor by its name
+    at = good.find(b"biogpt.embed_tokens.weight")
+    hdr = at - 8 - 12                                   # n_dims, name_len, ttype, ne[0], ne[1] precede the name
+    cases["negative_dim"] = good[:hdr + 12] + struct.pack("<i", -64) + good[hdr + 16:]
+    for name, blob in cases.items():
+        p = os.path.join(model_dir, f"corrupt-{name}.bin")
+        open(p, "wb").write(blob)
+        assert not host.bgpt_host_open(p.encode(), 8), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ftype", ["q4_0", "f16"])
+def test_reference_main_binary_end_to_end(checkers, zoo, ftype):
+    """the reference's UNMODIFIED examples/main/main.cpp, linked against libbiogpt_b200.so (host/Makefile), run end to end on the GPU:
+    `biogpt -m model -p "a b c" -n 12 --top_k 1` -- tokenizer, prompt batch, greedy sampling, detokenizer -- must print the ids the
+    oracle's greedy loop produces (synthetic vocabulary: id 30 + i decodes to "tok{i}")"""
+    import re
+    exe = os.path.join(HOST, "_build", "biogpt")
+    if not os.path.exists(exe):
+        pytest.skip("front ends are only linked where /root/reference exists (the built binary travels to the GPU box)")
+    p = zoo.path("small", ftype)
+    r = subprocess.run([exe, "-m", p, "-p", "a b c", "-n", "12", "--top_k", "1", "-s", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert "number of tokens in prompt = 4, first 8 tokens: 2 4 5 6" in r.stdout, r.stdout[-800:]
+    body = r.stdout.split("first 8 tokens:")[1].split("load time")[0]
+    got = [30 + int(x) for x in re.findall(r"tok(\d+)", body)]
+    O = checkers.Oracle(p)
+    l = O.eval(np.array([2, 4, 5, 6], np.int32), 0)
+    want = []
+    for i in range(12):
+        tok = int(np.argmax(l)); want.append(tok)
+        l = O.eval(np.array([tok], np.int32), 4 + i)
+    O.close()
+    want_printed = [t for t in want if t >= 30]          # ids below 30 are "<s>", "a".."z" etc.
+    assert got == want_printed, (got, want)

@@ -28,6 +28,29 @@ promptsweep)
     BGPT_TCX_MIN_ROWS=0 timeout 600 python tools/prompt_bench.py --ftype $ft --n 128,256,1024 > $OUT/prompt_skinny_$ft.log 2>&1; cat $OUT/prompt_skinny_$ft.log
     timeout 600 python tools/prompt_bench.py --ftype $ft --n 8,64,128,256,1024 > $OUT/prompt_tcx_$ft.log 2>&1; cat $OUT/prompt_tcx_$ft.log
   done ;;
+sanitize)
+  # compute-sanitizer on the tiny / small models through the C ABI: memcheck over prompt + decode on every schedule, racecheck on the decode kernel
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_run.py > $OUT/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/sanitizer_memcheck.log
+  tail -4 $OUT/sanitizer_memcheck.log
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_run.py --quick > $OUT/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/sanitizer_racecheck.log
+  tail -4 $OUT/sanitizer_racecheck.log ;;
+hostlib)
+  timeout 600 python -m pytest tests/test_host_lib.py tests/test_replica_driver.py -m gpu -q --maxfail=6 > $OUT/pytest_host.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_host.log
+  grep -E "passed|failed|FAILED|Error|differ" $OUT/pytest_host.log | tail ;;
+ncu5)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_decode.csv \
+      python tools/profile_decode.py --n-past 511 --steps 8 --warm 0 > $OUT/launches_decode.log 2>&1; echo "launches rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mega5 -s 3 -c 1 -f -o $OUT/mega5_full \
+      python tools/profile_decode.py --n-past 511 --steps 5 --warm 0 > $OUT/mega5_full.log 2>&1; echo "full rc=$?"
+  ncu -i $OUT/mega5_full.ncu-rep --page raw --csv > $OUT/mega5_full_raw.csv 2>/dev/null
+  tail -3 $OUT/mega5_full.log ;;
+ncutcx)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_prompt.csv \
+      python tools/profile_prompt.py --ftype q8_0 --n 1024 > $OUT/launches_prompt.log 2>&1; echo "promptncu rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc_x -s 8 -c 1 -f -o $OUT/gemm_tcx_full \
+      python tools/profile_prompt.py --ftype q8_0 --n 1024 > $OUT/gemm_tcx_full.log 2>&1; echo "tcxfull rc=$?"
+  ncu -i $OUT/gemm_tcx_full.ncu-rep --page raw --csv > $OUT/gemm_tcx_full_raw.csv 2>/dev/null
+  tail -3 $OUT/gemm_tcx_full.log ;;
 smoke)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
   tail -5 $OUT/smoke.log ;;
