@@ -496,9 +496,14 @@ static int launch_gemm_tcx(bgpt_model * m, cudaStream_t s, const DevTensor * con
                            int n, int tok0, const Epi & epi) {
     const RowLayout & L = W[0]->L;
     static unsigned long long done = 0;
-    const size_t smem = std::max(sizeof(TcxShared) + 128, (size_t) 120 * 1024);       // >= half the SM: one CTA (512 TMEM columns) per SM
+    // kind::f16 (partial sums arrive as f32: k_gemm_tc_xf) unless BGPT_TCX_KIND=i8 (int32 partial sums: k_gemm_tc_x); same bits
+    static const bool f16k = !(getenv("BGPT_TCX_KIND") && !strcmp(getenv("BGPT_TCX_KIND"), "i8"));
+    const size_t smem = std::max(std::max(sizeof(TcxShared), sizeof(TcxfShared)) + 128, (size_t) 120 * 1024);   // >= half the SM: one CTA (512 TMEM columns) per SM
     if (first_use_on_current_device(done)) {
-        for (int t : { BG_Q4_0, BG_Q4_1, BG_Q5_0, BG_Q5_1, BG_Q8_0 }) cudaFuncSetAttribute(bgpt_k_gemm_tcx_fn(t), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        for (int t : { BG_Q4_0, BG_Q4_1, BG_Q5_0, BG_Q5_1, BG_Q8_0 }) {
+            cudaFuncSetAttribute(bgpt_k_gemm_tcx_fn(t), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            cudaFuncSetAttribute(bgpt_k_gemm_tcxf_fn(t), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        }
         cudaGetLastError();
     }
     GemvArgs a{};
@@ -508,7 +513,7 @@ static int launch_gemm_tcx(bgpt_model * m, cudaStream_t s, const DevTensor * con
     a.act = act; a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s;
     a.n = n; a.tok0 = tok0; a.epi = epi;
     dim3 grid((a.M + TC_ROWS - 1) / TC_ROWS, (n - tok0 + TCX_TOK - 1) / TCX_TOK);
-    const void * fn = bgpt_k_gemm_tcx_fn(L.type);
+    const void * fn = f16k ? bgpt_k_gemm_tcxf_fn(L.type) : bgpt_k_gemm_tcx_fn(L.type);
     if (!fn) return fail(BGPT_E_UNSUPPORTED, "tensor-core matmul: type %d", L.type);
     void * args[] = { &a };
     CK(cudaLaunchKernel(fn, grid, dim3(TC_THREADS), args, smem, s));
@@ -996,7 +1001,10 @@ static int launch_cluster_kernel(const void * fn, int grid, int threads, int clu
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;       // all CTAs co-resident: they spin on each other's words
-    cfg.attrs = at; cfg.numAttrs = 2;
+    // BGPT_M5_COOP=0: without the cooperative attribute (ncu cannot replay a cooperative cluster launch); the 128 CTAs are still
+    // co-resident on an otherwise idle GPU -- the occupancy check in mega5_setup is the same
+    static const bool coop = !(getenv("BGPT_M5_COOP") && atoi(getenv("BGPT_M5_COOP")) == 0);
+    cfg.attrs = at; cfg.numAttrs = coop ? 2 : 1;
     CK(cudaLaunchKernelExC(&cfg, fn, args));
     return BGPT_OK;
 }
@@ -1052,7 +1060,14 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     }
     const size_t xb = (size_t) 2 * M5_LW * sizeof(unsigned long long);
     CK(cudaMalloc(&m->d_xch5, xb)); CK(cudaMemset(m->d_xch5, 0, xb));
-    CK(cudaMalloc(&m->d_err5, sizeof(int))); CK(cudaMemset(m->d_err5, 0, sizeof(int)));
+    {   // [0] time-out code, [2..3] watchdog limit in cycles (~0.15 s; BGPT_M5_WATCHDOG_MCYC = millions of cycles, for sanitizer runs)
+        CK(cudaMalloc(&m->d_err5, 4 * sizeof(int)));
+        long long limit = 300000000LL;
+        if (getenv("BGPT_M5_WATCHDOG_MCYC")) limit = std::max(1LL, atoll(getenv("BGPT_M5_WATCHDOG_MCYC"))) * 1000000LL;
+        int init[4] = { 0, 0, 0, 0 };
+        memcpy(init + 2, &limit, sizeof limit);
+        CK(cudaMemcpy(m->d_err5, init, sizeof init, cudaMemcpyHostToDevice));
+    }
     CK(cudaMallocHost(&m->h_err5, sizeof(int))); *m->h_err5 = 0;
     P.xch = m->d_xch5; P.err = m->d_err5;
     P.trace = nullptr; P.prof_n = (m->n_layer + 1) * 5 * M5_PK;
@@ -1230,7 +1245,7 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     const size_t tk_bytes = (size_t) TOPK_MAXK * 8 + 8;
     if (!m->d_topk) {
         CK(cudaMalloc(&m->d_topk, tk_bytes)); CK(cudaMallocHost(&m->h_topk, tk_bytes));
-        cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);   // + 34 KB of static histograms
         cudaGetLastError();
     }
     cudaStream_t s = m->stream;
@@ -1244,7 +1259,7 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
         RET(forward(m, m->d_tokens, n, 0));
     }
-    const int staged = (size_t) m->n_vocab * 4 <= (size_t) 200 * 1024;
+    const int staged = (size_t) m->n_vocab * 4 <= (size_t) 190 * 1024;
     // packed as [info: 2 ints][vals: k floats][ids: k ints] so that ONE copy of 8 + 8 k bytes brings everything back
     int * dinfo = (int *) m->d_topk; float * dv = (float *) (m->d_topk + 8); int * di = (int *) (m->d_topk + 8 + (size_t) k * 4);
     k_topk<<<1, TOPK_NT, staged ? (size_t) m->n_vocab * 4 : 0, s>>>(m->logits, m->n_vocab, k, staged, dv, di, dinfo);

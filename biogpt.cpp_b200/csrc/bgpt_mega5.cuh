@@ -53,7 +53,6 @@
 #define M5_LW (M5_E5 + M5_R * M5_D)
 #define M5_MAXL 24
 #define M5_PK 12              // trace stamps per (layer, stage)
-#define M5_WATCHDOG 300000000LL   // cycles (~0.15 s) before a wait gives up
 
 struct M5Params {
     MegaParams b;
@@ -84,9 +83,11 @@ __device__ __forceinline__ void m5_bcast32(const void * local_dst, uint32_t v) {
 }
 
 // ---- waits with a watchdog ---------------------------------------------------------------------------------------------------
+// err[0]: the first time-out's code; err[2..3]: the watchdog limit in cycles (written by the host next to the flag)
 __device__ __forceinline__ bool m5_give_up(int * err, int code, long long t0) {
     if (*(volatile int *) err != 0) return true;
-    if (clock64() - t0 > M5_WATCHDOG) { atomicCAS(err, 0, code); return true; }
+    const long long limit = *(const long long *) (err + 2);
+    if (clock64() - t0 > limit) { atomicCAS(err, 0, code); return true; }
     return false;
 }
 __device__ __forceinline__ void m5_poll2(const unsigned long long * p, uint32_t tag, uint32_t & a, uint32_t & b, int * err, int code) {

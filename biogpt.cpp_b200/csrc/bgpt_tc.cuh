@@ -457,3 +457,206 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_x(GemvArgs a) {
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
 }
+
+// ================================================================================================================================
+// k_gemm_tc_xf -- the bit-exact matmul on kind::f16: the tensor core hands the partial sums over as f32
+// ================================================================================================================================
+// k_gemm_tc_x above spends 16 of its ~27 f32-pipe instructions per (row, token, block) turning int32 partial sums into floats.
+// The 4-element partial sums are small integers (|isum_l| <= 4 * 127 * 128 < 2^17): computed from fp16 operands with f32
+// accumulation they are exact, so the same masked-column scheme on tcgen05.mma.kind::f16 delivers (float) isum_l directly and the
+// epilogue is the reference's arithmetic and nothing else (8 fma + 1 mul per (row, token, block)).  K = 16 per instruction: a
+// block is two MMAs (elements 0..15 -> sums 0..3, elements 16..31 -> sums 4..7), each over 16 tokens x 4 masked columns (N = 64),
+// which also halves the redundant multiplications by zero.
+struct TcxfShared {
+    uint8_t A[4][2][TC_ROWS * 32];     // [block in group][half of the block][128 rows x 16 fp16, canonical K-major layout]
+    uint8_t B[4][2][TCX_TOK * 4 * 32]; // [block][half][column (n, l')][16 fp16]
+    float sw[4][TC_ROWS];
+    float mw[4][TC_ROWS];
+    float sa[4][TCX_TOK];
+    float ss[4][TCX_TOK];
+    unsigned long long mbar;
+    uint32_t tmem_base;
+};
+__device__ __forceinline__ uint32_t tcxf_idesc() {             // D = F32, A = B = F16, both K-major, M = 128, N = 64
+    return (1u << 4) | ((uint32_t) ((TCX_TOK * 4) >> 3) << 17) | ((uint32_t) (TC_ROWS >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// 4 signed bytes -> 4 fp16 values (exact): 0x6400 | (b ^ 0x80) is the fp16 number 1024 + (b + 128)
+__device__ __forceinline__ uint2 tc_s8x4_to_h4(uint32_t w) {
+    const uint32_t x = w ^ 0x80808080u;
+    uint32_t lo = __byte_perm(x, 0x64646464u, 0x5140), hi = __byte_perm(x, 0x64646464u, 0x5342);
+    const __half2 off = __floats2half2_rn(1152.0f, 1152.0f);
+    __half2 l2 = __hsub2(*reinterpret_cast<__half2 *>(&lo), off), h2 = __hsub2(*reinterpret_cast<__half2 *>(&hi), off);
+    return make_uint2(*reinterpret_cast<uint32_t *>(&l2), *reinterpret_cast<uint32_t *>(&h2));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc_xf(GemvArgs a) {
+    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+    TcxfShared & S = *reinterpret_cast<TcxfShared *>(tc_smem_raw);
+    constexpr bool IS8   = (FMT == BG_Q8_0);
+    constexpr bool HASQH = (FMT == BG_Q5_0 || FMT == BG_Q5_1);
+    constexpr bool HASM  = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * TC_ROWS;
+    const int tok0 = a.tok0 + blockIdx.y * TCX_TOK;
+
+    if (tid == 0) { tc_mbar_init(tc_smem_u32(&S.mbar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < (int) (sizeof(S.B) / 16); i += TC_THREADS) ((uint4 *) &S.B[0][0][0])[i] = make_uint4(0, 0, 0, 0);   // the zero pattern, once
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t idesc = tcxf_idesc();
+
+    const int frow = tid >> 1, fkc = tid & 1;               // weights: thread (row, half of the block)
+    const uint8_t * wrow;
+    {
+        int r = row0 + frow; r = r < a.M ? r : a.M - 1;
+        const int mat = r / a.rows_per;
+        wrow = a.W[mat] + (size_t) (r - mat * a.rows_per) * a.stride;
+    }
+    const int atk = tid >> 3, al = tid & 7;                 // activations: thread (token, element group l)
+    const bool a_thread = tid < 8 * TCX_TOK;
+    const bool a_valid = a_thread && (tok0 + atk) < a.n;
+    const uint8_t * arec = a.act + (size_t) (a_valid ? tok0 + atk : 0) * a.act_bytes;
+    uint4 wreg[4], areg; uint32_t qhreg[4]; uint2 sreg; float4 asreg;
+    auto load_group = [&](int g) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            wreg[j] = IS8 ? ldg_stream128(wrow + (size_t) ((g * 2 + fkc) * 4 + j) * 16) : ldg_stream128(wrow + (size_t) (g * 4 + j) * 16);
+            if (HASQH) qhreg[j] = ldg_stream32(wrow + a.off_qh + g * 16 + j * 4);
+        }
+        sreg = make_uint2(0, 0);
+        if (fkc == 0) sreg = ldg_stream64(wrow + a.off_d + g * 8);
+        else if (HASM) sreg = ldg_stream64(wrow + a.off_m + g * 8);
+        asreg = make_float4(0.f, 0.f, 0.f, 0.f);
+        areg = make_uint4(0, 0, 0, 0);
+        if (a_valid) {
+            areg = *(const uint4 *) (arec + (size_t) (g * 8 + al) * 16);
+            if (al == 0) asreg = *(const float4 *) (arec + a.off_dd + g * 16);
+            else if (HASM && al == 1) asreg = *(const float4 *) (arec + a.off_s + g * 16);
+        }
+    };
+    auto store_group = [&]() {
+        {
+            uint32_t out[4][4];                              // [block i][word j]: signed int8 codes of elements 16 fkc + 4j .. + 3
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t ww[4] = { wreg[j].x, wreg[j].y, wreg[j].z, wreg[j].w };
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t v = ww[i];
+                    if (!IS8) {
+                        v = fkc ? ((ww[i] >> 4) & 0x0F0F0F0Fu) : (ww[i] & 0x0F0F0F0Fu);
+                        if (HASQH) { const uint32_t hb = (qhreg[j] >> (8 * i)) & 0xFFu; v |= bg_spread4(fkc ? (hb >> 4) : (hb & 0xFu)); }
+                        if (FMT == BG_Q4_0) v = tc_sub8(v);
+                        if (FMT == BG_Q5_0) v = tc_sub16(v);
+                    }
+                    out[i][j] = v;
+                }
+            }
+            const int off = (frow >> 3) * 256 + (frow & 7) * 16;     // + 128 for the second 8 elements of the 16
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint2 h0 = tc_s8x4_to_h4(out[i][0]), h1 = tc_s8x4_to_h4(out[i][1]), h2 = tc_s8x4_to_h4(out[i][2]), h3 = tc_s8x4_to_h4(out[i][3]);
+                *(uint4 *) (&S.A[i][fkc][off])       = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *(uint4 *) (&S.A[i][fkc][off + 128]) = make_uint4(h2.x, h2.y, h3.x, h3.y);
+            }
+            float * dst = (fkc == 0) ? &S.sw[0][0] : &S.mw[0][0];
+            if (fkc == 0 || HASM) {
+                dst[0 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.x & 0xFFFF)); dst[1 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.x >> 16));
+                dst[2 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.y & 0xFFFF)); dst[3 * TC_ROWS + frow] = bg_h2f((uint16_t) (sreg.y >> 16));
+            }
+        }
+        if (a_thread) {
+            // column (n, l') of half c = l >> 2, l' = l & 3: operand row n * 4 + l'; its four live fp16 values are elements 4 l' .. 4 l' + 3
+            const int c = al >> 2, lp = al & 3, nr = atk * 4 + lp;
+            const int off = (nr >> 3) * 256 + (lp >> 1) * 128 + (nr & 7) * 16 + (lp & 1) * 8;
+            *(uint2 *) (&S.B[0][c][off]) = tc_s8x4_to_h4(areg.x); *(uint2 *) (&S.B[1][c][off]) = tc_s8x4_to_h4(areg.y);
+            *(uint2 *) (&S.B[2][c][off]) = tc_s8x4_to_h4(areg.z); *(uint2 *) (&S.B[3][c][off]) = tc_s8x4_to_h4(areg.w);
+            if (al == 0) { S.sa[0][atk] = asreg.x; S.sa[1][atk] = asreg.y; S.sa[2][atk] = asreg.z; S.sa[3][atk] = asreg.w; }
+            else if (HASM && al == 1) { S.ss[0][atk] = asreg.x; S.ss[1][atk] = asreg.y; S.ss[2][atk] = asreg.z; S.ss[3][atk] = asreg.w; }
+        }
+    };
+
+    const int quad = warp & 3, chalf = warp >> 2;           // rows quad * 32 + lane; tokens chalf * 8 .. + 7
+    const int erow = quad * 32 + lane;
+    float acc[8][8], summ[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) { summ[t] = 0.0f;
+#pragma unroll
+        for (int l = 0; l < 8; l++) acc[t][l] = 0.0f; }
+
+    const int G = a.G;
+    load_group(0);
+    for (int g = 0; g < G; g++) {
+        store_group();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+                    tc_mma_f16(tmem + (uint32_t) (i * TCX_N + c * 64), tc_make_desc(tc_smem_u32(&S.A[i][c][0])), tc_make_desc(tc_smem_u32(&S.B[i][c][0])), idesc, 0u);
+            tc_commit(tc_smem_u32(&S.mbar));
+        }
+        if (g + 1 < G) load_group(g + 1);
+        tc_mbar_wait(tc_smem_u32(&S.mbar), (uint32_t) (g & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // TMEM columns of block i: [i * 128 + c * 64 + n * 4 + l'] = (float) isum_{4c + l'} of token n; this thread reads n = chalf * 8 .. + 7
+        uint32_t v[2][32];
+        const uint32_t lanebase = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (chalf * 32);
+        tc_ld32(lanebase, v[0]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float dw = S.sw[i][erow];
+            const float mwv = HASM ? S.mw[i][erow] : 0.0f;
+            float sc[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) sc[t] = __fmul_rn(dw, S.sa[i][chalf * 8 + t]);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int k = i * 2 + c;
+                tc_ld_wait();
+                if (k < 7) tc_ld32(lanebase + (uint32_t) (((k + 1) >> 1) * TCX_N + ((k + 1) & 1) * 64), v[(k + 1) & 1]);
+#pragma unroll
+                for (int t = 0; t < 8; t++)
+#pragma unroll
+                    for (int lp = 0; lp < 4; lp++) acc[t][c * 4 + lp] = fmaf(sc[t], __uint_as_float(v[k & 1][t * 4 + lp]), acc[t][c * 4 + lp]);
+            }
+            if (HASM) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) summ[t] = fmaf(mwv, S.ss[i][chalf * 8 + t], summ[t]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+
+    const int r = row0 + erow;
+    if (r < a.M) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int n = tok0 + chalf * 8 + t;
+            float x = __fadd_rn(__fadd_rn(__fadd_rn(acc[t][0], acc[t][4]), __fadd_rn(acc[t][2], acc[t][6])),
+                                __fadd_rn(__fadd_rn(acc[t][1], acc[t][5]), __fadd_rn(acc[t][3], acc[t][7])));
+            if (HASM) x = __fadd_rn(x, summ[t]);
+            if (n < a.n) bg_epilogue(a.epi, n, r, x);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}

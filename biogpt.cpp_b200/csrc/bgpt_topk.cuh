@@ -8,7 +8,10 @@
 // (info[1] = 0) and the caller falls back to the full-logit path, so the drawn id is the reference's in every case.
 //
 // One CTA: the keys (order-preserving uint32 images of the floats) are staged in shared memory once (170 KB for 42384 logits),
-// the K-th largest key is found by a 4-pass radix select on 8-bit digits, the <= K survivors are ranked by counting.
+// the K-th largest key is found by a 4-pass radix select on 8-bit digits, the <= K survivors are ranked by counting.  Logits
+// share their leading digits, so the histogram of a pass is one or two hot bins: every warp counts into its OWN histogram and
+// aggregates equal digits with match.any first (one shared-memory atomic per distinct digit per warp instead of 32 colliding ones;
+// the naive version spent 50 us in those collisions).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,6 +29,7 @@ static __global__ void __launch_bounds__(TOPK_NT) k_topk(const float * __restric
                                                           float * __restrict__ out_val, int * __restrict__ out_idx, int * __restrict__ info) {
     extern __shared__ uint32_t s_keys[];                            // n keys when `staged`
     __shared__ unsigned hist[256];
+    __shared__ unsigned whist[TOPK_NT / 32][256];                  // per-warp histograms
     __shared__ uint32_t s_prefix, s_remaining;
     __shared__ unsigned s_cnt, s_eq;
     __shared__ uint32_t c_key[TOPK_MAXK]; __shared__ int c_idx[TOPK_MAXK];
@@ -38,12 +42,24 @@ static __global__ void __launch_bounds__(TOPK_NT) k_topk(const float * __restric
     __syncthreads();
     uint32_t mask = 0u;
     for (int pass = 3; pass >= 0; pass--) {
-        for (int b = tid; b < 256; b += TOPK_NT) hist[b] = 0u;
+        for (int b = tid; b < (TOPK_NT / 32) * 256; b += TOPK_NT) (&whist[0][0])[b] = 0u;
         __syncthreads();
         const uint32_t prefix = s_prefix;
-        for (int i = tid; i < n; i += TOPK_NT) {
-            const uint32_t u = staged ? s_keys[i] : topk_key(logits[i]);
-            if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1u);
+        unsigned * mine = whist[tid >> 5];
+        const int n_pad = (n + 31) & ~31;                          // whole warps take part in match.any
+        for (int i = tid; i < n_pad; i += TOPK_NT) {
+            const uint32_t u = i < n ? (staged ? s_keys[i] : topk_key(logits[i])) : 0u;
+            const bool live = i < n && (u & mask) == prefix;
+            const unsigned digit = live ? ((u >> (8 * pass)) & 255u) : 256u + (tid & 31);     // dead lanes match nobody
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (live && (int) (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&mine[digit], (unsigned) __popc(peers));
+        }
+        __syncthreads();
+        for (int b = tid; b < 256; b += TOPK_NT) {
+            unsigned c = 0;
+#pragma unroll 8
+            for (int w = 0; w < TOPK_NT / 32; w++) c += whist[w][b];
+            hist[b] = c;
         }
         __syncthreads();
         if (tid == 0) {                                             // the digit of the remaining-th largest key among the survivors

@@ -12,4 +12,5 @@ const void * bgpt_k_sk_ln_fn(int wtype);
 const void * bgpt_k_sk_gq_fn(int wtype);
 const void * bgpt_k_sk_attn_fn(int wtype);
 const void * bgpt_k_gemm_tc_fn(int wtype);                      // tu_tc.cu    : k_gemm_tc_q<FMT>  (one f32 term per block: tolerance-close)
+const void * bgpt_k_gemm_tcxf_fn(int wtype);                    // tu_tc.cu    : k_gemm_tc_xf<FMT> (bit-exact, kind::f16: partial sums arrive as f32)
 const void * bgpt_k_gemm_tcx_fn(int wtype);                     // tu_tc.cu    : k_gemm_tc_x<FMT>  (8 running sums per row: bit-exact)

@@ -19,3 +19,12 @@ const void * bgpt_k_gemm_tcx_fn(int wtype) {
     }
     return nullptr;
 }
+
+const void * bgpt_k_gemm_tcxf_fn(int wtype) {
+    switch (wtype) {
+        case BG_Q4_0: return (const void *) k_gemm_tc_xf<BG_Q4_0>; case BG_Q4_1: return (const void *) k_gemm_tc_xf<BG_Q4_1>;
+        case BG_Q5_0: return (const void *) k_gemm_tc_xf<BG_Q5_0>; case BG_Q5_1: return (const void *) k_gemm_tc_xf<BG_Q5_1>;
+        case BG_Q8_0: return (const void *) k_gemm_tc_xf<BG_Q8_0>;
+    }
+    return nullptr;
+}

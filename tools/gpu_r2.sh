@@ -23,6 +23,14 @@ headline)
 tcx)
   timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q --maxfail=6 -k "tensor_core_exact or large_prompt or eval_path_map or opt_in" > $OUT/pytest_tcx.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_tcx.log
   grep -E "passed|failed|FAILED|Error|differ|timed out" $OUT/pytest_tcx.log | tail -20 ;;
+tcxkinds)
+  for kind in f16 i8; do
+    BGPT_TCX_KIND=$kind timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q --maxfail=6 -k "tensor_core_exact or large_prompt" > $OUT/pytest_tcx_$kind.log 2>&1; echo "pytest $kind rc=$?" | tee -a $OUT/pytest_tcx_$kind.log
+    grep -E "passed|failed|FAILED|Error|differ" $OUT/pytest_tcx_$kind.log | tail -8
+    for ft in q8_0 q4_0; do BGPT_TCX_KIND=$kind timeout 600 python tools/prompt_bench.py --ftype $ft --n 128,1024 > $OUT/prompt_${kind}_$ft.log 2>&1; cat $OUT/prompt_${kind}_$ft.log; done
+  done
+  BGPT_TCX_MIN_ROWS=32 timeout 600 python tools/prompt_bench.py --ftype q8_0 --n 32,64,96 > $OUT/prompt_tcx_small_q8_0.log 2>&1; cat $OUT/prompt_tcx_small_q8_0.log
+  timeout 600 python tools/prompt_bench.py --ftype q8_0 --n 32,64,96 > $OUT/prompt_sk_small_q8_0.log 2>&1; cat $OUT/prompt_sk_small_q8_0.log ;;
 promptsweep)
   for ft in ${FTYPES:-q8_0}; do
     BGPT_TCX_MIN_ROWS=0 timeout 600 python tools/prompt_bench.py --ftype $ft --n 128,256,1024 > $OUT/prompt_skinny_$ft.log 2>&1; cat $OUT/prompt_skinny_$ft.log
@@ -32,15 +40,15 @@ sanitize)
   # compute-sanitizer on the tiny / small models through the C ABI: memcheck over prompt + decode on every schedule, racecheck on the decode kernel
   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_run.py > $OUT/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/sanitizer_memcheck.log
   tail -4 $OUT/sanitizer_memcheck.log
-  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_run.py --quick > $OUT/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/sanitizer_racecheck.log
+  BGPT_M5_WATCHDOG_MCYC=400000 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_run.py --quick > $OUT/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/sanitizer_racecheck.log
   tail -4 $OUT/sanitizer_racecheck.log ;;
 hostlib)
   timeout 600 python -m pytest tests/test_host_lib.py tests/test_replica_driver.py -m gpu -q --maxfail=6 > $OUT/pytest_host.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_host.log
   grep -E "passed|failed|FAILED|Error|differ" $OUT/pytest_host.log | tail ;;
 ncu5)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_decode.csv \
+  BGPT_M5_COOP=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_decode.csv \
       python tools/profile_decode.py --n-past 511 --steps 8 --warm 0 > $OUT/launches_decode.log 2>&1; echo "launches rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mega5 -s 3 -c 1 -f -o $OUT/mega5_full \
+  BGPT_M5_COOP=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mega5 -s 3 -c 1 -f -o $OUT/mega5_full \
       python tools/profile_decode.py --n-past 511 --steps 5 --warm 0 > $OUT/mega5_full.log 2>&1; echo "full rc=$?"
   ncu -i $OUT/mega5_full.ncu-rep --page raw --csv > $OUT/mega5_full_raw.csv 2>/dev/null
   tail -3 $OUT/mega5_full.log ;;
