@@ -377,6 +377,74 @@ def run_streams_workload(args, capi, dist, barrier, rank, local_rank, world):
           "cpu_baseline": None})
 
 
+def run_streams_cpp_driver(args):
+    """BASELINE.json configs[3] through the C++ replica driver (include/bgpt_replicas.h, host/replicas.cpp): ONE process, one host
+    thread + one engine per GPU, stream s on device s % G, `--streams` lock-step streams per GPU, every device running its whole
+    greedy loop on the GPU.  value = all streams' tokens / max over devices of the CUDA-event time of the device's loop; e2e = the
+    same streams through bgpt_replicas_eval (host tokens in, host logits out, host argmax), wall clock."""
+    import ctypes as C
+    ftype = "q5_1" if args.ftype == "q4_0" else args.ftype
+    G, S, seq = args.gpus, args.streams, args.seq
+    L = C.CDLL(os.path.join(ROOT, "biogpt.cpp_b200", "host", "libbiogpt_b200.so"))
+    L.bgpt_replicas_open.restype = C.c_void_p
+    L.bgpt_replicas_open.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.bgpt_replicas_close.argtypes = [C.c_void_p]
+    L.bgpt_replicas_devices.argtypes = [C.c_void_p]
+    L.bgpt_replicas_n_vocab.argtypes = [C.c_void_p]
+    i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    L.bgpt_replicas_eval.argtypes = [C.c_void_p, i32p, C.c_int, f32p]
+    L.bgpt_replicas_decode_greedy.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, i32p, f32p]
+    L.bgpt_replicas_last_error.restype = C.c_char_p
+    r = L.bgpt_replicas_open(model_path(ftype).encode(), G, G * S)
+    if not r:
+        raise SystemExit("bench.py: bgpt_replicas_open: " + L.bgpt_replicas_last_error().decode())
+    G = L.bgpt_replicas_devices(r)
+    n_streams, n_vocab = G * S, L.bgpt_replicas_n_vocab(r)
+    first = gf.synth_tokens(n_streams, gf.BASE.n_vocab, seed=9).astype(np.int32)
+    ids = np.zeros(seq * n_streams, np.int32)
+    dev_ms = np.zeros(G, np.float32)
+
+    def one_pass():
+        if L.bgpt_replicas_decode_greedy(r, first, 0, seq, ids, dev_ms) != 0:
+            raise SystemExit("bench.py: " + L.bgpt_replicas_last_error().decode())
+        return float(dev_ms.max())
+    for _ in range(max(1, args.warmup)):
+        one_pass()
+    sampler = ClockSampler(0).start()
+    ms_total = sum(one_pass() for _ in range(args.steps))
+    clocks = sampler.stop()
+    # host buffers: one bgpt_replicas_eval per lock-step token, logits back, argmax on the host (a bounded 64-step sample)
+    n_e2e = min(seq, 64)
+    logits = np.zeros((n_streams, n_vocab), np.float32)
+    cur = first.copy()
+    t0 = time.perf_counter()
+    for p in range(n_e2e):
+        if L.bgpt_replicas_eval(r, cur, p, logits.reshape(-1)) != 0:
+            raise SystemExit("bench.py: " + L.bgpt_replicas_last_error().decode())
+        cur = np.argmax(logits, axis=1).astype(np.int32)
+    wall = time.perf_counter() - t0
+    same = bool(np.array_equal(cur, ids.reshape(seq, n_streams)[n_e2e - 1]))
+    L.bgpt_replicas_close(r)
+    pk, pk_src = peaks()
+    nbytes = sum(bytes_per_token(ftype, p) + (S - 1) * (196_608 * (p + 1) + 196_608 + 169_536 + 2 * 768) for p in range(seq))
+    step_ms = ms_total / args.steps
+    achieved = nbytes / (step_ms / 1e3) / 1e9
+    emit({"metric": "tokens/sec BioGPT-base Q5_1 decode, lock-step streams", "value": n_streams * seq * args.steps / (ms_total / 1e3), "unit": UNIT,
+          "n_gpus": G, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "int8*int8->f32 (Q8_1 activations), f32 KV", "data": "synthetic",
+          "config": {"workload": f"BioGPT-base {ftype}, {S} lock-step streams per GPU x {G} GPUs, seq 1->{seq} (BASELINE.json configs[3])",
+                     "ftype": ftype, "seq": seq, "streams_per_gpu": S, "parallelism": f"replicas x{G}", "driver": "C++ replica driver, one host thread per GPU (no torch, no NCCL)",
+                     "l2": "inputs larger than L2: every step streams the full weight set and S KV caches"},
+          "clocks": clocks,
+          "e2e": {"value": n_streams * n_e2e / wall, "unit": UNIT, "h2d_bytes_per_step": seq * 4 * n_streams, "d2h_bytes_per_step": seq * n_streams * n_vocab * 4,
+                  "sample": f"first {n_e2e} lock-step tokens through bgpt_replicas_eval", "ids_equal_device_loop": same},
+          "gpu_launches": None, "per_device_ms": [float(x) for x in dev_ms],
+          "roofline": {"bound": "hbm", "kernel": "fused skinny-batch schedule (k_sk_mm / k_sk_attn / k_sk_ln / k_sk_gq), per GPU", "achieved": achieved,
+                       "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": _traffic("streams_q5_1_x8")},
+          "cpu_baseline": None})
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  A "step" is a BOUNDED sample
     of the workload (9 evenly spaced positions of the 1024-token decode, `reps` evals each); ms_per_step is the time that sample
@@ -419,6 +487,9 @@ def main():
                     help="decode: BASELINE configs[1] (the headline, default); streams: configs[3] -- `--streams` lock-step Q5_1 sequences per GPU, "
                          "replicated over the ranks (64 streams on 8 GPUs)")
     ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--driver", default="ranks", choices=["ranks", "cpp"],
+                    help="streams workload: ranks = one engine per torchrun rank (default); cpp = ONE process drives --gpus devices through the "
+                         "C++ replica driver of libbiogpt_b200.so (include/bgpt_replicas.h: one host thread per GPU, no torch)")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE.json configs[2] / configs[3] side measurements")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -450,6 +521,12 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
 
+    if args.workload == "streams" and args.driver == "cpp":
+        if rank == 0:
+            run_streams_cpp_driver(args)
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
     if args.workload == "streams":
         run_streams_workload(args, capi, dist, barrier, rank, local_rank, world)
         return
