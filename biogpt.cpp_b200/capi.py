@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_topk", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_read_rows_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_mul_mat_tcx", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -86,6 +86,7 @@ def lib():
     L.bgpt_cuda_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bgpt_cuda_op_quantize_weights.argtypes = [C.c_int, _f32p, C.c_longlong, _u8p]
     L.bgpt_cuda_get_eval_path.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_debug_read_rows_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bgpt_cuda_set_tc_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_tcx_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
@@ -232,7 +233,7 @@ class Model:
         _check(lib().bgpt_cuda_set_decode_path(self.h, path), "set_decode_path")
 
     def set_batch_path(self, path: int):
-        """1: fused skinny-batch schedule for 2..111 rows where it applies (default), 0: per-operator kernels"""
+        """2: persistent multi-row kernel for 2..8 rows, skinny beyond (default); 1: fused skinny-batch schedule; 0: per-operator kernels"""
         _check(lib().bgpt_cuda_set_batch_path(self.h, path), "set_batch_path")
 
     def read_buffer(self, which: int, rows: int) -> np.ndarray:
@@ -255,8 +256,8 @@ class Model:
         _check(lib().bgpt_cuda_set_tc_min_rows(self.h, rows), "set_tc_min_rows")
 
     def eval_path(self, n_rows: int) -> int:
-        """3 persistent decode kernel, 1 fused skinny-batch schedule, 0 per-operator exact SIMT, 2 per-operator with the
-        tcgen05 matmul (the only one that is tolerance-close instead of bit-identical)"""
+        """3 persistent decode kernel, 5 persistent multi-row kernel, 1 fused skinny-batch schedule, 0 per-operator exact SIMT,
+        4 per-operator with the bit-exact tcgen05 matmul, 2 per-operator with the tolerance-close tcgen05 matmul (opt-in)"""
         return int(lib().bgpt_cuda_get_eval_path(self.h, n_rows))
 
     @property
@@ -283,6 +284,12 @@ class Model:
             return None
         nc, per = nc.value, per.value
         return buf[:nc * per].reshape(nc, -1, 5, 12), buf[nc * per:nc * per + 4 * nc].reshape(nc, 4)
+
+    def read_rows_trace(self):
+        """multi-row kernel: [n_layer + 1][8] clock64 stamps of CTA 0 (needs BGPT_MEGA_PROF=1 before load) or None"""
+        buf = np.zeros(4096, dtype=np.int64)
+        n = lib().bgpt_cuda_debug_read_rows_trace(self.h, buf.ctypes.data, buf.size)
+        return buf[:n].reshape(-1, 8) if n else None
 
     def set_streams(self, n: int):
         _check(lib().bgpt_cuda_set_streams(self.h, n), "set_streams")

@@ -30,6 +30,7 @@
 #include "bgpt_quant.cuh"
 #include "bgpt_topk.cuh"
 #include "bgpt_skinny.cuh"
+#include "bgpt_rows.cuh"
 #include "bgpt_tu.h"
 
 #include <cstdarg>
@@ -123,11 +124,14 @@ struct bgpt_model {
     // generation-5 persistent kernel (bgpt_mega5.cuh): clusters of 4, one attention head per cluster, DSMEM exchange inside the head
     bool mega5_ok = false; M5Params m5{}; unsigned long long * d_xch5 = nullptr; unsigned int m5_tag = 0;
     int * d_err5 = nullptr; int * h_err5 = nullptr; long long * d_trace5 = nullptr; size_t trace5_n = 0;
+    // persistent multi-row kernel (bgpt_rows.cuh): 2..8 token rows per eval in one launch
+    bool rows_ok = false; RowsParams rw{}; unsigned int * d_cnt_rows = nullptr; int * d_err_rows = nullptr; long long * d_trace_rows = nullptr;
+    bool rows_used = false; int rows_coop = 1;
     int mega_gen_pref = 5;                               // highest generation allowed (BGPT_MEGA_V / bgpt_cuda_set_decode_path)
     // per-operator schedule replayed as a CUDA graph, one per (rows, mode, token buffer): every kernel reads n_past from m->st
     struct FwdGraph { cudaGraphExec_t exec; uint64_t launches; };
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
-    int batch_path = 1;                                   // 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies, 0: per-operator kernels
+    int batch_path = 2;                                   // 2: persistent multi-row kernel (bgpt_rows.cuh) for 2..8 rows, skinny beyond; 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies; 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
     int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;
     int sk_fc1_split = 1;                                 // 1: fc1 as plain 8-row CTAs + k_sk_gq (8 Q5_1 streams 979 -> 943 us per step, prompt unchanged), 0: quantising epilogue (BGPT_SK_FC1_SPLIT)
@@ -226,6 +230,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
     cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch); cudaFree(m->d_trace);
     cudaFree(m->d_xch5); cudaFree(m->d_err5); cudaFree(m->d_trace5);
+    cudaFree(m->d_cnt_rows); cudaFree(m->d_err_rows); cudaFree(m->d_trace_rows);
     if (m->h_err5) cudaFreeHost(m->h_err5);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
@@ -341,6 +346,7 @@ static void init_kernel_attrs() {
 static int mega_setup(bgpt_model * m);
 static int mega4_setup(bgpt_model * m, const cudaDeviceProp & prop);
 static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop);
+static int rows_setup(bgpt_model * m, const cudaDeviceProp & prop);
 
 extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (!m) return fail(BGPT_E_ARG, "finalize: NULL model");
@@ -372,7 +378,7 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     init_kernel_attrs();
     if (getenv("BGPT_GRAPH")) m->use_graphs = atoi(getenv("BGPT_GRAPH")) != 0;
     if (getenv("BGPT_PDL")) m->use_pdl = atoi(getenv("BGPT_PDL")) != 0;
-    if (getenv("BGPT_BATCH_PATH")) m->batch_path = atoi(getenv("BGPT_BATCH_PATH")) != 0;
+    if (getenv("BGPT_BATCH_PATH")) m->batch_path = std::max(0, std::min(2, atoi(getenv("BGPT_BATCH_PATH"))));
     if (getenv("BGPT_SK_PDL_TRIG")) m->sk_pdl_trig = atoi(getenv("BGPT_SK_PDL_TRIG")) != 0;
     if (getenv("BGPT_SK_TN_PROJ")) m->sk_tn_proj = atoi(getenv("BGPT_SK_TN_PROJ")) == 8 ? 8 : (atoi(getenv("BGPT_SK_TN_PROJ")) == 4 ? 4 : 0);
     if (getenv("BGPT_SK_TN_QKV")) m->sk_tn_qkv = atoi(getenv("BGPT_SK_TN_QKV")) == 4 ? 4 : 8;
@@ -624,6 +630,41 @@ static bool skinny_ok(const bgpt_model * m, int n) {
     return m->batch_path >= 1 && !m->taps_armed && bg_is_quant(m->wtype) && m->d_model == SK_D && m->d_ff == 4096 &&
            m->d_model / m->n_head == SK_DK && m->n_positions <= 1024 && n >= 2 && n < std::min(m->tc_min_rows, m->tcx_min_rows);
 }
+// persistent multi-row kernel: one launch per eval of 2..8 rows
+static bool rows_path_ok(const bgpt_model * m, int n) {
+    return m->rows_ok && m->batch_path >= 2 && n <= RW_MAXS && skinny_ok(m, n);
+}
+static int enqueue_forward_rows(bgpt_model * m, const int * d_tokens, int n, int mode) {
+    RowsParams P = m->rw;
+    MegaParams & q = P.b;
+    q.kcache = m->kcache; q.vcache = m->vcache; q.logits = m->logits;
+    q.x = m->x; q.x1 = m->x1; q.q = m->q; q.att = m->att; q.hff = m->hff;
+    P.tokens = d_tokens; P.st = m->st; P.n = n; P.mode = mode; P.stream_stride = (unsigned long long) m->stream_stride;
+    P.rec_d = m->act_d; P.rec_f = m->act_ff;
+    CK(cudaMemsetAsync(m->d_cnt_rows, 0, (size_t) (m->n_layer + 1) * RW_NST * sizeof(unsigned int), m->stream));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(RW_NC); cfg.blockDim = dim3(RW_NT); cfg.dynamicSmemBytes = (size_t) P.sm_total; cfg.stream = m->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;        // all CTAs co-resident: they wait on each other's counters
+    cfg.attrs = at; cfg.numAttrs = m->rows_coop ? 1 : 0;
+    void * args[] = { &P };
+    CK(cudaLaunchKernelExC(&cfg, bgpt_k_rows_fn(m->wtype), args));
+    m->launches++;
+    m->rows_used = true;
+    return BGPT_OK;
+}
+// a watchdog code left by the multi-row kernel (checked after the stream has been synchronised)
+static int check_rows_error(bgpt_model * m) {
+    if (!m->rows_used) return BGPT_OK;
+    m->rows_used = false;
+    int code = 0;
+    CK(cudaMemcpy(&code, m->d_err_rows, sizeof(int), cudaMemcpyDeviceToHost));
+    if (code == 0) return BGPT_OK;
+    CK(cudaMemset(m->d_err_rows, 0, sizeof(int)));
+    return fail(BGPT_E_CUDA, "persistent multi-row kernel: a wait timed out -- stage %d, layer %d, wait %d; results are invalid",
+                code >> 16, (code >> 8) & 0xff, code & 0xff);
+}
+
 static void sk_init_attrs() {
     static unsigned long long done = 0;
     if (!first_use_on_current_device(done)) return;
@@ -765,6 +806,7 @@ static int enqueue_forward_skinny(bgpt_model * m, const int * d_tokens, int n, i
 // (4-5 us each on the host side); a graph replays them back to back.  n_past, the step counter and the token ids live in device
 // memory (m->st, d_tokens), so one graph per (rows, mode, token buffer) serves every position.  BGPT_GRAPH=0 disables.
 static int enqueue_any(bgpt_model * m, const int * d_tokens, int n, int mode) {
+    if (rows_path_ok(m, n)) return enqueue_forward_rows(m, d_tokens, n, mode);
     return skinny_ok(m, n) ? enqueue_forward_skinny(m, d_tokens, n, mode) : enqueue_forward(m, d_tokens, n, mode);
 }
 static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
@@ -788,6 +830,7 @@ static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
             if (rc == BGPT_OK && ie == cudaSuccess) break;
             fg.exec = nullptr;
             cudaGetLastError();
+            if (attempt == 0 && m->rows_coop && rows_path_ok(m, n)) { m->rows_coop = 0; continue; }   // cooperative launch refused inside a graph: plain launch (co-residency was checked in rows_setup)
             if (attempt == 0 && m->use_pdl && skinny_ok(m, n)) { m->use_pdl = 0; continue; }   // programmatic edges refused: plain edges
             if (rc != BGPT_OK) return rc;
             CK(ie);
@@ -801,7 +844,7 @@ static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
 }
 
 extern "C" int bgpt_cuda_set_batch_path(bgpt_model * m, int path) {
-    if (!m || path < 0 || path > 1) return fail(BGPT_E_ARG, "set_batch_path: path must be 0 or 1");
+    if (!m || path < 0 || path > 2) return fail(BGPT_E_ARG, "set_batch_path: path must be 0 (per-operator), 1 (skinny-batch schedule) or 2 (persistent multi-row kernel up to 8 rows, skinny beyond)");
     CK(cudaSetDevice(m->device));
     CK(cudaStreamSynchronize(m->stream));
     if (path != m->batch_path) drop_graphs(m);
@@ -840,13 +883,14 @@ extern "C" int bgpt_cuda_set_tcx_min_rows(bgpt_model * m, int rows) {
     m->tcx_min_rows = rows == 0 ? (1 << 30) : std::max(2, rows);
     return BGPT_OK;
 }
-extern "C" int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows) { return m && skinny_ok(m, n_rows) ? 1 : 0; }
+extern "C" int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows) { return !m ? 0 : rows_path_ok(m, n_rows) ? 2 : skinny_ok(m, n_rows) ? 1 : 0; }
 static bool use_mega(const bgpt_model * m);
 // which schedule an eval of n_rows token rows takes: 3 persistent decode kernel, 1 fused skinny-batch schedule (exact), 2 per-operator
 // schedule with the tcgen05 matmul (tolerance-close), 0 per-operator schedule with the exact-order SIMT matmul
 extern "C" int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows) {
     if (!m || n_rows < 1) return -1;
     if (n_rows == 1 && use_mega(m)) return 3;
+    if (rows_path_ok(m, n_rows)) return 5;
     if (skinny_ok(m, n_rows)) return 1;
     if (bg_is_quant(m->wtype) && n_rows >= m->tc_min_rows) return 2;
     if (bg_is_quant(m->wtype) && n_rows >= m->tcx_min_rows) return 4;
@@ -934,6 +978,7 @@ static int mega_setup(bgpt_model * m) {
     if (e) m->decode_path = atoi(e);
     if (m->mega_ok) RET(mega4_setup(m, prop));
     if (m->mega_ok) RET(mega5_setup(m, prop));
+    if (m->mega_ok) RET(rows_setup(m, prop));
     return BGPT_OK;
 }
 
@@ -1090,6 +1135,58 @@ static int mega_generation(const bgpt_model * m) {
     if (m->mega4_ok && m->mega_gen_pref >= 4) return 4;
     return 3;
 }
+// persistent multi-row kernel (bgpt_rows.cuh): shared-memory plan, co-residency, counters
+static int rows_setup(bgpt_model * m, const cudaDeviceProp & prop) {
+    m->rows_ok = false;
+    const void * fn = bgpt_k_rows_fn(m->wtype);
+    static_assert(sizeof(RowsParams) <= 4096, "RowsParams must fit the 4 KB kernel parameter space");
+    if (!fn || m->n_layer > M5_MAXL || m->d_model != M5_D || m->d_ff != M5_FF || m->n_head != M5_NH || m->n_positions > 1024 ||
+        prop.multiProcessorCount < RW_NC || m->n_vocab < RW_NC) return BGPT_OK;
+    RowsParams & P = m->rw;
+    P.b = m->mp;
+    for (int i = 0; i < m->n_layer; i++) P.layers[i] = m->h_mega_layers[i];
+    auto al = [](int x) { return (x + 127) & ~127; };
+    const int sd = P.b.stride_d, sf = P.b.stride_f;
+    const int lim = (int) prop.sharedMemPerBlockOptin - 4096;                 // static shared memory + margin
+    P.slot_bytes = al(std::max(std::max(32 * sd, 8 * sf), RW_LMRT * sd));
+    const int rec = al(std::max(RW_MAXS * std::max(P.b.actb_d, P.b.actb_f), (1024 + 32 * SK_DK + 31 * SK_DK) * 4));
+    P.nslot = M4_NSLOT;
+    while (P.nslot > 2 && P.nslot * P.slot_bytes + rec > lim) P.nslot--;
+    if (P.nslot * P.slot_bytes + rec > lim) return BGPT_OK;
+    P.sm_w = 0; P.sm_rec = P.nslot * P.slot_bytes; P.sm_total = P.sm_rec + rec;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sm_total));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RW_NT, (size_t) P.sm_total) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return BGPT_OK; }
+    const size_t cb = (size_t) (m->n_layer + 1) * RW_NST * sizeof(unsigned int);
+    CK(cudaMalloc(&m->d_cnt_rows, cb)); CK(cudaMemset(m->d_cnt_rows, 0, cb));
+    {
+        CK(cudaMalloc(&m->d_err_rows, 4 * sizeof(int)));
+        long long limit = 300000000LL;
+        if (getenv("BGPT_M5_WATCHDOG_MCYC")) limit = std::max(1LL, atoll(getenv("BGPT_M5_WATCHDOG_MCYC"))) * 1000000LL;
+        int init[4] = { 0, 0, 0, 0 };
+        memcpy(init + 2, &limit, sizeof limit);
+        CK(cudaMemcpy(m->d_err_rows, init, sizeof init, cudaMemcpyHostToDevice));
+    }
+    P.cnt = m->d_cnt_rows; P.err = m->d_err_rows; P.trace = nullptr;
+    if (m->d_prof) {
+        const size_t tb = (size_t) (m->n_layer + 1) * RW_NST * sizeof(long long);
+        CK(cudaMalloc(&m->d_trace_rows, tb)); CK(cudaMemset(m->d_trace_rows, 0, tb));
+        P.trace = m->d_trace_rows;
+    }
+    if (getenv("BGPT_ROWS_COOP")) m->rows_coop = atoi(getenv("BGPT_ROWS_COOP")) != 0;
+    m->rows_ok = true;
+    return BGPT_OK;
+}
+// debug: clock64 stamps of CTA 0 in the last multi-row launch (BGPT_MEGA_PROF=1): [n_layer + 1][RW_NST]
+extern "C" int bgpt_cuda_debug_read_rows_trace(bgpt_model * m, long long * out, int cap) {
+    if (!m || !out || !m->d_trace_rows) return 0;
+    const int n = (m->n_layer + 1) * RW_NST;
+    if (cap < n) return 0;
+    cudaStreamSynchronize(m->stream);
+    if (cudaMemcpy(out, m->d_trace_rows, (size_t) n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+
 // a watchdog code left by the generation-5 kernel (checked after the stream has been synchronised)
 static int check_mega5_error(bgpt_model * m) {
     if (!m->mega5_ok) return BGPT_OK;
@@ -1224,6 +1321,7 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
     CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
+    RET(check_rows_error(m));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     if (n == 1 && use_mega(m) && mega_generation(m) == 5) RET(check_mega5_error(m));
     memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
@@ -1268,6 +1366,7 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     CK(cudaMemcpyAsync(m->h_topk, m->d_topk, 8 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
+    RET(check_rows_error(m));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     if (mega && mega_generation(m) == 5) RET(check_mega5_error(m));
     const int * hinfo = (const int *) m->h_topk;
@@ -1297,6 +1396,7 @@ extern "C" int bgpt_cuda_synchronize(bgpt_model * m) {
     if (!m) return fail(BGPT_E_ARG, "synchronize: NULL model");
     CK(cudaSetDevice(m->device));
     CK(cudaStreamSynchronize(m->stream));
+    RET(check_rows_error(m));
     return BGPT_OK;
 }
 
@@ -1315,6 +1415,7 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
         m->idlog_cap = n_steps;
     }
     CK(cudaStreamSynchronize(s));
+    RET(check_rows_error(m));
     m->h_tokens[0] = first_token;
     m->h_st->n_past = n_past; m->h_st->step = 0;
     CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1340,6 +1441,7 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaMemcpyAsync(m->h_idlog, m->d_idlog, (size_t) n_steps * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    RET(check_rows_error(m));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     if (use_mega(m) && mega_generation(m) == 5) RET(check_mega5_error(m));
     memcpy(ids_out, m->h_idlog, (size_t) n_steps * sizeof(int));
@@ -1372,6 +1474,7 @@ extern "C" int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, in
     if (logits_out) CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) n_streams * m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
+    RET(check_rows_error(m));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     if (logits_out) memcpy(logits_out, m->h_logits, (size_t) n_streams * m->n_vocab * 4);
     return BGPT_OK;
@@ -1398,6 +1501,7 @@ extern "C" int bgpt_cuda_decode_greedy_streams(bgpt_model * m, const int32_t * f
         m->idlog_cap = need;
     }
     CK(cudaStreamSynchronize(s));
+    RET(check_rows_error(m));
     memcpy(m->h_tokens, first_tokens, (size_t) n_streams * sizeof(int));
     m->h_st->n_past = n_past; m->h_st->step = 0;
     CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n_streams * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1413,6 +1517,7 @@ extern "C" int bgpt_cuda_decode_greedy_streams(bgpt_model * m, const int32_t * f
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaMemcpyAsync(m->h_idlog, m->d_idlog, (size_t) need * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    RET(check_rows_error(m));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
     memcpy(ids_out, m->h_idlog, (size_t) need * sizeof(int));
     if (ms_out) *ms_out = m->last_ms;

@@ -122,17 +122,17 @@ int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int
  * fused operator.  All produce identical bits; tests compare them.  BGPT_MEGA_V=3|4 caps the generation at load time. */
 int bgpt_cuda_set_decode_path(bgpt_model * m, int path);
 int bgpt_cuda_get_decode_path(const bgpt_model * m);
-/* Which schedule evaluates skinny batches (2 <= n < 112 token rows: prompt chunks of the reference's
- * n_batch = 8 and lock-step streams): 1 = the fused schedule of csrc/bgpt_skinny.cuh (default where
- * it applies: quantised weights at BioGPT-base layer shapes; 5 launches per layer, LayerNorm /
- * quantise / GELU folded into the matmul kernels, programmatic dependent launch), 0 = one kernel
- * per fused operator.  Identical bits; tests compare them.  get: 1 if an n_rows-row eval would run
- * on the fused schedule. */
+/* Which schedule evaluates skinny batches (2 <= n < 128 token rows: prompt chunks of the reference's
+ * n_batch = 8 and lock-step streams): 2 (default) = the persistent multi-row kernel of csrc/bgpt_rows.cuh
+ * for 2..8 rows -- ONE launch per eval, stage boundaries are counters in L2 -- and the fused schedule
+ * beyond; 1 = the fused schedule of csrc/bgpt_skinny.cuh (quantised weights at BioGPT-base layer shapes;
+ * 8 launches per layer chained by programmatic dependent launch); 0 = one kernel per fused operator.
+ * Identical bits; tests compare them.  get: 2 / 1 / 0 = what an n_rows-row eval would run on. */
 int bgpt_cuda_set_batch_path(bgpt_model * m, int path);
 int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows);
-/* Which schedule an eval of n_rows token rows takes on this model: 3 = persistent decode kernel (n_rows == 1), 1 = fused
- * skinny-batch schedule, 0 = per-operator schedule with the exact-order SIMT matmul -- these three give the reference's bits
- * -- as does 4 = per-operator schedule with the bit-exact tcgen05 matmul (k_gemm_tc_x; quantised evals of 128+ rows); these four
+/* Which schedule an eval of n_rows token rows takes on this model: 3 = persistent decode kernel (n_rows == 1), 5 = persistent
+ * multi-row kernel (2..8 rows), 1 = fused skinny-batch schedule, 0 = per-operator schedule with the exact-order SIMT matmul -- these give the reference's bits
+ * -- as does 4 = per-operator schedule with the bit-exact tcgen05 matmul (k_gemm_tc_x; quantised evals of 128+ rows); these five
  * are the only ones used by default -- 2 = per-operator schedule with the one-term-per-block tcgen05 matmul of csrc/bgpt_tc.cuh
  * (exact integer block dots but one f32 term per block: logits drift by ~5e-2, see tests/test_gpu_eval.py), which is OFF
  * unless enabled with bgpt_cuda_set_tc_min_rows / BGPT_TC_MIN_ROWS. */
@@ -156,6 +156,8 @@ int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap);
  * {globaltimer ns, clock64} pairs taken at the start and the end of the launch, which put the
  * per-SM clocks on one time axis.  Returns the number of entries copied (0: off / cap too small). */
 int bgpt_cuda_debug_read_trace(bgpt_model * m, long long * out, int cap, int * n_cta, int * per_cta);
+/* debug (BGPT_MEGA_PROF=1): clock64 stamps of CTA 0 in the last multi-row launch, [n_layer + 1][8 stages]; [n_layer][7] = start */
+int bgpt_cuda_debug_read_rows_trace(bgpt_model * m, long long * out, int cap);
 /* f32 -> Q4_0/Q4_1/Q5_0/Q5_1/Q8_0 blocks in the file layout, on the device; bit-identical to the reference's
  * quantize_row_q*_reference as its `quantize` tool runs them (ggml.c:892-1094, biogpt.cpp:459-621).  `type` is a
  * ggml_type; n (a multiple of 32) host floats in, n/32 blocks out. */

@@ -189,6 +189,8 @@ def test_skinny_schedule_equals_oracle_and_per_op_path(checkers, capi, zoo, ftyp
     p = zoo.path("narrow", ftype)
     O = checkers.Oracle(p)
     M = capi.Model.load(p, max_batch=128)
+    assert M.batch_path(8) == 2 and M.batch_path(2) == 2 and M.batch_path(9) == 1, capi.last_error()    # 2..8 rows: bgpt_rows.cuh
+    M.set_batch_path(1)
     assert M.batch_path(8) == 1 and M.batch_path(1) == 0 and M.batch_path(111) == 1 and M.batch_path(128) == 0, capi.last_error()
     toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=55)
     sizes = [8, 8, 5, 2, 3, 4, 7, 16, 9, 1, 8, 31, 8, 6]             # 116 positions: T = 8, 16, 21, 23, 26, 30, 37, 53, 62, 63, 71, 102, ...
@@ -229,11 +231,74 @@ def test_skinny_lockstep_streams_equal_single_stream(capi, zoo, ftype):
         M = capi.Model.load(p, max_batch=16)
         single = [np.stack([M.eval(seqs[s][i:i + 1], i) for i in range(steps)]) for s in range(S)]
         M.set_streams(S)
+        M.set_batch_path(1)
         assert M.batch_path(S) == 1
         for i in range(steps):
             out = M.eval_streams(np.array([seqs[s][i] for s in range(S)], np.int32), i)
             for s in range(S):
                 assert np.array_equal(_bits(out[s]), _bits(single[s][i])), _diff(f"{ftype} S={S} stream {s} step {i}", out[s], single[s][i])
+        M.close()
+
+
+@pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_multi_row_kernel_equals_oracle_and_skinny_schedule(checkers, capi, zoo, ftype):
+    """BioGPT-base layer shapes, 2..8 token rows on the persistent multi-row kernel (csrc/bgpt_rows.cuh: one launch per eval,
+    stage boundaries are counters in L2).  Un-masked prompt batches of every size 2..8 at T across the 32-wide boundary, both
+    scalar tails of the V product, T > 512 and the end of the context must give the oracle's bits; the KV cache the kernel
+    wrote must serve the single-token persistent kernel and the skinny schedule (and theirs must serve it)."""
+    hp = gf.NARROW
+    p = zoo.path("narrow", ftype)
+    O = checkers.Oracle(p)
+    M = capi.Model.load(p, max_batch=16)
+    assert [M.eval_path(n) for n in (1, 2, 8, 9)] == [3, 5, 5, 1], capi.last_error()
+    toks = gf.synth_tokens(hp.n_positions, hp.n_vocab, seed=4242)
+    sizes = [8, 8, 5, 2, 3, 4, 7, 6, 1, 8, 2, 8, 12, 3, 8]            # 1 row: decode kernel, 12 rows: skinny schedule, on the same cache
+    sched, pos = [], 0
+    for n in sizes:
+        sched.append((pos, n)); pos += n
+    while pos < 520:
+        sched.append((pos, 8)); pos += 8
+    for n in (7, 5, 3, 2, 4, 6):
+        sched.append((pos, n)); pos += n
+    while pos < hp.n_positions:
+        n = min(8, hp.n_positions - pos); sched.append((pos, n)); pos += n
+    got_rows = []
+    for pos, n in sched:
+        want = O.eval(toks[pos:pos + n], pos)
+        got = M.eval(toks[pos:pos + n], pos)
+        assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} multi-row kernel n={n} at {pos} (path {M.eval_path(n)})", got, want)
+        got_rows.append(got)
+    M.set_batch_path(1)
+    assert M.eval_path(8) == 1
+    for (pos, n), ref in zip(sched, got_rows):
+        got = M.eval(toks[pos:pos + n], pos)
+        assert np.array_equal(_bits(got), _bits(ref)), (ftype, pos, n)
+    O.close(); M.close()
+
+
+@pytest.mark.parametrize("ftype", ["q5_1", "q4_0", "q8_0"])
+def test_multi_row_kernel_lockstep_streams_equal_single_stream(capi, zoo, ftype):
+    """BASELINE configs[3] per GPU at BioGPT-base layer shapes: S <= 8 sequences in lock step on the persistent multi-row kernel;
+    every stream must equal its own single-stream run (persistent decode kernel) bit for bit -- through the host-buffer call and
+    through the device-side greedy loop"""
+    hp = gf.NARROW
+    p = zoo.path("narrow", ftype)
+    steps = 40
+    for S in (8, 2, 5):
+        seqs = [gf.synth_tokens(steps, hp.n_vocab, seed=900 + 7 * S + s) for s in range(S)]
+        M = capi.Model.load(p, max_batch=16)
+        single = [np.stack([M.eval(seqs[s][i:i + 1], i) for i in range(steps)]) for s in range(S)]
+        M.set_streams(S)
+        assert M.batch_path(S) == 2 and M.eval_path(S) == 5
+        for i in range(steps):
+            out = M.eval_streams(np.array([seqs[s][i] for s in range(S)], np.int32), i)
+            for s in range(S):
+                assert np.array_equal(_bits(out[s]), _bits(single[s][i])), _diff(f"{ftype} S={S} stream {s} step {i}", out[s], single[s][i])
+        first = [int(seqs[s][0]) for s in range(S)]
+        ids_rows, _ = M.decode_greedy_streams(first, 0, 24)
+        M.set_batch_path(1)
+        ids_sk, _ = M.decode_greedy_streams(first, 0, 24)
+        assert np.array_equal(np.asarray(ids_rows), np.asarray(ids_sk)), (ftype, S)
         M.close()
 
 
@@ -378,11 +443,13 @@ def test_base_model_64_token_continuation(checkers, capi, zoo, ftype):
 def test_eval_path_map(capi, zoo):
     """which schedule a (model, rows) pair takes: only quantised evals of 112+ rows leave the bit-exact kernels"""
     M = capi.Model.load(zoo.path("narrow", "q5_1"), max_batch=128)
-    assert [M.eval_path(n) for n in (1, 2, 8, 111, 127, 128, 1024)] == [3, 1, 1, 1, 1, 4, 4]
+    assert [M.eval_path(n) for n in (1, 2, 8, 9, 111, 127, 128, 1024)] == [3, 5, 5, 1, 1, 1, 4, 4]
     M.set_tc_min_rows(112)
-    assert [M.eval_path(n) for n in (1, 8, 111, 112, 128)] == [3, 1, 1, 2, 2]
+    assert [M.eval_path(n) for n in (1, 8, 111, 112, 128)] == [3, 5, 1, 2, 2]
     M.set_tc_min_rows(0); M.set_tcx_min_rows(0)
-    assert [M.eval_path(n) for n in (1, 8, 128, 1024)] == [3, 1, 1, 1]
+    assert [M.eval_path(n) for n in (1, 8, 128, 1024)] == [3, 5, 1, 1]
+    M.set_batch_path(1)
+    assert [M.eval_path(n) for n in (2, 8)] == [1, 1]
     M.close()
     M = capi.Model.load(zoo.path("small", "q4_0"), max_batch=128)          # not BioGPT-base layer shapes: no skinny schedule
     assert [M.eval_path(n) for n in (1, 2, 32, 127, 128)] == [3, 0, 0, 0, 4]

@@ -67,6 +67,22 @@ bench)
   cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
 trace5)
   for np in 4 507 1015; do BGPT_MEGA_PROF=1 timeout 200 python tools/trace_decode5.py --n-past $np; done > $OUT/trace.log 2>&1; grep -v "Warning\|nanm\|return np" $OUT/trace.log | head -150 ;;
+rows)
+  timeout 1500 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=4 -x -k "multi_row or eval_path_map or skinny" > $OUT/pytest_rows.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_rows.log
+  grep -E "passed|failed|FAILED|Error|differ|timed out" $OUT/pytest_rows.log | tail -20 ;;
+rowsbench)
+  for bp in 2 1; do
+    BGPT_BATCH_PATH=$bp timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64 --n-past 0 2>&1 | tail -1
+    BGPT_BATCH_PATH=$bp timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 8 --steps 64 --n-past 900 2>&1 | tail -1
+    BGPT_BATCH_PATH=$bp timeout 300 python tools/streams_bench.py --ftype q5_1 --streams 4 --steps 64 --n-past 448 2>&1 | tail -1
+    BGPT_BATCH_PATH=$bp timeout 300 python tools/streams_bench.py --ftype q4_0 --streams 2 --steps 64 --n-past 448 2>&1 | tail -1
+    BGPT_BATCH_PATH=$bp BGPT_TCX_MIN_ROWS=0 timeout 300 python tools/prompt_bench.py --ftype q8_0 --n 8,4,2 2>&1 | tail -3
+  done > $OUT/rowsbench.log 2>&1
+  cat $OUT/rowsbench.log ;;
+rowstrace)
+  for np in 8 511 1000; do BGPT_MEGA_PROF=1 timeout 300 python tools/trace_rows.py --ftype q5_1 --rows 8 --mode streams --n-past $np; done > $OUT/rows_trace.log 2>&1
+  BGPT_MEGA_PROF=1 timeout 300 python tools/trace_rows.py --ftype q8_0 --rows 8 --mode prompt --n-past 504 >> $OUT/rows_trace.log 2>&1
+  cat $OUT/rows_trace.log ;;
 decode)
   for ft in ${FTYPES:-q4_0}; do for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
   cat $OUT/decode.log ;;
