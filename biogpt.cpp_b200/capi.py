@@ -30,10 +30,10 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_topk", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_read_rows_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_read_rows_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_set_tcw", "bgpt_cuda_set_f16_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
-    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_mul_mat_tcx", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
+    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_mul_mat_tcx", "bgpt_cuda_op_mul_mat_tcw", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
     "bgpt_cuda_op_attention", "bgpt_cuda_op_gelu", "bgpt_cuda_op_dequantize",
 ]
 
@@ -89,6 +89,8 @@ def lib():
     L.bgpt_cuda_debug_read_rows_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bgpt_cuda_set_tc_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_tcx_min_rows.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_set_tcw.argtypes = [C.c_void_p, C.c_int]
+    L.bgpt_cuda_set_f16_tc_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
     L.bgpt_cuda_decode_greedy_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.POINTER(C.c_float)]
@@ -104,6 +106,7 @@ def lib():
     L.bgpt_cuda_op_mul_mat.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_mul_mat_tc.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_mul_mat_tcx.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+    L.bgpt_cuda_op_mul_mat_tcw.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_quantize_act.argtypes = [C.c_int, _f32p, _u8p, C.c_int]
     L.bgpt_cuda_op_norm.argtypes = [_f32p, C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float]
     L.bgpt_cuda_op_attention.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u16p]
@@ -233,7 +236,7 @@ class Model:
         _check(lib().bgpt_cuda_set_decode_path(self.h, path), "set_decode_path")
 
     def set_batch_path(self, path: int):
-        """2: persistent multi-row kernel for 2..8 rows, skinny beyond (default); 1: fused skinny-batch schedule; 0: per-operator kernels"""
+        """1: fused skinny-batch schedule (default); 2: persistent multi-row kernel for 2..8 rows, skinny beyond (opt-in, slower); 0: per-operator kernels"""
         _check(lib().bgpt_cuda_set_batch_path(self.h, path), "set_batch_path")
 
     def read_buffer(self, which: int, rows: int) -> np.ndarray:
@@ -250,6 +253,14 @@ class Model:
     def set_tcx_min_rows(self, rows: int):
         """bit-exact tcgen05 matmul for quantised evals of `rows`+ rows (default 128; 0 = off)"""
         _check(lib().bgpt_cuda_set_tcx_min_rows(self.h, rows), "set_tcx_min_rows")
+
+    def set_tcw(self, on: int):
+        """1 (default): the bit-exact tcgen05 matmul runs as the warp-specialised TMA-fed kernel (k_tcw_exact); 0: k_gemm_tc_xf"""
+        _check(lib().bgpt_cuda_set_tcw(self.h, on), "set_tcw")
+
+    def set_f16_tc_min_rows(self, rows: int):
+        """F16 weights, opt-in: K-accumulating tcgen05 matmul (tolerance-close) for evals of `rows`+ rows (default 0 = off, all exact)"""
+        _check(lib().bgpt_cuda_set_f16_tc_min_rows(self.h, rows), "set_f16_tc_min_rows")
 
     def set_tc_min_rows(self, rows: int):
         """opt in to the tolerance-close integer tcgen05 matmul for quantised evals of `rows`+ rows (0 = off, the default)"""
@@ -351,6 +362,15 @@ def op_mul_mat_tcx(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int
     y = np.empty((n, rows), dtype=np.float32)
     _check(lib().bgpt_cuda_op_mul_mat_tcx(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
            "op_mul_mat_tcx")
+    return y
+
+
+def op_mul_mat_tcw(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, k = x.shape
+    y = np.empty((n, rows), dtype=np.float32)
+    _check(lib().bgpt_cuda_op_mul_mat_tcw(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
+           "op_mul_mat_tcw")
     return y
 
 

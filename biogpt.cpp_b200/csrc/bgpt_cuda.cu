@@ -112,6 +112,20 @@ struct bgpt_model {
     // the bit-exact tcgen05 matmul (k_gemm_tc_x: the 8 running sums per row through masked activation columns) serves quantised
     // evals of this many token rows and more on the per-operator schedule (BGPT_TCX_MIN_ROWS / bgpt_cuda_set_tcx_min_rows; 0 = off)
     int tcx_min_rows = 128;
+    // warp-specialised, TMA-fed form of that matmul (bgpt_tcw.cuh: k_tcw_exact, same bits) where the shapes allow it (rows % 128 == 0,
+    // K % 64 == 0: all BioGPT shapes); BGPT_TCW=0 keeps k_gemm_tc_xf.  Its operands: the prompt-operand cache (fp16 codes + f32 scale
+    // planes of every layer's matmul weights, decoded once on the first 128+-row eval: 2 bytes per weight) and, per matmul, the
+    // expanded activations of the eval.
+    int tcw = 1; int n_sm = 0;
+    struct TcwWeights { void * a16 = nullptr; float * sw = nullptr; float * mw = nullptr; };
+    std::map<const DevTensor *, TcwWeights> tcw_w; bool tcw_w_ready = false;
+    void * tcw_b16[2] = { nullptr, nullptr }; float * tcw_sa[2] = { nullptr, nullptr }; float * tcw_ss[2] = { nullptr, nullptr }; int tcw_cap = 0;
+    // F16 weights, OPT-IN: evals of this many token rows and more run their matmuls on k_tcw_f16 (tcgen05 kind::f16, f32 accumulation
+    // in TMEM + rounded f32 adds per 64 K: every matmul within 3e-7 of the reference's 32-lane sums, i.e. ordinary f32 summation-order
+    // noise -- which 24 layers of fp16 re-rounding and table look-ups amplify to 1.9e-3 on the logits of the full-size synthetic model
+    // (8e-4 on 2 layers; same argmax and top-5), beyond the north star's 1e-3, so the default stays the exact-order SIMT kernel).
+    // BGPT_F16_TC_MIN_ROWS / bgpt_cuda_set_f16_tc_min_rows; 0 = off (default).
+    int f16_tc_min_rows = 0; void * tcw_h16 = nullptr; int tcw_h_cap = 0;
     bool mega_ok = false; int decode_path = 1;          // 1: k_mega for n == 1, 0: per-op kernels
     MegaParams mp{}; MegaLayer * d_mega_layers = nullptr; std::vector<MegaLayer> h_mega_layers;
     unsigned long long * d_bar = nullptr; unsigned long long bar_epoch = 0;
@@ -131,7 +145,7 @@ struct bgpt_model {
     // per-operator schedule replayed as a CUDA graph, one per (rows, mode, token buffer): every kernel reads n_past from m->st
     struct FwdGraph { cudaGraphExec_t exec; uint64_t launches; };
     std::map<uint64_t, FwdGraph> graphs; int use_graphs = 1;
-    int batch_path = 2;                                   // 2: persistent multi-row kernel (bgpt_rows.cuh) for 2..8 rows, skinny beyond; 1: fused skinny-batch schedule (bgpt_skinny.cuh) where it applies; 0: per-operator kernels
+    int batch_path = 1;                                   // 1 (default): fused skinny-batch schedule (bgpt_skinny.cuh) where it applies; 2: persistent multi-row kernel (bgpt_rows.cuh) for 2..8 rows, skinny beyond -- opt-in, it measures slower (profiles/README.md); 0: per-operator kernels
     int use_pdl = 1;                                      // programmatic dependent launch inside that schedule (BGPT_PDL=0 disables)
     int sk_pdl_trig = 0, sk_tn_proj = 0, sk_tn_qkv = 8, sk_fc1_nw = 16, sk_skip = 0, sk_kv_prefetch = 1;
     int sk_fc1_split = 1;                                 // 1: fc1 as plain 8-row CTAs + k_sk_gq (8 Q5_1 streams 979 -> 943 us per step, prompt unchanged), 0: quantising epilogue (BGPT_SK_FC1_SPLIT)
@@ -151,8 +165,14 @@ static void drop_graphs(bgpt_model * m) {
     for (auto & g : m->graphs) cudaGraphExecDestroy(g.second.exec);
     m->graphs.clear();
 }
+static void free_tcw_acts(bgpt_model * m) {
+    for (int i = 0; i < 2; i++) { cudaFree(m->tcw_b16[i]); cudaFree(m->tcw_sa[i]); cudaFree(m->tcw_ss[i]); m->tcw_b16[i] = nullptr; m->tcw_sa[i] = m->tcw_ss[i] = nullptr; }
+    cudaFree(m->tcw_h16); m->tcw_h16 = nullptr;
+    m->tcw_cap = 0; m->tcw_h_cap = 0;
+}
 static void free_arena(bgpt_model * m) {
     drop_graphs(m);                                   // the graphs hold the arena's pointers
+    free_tcw_acts(m);
     cudaFree(m->d_tokens); cudaFree(m->x); cudaFree(m->x1); cudaFree(m->q); cudaFree(m->att); cudaFree(m->hff);
     cudaFree(m->logits); cudaFree(m->act_d); cudaFree(m->act_ff);
     for (int i = 0; i < 5; i++) { cudaFree(m->d_taps[i]); m->d_taps[i] = nullptr; }
@@ -226,6 +246,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (auto & kv : m->tensors) cudaFree(kv.second.ptr);
+    for (auto & kv : m->tcw_w) { cudaFree(kv.second.a16); cudaFree(kv.second.sw); cudaFree(kv.second.mw); }
     free_arena(m);
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
     cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch); cudaFree(m->d_trace);
@@ -388,6 +409,8 @@ extern "C" int bgpt_cuda_model_finalize(bgpt_model * m) {
     if (getenv("BGPT_SK_TN_FC1")) { const int v = atoi(getenv("BGPT_SK_TN_FC1")); m->sk_tn_fc1 = v == 8 ? 8 : (v == 4 ? 4 : 0); }
     if (getenv("BGPT_SK_FC1_SPLIT")) m->sk_fc1_split = atoi(getenv("BGPT_SK_FC1_SPLIT")) != 0;
     if (getenv("BGPT_TCX_MIN_ROWS")) { const int v = atoi(getenv("BGPT_TCX_MIN_ROWS")); m->tcx_min_rows = v > 0 ? std::max(2, v) : (1 << 30); }
+    if (getenv("BGPT_TCW")) m->tcw = atoi(getenv("BGPT_TCW")) != 0;
+    if (getenv("BGPT_F16_TC_MIN_ROWS")) { const int v = atoi(getenv("BGPT_F16_TC_MIN_ROWS")); m->f16_tc_min_rows = v > 0 ? std::max(2, v) : 0; }
     if (getenv("BGPT_TC_MIN_ROWS")) { const int v = atoi(getenv("BGPT_TC_MIN_ROWS")); m->tc_min_rows = v > 0 ? std::max(2, v) : (1 << 30); }
     RET(mega_setup(m));
     m->finalized = true;
@@ -431,6 +454,10 @@ static int launch_gemm_tc(bgpt_model * m, cudaStream_t s, const DevTensor * cons
                           int n, int tok0, const Epi & epi);
 static int launch_gemm_tcx(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
                            int n, int tok0, const Epi & epi);
+static bool tcw_exact_applies(const bgpt_model * m, const DevTensor * W0, int cnt, int tok0);
+static bool tcw_f16_applies(const bgpt_model * m, const DevTensor * W0, int cnt);
+static int launch_gemm_tcw(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], const GemvArgs & a);
+static int launch_gemm_tcw_f16(bgpt_model * m, cudaStream_t s, const GemvArgs & a, int K);
 
 // y = W . act for rows tok0..n-1; W = up to 3 stacked matrices sharing one layout
 static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], int nmat, const uint8_t * act, const ActLayout & A,
@@ -444,7 +471,9 @@ static int launch_gemv(bgpt_model * m, cudaStream_t s, const DevTensor * const W
     a.n = n; a.tok0 = tok0; a.epi = epi;
     const int cnt = n - tok0;
     if (bg_is_quant(L.type) && m && cnt >= m->tc_min_rows) return launch_gemm_tc(m, s, W, nmat, act, A, n, tok0, epi);
-    if (bg_is_quant(L.type) && m && cnt >= m->tcx_min_rows) return launch_gemm_tcx(m, s, W, nmat, act, A, n, tok0, epi);
+    if (bg_is_quant(L.type) && m && cnt >= m->tcx_min_rows)
+        return tcw_exact_applies(m, W[0], cnt, tok0) ? launch_gemm_tcw(m, s, W, a) : launch_gemm_tcx(m, s, W, nmat, act, A, n, tok0, epi);
+    if (L.type == BG_F16 && m && tcw_f16_applies(m, W[0], cnt)) return launch_gemm_tcw_f16(m, s, a, L.K);
     const int TN = cnt <= 1 ? 1 : cnt == 2 ? 2 : cnt <= 4 ? 4 : 8;
     const int gy = (cnt + TN - 1) / TN;
     const size_t smem = (size_t) TN * A.bytes;
@@ -525,6 +554,96 @@ static int launch_gemm_tcx(bgpt_model * m, cudaStream_t s, const DevTensor * con
     CK(cudaLaunchKernel(fn, grid, dim3(TC_THREADS), args, smem, s));
     if (m) m->launches++;
     CK(cudaGetLastError());
+    return BGPT_OK;
+}
+
+// ---- warp-specialised, TMA-fed tcgen05 matmuls (bgpt_tcw.cuh, tu_tcw.cu)
+static bool tcw_shape_ok(const DevTensor * W0) { return W0->ne1 % TW_ROWS == 0 && W0->L.K % TW_BK == 0; }
+static bool tcw_exact_applies(const bgpt_model * m, const DevTensor * W0, int cnt, int tok0) {
+    if (!m->tcw || !m->tcw_w_ready || tok0 != 0 || !tcw_shape_ok(W0) || cnt > m->tcw_cap) return false;
+    if (W0->L.K != m->d_model && W0->L.K != m->d_ff) return false;
+    return m->tcw_w.count(W0) != 0;
+}
+static bool tcw_f16_applies(const bgpt_model * m, const DevTensor * W0, int cnt) {
+    return m->f16_tc_min_rows > 0 && cnt >= m->f16_tc_min_rows && tcw_shape_ok(W0) && W0->L.stride == W0->L.K * 2 && cnt <= m->tcw_h_cap && m->tcw_h16;
+}
+// fp16 codes + f32 scale planes of one (stacked) weight: allocate and decode
+static int tcw_fill_weights(int wtype, cudaStream_t s, const DevTensor * const W[3], int nmat, bgpt_model::TcwWeights & o) {
+    const RowLayout & L = W[0]->L;
+    GemvArgs a{};
+    for (int i = 0; i < 3; i++) a.W[i] = W[i < nmat ? i : 0]->ptr;
+    a.rows_per = (int) W[0]->ne1; a.M = a.rows_per * nmat; a.G = L.G; a.stride = L.stride;
+    a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
+    const size_t nsc = (size_t) (L.K / 64) * a.M * 2 * sizeof(float);
+    CK(cudaMalloc(&o.a16, (size_t) a.M * L.K * 2));
+    CK(cudaMalloc(&o.sw, nsc));
+    if (wtype == BG_Q4_1 || wtype == BG_Q5_1) CK(cudaMalloc(&o.mw, nsc));
+    CK(bgpt_tcw_decode(wtype, s, a, L.K, o.a16, o.sw, o.mw));
+    return BGPT_OK;
+}
+// Everything the tcgen05 paths need that must not happen inside a stream capture: buffers for the expanded / fp16 activations of an
+// n-row eval and (quantised models, once) the prompt-operand cache of all layers.
+static int tcw_prepare(bgpt_model * m, int n) {
+    if (!bgpt_tcw_available()) return BGPT_OK;
+    const int d = m->d_model, ff = m->d_ff;
+    if (d % TW_ROWS || ff % TW_ROWS || d % TW_BK || ff % TW_BK) return BGPT_OK;
+    if (!m->n_sm) { CK(cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, m->device)); }
+    if (m->wtype == BG_F16) {
+        if (m->f16_tc_min_rows <= 0 || n < m->f16_tc_min_rows || n <= m->tcw_h_cap) return BGPT_OK;
+        CK(cudaStreamSynchronize(m->stream));
+        drop_graphs(m);
+        cudaFree(m->tcw_h16); m->tcw_h16 = nullptr; m->tcw_h_cap = 0;
+        const int cap = std::max(n, m->cap);
+        CK(cudaMalloc(&m->tcw_h16, (size_t) cap * ff * 2));
+        m->tcw_h_cap = cap;
+        return BGPT_OK;
+    }
+    if (!bg_is_quant(m->wtype) || !m->tcw || n < m->tcx_min_rows || n >= m->tc_min_rows) return BGPT_OK;
+    if (n > m->tcw_cap) {
+        CK(cudaStreamSynchronize(m->stream));
+        drop_graphs(m);
+        const int cap = (std::max(n, m->cap) + TWX_TOK - 1) / TWX_TOK * TWX_TOK;
+        for (int i = 0; i < 2; i++) { cudaFree(m->tcw_b16[i]); cudaFree(m->tcw_sa[i]); cudaFree(m->tcw_ss[i]); m->tcw_b16[i] = nullptr; m->tcw_sa[i] = m->tcw_ss[i] = nullptr; }
+        m->tcw_cap = 0;
+        for (int i = 0; i < 2; i++) {
+            const int K = i ? ff : d;
+            const size_t nb = (size_t) cap * 4 * K * 2, nsc = (size_t) (K / 64) * cap * 2 * sizeof(float);
+            CK(cudaMalloc(&m->tcw_b16[i], nb)); CK(cudaMemset(m->tcw_b16[i], 0, nb));       // the zero pattern of the masked columns, once
+            CK(cudaMalloc(&m->tcw_sa[i], nsc)); CK(cudaMalloc(&m->tcw_ss[i], nsc));
+        }
+        m->tcw_cap = cap;
+    }
+    if (!m->tcw_w_ready) {
+        CK(cudaStreamSynchronize(m->stream));
+        for (int l = 0; l < m->n_layer; l++) {
+            const LayerW & L = m->layers[l];
+            const DevTensor * Wq[3] = { L.q_w, L.k_w, L.v_w };
+            RET(tcw_fill_weights(m->wtype, m->stream, Wq, 3, m->tcw_w[L.q_w]));
+            for (const DevTensor * w : { L.o_w, L.fc1_w, L.fc2_w }) {
+                const DevTensor * W1[3] = { w, nullptr, nullptr };
+                RET(tcw_fill_weights(m->wtype, m->stream, W1, 1, m->tcw_w[w]));
+            }
+        }
+        CK(cudaStreamSynchronize(m->stream));
+        m->tcw_w_ready = true;
+    }
+    return BGPT_OK;
+}
+static int launch_gemm_tcw(bgpt_model * m, cudaStream_t s, const DevTensor * const W[3], const GemvArgs & a) {
+    const RowLayout & L = W[0]->L;
+    const bgpt_model::TcwWeights & w = m->tcw_w.at(W[0]);
+    const int ki = L.K == m->d_model ? 0 : 1;
+    const int cnt = a.n - a.tok0, n_pad = (cnt + TWX_TOK - 1) / TWX_TOK * TWX_TOK;
+    const int hasm = (L.type == BG_Q4_1 || L.type == BG_Q5_1) ? 1 : 0;
+    CK(bgpt_tcw_expand(s, a, L.K, n_pad, m->tcw_b16[ki], m->tcw_sa[ki], m->tcw_ss[ki], hasm));
+    CK(bgpt_tcw_gemm_exact(L.type, s, w.a16, w.sw, w.mw, m->tcw_b16[ki], m->tcw_sa[ki], m->tcw_ss[ki], a.M, L.K, a.n, a.tok0, n_pad, a.epi, m->n_sm));
+    m->launches += 2;
+    return BGPT_OK;
+}
+static int launch_gemm_tcw_f16(bgpt_model * m, cudaStream_t s, const GemvArgs & a, int K) {
+    CK(bgpt_tcw_act_h(s, a, K, m->tcw_h16));
+    CK(bgpt_tcw_gemm_f16(s, a, K, m->tcw_h16, m->n_sm));
+    m->launches += 2;
     return BGPT_OK;
 }
 
@@ -810,6 +929,7 @@ static int enqueue_any(bgpt_model * m, const int * d_tokens, int n, int mode) {
     return skinny_ok(m, n) ? enqueue_forward_skinny(m, d_tokens, n, mode) : enqueue_forward(m, d_tokens, n, mode);
 }
 static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
+    RET(tcw_prepare(m, n));
     if (!m->use_graphs || m->taps_armed) return enqueue_any(m, d_tokens, n, mode);
     const uint64_t key = ((uint64_t) (uintptr_t) d_tokens << 16) ^ ((uint64_t) n << 1) ^ (uint64_t) mode;
     auto it = m->graphs.find(key);
@@ -894,7 +1014,26 @@ extern "C" int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows) {
     if (skinny_ok(m, n_rows)) return 1;
     if (bg_is_quant(m->wtype) && n_rows >= m->tc_min_rows) return 2;
     if (bg_is_quant(m->wtype) && n_rows >= m->tcx_min_rows) return 4;
+    if (m->wtype == BG_F16 && m->f16_tc_min_rows > 0 && n_rows >= m->f16_tc_min_rows && bgpt_tcw_available() &&
+        m->d_model % TW_ROWS == 0 && m->d_ff % TW_ROWS == 0) return 7;
     return 0;
+}
+extern "C" int bgpt_cuda_set_f16_tc_min_rows(bgpt_model * m, int rows) {
+    if (!m || rows < 0) return fail(BGPT_E_ARG, "set_f16_tc_min_rows: bad arguments");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    drop_graphs(m);
+    m->f16_tc_min_rows = rows == 0 ? 0 : std::max(2, rows);
+    return BGPT_OK;
+}
+// 1: the warp-specialised TMA-fed kernel serves the bit-exact tcgen05 matmul (default), 0: k_gemm_tc_xf
+extern "C" int bgpt_cuda_set_tcw(bgpt_model * m, int on) {
+    if (!m) return fail(BGPT_E_ARG, "set_tcw: bad arguments");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    drop_graphs(m);
+    m->tcw = on != 0;
+    return BGPT_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1783,6 +1922,51 @@ extern "C" int bgpt_cuda_op_mul_mat_tcx(int type, const void * w, const float * 
     Epi e = make_epi(EPI_STORE, nullptr, dy.as<float>(), rows);
     RET(launch_gemm_tcx(nullptr, 0, W, 1, da.as<uint8_t>(), A, n, 0, e));
     CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(y, dy.p, (size_t) n * rows * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+// y = W . x through the warp-specialised TMA-fed kernels regardless of n (parity tests): quantised types -> k_tcw_exact (bit-exact),
+// F16 -> k_tcw_f16 (tolerance-close).  rows % 128 == 0 and k % 64 == 0.
+extern "C" int bgpt_cuda_op_mul_mat_tcw(int type, const void * w, const float * x, float * y, int k, int rows, int n) {
+    RET(need_device());
+    if (!bg_is_quant(type) && type != BG_F16) return fail(BGPT_E_UNSUPPORTED, "op_mul_mat_tcw: quantised or F16 weights only");
+    if (!w || !x || !y || k <= 0 || k % TW_BK || rows <= 0 || rows % TW_ROWS || n <= 0) return fail(BGPT_E_ARG, "op_mul_mat_tcw: bad arguments");
+    if (!bgpt_tcw_available()) return fail(BGPT_E_UNSUPPORTED, "op_mul_mat_tcw: the driver has no cuTensorMapEncodeTiled");
+    DevTensor t; t.type = type; t.ne0 = k; t.ne1 = rows;
+    RET(upload_matrix(t, type, k, rows, (const uint8_t *) w));
+    DevBuf wguard; wguard.p = t.ptr;
+    const ActLayout A = bg_act_layout(type, k);
+    DevBuf dx, da, dy;
+    RET(dx.alloc((size_t) n * k * 4)); RET(da.alloc((size_t) n * A.bytes)); RET(dy.alloc((size_t) n * rows * 4));
+    CK(cudaMemcpy(dx.p, x, (size_t) n * k * 4, cudaMemcpyHostToDevice));
+    RET(launch_act(nullptr, 0, dx.as<float>(), k, nullptr, nullptr, k, type, da.as<uint8_t>(), A, n, nullptr, 0));
+    int n_sm = 0; CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0));
+    const RowLayout & L = t.L;
+    GemvArgs a{};
+    for (int i = 0; i < 3; i++) a.W[i] = t.ptr;
+    a.rows_per = rows; a.M = rows; a.G = L.G; a.stride = L.stride; a.off_qh = L.off_qh; a.off_d = L.off_d; a.off_m = L.off_m;
+    a.act = da.as<uint8_t>(); a.act_bytes = A.bytes; a.off_n = A.off_n; a.off_dd = A.off_d; a.off_s = A.off_s;
+    a.n = n; a.tok0 = 0; a.epi = make_epi(EPI_STORE, nullptr, dy.as<float>(), rows);
+    if (type == BG_F16) {
+        if (L.stride != k * 2) return fail(BGPT_E_ARG, "op_mul_mat_tcw: F16 needs k %% 256 == 0");
+        DevBuf h; RET(h.alloc((size_t) n * k * 2));
+        CK(bgpt_tcw_act_h(0, a, k, h.p));
+        CK(bgpt_tcw_gemm_f16(0, a, k, h.p, n_sm));
+        CK(cudaDeviceSynchronize());
+    } else {
+        const int n_pad = (n + TWX_TOK - 1) / TWX_TOK * TWX_TOK;
+        const int hasm = (type == BG_Q4_1 || type == BG_Q5_1) ? 1 : 0;
+        const size_t nscw = (size_t) (k / 64) * rows * 2 * 4, nsca = (size_t) (k / 64) * n_pad * 2 * 4;
+        DevBuf a16, sw, mw, b16, sa, ss;
+        RET(a16.alloc((size_t) rows * k * 2)); RET(sw.alloc(nscw)); RET(mw.alloc(nscw));
+        RET(b16.alloc((size_t) n_pad * 4 * k * 2)); RET(sa.alloc(nsca)); RET(ss.alloc(nsca));
+        CK(cudaMemset(b16.p, 0, (size_t) n_pad * 4 * k * 2));
+        CK(bgpt_tcw_decode(type, 0, a, k, a16.p, sw.as<float>(), hasm ? mw.as<float>() : nullptr));
+        CK(bgpt_tcw_expand(0, a, k, n_pad, b16.p, sa.as<float>(), ss.as<float>(), hasm));
+        CK(bgpt_tcw_gemm_exact(type, 0, a16.p, sw.as<float>(), mw.as<float>(), b16.p, sa.as<float>(), ss.as<float>(), rows, k, n, 0, n_pad, a.epi, n_sm));
+        CK(cudaDeviceSynchronize());
+    }
     CK(cudaMemcpy(y, dy.p, (size_t) n * rows * 4, cudaMemcpyDeviceToHost));
     return BGPT_OK;
 }

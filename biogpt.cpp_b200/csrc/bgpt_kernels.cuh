@@ -334,6 +334,54 @@ __device__ __forceinline__ void bg_epilogue(const Epi & e, int tok, int r, float
     }
 }
 
+// the same epilogues for NT consecutive token rows n0 .. n0 + NT - 1 of one weight row r (the tensor-core kernels: a thread owns a
+// row and a run of tokens): everything that is loaded (bias, residual, GELU table) is loaded before the first store, so the loads
+// of the NT tokens travel together instead of one dependent round trip per token
+template <int NT>
+__device__ __forceinline__ void bg_epilogue_rows(const Epi & e, int n0, int nmax, int r, const float (&v)[NT]) {
+    switch (e.kind) {
+    case EPI_STORE: {
+        const bool hb = e.bias[0] != nullptr;
+        const float b = hb ? e.bias[0][r] : 0.0f;
+#pragma unroll
+        for (int t = 0; t < NT; t++) if (n0 + t < nmax) e.out[(size_t) (n0 + t) * e.ld_out + r] = hb ? __fadd_rn(b, v[t]) : v[t];
+        break; }
+    case EPI_QKV: {
+        const int mat = r / e.d, rr = r - mat * e.d;
+        const float b = e.bias[mat][rr];
+        if (mat == 0) {
+#pragma unroll
+            for (int t = 0; t < NT; t++) if (n0 + t < nmax) e.out[(size_t) (n0 + t) * e.ld_out + rr] = __fmul_rn(__fadd_rn(b, v[t]), e.qscale);
+        } else {
+            const int n_past = e.st->n_past;
+            float * base = mat == 1 ? e.kcache : e.vcache;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                if (n0 + t >= nmax) continue;
+                int stream, pos, T; bg_row_info(e.mode, e.n, n_past, n0 + t, stream, pos, T);
+                base[(size_t) stream * e.stream_stride + (size_t) pos * e.d + rr] = __fadd_rn(b, v[t]);
+            }
+        }
+        break; }
+    case EPI_RESID: {
+        const float b = e.bias[0][r];
+        float res[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) res[t] = n0 + t < nmax ? e.resid[(size_t) (n0 + t) * e.ld_resid + r] : 0.0f;
+#pragma unroll
+        for (int t = 0; t < NT; t++) if (n0 + t < nmax) e.out[(size_t) (n0 + t) * e.ld_out + r] = __fadd_rn(__fadd_rn(v[t], b), res[t]);
+        break; }
+    case EPI_GELU: {
+        const float b = e.bias[0][r];
+        uint16_t g[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) g[t] = e.gelu[bg_f2h(__fadd_rn(b, v[t]))];
+#pragma unroll
+        for (int t = 0; t < NT; t++) if (n0 + t < nmax) e.out[(size_t) (n0 + t) * e.ld_out + r] = bg_h2f(g[t]);
+        break; }
+    }
+}
+
 struct GemvArgs {
     const uint8_t * W[3];     // up to three stacked matrices (q,k,v) of rows_per rows each
     int rows_per;             // rows of one matrix

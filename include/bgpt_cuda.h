@@ -123,17 +123,19 @@ int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int n_past, int
 int bgpt_cuda_set_decode_path(bgpt_model * m, int path);
 int bgpt_cuda_get_decode_path(const bgpt_model * m);
 /* Which schedule evaluates skinny batches (2 <= n < 128 token rows: prompt chunks of the reference's
- * n_batch = 8 and lock-step streams): 2 (default) = the persistent multi-row kernel of csrc/bgpt_rows.cuh
- * for 2..8 rows -- ONE launch per eval, stage boundaries are counters in L2 -- and the fused schedule
- * beyond; 1 = the fused schedule of csrc/bgpt_skinny.cuh (quantised weights at BioGPT-base layer shapes;
- * 8 launches per layer chained by programmatic dependent launch); 0 = one kernel per fused operator.
+ * n_batch = 8 and lock-step streams): 1 (default) = the fused schedule of csrc/bgpt_skinny.cuh (quantised
+ * weights at BioGPT-base layer shapes; 8 launches per layer chained by programmatic dependent launch);
+ * 2 = the persistent multi-row kernel of csrc/bgpt_rows.cuh for 2..8 rows -- ONE launch per eval, stage
+ * boundaries are counters in L2 -- and the fused schedule beyond (opt-in: it measures 15-25 % slower than
+ * the fused schedule, profiles/README.md); 0 = one kernel per fused operator.
  * Identical bits; tests compare them.  get: 2 / 1 / 0 = what an n_rows-row eval would run on. */
 int bgpt_cuda_set_batch_path(bgpt_model * m, int path);
 int bgpt_cuda_get_batch_path(const bgpt_model * m, int n_rows);
 /* Which schedule an eval of n_rows token rows takes on this model: 3 = persistent decode kernel (n_rows == 1), 5 = persistent
  * multi-row kernel (2..8 rows), 1 = fused skinny-batch schedule, 0 = per-operator schedule with the exact-order SIMT matmul -- these give the reference's bits
- * -- as does 4 = per-operator schedule with the bit-exact tcgen05 matmul (k_gemm_tc_x; quantised evals of 128+ rows); these five
- * are the only ones used by default -- 2 = per-operator schedule with the one-term-per-block tcgen05 matmul of csrc/bgpt_tc.cuh
+ * -- as does 4 = per-operator schedule with the bit-exact tcgen05 matmul (k_tcw_exact / k_gemm_tc_xf; quantised evals of 128+ rows);
+ * these are the only ones used by default -- 7 = F16 weights, opt-in (bgpt_cuda_set_f16_tc_min_rows): per-operator schedule with
+ * the K-accumulating tcgen05 matmul (k_tcw_f16; tolerance-close); 2 = per-operator schedule with the one-term-per-block tcgen05 matmul of csrc/bgpt_tc.cuh
  * (exact integer block dots but one f32 term per block: logits drift by ~5e-2, see tests/test_gpu_eval.py), which is OFF
  * unless enabled with bgpt_cuda_set_tc_min_rows / BGPT_TC_MIN_ROWS. */
 int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows);
@@ -141,6 +143,19 @@ int bgpt_cuda_get_eval_path(const bgpt_model * m, int n_rows);
  * columns) serves quantised evals of `rows`+ token rows on the per-operator schedule (default 128; 0 = off: the skinny-batch
  * schedule then serves every batch size).  bgpt_cuda_get_eval_path reports 4 for it; results are the reference's bits. */
 int bgpt_cuda_set_tcx_min_rows(bgpt_model * m, int rows);
+/* 1 (default): that bit-exact matmul runs as the warp-specialised, TMA-fed kernel of csrc/bgpt_tcw.cuh (k_tcw_exact: a TMA
+ * producer warp, an MMA warp, eight epilogue warps, double-buffered TMEM; operands = the model's prompt-operand cache + the
+ * eval's expanded activations) wherever rows % 128 == 0 and K % 64 == 0 (all BioGPT shapes); 0: k_gemm_tc_xf.  Same bits.
+ * BGPT_TCW=0 at load does the same. */
+int bgpt_cuda_set_tcw(bgpt_model * m, int on);
+/* F16 weights, OPT-IN (default 0 = off: every F16 eval is bit-exact): evals of `rows`+ token rows run their matmuls on the
+ * K-accumulating tcgen05 kernel k_tcw_f16 (csrc/bgpt_tcw.cuh; fp16 x fp16 -> f32 in TMEM, fed by TMA from the weights where they
+ * lie; 1024 prompt tokens in one eval: 138 -> 12.6 ms).  The tensor core adds the reference's products in its own order: each
+ * matmul is within 3e-7 (relative to its largest output) of the reference, the error of any f32 re-ordering, and the logits of
+ * the 2-layer test model within 8e-4 -- but 24 layers of fp16 re-rounding amplify it to 1.9e-3 on the full-size synthetic model
+ * (same argmax and top-5), outside the north star's 1e-3 gate for f16, hence opt-in.  bgpt_cuda_get_eval_path reports 7 for it.
+ * BGPT_F16_TC_MIN_ROWS at load does the same. */
+int bgpt_cuda_set_f16_tc_min_rows(bgpt_model * m, int rows);
 /* opt in to the tolerance-close integer tcgen05 matmul for quantised evals of `rows`+ token rows (0 = off, the default) */
 int bgpt_cuda_set_tc_min_rows(bgpt_model * m, int rows);
 /* debug: copy one of the eval arena's buffers as the last eval left it (0 x, 1 x1, 2 q, 3 the d_model-wide activation
@@ -196,6 +211,10 @@ int bgpt_cuda_op_mul_mat(int ggml_type, const void * w, const float * x, float *
 /* the same product through the BIT-EXACT tcgen05 tensor-core kernel used for prompt batches of 128+ rows (csrc/bgpt_tc.cuh,
  * k_gemm_tc_x; quantised types only): identical bits to bgpt_cuda_op_mul_mat */
 int bgpt_cuda_op_mul_mat_tcx(int ggml_type, const void * w, const float * x, float * y,
+                             int k, int rows, int n);
+/* the same product through the warp-specialised TMA-fed kernels of csrc/bgpt_tcw.cuh: quantised types -> k_tcw_exact (identical
+ * bits to bgpt_cuda_op_mul_mat), F16 -> k_tcw_f16 (tolerance-close).  rows % 128 == 0, k % 64 == 0 (F16: k % 256 == 0). */
+int bgpt_cuda_op_mul_mat_tcw(int ggml_type, const void * w, const float * x, float * y,
                              int k, int rows, int n);
 /* the same product through the opt-in one-term-per-block tcgen05 kernel (k_gemm_tc_q).  Exact integer block dots, f32 block
  * accumulation in block order: close to, not bit-identical with, the CPU reference (see the file header). */

@@ -192,6 +192,46 @@ def test_mul_mat_tensor_core_exact(checkers, capi, name, shape):
 
 
 @pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+@pytest.mark.parametrize("shape", [(1024, 256, 64), (4096, 128, 70), (1024, 1024, 200), (64, 128, 5), (128, 128, 33), (1024, 3072, 17),
+                                   (1024, 2560, 160)])
+def test_mul_mat_tensor_core_exact_tma_fed(checkers, capi, name, shape):
+    """the warp-specialised, TMA-fed form of the bit-exact tcgen05 matmul (csrc/bgpt_tcw.cuh, k_tcw_exact: operands from the decoded
+    weight planes and the expanded activations by cp.async.bulk.tensor, double-buffered TMEM, FFMA2 chains) -- the oracle's bits for
+    every format, ragged token counts, one to many tiles per CTA and K = 64 .. 4096"""
+    k, rows, n = shape
+    t = TYPES[name]
+    rng = np.random.default_rng(k + rows * 3 + n + t)
+    w = (rng.standard_normal((rows, k)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    x[0, :32] = 0.0                                       # an all-zero activation block
+    wb = np.frombuffer(gf.encode_tensor(w, t), dtype=np.uint8).copy()
+    want = np.zeros((n, rows), dtype=np.float32)
+    checkers.oracle_lib().bo_mul_mat(t, wb, x, want, k, rows, n)
+    got = capi.op_mul_mat_tcw(t, wb, x, rows)
+    bad = np.flatnonzero(got.view(np.uint32).ravel() != want.view(np.uint32).ravel())
+    assert bad.size == 0, f"{name} {shape}: {bad.size}/{got.size} outputs differ, max|d|={np.abs(got - want).max():.3e}, first={bad[:6]}"
+
+
+@pytest.mark.parametrize("shape", [(1024, 256, 64), (4096, 128, 130), (256, 128, 5), (1024, 3072, 300), (1024, 1024, 128)])
+def test_mul_mat_tensor_core_f16(checkers, capi, shape):
+    """F16 weights on the K-accumulating tcgen05 matmul (csrc/bgpt_tcw.cuh, k_tcw_f16: weights by TMA where they lie, fp16-rounded
+    activations, f32 accumulation in TMEM).  Same products as ggml_vec_dot_f16 (ggml.c:2409-2443), added in the tensor core's order:
+    tolerance 2e-5 of the largest output (the f32 summation-order noise of a K <= 4096 dot), not bit equality."""
+    k, rows, n = shape
+    rng = np.random.default_rng(k + rows * 5 + n)
+    w = (rng.standard_normal((rows, k)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    wb = np.frombuffer(gf.encode_tensor(w, 1), dtype=np.uint8).copy()
+    want = np.zeros((n, rows), dtype=np.float32)
+    checkers.oracle_lib().bo_mul_mat(1, wb, x, want, k, rows, n)
+    got = capi.op_mul_mat_tcw(1, wb, x, rows)
+    err = np.abs(got - want).max()
+    tol = 2e-5 * np.abs(want).max() + 1e-7
+    print(f"f16 tcgen05 matmul {shape}: max|d| = {err:.3e} = {err / np.abs(want).max():.2e} of the largest output; mean signed d = {np.mean(got - want):.2e}")
+    assert err <= tol, f"f16 {shape}: max|d|={err:.3e} tol={tol:.3e}"
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_quantize_weights_equals_reference_quantiser(capi, name):
     """device f32 -> Qx blocks (csrc/bgpt_quant.cuh) == quantize_row_q*_reference as the reference's `quantize` tool
     runs it (ggml.c:892-1094).  The checker is ggml_file's numpy restatement, itself pinned to the tool's output and to

@@ -83,6 +83,36 @@ rowstrace)
   for np in 8 511 1000; do BGPT_MEGA_PROF=1 timeout 300 python tools/trace_rows.py --ftype q5_1 --rows 8 --mode streams --n-past $np; done > $OUT/rows_trace.log 2>&1
   BGPT_MEGA_PROF=1 timeout 300 python tools/trace_rows.py --ftype q8_0 --rows 8 --mode prompt --n-past 504 >> $OUT/rows_trace.log 2>&1
   cat $OUT/rows_trace.log ;;
+tcw)
+  timeout 1200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q --maxfail=8 -s -k "tma_fed or tensor_core_f16 or large_prompt or eval_path_map or f16_prompt" > $OUT/pytest_tcw.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_tcw.log
+  grep -E "passed|failed|FAILED|Error|differ|timed out|max\|d" $OUT/pytest_tcw.log | tail -40 ;;
+tcwbench)
+  for ft in ${FTYPES:-q8_0 q4_0 f16}; do BGPT_F16_TC_MIN_ROWS=32 timeout 600 python tools/prompt_bench.py --ftype $ft --n 32,128,256,1024 2>&1 | tail -4; done > $OUT/prompt_tcw.log 2>&1
+  BGPT_TCW=0 timeout 600 python tools/prompt_bench.py --ftype q8_0 --n 128,1024 2>&1 | tail -2 >> $OUT/prompt_tcw.log
+  BGPT_F16_TC_MIN_ROWS=0 timeout 600 python tools/prompt_bench.py --ftype f16 --n 32,128,1024 2>&1 | tail -3 >> $OUT/prompt_tcw.log
+  cat $OUT/prompt_tcw.log ;;
+ncutcw)
+  timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -s -k "tensor_core_f16" 2>&1 | grep -E "max\|d|passed|failed" > $OUT/f16_mm_err.log; cat $OUT/f16_mm_err.log
+  for ft in ${FTYPES:-q8_0 f16}; do
+    BGPT_F16_TC_MIN_ROWS=32 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_prompt_$ft.csv \
+        python tools/profile_prompt.py --ftype $ft --n 1024 > $OUT/launches_prompt_$ft.log 2>&1; echo "promptncu $ft rc=$?"
+    python tools/launch_summary.py $OUT/launches_prompt_$ft.csv 2>&1 | tail -12
+  done ;;
+ncutcwfull)
+  BGPT_F16_TC_MIN_ROWS=32 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tcw_f16 -s 4 -c 4 -f -o $OUT/tcw_f16_full \
+      python tools/profile_prompt.py --ftype f16 --n 1024 > $OUT/tcw_f16_full.log 2>&1; echo "f16 full rc=$?"
+  ncu -i $OUT/tcw_f16_full.ncu-rep --page raw --csv > $OUT/tcw_f16_full_raw.csv 2>/dev/null
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tcw_exact -s 4 -c 4 -f -o $OUT/tcw_exact_full \
+      python tools/profile_prompt.py --ftype q8_0 --n 1024 > $OUT/tcw_exact_full.log 2>&1; echo "exact full rc=$?"
+  ncu -i $OUT/tcw_exact_full.ncu-rep --page raw --csv > $OUT/tcw_exact_full_raw.csv 2>/dev/null
+  ls -la $OUT ;;
+tcwab)
+  for ft in q8_0 q5_1; do
+    for tpt in 4 8; do echo "BGPT_TCW_TPT=$tpt"; BGPT_TCW_TPT=$tpt timeout 600 python tools/prompt_bench.py --ftype $ft --n 128,1024 2>&1 | tail -2; done
+  done > $OUT/prompt_tcw_ab.log 2>&1
+  for sp in 1 0; do echo "BGPT_F16_TC_SPLIT=$sp"; BGPT_F16_TC_MIN_ROWS=32 BGPT_F16_TC_SPLIT=$sp timeout 600 python tools/prompt_bench.py --ftype f16 --n 32,128,1024 2>&1 | tail -3
+    BGPT_F16_TC_SPLIT=$sp timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q -s -k "tensor_core_f16 or f16_prompt" 2>&1 | grep -E "max\|d|passed|failed"; done >> $OUT/prompt_tcw_ab.log 2>&1
+  cat $OUT/prompt_tcw_ab.log ;;
 decode)
   for ft in ${FTYPES:-q4_0}; do for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
   cat $OUT/decode.log ;;

@@ -17,6 +17,7 @@ a = ap.parse_args()
 capi = importlib.import_module("biogpt_cpp_b200.capi")
 gf = bench.gf
 M = capi.Model.load(bench.model_path(a.ftype), max_batch=8)
+M.set_batch_path(2)                                  # the multi-row kernel is opt-in
 tok = gf.synth_tokens(a.rows, gf.BASE.n_vocab, seed=9).astype(np.int32)
 if a.mode == "streams":
     M.set_streams(a.rows)
