@@ -33,7 +33,7 @@ SYMBOLS = [
     "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_read_rows_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_set_tcw", "bgpt_cuda_set_f16_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
-    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_mul_mat_tcx", "bgpt_cuda_op_mul_mat_tcw", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
+    "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_mul_mat_tcx", "bgpt_cuda_op_mul_mat_tcw", "bgpt_cuda_op_topk", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
     "bgpt_cuda_op_attention", "bgpt_cuda_op_gelu", "bgpt_cuda_op_dequantize",
 ]
 
@@ -107,6 +107,7 @@ def lib():
     L.bgpt_cuda_op_mul_mat_tc.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_mul_mat_tcx.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     L.bgpt_cuda_op_mul_mat_tcw.argtypes = [C.c_int, _u8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+    L.bgpt_cuda_op_topk.argtypes = [_f32p, C.c_int, C.c_int, _f32p, _i32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bgpt_cuda_op_quantize_act.argtypes = [C.c_int, _f32p, _u8p, C.c_int]
     L.bgpt_cuda_op_norm.argtypes = [_f32p, C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float]
     L.bgpt_cuda_op_attention.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u16p]
@@ -216,12 +217,15 @@ class Model:
     def eval_topk(self, tokens: Sequence[int], n_past: int, k: int, fallback: bool = True):
         """(vals[K], ids[K], exact, full_logits_or_None): the K largest logits of the eval's last row, selected on the device"""
         t = np.ascontiguousarray(tokens, dtype=np.int32)
-        vals = np.zeros(k, dtype=np.float32)
-        ids = np.zeros(k, dtype=np.int32)
-        n_out, exact = C.c_int(0), C.c_int(0)
-        full = np.empty(self.n_vocab, dtype=np.float32) if fallback else None
-        _check(lib().bgpt_cuda_eval_topk(self.h, t, len(t), n_past, k, vals, ids, C.byref(n_out), C.byref(exact),
-                                         full.ctypes.data if fallback else None), "eval_topk")
+        st = getattr(self, "_topk_state", None)
+        if st is None or st[0] != k:                    # the output buffers are reused from call to call (the returned views are overwritten by the next call)
+            st = self._topk_state = (k, np.zeros(k, dtype=np.float32), np.zeros(k, dtype=np.int32), C.c_int(0), C.c_int(0),
+                                     np.empty(self.n_vocab, dtype=np.float32))
+        _, vals, ids, n_out, exact, full = st
+        rc = lib().bgpt_cuda_eval_topk(self.h, t, len(t), n_past, k, vals, ids, C.byref(n_out), C.byref(exact),
+                                       full.ctypes.data if fallback else None)
+        if rc != 0:
+            _check(rc, "eval_topk")
         return vals[:n_out.value], ids[:n_out.value], bool(exact.value), (full if fallback and not exact.value else None)
 
     def eval_streams(self, tokens: Sequence[int], n_past: int, fetch: bool = True) -> Optional[np.ndarray]:
@@ -363,6 +367,15 @@ def op_mul_mat_tcx(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int
     _check(lib().bgpt_cuda_op_mul_mat_tcx(ggml_type, np.ascontiguousarray(w_bytes, dtype=np.uint8), x, y, k, rows, n),
            "op_mul_mat_tcx")
     return y
+
+
+def op_topk(logits: np.ndarray, k: int):
+    """(vals, ids, exact): the device top-k selection on a host logit row"""
+    x = np.ascontiguousarray(logits, dtype=np.float32)
+    vals = np.zeros(k, dtype=np.float32); ids = np.zeros(k, dtype=np.int32)
+    n_out, exact = C.c_int(0), C.c_int(0)
+    _check(lib().bgpt_cuda_op_topk(x, len(x), k, vals, ids, C.byref(n_out), C.byref(exact)), "op_topk")
+    return vals[:n_out.value], ids[:n_out.value], bool(exact.value)
 
 
 def op_mul_mat_tcw(ggml_type: int, w_bytes: np.ndarray, x: np.ndarray, rows: int) -> np.ndarray:

@@ -95,6 +95,7 @@ struct bgpt_model {
     // arena for `cap` token rows
     int cap = 0;
     int * d_tokens = nullptr; int * d_idlog = nullptr; int * h_idlog = nullptr; int idlog_cap = 0;
+    uint8_t * d_topk_cand = nullptr; uint8_t * h_topk_dev = nullptr; unsigned topk_seq = 0; bool last_ms_pending = false;
     uint8_t * d_topk = nullptr; uint8_t * h_topk = nullptr;      // [TOPK_MAXK floats | TOPK_MAXK ints | 2 ints], device and pinned host   // h_idlog: pinned, idlog_cap ints
     float *x = nullptr, *x1 = nullptr, *q = nullptr, *att = nullptr, *hff = nullptr, *logits = nullptr;
     uint8_t *act_d = nullptr, *act_ff = nullptr;
@@ -255,7 +256,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     if (m->h_err5) cudaFreeHost(m->h_err5);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
-    cudaFree(m->d_topk); if (m->h_topk) cudaFreeHost(m->h_topk);
+    cudaFree(m->d_topk); cudaFree(m->d_topk_cand); if (m->h_topk) cudaFreeHost(m->h_topk);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -267,7 +268,14 @@ extern "C" void bgpt_cuda_hparams(const bgpt_model * m, int32_t o[7]) {
 }
 extern "C" size_t bgpt_cuda_weight_bytes(const bgpt_model * m) { return m->weight_bytes; }
 extern "C" uint64_t bgpt_cuda_launch_count(const bgpt_model * m) { return m->launches; }
-extern "C" float bgpt_cuda_last_eval_ms(const bgpt_model * m) { return m->last_ms; }
+extern "C" float bgpt_cuda_last_eval_ms(const bgpt_model * cm) {
+    bgpt_model * m = const_cast<bgpt_model *>(cm);
+    if (m->last_ms_pending) {                            // eval_topk returns on the result packet, before the closing event has completed
+        m->last_ms_pending = false;
+        if (cudaSetDevice(m->device) != cudaSuccess || cudaEventSynchronize(m->ev1) != cudaSuccess || cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) { cudaGetLastError(); m->last_ms = 0.f; }
+    }
+    return m->last_ms;
+}
 
 // which tensors are matmul operands (re-tiled) vs gather tables / vectors (kept as in the file)
 static bool is_matmul_weight(const std::string & n) {
@@ -1468,6 +1476,25 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
     return BGPT_OK;
 }
 
+// the large-vocabulary form of the device top-k (bgpt_topk.cuh): slices of 256 logits -> groups of 16 slices -> one CTA
+static size_t topk3_scratch_bytes(int n) {
+    const size_t n_slices = ((size_t) n + TOPK_SLICE - 1) / TOPK_SLICE, n_groups = (n_slices + TOPK_FAN - 1) / TOPK_FAN;
+    return (n_slices + n_groups) * (TOPK_MAXK + 1) * 8;
+}
+static int launch_topk3(cudaStream_t s, const float * logits, int n, int k, uint8_t * scratch, float * dv, int * di, int * dinfo, const int * errp, unsigned seq) {
+    const int kc = k + 1;
+    const int n_slices = (n + TOPK_SLICE - 1) / TOPK_SLICE, n_groups = (n_slices + TOPK_FAN - 1) / TOPK_FAN;
+    if ((size_t) n_groups * kc > TOPK_RANK_MAX) return fail(BGPT_E_UNSUPPORTED, "top-k: vocabulary of %d entries is too large for k = %d", n, k);
+    float * v1 = (float *) scratch;                 int * i1 = (int *) (scratch + (size_t) n_slices * kc * 4);
+    uint8_t * l2 = scratch + (size_t) n_slices * kc * 8;
+    float * v2 = (float *) l2;                      int * i2 = (int *) (l2 + (size_t) n_groups * kc * 4);
+    k_topk_part<<<n_slices, TOPK_SLICE, 0, s>>>(logits, n, kc, v1, i1);
+    k_topk_rank<false><<<n_groups, TOPK_RANK_NT, 0, s>>>(v1, i1, n_slices * kc, TOPK_FAN * kc, kc, v2, i2, k, nullptr, nullptr, 0u);
+    k_topk_rank<true><<<1, TOPK_RANK_NT, 0, s>>>(v2, i2, n_groups * kc, n_groups * kc, kc, dv, di, k, dinfo, errp, seq);
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+
 // eval + the K largest logits of the last row, for the sampler (bgpt_topk.cuh).  Host buffers: tokens in; vals / ids (K entries,
 // logit descending) and *exact out.  *exact = 0 means equal values make std::partial_sort's choice / order ambiguous: then (and
 // only then) the full logit row is copied to logits_fallback (n_vocab floats, may be NULL) so the caller can run the reference's
@@ -1479,9 +1506,18 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     if (k > TOPK_MAXK) return fail(BGPT_E_ARG, "eval_topk: k=%d exceeds %d; use bgpt_cuda_eval and sample on the host", k, TOPK_MAXK);
     CK(cudaSetDevice(m->device));
     RET(ensure_arena(m, n));
-    const size_t tk_bytes = (size_t) TOPK_MAXK * 8 + 8;
+    // packet: [info: entries, exact, forward-pass error code, sequence number][vals: k floats][ids: k ints]
+    const size_t tk_bytes = (size_t) TOPK_MAXK * 8 + 16;
+    const int kc = k + 1;
+    const int n_slices = (m->n_vocab + TOPK_SLICE - 1) / TOPK_SLICE;
     if (!m->d_topk) {
-        CK(cudaMalloc(&m->d_topk, tk_bytes)); CK(cudaMallocHost(&m->h_topk, tk_bytes));
+        static const bool zc = !(getenv("BGPT_TOPK_ZC") && atoi(getenv("BGPT_TOPK_ZC")) == 0);
+        CK(cudaMalloc(&m->d_topk, tk_bytes));
+        CK(cudaHostAlloc(&m->h_topk, tk_bytes, cudaHostAllocMapped));
+        memset(m->h_topk, 0, tk_bytes);
+        void * dp = nullptr;
+        if (zc && cudaHostGetDevicePointer(&dp, m->h_topk, 0) == cudaSuccess && dp) m->h_topk_dev = (uint8_t *) dp; else cudaGetLastError();
+        CK(cudaMalloc(&m->d_topk_cand, topk3_scratch_bytes(m->n_vocab)));
         cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);   // + 34 KB of static histograms
         cudaGetLastError();
     }
@@ -1496,22 +1532,52 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
         RET(forward(m, m->d_tokens, n, 0));
     }
-    const int staged = (size_t) m->n_vocab * 4 <= (size_t) 190 * 1024;
-    // packed as [info: 2 ints][vals: k floats][ids: k ints] so that ONE copy of 8 + 8 k bytes brings everything back
-    int * dinfo = (int *) m->d_topk; float * dv = (float *) (m->d_topk + 8); int * di = (int *) (m->d_topk + 8 + (size_t) k * 4);
-    k_topk<<<1, TOPK_NT, staged ? (size_t) m->n_vocab * 4 : 0, s>>>(m->logits, m->n_vocab, k, staged, dv, di, dinfo);
-    m->launches++;
+    // The packet goes straight into mapped pinned host memory when the device can address it (no copy, no stream synchronisation: the
+    // host polls the sequence number); otherwise into device memory + one D2H copy.
+    uint8_t * pk = m->h_topk_dev ? m->h_topk_dev : m->d_topk;
+    int * dinfo = (int *) pk; float * dv = (float *) (pk + 16); int * di = (int *) (pk + 16 + (size_t) k * 4);
+    const unsigned seq = ++m->topk_seq ? m->topk_seq : ++m->topk_seq;
+    const int * errp = (mega && mega_generation(m) == 5 && m->mega5_ok) ? m->d_err5 : nullptr;
+    if (m->n_vocab >= 4096) {
+        // every 256-logit slice ranks itself and keeps its k + 1 best; the single-CTA selection then runs over those candidates
+        RET(launch_topk3(s, m->logits, m->n_vocab, k, m->d_topk_cand, dv, di, dinfo, errp, seq));
+        m->launches += 3;
+    } else {
+        const int staged = (size_t) m->n_vocab * 4 <= (size_t) 190 * 1024;
+        k_topk<<<1, TOPK_NT, staged ? (size_t) m->n_vocab * 4 : 0, s>>>(m->logits, m->n_vocab, k, staged, dv, di, dinfo, nullptr, errp, seq);
+        m->launches++;
+    }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(m->h_topk, m->d_topk, 8 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
+    if (!m->h_topk_dev) CK(cudaMemcpyAsync(m->h_topk, m->d_topk, 16 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
-    CK(cudaStreamSynchronize(s));
+    m->last_ms_pending = true;
+    const volatile int * hinfo = (const volatile int *) m->h_topk;
+    if (m->h_topk_dev) {
+        bool got = false;
+        for (unsigned spins = 0; ; ) {
+            if ((unsigned) hinfo[3] == seq) { got = true; break; }
+            if ((++spins & 0x3FFu) == 0) {
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) return fail(BGPT_E_CUDA, "eval_topk: %s", cudaGetErrorString(q));
+                got = (unsigned) hinfo[3] == seq;
+                break;
+            }
+        }
+        if (!got) { CK(cudaStreamSynchronize(s)); if ((unsigned) hinfo[3] != seq) return fail(BGPT_E_CUDA, "eval_topk: the result packet never arrived"); }
+        __sync_synchronize();
+    } else CK(cudaStreamSynchronize(s));
     RET(check_rows_error(m));
-    CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
-    if (mega && mega_generation(m) == 5) RET(check_mega5_error(m));
-    const int * hinfo = (const int *) m->h_topk;
-    *n_out = hinfo[0]; *exact = hinfo[1];
-    memcpy(vals, m->h_topk + 8, (size_t) hinfo[0] * 4);
-    memcpy(ids, m->h_topk + 8 + (size_t) k * 4, (size_t) hinfo[0] * 4);
+    if (hinfo[2] != 0) {
+        const int code = hinfo[2];
+        cudaStreamSynchronize(s); cudaMemset(m->d_err5, 0, sizeof(int));
+        return fail(BGPT_E_CUDA, "persistent decode kernel (generation 5): a wait timed out -- stage %d, layer %d, wait %d; results are invalid",
+                    code >> 16, (code >> 8) & 0xff, code & 0xff);
+    }
+    const int got_n = hinfo[0];
+    *n_out = got_n; *exact = hinfo[1];
+    memcpy(vals, m->h_topk + 16, (size_t) got_n * 4);
+    memcpy(ids, m->h_topk + 16 + (size_t) k * 4, (size_t) got_n * 4);
     if (!hinfo[1] && logits_fallback) CK(cudaMemcpy(logits_fallback, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost));
     return BGPT_OK;
 }
@@ -1968,6 +2034,35 @@ extern "C" int bgpt_cuda_op_mul_mat_tcw(int type, const void * w, const float * 
         CK(cudaDeviceSynchronize());
     }
     CK(cudaMemcpy(y, dy.p, (size_t) n * rows * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
+// the device top-k of bgpt_cuda_eval_topk on a caller-supplied logit row (parity tests): n >= 4096 takes the two-launch form
+extern "C" int bgpt_cuda_op_topk(const float * logits, int n, int k, float * vals, int32_t * ids, int * n_out, int * exact) {
+    RET(need_device());
+    if (!logits || !vals || !ids || !n_out || !exact || n < 1 || k < 1 || k > TOPK_MAXK) return fail(BGPT_E_ARG, "op_topk: bad arguments");
+    cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);
+    cudaGetLastError();
+    const int kc = k + 1, n_slices = (n + TOPK_SLICE - 1) / TOPK_SLICE;
+    DevBuf dl, dp, dc;
+    RET(dl.alloc((size_t) n * 4)); RET(dp.alloc(16 + (size_t) k * 8)); RET(dc.alloc(topk3_scratch_bytes(n)));
+    CK(cudaMemcpy(dl.p, logits, (size_t) n * 4, cudaMemcpyHostToDevice));
+    uint8_t * pk = dp.as<uint8_t>();
+    int * dinfo = (int *) pk; float * dv = (float *) (pk + 16); int * di = (int *) (pk + 16 + (size_t) k * 4);
+    if (n >= 4096) {
+        RET(launch_topk3(0, dl.as<float>(), n, k, dc.as<uint8_t>(), dv, di, dinfo, nullptr, 1u));
+    } else {
+        const int staged = (size_t) n * 4 <= (size_t) 190 * 1024;
+        k_topk<<<1, TOPK_NT, staged ? (size_t) n * 4 : 0>>>(dl.as<float>(), n, k, staged, dv, di, dinfo, nullptr, nullptr, 1u);
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<uint8_t> h(16 + (size_t) k * 8);
+    CK(cudaMemcpy(h.data(), pk, h.size(), cudaMemcpyDeviceToHost));
+    const int * hi = (const int *) h.data();
+    *n_out = hi[0]; *exact = hi[1];
+    memcpy(vals, h.data() + 16, (size_t) hi[0] * 4);
+    memcpy(ids, h.data() + 16 + (size_t) k * 4, (size_t) hi[0] * 4);
     return BGPT_OK;
 }
 

@@ -24,9 +24,105 @@ __device__ __forceinline__ uint32_t topk_key(float f) {            // ascending 
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Large vocabularies go through three short launches instead of one CTA scanning every logit (the 4-pass radix select below measures
+// ~50 us even on 7 k keys: zeroing 32 per-warp histograms, match.any, a serial scan of 256 bins per pass): k_topk_part lets every
+// slice of TOPK_SLICE logits rank itself by counting (166 CTAs for 42384 logits) and keep its K + 1 best, k_topk_rank<false> merges
+// TOPK_FAN slices' candidates per CTA the same way, k_topk_rank<true> ranks the remaining few hundred and writes the result packet.
+// The global K + 1 largest values all lie in the union of the slices' K + 1 largest at every level, so the selection, its order
+// and the tie flags are the ones of the single-kernel form.
+#define TOPK_SLICE 256
+// grid = ceil(n / TOPK_SLICE), block = TOPK_SLICE: thread i owns logit i of the slice; its rank = number of slice entries before it
+// in (value descending, index ascending) order; ranks below kc are written to cand_*[slice][rank] (pads: -inf, index -1)
+static __global__ void __launch_bounds__(TOPK_SLICE) k_topk_part(const float * __restrict__ logits, int n, int kc,
+                                                                  float * __restrict__ cand_val, int * __restrict__ cand_idx) {
+    __shared__ __align__(16) uint32_t s_k[TOPK_SLICE];
+    const int tid = threadIdx.x, i = blockIdx.x * TOPK_SLICE + tid;
+    const float f = i < n ? logits[i] : -INFINITY;
+    const uint32_t u = i < n ? topk_key(f) : 0u;
+    s_k[tid] = u;
+    __syncthreads();
+    int rank = 0;
+#pragma unroll 8
+    for (int j4 = 0; j4 < TOPK_SLICE / 4; j4++) {
+        const uint4 o = ((const uint4 *) s_k)[j4];
+        const int j = j4 * 4;
+        rank += (o.x > u || (o.x == u && j + 0 < tid)) ? 1 : 0;
+        rank += (o.y > u || (o.y == u && j + 1 < tid)) ? 1 : 0;
+        rank += (o.z > u || (o.z == u && j + 2 < tid)) ? 1 : 0;
+        rank += (o.w > u || (o.w == u && j + 3 < tid)) ? 1 : 0;
+    }
+    if (rank < kc) {
+        cand_val[(size_t) blockIdx.x * kc + rank] = f;
+        cand_idx[(size_t) blockIdx.x * kc + rank] = i < n ? i : -1;
+    }
+}
+
+// second and third launch of the large-vocabulary form: rank-by-counting over a slice of `per` candidates (value, index) held in shared
+// memory, keep the kc best.  !FINAL: grid = slices, the survivors go to out_*[slice][rank] (pads: -inf, -1).  FINAL: one CTA over all
+// remaining candidates: the k best in order, info = { entries, exact, error code of the forward pass, sequence number } -- `exact`
+// is 0 when two neighbours among the k + 1 largest values are equal (a duplicate inside the top k, or the k-th tied with the
+// (k+1)-th: std::partial_sort's choice or order would be ambiguous).  The outputs may live in mapped pinned HOST memory: the sequence
+// number is written last, behind a system-scope fence, so a host thread that polls it sees a complete packet.
+#define TOPK_RANK_NT 512
+#define TOPK_FAN 16                     // slices merged per second-level CTA
+#define TOPK_RANK_MAX (TOPK_FAN * (TOPK_MAXK + 1))
+template <bool FINAL>
+static __global__ void __launch_bounds__(TOPK_RANK_NT) k_topk_rank(const float * __restrict__ val, const int * __restrict__ idx, int n_c, int per, int kc,
+                                                                    float * __restrict__ out_val, int * __restrict__ out_idx,
+                                                                    int k, int * __restrict__ info, const int * __restrict__ err, unsigned seq) {
+    __shared__ __align__(16) uint32_t s_k[TOPK_RANK_MAX + 4];
+    __shared__ uint32_t s_sorted[TOPK_MAXK + 2];
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * per;
+    int cnt = n_c - b0; cnt = cnt < per ? cnt : per; cnt = cnt < TOPK_RANK_MAX ? cnt : TOPK_RANK_MAX;
+    const int cnt4 = (cnt + 3) & ~3;
+    for (int i = tid; i < cnt4; i += TOPK_RANK_NT) s_k[i] = i < cnt ? topk_key(val[b0 + i]) : 0u;
+    if (FINAL) for (int i = tid; i < TOPK_MAXK + 2; i += TOPK_RANK_NT) s_sorted[i] = 0u;
+    __syncthreads();
+    for (int e = tid; e < cnt; e += TOPK_RANK_NT) {
+        const uint32_t u = s_k[e];
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < cnt4; j += 4) {
+            const uint4 o = *(const uint4 *) (s_k + j);
+            rank += (o.x > u || (o.x == u && j + 0 < e)) ? 1 : 0;
+            rank += (o.y > u || (o.y == u && j + 1 < e)) ? 1 : 0;
+            rank += (o.z > u || (o.z == u && j + 2 < e)) ? 1 : 0;
+            rank += (o.w > u || (o.w == u && j + 3 < e)) ? 1 : 0;
+        }
+        if (rank < kc) {
+            if (FINAL) {
+                s_sorted[rank] = u;
+                if (rank < k) { out_val[rank] = val[b0 + e]; out_idx[rank] = idx[b0 + e]; }
+            } else {
+                out_val[(size_t) blockIdx.x * kc + rank] = val[b0 + e];
+                out_idx[(size_t) blockIdx.x * kc + rank] = idx[b0 + e];
+            }
+        }
+    }
+    if (!FINAL) {
+        for (int r = cnt + tid; r < kc; r += TOPK_RANK_NT) { out_val[(size_t) blockIdx.x * kc + r] = -INFINITY; out_idx[(size_t) blockIdx.x * kc + r] = -1; }
+        return;
+    }
+    __threadfence_system();
+    __syncthreads();
+    const int k_eff = k < cnt ? k : cnt;
+    int dup = 0;
+    for (int j = tid; j < k_eff && j + 1 < cnt; j += TOPK_RANK_NT) dup |= (s_sorted[j] == s_sorted[j + 1]) ? 1 : 0;
+    dup = __syncthreads_or(dup);
+    if (tid == 0) {
+        info[0] = k_eff; info[1] = dup ? 0 : 1; info[2] = err ? *(volatile const int *) err : 0;
+        __threadfence_system();
+        *(volatile unsigned *) (info + 3) = seq;
+    }
+}
+
 // out_val / out_idx: K entries; info[0] = entries written (min(K, n)), info[1] = 1 if the selection and its order are unambiguous
+// (info: 4 ints, see the end of the kernel).
+// remap (optional): out_idx[rank] = remap[position] -- the input is a candidate list, not the logit row.
 static __global__ void __launch_bounds__(TOPK_NT) k_topk(const float * __restrict__ logits, int n, int k, int staged,
-                                                          float * __restrict__ out_val, int * __restrict__ out_idx, int * __restrict__ info) {
+                                                          float * __restrict__ out_val, int * __restrict__ out_idx, int * __restrict__ info,
+                                                          const int * __restrict__ remap, const int * __restrict__ err, unsigned seq) {
     extern __shared__ uint32_t s_keys[];                            // n keys when `staged`
     __shared__ unsigned hist[256];
     __shared__ unsigned whist[TOPK_NT / 32][256];                  // per-warp histograms
@@ -109,8 +205,16 @@ static __global__ void __launch_bounds__(TOPK_NT) k_topk(const float * __restric
         const uint32_t u = mk;
         const uint32_t bits = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
         out_val[rank] = __uint_as_float(bits);
-        out_idx[rank] = mi;
+        out_idx[rank] = remap ? remap[mi] : mi;
     }
+    // info = { entries, exact, error code of the forward pass (the persistent kernel's watchdog flag), sequence number }.  The outputs
+    // may live in mapped pinned HOST memory: the sequence number is written last, behind a system-scope fence, so a host thread that
+    // polls it sees a complete packet without a stream synchronisation.
+    __threadfence_system();
     __syncthreads();
-    if (tid == 0) { info[0] = k; info[1] = s_dup ? 0 : 1; }
+    if (tid == 0) {
+        info[0] = k; info[1] = s_dup ? 0 : 1; info[2] = err ? *(volatile const int *) err : 0;
+        __threadfence_system();
+        *(volatile unsigned *) (info + 3) = seq;
+    }
 }

@@ -220,6 +220,9 @@ int bgpt_cuda_op_mul_mat_tcw(int ggml_type, const void * w, const float * x, flo
  * accumulation in block order: close to, not bit-identical with, the CPU reference (see the file header). */
 int bgpt_cuda_op_mul_mat_tc(int ggml_type, const void * w, const float * x, float * y,
                             int k, int rows, int n);
+/* the device top-k selection of bgpt_cuda_eval_topk applied to a HOST logit row: the k largest (value, index) pairs by value
+ * descending; *exact = 0 when equal values make std::partial_sort's choice or order ambiguous (biogpt.cpp:908-980) */
+int bgpt_cuda_op_topk(const float * logits, int n, int k, float * vals, int32_t * ids, int * n_out, int * exact);
 /* activation quantisers applied to src1 by mul_mat (ggml.c:1166-1249, 1403-1494, 493-510):
  * out = k/32 blocks of block_q8_0 (34 B) / block_q8_1 (40 B) for the weight type's
  * vec_dot_type, or k fp16 values for F16 weights. */

@@ -274,3 +274,44 @@ def test_device_topk_selects_what_partial_sort_selects(capi, zoo):
                 assert fb is not None and np.array_equal(fb.view(np.uint32), full.view(np.uint32))
             assert np.array_equal(np.sort(vals)[::-1], vals)
     M.close()
+
+
+@pytest.mark.parametrize("n", [1000, 4096, 42384, 50001])
+def test_device_topk_selection_and_tie_flags(capi, n):
+    """the selection kernel(s) on crafted logit rows: n >= 4096 runs the two-launch form (every 256-logit slice keeps its K + 1
+    best, one CTA selects among the candidates), below that the single-CTA radix select.  Distinct values: ids == stable argsort.
+    Ties that make std::partial_sort's choice or order ambiguous (biogpt.cpp:908-980) must be flagged: the K-th value equal to the
+    (K+1)-th in another slice, in the same slice, more than K + 1 equal values inside one slice, two equal values inside the top K;
+    ties strictly below the K-th value must NOT be flagged."""
+    rng = np.random.default_rng(n)
+    base = rng.permutation(n).astype(np.float32) * 0.25 - 1000.0          # all distinct
+    for k in (1, 5, 40, 128):
+        order = np.argsort(-base, kind="stable")
+        vals, ids, exact = capi.op_topk(base, k)
+        assert exact and ids.tolist() == order[:k].tolist() and np.array_equal(vals, base[order[:k]]), (n, k)
+        kth, nxt = order[k - 1], order[k]
+        # boundary tie: the (K+1)-th gets the K-th value -- once far away (another slice), once right next to it
+        for where in ((int(kth) + n // 2) % n, (int(kth) + 1) % n):
+            x = base.copy()
+            if where in order[:k].tolist():
+                continue
+            x[where] = x[kth]
+            _, _, exact = capi.op_topk(x, k)
+            assert not exact, (n, k, where)
+        # more than K + 1 equal values at the threshold inside one slice
+        x = base.copy()
+        s0 = (int(kth) // 256) * 256
+        idx = [i for i in range(s0, min(s0 + 256, n)) if i not in set(order[:k - 1].tolist())][:k + 3]
+        x[idx] = x[kth]
+        _, _, exact = capi.op_topk(x, k)
+        assert not exact, (n, k, "slice full of ties")
+        if k >= 2:                                                   # duplicate inside the top K
+            x = base.copy(); x[order[0]] = x[order[1]]
+            _, _, exact = capi.op_topk(x, k)
+            assert not exact, (n, k, "duplicate in the top K")
+        # ties below the K-th value are harmless
+        x = base.copy(); x[order[k + 5]] = x[order[k + 6]] if k + 6 < n else x[order[k + 5]]
+        x[nxt] = np.float32(x[kth] - 0.125)
+        vals, ids, exact = capi.op_topk(x, k)
+        want = np.argsort(-x, kind="stable")[:k]
+        assert exact and ids.tolist() == want.tolist(), (n, k, "ties below the threshold")

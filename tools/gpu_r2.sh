@@ -113,6 +113,12 @@ tcwab)
   for sp in 1 0; do echo "BGPT_F16_TC_SPLIT=$sp"; BGPT_F16_TC_MIN_ROWS=32 BGPT_F16_TC_SPLIT=$sp timeout 600 python tools/prompt_bench.py --ftype f16 --n 32,128,1024 2>&1 | tail -3
     BGPT_F16_TC_SPLIT=$sp timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q -s -k "tensor_core_f16 or f16_prompt" 2>&1 | grep -E "max\|d|passed|failed"; done >> $OUT/prompt_tcw_ab.log 2>&1
   cat $OUT/prompt_tcw_ab.log ;;
+e2e)
+  timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_host_lib.py -m gpu -q --maxfail=5 -k "topk or sampler" > $OUT/pytest_topk.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_topk.log
+  grep -E "passed|failed|FAILED|Error|assert" $OUT/pytest_topk.log | tail -12
+  timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 > $OUT/e2e.log 2>&1
+  BGPT_TOPK_ZC=0 timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 >> $OUT/e2e.log 2>&1
+  cat $OUT/e2e.log ;;
 decode)
   for ft in ${FTYPES:-q4_0}; do for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
   cat $OUT/decode.log ;;
