@@ -301,6 +301,27 @@ def side_configs(capi, device: int, seq: int):
                      "decode_kernel_generation": M.decode_generation}
         M.close()
     out["format_sweep_n_past_511"] = {"workload": "single-token decode at n_past ~511, all six formats (BASELINE.json configs[4])", "formats": sweep}
+    # ---- the tcgen05 prompt path: the whole context as ONE un-masked eval (n_batch = seq).  Quantised: bit-exact k_tcw_exact
+    #      (warp-specialised, TMA-fed; csrc/bgpt_tcw.cuh); F16: the exact-order SIMT kernels by default, k_tcw_f16 when opted in.
+    big = {}
+    toks = gf.synth_tokens(seq, gf.BASE.n_vocab, seed=5)
+    flops = 2.0 * seq * 301989888 + 2 * 43401216 + 98304.0 * seq * seq
+    for ft, opt in (("q8_0", None), ("f16", 0), ("f16", 32)):
+        try:
+            M = capi.Model.load(model_path(ft), device=device, max_batch=seq)
+            if opt is not None:
+                M.set_f16_tc_min_rows(opt)
+            M.eval(toks, 0); M.eval(toks, 0)
+            ms = M.last_eval_ms
+            key = ft if opt is None else f"{ft}_tc_{'on' if opt else 'off'}"
+            big[key] = {"ms": ms, "tokens_per_s": seq / (ms / 1e3), "tflops": flops / (ms / 1e3) / 1e12,
+                        "frac_of_bf16_tensor_peak": flops / (ms / 1e3) / 1e12 / pk.get("bf16_tflops_sustained", 1391.1), "eval_path": M.eval_path(seq),
+                        "parity": "bit-identical to the reference" if M.eval_path(seq) != 7 else "tolerance-close (opt-in), see include/bgpt_cuda.h"}
+            M.close()
+        except Exception as e:                                # never lose the headline line to a side measurement
+            big[f"{ft}_{opt}"] = {"error": repr(e)}
+    out["prompt_one_eval"] = {"workload": f"BioGPT-base, {seq} prompt tokens in one un-masked eval (tcgen05 matmuls; un-masked f32 attention in exact lane order)",
+                              "formats": big}
     return out
 
 

@@ -1212,13 +1212,15 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     for (int i = 0; i < m->n_layer; i++) P.layers[i] = m->h_mega_layers[i];
     auto al = [](int x) { return (x + 127) & ~127; };
     const int sd = P.b.stride_d, sf = P.b.stride_f;
-    const int base = al(P.b.actb_d) + al(P.b.actb_f) + 2 * al(M5_D * 4) + al(1024 * 4) + al(32 * M5_HR * 4) + al(31 * M5_HR * 4);
+    const bool f16 = m->wtype == BG_F16;                                      // F16: fp16 records in the weights' in-row order (bgpt_mega5.cuh)
+    const int recd = f16 ? M5_D * 2 : P.b.actb_d, recf = f16 ? M5_FF * 2 : P.b.actb_f;
+    const int base = al(recd) + al(recf) + 2 * al(M5_D * 4) + al(1024 * 4) + al(32 * M5_HR * 4) + al(31 * M5_HR * 4);
     const int hasm = (m->wtype == BG_Q4_1 || m->wtype == BG_Q5_1) ? 2 : 1;
     const int scratch = al(8 * 8 * M5_PS * 4) + al(hasm * 8 * M5_NB_F * 4);      // fc2 two-phase: block products + scale products (+ minima)
     const int lim = (int) prop.sharedMemPerBlockOptin - 2048;             // static shared memory + margin
     auto slot_for = [&](int lmrt) { return al(std::max(std::max(32 * sd, 8 * sf), std::max(3 * M5_HR, lmrt) * sd)); };
     // preference: 4 ring slots; then the fc2 scratch (relay otherwise); then 64-row lm_head tiles
-    bool use_scratch = !(getenv("BGPT_M5_FC2") && atoi(getenv("BGPT_M5_FC2")) == 0);
+    bool use_scratch = !f16 && !(getenv("BGPT_M5_FC2") && atoi(getenv("BGPT_M5_FC2")) == 0);
     P.nslot = M4_NSLOT; P.lmrt = 64;
     auto total = [&]() { return P.nslot * slot_for(P.lmrt) + base + (use_scratch ? scratch : 0); };
     if (total() > lim) P.lmrt = 32;
@@ -1230,8 +1232,8 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     P.slot_bytes = slot_for(P.lmrt);
     int o = 0;
     P.sm_w = o; o += P.nslot * P.slot_bytes;
-    P.sm_rec0 = o; o += al(P.b.actb_d);
-    P.sm_rec1 = o; o += al(P.b.actb_f);
+    P.sm_rec0 = o; o += al(recd);
+    P.sm_rec1 = o; o += al(recf);
     P.sm_x = o; o += al(M5_D * 4);
     P.sm_x1 = o; o += al(M5_D * 4);
     P.sm_sc = o; o += al(1024 * 4);

@@ -49,7 +49,8 @@
 #define M5_E2 0
 #define M5_E3 (M5_E2 + M5_R * M5_D)
 #define M5_E4 (M5_E3 + M5_R * M5_D)
-#define M5_E5 (M5_E4 + M5_R * M5_NB_F * 10)
+#define M5_E4W (M5_FF / 2)     // words per replica of the E4 region: 128 blocks x 10 words (quantised) or 4096 fp16 values, two per word (F16)
+#define M5_E5 (M5_E4 + M5_R * M5_E4W)
 #define M5_LW (M5_E5 + M5_R * M5_D)
 #define M5_MAXL 24
 #define M5_PK 12              // trace stamps per (layer, stage)
@@ -372,6 +373,42 @@ __device__ __forceinline__ void m5_scatter_word(uint8_t * rec, int off_n, int of
     else               ((float *) (rec + off_s))[b] = __uint_as_float(v);
 }
 
+// ---- F16 weights (FMT == BG_F16) ----------------------------------------------------------------------------------------------
+// The reference converts the activation row to fp16 and keeps 32 running sums, sum l taking the elements with index % 32 == l in
+// order, fma(w, a, sum) in f32 (ggml_vec_dot_f16, ggml.c:2409-2443), then GGML_F32x8_REDUCE.  A weight row lies in HBM / the
+// shared-memory tile as [gg][lane][e] fp16 with element = gg * 256 + e * 32 + lane (bgpt_layout.h); the activation record is written
+// in the same order, so a lane's 8 weights and 8 activations of a group are one 16-byte load each.
+__device__ __forceinline__ int m5_h_pos(int c) { return (((c >> 8) * 32 + (c & 31)) << 3) + ((c >> 5) & 7); }
+// prep thread t < 128 owns elements 8t .. 8t + 7
+__device__ __forceinline__ void m5_record8_f16(const float (&y)[8], uint8_t * rec) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ((uint16_t *) rec)[m5_h_pos(8 * t + i)] = bg_f2h(y[i]);
+}
+// one weight row (NG groups of 256 elements) x the record, by a whole warp; the finished dot is in every lane
+template <int NG>
+__device__ __forceinline__ float m5_row_dot_f16(const uint8_t * wrow, const uint8_t * rec) {
+    const int lane = threadIdx.x & 31;
+    float c = 0.0f;
+#pragma unroll 4
+    for (int g = 0; g < NG; g++) {
+        const uint4 w = *(const uint4 *) (wrow + (size_t) (g * 32 + lane) * 16);
+        const uint4 a = *(const uint4 *) (rec + (size_t) (g * 32 + lane) * 16);
+        const uint32_t ww[4] = { w.x, w.y, w.z, w.w }, aa[4] = { a.x, a.y, a.z, a.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            c = fmaf(bg_h2f((uint16_t) (ww[i] & 0xFFFF)), bg_h2f((uint16_t) (aa[i] & 0xFFFF)), c);
+            c = fmaf(bg_h2f((uint16_t) (ww[i] >> 16)), bg_h2f((uint16_t) (aa[i] >> 16)), c);
+        }
+    }
+    c = __fadd_rn(c, __shfl_xor_sync(FULLMASK, c, 16));
+    c = __fadd_rn(c, __shfl_xor_sync(FULLMASK, c, 8));
+    c = __fadd_rn(c, __shfl_xor_sync(FULLMASK, c, 4));
+    c = __fadd_rn(c, __shfl_xor_sync(FULLMASK, c, 1));
+    c = __fadd_rn(c, __shfl_xor_sync(FULLMASK, c, 2));
+    return c;
+}
+
 #define M5PROF(ph, k) do { if (PROF && P.trace && threadIdx.x == 0) P.trace[(size_t) blockIdx.x * P.prof_n + (l * 5 + (ph)) * M5_PK + (k)] = clock64(); } while (0)
 
 template <int FMT, bool PROF>
@@ -387,6 +424,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     __shared__ __align__(16) float s_vn[M5_HR];                    // new v values of this CTA's 16 columns
     __shared__ float s_cv[M5_NW]; __shared__ int s_ci[M5_NW];
     __shared__ int s_tok;
+    constexpr bool ISF = (FMT == BG_F16);                          // F16 weights: fp16 records, one row per warp with lane = running sum
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
     const bool is_head = cta < M5_HC;                              // clusters 0..15: one attention head each
@@ -557,9 +595,19 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         // row per warp, finished in lane 24; the 8 results are gathered and published by warp 0.
         const bool relay = kind == 1 || kind == 3;
         const int myrow = 4 * warp + (lane >> 3);
-        const bool owner = !relay && (lane & 7) == 0 && myrow < rt;
+        const bool owner = !ISF && !relay && (lane & 7) == 0 && myrow < rt;
         // ---- whoever finishes a row fetches its bias before anything can stall
         float bias = 0.f;
+        float fbias[3] = { 0.f, 0.f, 0.f };                        // F16: lane 0 of warp w finishes local rows w, w + 16, w + 32
+        if (ISF && !relay && lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int rr = warp + M5_NW * j;
+                if (rr >= rt) break;
+                if (kind == 0) { const int mat = rr >> 4; fbias[j] = (mat == 0 ? L.q_b : mat == 1 ? L.k_b : L.v_b)[hrow0 + (rr & 15)]; }
+                else if (kind == 2) fbias[j] = L.fc1_b[rbase + rr];
+            }
+        }
         if (kind == 0) { if (owner) { const int mat = myrow >> 4; bias = (mat == 0 ? L.q_b : mat == 1 ? L.k_b : L.v_b)[hrow0 + (myrow & 15)]; } }
         else if (kind == 2) { if (owner) bias = L.fc1_b[rbase + myrow]; }
         else if (relay) { if (warp == 0 && lane < 8) bias = (kind == 1 ? L.o_b : L.fc2_b)[rbase + lane]; }
@@ -613,9 +661,35 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                     for (int i = 0; i < 8; i++) y[i] = v[i];
                 }
                 M5PROF(phs, 4);
-                m5_quant8<FMT>(y, rec, D.off_n, D.off_dd, D.off_s, p.code_off);
+                if (ISF) m5_record8_f16(y, rec);
+                else m5_quant8<FMT>(y, rec, D.off_n, D.off_dd, D.off_s, p.code_off);
                 M5PROF(phs, 5);
             }
+        } else if (kind == 3 && ISF) {
+            // 4096 fp16 GELU outputs, two per word: prep thread t polls the 16 words of elements 32 t .. 32 t + 31 and writes them into the
+            // K = 4096 record in lane order
+            if (tid < M5_PT) {
+                const unsigned long long * src = X + M5_E4 + (size_t) rep * M5_E4W + (size_t) tid * 16;
+                unsigned long long w[16];
+                unsigned spins = 0; long long t0 = 0;
+                for (;;) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[2 * i]), "=l"(w[2 * i + 1]) : "l"(src + 2 * i) : "memory");
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) ok = ok && (uint32_t) (w[i] >> 32) == tag;
+                    if (ok) break;
+                    if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, wcode | 1, t0)) break; }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t v = (uint32_t) w[j];
+                    ((uint16_t *) rec)[m5_h_pos(32 * tid + 2 * j)] = (uint16_t) (v & 0xFFFF);
+                    ((uint16_t *) rec)[m5_h_pos(32 * tid + 2 * j + 1)] = (uint16_t) (v >> 16);
+                }
+            }
+            M5PROF(phs, 3);
         } else if (kind == 3) {
             // 128 blocks x 10 words: prep thread t polls block t (5 loads in flight) and scatters it into the K = 4096 record
             if (tid < M5_PT) {
@@ -651,7 +725,35 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         // ---- dot products
         constexpr bool HASMF = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
         float dot = 0.f;
-        if (!relay) {
+        // finishes one row of the direct kinds (P1, P4, lm_head): called by the lane that holds the row's dot
+        auto finish_direct = [&](int row_l, float dotv, float b) {
+            if (kind == 0) {
+                const int mat = row_l >> 4, idx = row_l & 15;
+                float t = __fadd_rn(b, dotv);
+                if (mat == 0) { t = __fmul_rn(t, p.qscale); m5_bcast32(&s_q[rank * M5_HR + idx], __float_as_uint(t)); }
+                else if (mat == 1) { kc[(size_t) pos * M5_D + hrow0 + idx] = t; m5_bcast32(&s_kn[rank * M5_HR + idx], __float_as_uint(t)); }
+                else { vc[(size_t) pos * M5_D + hrow0 + idx] = t; s_vn[idx] = t; }
+            } else if (kind == 2) {
+                s_blk[row_l] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(b, dotv))]);
+            } else {
+                const int r_own = rbase + row_l;
+                p.logits[r_own] = dotv;
+                if (dotv > best || (dotv == best && r_own < bi)) { best = dotv; bi = r_own; }
+            }
+        };
+        if (ISF) {
+            if (!relay) {
+#pragma unroll 1
+                for (int j = 0; j < 3; j++) {
+                    const int rr = warp + M5_NW * j;
+                    if (rr >= rt) break;
+                    const float dv = m5_row_dot_f16<M5_D / 256>(wt + (size_t) rr * D.stride, rec);
+                    if (lane == 0) finish_direct(rr, dv, fbias[j]);
+                }
+            } else if (warp < 8) {
+                dot = Kff ? m5_row_dot_f16<M5_FF / 256>(wt + (size_t) warp * D.stride, rec) : m5_row_dot_f16<M5_D / 256>(wt + (size_t) warp * D.stride, rec);
+            }
+        } else if (!relay) {
             if (4 * warp < rt) dot = m5_row_dot<FMT, M5_D / 128>(wt + (size_t) min(myrow, rt - 1) * D.stride, rec, D);
         } else if (kind == 1) {
             if (warp < 8) dot = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) warp * D.stride, rec, D);
@@ -727,13 +829,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         if (!lm) M5PROF(phs, 10);
         // ---- epilogues
         if (kind == 0) {
-            if (owner) {
-                const int mat = myrow >> 4, idx = myrow & 15;
-                float t = __fadd_rn(bias, dot);
-                if (mat == 0) { t = __fmul_rn(t, p.qscale); m5_bcast32(&s_q[rank * M5_HR + idx], __float_as_uint(t)); }
-                else if (mat == 1) { kc[(size_t) pos * M5_D + hrow0 + idx] = t; m5_bcast32(&s_kn[rank * M5_HR + idx], __float_as_uint(t)); }
-                else { vc[(size_t) pos * M5_D + hrow0 + idx] = t; s_vn[idx] = t; }
-            }
+            if (owner) finish_direct(myrow, dot, bias);
         } else if (kind == 1 || kind == 3) {
             // gather the 8 rows; warp 0 finishes them (bias, residual) and writes 8 rows x 8 replicas as consecutive words
             const bool two_phase = kind == 3 && P.sm_p >= 0;
@@ -754,15 +850,21 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 m4_put(dst + (size_t) ((lane >> 3) + 4) * M5_D, __float_as_uint(mine), tag);
             }
         } else if (kind == 2) {
-            if (owner) s_blk[myrow] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dot))]);
+            if (owner) finish_direct(myrow, dot, bias);
             __syncthreads();
-            if (tid < 32) m4_quant_publish<FMT>(s_blk, X + M5_E4 + (size_t) cta * 10, M5_NB_F * 10, tag);
+            if (ISF) {
+                // the CTA's 32 GELU outputs (fp16 values) as 16 words, two per word, to the 8 replicas: 128 words by warp 0
+                if (tid < 32) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int ix = lane + 32 * i, r = ix >> 4, wd = ix & 15;
+                        const uint32_t pay = (uint32_t) bg_f2h(s_blk[2 * wd]) | ((uint32_t) bg_f2h(s_blk[2 * wd + 1]) << 16);
+                        m4_put(X + M5_E4 + (size_t) r * M5_E4W + (size_t) cta * 16 + wd, pay, tag);
+                    }
+                }
+            } else if (tid < 32) m4_quant_publish<FMT>(s_blk, X + M5_E4 + (size_t) cta * 10, M5_NB_F * 10, tag);
         } else {
-            if (owner) {
-                const int r_own = rbase + myrow;
-                p.logits[r_own] = dot;
-                if (dot > best || (dot == best && r_own < bi)) { best = dot; bi = r_own; }
-            }
+            if (owner) finish_direct(myrow, dot, bias);
         }
         if (!lm) M5PROF(phs, 2);
         // ================= attention: cluster `head`; this CTA scores T/4 positions and reduces V for its 16 columns =================

@@ -10,6 +10,7 @@ const void * bgpt_k_mega5_fn(int wtype, bool prof) {
         case BG_Q5_0: return prof ? (const void *) k_mega5<BG_Q5_0, true> : (const void *) k_mega5<BG_Q5_0, false>;
         case BG_Q5_1: return prof ? (const void *) k_mega5<BG_Q5_1, true> : (const void *) k_mega5<BG_Q5_1, false>;
         case BG_Q8_0: return prof ? (const void *) k_mega5<BG_Q8_0, true> : (const void *) k_mega5<BG_Q8_0, false>;
+        case BG_F16:  return prof ? (const void *) k_mega5<BG_F16, true>  : (const void *) k_mega5<BG_F16, false>;
     }
     return nullptr;
 }

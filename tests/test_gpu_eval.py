@@ -135,13 +135,14 @@ def test_persistent_kernel_equals_oracle_and_per_op_path(checkers, capi, zoo, si
     O.close(); M.close()
 
 
-@pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+@pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0", "f16"])
 def test_persistent_generations_equal_oracle_and_each_other(checkers, capi, zoo, ftype):
     """BioGPT-base layer shapes: single-token steps run on the generation-5 persistent kernel (clusters of 4 CTAs, one
     attention head per cluster, DSMEM exchange inside the head, chain-order dot products, TMA weight ring).  Bits must equal
     the oracle's, generation 4's (tagged-word exchange, no clusters) and generation 3's (grid barriers) at every position
     class: T = 1, the 32-wide boundary and both scalar tails, the second K pass (T > 512) and the end of the context; the
-    vocabulary (3001 rows) leaves ragged lm_head tiles."""
+    vocabulary (3001 rows) leaves ragged lm_head tiles.  F16 weights run the same kernel with fp16 records and one row per
+    warp (lane = running sum, ggml_vec_dot_f16's 32 lanes)."""
     hp = gf.NARROW
     p = zoo.path("narrow", ftype)
     O = checkers.Oracle(p)
@@ -163,7 +164,7 @@ def test_persistent_generations_equal_oracle_and_each_other(checkers, capi, zoo,
             assert np.array_equal(_bits(got), _bits(want)), _diff(f"{ftype} generation 5 at n_past={i}", got, want)
             got5[i] = got
         pos = hi
-    for path, gen in ((3, 4), (2, 3)):
+    for path, gen in ((3, 4 if ftype != "f16" else 3), (2, 3)):       # F16: generations 5 and 3 (generation 4 is quantised-only)
         M.set_decode_path(path)
         assert M.decode_generation == gen
         for lo, hi in windows:

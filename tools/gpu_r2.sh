@@ -119,6 +119,11 @@ e2e)
   timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 > $OUT/e2e.log 2>&1
   BGPT_TOPK_ZC=0 timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 >> $OUT/e2e.log 2>&1
   cat $OUT/e2e.log ;;
+f16g5)
+  timeout 1500 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=3 -x -k "persistent_generations and f16 or base_shape_matches_oracle and f16 or base_model_64 and f16" > $OUT/pytest_f16g5.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_f16g5.log
+  grep -E "passed|failed|FAILED|Error|differ|timed out|generation" $OUT/pytest_f16g5.log | tail -20
+  for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype f16 --n-past $np --steps 32 --warm 8 | head -1; done > $OUT/decode_f16.log 2>&1
+  cat $OUT/decode_f16.log ;;
 decode)
   for ft in ${FTYPES:-q4_0}; do for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
   cat $OUT/decode.log ;;
