@@ -368,7 +368,7 @@ static void init_kernel_attrs() {
 #define ATTR_F(F) allow_big_smem(k_gemv_f<F, 1>); allow_big_smem(k_gemv_f<F, 2>); allow_big_smem(k_gemv_f<F, 4>); allow_big_smem(k_gemv_f<F, 8>);
     ATTR_Q(BG_Q4_0) ATTR_Q(BG_Q4_1) ATTR_Q(BG_Q5_0) ATTR_Q(BG_Q5_1) ATTR_Q(BG_Q8_0) ATTR_F(BG_F16) ATTR_F(BG_F32)
     allow_big_smem(k_attn<16>); allow_big_smem(k_attn<32>); allow_big_smem(k_attn<64>); allow_big_smem(k_attn<128>);
-    allow_big_smem(k_act); allow_big_smem(k_attn_tile);
+    allow_big_smem(k_act); allow_big_smem(k_attn_tile); allow_big_smem(k_attn_tile2);
     cudaGetLastError();
 }
 
@@ -659,7 +659,8 @@ static int launch_attn(bgpt_model * m, cudaStream_t s, const AttnArgs & a, int n
     if (dk == 64 && a.mode == 0 && rows >= 4 && (a.d % 4) == 0 && (a.ld_out % 4) == 0) {      // prompt batch: tile of query rows per CTA
         const size_t smem_t = (size_t) AT_R * (((size_t) a.Tmax + 31) / 32 * 32 + 64) * 4;
         dim3 grid_t(n_head, (rows + AT_R - 1) / AT_R);
-        k_attn_tile<<<grid_t, 256, smem_t, s>>>(a);
+        static const bool v1 = getenv("BGPT_ATTN_TILE") && atoi(getenv("BGPT_ATTN_TILE")) == 1;      // 1: the butterfly form (k_attn_tile)
+        if (v1) k_attn_tile<<<grid_t, 256, smem_t, s>>>(a); else k_attn_tile2<<<grid_t, 256, smem_t, s>>>(a);
         if (m) m->launches++;
         CK(cudaGetLastError());
         return BGPT_OK;

@@ -838,6 +838,154 @@ static __global__ void __launch_bounds__(256) k_attn_tile(AttnArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_attn_tile2: the same un-masked attention tile with the reference's arithmetic mapped so that no score needs a shuffle.
+//   scores: THREAD = key.  The reference's dot of one (query, key) pair is 32 lanes of fma(k[32+i], q[32+i], fma(k[i], q[i], 0))
+//           reduced by the tree 16, 8, 4, 1, 2 (ggml_vec_dot_f32 + GGML_F32x8_REDUCE, ggml.c:2372-2407, 1981-1999).  k_attn_tile
+//           spreads the 32 lanes over a warp (32 keys in flight, a transposing butterfly: ~190 instructions per 32 scores); here
+//           one thread holds its key's 64 values in registers and evaluates the 32 lanes AND the tree itself, as packed f32x2
+//           operations (two IEEE operations per instruction, same bits): 16 + 16 FFMA2, 14 FADD2, 3 FADD = 49 instructions per
+//           score and thread, the query values broadcast from shared memory.
+//   V     : as k_attn_tile (warp = 4 output columns, lane = running sum t % 32) with FFMA2 for the (x, y) / (z, w) halves.
+// Same bits as k_attn_tile and k_attn (tests/test_gpu_ops.py::test_attention, the whole-eval tests).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t bg_pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void bg_unpack2(uint64_t v, float & a, float & b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t bg_fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t bg_add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+static __global__ void __launch_bounds__(256) k_attn_tile2(AttnArgs a) {
+    constexpr int DK = 64, NW = 8;
+    extern __shared__ __align__(16) float s_at[];
+    const int h = blockIdx.x, r0 = blockIdx.y * AT_R, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.st->n_past + a.n;                       // mode 0 only
+    const int Tpad = (T + 31) & ~31;
+    float * sq = s_at;                                      // [AT_R][64]
+    float * sc = s_at + AT_R * DK;                          // [AT_R][Tpad]
+    const float * Kb = a.kcache + (size_t) h * DK;
+    const float * Vb = a.vcache + (size_t) h * DK;
+    for (int i = tid; i < AT_R * DK; i += 256) {
+        int row = r0 + i / DK; row = row < a.n ? row : a.n - 1;
+        sq[i] = a.q[(size_t) row * a.ld_q + (size_t) h * DK + (i % DK)];
+    }
+    __syncthreads();
+    // ---- scores: thread = key
+    for (int t = tid; t < T; t += 256) {
+        uint64_t k0[16], k1[16];                            // pairs (k[2i], k[2i+1]) and (k[32+2i], k[32+2i+1])
+        const float4 * kp = (const float4 *) (Kb + (size_t) t * a.d);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 f = __ldcg(kp + j), g = __ldcg(kp + 8 + j);
+            k0[2 * j] = bg_pack2(f.x, f.y); k0[2 * j + 1] = bg_pack2(f.z, f.w);
+            k1[2 * j] = bg_pack2(g.x, g.y); k1[2 * j + 1] = bg_pack2(g.z, g.w);
+        }
+        const uint64_t zero2 = bg_pack2(0.0f, 0.0f);
+#pragma unroll 2
+        for (int r = 0; r < AT_R; r++) {
+            const float4 * qp = (const float4 *) (sq + r * DK);
+            uint64_t v[16];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 q0 = qp[j], q1 = qp[8 + j];      // broadcast: every thread of the CTA reads the same query
+                v[2 * j]     = bg_fma2(k1[2 * j],     bg_pack2(q1.x, q1.y), bg_fma2(k0[2 * j],     bg_pack2(q0.x, q0.y), zero2));
+                v[2 * j + 1] = bg_fma2(k1[2 * j + 1], bg_pack2(q1.z, q1.w), bg_fma2(k0[2 * j + 1], bg_pack2(q0.z, q0.w), zero2));
+            }
+            uint64_t a8[8], a4[4], a2[2];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a8[i] = bg_add2(v[i], v[i + 8]);          // lanes i, i + 16
+#pragma unroll
+            for (int i = 0; i < 4; i++) a4[i] = bg_add2(a8[i], a8[i + 4]);        // + 8
+#pragma unroll
+            for (int i = 0; i < 2; i++) a2[i] = bg_add2(a4[i], a4[i + 2]);        // + 4: (c0, c1), (c2, c3)
+            float c0, c1, c2, c3;
+            bg_unpack2(a2[0], c0, c1); bg_unpack2(a2[1], c2, c3);
+            sc[r * Tpad + t] = __fadd_rn(__fadd_rn(c0, c1), __fadd_rn(c2, c3));   // xor 1, then xor 2
+        }
+    }
+    __syncthreads();
+    // ---- softmax, one warp per query row
+    for (int r = warp; r < AT_R; r += NW) {
+        float * row = sc + r * Tpad;
+        float mx = -INFINITY;
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, row[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULLMASK, mx, o));
+        double sum = 0.0;
+        for (int t = lane; t < T; t += 32) {
+            const float v = bg_h2f(a.exp_tab[bg_f2h(__fsub_rn(row[t], mx))]);
+            row[t] = v; sum += (double) v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULLMASK, sum, o);
+        const float inv = (float) (1.0 / sum);
+        for (int t = lane; t < T; t += 32) row[t] = __fmul_rn(row[t], inv);
+    }
+    __syncthreads();
+    // ---- V: warp = 4 output columns, lane = running sum (t % 32), AT_R queries at once
+    const int np = T & ~31, nv = np + ((T - np) & ~3);
+    for (int cg = warp; cg < DK / 4; cg += NW) {
+        uint64_t axy[AT_R], azw[AT_R];
+#pragma unroll
+        for (int r = 0; r < AT_R; r++) { axy[r] = bg_pack2(0.f, 0.f); azw[r] = bg_pack2(0.f, 0.f); }
+        const float * vp = Vb + cg * 4;
+        for (int s0 = 0; s0 < np; s0 += 64) {
+            const int t0 = s0 + lane, t1 = s0 + 32 + lane;
+            const float4 v0 = __ldcg((const float4 *) (vp + (size_t) t0 * a.d));
+            float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool two = s0 + 32 < np;
+            if (two) v1 = __ldcg((const float4 *) (vp + (size_t) t1 * a.d));
+            const uint64_t v0xy = bg_pack2(v0.x, v0.y), v0zw = bg_pack2(v0.z, v0.w);
+#pragma unroll
+            for (int r = 0; r < AT_R; r++) {
+                const float p0 = sc[r * Tpad + t0];
+                const uint64_t pp = bg_pack2(p0, p0);
+                axy[r] = bg_fma2(v0xy, pp, axy[r]); azw[r] = bg_fma2(v0zw, pp, azw[r]);
+            }
+            if (two) {
+                const uint64_t v1xy = bg_pack2(v1.x, v1.y), v1zw = bg_pack2(v1.z, v1.w);
+#pragma unroll
+                for (int r = 0; r < AT_R; r++) {
+                    const float p1 = sc[r * Tpad + t1];
+                    const uint64_t pp = bg_pack2(p1, p1);
+                    axy[r] = bg_fma2(v1xy, pp, axy[r]); azw[r] = bg_fma2(v1zw, pp, azw[r]);
+                }
+            }
+        }
+        float4 acc[AT_R];
+#pragma unroll
+        for (int r = 0; r < AT_R; r++) { bg_unpack2(axy[r], acc[r].x, acc[r].y); bg_unpack2(azw[r], acc[r].z, acc[r].w); }
+#pragma unroll
+        for (int r = 0; r < AT_R; r++) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int o = k == 0 ? 16 : k == 1 ? 8 : k == 2 ? 4 : k == 3 ? 1 : 2;
+                acc[r].x = __fadd_rn(acc[r].x, __shfl_xor_sync(FULLMASK, acc[r].x, o));
+                acc[r].y = __fadd_rn(acc[r].y, __shfl_xor_sync(FULLMASK, acc[r].y, o));
+                acc[r].z = __fadd_rn(acc[r].z, __shfl_xor_sync(FULLMASK, acc[r].z, o));
+                acc[r].w = __fadd_rn(acc[r].w, __shfl_xor_sync(FULLMASK, acc[r].w, o));
+            }
+        }
+        for (int t = np; t < T; t++) {                       // scalar tail, identical on every lane
+            const float4 v = __ldcg((const float4 *) (vp + (size_t) t * a.d));
+            const bool fused = t >= nv;
+#pragma unroll
+            for (int r = 0; r < AT_R; r++) {
+                const float pw = sc[r * Tpad + t];
+                if (fused) {
+                    acc[r].x = fmaf(v.x, pw, acc[r].x); acc[r].y = fmaf(v.y, pw, acc[r].y);
+                    acc[r].z = fmaf(v.z, pw, acc[r].z); acc[r].w = fmaf(v.w, pw, acc[r].w);
+                } else {
+                    acc[r].x = __fadd_rn(acc[r].x, __fmul_rn(v.x, pw)); acc[r].y = __fadd_rn(acc[r].y, __fmul_rn(v.y, pw));
+                    acc[r].z = __fadd_rn(acc[r].z, __fmul_rn(v.z, pw)); acc[r].w = __fadd_rn(acc[r].w, __fmul_rn(v.w, pw));
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < AT_R; r++)
+            if (lane == r && r0 + r < a.n) *(float4 *) (a.out + (size_t) (r0 + r) * a.ld_out + (size_t) h * DK + cg * 4) = acc[r];
+    }
+}
+
 // fp16-table GELU as a stand-alone op (unit tests); the eval fuses it into the fc1 epilogue
 static __global__ void k_gelu(const float * __restrict__ x, float * __restrict__ y, int n, const uint16_t * __restrict__ tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -124,6 +124,12 @@ f16g5)
   grep -E "passed|failed|FAILED|Error|differ|timed out|generation" $OUT/pytest_f16g5.log | tail -20
   for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype f16 --n-past $np --steps 32 --warm 8 | head -1; done > $OUT/decode_f16.log 2>&1
   cat $OUT/decode_f16.log ;;
+attn2)
+  timeout 1500 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q --maxfail=6 -k "attention or large_prompt or small_matches or tiny_matches or f16_prompt" > $OUT/pytest_attn2.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_attn2.log
+  grep -E "passed|failed|FAILED|Error|differ" $OUT/pytest_attn2.log | tail -12
+  for v in 2 1; do echo "BGPT_ATTN_TILE=$v"; BGPT_ATTN_TILE=$v timeout 600 python tools/prompt_bench.py --ftype q8_0 --n 128,1024 2>&1 | tail -2
+    BGPT_ATTN_TILE=$v BGPT_F16_TC_MIN_ROWS=32 timeout 600 python tools/prompt_bench.py --ftype f16 --n 8,1024 2>&1 | tail -2; done > $OUT/prompt_attn2.log 2>&1
+  cat $OUT/prompt_attn2.log ;;
 decode)
   for ft in ${FTYPES:-q4_0}; do for np in 0 511 980; do timeout 300 python tools/profile_decode.py --ftype $ft --n-past $np --steps 32 --warm 8 | head -1; done; done > $OUT/decode.log 2>&1
   cat $OUT/decode.log ;;
