@@ -95,7 +95,7 @@ struct bgpt_model {
     // arena for `cap` token rows
     int cap = 0;
     int * d_tokens = nullptr; int * d_idlog = nullptr; int * h_idlog = nullptr; int idlog_cap = 0;
-    uint8_t * d_topk_cand = nullptr; uint8_t * h_topk_dev = nullptr; unsigned topk_seq = 0; bool last_ms_pending = false;
+    uint8_t * d_topk_cand = nullptr; uint8_t * d_topk_filt = nullptr; uint8_t * h_topk_dev = nullptr; unsigned topk_seq = 0; bool last_ms_pending = false;
     uint8_t * d_topk = nullptr; uint8_t * h_topk = nullptr;      // [TOPK_MAXK floats | TOPK_MAXK ints | 2 ints], device and pinned host   // h_idlog: pinned, idlog_cap ints
     float *x = nullptr, *x1 = nullptr, *q = nullptr, *att = nullptr, *hff = nullptr, *logits = nullptr;
     uint8_t *act_d = nullptr, *act_ff = nullptr;
@@ -256,7 +256,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     if (m->h_err5) cudaFreeHost(m->h_err5);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
-    cudaFree(m->d_topk); cudaFree(m->d_topk_cand); if (m->h_topk) cudaFreeHost(m->h_topk);
+    cudaFree(m->d_topk); cudaFree(m->d_topk_cand); cudaFree(m->d_topk_filt); if (m->h_topk) cudaFreeHost(m->h_topk);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -1492,8 +1492,19 @@ static int launch_topk3(cudaStream_t s, const float * logits, int n, int k, uint
     uint8_t * l2 = scratch + (size_t) n_slices * kc * 8;
     float * v2 = (float *) l2;                      int * i2 = (int *) (l2 + (size_t) n_groups * kc * 4);
     k_topk_part<<<n_slices, TOPK_SLICE, 0, s>>>(logits, n, kc, v1, i1);
-    k_topk_rank<false><<<n_groups, TOPK_RANK_NT, 0, s>>>(v1, i1, n_slices * kc, TOPK_FAN * kc, kc, v2, i2, k, nullptr, nullptr, 0u);
-    k_topk_rank<true><<<1, TOPK_RANK_NT, 0, s>>>(v2, i2, n_groups * kc, n_groups * kc, kc, dv, di, k, dinfo, errp, seq);
+    k_topk_rank<false><<<n_groups, TOPK_RANK_NT, 0, s>>>(v1, i1, n_slices * kc, TOPK_FAN * kc, kc, v2, i2, k, nullptr, nullptr, 0u, nullptr);
+    k_topk_rank<true><<<1, TOPK_RANK_NT, 0, s>>>(v2, i2, n_groups * kc, n_groups * kc, kc, dv, di, k, dinfo, errp, seq, nullptr);
+    CK(cudaGetLastError());
+    return BGPT_OK;
+}
+// after a persistent decode kernel: its per-CTA maxima give a threshold, two launches (bgpt_topk.cuh: k_topk_filter).  scratch:
+// [TOPK_RANK_MAX floats | TOPK_RANK_MAX ints | counter], the counter zeroed once by the caller and re-zeroed by every call.
+static size_t topk2_scratch_bytes() { return (size_t) TOPK_RANK_MAX * 8 + 16; }
+static int launch_topk2(cudaStream_t s, const float * logits, int n, int k, const float * slice_max, int n_max, uint8_t * scratch,
+                        float * dv, int * di, int * dinfo, const int * errp, unsigned seq) {
+    float * cv = (float *) scratch; int * ci = (int *) (scratch + (size_t) TOPK_RANK_MAX * 4); int * counter = (int *) (scratch + (size_t) TOPK_RANK_MAX * 8);
+    k_topk_filter<<<(n + TOPK_SLICE - 1) / TOPK_SLICE, TOPK_SLICE, 0, s>>>(logits, n, k, slice_max, n_max, cv, ci, counter, TOPK_RANK_MAX);
+    k_topk_rank<true><<<1, TOPK_RANK_NT, 0, s>>>(cv, ci, 0, 0, k + 1, dv, di, k, dinfo, errp, seq, counter);
     CK(cudaGetLastError());
     return BGPT_OK;
 }
@@ -1521,6 +1532,7 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         void * dp = nullptr;
         if (zc && cudaHostGetDevicePointer(&dp, m->h_topk, 0) == cudaSuccess && dp) m->h_topk_dev = (uint8_t *) dp; else cudaGetLastError();
         CK(cudaMalloc(&m->d_topk_cand, topk3_scratch_bytes(m->n_vocab)));
+        CK(cudaMalloc(&m->d_topk_filt, topk2_scratch_bytes())); CK(cudaMemset(m->d_topk_filt, 0, topk2_scratch_bytes()));
         cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);   // + 34 KB of static histograms
         cudaGetLastError();
     }
@@ -1535,13 +1547,22 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
         RET(forward(m, m->d_tokens, n, 0));
     }
+    static const bool tk_prof = getenv("BGPT_TOPK_PROF") != nullptr;      // debug: where the call's device time goes (stderr every 256 calls)
+    static cudaEvent_t ev_mid = nullptr;
+    if (tk_prof) { if (!ev_mid) cudaEventCreate(&ev_mid); cudaEventRecord(ev_mid, s); }
     // The packet goes straight into mapped pinned host memory when the device can address it (no copy, no stream synchronisation: the
     // host polls the sequence number); otherwise into device memory + one D2H copy.
     uint8_t * pk = m->h_topk_dev ? m->h_topk_dev : m->d_topk;
     int * dinfo = (int *) pk; float * dv = (float *) (pk + 16); int * di = (int *) (pk + 16 + (size_t) k * 4);
     const unsigned seq = ++m->topk_seq ? m->topk_seq : ++m->topk_seq;
     const int * errp = (mega && mega_generation(m) == 5 && m->mega5_ok) ? m->d_err5 : nullptr;
-    if (m->n_vocab >= 4096) {
+    const int n_max = mega ? (mega_generation(m) == 5 ? M5_NC : m->mega_grid) : 0;
+    static const bool use_filter = !(getenv("BGPT_TOPK_FILTER") && atoi(getenv("BGPT_TOPK_FILTER")) == 0);
+    if (use_filter && m->n_vocab >= 4096 && n_max > 0 && n_max <= TOPK_SLICE && k <= n_max) {
+        // the persistent kernel's per-CTA maxima bound the k-th largest logit from below: filter, then rank the few survivors
+        RET(launch_topk2(s, m->logits, m->n_vocab, k, m->d_cand_val, n_max, m->d_topk_filt, dv, di, dinfo, errp, seq));
+        m->launches += 2;
+    } else if (m->n_vocab >= 4096) {
         // every 256-logit slice ranks itself and keeps its k + 1 best; the single-CTA selection then runs over those candidates
         RET(launch_topk3(s, m->logits, m->n_vocab, k, m->d_topk_cand, dv, di, dinfo, errp, seq));
         m->launches += 3;
@@ -1576,6 +1597,14 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         cudaStreamSynchronize(s); cudaMemset(m->d_err5, 0, sizeof(int));
         return fail(BGPT_E_CUDA, "persistent decode kernel (generation 5): a wait timed out -- stage %d, layer %d, wait %d; results are invalid",
                     code >> 16, (code >> 8) & 0xff, code & 0xff);
+    }
+    if (tk_prof) {
+        static double t_fwd = 0, t_topk = 0; static int calls = 0;
+        float a = 0, b = 0;
+        cudaEventSynchronize(m->ev1);
+        cudaEventElapsedTime(&a, m->ev0, ev_mid); cudaEventElapsedTime(&b, ev_mid, m->ev1);
+        t_fwd += a; t_topk += b;
+        if (++calls % 256 == 0) { fprintf(stderr, "eval_topk: forward %.1f us, top-k %.1f us per call (CUDA events, last 256 calls)\n", t_fwd * 1e3 / 256, t_topk * 1e3 / 256); t_fwd = t_topk = 0; }
     }
     const int got_n = hinfo[0];
     *n_out = got_n; *exact = hinfo[1];

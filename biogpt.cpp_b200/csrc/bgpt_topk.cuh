@@ -30,6 +30,29 @@ __device__ __forceinline__ uint32_t topk_key(float f) {            // ascending 
 // TOPK_FAN slices' candidates per CTA the same way, k_topk_rank<true> ranks the remaining few hundred and writes the result packet.
 // The global K + 1 largest values all lie in the union of the slices' K + 1 largest at every level, so the selection, its order
 // and the tie flags are the ones of the single-kernel form.
+// rank of entry e (key u) among the n4 (multiple of 4) keys s_k[]: how many precede it in (key descending, position ascending)
+// order = #{ j < e : key_j >= u } + #{ j > e : key_j > u } -- one compare and one add per key, no tie-break inside the loops
+__device__ __forceinline__ int topk_rank_of(const uint32_t * s_k, int n4, int e, uint32_t u) {
+    int rank = 0;
+    const int e4 = e & ~3;
+#pragma unroll 4
+    for (int j = 0; j < e4; j += 4) {
+        const uint4 o = *(const uint4 *) (s_k + j);
+        rank += (o.x >= u) + (o.y >= u) + (o.z >= u) + (o.w >= u);
+    }
+    {
+        const uint4 o = *(const uint4 *) (s_k + e4);
+        const int k = e - e4;
+        rank += (k > 0 ? (o.x >= u) : 0) + (k > 1 ? (o.y >= u) : (k < 1 ? (o.y > u) : 0)) + (k > 2 ? (o.z >= u) : (k < 2 ? (o.z > u) : 0)) + (k < 3 ? (o.w > u) : 0);
+    }
+#pragma unroll 4
+    for (int j = e4 + 4; j < n4; j += 4) {
+        const uint4 o = *(const uint4 *) (s_k + j);
+        rank += (o.x > u) + (o.y > u) + (o.z > u) + (o.w > u);
+    }
+    return rank;
+}
+
 #define TOPK_SLICE 256
 // grid = ceil(n / TOPK_SLICE), block = TOPK_SLICE: thread i owns logit i of the slice; its rank = number of slice entries before it
 // in (value descending, index ascending) order; ranks below kc are written to cand_*[slice][rank] (pads: -inf, index -1)
@@ -41,16 +64,7 @@ static __global__ void __launch_bounds__(TOPK_SLICE) k_topk_part(const float * _
     const uint32_t u = i < n ? topk_key(f) : 0u;
     s_k[tid] = u;
     __syncthreads();
-    int rank = 0;
-#pragma unroll 8
-    for (int j4 = 0; j4 < TOPK_SLICE / 4; j4++) {
-        const uint4 o = ((const uint4 *) s_k)[j4];
-        const int j = j4 * 4;
-        rank += (o.x > u || (o.x == u && j + 0 < tid)) ? 1 : 0;
-        rank += (o.y > u || (o.y == u && j + 1 < tid)) ? 1 : 0;
-        rank += (o.z > u || (o.z == u && j + 2 < tid)) ? 1 : 0;
-        rank += (o.w > u || (o.w == u && j + 3 < tid)) ? 1 : 0;
-    }
+    const int rank = topk_rank_of(s_k, TOPK_SLICE, tid, u);
     if (rank < kc) {
         cand_val[(size_t) blockIdx.x * kc + rank] = f;
         cand_idx[(size_t) blockIdx.x * kc + rank] = i < n ? i : -1;
@@ -69,11 +83,16 @@ static __global__ void __launch_bounds__(TOPK_SLICE) k_topk_part(const float * _
 template <bool FINAL>
 static __global__ void __launch_bounds__(TOPK_RANK_NT) k_topk_rank(const float * __restrict__ val, const int * __restrict__ idx, int n_c, int per, int kc,
                                                                     float * __restrict__ out_val, int * __restrict__ out_idx,
-                                                                    int k, int * __restrict__ info, const int * __restrict__ err, unsigned seq) {
+                                                                    int k, int * __restrict__ info, const int * __restrict__ err, unsigned seq,
+                                                                    int * __restrict__ n_c_dev) {
     __shared__ __align__(16) uint32_t s_k[TOPK_RANK_MAX + 4];
     __shared__ uint32_t s_sorted[TOPK_MAXK + 2];
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * per;
+    // FINAL after k_topk_filter: the number of candidates is the filter's counter; more than fit = a plateau of equal logits:
+    // the packet says "not exact" and the caller takes the full-row path
+    bool overflow = false;
+    if (FINAL && n_c_dev) { n_c = *(volatile int *) n_c_dev; per = n_c; overflow = n_c > TOPK_RANK_MAX; }
     int cnt = n_c - b0; cnt = cnt < per ? cnt : per; cnt = cnt < TOPK_RANK_MAX ? cnt : TOPK_RANK_MAX;
     const int cnt4 = (cnt + 3) & ~3;
     for (int i = tid; i < cnt4; i += TOPK_RANK_NT) s_k[i] = i < cnt ? topk_key(val[b0 + i]) : 0u;
@@ -81,15 +100,7 @@ static __global__ void __launch_bounds__(TOPK_RANK_NT) k_topk_rank(const float *
     __syncthreads();
     for (int e = tid; e < cnt; e += TOPK_RANK_NT) {
         const uint32_t u = s_k[e];
-        int rank = 0;
-#pragma unroll 4
-        for (int j = 0; j < cnt4; j += 4) {
-            const uint4 o = *(const uint4 *) (s_k + j);
-            rank += (o.x > u || (o.x == u && j + 0 < e)) ? 1 : 0;
-            rank += (o.y > u || (o.y == u && j + 1 < e)) ? 1 : 0;
-            rank += (o.z > u || (o.z == u && j + 2 < e)) ? 1 : 0;
-            rank += (o.w > u || (o.w == u && j + 3 < e)) ? 1 : 0;
-        }
+        const int rank = topk_rank_of(s_k, cnt4, e, u);
         if (rank < kc) {
             if (FINAL) {
                 s_sorted[rank] = u;
@@ -111,9 +122,34 @@ static __global__ void __launch_bounds__(TOPK_RANK_NT) k_topk_rank(const float *
     for (int j = tid; j < k_eff && j + 1 < cnt; j += TOPK_RANK_NT) dup |= (s_sorted[j] == s_sorted[j + 1]) ? 1 : 0;
     dup = __syncthreads_or(dup);
     if (tid == 0) {
-        info[0] = k_eff; info[1] = dup ? 0 : 1; info[2] = err ? *(volatile const int *) err : 0;
+        if (n_c_dev) *n_c_dev = 0;                                   // ready for the next call's filter
+        info[0] = k_eff; info[1] = (dup || overflow) ? 0 : 1; info[2] = err ? *(volatile const int *) err : 0;
         __threadfence_system();
         *(volatile unsigned *) (info + 3) = seq;
+    }
+}
+
+// Single-token steps on a persistent decode kernel leave one maximum per CTA (the argmax candidates of its lm_head rows).  The k-th
+// largest of those n_max maxima, t0, is a lower bound of the k-th largest logit (k logits -- the maxima themselves -- are >= t0),
+// so the k + 1 largest logits that matter (the (k+1)-th only if it ties or beats t0) are all among { logit >= t0 }: typically a few
+// hundred entries.  grid = ceil(n / 256): every CTA derives t0 itself (rank-counting n_max <= 256 values), then appends its
+// logits >= t0 to the candidate list; k_topk_rank<true> ranks the list, writes the packet and resets the counter.
+static __global__ void __launch_bounds__(TOPK_SLICE) k_topk_filter(const float * __restrict__ logits, int n, int k,
+                                                                    const float * __restrict__ slice_max, int n_max,
+                                                                    float * __restrict__ out_val, int * __restrict__ out_idx,
+                                                                    int * __restrict__ counter, int cap) {
+    __shared__ __align__(16) uint32_t s_m[TOPK_SLICE];
+    __shared__ uint32_t s_t0;
+    const int tid = threadIdx.x, i = blockIdx.x * TOPK_SLICE + tid;
+    const float f = i < n ? logits[i] : 0.0f;
+    const uint32_t mk = tid < n_max ? topk_key(slice_max[tid]) : 0u;
+    s_m[tid] = mk;
+    __syncthreads();
+    if (tid < n_max && topk_rank_of(s_m, (n_max + 3) & ~3, tid, mk) == k - 1) s_t0 = mk;     // ranks are unique: exactly one writer
+    __syncthreads();
+    if (i < n && topk_key(f) >= s_t0) {
+        const int p = atomicAdd(counter, 1);
+        if (p < cap) { out_val[p] = f; out_idx[p] = i; }
     }
 }
 
