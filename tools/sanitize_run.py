@@ -17,7 +17,9 @@ import importlib  # noqa: E402
 capi = importlib.import_module("biogpt_cpp_b200.capi")
 quick = "--quick" in sys.argv
 tmp = tempfile.mkdtemp()
-jobs = [("narrow", gf.NARROW, "q4_0")] if quick else [("narrow", gf.NARROW, "q4_0"), ("narrow", gf.NARROW, "q5_1"), ("small", gf.SMALL, "f16"), ("tiny", gf.TINY, "q8_0")]
+WIDE = gf.HParams(**{**gf.NARROW.__dict__, "n_vocab": 4500})        # vocabulary >= 4096: the two- / three-launch device top-k
+jobs = [("narrow", gf.NARROW, "q4_0"), ("narrow", gf.NARROW, "f16")] if quick else [
+    ("narrow", gf.NARROW, "q4_0"), ("narrow", gf.NARROW, "q5_1"), ("narrow", gf.NARROW, "f16"), ("wide", WIDE, "q8_0"), ("small", gf.SMALL, "f16"), ("tiny", gf.TINY, "q8_0")]
 for name, hp, ft in jobs:
     path = os.path.join(tmp, f"{name}-{ft}.bin")
     gf.write_model(path, hp, gf.synth_tensors(hp, seed=1234), gf.FTYPE_BY_NAME[ft])
@@ -28,15 +30,22 @@ for name, hp, ft in jobs:
         for n in (8, 5, 16):
             M.eval(toks[pos:pos + n], pos); pos += n
         if hp.n_positions >= 256:
-            M.eval(toks[pos:pos + 128], pos); pos += 128       # bit-exact tcgen05 matmul (quantised) / per-operator (f16)
-    for path_id in ((1, 3, 2) if name == "narrow" else (1,)):
+            M.eval(toks[pos:pos + 128], pos); pos += 128       # warp-specialised bit-exact tcgen05 matmul (quantised) / per-operator (f16)
+            if ft == "f16" and name == "narrow":
+                M.set_f16_tc_min_rows(32)
+                M.eval(toks[pos:pos + 130], pos); pos += 130   # opt-in K-accumulating tcgen05 matmul, ragged token tile
+                M.set_f16_tc_min_rows(0)
+            elif name == "narrow":
+                M.set_tcw(0); M.eval(toks[pos:pos + 128], pos); pos += 128; M.set_tcw(1)     # the single-stage form
+    for path_id in ((1, 3, 2) if name in ("narrow", "wide") else (1,)):
         M.set_decode_path(path_id)
         for i in range(3):
             M.eval(toks[pos + i:pos + i + 1], pos + i)
     M.set_decode_path(1)
     M.decode_greedy(2, pos, 4)
     if not quick:
-        M.eval_topk(toks[pos:pos + 1], pos, 40)
+        M.eval_topk(toks[pos:pos + 1], pos, 40)                # after the persistent kernel: threshold filter + ranking CTA (vocabulary >= 4096)
+        M.eval_topk(toks[pos:pos + 4], pos, 40)                # after a prompt batch: slices -> groups -> one CTA
         M.set_streams(3)
         M.eval_streams(toks[:3], 0)
         M.decode_greedy_streams(toks[:3], 0, 3)
