@@ -1253,7 +1253,7 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
         int ncl = 0;
         if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl * M5_CL < M5_NC) { cudaGetLastError(); return BGPT_OK; }
     }
-    const size_t xb = (size_t) 2 * M5_LW * sizeof(unsigned long long);
+    const size_t xb = (size_t) M5_XCH_WORDS * sizeof(unsigned long long);
     CK(cudaMalloc(&m->d_xch5, xb)); CK(cudaMemset(m->d_xch5, 0, xb));
     {   // [0] time-out code, [2..3] watchdog limit in cycles (~0.15 s; BGPT_M5_WATCHDOG_MCYC = millions of cycles, for sanitizer runs)
         CK(cudaMalloc(&m->d_err5, 4 * sizeof(int)));

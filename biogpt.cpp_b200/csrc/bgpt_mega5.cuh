@@ -49,9 +49,13 @@
 #define M5_E2 0
 #define M5_E3 (M5_E2 + M5_R * M5_D)
 #define M5_E4 (M5_E3 + M5_R * M5_D)
-#define M5_E4W (M5_FF / 2)     // words per replica of the E4 region: 128 blocks x 10 words (quantised) or 4096 fp16 values, two per word (F16)
-#define M5_E5 (M5_E4 + M5_R * M5_E4W)
+#define M5_E5 (M5_E4 + M5_R * M5_NB_F * 10)
 #define M5_LW (M5_E5 + M5_R * M5_D)
+// F16 weights exchange the 4096 GELU outputs as fp16 values, two per word: 2048 words per replica, more than the 1280 of the
+// quantised form.  They live BEHIND the two parity buffers, so the quantised kernels' addresses are unchanged.
+#define M5_E4W (M5_FF / 2)
+#define M5_E4F(parity) (2 * M5_LW + (parity) * (M5_R * M5_E4W))
+#define M5_XCH_WORDS (2 * M5_LW + 2 * M5_R * M5_E4W)
 #define M5_MAXL 24
 #define M5_PK 12              // trace stamps per (layer, stage)
 
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             // 4096 fp16 GELU outputs, two per word: prep thread t polls the 16 words of elements 32 t .. 32 t + 31 and writes them into the
             // K = 4096 record in lane order
             if (tid < M5_PT) {
-                const unsigned long long * src = X + M5_E4 + (size_t) rep * M5_E4W + (size_t) tid * 16;
+                const unsigned long long * src = P.xch + M5_E4F(lx & 1) + (size_t) rep * M5_E4W + (size_t) tid * 16;
                 unsigned long long w[16];
                 unsigned spins = 0; long long t0 = 0;
                 for (;;) {
@@ -725,23 +729,23 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         // ---- dot products
         constexpr bool HASMF = (FMT == BG_Q4_1 || FMT == BG_Q5_1);
         float dot = 0.f;
-        // finishes one row of the direct kinds (P1, P4, lm_head): called by the lane that holds the row's dot
-        auto finish_direct = [&](int row_l, float dotv, float b) {
-            if (kind == 0) {
-                const int mat = row_l >> 4, idx = row_l & 15;
-                float t = __fadd_rn(b, dotv);
-                if (mat == 0) { t = __fmul_rn(t, p.qscale); m5_bcast32(&s_q[rank * M5_HR + idx], __float_as_uint(t)); }
-                else if (mat == 1) { kc[(size_t) pos * M5_D + hrow0 + idx] = t; m5_bcast32(&s_kn[rank * M5_HR + idx], __float_as_uint(t)); }
-                else { vc[(size_t) pos * M5_D + hrow0 + idx] = t; s_vn[idx] = t; }
-            } else if (kind == 2) {
-                s_blk[row_l] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(b, dotv))]);
-            } else {
-                const int r_own = rbase + row_l;
-                p.logits[r_own] = dotv;
-                if (dotv > best || (dotv == best && r_own < bi)) { best = dotv; bi = r_own; }
-            }
-        };
-        if (ISF) {
+        if constexpr (ISF) {                                      // (if constexpr: a by-reference lambda that merely EXISTS in the quantised instantiation cost it 1.4 %)
+            // F16: finishes one row of the direct kinds (P1, P4, lm_head); called by lane 0 of the warp that computed the row's dot
+            auto finish_direct = [&](int row_l, float dotv, float b) {
+                if (kind == 0) {
+                    const int mat = row_l >> 4, idx = row_l & 15;
+                    float t = __fadd_rn(b, dotv);
+                    if (mat == 0) { t = __fmul_rn(t, p.qscale); m5_bcast32(&s_q[rank * M5_HR + idx], __float_as_uint(t)); }
+                    else if (mat == 1) { kc[(size_t) pos * M5_D + hrow0 + idx] = t; m5_bcast32(&s_kn[rank * M5_HR + idx], __float_as_uint(t)); }
+                    else { vc[(size_t) pos * M5_D + hrow0 + idx] = t; s_vn[idx] = t; }
+                } else if (kind == 2) {
+                    s_blk[row_l] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(b, dotv))]);
+                } else {
+                    const int r_own = rbase + row_l;
+                    p.logits[r_own] = dotv;
+                    if (dotv > best || (dotv == best && r_own < bi)) { best = dotv; bi = r_own; }
+                }
+            };
             if (!relay) {
 #pragma unroll 1
                 for (int j = 0; j < 3; j++) {
@@ -829,7 +833,13 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         if (!lm) M5PROF(phs, 10);
         // ---- epilogues
         if (kind == 0) {
-            if (owner) finish_direct(myrow, dot, bias);
+            if (!ISF && owner) {
+                const int mat = myrow >> 4, idx = myrow & 15;
+                float t = __fadd_rn(bias, dot);
+                if (mat == 0) { t = __fmul_rn(t, p.qscale); m5_bcast32(&s_q[rank * M5_HR + idx], __float_as_uint(t)); }
+                else if (mat == 1) { kc[(size_t) pos * M5_D + hrow0 + idx] = t; m5_bcast32(&s_kn[rank * M5_HR + idx], __float_as_uint(t)); }
+                else { vc[(size_t) pos * M5_D + hrow0 + idx] = t; s_vn[idx] = t; }
+            }
         } else if (kind == 1 || kind == 3) {
             // gather the 8 rows; warp 0 finishes them (bias, residual) and writes 8 rows x 8 replicas as consecutive words
             const bool two_phase = kind == 3 && P.sm_p >= 0;
@@ -850,7 +860,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 m4_put(dst + (size_t) ((lane >> 3) + 4) * M5_D, __float_as_uint(mine), tag);
             }
         } else if (kind == 2) {
-            if (owner) finish_direct(myrow, dot, bias);
+            if (!ISF && owner) s_blk[myrow] = bg_h2f(p.gelu[bg_f2h(__fadd_rn(bias, dot))]);
             __syncthreads();
             if (ISF) {
                 // the CTA's 32 GELU outputs (fp16 values) as 16 words, two per word, to the 8 replicas: 128 words by warp 0
@@ -859,12 +869,16 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                     for (int i = 0; i < 4; i++) {
                         const int ix = lane + 32 * i, r = ix >> 4, wd = ix & 15;
                         const uint32_t pay = (uint32_t) bg_f2h(s_blk[2 * wd]) | ((uint32_t) bg_f2h(s_blk[2 * wd + 1]) << 16);
-                        m4_put(X + M5_E4 + (size_t) r * M5_E4W + (size_t) cta * 16 + wd, pay, tag);
+                        m4_put(P.xch + M5_E4F(lx & 1) + (size_t) r * M5_E4W + (size_t) cta * 16 + wd, pay, tag);
                     }
                 }
             } else if (tid < 32) m4_quant_publish<FMT>(s_blk, X + M5_E4 + (size_t) cta * 10, M5_NB_F * 10, tag);
         } else {
-            if (owner) finish_direct(myrow, dot, bias);
+            if (!ISF && owner) {
+                const int r_own = rbase + myrow;
+                p.logits[r_own] = dot;
+                if (dot > best || (dot == best && r_own < bi)) { best = dot; bi = r_own; }
+            }
         }
         if (!lm) M5PROF(phs, 2);
         // ================= attention: cluster `head`; this CTA scores T/4 positions and reduces V for its 16 columns =================
