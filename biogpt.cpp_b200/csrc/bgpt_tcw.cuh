@@ -120,6 +120,7 @@ struct TwxArgs {
     const float * sw; const float * mw;     // weight scales / minima as f32 [K / 64][M][2]
     const float * sa; const float * ss;     // activation scales d / s as f32 [K / 64][n_pad][2]
     int M, n, n_pad, tok0, nkb, n_row_tiles, n_tok_tiles;
+    int dbg;                       // timing experiments only (BGPT_TCW_DBG; results are wrong): 1 = read half of the TMEM columns, 2 = no activation-operand loads
     Epi epi;
 };
 
@@ -170,9 +171,9 @@ __global__ void __launch_bounds__(64 + 32 * 4 * (TWX_TOK / TPT), 1) k_tcw_exact(
                     const int s = (int) (it % TWX_STAGES); const uint32_t ph = (it / TWX_STAGES) & 1u;
                     tw_wait(empty(s), ph ^ 1u);
                     const uint32_t st = sbase + (uint32_t) s * TWX_STAGE_BYTES;
-                    tw_mbar_expect_tx(full(s), TX);
+                    tw_mbar_expect_tx(full(s), (P.dbg & 2) ? TX - 8192u : TX);
                     tw_tma_2d(st, &P.tmA, kb * TW_BK, rt * TW_ROWS, full(s));
-                    tw_tma_2d(st + TWX_OFF_B, &P.tmB, kb * TW_BK, tt * TWX_BROWS, full(s));
+                    if (!(P.dbg & 2)) tw_tma_2d(st + TWX_OFF_B, &P.tmB, kb * TW_BK, tt * TWX_BROWS, full(s));
                     tw_bulk(st + TWX_OFF_DW, P.sw + ((size_t) kb * P.M + (size_t) rt * TW_ROWS) * 2, 1024u, full(s));
                     tw_bulk(st + TWX_OFF_DA, P.sa + ((size_t) kb * P.n_pad + (size_t) tt * TWX_TOK) * 2, 128u, full(s));
                     if (HASM) {
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(64 + 32 * 4 * (TWX_TOK / TPT), 1) k_tcw_exact(
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     tc_ld_wait();
-                    if (q < 3) tw_ld<NC>(tb + (uint32_t) ((q + 1) * 64), v[(q + 1) & 1]);
+                    if (q < 3) { if (!(P.dbg & 1) || q == 2) tw_ld<NC>(tb + (uint32_t) ((q + 1) * 64), v[(q + 1) & 1]); }
                     else {
                         // all four accumulators of the stage are in registers: hand the TMEM stage back before doing the last chains
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -114,6 +114,7 @@ cudaError_t bgpt_tcw_gemm_exact(int wtype, cudaStream_t s, const void * a16, con
     P.sw = sw; P.mw = mw; P.sa = sa; P.ss = ss;
     P.M = M; P.n = n; P.n_pad = n_pad; P.tok0 = tok0; P.nkb = K / TW_BK;
     P.n_row_tiles = M / TW_ROWS; P.n_tok_tiles = n_pad / TWX_TOK; P.epi = epi;
+    { static const int dbg = getenv("BGPT_TCW_DBG") ? atoi(getenv("BGPT_TCW_DBG")) : 0; P.dbg = dbg; }
     const int tiles = P.n_row_tiles * P.n_tok_tiles;
     void * args[] = { &P };
     return cudaLaunchKernel(fn, dim3((unsigned) (tiles < n_sm ? tiles : n_sm)), dim3(64 + 32 * 4 * (TWX_TOK / tpt)), args, TWX_SMEM, s);
