@@ -586,15 +586,17 @@ def main():
     if not args.no_e2e:
         TOPK = 40                                    # the reference's default top_k (biogpt.h:113)
 
+        import ctypes as C
+        H = C.CDLL(os.path.join(ROOT, "biogpt.cpp_b200", "host", "libbiogpt_b200.so"))
+        H.bgpt_host_sampling_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        e2e_buf = np.zeros(seq, np.int32)
+
         def e2e_pass():
-            tok = np.array([first_token], dtype=np.int32)
-            out = []
-            for p in range(seq):
-                vals, tids, exact, full = M.eval_topk(tok, p, TOPK)      # id H2D, 40 (logit, id) pairs D2H, inside the call
-                nxt = int(tids[0]) if exact else int(np.argmax(full))     # greedy = top_k 1: the best candidate (ties: the full row decides)
-                out.append(nxt)
-                tok[0] = nxt
-            return out
+            # the token loop of examples/main/main.cpp:93-151 in C++ (host/host_capi.cpp: bgpt_host_sampling_loop): per token ONE
+            # bgpt_cuda_eval_topk call with host buffers -- token id in, 40 (logit, id) pairs out -- and the host picks the next token
+            rc = H.bgpt_host_sampling_loop(M.h, first_token, 0, seq, TOPK, e2e_buf.ctypes.data, None)
+            assert rc == 0, f"bgpt_host_sampling_loop: {rc}"
+            return e2e_buf.tolist()
         e2e_pass()
         barrier()
         t0 = time.perf_counter()
@@ -610,7 +612,7 @@ def main():
         assert ids is None or e2e_ids == ids.tolist(), "device-side greedy ids differ from the host-sampled ids"
         e2e = {"value": world * seq * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": seq * 4, "d2h_bytes_per_step": seq * (8 * TOPK + 8),
-               "call": "bgpt_cuda_eval_topk (C ABI; what biogpt_eval_sample calls): host token in, top-40 (logit, id) pairs out"}
+               "call": "bgpt_cuda_eval_topk (C ABI; what biogpt_eval_sample calls) once per token from a C++ loop (host_capi: bgpt_host_sampling_loop): host token in, top-40 (logit, id) pairs out, next token picked on the host"}
 
     if rank != 0:
         M.close()

@@ -29,7 +29,7 @@ SYMBOLS = [
     "bgpt_cuda_last_error", "bgpt_cuda_device_count", "bgpt_cuda_version",
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
-    "bgpt_cuda_eval", "bgpt_cuda_eval_topk", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
+    "bgpt_cuda_eval", "bgpt_cuda_eval_topk", "bgpt_cuda_set_chain", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
     "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_read_rows_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_set_tcw", "bgpt_cuda_set_f16_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
@@ -75,6 +75,7 @@ def lib():
     L.bgpt_cuda_synchronize.argtypes = [C.c_void_p]
     L.bgpt_cuda_decode_greedy.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_int, _i32p,
                                           C.POINTER(C.c_float)]
+    L.bgpt_cuda_set_chain.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_decode_path.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_get_decode_path.argtypes = [C.c_void_p]
     L.bgpt_cuda_decode_kernel_generation.argtypes = [C.c_void_p]
@@ -234,6 +235,10 @@ class Model:
         _check(lib().bgpt_cuda_eval_streams(self.h, t, len(t), n_past,
                                             out.ctypes.data if fetch else None), "eval_streams")
         return out
+
+    def set_chain(self, on: int):
+        """chained launches of eval_topk (the next position's kernel is queued while this call waits): 1 / 0, -1 = BGPT_CHAIN default (on)"""
+        _check(lib().bgpt_cuda_set_chain(self.h, on), "set_chain")
 
     def set_decode_path(self, path: int):
         """1: persistent kernel per token, newest generation (default); 3: generation 4; 2: generation 3; 0: one kernel per fused operator"""

@@ -138,6 +138,12 @@ struct bgpt_model {
     long long * d_trace = nullptr; size_t trace_n = 0;
     // generation-5 persistent kernel (bgpt_mega5.cuh): clusters of 4, one attention head per cluster, DSMEM exchange inside the head
     bool mega5_ok = false; M5Params m5{}; unsigned long long * d_xch5 = nullptr; unsigned int m5_tag = 0;
+    unsigned * d_tk_ticket = nullptr;                             // generation 5: ticket counter of the sampler tail
+    // chained launches of bgpt_cuda_eval_topk (generation 5): the kernel of position p + 1 is queued while the call for p is still
+    // waiting for its packet; its token arrives through `h_feed` (mapped pinned memory) when the next call names it
+    struct Chain { bool active = false; int n_past = 0, k = 0; unsigned seq = 0, feed_seq = 0; } chain;
+    unsigned long long * h_feed = nullptr; unsigned long long * h_feed_dev = nullptr; unsigned feed_seq = 0;
+    int chain_mode = -1;                                          // -1: BGPT_CHAIN (default on), 0 off, 1 on
     int * d_err5 = nullptr; int * h_err5 = nullptr; long long * d_trace5 = nullptr; size_t trace5_n = 0;
     // persistent multi-row kernel (bgpt_rows.cuh): 2..8 token rows per eval in one launch
     bool rows_ok = false; RowsParams rw{}; unsigned int * d_cnt_rows = nullptr; int * d_err_rows = nullptr; long long * d_trace_rows = nullptr;
@@ -242,21 +248,35 @@ extern "C" bgpt_model * bgpt_cuda_model_create(const int32_t hp[7], int device, 
     return m;
 }
 
+// the token word the queued kernel polls: {token, serial}, one aligned 8-byte store
+static void chain_feed(bgpt_model * m, int tok, unsigned serial) {
+    __atomic_store_n(m->h_feed, ((unsigned long long) serial << 32) | (unsigned long long) (uint32_t) tok, __ATOMIC_RELEASE);
+}
+// withdraw the queued kernel (it exits without touching the KV cache or the logits); every entry point that uses the model's stream or
+// its buffers calls this first, so the stream never waits for a token that is not coming
+static void chain_cancel(bgpt_model * m) {
+    if (!m || !m->chain.active) return;
+    chain_feed(m, -2 /* M5_TOK_CANCEL */, m->chain.feed_seq);
+    m->chain.active = false;
+}
+
 extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    chain_cancel(m);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (auto & kv : m->tensors) cudaFree(kv.second.ptr);
     for (auto & kv : m->tcw_w) { cudaFree(kv.second.a16); cudaFree(kv.second.sw); cudaFree(kv.second.mw); }
     free_arena(m);
     cudaFree(m->kcache); cudaFree(m->vcache); cudaFree(m->gelu_tab); cudaFree(m->exp_tab); cudaFree(m->st); cudaFree(m->d_idlog);
     cudaFree(m->d_prof); cudaFree(m->d_rec_att); cudaFree(m->d_rec_hff); cudaFree(m->d_mega_layers); cudaFree(m->d_bar); cudaFree(m->d_cand_val); cudaFree(m->d_cand_idx); cudaFree(m->d_xch); cudaFree(m->d_trace);
-    cudaFree(m->d_xch5); cudaFree(m->d_err5); cudaFree(m->d_trace5);
+    cudaFree(m->d_xch5); cudaFree(m->d_err5); cudaFree(m->d_tk_ticket); cudaFree(m->d_trace5);
     cudaFree(m->d_cnt_rows); cudaFree(m->d_err_rows); cudaFree(m->d_trace_rows);
     if (m->h_err5) cudaFreeHost(m->h_err5);
     if (m->h_st) cudaFreeHost(m->h_st);
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
     cudaFree(m->d_topk); cudaFree(m->d_topk_cand); cudaFree(m->d_topk_filt); if (m->h_topk) cudaFreeHost(m->h_topk);
+    if (m->h_feed) cudaFreeHost(m->h_feed);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -270,6 +290,7 @@ extern "C" size_t bgpt_cuda_weight_bytes(const bgpt_model * m) { return m->weigh
 extern "C" uint64_t bgpt_cuda_launch_count(const bgpt_model * m) { return m->launches; }
 extern "C" float bgpt_cuda_last_eval_ms(const bgpt_model * cm) {
     bgpt_model * m = const_cast<bgpt_model *>(cm);
+    chain_cancel(m);
     if (m->last_ms_pending) {                            // eval_topk returns on the result packet, before the closing event has completed
         m->last_ms_pending = false;
         if (cudaSetDevice(m->device) != cudaSuccess || cudaEventSynchronize(m->ev1) != cudaSuccess || cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) { cudaGetLastError(); m->last_ms = 0.f; }
@@ -973,6 +994,7 @@ static int forward(bgpt_model * m, const int * d_tokens, int n, int mode) {
 }
 
 extern "C" int bgpt_cuda_set_batch_path(bgpt_model * m, int path) {
+    chain_cancel(m);
     if (!m || path < 0 || path > 2) return fail(BGPT_E_ARG, "set_batch_path: path must be 0 (per-operator), 1 (skinny-batch schedule) or 2 (persistent multi-row kernel up to 8 rows, skinny beyond)");
     CK(cudaSetDevice(m->device));
     CK(cudaStreamSynchronize(m->stream));
@@ -981,6 +1003,7 @@ extern "C" int bgpt_cuda_set_batch_path(bgpt_model * m, int path) {
     return BGPT_OK;
 }
 extern "C" long long bgpt_cuda_debug_read_buffer(bgpt_model * m, int which, int rows, void * out, long long cap) {
+    chain_cancel(m);
     if (!m || !out || rows < 1 || rows > m->cap) { fail(BGPT_E_ARG, "debug_read_buffer: bad arguments"); return -1; }
     const void * src = nullptr; size_t bytes = 0;
     switch (which) {
@@ -1253,7 +1276,7 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
         int ncl = 0;
         if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl * M5_CL < M5_NC) { cudaGetLastError(); return BGPT_OK; }
     }
-    const size_t xb = (size_t) M5_XCH_WORDS * sizeof(unsigned long long);
+    const size_t xb = (size_t) M5_XCH_TOTAL * sizeof(unsigned long long);
     CK(cudaMalloc(&m->d_xch5, xb)); CK(cudaMemset(m->d_xch5, 0, xb));
     {   // [0] time-out code, [2..3] watchdog limit in cycles (~0.15 s; BGPT_M5_WATCHDOG_MCYC = millions of cycles, for sanitizer runs)
         CK(cudaMalloc(&m->d_err5, 4 * sizeof(int)));
@@ -1264,6 +1287,7 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
         CK(cudaMemcpy(m->d_err5, init, sizeof init, cudaMemcpyHostToDevice));
     }
     CK(cudaMallocHost(&m->h_err5, sizeof(int))); *m->h_err5 = 0;
+    CK(cudaMalloc(&m->d_tk_ticket, 16)); CK(cudaMemset(m->d_tk_ticket, 0, 16));
     P.xch = m->d_xch5; P.err = m->d_err5;
     P.trace = nullptr; P.prof_n = (m->n_layer + 1) * 5 * M5_PK;
     if (prof) {
@@ -1329,6 +1353,7 @@ static int rows_setup(bgpt_model * m, const cudaDeviceProp & prop) {
 }
 // debug: clock64 stamps of CTA 0 in the last multi-row launch (BGPT_MEGA_PROF=1): [n_layer + 1][RW_NST]
 extern "C" int bgpt_cuda_debug_read_rows_trace(bgpt_model * m, long long * out, int cap) {
+    chain_cancel(m);
     if (!m || !out || !m->d_trace_rows) return 0;
     const int n = (m->n_layer + 1) * RW_NST;
     if (cap < n) return 0;
@@ -1350,10 +1375,22 @@ static int check_mega5_error(bgpt_model * m) {
 
 // one token at n_past on the persistent kernel.  token source: d_tok (device) or the previous
 // launch's argmax candidates (use_cand).  Asynchronous on the model's stream.
-static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot, int tok_imm = 0) {
+// generation 5: the sampler tail (bgpt_mega5.cuh); use_cand == 3: + the serial under which the token will arrive in the token word
+struct MegaTopk { int k; unsigned seq; uint8_t * pk; int stride; unsigned feed_seq; };
+static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot, int tok_imm = 0, const MegaTopk * tk = nullptr) {
     const int gen = mega_generation(m);
+    if (tk && gen != 5) return fail(BGPT_E_STATE, "launch_mega: the sampler tail needs the generation-5 kernel");
     if (gen == 5) {
         M5Params P = m->m5;
+        P.tk_k = 0; P.feed = nullptr; P.feed_seq = 0; P.feed_limit = 0;
+        if (tk) {
+            P.tk_k = tk->k; P.tk_seq = tk->seq; P.tk_pk = tk->pk; P.tk_stride = tk->stride; P.tk_ticket = m->d_tk_ticket;
+            if (use_cand == 3) {
+                if (!m->h_feed_dev) return fail(BGPT_E_STATE, "launch_mega: a chained launch needs the token word");
+                static const long long feed_limit = getenv("BGPT_CHAIN_WAIT_US") ? std::max(1LL, atoll(getenv("BGPT_CHAIN_WAIT_US"))) * 2000LL : 4000000LL;   // ~2 ms
+                P.feed = m->h_feed_dev; P.feed_seq = tk->feed_seq; P.feed_limit = feed_limit;
+            }
+        } else if (use_cand == 3) return fail(BGPT_E_STATE, "launch_mega: a fed token needs the sampler tail");
         MegaParams & q = P.b;
         q.kcache = m->kcache; q.vcache = m->vcache; q.logits = m->logits;
         q.x = m->x; q.x1 = m->x1; q.q = m->q; q.att = m->att; q.hff = m->hff;
@@ -1394,6 +1431,7 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
 static bool use_mega(const bgpt_model * m) { return m->mega_ok && m->decode_path >= 1 && !m->taps_armed; }
 
 extern "C" int bgpt_cuda_set_decode_path(bgpt_model * m, int path) {
+    chain_cancel(m);
     if (!m || path < 0 || path > 3) return fail(BGPT_E_ARG, "set_decode_path: path must be 0 (per-op kernels), 1 (persistent kernel, newest generation), 2 (generation 3: grid barriers) or 3 (generation 4)");
     if (path >= 1 && !m->mega_ok) return fail(BGPT_E_UNSUPPORTED, "set_decode_path: the persistent kernel is not available for this model/device");
     m->decode_path = path;
@@ -1402,6 +1440,7 @@ extern "C" int bgpt_cuda_set_decode_path(bgpt_model * m, int path) {
 // debug: clock64 stamps of CTA 0 in the last persistent-kernel launch (BGPT_MEGA_PROF=1),
 // [n_layer+1][5 phases][start, matmul start, matmul end]
 extern "C" int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int cap) {
+    chain_cancel(m);
     if (!m || !m->d_prof) return 0;
     const int n = cap < m->prof_n ? cap : m->prof_n;
     cudaStreamSynchronize(m->stream);
@@ -1413,6 +1452,7 @@ extern "C" int bgpt_cuda_debug_read_prof(bgpt_model * m, long long * out, int ca
 // debug: generation-4 kernel, stamps of EVERY CTA: [n_cta][prof_n] then [n_cta][4] = {globaltimer ns, clock64} at the
 // start and at the end of the launch (clock64 is per SM; the pairs put all CTAs on one time axis)
 extern "C" int bgpt_cuda_debug_read_trace(bgpt_model * m, long long * out, int cap, int * n_cta, int * per_cta) {
+    chain_cancel(m);
     if (!m || !out) return 0;
     const bool g5 = mega_generation(m) == 5;
     const long long * src = g5 ? m->d_trace5 : m->d_trace;
@@ -1431,6 +1471,7 @@ extern "C" int bgpt_cuda_decode_kernel_generation(const bgpt_model * m) {
 
 static int check_eval_args(bgpt_model * m, int n, int n_past, int rows_of_stream) {
     if (!m) return fail(BGPT_E_ARG, "eval: NULL model");
+    chain_cancel(m);
     if (!m->finalized) return fail(BGPT_E_STATE, "eval before bgpt_cuda_model_finalize");
     if (n < 1 || n_past < 0 || n_past + rows_of_stream > m->n_positions)
         return fail(BGPT_E_ARG, "eval: n=%d n_past=%d exceeds n_positions=%d", n, n_past, m->n_positions);
@@ -1446,6 +1487,7 @@ static int fetch_taps(bgpt_model * m, int n) {
 }
 
 extern "C" int bgpt_cuda_set_taps(bgpt_model * m, float * const taps5[5]) {
+    chain_cancel(m);
     if (!m) return fail(BGPT_E_ARG, "set_taps: NULL model");
     m->taps_armed = false;
     if (taps5) for (int i = 0; i < 5; i++) { m->taps[i] = taps5[i]; if (taps5[i]) m->taps_armed = true; }
@@ -1513,92 +1555,150 @@ static int launch_topk2(cudaStream_t s, const float * logits, int n, int k, cons
 // logit descending) and *exact out.  *exact = 0 means equal values make std::partial_sort's choice / order ambiguous: then (and
 // only then) the full logit row is copied to logits_fallback (n_vocab floats, may be NULL) so the caller can run the reference's
 // sampler on it.  8 K + 8 bytes cross PCIe per token instead of 4 n_vocab.
+extern "C" int bgpt_cuda_set_chain(bgpt_model * m, int on) {
+    if (!m) return fail(BGPT_E_ARG, "set_chain: NULL model");
+    chain_cancel(m);
+    m->chain_mode = on < 0 ? -1 : (on ? 1 : 0);
+    return BGPT_OK;
+}
+static bool chain_enabled(const bgpt_model * m) {
+    static const bool env_on = !(getenv("BGPT_CHAIN") && atoi(getenv("BGPT_CHAIN")) == 0);
+    return m->chain_mode < 0 ? env_on : m->chain_mode != 0;
+}
+
+// Waits for the result packet `seq` in the mapped buffer `hinfo` (the kernel writes the serial last, behind a system-scope fence).
+static int wait_packet(bgpt_model * m, const volatile int * hinfo, unsigned seq) {
+    cudaStream_t s = m->stream;
+    for (unsigned spins = 0; ; ) {
+        if ((unsigned) hinfo[3] == seq) break;
+        if ((++spins & 0x3FFu) == 0) {
+            const cudaError_t q = cudaStreamQuery(s);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) return fail(BGPT_E_CUDA, "eval_topk: %s", cudaGetErrorString(q));
+            if ((unsigned) hinfo[3] != seq) return fail(BGPT_E_CUDA, "eval_topk: the result packet never arrived");
+            break;
+        }
+    }
+    __sync_synchronize();
+    return BGPT_OK;
+}
+
 extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
                                    float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback) {
+    if (!m) return fail(BGPT_E_ARG, "eval: NULL model");
+    // a kernel queued by the previous call (chained launch) serves this call if it was queued for exactly this position and k
+    const bool chained = m->chain.active && n == 1 && tokens && vals && ids && n_out && exact && n_past == m->chain.n_past && k == m->chain.k;
+    bgpt_model::Chain served = m->chain;
+    if (chained) m->chain.active = false;                // check_eval_args would withdraw it
     RET(check_eval_args(m, n, n_past, n));
     if (!tokens || !vals || !ids || !n_out || !exact || k < 1) return fail(BGPT_E_ARG, "eval_topk: bad arguments");
     if (k > TOPK_MAXK) return fail(BGPT_E_ARG, "eval_topk: k=%d exceeds %d; use bgpt_cuda_eval and sample on the host", k, TOPK_MAXK);
     CK(cudaSetDevice(m->device));
     RET(ensure_arena(m, n));
-    // packet: [info: entries, exact, forward-pass error code, sequence number][vals: k floats][ids: k ints]
+    // packet: [info: entries, exact, forward-pass error code, sequence number][vals: k floats][ids: k ints]; two of them, by serial parity
     const size_t tk_bytes = (size_t) TOPK_MAXK * 8 + 16;
-    const int kc = k + 1;
-    const int n_slices = (m->n_vocab + TOPK_SLICE - 1) / TOPK_SLICE;
     if (!m->d_topk) {
         static const bool zc = !(getenv("BGPT_TOPK_ZC") && atoi(getenv("BGPT_TOPK_ZC")) == 0);
-        CK(cudaMalloc(&m->d_topk, tk_bytes));
-        CK(cudaHostAlloc(&m->h_topk, tk_bytes, cudaHostAllocMapped));
-        memset(m->h_topk, 0, tk_bytes);
+        CK(cudaMalloc(&m->d_topk, 2 * tk_bytes));
+        CK(cudaHostAlloc(&m->h_topk, 2 * tk_bytes, cudaHostAllocMapped));
+        memset(m->h_topk, 0, 2 * tk_bytes);
         void * dp = nullptr;
         if (zc && cudaHostGetDevicePointer(&dp, m->h_topk, 0) == cudaSuccess && dp) m->h_topk_dev = (uint8_t *) dp; else cudaGetLastError();
+        CK(cudaHostAlloc(&m->h_feed, 64, cudaHostAllocMapped));
+        memset(m->h_feed, 0, 64);
+        dp = nullptr;
+        if (zc && cudaHostGetDevicePointer(&dp, m->h_feed, 0) == cudaSuccess && dp) m->h_feed_dev = (unsigned long long *) dp; else cudaGetLastError();
         CK(cudaMalloc(&m->d_topk_cand, topk3_scratch_bytes(m->n_vocab)));
         CK(cudaMalloc(&m->d_topk_filt, topk2_scratch_bytes())); CK(cudaMemset(m->d_topk_filt, 0, topk2_scratch_bytes()));
         cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);   // + 34 KB of static histograms
         cudaGetLastError();
     }
     cudaStream_t s = m->stream;
-    memcpy(m->h_tokens, tokens, (size_t) n * sizeof(int));
-    m->h_st->n_past = n_past; m->h_st->step = 0; m->h_st->pad0 = m->h_st->pad1 = 0;
-    CK(cudaEventRecord(m->ev0, s));
     const bool mega = n == 1 && use_mega(m);
-    if (mega) { RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0])); }
-    else {
-        CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
-        RET(forward(m, m->d_tokens, n, 0));
+    static const bool use_tail = !(getenv("BGPT_TOPK_TAIL") && atoi(getenv("BGPT_TOPK_TAIL")) == 0);
+    // generation 5 selects inside the forward kernel (the CTA that finishes last: bgpt_topk.cuh, topk_tail): no further launch
+    const bool tail = mega && use_tail && mega_generation(m) == 5 && m->mega5_ok && k <= M5_NC && m->n_vocab >= M5_NC;
+    const bool chain = tail && m->h_topk_dev && m->h_feed_dev && chain_enabled(m);
+    auto packet = [&](unsigned serial, bool host_view) { return (host_view || !m->h_topk_dev ? (host_view ? m->h_topk : m->d_topk) : m->h_topk_dev) + (serial & 1u) * tk_bytes; };
+    auto next_seq = [&]() { const unsigned q = ++m->topk_seq ? m->topk_seq : ++m->topk_seq; return q; };
+    auto next_feed = [&]() { const unsigned q = ++m->feed_seq ? m->feed_seq : ++m->feed_seq; return q; };
+    unsigned seq = 0;
+    bool timed = false;                                  // ev0 / ev1 bracket this call's device work (not when launches are chained)
+    if (chained && chain) {
+        // the kernel is in the stream already (running, if its predecessor has ended), polling the token word: name the token
+        seq = served.seq;
+        chain_feed(m, tokens[0] < 0 ? 0 : tokens[0], served.feed_seq);
+    } else {
+        if (chained) chain_feed(m, -2, served.feed_seq);                     // (settings changed in between) withdraw it
+        seq = next_seq();
+        memcpy(m->h_tokens, tokens, (size_t) n * sizeof(int));
+        m->h_st->n_past = n_past; m->h_st->step = 0; m->h_st->pad0 = m->h_st->pad1 = 0;
+        if (!chain) { CK(cudaEventRecord(m->ev0, s)); timed = true; }
+        if (tail) { const MegaTopk tk{ k, seq, packet(0u, false), (int) tk_bytes, 0u }; RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0], &tk)); }
+        else if (mega) { RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0])); }
+        else {
+            CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+            RET(forward(m, m->d_tokens, n, 0));
+        }
     }
     static const bool tk_prof = getenv("BGPT_TOPK_PROF") != nullptr;      // debug: where the call's device time goes (stderr every 256 calls)
     static cudaEvent_t ev_mid = nullptr;
-    if (tk_prof) { if (!ev_mid) cudaEventCreate(&ev_mid); cudaEventRecord(ev_mid, s); }
-    // The packet goes straight into mapped pinned host memory when the device can address it (no copy, no stream synchronisation: the
-    // host polls the sequence number); otherwise into device memory + one D2H copy.
-    uint8_t * pk = m->h_topk_dev ? m->h_topk_dev : m->d_topk;
-    int * dinfo = (int *) pk; float * dv = (float *) (pk + 16); int * di = (int *) (pk + 16 + (size_t) k * 4);
-    const unsigned seq = ++m->topk_seq ? m->topk_seq : ++m->topk_seq;
-    const int * errp = (mega && mega_generation(m) == 5 && m->mega5_ok) ? m->d_err5 : nullptr;
-    const int n_max = mega ? (mega_generation(m) == 5 ? M5_NC : m->mega_grid) : 0;
-    static const bool use_filter = !(getenv("BGPT_TOPK_FILTER") && atoi(getenv("BGPT_TOPK_FILTER")) == 0);
-    if (use_filter && m->n_vocab >= 4096 && n_max > 0 && n_max <= TOPK_SLICE && k <= n_max) {
-        // the persistent kernel's per-CTA maxima bound the k-th largest logit from below: filter, then rank the few survivors
-        RET(launch_topk2(s, m->logits, m->n_vocab, k, m->d_cand_val, n_max, m->d_topk_filt, dv, di, dinfo, errp, seq));
-        m->launches += 2;
-    } else if (m->n_vocab >= 4096) {
-        // every 256-logit slice ranks itself and keeps its k + 1 best; the single-CTA selection then runs over those candidates
-        RET(launch_topk3(s, m->logits, m->n_vocab, k, m->d_topk_cand, dv, di, dinfo, errp, seq));
-        m->launches += 3;
-    } else {
-        const int staged = (size_t) m->n_vocab * 4 <= (size_t) 190 * 1024;
-        k_topk<<<1, TOPK_NT, staged ? (size_t) m->n_vocab * 4 : 0, s>>>(m->logits, m->n_vocab, k, staged, dv, di, dinfo, nullptr, errp, seq);
-        m->launches++;
-    }
-    CK(cudaGetLastError());
-    if (!m->h_topk_dev) CK(cudaMemcpyAsync(m->h_topk, m->d_topk, 16 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(m->ev1, s));
-    m->last_ms_pending = true;
-    const volatile int * hinfo = (const volatile int *) m->h_topk;
-    if (m->h_topk_dev) {
-        bool got = false;
-        for (unsigned spins = 0; ; ) {
-            if ((unsigned) hinfo[3] == seq) { got = true; break; }
-            if ((++spins & 0x3FFu) == 0) {
-                const cudaError_t q = cudaStreamQuery(s);
-                if (q == cudaErrorNotReady) continue;
-                if (q != cudaSuccess) return fail(BGPT_E_CUDA, "eval_topk: %s", cudaGetErrorString(q));
-                got = (unsigned) hinfo[3] == seq;
-                break;
-            }
+    if (tk_prof && timed) { if (!ev_mid) cudaEventCreate(&ev_mid); cudaEventRecord(ev_mid, s); }
+    if (!tail) {
+        // The packet goes straight into mapped pinned host memory when the device can address it (no copy, no stream synchronisation: the
+        // host polls the sequence number); otherwise into device memory + one D2H copy.
+        uint8_t * pk = packet(seq, false);
+        int * dinfo = (int *) pk; float * dv = (float *) (pk + 16); int * di = (int *) (pk + 16 + (size_t) k * 4);
+        const int * errp = (mega && mega_generation(m) == 5 && m->mega5_ok) ? m->d_err5 : nullptr;
+        const int n_max = mega ? (mega_generation(m) == 5 ? M5_NC : m->mega_grid) : 0;
+        static const bool use_filter = !(getenv("BGPT_TOPK_FILTER") && atoi(getenv("BGPT_TOPK_FILTER")) == 0);
+        if (use_filter && m->n_vocab >= 4096 && n_max > 0 && n_max <= TOPK_SLICE && k <= n_max) {
+            // the persistent kernel's per-CTA maxima bound the k-th largest logit from below: filter, then rank the few survivors
+            RET(launch_topk2(s, m->logits, m->n_vocab, k, m->d_cand_val, n_max, m->d_topk_filt, dv, di, dinfo, errp, seq));
+            m->launches += 2;
+        } else if (m->n_vocab >= 4096) {
+            // every 256-logit slice ranks itself and keeps its k + 1 best; the single-CTA selection then runs over those candidates
+            RET(launch_topk3(s, m->logits, m->n_vocab, k, m->d_topk_cand, dv, di, dinfo, errp, seq));
+            m->launches += 3;
+        } else {
+            const int staged = (size_t) m->n_vocab * 4 <= (size_t) 190 * 1024;
+            k_topk<<<1, TOPK_NT, staged ? (size_t) m->n_vocab * 4 : 0, s>>>(m->logits, m->n_vocab, k, staged, dv, di, dinfo, nullptr, errp, seq);
+            m->launches++;
         }
-        if (!got) { CK(cudaStreamSynchronize(s)); if ((unsigned) hinfo[3] != seq) return fail(BGPT_E_CUDA, "eval_topk: the result packet never arrived"); }
-        __sync_synchronize();
+        CK(cudaGetLastError());
+        if (!m->h_topk_dev) CK(cudaMemcpyAsync(packet(seq, true), packet(seq, false), 16 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (timed) { CK(cudaEventRecord(m->ev1, s)); m->last_ms_pending = true; }
+    else { m->last_ms_pending = false; m->last_ms = 0.f; }
+    // chained launch: the kernel of the next position goes into the stream now, behind the one this call waits for; it starts the
+    // moment its predecessor ends, fetches its first weights and polls the token word until the next call (or a withdrawal) writes it
+    if (chain && n_past + 1 < m->n_positions) {
+        bgpt_model::Chain c; c.active = true; c.n_past = n_past + 1; c.k = k; c.seq = next_seq(); c.feed_seq = next_feed();
+        const MegaTopk tk{ k, c.seq, packet(0u, false), (int) tk_bytes, c.feed_seq };
+        RET(launch_mega(m, m->d_tokens, 3, n_past + 1, -1, 0, &tk));
+        m->chain = c;
+    }
+    const uint8_t * hp = packet(seq, true);
+    const volatile int * hinfo = (const volatile int *) hp;
+    if (m->h_topk_dev) {
+        RET(wait_packet(m, hinfo, seq));
+        if (hinfo[1] == -2) {
+            // the queued kernel gave up before the token came (the caller took longer than BGPT_CHAIN_WAIT_US): a fresh launch serves the
+            // position; the kernel queued behind it just now is withdrawn first (it was promised position n_past + 1)
+            chain_cancel(m);
+            return bgpt_cuda_eval_topk(m, tokens, n, n_past, k, vals, ids, n_out, exact, logits_fallback);
+        }
     } else CK(cudaStreamSynchronize(s));
-    RET(check_rows_error(m));
+    if (!m->chain.active) RET(check_rows_error(m));
     if (hinfo[2] != 0) {
         const int code = hinfo[2];
+        chain_cancel(m);
         cudaStreamSynchronize(s); cudaMemset(m->d_err5, 0, sizeof(int));
         return fail(BGPT_E_CUDA, "persistent decode kernel (generation 5): a wait timed out -- stage %d, layer %d, wait %d; results are invalid",
                     code >> 16, (code >> 8) & 0xff, code & 0xff);
     }
-    if (tk_prof) {
+    if (tk_prof && timed) {
         static double t_fwd = 0, t_topk = 0; static int calls = 0;
         float a = 0, b = 0;
         cudaEventSynchronize(m->ev1);
@@ -1608,9 +1708,12 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     }
     const int got_n = hinfo[0];
     *n_out = got_n; *exact = hinfo[1];
-    memcpy(vals, m->h_topk + 16, (size_t) got_n * 4);
-    memcpy(ids, m->h_topk + 16 + (size_t) k * 4, (size_t) got_n * 4);
-    if (!hinfo[1] && logits_fallback) CK(cudaMemcpy(logits_fallback, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost));
+    memcpy(vals, hp + 16, (size_t) got_n * 4);
+    memcpy(ids, hp + 16 + (size_t) k * 4, (size_t) got_n * 4);
+    if (!hinfo[1] && logits_fallback) {
+        chain_cancel(m);                                 // the full row is read behind the stream: nothing may wait in front of the copy
+        CK(cudaMemcpy(logits_fallback, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost));
+    }
     return BGPT_OK;
 }
 
@@ -1631,6 +1734,7 @@ extern "C" int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, i
 extern "C" const float * bgpt_cuda_logits_device(bgpt_model * m) { return m ? m->logits : nullptr; }
 extern "C" int bgpt_cuda_synchronize(bgpt_model * m) {
     if (!m) return fail(BGPT_E_ARG, "synchronize: NULL model");
+    chain_cancel(m);
     CK(cudaSetDevice(m->device));
     CK(cudaStreamSynchronize(m->stream));
     RET(check_rows_error(m));
@@ -1687,6 +1791,7 @@ extern "C" int bgpt_cuda_decode_greedy(bgpt_model * m, int32_t first_token, int 
 }
 
 extern "C" int bgpt_cuda_set_streams(bgpt_model * m, int n_streams) {
+    chain_cancel(m);
     if (!m || n_streams < 1) return fail(BGPT_E_ARG, "set_streams: bad arguments");
     CK(cudaSetDevice(m->device));
     CK(cudaStreamSynchronize(m->stream));

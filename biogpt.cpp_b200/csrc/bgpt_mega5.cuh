@@ -32,6 +32,7 @@
 // the three generations with each other and with the oracle bit for bit.
 #pragma once
 #include "bgpt_mega4.cuh"
+#include "bgpt_topk.cuh"
 
 #define M5_NT 512
 #define M5_NW (M5_NT / 32)
@@ -56,6 +57,11 @@
 #define M5_E4W (M5_FF / 2)
 #define M5_E4F(parity) (2 * M5_LW + (parity) * (M5_R * M5_E4W))
 #define M5_XCH_WORDS (2 * M5_LW + 2 * M5_R * M5_E4W)
+// the fed token (use_cand == 3): M5_R replicas of one tagged word, 128 bytes apart, behind everything else; tag = launch serial << 6
+#define M5_TOKX M5_XCH_WORDS
+#define M5_XCH_TOTAL (M5_XCH_WORDS + M5_R * 16)
+#define M5_TOK_CANCEL (-2)     // the host withdrew the launch
+#define M5_TOK_TIMEOUT (-3)    // no token arrived within feed_limit cycles
 #define M5_MAXL 24
 #define M5_PK 12              // trace stamps per (layer, stage)
 
@@ -69,6 +75,19 @@ struct M5Params {
     int prof_n;
     int nslot, slot_bytes, lmrt;   // weight ring: slots, bytes per slot, lm_head rows per tile (32 or 64)
     int sm_w, sm_rec0, sm_rec1, sm_x, sm_x1, sm_sc, sm_red, sm_tail, sm_p, sm_s, sm_total;   // sm_p < 0: no fc2 scratch (relay instead)
+    // sampler tail (bgpt_cuda_eval_topk): tk_k > 0 -> the CTA that finishes last selects the tk_k largest logits (bgpt_topk.cuh:
+    // topk_tail) and writes the result packet {info[4], vals, ids} -- possibly straight into mapped pinned host memory
+    int tk_k; unsigned tk_seq;     // packet of serial s: tk_pk + (s & 1) * tk_stride = { info[4], tk_k vals, tk_k ids }
+    uint8_t * tk_pk; int tk_stride;
+    unsigned * tk_ticket;          // device counter, 0 between launches
+    // chained launch (use_cand == 3): the kernel is queued BEFORE its input token exists; CTA 0 polls the 8-byte word {token, serial} in
+    // mapped pinned host memory until the serial is feed_seq and hands the token to the other CTAs through L2.  No token within
+    // feed_limit cycles, or the value M5_TOK_CANCEL: the kernel exits without touching the KV cache or the logits (a time-out leaves a
+    // packet with info[1] = -2 under the serial tk_seq).
+    // (A RESIDENT form -- the kernel loops over positions instead of exiting, 5 us per token less than a queued launch -- was built and
+    // measured: any back edge around the layer loop costs the quantised instantiations, which sit at the 128-register budget, 100-280
+    // bytes of spills in the hot loop: 370 -> 415-458 us per token.  profiles/README.md, round 2.)
+    const unsigned long long * feed; unsigned feed_seq; long long feed_limit;
 };
 
 // ---- cluster / DSMEM -------------------------------------------------------------------------------------------------------
@@ -434,7 +453,6 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     const bool is_head = cta < M5_HC;                              // clusters 0..15: one attention head each
     const int head = cta >> 2;
     const int rank = (int) m5_cluster_rank();                      // == cta & 3 for a 1-D cluster of 4
-    const uint32_t tag0 = P.tag;
     int * const err = P.err;
     uint8_t * s_w = smem + P.sm_w;
     uint8_t * rec0 = smem + P.sm_rec0;
@@ -497,12 +515,10 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == ISSUER) {
-#pragma unroll 1
-        for (int n = 0; n < P.nslot - 1; n++) fire_tile(n, describe_tile(n));
-    }
 
     const int pos = p.n_past, T = p.n_past + 1;
+    const uint32_t tag0 = P.tag;
+    const bool fed = p.use_cand == 3;
     // L2 prefetch of the K/V lines this head reads in layer Ln (2 lines per position and tensor, spread over the cluster) and of
     // Ln's small f32 vectors
     auto prefetch_layer = [&](int Ln) {
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         if (is_head) {
             const int pr = rank * 512 + tid;
             const int t = pr >> 1, half = pr & 1;
-            if (t < p.n_past) {
+            if (t < pos) {
                 const size_t o = (size_t) Ln * n_pos * M5_D + (size_t) t * M5_D + head * M5_DK + half * 32;
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(p.kcache + o));
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(p.vcache + o));
@@ -525,8 +541,13 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 asm volatile("prefetch.global.L2 [%0];" :: "l"((const uint8_t *) vecs[who] + off));
         }
     };
-    prefetch_layer(0);
     if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) M5_NC * P.prof_n + 4 * cta);
+    // the first tiles and layer 0's K/V lines are on their way while the token may still be unknown
+    if (tid == ISSUER) {
+#pragma unroll 1
+        for (int n = 0; n < P.nslot - 1; n++) fire_tile(n, describe_tile(n));
+    }
+    prefetch_layer(0);
 
     // ---- input token: given, or argmax over the candidates the previous launch left
     if (tid < 32) {
@@ -544,6 +565,34 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
                 if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
             }
             tok = bi == 0x7fffffff ? 0 : bi;
+        } else if (fed) {
+            tok = 0;
+            if (tid == 0) {
+                if (cta == 0) {
+                    int t = M5_TOK_TIMEOUT;
+                    const long long t0 = clock64();
+                    const unsigned fseq = P.feed_seq;
+                    for (;;) {
+                        unsigned long long w;
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(P.feed) : "memory");
+                        if ((uint32_t) (w >> 32) == fseq) { t = (int) (uint32_t) w; break; }
+                        if (clock64() - t0 > P.feed_limit) break;
+                    }
+#pragma unroll
+                    for (int r = 0; r < M5_R; r++) m4_put(P.xch + M5_TOKX + r * 16, (uint32_t) t, tag0);
+                    tok = t;
+                } else {
+                    const unsigned long long * src = P.xch + M5_TOKX + (cta % M5_R) * 16;
+                    unsigned long long w = 0; unsigned spins = 0; long long t0 = 0;
+                    for (;;) {
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                        if ((uint32_t) (w >> 32) == tag0) break;
+                        if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, 1, t0)) break; }
+                    }
+                    tok = (int) (uint32_t) w;
+                }
+            }
+            tok = __shfl_sync(FULLMASK, tok, 0);
         } else tok = p.use_cand == 2 ? p.tok_imm : __ldcg(p.tok);
         if (tid == 0) {
             s_tok = tok;
@@ -552,10 +601,25 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     }
     // every CTA of the cluster is running (its shared memory exists) before anyone stores into a peer; also publishes s_tok
     m5_cluster_sync();
+    if (fed && s_tok < 0) {
+        // withdrawn (or no token in time): nothing was written; the weight tiles fired above must land before the CTA may exit
+        if (tid == ISSUER) {
+#pragma unroll 1
+            for (int n = 0; n < P.nslot - 1; n++) if (describe_tile(n).b0) m5_mbar_wait(&mbar[n], (wphase >> n) & 1u, err, 2);
+        }
+        if (cta == 0 && tid == 0 && s_tok == M5_TOK_TIMEOUT && P.tk_k > 0) {
+            const unsigned tk_seq = P.tk_seq;
+            int * info = (int *) (P.tk_pk + (size_t) (tk_seq & 1u) * P.tk_stride);
+            info[0] = 0; info[1] = -2; info[2] = 0;
+            __threadfence_system();
+            *(volatile unsigned *) (info + 3) = tk_seq;
+        }
+        return;
+    }
     // ---- embedding: every CTA, 8 elements per prep thread, into s_x (read back by the first tile)
     if (tid < M5_PT) {
         int tok = s_tok; tok = tok < 0 ? 0 : (tok >= p.n_vocab ? p.n_vocab - 1 : tok);
-        int prow = p.n_past + 2; prow = prow >= p.n_pos_rows ? p.n_pos_rows - 1 : prow;
+        int prow = pos + 2; prow = prow >= p.n_pos_rows ? p.n_pos_rows - 1 : prow;
         const size_t rb = bg_file_row_bytes(FMT, M5_D);
         const uint8_t * tr = p.embed_tok + rb * (size_t) tok;
         const uint8_t * pr = p.embed_pos + rb * (size_t) prow;
@@ -1036,6 +1100,21 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
 #pragma unroll 1
         for (int i = 1; i < M5_NW; i++) if (s_cv[i] > best || (s_cv[i] == best && s_ci[i] < bi)) { best = s_cv[i]; bi = s_ci[i]; }
         p.cand_val[cta] = best; p.cand_idx[cta] = bi;
+    }
+    // ---- sampler tail: whoever takes the last ticket sees every CTA's logits and maximum (fence + atomic on both sides)
+    if (P.tk_k > 0) {
+        __shared__ int s_last;
+        if (tid == 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            s_last = atomicAdd(P.tk_ticket, 1u) == (unsigned) (M5_NC - 1);
+            if (s_last) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); *P.tk_ticket = 0u; }
+        }
+        __syncthreads();
+        if (s_last) {
+            const unsigned tk_seq = P.tk_seq;
+            uint8_t * pk = P.tk_pk + (size_t) (tk_seq & 1u) * P.tk_stride;
+            topk_tail<M5_NT>(p.logits, p.n_vocab, P.tk_k, p.cand_val, M5_NC, s_w, (float *) (pk + 16), (int *) (pk + 16 + (size_t) P.tk_k * 4), (int *) pk, err, tk_seq);
+        }
     }
     { const int l = p.n_layer; M5PROF(0, 2); }
     if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) M5_NC * P.prof_n + 4 * cta + 2);

@@ -153,6 +153,87 @@ static __global__ void __launch_bounds__(TOPK_SLICE) k_topk_filter(const float *
     }
 }
 
+// The same selection as k_topk_filter + k_topk_rank<true>, as the TAIL of a persistent decode kernel: the CTA that finishes its
+// lm_head rows last (an atomic ticket) derives t0 from the n_max per-CTA maxima, scans the logit row in L2 for { logit >= t0 },
+// ranks the survivors by counting and writes the result packet -- no extra launch, no extra grid-wide exchange.  Called by every
+// thread of that CTA (NT threads); scratch: TOPK_TAIL_SMEM bytes of shared memory, 16-byte aligned; n_max <= 256.
+#define TOPK_TAIL_SMEM (2 * (TOPK_RANK_MAX + 4) * 4 + (2 * (TOPK_MAXK + 4) + 256) * 4)
+template <int NT>
+__device__ __noinline__ void topk_tail(const float * logits, int n, int k, const float * cta_max, int n_max, uint8_t * scratch,
+                                          float * out_val, int * out_idx, int * info, const int * err, unsigned seq) {
+    __shared__ int s_cnt; __shared__ uint32_t s_t0;
+    uint32_t * s_k = (uint32_t *) scratch;
+    int * s_i = (int *) (s_k + TOPK_RANK_MAX + 4);
+    uint32_t * s_sorted = (uint32_t *) (s_i + TOPK_RANK_MAX + 4);
+    uint32_t * s_m = s_sorted + TOPK_MAXK + 4;
+    const int tid = threadIdx.x;
+    const int n_max4 = (n_max + 3) & ~3;
+    // the row is read in rounds of TB 16-byte loads per thread, all in flight together (a load per loop iteration would cost one L2
+    // round trip each: 21 x 0.7 us); the first round is issued before the threshold is known
+    constexpr int TB = 11;
+    const int n4 = n >> 2;
+    float4 v[TB];
+#pragma unroll
+    for (int j = 0; j < TB; j++) { const int i = j * NT + tid; if (i < n4) v[j] = __ldcg((const float4 *) logits + i); }
+    for (int i = tid; i < n_max4; i += NT) s_m[i] = i < n_max ? topk_key(__ldcg(cta_max + i)) : 0u;
+    for (int i = tid; i < TOPK_MAXK + 2; i += NT) s_sorted[i] = 0u;
+    if (tid == 0) { s_cnt = 0; s_t0 = 0u; }
+    __syncthreads();
+    for (int i = tid; i < n_max; i += NT) { const uint32_t mk = s_m[i]; if (topk_rank_of(s_m, n_max4, i, mk) == k - 1) s_t0 = mk; }   // ranks are unique
+    __syncthreads();
+    const uint32_t t0 = s_t0;
+#pragma unroll 1
+    for (int base = 0; base < n4; base += TB * NT) {
+        if (base > 0) {
+#pragma unroll
+            for (int j = 0; j < TB; j++) { const int i = base + j * NT + tid; if (i < n4) v[j] = __ldcg((const float4 *) logits + i); }
+        }
+#pragma unroll
+        for (int j = 0; j < TB; j++) {
+            const int i = base + j * NT + tid;
+            if (i >= n4) break;
+            const float f[4] = { v[j].x, v[j].y, v[j].z, v[j].w };
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t u = topk_key(f[c]);
+                if (u >= t0) { const int p = atomicAdd(&s_cnt, 1); if (p < TOPK_RANK_MAX) { s_k[p] = u; s_i[p] = 4 * i + c; } }
+            }
+        }
+    }
+    for (int i = 4 * n4 + tid; i < n; i += NT) {
+        const uint32_t u = topk_key(__ldcg(logits + i));
+        if (u >= t0) { const int p = atomicAdd(&s_cnt, 1); if (p < TOPK_RANK_MAX) { s_k[p] = u; s_i[p] = i; } }
+    }
+    __syncthreads();
+    const bool overflow = s_cnt > TOPK_RANK_MAX;                   // a plateau of equal logits: "not exact", the caller takes the full row
+    const int cnt = overflow ? TOPK_RANK_MAX : s_cnt, cnt4 = (cnt + 3) & ~3;
+    if (tid < cnt4 - cnt) s_k[cnt + tid] = 0u;
+    __syncthreads();
+    // the winners are staged in shared memory (values in s_sorted, ids in s_oi) and leave as consecutive words from ONE warp: the packet
+    // may live in mapped pinned host memory, where 2 k scattered 4-byte stores from 40 warps are 2 k PCIe writes
+    int * s_oi = (int *) (s_m + 256);
+    for (int e = tid; e < cnt; e += NT) {
+        const uint32_t u = s_k[e];
+        const int rank = topk_rank_of(s_k, cnt4, e, u);
+        if (rank < k + 1) { s_sorted[rank] = u; if (rank < k) s_oi[rank] = s_i[e]; }
+    }
+    __syncthreads();
+    const int k_eff = k < cnt ? k : cnt;
+    int dup = 0;
+    for (int j = tid; j < k_eff && j + 1 < cnt; j += NT) dup |= (s_sorted[j] == s_sorted[j + 1]) ? 1 : 0;
+    dup = __syncthreads_or(dup);
+    if (tid < 32) {
+        for (int j = tid; j < k_eff; j += 32) {
+            const uint32_t u = s_sorted[j];
+            out_val[j] = __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+            out_idx[j] = s_oi[j];
+        }
+        if (tid == 0) { info[0] = k_eff; info[1] = (dup || overflow) ? 0 : 1; info[2] = err ? *(volatile const int *) err : 0; }
+        __syncwarp();
+        if (tid == 0) { __threadfence_system(); *(volatile unsigned *) (info + 3) = seq; }
+    }
+}
+
 // out_val / out_idx: K entries; info[0] = entries written (min(K, n)), info[1] = 1 if the selection and its order are unambiguous
 // (info: 4 ints, see the end of the kernel).
 // remap (optional): out_idx[rank] = remap[position] -- the input is a candidate list, not the logit row.

@@ -5,6 +5,8 @@
 #include "mosestokenizer.h"
 
 #include <cstring>
+#include <chrono>
+#include "../../include/bgpt_cuda.h"
 
 namespace {
 int join(const std::vector<std::string> & v, char * out, int cap) {
@@ -87,6 +89,27 @@ int bgpt_host_tokenize(void * h, const char * text, int32_t * out, int cap) {
     if ((int) ids.size() > cap) return -1;
     for (size_t i = 0; i < ids.size(); i++) out[i] = ids[i];
     return (int) ids.size();
+}
+// The token-by-token loop of examples/main/main.cpp:93-151 on an engine handle, for bench.py's end-to-end leg and tools/e2e_bench.py:
+// ONE bgpt_cuda_eval_topk call per token with host buffers (token id in, top_k (logit, id) pairs out), the host picks the next token
+// from the returned pairs -- the best one, so the ids can be compared with the device-resident greedy loop; equal logits among the
+// pairs (exact = 0) are decided on the full row the call then delivers.  *wall_s = time inside the loop (std::chrono::steady_clock).
+int bgpt_host_sampling_loop(bgpt_model * engine, int first_token, int n_past, int n_steps, int top_k, int32_t * ids_out, double * wall_s) {
+    if (!engine || !ids_out || n_steps < 1 || top_k < 1 || top_k > 128) return -1;
+    int32_t hp[7]; bgpt_cuda_hparams(engine, hp);
+    std::vector<float> full((size_t) hp[0]);
+    float vals[128]; int32_t ids[128]; int n_out = 0, exact = 0;
+    int32_t tok = first_token;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n_steps; i++) {
+        const int rc = bgpt_cuda_eval_topk(engine, &tok, 1, n_past + i, top_k, vals, ids, &n_out, &exact, full.data());
+        if (rc != BGPT_OK) return rc < 0 ? rc : -rc;
+        if (exact && n_out > 0) tok = ids[0];
+        else { int best = 0; for (int j = 1; j < hp[0]; j++) if (full[j] > full[best]) best = j; tok = best; }
+        ids_out[i] = tok;
+    }
+    if (wall_s) *wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
 }
 void bgpt_host_close(void * h) {
     Session * s = (Session *) h;

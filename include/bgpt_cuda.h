@@ -106,6 +106,14 @@ int bgpt_cuda_synchronize(bgpt_model * m);
  * drawn id is the reference's in every case.  K <= 128. */
 int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
                         float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback);
+/* Chained launches of bgpt_cuda_eval_topk (generation-5 decode kernel; default on, BGPT_CHAIN=0 turns it off): a sampling loop
+ * (examples/main/main.cpp:93-151) asks for position p + 1 right after position p, so the call for p also queues the kernel of p + 1
+ * behind the one it waits for.  That kernel starts the moment its predecessor ends, fetches its first weights and polls an 8-byte
+ * word in mapped pinned host memory; the next call only writes the sampled token id there -- no launch and no front-end latency on
+ * the token-to-token path.  Any other call on the model withdraws the queued kernel first (it exits without touching the KV cache);
+ * a kernel that saw no token within BGPT_CHAIN_WAIT_US (default 2000) gives up and the position is evaluated by a fresh launch.
+ * bgpt_cuda_last_eval_ms is 0 for chained calls.  on: 1 / 0, -1 = the BGPT_CHAIN default. */
+int bgpt_cuda_set_chain(bgpt_model * m, int on);
 
 /* Greedy decode entirely on the device: starting from `first_token` at position n_past,
  * run `n_steps` evals of one token each, feeding argmax(logits) back in (first index wins

@@ -294,6 +294,50 @@ def test_device_topk_after_the_persistent_kernel_full_vocabulary(capi, zoo):
     M.close()
 
 
+@pytest.mark.parametrize("ftype", ["q4_0", "q5_1", "f16"])
+def test_chained_launches_return_what_single_launches_return(capi, zoo, ftype):
+    """bgpt_cuda_eval_topk queues the kernel of position p + 1 while the call for p waits (bgpt_cuda_set_chain): the sampling loop must
+    see the same (logit, id) pairs with and without it, through withdrawals (another call in between, a jump in n_past, another k),
+    through a caller that is slower than the kernel's patience (the queued kernel gives up, a fresh launch serves the call) and up to
+    the last position of the context"""
+    import time
+    M = capi.Model.load(zoo.path("base", ftype))
+    if M.decode_generation != 5:
+        M.close(); pytest.skip("chained launches need the generation-5 decode kernel")
+    n_pos = gf.BASE.n_positions
+    M.decode_greedy(2, 0, n_pos)                                        # every position of the KV cache holds defined values
+
+    def run(chain, plan):
+        M.set_chain(chain)
+        out = []
+        tok = np.array([2], dtype=np.int32)
+        for what, p, k in plan:
+            if what == "full":
+                full = M.eval(tok, p)
+                out.append(("full", p, int(np.argmax(full))))
+                continue
+            if what == "sleep":
+                time.sleep(0.02)
+                continue
+            vals, ids, exact, fb = M.eval_topk(tok, p, k)
+            out.append((p, k, vals.copy().view(np.uint32).tolist(), ids.copy().tolist(), exact))
+            tok[0] = int(ids[0]) if exact else int(np.argmax(fb))
+        return out
+
+    plan = [("topk", p, 40) for p in range(0, 24)]                     # a plain sampling loop
+    plan += [("full", 24, 0)] + [("topk", p, 40) for p in range(24, 30)]   # another call withdraws the queued kernel
+    plan += [("topk", p, 5) for p in range(30, 34)]                    # another k
+    plan += [("topk", 12, 40), ("topk", 13, 40)]                       # back in the context
+    plan += [("sleep", 0, 0), ("topk", 14, 40), ("sleep", 0, 0), ("topk", 15, 40), ("topk", 16, 40)]   # slower than the queued kernel's patience
+    plan += [("topk", p, 40) for p in range(n_pos - 3, n_pos)]         # the last positions: nothing is queued behind the last one
+    want = run(0, plan)
+    got = run(1, plan)
+    assert got == want
+    got2 = run(-1, plan)                                               # the default (on unless BGPT_CHAIN=0)
+    assert got2 == want
+    M.close()
+
+
 @pytest.mark.parametrize("n", [1000, 4096, 42384, 50001])
 def test_device_topk_selection_and_tie_flags(capi, n):
     """the selection kernel(s) on crafted logit rows: n >= 4096 runs the two-launch form (every 256-logit slice keeps its K + 1

@@ -38,6 +38,14 @@ for p in range(a.n_past, a.n_past + a.steps):
     tok[0] = idsb[0]
 wall3 = (time.perf_counter() - t0) / a.steps * 1e6
 print(f"   raw ctypes call loop {wall3:.1f} us per token")
+# the same loop in C++ (host/host_capi.cpp: bgpt_host_sampling_loop) -- what a C++ caller such as examples/main pays
+H = C.CDLL(os.path.join(ROOT, "biogpt.cpp_b200", "host", "libbiogpt_b200.so"))
+H.bgpt_host_sampling_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+out_ids = np.zeros(a.steps, np.int32); ws = C.c_double(0)
+for rep in range(2):
+    rc = H.bgpt_host_sampling_loop(M.h, 2, a.n_past, a.steps, a.k, out_ids.ctypes.data, C.byref(ws))
+    assert rc == 0, rc
+print(f"   C++ loop {ws.value / a.steps * 1e6:.1f} us per token")
 ids_dev, ms = M.decode_greedy(2, a.n_past, a.steps) if a.n_past == 0 else (None, 0.0)
 dev = ms * 1e3 / a.steps if ms else float("nan")
 print(f"{a.ftype} eval_topk k={a.k}: {wall:.1f} us per token wall (n_past {a.n_past}..{a.n_past + a.steps - 1}); device-resident greedy loop {dev:.1f} us per token; "

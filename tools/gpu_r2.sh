@@ -114,10 +114,12 @@ tcwab)
     BGPT_F16_TC_SPLIT=$sp timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_eval.py -m gpu -q -s -k "tensor_core_f16 or f16_prompt" 2>&1 | grep -E "max\|d|passed|failed"; done >> $OUT/prompt_tcw_ab.log 2>&1
   cat $OUT/prompt_tcw_ab.log ;;
 e2e)
-  timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_host_lib.py -m gpu -q --maxfail=5 -k "topk or sampler" > $OUT/pytest_topk.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_topk.log
+  timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_host_lib.py -m gpu -q --maxfail=5 -k "topk or sampler or chained" > $OUT/pytest_topk.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_topk.log
   grep -E "passed|failed|FAILED|Error|assert" $OUT/pytest_topk.log | tail -12
   timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 > $OUT/e2e.log 2>&1
-  BGPT_TOPK_ZC=0 timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 >> $OUT/e2e.log 2>&1
+  BGPT_CHAIN=0 timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 >> $OUT/e2e.log 2>&1
+  BGPT_CHAIN=0 BGPT_TOPK_TAIL=0 timeout 300 python tools/e2e_bench.py --ftype q4_0 --steps 256 >> $OUT/e2e.log 2>&1
+  timeout 300 python tools/e2e_bench.py --ftype f16 --steps 256 >> $OUT/e2e.log 2>&1
   cat $OUT/e2e.log ;;
 f16g5)
   timeout 1500 python -m pytest tests/test_gpu_eval.py -m gpu -q --maxfail=3 -x -k "persistent_generations and f16 or base_shape_matches_oracle and f16 or base_model_64 and f16" > $OUT/pytest_f16g5.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_f16g5.log
