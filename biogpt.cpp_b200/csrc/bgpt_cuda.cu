@@ -138,6 +138,7 @@ struct bgpt_model {
     long long * d_trace = nullptr; size_t trace_n = 0;
     // generation-5 persistent kernel (bgpt_mega5.cuh): clusters of 4, one attention head per cluster, DSMEM exchange inside the head
     bool mega5_ok = false; M5Params m5{}; unsigned long long * d_xch5 = nullptr; unsigned int m5_tag = 0;
+    size_t xch5_off = 0;
     unsigned * d_tk_ticket = nullptr;                             // generation 5: ticket counter of the sampler tail
     // chained launches of bgpt_cuda_eval_topk (generation 5): the kernel of position p + 1 is queued while the call for p is still
     // waiting for its packet; its token arrives through `h_feed` (mapped pinned memory) when the next call names it
@@ -1227,7 +1228,8 @@ static int launch_cluster_kernel(const void * fn, int grid, int threads, int clu
 static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     m->mega5_ok = false;
     const bool prof = m->d_prof != nullptr;
-    const void * fn = bgpt_k_mega5_fn(m->wtype, prof);
+    const void * fn = bgpt_k_mega5_fn(m->wtype, prof, false);
+    const void * fn_tk = bgpt_k_mega5_fn(m->wtype, false, true);
     static_assert(sizeof(M5Params) <= 4096, "M5Params must fit the 4 KB kernel parameter space");
     if (!fn || m->n_layer > M5_MAXL || m->d_model != M5_D || m->d_ff != M5_FF || m->n_head != M5_NH || m->n_positions > 1024 ||
         prop.multiProcessorCount < M5_NC || m->n_vocab < M5_NC) return BGPT_OK;
@@ -1267,6 +1269,7 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     if (use_scratch) { P.sm_p = o; o += al(8 * 8 * M5_PS * 4); P.sm_s = o; o += al(hasm * 8 * M5_NB_F * 4); }
     P.sm_total = o;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sm_total));
+    if (fn_tk) CK(cudaFuncSetAttribute(fn_tk, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sm_total));
     {   // 32 clusters of 4 must be co-resident
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(M5_NC); cfg.blockDim = dim3(M5_NT); cfg.dynamicSmemBytes = (size_t) P.sm_total;
@@ -1277,7 +1280,11 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
         if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl * M5_CL < M5_NC) { cudaGetLastError(); return BGPT_OK; }
     }
     const size_t xb = (size_t) M5_XCH_TOTAL * sizeof(unsigned long long);
-    CK(cudaMalloc(&m->d_xch5, xb)); CK(cudaMemset(m->d_xch5, 0, xb));
+    // BGPT_M5_XCH_OFF (units of 256 bytes, < 4096): where the exchange words start inside their 1 MB-padded allocation -- which L2
+    // slices (and which die) the polled lines live on moves the step time by a few per cent
+    const size_t xpad = (size_t) 1 << 20;
+    CK(cudaMalloc(&m->d_xch5, xb + xpad)); CK(cudaMemset(m->d_xch5, 0, xb + xpad));
+    m->xch5_off = getenv("BGPT_M5_XCH_OFF") ? (size_t) (atoi(getenv("BGPT_M5_XCH_OFF")) & 4095) * 256 : 0;
     {   // [0] time-out code, [2..3] watchdog limit in cycles (~0.15 s; BGPT_M5_WATCHDOG_MCYC = millions of cycles, for sanitizer runs)
         CK(cudaMalloc(&m->d_err5, 4 * sizeof(int)));
         long long limit = 300000000LL;
@@ -1288,7 +1295,7 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     }
     CK(cudaMallocHost(&m->h_err5, sizeof(int))); *m->h_err5 = 0;
     CK(cudaMalloc(&m->d_tk_ticket, 16)); CK(cudaMemset(m->d_tk_ticket, 0, 16));
-    P.xch = m->d_xch5; P.err = m->d_err5;
+    P.xch = m->d_xch5 + m->xch5_off / sizeof(unsigned long long); P.err = m->d_err5;
     P.trace = nullptr; P.prof_n = (m->n_layer + 1) * 5 * M5_PK;
     if (prof) {
         m->trace5_n = (size_t) M5_NC * P.prof_n + 4 * (size_t) M5_NC;
@@ -1399,7 +1406,7 @@ static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_pa
         if (++m->m5_tag >= (1u << 26)) m->m5_tag = 1;        // 0 is the "never written" tag of a fresh buffer
         P.tag = m->m5_tag << 6;
         void * args[] = { &P };
-        RET(launch_cluster_kernel(bgpt_k_mega5_fn(m->wtype, m->d_trace5 != nullptr), M5_NC, M5_NT, M5_CL, (size_t) P.sm_total, m->stream, args));
+        RET(launch_cluster_kernel(bgpt_k_mega5_fn(m->wtype, !tk && m->d_trace5 != nullptr, tk != nullptr), M5_NC, M5_NT, M5_CL, (size_t) P.sm_total, m->stream, args));
         m->launches++;
         return BGPT_OK;
     }
@@ -1615,8 +1622,12 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     }
     cudaStream_t s = m->stream;
     const bool mega = n == 1 && use_mega(m);
-    static const bool use_tail = !(getenv("BGPT_TOPK_TAIL") && atoi(getenv("BGPT_TOPK_TAIL")) == 0);
-    // generation 5 selects inside the forward kernel (the CTA that finishes last: bgpt_topk.cuh, topk_tail): no further launch
+    // generation 5 selects inside the forward kernel (the CTA that finishes last: bgpt_topk.cuh, topk_tail): no further launch.
+    // BGPT_TOPK_TAIL: 0 never, 2 always, default = where it measured faster -- every format but Q5_0, whose instantiation WITH the tail
+    // and the token feed (k_mega5<.., TK = true>) comes out of ptxas 100 us per token slower than the one without, whatever is moved out
+    // of line (546 against 444 us per token through this call at n_past 384..639; profiles/README.md)
+    static const int tail_mode = getenv("BGPT_TOPK_TAIL") ? atoi(getenv("BGPT_TOPK_TAIL")) : 1;
+    const bool use_tail = tail_mode == 2 || (tail_mode == 1 && m->wtype != BG_Q5_0);
     const bool tail = mega && use_tail && mega_generation(m) == 5 && m->mega5_ok && k <= M5_NC && m->n_vocab >= M5_NC;
     const bool chain = tail && m->h_topk_dev && m->h_feed_dev && chain_enabled(m);
     auto packet = [&](unsigned serial, bool host_view) { return (host_view || !m->h_topk_dev ? (host_view ? m->h_topk : m->d_topk) : m->h_topk_dev) + (serial & 1u) * tk_bytes; };

@@ -432,9 +432,68 @@ __device__ __forceinline__ float m5_row_dot_f16(const uint8_t * wrow, const uint
     return c;
 }
 
+// ---- chained launch: the token arrives after the kernel has started -------------------------------------------------------------
+// One thread per CTA.  CTA 0 polls the 8-byte word {token, serial} in mapped pinned HOST memory until the serial is `fseq` (or `limit`
+// cycles have passed: M5_TOK_TIMEOUT) and publishes the token as M5_R tagged words in L2; the other CTAs poll their replica.
+// Out of line on purpose: the quantised instantiations of k_mega5 sit at the 128-register budget, and code added inline -- even in the
+// prologue -- reshuffles the allocation of the layer loop (Q5_0: 420 -> 527 us per token with this block inline).
+static __device__ __noinline__ int m5_fetch_token(const unsigned long long * feed, unsigned fseq, long long limit, unsigned long long * xtok,
+                                                   uint32_t tag0, int cta, int * err) {
+    if (cta == 0) {
+        int t = M5_TOK_TIMEOUT;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long w;
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(feed) : "memory");
+            if ((uint32_t) (w >> 32) == fseq) { t = (int) (uint32_t) w; break; }
+            if (clock64() - t0 > limit) break;
+        }
+#pragma unroll
+        for (int r = 0; r < M5_R; r++) m4_put(xtok + r * 16, (uint32_t) t, tag0);
+        return t;
+    }
+    const unsigned long long * src = xtok + (cta % M5_R) * 16;
+    unsigned long long w = 0; unsigned spins = 0; long long t0 = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+        if ((uint32_t) (w >> 32) == tag0) break;
+        if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, 1, t0)) break; }
+    }
+    return (int) (uint32_t) w;
+}
+
+// a withdrawn launch: the ISSUER thread (n_fired > 0) waits for the first-use phase of the ring slots it has fired -- a CTA must not
+// exit with bulk copies in flight into its shared memory; CTA 0's thread 0 reports a time-out under the serial the launch owed
+static __device__ __noinline__ void m5_withdrawn(uint64_t * mbar, int n_fired, bool is_head, int * err, bool announce, uint8_t * pk, unsigned seq) {
+#pragma unroll 1
+    for (int n = is_head ? 0 : 1; n < n_fired; n++) m5_mbar_wait(&mbar[n], 0u, err, 2);
+    if (announce) {
+        int * info = (int *) pk;
+        info[0] = 0; info[1] = -2; info[2] = 0;
+        __threadfence_system();
+        *(volatile unsigned *) (info + 3) = seq;
+    }
+}
+// the sampler tail: whoever takes the last ticket sees every CTA's logits and maximum (fence + atomic on both sides) and selects
+// (bgpt_topk.cuh); called by every thread of every CTA
+static __device__ __noinline__ void m5_sampler_tail(unsigned * ticket, const float * logits, int n_vocab, int k, const float * cand_val, uint8_t * scratch,
+                                                    uint8_t * pk, const int * err, unsigned seq) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        s_last = atomicAdd(ticket, 1u) == (unsigned) (M5_NC - 1);
+        if (s_last) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); *ticket = 0u; }
+    }
+    __syncthreads();
+    if (s_last) topk_tail<M5_NT>(logits, n_vocab, k, cand_val, M5_NC, scratch, (float *) (pk + 16), (int *) (pk + 16 + (size_t) k * 4), (int *) pk, err, seq);
+}
+
 #define M5PROF(ph, k) do { if (PROF && P.trace && threadIdx.x == 0) P.trace[(size_t) blockIdx.x * P.prof_n + (l * 5 + (ph)) * M5_PK + (k)] = clock64(); } while (0)
 
-template <int FMT, bool PROF>
+// TK: the instantiation bgpt_cuda_eval_topk launches -- token feed (use_cand == 3) and the sampler tail.  A template flag, not a
+// run-time one: the quantised instantiations sit at the 128-register budget, and the mere presence of that code reshuffles the layer
+// loop's allocation (Q5_0: 434 -> 547 us per token, Q4_1 + 3.6 %, Q4_0 + 1.3 %); the decode loop keeps the instantiation without it.
+template <int FMT, bool PROF, bool TK>
 __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Params P) {
     const MegaParams & p = P.b;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -518,7 +577,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
 
     const int pos = p.n_past, T = p.n_past + 1;
     const uint32_t tag0 = P.tag;
-    const bool fed = p.use_cand == 3;
+    const bool fed = TK && p.use_cand == 3;
     // L2 prefetch of the K/V lines this head reads in layer Ln (2 lines per position and tensor, spread over the cluster) and of
     // Ln's small f32 vectors
     auto prefetch_layer = [&](int Ln) {
@@ -567,31 +626,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             tok = bi == 0x7fffffff ? 0 : bi;
         } else if (fed) {
             tok = 0;
-            if (tid == 0) {
-                if (cta == 0) {
-                    int t = M5_TOK_TIMEOUT;
-                    const long long t0 = clock64();
-                    const unsigned fseq = P.feed_seq;
-                    for (;;) {
-                        unsigned long long w;
-                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(P.feed) : "memory");
-                        if ((uint32_t) (w >> 32) == fseq) { t = (int) (uint32_t) w; break; }
-                        if (clock64() - t0 > P.feed_limit) break;
-                    }
-#pragma unroll
-                    for (int r = 0; r < M5_R; r++) m4_put(P.xch + M5_TOKX + r * 16, (uint32_t) t, tag0);
-                    tok = t;
-                } else {
-                    const unsigned long long * src = P.xch + M5_TOKX + (cta % M5_R) * 16;
-                    unsigned long long w = 0; unsigned spins = 0; long long t0 = 0;
-                    for (;;) {
-                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
-                        if ((uint32_t) (w >> 32) == tag0) break;
-                        if ((++spins & 1023u) == 0) { if (t0 == 0) t0 = clock64(); else if (m5_give_up(err, 1, t0)) break; }
-                    }
-                    tok = (int) (uint32_t) w;
-                }
-            }
+            if constexpr (TK) if (tid == 0) tok = m5_fetch_token(P.feed, P.feed_seq, P.feed_limit, P.xch + M5_TOKX, tag0, cta, err);
             tok = __shfl_sync(FULLMASK, tok, 0);
         } else tok = p.use_cand == 2 ? p.tok_imm : __ldcg(p.tok);
         if (tid == 0) {
@@ -601,19 +636,12 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     }
     // every CTA of the cluster is running (its shared memory exists) before anyone stores into a peer; also publishes s_tok
     m5_cluster_sync();
-    if (fed && s_tok < 0) {
-        // withdrawn (or no token in time): nothing was written; the weight tiles fired above must land before the CTA may exit
-        if (tid == ISSUER) {
-#pragma unroll 1
-            for (int n = 0; n < P.nslot - 1; n++) if (describe_tile(n).b0) m5_mbar_wait(&mbar[n], (wphase >> n) & 1u, err, 2);
-        }
-        if (cta == 0 && tid == 0 && s_tok == M5_TOK_TIMEOUT && P.tk_k > 0) {
-            const unsigned tk_seq = P.tk_seq;
-            int * info = (int *) (P.tk_pk + (size_t) (tk_seq & 1u) * P.tk_stride);
-            info[0] = 0; info[1] = -2; info[2] = 0;
-            __threadfence_system();
-            *(volatile unsigned *) (info + 3) = tk_seq;
-        }
+    if constexpr (TK) if (fed && s_tok < 0) {
+        // withdrawn (or no token in time): nothing was written; the weight tiles fired above (tile 0 only by the head CTAs) must land
+        // before the CTA may exit
+        if (tid == ISSUER || (cta == 0 && tid == 0))
+            m5_withdrawn(mbar, tid == ISSUER ? P.nslot - 1 : 0, is_head, err, cta == 0 && tid == 0 && s_tok == M5_TOK_TIMEOUT && P.tk_k > 0,
+                         P.tk_pk + (size_t) (P.tk_seq & 1u) * P.tk_stride, P.tk_seq);
         return;
     }
     // ---- embedding: every CTA, 8 elements per prep thread, into s_x (read back by the first tile)
@@ -1101,21 +1129,9 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
         for (int i = 1; i < M5_NW; i++) if (s_cv[i] > best || (s_cv[i] == best && s_ci[i] < bi)) { best = s_cv[i]; bi = s_ci[i]; }
         p.cand_val[cta] = best; p.cand_idx[cta] = bi;
     }
-    // ---- sampler tail: whoever takes the last ticket sees every CTA's logits and maximum (fence + atomic on both sides)
-    if (P.tk_k > 0) {
-        __shared__ int s_last;
-        if (tid == 0) {
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            s_last = atomicAdd(P.tk_ticket, 1u) == (unsigned) (M5_NC - 1);
-            if (s_last) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); *P.tk_ticket = 0u; }
-        }
-        __syncthreads();
-        if (s_last) {
-            const unsigned tk_seq = P.tk_seq;
-            uint8_t * pk = P.tk_pk + (size_t) (tk_seq & 1u) * P.tk_stride;
-            topk_tail<M5_NT>(p.logits, p.n_vocab, P.tk_k, p.cand_val, M5_NC, s_w, (float *) (pk + 16), (int *) (pk + 16 + (size_t) P.tk_k * 4), (int *) pk, err, tk_seq);
-        }
-    }
+    // ---- sampler tail
+    if constexpr (TK) if (P.tk_k > 0)
+        m5_sampler_tail(P.tk_ticket, p.logits, p.n_vocab, P.tk_k, p.cand_val, s_w, P.tk_pk + (size_t) (P.tk_seq & 1u) * P.tk_stride, err, P.tk_seq);
     { const int l = p.n_layer; M5PROF(0, 2); }
     if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) M5_NC * P.prof_n + 4 * cta + 2);
 }

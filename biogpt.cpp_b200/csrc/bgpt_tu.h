@@ -6,7 +6,7 @@
 const void * bgpt_k_mega_fn(int wtype, int dk);                 // tu_mega3.cu : k_mega<FMT, DK>
 const void * bgpt_k_mega_pick_fn();                             // tu_mega3.cu : k_mega_pick
 const void * bgpt_k_mega4_fn(int wtype, bool prof);             // tu_mega4.cu : k_mega4<FMT, PROF>
-const void * bgpt_k_mega5_fn(int wtype, bool prof);             // tu_mega5.cu : k_mega5<FMT, PROF>
+const void * bgpt_k_mega5_fn(int wtype, bool prof, bool tk);    // tu_mega5.cu : k_mega5<FMT, PROF, TK> (tk: token feed + sampler tail)
 const void * bgpt_k_rows_fn(int wtype);                          // tu_rows.cu  : k_rows<FMT>
 const void * bgpt_k_sk_mm_fn(int wtype, int TN);                // tu_skinny.cu: k_sk_mm<FMT, TN>
 const void * bgpt_k_sk_ln_fn(int wtype);

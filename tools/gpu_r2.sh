@@ -59,6 +59,10 @@ ncutcx)
       python tools/profile_prompt.py --ftype q8_0 --n 1024 > $OUT/gemm_tcx_full.log 2>&1; echo "tcxfull rc=$?"
   ncu -i $OUT/gemm_tcx_full.ncu-rep --page raw --csv > $OUT/gemm_tcx_full_raw.csv 2>/dev/null
   tail -3 $OUT/gemm_tcx_full.log ;;
+e2esweep)
+  for ft in q4_0 q4_1 q5_0 q5_1 q8_0 f16; do for cfg in "1 1" "0 1" "0 0"; do set -- $cfg; echo "$ft chain=$1 tail=$2"; BGPT_CHAIN=$1 BGPT_TOPK_TAIL=$2 timeout 120 python tools/e2e_bench.py --ftype $ft --steps 256 --n-past 384 2>&1 | grep "C++ loop"; done; done | tee $OUT/e2esweep.log ;;
+fmtsweep)
+  for ft in q4_0 q4_1 q5_0 q5_1 q8_0 f16; do timeout 120 python tools/profile_decode.py --ftype $ft --n-past 511 --steps 64 --warm 4 2>&1 | grep "us/token"; done | tee $OUT/fmtsweep.log ;;
 smoke)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log
   tail -5 $OUT/smoke.log ;;

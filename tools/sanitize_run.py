@@ -19,7 +19,7 @@ quick = "--quick" in sys.argv
 tmp = tempfile.mkdtemp()
 WIDE = gf.HParams(**{**gf.NARROW.__dict__, "n_vocab": 4500})        # vocabulary >= 4096: the two- / three-launch device top-k
 jobs = [("narrow", gf.NARROW, "q4_0"), ("narrow", gf.NARROW, "f16")] if quick else [
-    ("narrow", gf.NARROW, "q4_0"), ("narrow", gf.NARROW, "q5_1"), ("narrow", gf.NARROW, "f16"), ("wide", WIDE, "q8_0"), ("small", gf.SMALL, "f16"), ("tiny", gf.TINY, "q8_0")]
+    ("narrow", gf.NARROW, "q4_0"), ("narrow", gf.NARROW, "q5_1"), ("narrow", gf.NARROW, "f16"), ("wide", WIDE, "q8_0"), ("wide", WIDE, "q5_0"), ("small", gf.SMALL, "f16"), ("tiny", gf.TINY, "q8_0")]
 for name, hp, ft in jobs:
     path = os.path.join(tmp, f"{name}-{ft}.bin")
     gf.write_model(path, hp, gf.synth_tensors(hp, seed=1234), gf.FTYPE_BY_NAME[ft])
@@ -43,8 +43,13 @@ for name, hp, ft in jobs:
             M.eval(toks[pos + i:pos + i + 1], pos + i)
     M.set_decode_path(1)
     M.decode_greedy(2, pos, 4)
+    # the sampler's form of the generation-5 kernel: selection as the kernel's tail, the next position's launch queued and fed its token
+    # through mapped host memory (chained), a withdrawal (the jump back), and the unchained form
+    for p2 in (pos, pos + 1, pos + 2, pos):
+        M.eval_topk(toks[p2:p2 + 1], p2, 40)
+    M.set_chain(0); M.eval_topk(toks[pos:pos + 1], pos, 5); M.set_chain(-1)
     if not quick:
-        M.eval_topk(toks[pos:pos + 1], pos, 40)                # after the persistent kernel: threshold filter + ranking CTA (vocabulary >= 4096)
+        # (Q5_0 models: selection AFTER the persistent kernel -- threshold filter + ranking CTA for a vocabulary >= 4096)
         M.eval_topk(toks[pos:pos + 4], pos, 40)                # after a prompt batch: slices -> groups -> one CTA
         M.set_streams(3)
         M.eval_streams(toks[:3], 0)
