@@ -230,7 +230,7 @@ def side_configs(capi, device: int, seq: int):
     l0 = M.launch_count; M.eval(toks[:8], 0); out["prompt_q8_0_n_batch_8"]["launches_per_eval"] = M.launch_count - l0
     M.close()
     # ---- configs[3]: 8 independent sequences per GPU in lock step, each with its own F32 KV cache.  Device-resident: the greedy loop
-    #      runs on the GPU (bgpt_cuda_decode_greedy_streams); host buffers: one bgpt_cuda_eval_streams call per step, logits D2H
+    #      runs on the GPU (bgpt_cuda_decode_greedy_streams); host buffers: one bgpt_cuda_eval_streams_topk call per step (40 pairs per stream D2H)
     S = 8
     M = capi.Model.load(model_path("q5_1"), device=device, max_batch=S)
     M.set_streams(S)
@@ -242,8 +242,10 @@ def side_configs(capi, device: int, seq: int):
     t0 = time.perf_counter()
     ids_host = []
     for p in range(seq):
-        logits = M.eval_streams(cur, p)
-        cur = np.argmax(logits, axis=1).astype(np.int32)
+        vals, tids, n_out, exact, full = M.eval_streams_topk(cur, p, 40)     # host ids in, 40 (logit, id) pairs per stream out
+        cur = tids[:, 0].copy()
+        for s_ in np.flatnonzero(exact == 0):
+            cur[s_] = int(np.argmax(full[s_]))
         ids_host.append(cur.copy())
     wall = time.perf_counter() - t0
     out["streams_q5_1_x8"] = {
@@ -355,9 +357,12 @@ def run_streams_workload(args, capi, dist, barrier, rank, local_rank, world):
     def one_pass():
         cur = first.copy(); ms = 0.0
         for p in range(seq):
-            logits = M.eval_streams(cur, p)
+            # host token ids in, per stream the 40 best (logit, id) pairs out (selected on the device), next token picked on the host
+            vals, tids, n_out, exact, full = M.eval_streams_topk(cur, p, 40)
             ms += M.last_eval_ms
-            cur = np.argmax(logits, axis=1).astype(np.int32)
+            cur = tids[:, 0].copy()
+            for s_ in np.flatnonzero(exact == 0):
+                cur[s_] = int(np.argmax(full[s_]))
         return ms
     for _ in range(max(1, args.warmup)):
         one_pass()
@@ -391,7 +396,8 @@ def run_streams_workload(args, capi, dist, barrier, rank, local_rank, world):
                      "ftype": ftype, "seq": seq, "streams_per_gpu": S, "parallelism": f"replicas x{world}",
                      "l2": "inputs larger than L2: every step streams the full weight set and S KV caches"},
           "clocks": clocks,
-          "e2e": {"value": world * S * seq * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": seq * (4 * S + 16), "d2h_bytes_per_step": seq * S * 42384 * 4},
+          "e2e": {"value": world * S * seq * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": seq * (4 * S + 16), "d2h_bytes_per_step": seq * S * (8 * 40 + 16),
+                  "call": "bgpt_cuda_eval_streams_topk per lock-step token (host ids in, top-40 pairs per stream out)"},
           "gpu_launches": launches,
           "roofline": {"bound": "hbm", "kernel": "fused skinny-batch schedule (k_sk_mm / k_sk_attn / k_sk_ln / k_sk_gq), per GPU", "achieved": achieved,
                        "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None},
@@ -416,6 +422,7 @@ def run_streams_cpp_driver(args):
     f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
     L.bgpt_replicas_eval.argtypes = [C.c_void_p, i32p, C.c_int, f32p]
     L.bgpt_replicas_decode_greedy.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, i32p, f32p]
+    L.bgpt_replicas_eval_topk.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, f32p, i32p, i32p, i32p, f32p]
     L.bgpt_replicas_last_error.restype = C.c_char_p
     r = L.bgpt_replicas_open(model_path(ftype).encode(), G, G * S)
     if not r:
@@ -435,15 +442,21 @@ def run_streams_cpp_driver(args):
     sampler = ClockSampler(0).start()
     ms_total = sum(one_pass() for _ in range(args.steps))
     clocks = sampler.stop()
-    # host buffers: one bgpt_replicas_eval per lock-step token, logits back, argmax on the host (a bounded 64-step sample)
+    # host buffers: one bgpt_replicas_eval_topk per lock-step token -- host token ids in, per stream the 40 best (logit, id) pairs out
+    # (selected on the device; a stream whose pairs tie also gets its full row), next token picked on the host (a bounded 64-step sample)
     n_e2e = min(seq, 64)
+    TOPK = 40
     logits = np.zeros((n_streams, n_vocab), np.float32)
+    tv = np.zeros(n_streams * TOPK, np.float32); ti = np.zeros(n_streams * TOPK, np.int32)
+    tn = np.zeros(n_streams, np.int32); tex = np.zeros(n_streams, np.int32)
     cur = first.copy()
     t0 = time.perf_counter()
     for p in range(n_e2e):
-        if L.bgpt_replicas_eval(r, cur, p, logits.reshape(-1)) != 0:
+        if L.bgpt_replicas_eval_topk(r, cur, p, TOPK, tv, ti, tn, tex, logits.reshape(-1)) != 0:
             raise SystemExit("bench.py: " + L.bgpt_replicas_last_error().decode())
-        cur = np.argmax(logits, axis=1).astype(np.int32)
+        cur = ti.reshape(n_streams, TOPK)[:, 0].copy()
+        for s_ in np.flatnonzero(tex == 0):
+            cur[s_] = int(np.argmax(logits[s_]))
     wall = time.perf_counter() - t0
     same = bool(np.array_equal(cur, ids.reshape(seq, n_streams)[n_e2e - 1]))
     L.bgpt_replicas_close(r)
@@ -458,8 +471,8 @@ def run_streams_cpp_driver(args):
                      "ftype": ftype, "seq": seq, "streams_per_gpu": S, "parallelism": f"replicas x{G}", "driver": "C++ replica driver, one host thread per GPU (no torch, no NCCL)",
                      "l2": "inputs larger than L2: every step streams the full weight set and S KV caches"},
           "clocks": clocks,
-          "e2e": {"value": n_streams * n_e2e / wall, "unit": UNIT, "h2d_bytes_per_step": seq * 4 * n_streams, "d2h_bytes_per_step": seq * n_streams * n_vocab * 4,
-                  "sample": f"first {n_e2e} lock-step tokens through bgpt_replicas_eval", "ids_equal_device_loop": same},
+          "e2e": {"value": n_streams * n_e2e / wall, "unit": UNIT, "h2d_bytes_per_step": seq * 4 * n_streams, "d2h_bytes_per_step": seq * n_streams * (8 * TOPK + 16),
+                  "sample": f"first {n_e2e} lock-step tokens through bgpt_replicas_eval_topk (top-40 pairs per stream)", "ids_equal_device_loop": same},
           "gpu_launches": None, "per_device_ms": [float(x) for x in dev_ms],
           "roofline": {"bound": "hbm", "kernel": "fused skinny-batch schedule (k_sk_mm / k_sk_attn / k_sk_ln / k_sk_gq), per GPU", "achieved": achieved,
                        "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": _traffic("streams_q5_1_x8")},

@@ -30,7 +30,7 @@ SYMBOLS = [
     "bgpt_cuda_model_create", "bgpt_cuda_upload_tensor", "bgpt_cuda_set_tables",
     "bgpt_host_build_tables", "bgpt_cuda_model_finalize", "bgpt_cuda_model_free",
     "bgpt_cuda_eval", "bgpt_cuda_eval_topk", "bgpt_cuda_set_chain", "bgpt_cuda_eval_device", "bgpt_cuda_logits_device", "bgpt_cuda_synchronize",
-    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_read_rows_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_set_tcw", "bgpt_cuda_set_f16_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_decode_greedy_streams",
+    "bgpt_cuda_decode_greedy", "bgpt_cuda_set_decode_path", "bgpt_cuda_get_decode_path", "bgpt_cuda_decode_kernel_generation", "bgpt_cuda_set_batch_path", "bgpt_cuda_get_batch_path", "bgpt_cuda_debug_read_buffer", "bgpt_cuda_debug_read_prof", "bgpt_cuda_debug_read_trace", "bgpt_cuda_debug_read_rows_trace", "bgpt_cuda_get_eval_path", "bgpt_cuda_set_tc_min_rows", "bgpt_cuda_set_tcx_min_rows", "bgpt_cuda_set_tcw", "bgpt_cuda_set_f16_tc_min_rows", "bgpt_cuda_op_quantize_weights", "bgpt_cuda_set_streams", "bgpt_cuda_eval_streams", "bgpt_cuda_eval_streams_topk", "bgpt_cuda_decode_greedy_streams",
     "bgpt_cuda_hparams", "bgpt_cuda_weight_bytes", "bgpt_cuda_launch_count",
     "bgpt_cuda_last_eval_ms", "bgpt_cuda_set_taps",
     "bgpt_cuda_op_mul_mat", "bgpt_cuda_op_mul_mat_tc", "bgpt_cuda_op_mul_mat_tcx", "bgpt_cuda_op_mul_mat_tcw", "bgpt_cuda_op_topk", "bgpt_cuda_op_quantize_act", "bgpt_cuda_op_norm",
@@ -94,6 +94,7 @@ def lib():
     L.bgpt_cuda_set_f16_tc_min_rows.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_set_streams.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_cuda_eval_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_void_p]
+    L.bgpt_cuda_eval_streams_topk.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bgpt_cuda_decode_greedy_streams.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int, _i32p, C.POINTER(C.c_float)]
     L.bgpt_cuda_hparams.restype = None
     L.bgpt_cuda_hparams.argtypes = [C.c_void_p, _i32p]
@@ -235,6 +236,17 @@ class Model:
         _check(lib().bgpt_cuda_eval_streams(self.h, t, len(t), n_past,
                                             out.ctypes.data if fetch else None), "eval_streams")
         return out
+
+    def eval_streams_topk(self, tokens: Sequence[int], n_past: int, k: int):
+        """(vals[S, k], ids[S, k], n_out[S], exact[S], full[S, n_vocab]): per stream the k largest logits, selected on the device; full[r] is
+        filled only for rows with exact[r] == 0"""
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        S = len(t)
+        vals = np.zeros((S, k), np.float32); ids = np.zeros((S, k), np.int32); n_out = np.zeros(S, np.int32); exact = np.zeros(S, np.int32)
+        full = np.zeros((S, self.n_vocab), np.float32)
+        _check(lib().bgpt_cuda_eval_streams_topk(self.h, t, S, n_past, k, vals.ctypes.data, ids.ctypes.data, n_out.ctypes.data, exact.ctypes.data,
+                                                 full.ctypes.data), "eval_streams_topk")
+        return vals, ids, n_out, exact, full
 
     def set_chain(self, on: int):
         """chained launches of eval_topk (the next position's kernel is queued while this call waits): 1 / 0, -1 = BGPT_CHAIN default (on)"""

@@ -139,6 +139,7 @@ struct bgpt_model {
     // generation-5 persistent kernel (bgpt_mega5.cuh): clusters of 4, one attention head per cluster, DSMEM exchange inside the head
     bool mega5_ok = false; M5Params m5{}; unsigned long long * d_xch5 = nullptr; unsigned int m5_tag = 0;
     size_t xch5_off = 0;
+    uint8_t * h_topk_rows = nullptr; uint8_t * h_topk_rows_dev = nullptr; uint8_t * d_topk_rows_scratch = nullptr; int topk_rows_cap = 0;   // bgpt_cuda_eval_streams_topk
     unsigned * d_tk_ticket = nullptr;                             // generation 5: ticket counter of the sampler tail
     // chained launches of bgpt_cuda_eval_topk (generation 5): the kernel of position p + 1 is queued while the call for p is still
     // waiting for its packet; its token arrives through `h_feed` (mapped pinned memory) when the next call names it
@@ -278,6 +279,8 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
     cudaFree(m->d_topk); cudaFree(m->d_topk_cand); cudaFree(m->d_topk_filt); if (m->h_topk) cudaFreeHost(m->h_topk);
     if (m->h_feed) cudaFreeHost(m->h_feed);
+    if (m->h_topk_rows) cudaFreeHost(m->h_topk_rows);
+    cudaFree(m->d_topk_rows_scratch);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -1529,20 +1532,22 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
 }
 
 // the large-vocabulary form of the device top-k (bgpt_topk.cuh): slices of 256 logits -> groups of 16 slices -> one CTA
-static size_t topk3_scratch_bytes(int n) {
+static size_t topk3_scratch_bytes(int n, int rows = 1) {
     const size_t n_slices = ((size_t) n + TOPK_SLICE - 1) / TOPK_SLICE, n_groups = (n_slices + TOPK_FAN - 1) / TOPK_FAN;
-    return (n_slices + n_groups) * (TOPK_MAXK + 1) * 8;
+    return (size_t) rows * (n_slices + n_groups) * (TOPK_MAXK + 1) * 8;
 }
-static int launch_topk3(cudaStream_t s, const float * logits, int n, int k, uint8_t * scratch, float * dv, int * di, int * dinfo, const int * errp, unsigned seq) {
+// rows > 1: `rows` consecutive logit rows (lock-step streams), one packet per row, pk_stride bytes apart, each with the serial `seq`
+static int launch_topk3(cudaStream_t s, const float * logits, int n, int k, uint8_t * scratch, float * dv, int * di, int * dinfo, const int * errp, unsigned seq,
+                        int rows = 1, int pk_stride = 0) {
     const int kc = k + 1;
     const int n_slices = (n + TOPK_SLICE - 1) / TOPK_SLICE, n_groups = (n_slices + TOPK_FAN - 1) / TOPK_FAN;
     if ((size_t) n_groups * kc > TOPK_RANK_MAX) return fail(BGPT_E_UNSUPPORTED, "top-k: vocabulary of %d entries is too large for k = %d", n, k);
-    float * v1 = (float *) scratch;                 int * i1 = (int *) (scratch + (size_t) n_slices * kc * 4);
-    uint8_t * l2 = scratch + (size_t) n_slices * kc * 8;
-    float * v2 = (float *) l2;                      int * i2 = (int *) (l2 + (size_t) n_groups * kc * 4);
-    k_topk_part<<<n_slices, TOPK_SLICE, 0, s>>>(logits, n, kc, v1, i1);
-    k_topk_rank<false><<<n_groups, TOPK_RANK_NT, 0, s>>>(v1, i1, n_slices * kc, TOPK_FAN * kc, kc, v2, i2, k, nullptr, nullptr, 0u, nullptr);
-    k_topk_rank<true><<<1, TOPK_RANK_NT, 0, s>>>(v2, i2, n_groups * kc, n_groups * kc, kc, dv, di, k, dinfo, errp, seq, nullptr);
+    float * v1 = (float *) scratch;                 int * i1 = (int *) (scratch + (size_t) rows * n_slices * kc * 4);
+    uint8_t * l2 = scratch + (size_t) rows * n_slices * kc * 8;
+    float * v2 = (float *) l2;                      int * i2 = (int *) (l2 + (size_t) rows * n_groups * kc * 4);
+    k_topk_part<<<dim3(n_slices, rows), TOPK_SLICE, 0, s>>>(logits, n, kc, v1, i1);
+    k_topk_rank<false><<<dim3(n_groups, rows), TOPK_RANK_NT, 0, s>>>(v1, i1, n_slices * kc, TOPK_FAN * kc, kc, v2, i2, k, nullptr, nullptr, 0u, nullptr);
+    k_topk_rank<true><<<dim3(1, rows), TOPK_RANK_NT, 0, s>>>(v2, i2, n_groups * kc, n_groups * kc, kc, dv, di, k, dinfo, errp, seq, nullptr, pk_stride);
     CK(cudaGetLastError());
     return BGPT_OK;
 }
@@ -1836,6 +1841,62 @@ extern "C" int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, in
 // Greedy decode of S lock-step streams entirely on the device (config 4 as a serving loop): every step is one forward pass
 // over the S rows (weights read once per step), S argmax blocks that feed the ids back, and a counter bump -- no host round trip
 // until the end.  ids_out (HOST) = [n_steps][n_streams].
+// bgpt_cuda_eval_streams + the K largest logits of EVERY stream's row (bgpt_cuda_eval_topk's selection, three launches over all rows):
+// vals / ids [n_streams][k], n_out / exact [n_streams] (HOST).  Rows whose selection is ambiguous (exact = 0) get their full logit
+// row in logits_fallback[row] ([n_streams][n_vocab], may be NULL).  8 K + 16 bytes per stream cross PCIe instead of 4 n_vocab.
+extern "C" int bgpt_cuda_eval_streams_topk(bgpt_model * m, const int32_t * tokens, int n_streams, int n_past, int k,
+                                           float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback) {
+    RET(check_eval_args(m, n_streams, n_past, 1));
+    if (!tokens || !vals || !ids || !n_out || !exact || k < 1) return fail(BGPT_E_ARG, "eval_streams_topk: bad arguments");
+    if (k > TOPK_MAXK || k > m->n_vocab) return fail(BGPT_E_ARG, "eval_streams_topk: k=%d exceeds %d", k, std::min(TOPK_MAXK, m->n_vocab));
+    if (n_streams > m->n_streams) return fail(BGPT_E_ARG, "eval_streams_topk: %d streams requested, %d allocated (bgpt_cuda_set_streams)", n_streams, m->n_streams);
+    CK(cudaSetDevice(m->device));
+    RET(ensure_arena(m, n_streams));
+    const size_t tk_bytes = (size_t) TOPK_MAXK * 8 + 16;
+    if (m->topk_rows_cap < n_streams) {
+        CK(cudaStreamSynchronize(m->stream));
+        if (m->h_topk_rows) cudaFreeHost(m->h_topk_rows);
+        cudaFree(m->d_topk_rows_scratch);
+        m->h_topk_rows = nullptr; m->d_topk_rows_scratch = nullptr; m->topk_rows_cap = 0; m->h_topk_rows_dev = nullptr;
+        CK(cudaHostAlloc(&m->h_topk_rows, (size_t) n_streams * tk_bytes, cudaHostAllocMapped));
+        memset(m->h_topk_rows, 0, (size_t) n_streams * tk_bytes);
+        void * dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, m->h_topk_rows, 0) != cudaSuccess || !dp) { cudaGetLastError(); return fail(BGPT_E_UNSUPPORTED, "eval_streams_topk: the device cannot address mapped host memory"); }
+        m->h_topk_rows_dev = (uint8_t *) dp;
+        CK(cudaMalloc(&m->d_topk_rows_scratch, topk3_scratch_bytes(m->n_vocab, n_streams)));
+        m->topk_rows_cap = n_streams;
+    }
+    cudaStream_t s = m->stream;
+    memcpy(m->h_tokens, tokens, (size_t) n_streams * sizeof(int));
+    m->h_st->n_past = n_past; m->h_st->step = 0;
+    CK(cudaEventRecord(m->ev0, s));
+    CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n_streams * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->st, m->h_st, sizeof(DevState), cudaMemcpyHostToDevice, s));
+    RET(forward(m, m->d_tokens, n_streams, 1));
+    const unsigned seq = ++m->topk_seq ? m->topk_seq : ++m->topk_seq;
+    uint8_t * pk = m->h_topk_rows_dev;
+    RET(launch_topk3(s, m->logits, m->n_vocab, k, m->d_topk_rows_scratch, (float *) (pk + 16), (int *) (pk + 16 + (size_t) k * 4), (int *) pk, nullptr, seq,
+                     n_streams, (int) tk_bytes));
+    m->launches += 3;
+    CK(cudaEventRecord(m->ev1, s));
+    m->last_ms_pending = true;
+    for (int r = 0; r < n_streams; r++) RET(wait_packet(m, (const volatile int *) (m->h_topk_rows + (size_t) r * tk_bytes), seq));
+    RET(check_rows_error(m));
+    bool need_full = false;
+    for (int r = 0; r < n_streams; r++) {
+        const uint8_t * hp = m->h_topk_rows + (size_t) r * tk_bytes;
+        const int * hinfo = (const int *) hp;
+        n_out[r] = hinfo[0]; exact[r] = hinfo[1];
+        memcpy(vals + (size_t) r * k, hp + 16, (size_t) hinfo[0] * 4);
+        memcpy(ids + (size_t) r * k, hp + 16 + (size_t) k * 4, (size_t) hinfo[0] * 4);
+        need_full = need_full || !hinfo[1];
+    }
+    if (need_full && logits_fallback)
+        for (int r = 0; r < n_streams; r++)
+            if (!exact[r]) CK(cudaMemcpy(logits_fallback + (size_t) r * m->n_vocab, m->logits + (size_t) r * m->n_vocab, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost));
+    return BGPT_OK;
+}
+
 extern "C" int bgpt_cuda_decode_greedy_streams(bgpt_model * m, const int32_t * first_tokens, int n_streams, int n_past, int n_steps,
                                                int32_t * ids_out, float * ms_out) {
     RET(check_eval_args(m, n_streams, n_past, n_steps));

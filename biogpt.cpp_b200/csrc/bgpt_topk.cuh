@@ -60,6 +60,8 @@ static __global__ void __launch_bounds__(TOPK_SLICE) k_topk_part(const float * _
                                                                   float * __restrict__ cand_val, int * __restrict__ cand_idx) {
     __shared__ __align__(16) uint32_t s_k[TOPK_SLICE];
     const int tid = threadIdx.x, i = blockIdx.x * TOPK_SLICE + tid;
+    logits += (size_t) blockIdx.y * n;                             // blockIdx.y: the logit row (lock-step streams), candidates per row
+    cand_val += (size_t) blockIdx.y * gridDim.x * kc; cand_idx += (size_t) blockIdx.y * gridDim.x * kc;
     const float f = i < n ? logits[i] : -INFINITY;
     const uint32_t u = i < n ? topk_key(f) : 0u;
     s_k[tid] = u;
@@ -84,10 +86,18 @@ template <bool FINAL>
 static __global__ void __launch_bounds__(TOPK_RANK_NT) k_topk_rank(const float * __restrict__ val, const int * __restrict__ idx, int n_c, int per, int kc,
                                                                     float * __restrict__ out_val, int * __restrict__ out_idx,
                                                                     int k, int * __restrict__ info, const int * __restrict__ err, unsigned seq,
-                                                                    int * __restrict__ n_c_dev) {
+                                                                    int * __restrict__ n_c_dev, int row_stride_bytes = 0) {
     __shared__ __align__(16) uint32_t s_k[TOPK_RANK_MAX + 4];
     __shared__ uint32_t s_sorted[TOPK_MAXK + 2];
     const int tid = threadIdx.x;
+    // blockIdx.y: the logit row (lock-step streams): n_c candidates per row in, gridDim.x * kc per row out (FINAL: one packet per row,
+    // row_stride_bytes apart, each with its own serial)
+    val += (size_t) blockIdx.y * n_c; idx += (size_t) blockIdx.y * n_c;
+    if (FINAL) {
+        out_val = (float *) ((uint8_t *) out_val + (size_t) blockIdx.y * row_stride_bytes);
+        out_idx = (int *) ((uint8_t *) out_idx + (size_t) blockIdx.y * row_stride_bytes);
+        info = (int *) ((uint8_t *) info + (size_t) blockIdx.y * row_stride_bytes);
+    } else { out_val += (size_t) blockIdx.y * gridDim.x * kc; out_idx += (size_t) blockIdx.y * gridDim.x * kc; }
     const int b0 = blockIdx.x * per;
     // FINAL after k_topk_filter: the number of candidates is the filter's counter; more than fit = a plateau of equal logits:
     // the packet says "not exact" and the caller takes the full-row path

@@ -20,7 +20,7 @@ extern "C" ggml_backend_t ggml_backend_b200_init(int device);
 namespace {
 thread_local std::string g_rep_err;
 
-enum Cmd { CMD_NONE = 0, CMD_LOAD, CMD_EVAL, CMD_DECODE, CMD_QUIT };
+enum Cmd { CMD_NONE = 0, CMD_LOAD, CMD_EVAL, CMD_EVAL_TOPK, CMD_DECODE, CMD_QUIT };
 
 struct Worker {
     int device = 0;
@@ -36,7 +36,8 @@ struct Worker {
     bool done = true;
     // arguments / results of the current command
     std::string path;
-    const int32_t * tokens = nullptr; int n_past = 0, n_steps = 0;
+    const int32_t * tokens = nullptr; int n_past = 0, n_steps = 0, top_k = 0; bool want_full = false;
+    std::vector<float> vals_local; std::vector<int32_t> tid_local; std::vector<int> nout_local, exact_local;
     std::vector<int32_t> tok_local, ids_local;
     std::vector<float> logits_local;
     int rc = 0; std::string err; float ms = 0.f;
@@ -69,6 +70,15 @@ void run(Worker * w) {
             for (int i = 0; i < nl; i++) w->tok_local[i] = w->tokens[w->streams[i]];
             w->logits_local.resize((size_t) nl * w->model.hparams.n_vocab);
             w->rc = bgpt_cuda_eval_streams(bgpt_host_engine_of(w->model), w->tok_local.data(), nl, w->n_past, w->logits_local.data());
+            if (w->rc) w->err = bgpt_cuda_last_error();
+        } else if (c == CMD_EVAL_TOPK && nl > 0) {
+            const int k = w->top_k;
+            w->tok_local.resize(nl);
+            for (int i = 0; i < nl; i++) w->tok_local[i] = w->tokens[w->streams[i]];
+            w->vals_local.resize((size_t) nl * k); w->tid_local.resize((size_t) nl * k); w->nout_local.resize(nl); w->exact_local.resize(nl);
+            if (w->want_full) w->logits_local.resize((size_t) nl * w->model.hparams.n_vocab);
+            w->rc = bgpt_cuda_eval_streams_topk(bgpt_host_engine_of(w->model), w->tok_local.data(), nl, w->n_past, k, w->vals_local.data(), w->tid_local.data(),
+                                                w->nout_local.data(), w->exact_local.data(), w->want_full ? w->logits_local.data() : nullptr);
             if (w->rc) w->err = bgpt_cuda_last_error();
         } else if (c == CMD_DECODE && nl > 0) {
             w->tok_local.resize(nl);
@@ -158,6 +168,24 @@ int bgpt_replicas_eval(bgpt_replicas * r, const int32_t * tokens, int n_past, fl
     for (auto & w : r->workers)
         for (size_t i = 0; i < w->streams.size(); i++)
             memcpy(logits_out + (size_t) w->streams[i] * r->n_vocab, w->logits_local.data() + i * r->n_vocab, (size_t) r->n_vocab * sizeof(float));
+    return 0;
+}
+
+int bgpt_replicas_eval_topk(bgpt_replicas * r, const int32_t * tokens, int n_past, int k, float * vals, int32_t * ids, int * n_out, int * exact,
+                            float * logits_fallback) {
+    if (!r || !tokens || !vals || !ids || !n_out || !exact || k < 1) { g_rep_err = "replicas_eval_topk: bad arguments"; return -1; }
+    for (auto & w : r->workers) { w->tokens = tokens; w->n_past = n_past; w->top_k = k; w->want_full = logits_fallback != nullptr; }
+    const int rc = r->all(CMD_EVAL_TOPK);
+    if (rc) return rc;
+    for (auto & w : r->workers)
+        for (size_t i = 0; i < w->streams.size(); i++) {
+            const size_t sg = (size_t) w->streams[i];
+            n_out[sg] = w->nout_local[i]; exact[sg] = w->exact_local[i];
+            memcpy(vals + sg * k, w->vals_local.data() + i * k, (size_t) k * sizeof(float));
+            memcpy(ids + sg * k, w->tid_local.data() + i * k, (size_t) k * sizeof(int32_t));
+            if (!w->exact_local[i] && logits_fallback)
+                memcpy(logits_fallback + sg * r->n_vocab, w->logits_local.data() + i * r->n_vocab, (size_t) r->n_vocab * sizeof(float));
+        }
     return 0;
 }
 

@@ -193,6 +193,12 @@ int bgpt_cuda_set_streams(bgpt_model * m, int n_streams);
  * on the HOST (may be NULL to leave them on the device). */
 int bgpt_cuda_eval_streams(bgpt_model * m, const int32_t * tokens, int n_streams, int n_past,
                            float * logits_out);
+/* bgpt_cuda_eval_streams + the K largest logits of every stream's row, selected on the device (bgpt_cuda_eval_topk's three-launch
+ * selection over all rows; biogpt.cpp:908-980): vals / ids [n_streams][k], n_out / exact [n_streams] (HOST).  A row with exact = 0
+ * (equal values make std::partial_sort's choice ambiguous) also gets its full logit row in logits_fallback[row] ([n_streams][n_vocab],
+ * may be NULL).  K <= 128. */
+int bgpt_cuda_eval_streams_topk(bgpt_model * m, const int32_t * tokens, int n_streams, int n_past, int k,
+                                float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback);
 
 /* greedy decode of n_streams lock-step streams entirely on the device: n_steps forward passes over the n_streams rows, per-row
  * argmax fed back on the device, one synchronisation at the end.  ids_out (HOST) = [n_steps][n_streams]; ms_out = device time. */

@@ -26,6 +26,12 @@ int  bgpt_replicas_n_vocab(const bgpt_replicas * r);
 int  bgpt_replicas_device_of(const bgpt_replicas * r, int stream);          /* s % n_devices */
 /* one lock-step token per stream at position n_past: tokens[n_streams] in, logits_out[n_streams][n_vocab] out (HOST buffers) */
 int  bgpt_replicas_eval(bgpt_replicas * r, const int32_t * tokens, int n_past, float * logits_out);
+/* the same step for a sampler: per stream the k largest (logit, id) pairs by logit descending, selected on the device
+ * (bgpt_cuda_eval_streams_topk; biogpt.cpp:908-980) -- vals / ids [n_streams][k], n_out / exact [n_streams].  A stream with exact = 0
+ * (equal logits make std::partial_sort's choice ambiguous) also gets its full row in logits_fallback[stream] ([n_streams][n_vocab],
+ * may be NULL).  8 k + 16 bytes per stream cross PCIe instead of 4 n_vocab. */
+int  bgpt_replicas_eval_topk(bgpt_replicas * r, const int32_t * tokens, int n_past, int k, float * vals, int32_t * ids, int * n_out, int * exact,
+                             float * logits_fallback);
 /* greedy continuation of every stream: first_tokens[n_streams] at n_past, n_steps tokens each; the devices run independently and
  * entirely device-side (argmax fed back on the GPU).  ids_out[n_steps][n_streams]; device_ms[n_devices] = CUDA-event time of each
  * device's loop (may be NULL).  Returns 0 or the first failing device's status. */

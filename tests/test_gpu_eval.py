@@ -93,6 +93,32 @@ def test_lockstep_streams_equal_single_stream(capi, zoo, ftype):
     M.close()
 
 
+@pytest.mark.parametrize("size,ftype,S", [("small", "q8_0", 5), ("base", "q5_1", 8), ("tiny", "f16", 3)])
+def test_lockstep_streams_topk_equals_full_rows(capi, zoo, size, ftype, S):
+    """bgpt_cuda_eval_streams_topk: per stream the k largest (logit, id) pairs by logit descending == the k best of the row
+    bgpt_cuda_eval_streams returns (ties are flagged exact = 0 and come with the full row)"""
+    hp = {"small": gf.SMALL, "base": gf.BASE, "tiny": gf.TINY}[size]
+    M = capi.Model.load(zoo.path(size, ftype))
+    M.set_streams(S)
+    steps = 4
+    seqs = [gf.synth_tokens(steps, hp.n_vocab, seed=300 + s) for s in range(S)]
+    for i in range(steps):
+        toks = np.array([seqs[s][i] for s in range(S)], np.int32)
+        full = M.eval_streams(toks, i).copy()
+        for k in (1, 40, 128):
+            if k > hp.n_vocab:
+                continue
+            vals, ids, n_out, exact, fb = M.eval_streams_topk(toks, i, k)
+            for s in range(S):
+                assert n_out[s] == k
+                order = np.argsort(-full[s], kind="stable")[:k]
+                if exact[s]:
+                    assert ids[s].tolist() == order.tolist() and np.array_equal(_bits(vals[s]), _bits(full[s][order])), (size, ftype, s, i, k)
+                else:
+                    assert np.array_equal(_bits(fb[s]), _bits(full[s])), (size, ftype, s, i, k)
+    M.close()
+
+
 @pytest.mark.parametrize("ftype", ["q4_0", "f16", "q8_0", "q5_1"])
 def test_base_shape_matches_oracle(checkers, capi, zoo, ftype):
     """true BioGPT-base shapes (d_model 1024, 24 layers, 16 heads, d_ff 4096, vocab 42384),

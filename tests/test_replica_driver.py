@@ -26,6 +26,7 @@ def rep():
     L.bgpt_replicas_device_of.argtypes = [C.c_void_p, C.c_int]
     L.bgpt_replicas_eval.argtypes = [C.c_void_p, _i32p, C.c_int, _f32p]
     L.bgpt_replicas_decode_greedy.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, _i32p, C.c_void_p]
+    L.bgpt_replicas_eval_topk.argtypes = [C.c_void_p, _i32p, C.c_int, C.c_int, _f32p, _i32p, _i32p, _i32p, C.c_void_p]
     L.bgpt_replicas_last_error.restype = C.c_char_p
     return L
 
@@ -67,6 +68,19 @@ def test_replica_streams_equal_single_stream(rep, capi, zoo, size, ftype, S):
         assert rep.bgpt_replicas_eval(r, toks, i, out) == 0, rep.bgpt_replicas_last_error()
         for s in range(S):
             assert np.array_equal(out[s].view(np.uint32), single[s][i].view(np.uint32)), (ftype, s, i)
+    # the sampler's form of the same step: per stream the 40 best (logit, id) pairs
+    K = 40
+    vals = np.zeros((S, K), np.float32); tids = np.zeros((S, K), np.int32); n_out = np.zeros(S, np.int32); exact = np.zeros(S, np.int32)
+    fb = np.zeros((S, hp.n_vocab), np.float32)
+    i = steps - 1
+    toks = np.array([seqs[s][i] for s in range(S)], np.int32)
+    assert rep.bgpt_replicas_eval_topk(r, toks, i, K, vals.reshape(-1), tids.reshape(-1), n_out, exact, fb.ctypes.data) == 0, rep.bgpt_replicas_last_error()
+    for s in range(S):
+        order = np.argsort(-single[s][i], kind="stable")[:K]
+        if exact[s]:
+            assert n_out[s] == K and tids[s].tolist() == order.tolist() and np.array_equal(vals[s].view(np.uint32), single[s][i][order].view(np.uint32)), (ftype, s)
+        else:
+            assert np.array_equal(fb[s].view(np.uint32), single[s][i].view(np.uint32)), (ftype, s)
     ids = np.zeros((steps, S), np.int32)
     ms = np.zeros(G, np.float32)
     first = np.array([seqs[s][0] for s in range(S)], np.int32)
