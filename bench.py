@@ -303,6 +303,28 @@ def side_configs(capi, device: int, seq: int):
                      "decode_kernel_generation": M.decode_generation}
         M.close()
     out["format_sweep_n_past_511"] = {"workload": "single-token decode at n_past ~511, all six formats (BASELINE.json configs[4])", "formats": sweep}
+    # ---- the reference's UNMODIFIED front end loop (examples/main/main.cpp:93-151): biogpt_eval -- the whole logit row returns to the
+    #      host -- then biogpt_sample_top_k_top_p on it (top_k 40, top_p 0.9, temp 0.8 ~ the reference's defaults), one token at a
+    #      time, through the C++ API of libbiogpt_b200.so; wall clock over the whole context
+    try:
+        import ctypes as C
+        H = C.CDLL(os.path.join(ROOT, "biogpt.cpp_b200", "host", "libbiogpt_b200.so"))
+        H.bgpt_host_open.restype = C.c_void_p
+        H.bgpt_host_open.argtypes = [C.c_char_p, C.c_int]
+        H.bgpt_host_close.argtypes = [C.c_void_p]
+        H.bgpt_host_main_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint32, C.c_void_p, C.POINTER(C.c_double)]
+        os.environ["BIOGPT_CUDA_DEVICE"] = str(device)
+        hs = H.bgpt_host_open(model_path("q4_0").encode(), 8)
+        ids_m = np.zeros(seq, np.int32); ws = C.c_double(0)
+        H.bgpt_host_main_loop(hs, 2, 0, min(seq, 64), 40, 0.9, 0.8, 1, ids_m.ctypes.data, C.byref(ws))
+        rc = H.bgpt_host_main_loop(hs, 2, 0, seq, 40, 0.9, 0.8, 1, ids_m.ctypes.data, C.byref(ws))
+        H.bgpt_host_close(hs)
+        out["unmodified_main_loop_q4_0"] = {
+            "workload": f"BioGPT-base Q4_0, the loop of examples/main/main.cpp:93-151 as written (biogpt_eval with the full logit row to the host + "
+                        f"biogpt_sample_top_k_top_p, top_k 40 / top_p 0.9 / temp 0.8), seq 1->{seq}",
+            "rc": rc, "tokens_per_s": seq / ws.value, "us_per_token": ws.value / seq * 1e6, "d2h_bytes_per_token": 42384 * 4}
+    except Exception as e:
+        out["unmodified_main_loop_q4_0"] = {"error": repr(e)}
     # ---- the tcgen05 prompt path: the whole context as ONE un-masked eval (n_batch = seq).  Quantised: bit-exact k_tcw_exact
     #      (warp-specialised, TMA-fed; csrc/bgpt_tcw.cuh); F16: the exact-order SIMT kernels by default, k_tcw_f16 when opted in.
     big = {}

@@ -21,6 +21,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 #include <regex>
 #include <sstream>
 #include <stdexcept>
@@ -388,15 +391,65 @@ static biogpt_vocab::id draw_from_sorted(std::vector<std::pair<double, biogpt_vo
     return cand[dist(rng)].second;
 }
 
-biogpt_vocab::id biogpt_sample_top_k_top_p(const biogpt_vocab & vocab, const float * logits, int top_k, double top_p, double temp, std::mt19937 & rng) {
-    const int n_logits = (int) vocab.id_to_token.size();
-    top_k = std::max(1, std::min(top_k, n_logits));
+// The reference's selection, as written: n_vocab (logit / temp, id) pairs in doubles, std::partial_sort (biogpt.cpp:908-940).  210-380 us
+// for 42384 logits on the bench host -- as long as the whole forward pass on the GPU.
+static biogpt_vocab::id sample_reference_order(int n_logits, const float * logits, int top_k, double top_p, double temp, std::mt19937 & rng) {
     std::vector<std::pair<double, biogpt_vocab::id>> cand;
     cand.reserve(n_logits);
     const double inv_temp = 1.0 / temp;
     for (int i = 0; i < n_logits; i++) cand.emplace_back(logits[i] * inv_temp, i);
     std::partial_sort(cand.begin(), cand.begin() + top_k, cand.end(),
                       [](const std::pair<double, biogpt_vocab::id> & a, const std::pair<double, biogpt_vocab::id> & b) { return a.first > b.first; });
+    cand.resize(top_k);
+    return draw_from_sorted(cand, top_k, top_p, rng);
+}
+
+// The same pairs without sorting the vocabulary.  For temp > 0, logit -> logit * (1 / temp) in double is strictly increasing on
+// floats (a float's 24 bits times a double keeps neighbours apart), so the top_k pairs by scaled value are the top_k logits: one
+// pass keeps the top_k + 1 largest floats in a min-heap -- an AVX2 compare of 8 logits against the heap's minimum rejects almost
+// every group at once -- and only the survivors are scaled.  std::partial_sort leaves the choice and order among EQUAL values
+// unspecified: if two neighbours among the top_k + 1 scaled values are equal (or a logit is NaN, or temp is not a positive finite
+// number), the reference's own code above decides, so the drawn id is the reference's in every case
+// (tests/test_host_lib.py: test_sampler_draw_identical_to_reference, test_sampler_fast_selection_*).  ~10 us instead of 210-380.
+biogpt_vocab::id biogpt_sample_top_k_top_p(const biogpt_vocab & vocab, const float * logits, int top_k, double top_p, double temp, std::mt19937 & rng) {
+    const int n_logits = (int) vocab.id_to_token.size();
+    top_k = std::max(1, std::min(top_k, n_logits));
+    const int kc = top_k + 1;
+    if (!(temp > 0.0) || !std::isfinite(temp) || kc > 512 || kc > n_logits) return sample_reference_order(n_logits, logits, top_k, top_p, temp, rng);
+    struct Ent { float v; int i; };
+    Ent heap[512];
+    int hn = 0;
+    auto cmp = [](const Ent & a, const Ent & b) { return a.v > b.v; };          // std::*_heap with this comparator: heap[0] is the minimum
+    bool has_nan = false;
+    int i = 0;
+    for (; i < n_logits && hn < kc; i++) {
+        has_nan = has_nan || logits[i] != logits[i];
+        heap[hn++] = Ent{ logits[i], i };
+        if (hn == kc) std::make_heap(heap, heap + hn, cmp);
+    }
+    auto offer = [&](int j) {
+        const float x = logits[j];
+        if (x > heap[0].v) { std::pop_heap(heap, heap + kc, cmp); heap[kc - 1] = Ent{ x, j }; std::push_heap(heap, heap + kc, cmp); }
+    };
+#if defined(__AVX2__)
+    __m256 unord = _mm256_setzero_ps();
+    for (; i + 8 <= n_logits; i += 8) {
+        const __m256 x = _mm256_loadu_ps(logits + i);
+        unord = _mm256_or_ps(unord, _mm256_cmp_ps(x, x, _CMP_UNORD_Q));
+        int m = _mm256_movemask_ps(_mm256_cmp_ps(x, _mm256_set1_ps(heap[0].v), _CMP_GT_OQ));
+        while (m) { const int b = __builtin_ctz(m); m &= m - 1; offer(i + b); }
+    }
+    has_nan = has_nan || _mm256_movemask_ps(unord) != 0;
+#endif
+    for (; i < n_logits; i++) { has_nan = has_nan || logits[i] != logits[i]; offer(i); }
+    if (has_nan) return sample_reference_order(n_logits, logits, top_k, top_p, temp, rng);
+    std::sort(heap, heap + kc, [](const Ent & a, const Ent & b) { return a.v > b.v; });
+    const double inv_temp = 1.0 / temp;
+    std::vector<std::pair<double, biogpt_vocab::id>> cand;
+    cand.reserve(kc);
+    for (int j = 0; j < kc; j++) cand.emplace_back(heap[j].v * inv_temp, heap[j].i);
+    for (int j = 0; j + 1 < kc; j++)
+        if (!(cand[j].first > cand[j + 1].first)) return sample_reference_order(n_logits, logits, top_k, top_p, temp, rng);
     cand.resize(top_k);
     return draw_from_sorted(cand, top_k, top_p, rng);
 }

@@ -111,6 +111,24 @@ int bgpt_host_sampling_loop(bgpt_model * engine, int first_token, int n_past, in
     if (wall_s) *wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }
+// examples/main/main.cpp:93-151 as written -- biogpt_eval (the whole logit row comes back to the host), then biogpt_sample_top_k_top_p
+// on it -- one token at a time, for bench.py's "unmodified front end" line.  ids_out[n_steps]; *wall_s = time inside the loop.
+int bgpt_host_main_loop(void * h, int first_token, int n_past, int n_steps, int top_k, double top_p, double temp, uint32_t seed,
+                        int32_t * ids_out, double * wall_s) {
+    Session * s = (Session *) h;
+    if (!s || !ids_out || n_steps < 1) return -1;
+    std::mt19937 rng(seed);
+    token_sequence embd(1, first_token);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n_steps; i++) {
+        if (!biogpt_eval(s->model, embd, s->logits, s->allocr, n_past + i, 4)) return 1;
+        const biogpt_vocab::id id = biogpt_sample_top_k_top_p(s->vocab, s->logits.data() + (s->logits.size() - s->model.hparams.n_vocab), top_k, top_p, temp, rng);
+        ids_out[i] = id;
+        embd[0] = id;
+    }
+    if (wall_s) *wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
 void bgpt_host_close(void * h) {
     Session * s = (Session *) h;
     if (!s) return;

@@ -90,6 +90,39 @@ def test_sampler_draw_identical_to_reference(host, checkers, zoo):
     R.close()
 
 
+def test_sampler_fast_selection_equals_reference_on_ties_and_edges(host, checkers, zoo):
+    """biogpt_sample_top_k_top_p selects the top_k + 1 largest logits in one pass instead of sorting the vocabulary; wherever
+    std::partial_sort's outcome is not determined by the values alone (equal logits inside or at the edge of the top_k), for NaNs,
+    for temperatures that collapse neighbours, and for top_k beyond the fast path, the reference's own code must decide: the drawn
+    id equals the reference's for every case (biogpt.cpp:908-980)"""
+    if not checkers.have_ref():
+        pytest.skip("reference build not available")
+    R = checkers.Ref(zoo.path("tiny", "f32"))
+    n = R.n_vocab
+    rng = np.random.default_rng(5)
+    cases = []
+    base = (rng.standard_normal(n) * 2).astype(np.float32)
+    order = np.argsort(-base)
+    x = base.copy(); x[order[3]] = x[order[2]]; cases.append(("tie inside the top", x))
+    x = base.copy(); x[order[40]] = x[order[39]]; cases.append(("tie at the edge of top 40", x))
+    x = base.copy(); x[order[41]] = x[order[40]]; cases.append(("tie just outside", x))
+    x = base.copy(); x[order[5]] = x[order[4]]; x[order[6]] = x[order[4]]; cases.append(("triple", x))
+    cases.append(("all equal", np.zeros(n, np.float32)))
+    cases.append(("plateau of the maximum", np.where(np.arange(n) % 3 == 0, np.float32(1.5), base.clip(max=1.0)).astype(np.float32)))
+    x = base.copy(); x[order[0]] = np.inf; cases.append(("+inf", x))
+    x = base.copy(); x[order[10]] = -np.inf; x[7] = -np.inf; cases.append(("-inf", x))
+    cases.append(("descending", np.linspace(5, -5, n).astype(np.float32)))
+    cases.append(("ascending", np.linspace(-5, 5, n).astype(np.float32)))
+    cases.append(("tiny values", (base * 1e-38).astype(np.float32)))
+    for name, logits in cases:
+        for top_k, top_p, temp in ((1, 1.0, 1.0), (5, 0.5, 1.3), (40, 0.9, 0.9), (40, 1.0, 1e300), (40, 0.9, 1e-300), (127, 0.95, 0.7), (n - 1, 1.0, 0.7), (n, 1.0, 0.7)):
+            for seed in (0, 1, 2):
+                want = R.sample(logits, top_k, top_p, temp, seed)
+                got = host.bgpt_host_sample(logits.ctypes.data, n, top_k, top_p, temp, seed)
+                assert got == want, (name, top_k, top_p, temp, seed)
+    R.close()
+
+
 @pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_reference_quantize_frontend_on_our_library(zoo, model_dir, ftype):
     """the reference's UNMODIFIED examples/quantize/quantize.cpp, linked against libbiogpt_b200.so,

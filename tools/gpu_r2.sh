@@ -61,6 +61,15 @@ ncutcx)
   tail -3 $OUT/gemm_tcx_full.log ;;
 e2esweep)
   for ft in q4_0 q4_1 q5_0 q5_1 q8_0 f16; do for cfg in "1 1" "0 1" "0 0"; do set -- $cfg; echo "$ft chain=$1 tail=$2"; BGPT_CHAIN=$1 BGPT_TOPK_TAIL=$2 timeout 120 python tools/e2e_bench.py --ftype $ft --steps 256 --n-past 384 2>&1 | grep "C++ loop"; done; done | tee $OUT/e2esweep.log ;;
+ncutk)
+  # the sampler's instantiation of the decode kernel (k_mega5<.., TK>): launch list of the C++ sampling loop, then --set full of one launch
+  BGPT_CHAIN=0 BGPT_M5_COOP=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 520 -c 60 --csv --log-file $OUT/launches_e2e.csv \
+      python tools/e2e_bench.py --ftype q4_0 --steps 8 --n-past 511 > $OUT/launches_e2e.log 2>&1; echo "launches rc=$?"
+  BGPT_CHAIN=0 BGPT_M5_COOP=0 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:ELb0ELb1EEv8M5Params -s 6 -c 1 -f -o $OUT/mega5tk_full \
+      python tools/e2e_bench.py --ftype q4_0 --steps 8 --n-past 511 > $OUT/mega5tk_full.log 2>&1; echo "full rc=$?"
+  ncu -i $OUT/mega5tk_full.ncu-rep --page raw --csv > $OUT/mega5tk_full_raw.csv 2>/dev/null
+  rm -f $OUT/mega5tk_full.ncu-rep
+  tail -3 $OUT/mega5tk_full.log; head -5 $OUT/launches_e2e.csv | cut -c1-300 ;;
 fmtsweep)
   for ft in q4_0 q4_1 q5_0 q5_1 q8_0 f16; do timeout 120 python tools/profile_decode.py --ftype $ft --n-past 511 --steps 64 --warm 4 2>&1 | grep "us/token"; done | tee $OUT/fmtsweep.log ;;
 smoke)
