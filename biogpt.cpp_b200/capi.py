@@ -242,8 +242,11 @@ class Model:
         filled only for rows with exact[r] == 0"""
         t = np.ascontiguousarray(tokens, dtype=np.int32)
         S = len(t)
-        vals = np.zeros((S, k), np.float32); ids = np.zeros((S, k), np.int32); n_out = np.zeros(S, np.int32); exact = np.zeros(S, np.int32)
-        full = np.zeros((S, self.n_vocab), np.float32)
+        st = getattr(self, "_stopk_state", None)
+        if st is None or st[0] != (S, k):               # the output buffers are reused from call to call (overwritten by the next call)
+            st = self._stopk_state = ((S, k), np.zeros((S, k), np.float32), np.zeros((S, k), np.int32), np.zeros(S, np.int32), np.zeros(S, np.int32),
+                                      np.zeros((S, self.n_vocab), np.float32))
+        _, vals, ids, n_out, exact, full = st
         _check(lib().bgpt_cuda_eval_streams_topk(self.h, t, S, n_past, k, vals.ctypes.data, ids.ctypes.data, n_out.ctypes.data, exact.ctypes.data,
                                                  full.ctypes.data), "eval_streams_topk")
         return vals, ids, n_out, exact, full
