@@ -17,7 +17,7 @@ import numpy as np
 from . import ggml_file as gf
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libbgpt_cuda.so")
+LIB_PATH = os.environ.get("BGPT_CUDA_LIB") or os.path.join(HERE, "csrc", "libbgpt_cuda.so")   # BGPT_CUDA_LIB: an alternative build, for A/B timing
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")

@@ -1249,12 +1249,13 @@ static int mega5_setup(bgpt_model * m, const cudaDeviceProp & prop) {
     const int lim = (int) prop.sharedMemPerBlockOptin - 2048;             // static shared memory + margin
     auto slot_for = [&](int lmrt) { return al(std::max(std::max(32 * sd, 8 * sf), std::max(3 * M5_HR, lmrt) * sd)); };
     // preference: 4 ring slots; then the fc2 scratch (relay otherwise); then 64-row lm_head tiles
-    bool use_scratch = !f16 && !(getenv("BGPT_M5_FC2") && atoi(getenv("BGPT_M5_FC2")) == 0);
+    const bool has_relay = M5_HAS_FC2_RELAY(m->wtype);            // the relay form of fc2 is built into this format's kernel (bgpt_mega5.cuh)
+    bool use_scratch = !f16 && !(has_relay && getenv("BGPT_M5_FC2") && atoi(getenv("BGPT_M5_FC2")) == 0);
     P.nslot = M4_NSLOT; P.lmrt = 64;
     auto total = [&]() { return P.nslot * slot_for(P.lmrt) + base + (use_scratch ? scratch : 0); };
     if (total() > lim) P.lmrt = 32;
     if (total() > lim && P.nslot > 3) P.nslot = 3;
-    if (total() > lim) use_scratch = false;
+    if (total() > lim && (has_relay || f16)) use_scratch = false;      // (without the relay form the scratch must fit)
     while (P.nslot > 2 && total() > lim) P.nslot--;
     if (total() > lim) return BGPT_OK;
     if (getenv("BGPT_M5_LMRT")) { const int v = atoi(getenv("BGPT_M5_LMRT")); if ((v == 32 || v == 64) && v <= P.lmrt) P.lmrt = v; }

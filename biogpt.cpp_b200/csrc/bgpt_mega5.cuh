@@ -64,6 +64,15 @@
 #define M5_TOK_TIMEOUT (-3)    // no token arrived within feed_limit cycles
 #define M5_MAXL 24
 #define M5_PK 12              // trace stamps per (layer, stage)
+// The relay form of fc2 (no shared-memory scratch: BGPT_M5_FC2=0) is ~10 KB of code in the middle of the layer loop that never runs on
+// a B200 (the scratch fits).  Built without it the kernels with the most code gain (Q4_1 461 -> 442, Q5_1 463 -> 452 us per token at
+// n_past 511), Q5_0 / Q8_0 do not move, and Q4_0 LOSES 2 % (421 -> 430: these instantiations sit at the register budget and every
+// rebuild re-rolls ptxas' register assignment, i.e. operand bank conflicts; A/B on one box, profiles/README.md).  So: kept for Q4_0
+// only; where it is not built, bgpt_cuda.cu requires the scratch to fit.  -DM5_FC2_RELAY=1 keeps it everywhere.
+#ifndef M5_FC2_RELAY
+#define M5_FC2_RELAY 0
+#endif
+#define M5_HAS_FC2_RELAY(fmt) (M5_FC2_RELAY || (fmt) == BG_Q4_0)
 
 struct M5Params {
     MegaParams b;
@@ -853,7 +862,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             if (4 * warp < rt) dot = m5_row_dot<FMT, M5_D / 128>(wt + (size_t) min(myrow, rt - 1) * D.stride, rec, D);
         } else if (kind == 1) {
             if (warp < 8) dot = m5_row_dot_relay<FMT, M5_D / 128, true>(wt + (size_t) warp * D.stride, rec, D);
-        } else if (P.sm_p < 0) {
+        } else if (M5_HAS_FC2_RELAY(FMT) && P.sm_p < 0) {
             if (warp < 8) dot = m5_row_dot_relay<FMT, M5_FF / 128, false>(wt + (size_t) warp * D.stride, rec, D);
             else if (HASMF) dot = m5_summs_chain(wt + (size_t) (warp - 8) * D.stride, rec, D);     // the row's summs chain, on an idle warp
         } else {
@@ -934,7 +943,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
             }
         } else if (kind == 1 || kind == 3) {
             // gather the 8 rows; warp 0 finishes them (bias, residual) and writes 8 rows x 8 replicas as consecutive words
-            const bool two_phase = kind == 3 && P.sm_p >= 0;
+            const bool two_phase = !ISF && kind == 3 && (!M5_HAS_FC2_RELAY(FMT) || P.sm_p >= 0);
             if (two_phase) { if (warp < 2 && (lane & 7) == 0) s_blk[4 * warp + (lane >> 3)] = dot; }
             else if (warp < 8) { if (lane == 24) s_blk[warp] = dot; }
             else if (kind == 3 && HASMF && lane == 0) s_blk[warp] = dot;
