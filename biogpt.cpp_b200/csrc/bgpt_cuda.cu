@@ -1629,11 +1629,10 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     cudaStream_t s = m->stream;
     const bool mega = n == 1 && use_mega(m);
     // generation 5 selects inside the forward kernel (the CTA that finishes last: bgpt_topk.cuh, topk_tail): no further launch.
-    // BGPT_TOPK_TAIL: 0 never, 2 always, default = where it measured faster -- every format but Q5_0, whose instantiation WITH the tail
-    // and the token feed (k_mega5<.., TK = true>) comes out of ptxas 100 us per token slower than the one without, whatever is moved out
-    // of line (546 against 444 us per token through this call at n_past 384..639; profiles/README.md)
-    static const int tail_mode = getenv("BGPT_TOPK_TAIL") ? atoi(getenv("BGPT_TOPK_TAIL")) : 1;
-    const bool use_tail = tail_mode == 2 || (tail_mode == 1 && m->wtype != BG_Q5_0);
+    // BGPT_TOPK_TAIL=0: two launches behind the decode kernel instead.  (The quantised instantiations sit at the register budget and
+    // their speed moves with every rebuild -- one build of k_mega5<Q5_0, .., TK> ran 100 us per token slower than its twin without
+    // the tail; the `e2esweep` / `fmtsweep` stages of tools/gpu_r2.sh check all twelve after a change.)
+    static const bool use_tail = !(getenv("BGPT_TOPK_TAIL") && atoi(getenv("BGPT_TOPK_TAIL")) == 0);
     const bool tail = mega && use_tail && mega_generation(m) == 5 && m->mega5_ok && k <= M5_NC && m->n_vocab >= M5_NC;
     const bool chain = tail && m->h_topk_dev && m->h_feed_dev && chain_enabled(m);
     auto packet = [&](unsigned serial, bool host_view) { return (host_view || !m->h_topk_dev ? (host_view ? m->h_topk : m->d_topk) : m->h_topk_dev) + (serial & 1u) * tk_bytes; };

@@ -500,8 +500,9 @@ static __device__ __noinline__ void m5_sampler_tail(unsigned * ticket, const flo
 #define M5PROF(ph, k) do { if (PROF && P.trace && threadIdx.x == 0) P.trace[(size_t) blockIdx.x * P.prof_n + (l * 5 + (ph)) * M5_PK + (k)] = clock64(); } while (0)
 
 // TK: the instantiation bgpt_cuda_eval_topk launches -- token feed (use_cand == 3) and the sampler tail.  A template flag, not a
-// run-time one: the quantised instantiations sit at the 128-register budget, and the mere presence of that code reshuffles the layer
-// loop's allocation (Q5_0: 434 -> 547 us per token, Q4_1 + 3.6 %, Q4_0 + 1.3 %); the decode loop keeps the instantiation without it.
+// run-time one: the quantised instantiations sit at the 128-register budget, and the mere presence of that code re-rolls ptxas'
+// allocation of the layer loop (one build: Q5_0 434 -> 547 us per token, Q4_1 + 3.6 %, Q4_0 + 1.3 %; the next build, with 10 KB of
+// unrelated code removed, had the Q5_0 twin back at 438).  The decode loop keeps the instantiation without it.
 template <int FMT, bool PROF, bool TK>
 __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Params P) {
     const MegaParams & p = P.b;

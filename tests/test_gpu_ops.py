@@ -277,20 +277,24 @@ def test_device_topk_selects_what_partial_sort_selects(capi, zoo):
 
 
 def test_device_topk_after_the_persistent_kernel_full_vocabulary(capi, zoo):
-    """the full-size vocabulary (42384): after a single-token step on the persistent decode kernel the selection is two launches --
-    the kernel's 128 per-CTA maxima give a threshold, k_topk_filter collects the logits above it, one CTA ranks them -- and after
-    a prompt batch three (slices of 256 -> groups of 16 slices -> one CTA); both must return the K best of the full row"""
+    """the full-size vocabulary (42384): a single-token step on the generation-5 kernel selects in the kernel's tail (the per-CTA maxima
+    give a threshold, the last CTA collects the logits above it and ranks them), on generation 4 in two launches behind the kernel
+    (k_topk_filter + one ranking CTA), a prompt batch in three (slices of 256 -> groups of 16 slices -> one CTA); all must return the
+    K best of the full row"""
     M = capi.Model.load(zoo.path("base", "q4_0"))
     toks = gf.synth_tokens(12, gf.BASE.n_vocab, seed=31)
-    for t, n_past in ((toks[:8], 0), (toks[8:9], 8), (toks[9:10], 9), (toks[10:11], 10)):
-        full = M.eval(t, n_past).copy()
-        for k in (1, 5, 40, 128):
-            vals, ids, exact, fb = M.eval_topk(t, n_past, k)
-            order = np.argsort(-full, kind="stable")[:k]
-            if exact:
-                assert ids.tolist() == order.tolist() and np.array_equal(vals.view(np.uint32), full[order].view(np.uint32)), (n_past, k)
-            else:
-                assert fb is not None and np.array_equal(fb.view(np.uint32), full.view(np.uint32))
+    # decode path 1: generation 5 -- the selection is the kernel's tail (topk_tail); 3: generation 4 -- filter + ranking launches
+    for path in (1, 3):
+        M.set_decode_path(path)
+        for t, n_past in ((toks[:8], 0), (toks[8:9], 8), (toks[9:10], 9), (toks[10:11], 10)):
+            full = M.eval(t, n_past).copy()
+            for k in (1, 5, 40, 128):
+                vals, ids, exact, fb = M.eval_topk(t, n_past, k)
+                order = np.argsort(-full, kind="stable")[:k]
+                if exact:
+                    assert ids.tolist() == order.tolist() and np.array_equal(vals.view(np.uint32), full[order].view(np.uint32)), (path, n_past, k)
+                else:
+                    assert fb is not None and np.array_equal(fb.view(np.uint32), full.view(np.uint32))
     M.close()
 
 

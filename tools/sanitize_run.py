@@ -48,8 +48,9 @@ for name, hp, ft in jobs:
     for p2 in (pos, pos + 1, pos + 2, pos):
         M.eval_topk(toks[p2:p2 + 1], p2, 40)
     M.set_chain(0); M.eval_topk(toks[pos:pos + 1], pos, 5); M.set_chain(-1)
+    if name in ("narrow", "wide"):
+        M.set_decode_path(3); M.eval_topk(toks[pos:pos + 1], pos, 40); M.set_decode_path(1)     # generation 4: selection in launches behind the kernel
     if not quick:
-        # (Q5_0 models: selection AFTER the persistent kernel -- threshold filter + ranking CTA for a vocabulary >= 4096)
         M.eval_topk(toks[pos:pos + 4], pos, 40)                # after a prompt batch: slices -> groups -> one CTA
         M.set_streams(3)
         M.eval_streams(toks[:3], 0)
