@@ -61,6 +61,31 @@ def test_mul_mat(checkers, capi, name, shape):
     assert np.array_equal(_bits(got), _bits(want)), _report(f"{name} {shape}", got, want)
 
 
+def test_norm_rows_where_the_double_sums_round(checkers, capi):
+    """LayerNorm's two sums run in double (ggml.c:11403-11420), sequentially in the reference and as a tree here.  A double sum of floats
+    is EXACT -- hence independent of the order -- while every element is within 2^29 of the running sum's magnitude, which covers any
+    activation row of the model; these rows leave that domain on purpose (20-40 binades of dynamic range, heavy cancellation, one
+    dominant element), so the individual double additions do round and the two orders can differ in the last bits of the double.  The
+    float results must still agree: the difference only shows if it moves the double across a float rounding boundary."""
+    rng = np.random.default_rng(77)
+    nc = 1024
+    rows = []
+    for e_lo in (-20, -30, -40):
+        rows.append((rng.standard_normal(nc) * np.exp2(rng.uniform(e_lo, 4, nc))).astype(np.float32))
+    big = (rng.standard_normal(nc) * 1e6).astype(np.float32)
+    rows.append(np.concatenate([big[:nc // 2], -big[:nc // 2]]) + (rng.standard_normal(nc) * 1e-3).astype(np.float32))   # cancellation
+    one = (rng.standard_normal(nc) * 1e-4).astype(np.float32); one[517] = 3e7; rows.append(one)                        # one dominant element
+    rows.append((rng.standard_normal(nc) * np.exp2(rng.integers(-60, 10, nc).astype(np.float64))).astype(np.float32))
+    x = np.stack(rows).astype(np.float32)
+    want = np.zeros_like(x)
+    for r in range(len(rows)):
+        y = np.zeros(nc, np.float32)
+        checkers.oracle_lib().bo_norm(x[r], y, nc, 1e-5)
+        want[r] = y
+    got = capi.op_norm(x, None, None, 1e-5)
+    assert np.array_equal(_bits(got), _bits(want)), _report("norm, rounding double sums", got, want)
+
+
 @pytest.mark.parametrize("nc", [64, 256, 1024, 4096])
 def test_norm(checkers, capi, nc):
     rng = np.random.default_rng(nc)
