@@ -1522,11 +1522,14 @@ extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int
         RET(forward(m, m->d_tokens, n, 0));
     }
     CK(cudaMemcpyAsync(m->h_logits, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost, s));
+    // the generation-5 kernel's watchdog code rides behind the logits (pinned word, same stream): no second, synchronous copy per token
+    const bool m5 = n == 1 && use_mega(m) && mega_generation(m) == 5 && m->mega5_ok;
+    if (m5) CK(cudaMemcpyAsync(m->h_err5, m->d_err5, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(m->ev1, s));
     CK(cudaStreamSynchronize(s));
     RET(check_rows_error(m));
     CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
-    if (n == 1 && use_mega(m) && mega_generation(m) == 5) RET(check_mega5_error(m));
+    if (m5 && *m->h_err5 != 0) RET(check_mega5_error(m));
     memcpy(logits_out, m->h_logits, (size_t) m->n_vocab * 4);
     RET(fetch_taps(m, n));
     return BGPT_OK;

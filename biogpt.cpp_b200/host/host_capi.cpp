@@ -26,6 +26,7 @@ struct Session { biogpt_model model; biogpt_vocab vocab; ggml_allocr * allocr = 
 }
 
 void bgpt_text_class_mask(int which, uint32_t out[8]);
+biogpt_vocab::id bgpt_sample_reference_order(int n_logits, const float * logits, int top_k, double top_p, double temp, std::mt19937 & rng);
 
 extern "C" {
 
@@ -55,6 +56,15 @@ int bgpt_host_sample(const float * logits, int n_vocab, int top_k, double top_p,
     for (int i = 0; i < n_vocab; i++) vocab.id_to_token[i] = "";
     std::mt19937 rng(seed);
     return biogpt_sample_top_k_top_p(vocab, logits, top_k, top_p, temp, rng);
+}
+
+// which = 0: biogpt_sample_top_k_top_p (one-pass selection); 1: the reference's partial_sort over the whole vocabulary.  vocab_cache: the
+// id -> token map of n_vocab empty strings is built once per size (the sampler only asks for its size)
+int bgpt_host_sample_n(const float * logits, int n_vocab, int top_k, double top_p, double temp, uint32_t seed, int which) {
+    static biogpt_vocab vocab;
+    if ((int) vocab.id_to_token.size() != n_vocab) { vocab.id_to_token.clear(); for (int i = 0; i < n_vocab; i++) vocab.id_to_token[i] = ""; }
+    std::mt19937 rng(seed);
+    return which ? bgpt_sample_reference_order(n_vocab, logits, top_k, top_p, temp, rng) : biogpt_sample_top_k_top_p(vocab, logits, top_k, top_p, temp, rng);
 }
 
 // the flow of examples/main/main.cpp:29-70: load, measure pass, allocator

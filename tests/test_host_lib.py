@@ -123,6 +123,32 @@ def test_sampler_fast_selection_equals_reference_on_ties_and_edges(host, checker
     R.close()
 
 
+def test_sampler_fast_selection_full_vocabulary(host):
+    """the one-pass selection at the real vocabulary size (42384: chunk maxima give a lower bound, chunks below it are skipped) against
+    the reference's partial_sort over all (logit / temp, id) pairs as written -- which test_sampler_* pin to the reference binary at the
+    tiny model's size: same id for random rows, rows with ties inside / at the edge of the top_k, plateaus, infinities and NaNs"""
+    host.bgpt_host_sample_n.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint32, C.c_int]
+    n = 42384
+    rng = np.random.default_rng(11)
+    rows = [(rng.standard_normal(n) * s).astype(np.float32) for s in (1.0, 3.0, 1e-3)]
+    base = rows[1]
+    order = np.argsort(-base)
+    x = base.copy(); x[order[7]] = x[order[6]]; rows.append(x)
+    x = base.copy(); x[order[40]] = x[order[39]]; rows.append(x)
+    x = base.copy(); x[order[41]] = x[order[40]]; rows.append(x)
+    rows.append(np.where(np.arange(n) % 1000 == 0, np.float32(9.0), base.clip(max=8.0)).astype(np.float32))      # a plateau of 43 maxima
+    x = base.copy(); x[order[0]] = np.inf; x[order[50]] = -np.inf; rows.append(x)
+    x = base.copy(); x[12345] = np.nan; rows.append(x)
+    rows.append(np.sort(base)); rows.append(np.sort(base)[::-1].copy())
+    rows.append(np.zeros(n, np.float32))
+    for r, logits in enumerate(rows):
+        for top_k, top_p, temp in ((1, 1.0, 1.0), (40, 0.9, 0.8), (40, 1.0, 1.0), (100, 0.95, 1.2), (127, 0.5, 0.7), (300, 0.9, 1.0), (600, 0.9, 1.0)):
+            for seed in (0, 1):
+                want = host.bgpt_host_sample_n(logits.ctypes.data, n, top_k, top_p, temp, seed, 1)
+                got = host.bgpt_host_sample_n(logits.ctypes.data, n, top_k, top_p, temp, seed, 0)
+                assert got == want, (r, top_k, top_p, temp, seed)
+
+
 @pytest.mark.parametrize("ftype", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_reference_quantize_frontend_on_our_library(zoo, model_dir, ftype):
     """the reference's UNMODIFIED examples/quantize/quantize.cpp, linked against libbiogpt_b200.so,
