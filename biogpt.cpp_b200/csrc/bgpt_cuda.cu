@@ -1686,8 +1686,8 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
             m->launches++;
         }
         CK(cudaGetLastError());
-        if (!m->h_topk_dev) CK(cudaMemcpyAsync(packet(seq, true), packet(seq, false), 16 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
     }
+    if (!m->h_topk_dev) CK(cudaMemcpyAsync(packet(seq, true), packet(seq, false), 16 + (size_t) k * 8, cudaMemcpyDeviceToHost, s));
     if (timed) { CK(cudaEventRecord(m->ev1, s)); m->last_ms_pending = true; }
     else { m->last_ms_pending = false; m->last_ms = 0.f; }
     // chained launch: the kernel of the next position goes into the stream now, behind the one this call waits for; it starts the
