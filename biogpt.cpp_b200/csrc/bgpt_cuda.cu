@@ -143,7 +143,8 @@ struct bgpt_model {
     unsigned * d_tk_ticket = nullptr;                             // generation 5: ticket counter of the sampler tail
     // chained launches of bgpt_cuda_eval_topk (generation 5): the kernel of position p + 1 is queued while the call for p is still
     // waiting for its packet; its token arrives through `h_feed` (mapped pinned memory) when the next call names it
-    struct Chain { bool active = false; int n_past = 0, k = 0; unsigned seq = 0, feed_seq = 0; } chain;
+    struct Chain { bool active = false; int n_past = 0, k = 0; unsigned seq = 0, feed_seq = 0; bool full = false; } chain;
+    float * h_full = nullptr; float * h_full_dev = nullptr;      // bgpt_cuda_eval on the sampler's kernel: the logit row lands here (mapped pinned)
     unsigned long long * h_feed = nullptr; unsigned long long * h_feed_dev = nullptr; unsigned feed_seq = 0;
     int chain_mode = -1;                                          // -1: BGPT_CHAIN (default on), 0 off, 1 on
     int * d_err5 = nullptr; int * h_err5 = nullptr; long long * d_trace5 = nullptr; size_t trace5_n = 0;
@@ -279,6 +280,7 @@ extern "C" void bgpt_cuda_model_free(bgpt_model * m) {
     if (m->h_idlog) cudaFreeHost(m->h_idlog);
     cudaFree(m->d_topk); cudaFree(m->d_topk_cand); cudaFree(m->d_topk_filt); if (m->h_topk) cudaFreeHost(m->h_topk);
     if (m->h_feed) cudaFreeHost(m->h_feed);
+    if (m->h_full) cudaFreeHost(m->h_full);
     if (m->h_topk_rows) cudaFreeHost(m->h_topk_rows);
     cudaFree(m->d_topk_rows_scratch);
     if (m->ev0) cudaEventDestroy(m->ev0);
@@ -1387,15 +1389,15 @@ static int check_mega5_error(bgpt_model * m) {
 // one token at n_past on the persistent kernel.  token source: d_tok (device) or the previous
 // launch's argmax candidates (use_cand).  Asynchronous on the model's stream.
 // generation 5: the sampler tail (bgpt_mega5.cuh); use_cand == 3: + the serial under which the token will arrive in the token word
-struct MegaTopk { int k; unsigned seq; uint8_t * pk; int stride; unsigned feed_seq; };
+struct MegaTopk { int k; unsigned seq; uint8_t * pk; int stride; unsigned feed_seq; float * full; };
 static int launch_mega(bgpt_model * m, const int * d_tok, int use_cand, int n_past, int log_slot, int tok_imm = 0, const MegaTopk * tk = nullptr) {
     const int gen = mega_generation(m);
     if (tk && gen != 5) return fail(BGPT_E_STATE, "launch_mega: the sampler tail needs the generation-5 kernel");
     if (gen == 5) {
         M5Params P = m->m5;
-        P.tk_k = 0; P.feed = nullptr; P.feed_seq = 0; P.feed_limit = 0;
+        P.tk_k = 0; P.tk_full = nullptr; P.feed = nullptr; P.feed_seq = 0; P.feed_limit = 0;
         if (tk) {
-            P.tk_k = tk->k; P.tk_seq = tk->seq; P.tk_pk = tk->pk; P.tk_stride = tk->stride; P.tk_ticket = m->d_tk_ticket;
+            P.tk_k = tk->k; P.tk_seq = tk->seq; P.tk_pk = tk->pk; P.tk_stride = tk->stride; P.tk_ticket = m->d_tk_ticket; P.tk_full = tk->full;
             if (use_cand == 3) {
                 if (!m->h_feed_dev) return fail(BGPT_E_STATE, "launch_mega: a chained launch needs the token word");
                 static const long long feed_limit = getenv("BGPT_CHAIN_WAIT_US") ? std::max(1LL, atoll(getenv("BGPT_CHAIN_WAIT_US"))) * 2000LL : 4000000LL;   // ~2 ms
@@ -1505,7 +1507,20 @@ extern "C" int bgpt_cuda_set_taps(bgpt_model * m, float * const taps5[5]) {
     return BGPT_OK;
 }
 
+#define BGPT_FALLBACK 1          // eval_topk_impl: the whole-row form is not available for this call (the caller takes the copy path)
+static int eval_topk_impl(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
+                          float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback, float * full_row);
+
 extern "C" int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int n_past, float * logits_out) {
+    // A single-token step on the generation-5 kernel (the loop of examples/main/main.cpp:93-151) takes the sampler's instantiation: every
+    // CTA writes its logit rows straight into mapped host memory in the kernel's tail and the next position's launch is chained -- no D2H
+    // copy command, no stream synchronisation, no launch on the token-to-token path (BGPT_EVAL_TAIL=0: the copy path below).
+    static const bool eval_tail = !(getenv("BGPT_EVAL_TAIL") && atoi(getenv("BGPT_EVAL_TAIL")) == 0);
+    if (eval_tail && m && m->finalized && n == 1 && tokens && logits_out && use_mega(m) && mega_generation(m) == 5 && m->mega5_ok) {
+        float v = 0.f; int32_t id = 0; int no = 0, ex = 0;
+        const int rc = eval_topk_impl(m, tokens, 1, n_past, 1, &v, &id, &no, &ex, nullptr, logits_out);
+        if (rc != BGPT_FALLBACK) return rc;
+    }
     RET(check_eval_args(m, n, n_past, n));
     if (!tokens || !logits_out) return fail(BGPT_E_ARG, "eval: NULL buffer");
     CK(cudaSetDevice(m->device));
@@ -1599,11 +1614,16 @@ static int wait_packet(bgpt_model * m, const volatile int * hinfo, unsigned seq)
     return BGPT_OK;
 }
 
-extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
-                                   float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback) {
+// full_row != NULL: bgpt_cuda_eval's form -- one token on the sampler's kernel, the whole logit row written to mapped host memory by the
+// kernel's tail (every CTA its own rows) and copied to full_row; chained like the sampler's calls.  Returns BGPT_FALLBACK when that form
+// does not apply.
+static int eval_topk_impl(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
+                          float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback, float * full_row) {
     if (!m) return fail(BGPT_E_ARG, "eval: NULL model");
-    // a kernel queued by the previous call (chained launch) serves this call if it was queued for exactly this position and k
-    const bool chained = m->chain.active && n == 1 && tokens && vals && ids && n_out && exact && n_past == m->chain.n_past && k == m->chain.k;
+    const bool want_full = full_row != nullptr;
+    // a kernel queued by the previous call (chained launch) serves this call if it was queued for exactly this position, k and form
+    const bool chained = m->chain.active && n == 1 && tokens && vals && ids && n_out && exact && n_past == m->chain.n_past && k == m->chain.k &&
+                         m->chain.full == want_full;
     bgpt_model::Chain served = m->chain;
     if (chained) m->chain.active = false;                // check_eval_args would withdraw it
     RET(check_eval_args(m, n, n_past, n));
@@ -1624,6 +1644,9 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         memset(m->h_feed, 0, 64);
         dp = nullptr;
         if (zc && cudaHostGetDevicePointer(&dp, m->h_feed, 0) == cudaSuccess && dp) m->h_feed_dev = (unsigned long long *) dp; else cudaGetLastError();
+        CK(cudaHostAlloc(&m->h_full, (size_t) m->n_vocab * 4, cudaHostAllocMapped));
+        dp = nullptr;
+        if (zc && cudaHostGetDevicePointer(&dp, m->h_full, 0) == cudaSuccess && dp) m->h_full_dev = (float *) dp; else cudaGetLastError();
         CK(cudaMalloc(&m->d_topk_cand, topk3_scratch_bytes(m->n_vocab)));
         CK(cudaMalloc(&m->d_topk_filt, topk2_scratch_bytes())); CK(cudaMemset(m->d_topk_filt, 0, topk2_scratch_bytes()));
         cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);   // + 34 KB of static histograms
@@ -1638,6 +1661,11 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     static const bool use_tail = !(getenv("BGPT_TOPK_TAIL") && atoi(getenv("BGPT_TOPK_TAIL")) == 0);
     const bool tail = mega && use_tail && mega_generation(m) == 5 && m->mega5_ok && k <= M5_NC && m->n_vocab >= M5_NC;
     const bool chain = tail && m->h_topk_dev && m->h_feed_dev && chain_enabled(m);
+    if (want_full && !(tail && m->h_topk_dev && m->h_full_dev)) {
+        if (chained) chain_feed(m, -2, served.feed_seq);
+        return BGPT_FALLBACK;
+    }
+    float * const full_dev = want_full ? m->h_full_dev : nullptr;
     auto packet = [&](unsigned serial, bool host_view) { return (host_view || !m->h_topk_dev ? (host_view ? m->h_topk : m->d_topk) : m->h_topk_dev) + (serial & 1u) * tk_bytes; };
     auto next_seq = [&]() { const unsigned q = ++m->topk_seq ? m->topk_seq : ++m->topk_seq; return q; };
     auto next_feed = [&]() { const unsigned q = ++m->feed_seq ? m->feed_seq : ++m->feed_seq; return q; };
@@ -1653,7 +1681,7 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
         memcpy(m->h_tokens, tokens, (size_t) n * sizeof(int));
         m->h_st->n_past = n_past; m->h_st->step = 0; m->h_st->pad0 = m->h_st->pad1 = 0;
         if (!chain) { CK(cudaEventRecord(m->ev0, s)); timed = true; }
-        if (tail) { const MegaTopk tk{ k, seq, packet(0u, false), (int) tk_bytes, 0u }; RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0], &tk)); }
+        if (tail) { const MegaTopk tk{ k, seq, packet(0u, false), (int) tk_bytes, 0u, full_dev }; RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0], &tk)); }
         else if (mega) { RET(launch_mega(m, m->d_tokens, 2, n_past, -1, tokens[0])); }
         else {
             CK(cudaMemcpyAsync(m->d_tokens, m->h_tokens, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1693,8 +1721,8 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     // chained launch: the kernel of the next position goes into the stream now, behind the one this call waits for; it starts the
     // moment its predecessor ends, fetches its first weights and polls the token word until the next call (or a withdrawal) writes it
     if (chain && n_past + 1 < m->n_positions) {
-        bgpt_model::Chain c; c.active = true; c.n_past = n_past + 1; c.k = k; c.seq = next_seq(); c.feed_seq = next_feed();
-        const MegaTopk tk{ k, c.seq, packet(0u, false), (int) tk_bytes, c.feed_seq };
+        bgpt_model::Chain c; c.active = true; c.n_past = n_past + 1; c.k = k; c.seq = next_seq(); c.feed_seq = next_feed(); c.full = want_full;
+        const MegaTopk tk{ k, c.seq, packet(0u, false), (int) tk_bytes, c.feed_seq, full_dev };
         RET(launch_mega(m, m->d_tokens, 3, n_past + 1, -1, 0, &tk));
         m->chain = c;
     }
@@ -1706,7 +1734,7 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
             // the queued kernel gave up before the token came (the caller took longer than BGPT_CHAIN_WAIT_US): a fresh launch serves the
             // position; the kernel queued behind it just now is withdrawn first (it was promised position n_past + 1)
             chain_cancel(m);
-            return bgpt_cuda_eval_topk(m, tokens, n, n_past, k, vals, ids, n_out, exact, logits_fallback);
+            return eval_topk_impl(m, tokens, n, n_past, k, vals, ids, n_out, exact, logits_fallback, full_row);
         }
     } else CK(cudaStreamSynchronize(s));
     if (!m->chain.active) RET(check_rows_error(m));
@@ -1729,11 +1757,17 @@ extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n
     *n_out = got_n; *exact = hinfo[1];
     memcpy(vals, hp + 16, (size_t) got_n * 4);
     memcpy(ids, hp + 16 + (size_t) k * 4, (size_t) got_n * 4);
+    if (want_full) { memcpy(full_row, m->h_full, (size_t) m->n_vocab * 4); return BGPT_OK; }
     if (!hinfo[1] && logits_fallback) {
         chain_cancel(m);                                 // the full row is read behind the stream: nothing may wait in front of the copy
         CK(cudaMemcpy(logits_fallback, m->logits, (size_t) m->n_vocab * 4, cudaMemcpyDeviceToHost));
     }
     return BGPT_OK;
+}
+
+extern "C" int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
+                                   float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback) {
+    return eval_topk_impl(m, tokens, n, n_past, k, vals, ids, n_out, exact, logits_fallback, nullptr);
 }
 
 extern "C" int bgpt_cuda_eval_device(bgpt_model * m, const int32_t * d_tokens, int n, int n_past) {

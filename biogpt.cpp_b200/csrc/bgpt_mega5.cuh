@@ -89,6 +89,7 @@ struct M5Params {
     int tk_k; unsigned tk_seq;     // packet of serial s: tk_pk + (s & 1) * tk_stride = { info[4], tk_k vals, tk_k ids }
     uint8_t * tk_pk; int tk_stride;
     unsigned * tk_ticket;          // device counter, 0 between launches
+    float * tk_full;               // bgpt_cuda_eval: mapped pinned HOST buffer that receives the whole logit row (every CTA its own rows), or NULL
     // chained launch (use_cand == 3): the kernel is queued BEFORE its input token exists; CTA 0 polls the 8-byte word {token, serial} in
     // mapped pinned host memory until the serial is feed_seq and hands the token to the other CTAs through L2.  No token within
     // feed_limit cycles, or the value M5_TOK_CANCEL: the kernel exits without touching the KV cache or the logits (a time-out leaves a
@@ -485,10 +486,19 @@ static __device__ __noinline__ void m5_withdrawn(uint64_t * mbar, int n_fired, b
 }
 // the sampler tail: whoever takes the last ticket sees every CTA's logits and maximum (fence + atomic on both sides) and selects
 // (bgpt_topk.cuh); called by every thread of every CTA
+// full != NULL (bgpt_cuda_eval): every CTA first copies ITS lm_head rows to the mapped host buffer -- 128 CTAs x 1.3 KB of posted writes
+// in parallel, no D2H copy command behind the kernel -- and releases at system scope, so the serial the last CTA writes orders them all
 static __device__ __noinline__ void m5_sampler_tail(unsigned * ticket, const float * logits, int n_vocab, int k, const float * cand_val, uint8_t * scratch,
-                                                    uint8_t * pk, const int * err, unsigned seq) {
+                                                    uint8_t * pk, const int * err, unsigned seq, float * full) {
     __shared__ int s_last;
+    if (full) {
+        const unsigned uc = blockIdx.x;
+        const int v0 = (int) ((uc * (unsigned) n_vocab) / (unsigned) M5_NC), v1 = (int) (((uc + 1u) * (unsigned) n_vocab) / (unsigned) M5_NC);
+        for (int i = v0 + (int) threadIdx.x; i < v1; i += M5_NT) full[i] = __ldcg(logits + i);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
+        if (full) asm volatile("fence.acq_rel.sys;" ::: "memory");
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         s_last = atomicAdd(ticket, 1u) == (unsigned) (M5_NC - 1);
         if (s_last) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); *ticket = 0u; }
@@ -1141,7 +1151,7 @@ __global__ void __launch_bounds__(M5_NT, 1) k_mega5(const __grid_constant__ M5Pa
     }
     // ---- sampler tail
     if constexpr (TK) if (P.tk_k > 0)
-        m5_sampler_tail(P.tk_ticket, p.logits, p.n_vocab, P.tk_k, p.cand_val, s_w, P.tk_pk + (size_t) (P.tk_seq & 1u) * P.tk_stride, err, P.tk_seq);
+        m5_sampler_tail(P.tk_ticket, p.logits, p.n_vocab, P.tk_k, p.cand_val, s_w, P.tk_pk + (size_t) (P.tk_seq & 1u) * P.tk_stride, err, P.tk_seq, P.tk_full);
     { const int l = p.n_layer; M5PROF(0, 2); }
     if (PROF && P.trace && tid == 0) m4_calibrate(P.trace + (size_t) M5_NC * P.prof_n + 4 * cta + 2);
 }
