@@ -88,7 +88,10 @@ void bgpt_cuda_model_free(bgpt_model * m);
  * `logits_out` (HOST) receives the n_vocab logits of the last token.  Attention is
  * un-masked over all n_past+n positions exactly like the reference graph
  * (biogpt.cpp:741-744). Host->device copy of the ids and device->host copy of the logits
- * are part of the call. */
+ * are part of the call.  Single-token steps on the generation-5 decode kernel (n == 1, the loop of
+ * examples/main/main.cpp:93-151) are served like bgpt_cuda_eval_topk's: the kernel writes the logit row into
+ * mapped pinned host memory itself and the launch for position n_past + 1 is chained (bgpt_cuda_set_chain);
+ * bgpt_cuda_last_eval_ms is 0 for those calls. */
 int bgpt_cuda_eval(bgpt_model * m, const int32_t * tokens, int n, int n_past, float * logits_out);
 
 /* Same step with everything resident in HBM: token ids are read from `d_tokens` (device
@@ -106,7 +109,8 @@ int bgpt_cuda_synchronize(bgpt_model * m);
  * drawn id is the reference's in every case.  K <= 128. */
 int bgpt_cuda_eval_topk(bgpt_model * m, const int32_t * tokens, int n, int n_past, int k,
                         float * vals, int32_t * ids, int * n_out, int * exact, float * logits_fallback);
-/* Chained launches of bgpt_cuda_eval_topk (generation-5 decode kernel; default on, BGPT_CHAIN=0 turns it off): a sampling loop
+/* Chained launches of bgpt_cuda_eval_topk and of single-token bgpt_cuda_eval (generation-5 decode kernel; default on, BGPT_CHAIN=0 turns
+ * it off): a sampling loop
  * (examples/main/main.cpp:93-151) asks for position p + 1 right after position p, so the call for p also queues the kernel of p + 1
  * behind the one it waits for.  That kernel starts the moment its predecessor ends, fetches its first weights and polls an 8-byte
  * word in mapped pinned host memory; the next call only writes the sampled token id there -- no launch and no front-end latency on
