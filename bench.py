@@ -472,6 +472,7 @@ def run_streams_cpp_driver(args):
     tv = np.zeros(n_streams * TOPK, np.float32); ti = np.zeros(n_streams * TOPK, np.int32)
     tn = np.zeros(n_streams, np.int32); tex = np.zeros(n_streams, np.int32)
     cur = first.copy()
+    L.bgpt_replicas_eval_topk(r, cur, 0, TOPK, tv, ti, tn, tex, logits.reshape(-1))      # untimed: the call's one-time buffers (mapped packets, scratch)
     t0 = time.perf_counter()
     for p in range(n_e2e):
         if L.bgpt_replicas_eval_topk(r, cur, p, TOPK, tv, ti, tn, tex, logits.reshape(-1)) != 0:
